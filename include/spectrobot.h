@@ -1,0 +1,208 @@
+/*
+ * spectrobot.h -- C ABI of libspectrobot.so: the B200 (sm_100a) implementation of the
+ * SpectRobot line-by-line hot path (Voigt/G-coefficient cross-sections, (P,T) LUT build,
+ * line-of-sight radiative transfer).
+ *
+ * The reference reaches this path through three f2py extension modules (`lineshape`,
+ * `fparts_mod`, `curgods`) plus Python loops around them; file:line citations below are
+ * relative to the reference tree.  INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every function returns an int status (0 = SR_OK) instead of the
+ *     Fortran `stop` that kills the reference's worker process (lineshape.f:255,263);
+ *     sr_last_error() gives the message for the calling thread.
+ *   - "_host" / Tier-1 entry points take HOST pointers and are synchronous (they copy in,
+ *     run the CUDA kernels, copy out).  Tier-2 entry points take DEVICE pointers plus a
+ *     cudaStream_t (passed as void*), are asynchronous and never allocate output.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     SR_ERR_CUDA.  Pure table look-ups (sr_bd_tips_2003, sr_partition_sum) are host-only.
+ */
+#ifndef SPECTROBOT_H
+#define SPECTROBOT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SR_OK            0
+#define SR_ERR_ARG       1   /* bad argument (incl. humliv_bb i1 > i2, lineshape.f:253) */
+#define SR_ERR_DW        2   /* humliv_bb called with dw <= 0 (lineshape.f:260-264) */
+#define SR_ERR_CUDA      3   /* CUDA runtime error / no device */
+#define SR_ERR_GEOMETRY  4   /* a line's Voigt window has an unsupported region geometry */
+#define SR_ERR_TABLE     5   /* no TIPS table for (mol, iso) (fparts_mod.f:294 falls through) */
+#define SR_ERR_LUT       6   /* LUT interpolation: cell not found / extrapolating in P
+                                (spect_main_module.py:989-991, 1058) */
+#define SR_ERR_LIMIT     7   /* size limit exceeded (shared memory for n_sets, imxlines ...) */
+
+#define SR_IMXSIG      13010     /* parameters.inc:65  - Voigt window length */
+#define SR_IMXLINES    40000     /* parameters.inc:64 */
+#define SR_IMXSIG_LONG 2000000   /* parameters.inc:64 */
+#define SR_IMXSTP      8000      /* parameters.inc:64 */
+#define SR_TIPS_N      119       /* fparts_mod.f:58 */
+
+int         sr_version(void);
+const char* sr_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long   sr_kernel_launch_count(void);
+int         sr_device_count(void);
+int         sr_set_device(int device);
+
+/* ===========================================================================================
+ * Tier 1 -- drop-ins for the f2py modules (HOST pointers, synchronous, run on the GPU)
+ * =========================================================================================*/
+
+/* lineshape.humliv_bb(x,i1,i2,x0,lw,dw) -> y        [lineshape.f:226-569; spect_classes.py:1999]
+ * x, y: n doubles (the reference fixes n = 13010); i1,i2 1-based inclusive.  y is written on
+ * [i1,i2] only, exactly where the Fortran writes.  dw is Doppler HWHM / sqrt(ln 2). */
+int sr_humliv_bb(const double* x, int n, int i1, int i2, double x0, double lw, double dw,
+                 double* y);
+
+/* lineshape.sum_all_lines(spe_ini, matrix, init, fin, n_lines, n_spe) -> spe_fin
+ * [lineshape.f:2-25; spect_classes.py:1092].  matrix is Fortran-ordered with leading dimension
+ * ld_lines (imxlines in the reference) and n_win columns (imxsig); init/fin 1-based inclusive;
+ * spe_ini/spe_fin have n_spe elements (the reference pads to imxsig_long). */
+int sr_sum_all_lines(const double* spe_ini, const double* matrix_colmajor, const int* init,
+                     const int* fin, int n_lines, int ld_lines, int n_win, int n_spe,
+                     double* spe_fin);
+
+/* fparts_mod.bd_tips_2003(mol, iso) -> gi, t_grid[119], QT_grid[119]
+ * [fparts_mod.f:33-295; spect_classes.py:1687].  Host table look-up. */
+int sr_bd_tips_2003(int mol, int iso, double* gi, double* t119, double* q119);
+/* CalcPartitionSum(mol, iso, temp) [spect_classes.py:1692-1710]: 4-point (3 below 85 K)
+ * Lagrange interpolation of the table above.  Host. */
+int sr_partition_sum(int mol, int iso, double temp, double* q);
+
+/* curgods.curgod_fort_k(...) -> res   [curgods.f:2-98].  n_batch independent integrals, each
+ * over n_p points; arrays are [n_batch][n_p] row-major; res[n_batch].  vmr / f may be NULL for
+ * the variants that do not take them (k=1: nd,x; k=2: nd,vmr,x; k=3,4: nd,vmr,f,x). */
+int sr_curgod(int k, const double* nd, const double* vmr, const double* f, const double* x,
+              int n_p, int n_batch, double* res);
+
+/* ===========================================================================================
+ * Tier 2 -- fused cross-section path (K1/K2): calc_shapes_lines + Calc_Gcoeffs + BuildCoeff +
+ * add_lines_to_spectrum + sum_all_lines for whole (P,T) cells
+ * [spect_classes.py:1378-1462, 312-343, 1277-1337, 1016-1147; spect_main_module.py:718-788,
+ *  1122-1168]
+ * =========================================================================================*/
+
+/* Physical constants as the host reads them from scipy (spect_classes.py:44-47, 1984) and the
+ * libm constants the Python side forms with math.log/sqrt (spect_classes.py:1984,1997,1999). */
+typedef struct {
+    double h_cgs, c_cgs, k_cgs, avogadro;
+    double ln2;          /* math.log(2.0) */
+    double sqrt_ln2;     /* math.sqrt(math.log(2.0)) */
+    double sqrt_pi_ln2;  /* math.sqrt(np.pi/math.log(2.0)) */
+} sr_consts;
+void sr_default_consts(sr_consts* c); /* CODATA-2018 exact SI values */
+
+/* Line table, HOST arrays of n_lines entries (HITRAN fields of SpectLine, spect_classes.py:50-53,
+ * with the level link of LinkToMolec :122-150 resolved to integers by the caller):
+ * up_set / lo_set = index of the LUT set (vibrational level) the line feeds as upper level
+ * (sp_emission, ind_emission) and as lower level (absorption); a negative value on either
+ * drops the line (spect_classes.py:1384-1388).  LTE isotopologue: n_sets = 1, both 0, e_vib 0. */
+typedef struct {
+    int n_lines;
+    const double *freq, *a_coeff, *air_broad, *t_dep, *e_lower, *g_up, *g_lo;
+    const double *e_vib_up, *e_vib_lo;
+    const int *up_set, *lo_set;
+} sr_lines;
+
+typedef struct sr_lineset sr_lineset; /* device-resident line table bound to one spectral grid */
+
+/* grid: the spectral grid EXACTLY as prepare_spe_grid builds it (np.arange), n_grid
+ * points; lin_grid: the SR_IMXSIG window offsets of PrepareCalcShapes (spect_classes.py:1446);
+ * mm: molar mass of the isotopologue (isomolec.MM).  Uploads everything, computes closest_grid
+ * (spect_classes.py:1937) per line on the device and groups lines by (upper, lower) set. */
+int sr_lineset_create(const sr_lines* lines, const double* grid, long n_grid,
+                      const double* lin_grid, int n_sets, double mm, const sr_consts* consts,
+                      sr_lineset** out);
+int sr_lineset_destroy(sr_lineset* ls);
+long sr_lineset_n_active(const sr_lineset* ls);   /* lines kept after the level-link filter */
+int sr_lineset_centres(const sr_lineset* ls, int* ind_host); /* closest_grid index per INPUT line
+                                                                (-1 for dropped lines) */
+
+/* G-coefficient spectra of n_cells (P,T) cells.  pt_host: [n_cells][2] = (P_hPa, T_K) on the
+ * host.  out: [n_cells][n_sets][3][n_grid] doubles, ctype order sp_emission, ind_emission,
+ * absorption; every element is written (no zero-fill needed).
+ * _dev: out is a DEVICE pointer, asynchronous on `stream`.  _host: out is a HOST pointer. */
+int sr_gcoeff_cells_dev(sr_lineset* ls, const double* pt_host, int n_cells, double* out_dev,
+                        void* stream);
+int sr_gcoeff_cells_host(sr_lineset* ls, const double* pt_host, int n_cells, double* out_host);
+/* Synchronise `stream` and report the humliv_bb STOP conditions / geometry errors that the
+ * asynchronous _dev calls on this lineset raised since the last check (SR_OK if none). */
+int sr_lineset_check(sr_lineset* ls, void* stream);
+/* Same, stored as float32 (the reference's split_and_compress_LUTS casts the LUT to float32,
+ * spect_main_module.py:1676 via spect_classes.py:732). out32_dev: [n_cells][n_sets][3][n_grid]. */
+int sr_gcoeff_cells_dev_f32(sr_lineset* ls, const double* pt_host, int n_cells, float* out32_dev,
+                            double* scratch_dev, void* stream);
+
+/* Per-line normalised shapes of one cell (MakeShapeLine with keep_memory, spect_classes.py:174):
+ * shapes_dev [n_active][SR_IMXSIG] in the lineset's internal (sorted) line order, and the three
+ * G coefficients g_dev [n_active][3]; order_host[n_active] maps sorted position -> input line. */
+int sr_line_shapes_dev(sr_lineset* ls, double pres_hpa, double temp, double* shapes_dev,
+                       double* g_dev, void* stream);
+int sr_lineset_order(const sr_lineset* ls, int* order_host);
+
+/* ===========================================================================================
+ * Tier 2 -- line-of-sight radiative transfer (K3 / K3a)
+ * [callers spect_main_module.py:2506-2545, 3133-3221; coefficient assembly :2134-2299;
+ *  LUT interpolation :997-1066.  The integral itself lives in the reference's missing
+ *  spect_base_module; DESIGN.md section 6 is the specification implemented here.]
+ * =========================================================================================*/
+
+/* K3: recursion over materialised layers.  tau, src: [n_los][n_steps_max][n_pts] doubles
+ * (device), n_steps[n_los] (device ints), steps ordered from the far end to the observer.
+ *   I <- I*exp(-tau) + src*(1-exp(-tau)),  I_0 = i0[los][pt] or 0 when i0 == NULL
+ * solo_absorption != 0 drops the emission term.  rad: [n_los][n_pts]. */
+int sr_los_rt_layers_dev(const double* tau, const double* src, const int* n_steps, int n_los,
+                         int n_steps_max, long n_pts, const double* i0, int solo_absorption,
+                         double* rad, void* stream);
+
+/* A float32 LUT of one isotopologue resident on the device (the compressed LUT of
+ * split_and_compress_LUTS).  g32_dev: [n_cells][n_sets][3][n_grid] floats (device, caller-owned,
+ * must outlive the handle); pt_host [n_cells][2]; level_energy_host[n_sets] (cm-1; ignored when
+ * lte_unidentified); mol/iso select the TIPS table for Q(T); iso_ratio multiplies the columns. */
+typedef struct sr_lut sr_lut;
+int sr_lut_create(const float* g32_dev, const double* pt_host, int n_cells, int n_sets,
+                  long n_grid, const double* level_energy_host, int mol, int iso,
+                  double iso_ratio, int lte_unidentified, const sr_consts* consts, sr_lut** out);
+int sr_lut_destroy(sr_lut* lut);
+
+/* Step tables of a LOS batch (HOST arrays, steps ordered far end -> observer):
+ *   n_steps[n_los]; temp, pres [n_los][n_steps_max] (Curtis-Godson T in K, P in hPa);
+ *   column [n_gas][n_los][n_steps_max] (molecules cm-2 of the gas, before the isotopic ratio);
+ *   tvib   [n_gas][n_sets_max][n_los][n_steps_max] vibrational temperatures (K); NULL = LTE
+ *          (T_vib = T, spect_main_module.py:2231-2234). */
+typedef struct {
+    int n_los, n_steps_max, n_gas, n_sets_max;
+    const int* n_steps;
+    const double *temp, *pres, *column, *tvib;
+} sr_los_steps;
+
+/* Fused K3a+K3: radiances of the batch on grid points [pt0, pt0+n_pts) from the LUTs of n_gas
+ * isotopologues.  rad_dev: [n_los][n_pts] doubles (device).  i0_dev as above (may be NULL). */
+int sr_los_rt_lut_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
+                      const double* i0_dev, int solo_absorption, double* rad_dev, void* stream);
+int sr_los_rt_lut_host(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
+                       const double* i0_host, int solo_absorption, double* rad_host);
+/* Synchronise `stream` and report LUT-interpolation errors (SR_ERR_LUT) raised by the
+ * asynchronous LOS calls that used luts[0] since the last check. */
+int sr_los_check(sr_lut* const* luts, void* stream);
+/* K3a alone: materialise tau/src [n_los][n_steps_max][n_pts] (device) for sr_los_rt_layers_dev. */
+int sr_los_tau_src_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
+                       double* tau_dev, double* src_dev, void* stream);
+
+/* LutSet.calculate(P,T) [spect_main_module.py:997-1066]: the (up to) 4 cells and weights the
+ * reference's nearest-node bilinear rule picks.  Host helper (index logic only). */
+int sr_lut_weights(const double* pt_host, int n_cells, double pres, double temp, int cell[4],
+                   double w[4]);
+
+/* FP64 FMA micro-benchmark used by bench.py for the K1/K2 roofline denominator: runs
+ * `iters` dependent-chain FMAs per thread on a full grid and returns achieved FLOP/s. */
+int sr_fp64_peak(int iters, double* flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECTROBOT_H */

@@ -1,0 +1,66 @@
+// sr_common.h -- host-side plumbing shared by the translation units of libspectrobot.so
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "../../include/spectrobot.h"
+
+namespace sr {
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define SR_CUDA(call)                                                                     \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return sr::fail(SR_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,       \
+                            cudaGetErrorString(e__));                                     \
+    } while (0)
+
+// every kernel launch in the library goes through this so that sr_kernel_launch_count() is exact
+#define SR_LAUNCH(kernel, grid, block, smem, stream, ...)                                 \
+    do {                                                                                  \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                       \
+        sr::g_launches.fetch_add(1, std::memory_order_relaxed);                           \
+        SR_CUDA(cudaGetLastError());                                                      \
+    } while (0)
+
+template <typename T>
+struct DevBuf {  // RAII device buffer
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc(&p, count * sizeof(T));
+    }
+    cudaError_t ensure(size_t count) { return count <= n ? cudaSuccess : alloc(count); }
+    cudaError_t upload(const T* h, size_t count, cudaStream_t s = 0) {
+        cudaError_t e = ensure(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+};
+
+}  // namespace sr

@@ -1,0 +1,129 @@
+// sr_device.cuh -- device-side Humlicek-w4 pieces of humliv_bb (lineshape.f:226-569)
+//
+// What must be reproduced to stay within 1e-6 of the reference:
+//   * core points: the complex argument is built with Fortran CMPLX() without KIND, i.e. both
+//     parts are rounded to float32 before the complex*16 arithmetic (lineshape.f:529);
+//   * the region-3/4 coefficients are real*4 literals widened to double (lineshape.f:539-558);
+//   * complex division with Smith's range reduction (gfortran -fcx-fortran-rules);
+//   * region 1/2 are real FP64 rationals in x^2 (lineshape.f:456-477, 492-522).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace srdev {
+
+struct cplx { double re, im; };
+
+__device__ __forceinline__ cplx c_mul(cplx a, cplx b) {
+    cplx r;
+    r.re = a.re * b.re - a.im * b.im;
+    r.im = a.re * b.im + a.im * b.re;
+    return r;
+}
+__device__ __forceinline__ cplx c_add_r(double r, cplx a) { a.re += r; return a; }
+__device__ __forceinline__ cplx c_r_sub(double r, cplx a) { a.re = r - a.re; a.im = -a.im; return a; }
+// real part of a/b with Smith's algorithm (only the real part is ever used, lineshape.f:546,560)
+__device__ __forceinline__ double c_div_re(cplx a, cplx b) {
+    if (fabs(b.re) < fabs(b.im)) {
+        double ratio = b.re / b.im;
+        double div = b.re * ratio + b.im;
+        return (a.re * ratio + a.im) / div;
+    } else {
+        double ratio = b.im / b.re;
+        double div = b.im * ratio + b.re;
+        return (a.im * ratio + a.re) / div;
+    }
+}
+
+#define SRF(x) ((double)x##f)  // real*4 literal widened to double
+
+// regions 3 and 4 (lineshape.f:527-561); rx >= 0 and ry in FP64, rounded to float32 inside
+static __device__ __noinline__ double humliv_core(double rx, double ry) {
+    double r2 = 0.195 * rx - 0.176;
+    cplx c2;
+    c2.re = (double)__double2float_rn(ry);
+    c2.im = (double)__double2float_rn(-rx);
+    if (ry < r2) {  // region 4
+        cplx c1 = c_mul(c2, c2);
+        cplx num;
+        num.re = c1.re * SRF(.56419);
+        num.im = c1.im * SRF(.56419);
+        num = c_r_sub(SRF(1.320522), num);
+        num = c_r_sub(SRF(35.76683), c_mul(c1, num));
+        num = c_r_sub(SRF(219.0313), c_mul(c1, num));
+        num = c_r_sub(SRF(1540.787), c_mul(c1, num));
+        num = c_r_sub(SRF(3321.9905), c_mul(c1, num));
+        num = c_r_sub(SRF(36183.31), c_mul(c1, num));
+        num = c_mul(c2, num);
+        cplx den = c_r_sub(SRF(1.841439), c1);
+        den = c_r_sub(SRF(61.57037), c_mul(c1, den));
+        den = c_r_sub(SRF(364.2191), c_mul(c1, den));
+        den = c_r_sub(SRF(2186.181), c_mul(c1, den));
+        den = c_r_sub(SRF(9022.228), c_mul(c1, den));
+        den = c_r_sub(SRF(24322.84), c_mul(c1, den));
+        den = c_r_sub(SRF(32066.6), c_mul(c1, den));
+        return exp(c1.re) * cos(c1.im) - c_div_re(num, den);
+    } else {  // region 3
+        cplx num;
+        num.re = c2.re * SRF(.5642236);
+        num.im = c2.im * SRF(.5642236);
+        num = c_add_r(SRF(3.778987), num);
+        num = c_add_r(SRF(11.96482), c_mul(c2, num));
+        num = c_add_r(SRF(20.20933), c_mul(c2, num));
+        num = c_add_r(SRF(16.4955), c_mul(c2, num));
+        cplx den = c_add_r(SRF(6.699398), c2);
+        den = c_add_r(SRF(21.69274), c_mul(c2, den));
+        den = c_add_r(SRF(39.27121), c_mul(c2, den));
+        den = c_add_r(SRF(38.82363), c_mul(c2, den));
+        den = c_add_r(SRF(16.4955), c_mul(c2, den));
+        return c_div_re(num, den);
+    }
+}
+#undef SRF
+
+// region 2 (lineshape.f:492-522), x2 = x*x
+static __device__ __noinline__ double humliv_reg2(double x2, double ry) {
+    double ry2 = ry * ry;
+    double a = ry * (1.0578555 + ry2 * (4.6545642 + ry2 * (3.1030428 + 0.5641896 * ry2)));
+    double b = ry * (2.9619954 + ry2 * (0.5641896 + 1.6925688 * ry2));
+    double c = ry * (-2.5388532 + ry2 * 1.6925688);
+    double d = ry * 0.5641896;
+    double e = 0.5625 + ry2 * (4.5 + ry2 * (10.5 + ry2 * (6. + ry2)));
+    double f = -4.5 + ry2 * (9. + ry2 * (6. + 4. * ry2));
+    double g = 10.5 + ry2 * (-6. + 6. * ry2);
+    double h = 4. * ry2 - 6.;
+    return (a + x2 * (b + x2 * (c + d * x2))) / (e + x2 * (f + x2 * (g + x2 * (h + x2))));
+}
+
+// region 1 exactly as written in the Fortran (lineshape.f:456-477); used by the Tier-1 drop-in
+__device__ __forceinline__ double humliv_reg1(double x2, double ry) {
+    double ry2 = ry * ry;
+    double a = ry * (1.1283792 + 2.2567584 * ry2);
+    double b = 2.2567584 * ry;
+    double c = (1. + 2. * ry2) * (1. + 2. * ry2);
+    double d = -4. + 8. * ry2;
+    return (a + x2 * b) / (c + x2 * (d + 4. * x2));
+}
+
+// Region 1 rewritten for the hot loop.  With q = 0.5 + ry^2 and s = x^2 the Fortran rational is
+//   K = (a + s b)/(c + s(d + 4 s)) = (b/4) * w / (w^2 - 2 s),  w = q + s
+//     = (b/4) * (u + 1) / (u^2 + 2 ry^2),                     u = s + ry^2 - 0.5
+// (a/b = q, c = 4 q^2, d = 8 q - 8).  Returns K/(b/4) given u and c2 = 2 ry^2.
+// The reciprocal is MUFU.RCP64H (rcp.approx.ftz.f64, ~2^-20 relative) plus one Newton step
+// folded into the product: w*r0*(1+e), e = 1 - den*r0  ->  relative error ~1e-12.
+__device__ __forceinline__ double rcp_approx(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+__device__ __forceinline__ double humliv_reg1_fast(double u, double c2) {
+    double den = fma(u, u, c2);
+    double w = u + 1.0;
+    double r0 = rcp_approx(den);
+    double e = fma(-den, r0, 1.0);
+    double t = w * r0;
+    return fma(t, e, t);
+}
+
+__device__ __forceinline__ long long f_nint(double x) { return llround(x); }  // Fortran NINT
+
+}  // namespace srdev

@@ -1,0 +1,607 @@
+// sr_los.cu -- K3 / K3a: line-of-sight radiative transfer, batched over LOS x wavenumber.
+//
+// Reference pieces restated here:
+//   LutSet.calculate              spect_main_module.py:997-1066  (nearest-node bilinear rule)
+//   SpectralGcoeff.interpolate    spect_classes.py:1349-1375
+//   make_abscoeff_LUTS_fast       spect_main_module.py:2134-2299 (level populations, abs/emi)
+//   CalcPartitionSum              spect_classes.py:1692-1710
+//   float32 LUT                   spect_main_module.py:1676 / spect_classes.py:732
+// The layer recursion itself (sbm.LineOfSight.radtran_fast) is NOT in the reference tree; the
+// specification implemented here is DESIGN.md section 6 ("parity unpinned" against the original).
+//
+// Kernels
+//   k_step_weights  one thread per (gas, LOS, step): LUT cell indices + combined weights
+//                   W[set][cell] = w_cell * pop_set * iso_ratio * column
+//   k_los_fused     K3a+K3: thread per grid point, sequential over steps; LUT rows are read as
+//                   coalesced float32 streams (L2-resident), tau/J never touch HBM
+//   k_los_tau_src   K3a alone: materialises tau and S = J/tau
+//   k_los_layers    K3 alone: HBM-streaming recursion over materialised tau/S
+#include <algorithm>
+#include <cmath>
+#include <vector>
+#include "sr_common.h"
+
+namespace {
+
+constexpr int MAX_GAS = 8;
+constexpr int TIPS_N = SR_TIPS_N;
+enum : int { LFLAG_EXTRAP_P = 1, LFLAG_NO_CELL = 2, LFLAG_NONFINITE = 4 };
+
+struct GasDev {
+    const float* g32;       // [n_cells][n_sets][3][n_grid]
+    const double* Ps;       // [nP] unique sorted pressures
+    const double* Ts;       // [nT] unique sorted temperatures
+    const int* cellmap;     // [nP][nT] -> cell index or -1
+    const double* qtab;     // [119] TIPS Q(T) row
+    const double* elev;     // [n_sets] level energies (cm-1)
+    int nP, nT, n_sets, lte_unidentified;
+    double iso_ratio;
+};
+
+struct StepArgs {
+    GasDev gas[MAX_GAS];
+    int n_gas, n_los, n_steps_max, n_sets_max;
+    const int* n_steps;       // [n_los]
+    const double* temp;       // [n_los][n_steps_max]
+    const double* pres;
+    const double* column;     // [n_gas][n_los][n_steps_max]
+    const double* tvib;       // [n_gas][n_sets_max][n_los][n_steps_max] or nullptr
+    int* cells;               // out [n_gas][n_los][n_steps_max][4]
+    double* W;                // out [n_gas][n_los][n_steps_max][n_sets_max][4]
+    int* flags;
+    double c2;                // h c / k  (spect_classes.py:47)
+};
+
+// nearest and second-nearest node, ties -> lower index (np.argmin / stable argsort()[1])
+__device__ void nearest_two(const double* __restrict__ nodes, int n, double v, int& i1, int& i2) {
+    int a = 0;
+    for (int i = 1; i < n; i++)
+        if (fabs(nodes[i] - v) < fabs(nodes[a] - v)) a = i;
+    int b = -1;
+    for (int i = 0; i < n; i++) {
+        if (i == a) continue;
+        if (b < 0 || fabs(nodes[i] - v) < fabs(nodes[b] - v)) b = i;
+    }
+    i1 = a;
+    i2 = b;
+}
+
+// CalcPartitionSum: Lagrange through the <=2 nodes at or below T and the <=2 nodes above
+__device__ double partition_sum(const double* __restrict__ q, double temp) {
+    int nle = 0;
+    while (nle < TIPS_N && 60.0 + 25.0 * nle <= temp) nle++;
+    const int lo = nle - 2 < 0 ? 0 : nle - 2;
+    const int hi = nle + 2 > TIPS_N ? TIPS_N : nle + 2;
+    double acc = 0.0;
+    for (int a = lo; a < hi; a++) {
+        double w = q[a];
+        const double ta = 60.0 + 25.0 * a;
+        for (int b = lo; b < hi; b++)
+            if (b != a) { const double tb = 60.0 + 25.0 * b; w *= (temp - tb) / (ta - tb); }
+        acc += w;
+    }
+    return acc;
+}
+
+__global__ void k_step_weights(StepArgs a) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y, m = blockIdx.z;
+    if (k >= a.n_steps_max) return;
+    const GasDev& G = a.gas[m];
+    const size_t sk = (size_t)l * a.n_steps_max + k;
+    const size_t o = ((size_t)m * a.n_los + l) * a.n_steps_max + k;
+    int* cells = a.cells + o * 4;
+    double* W = a.W + o * a.n_sets_max * 4;
+    cells[0] = cells[1] = cells[2] = cells[3] = -1;
+    for (int i = 0; i < a.n_sets_max * 4; i++) W[i] = 0.0;
+    if (k >= a.n_steps[l]) return;
+    const double temp = a.temp[sk], pres = a.pres[sk];
+    double wc[4] = {0.0, 0.0, 0.0, 0.0};
+    int flags = 0;
+    if (G.nT < 2) flags |= LFLAG_NO_CELL;
+    else if (pres <= G.Ps[0]) {                                   // smm:1007-1025
+        int ta, tb;
+        nearest_two(G.Ts, G.nT, temp, ta, tb);
+        cells[0] = G.cellmap[0 * G.nT + ta];
+        cells[1] = G.cellmap[0 * G.nT + tb];
+        if (cells[0] < 0 || cells[1] < 0) flags |= LFLAG_NO_CELL;
+        wc[0] = (G.Ts[tb] - temp) / (G.Ts[tb] - G.Ts[ta]);        // sbm.weight, DESIGN 6.2
+        wc[1] = (temp - G.Ts[ta]) / (G.Ts[tb] - G.Ts[ta]);
+    } else if (pres <= G.Ps[G.nP - 1]) {                          // smm:1026-1056
+        if (G.nP < 2) flags |= LFLAG_NO_CELL;
+        else {
+            int p1, p2, t1, t2;
+            nearest_two(G.Ps, G.nP, pres, p1, p2);
+            nearest_two(G.Ts, G.nT, temp, t1, t2);
+            cells[0] = G.cellmap[p1 * G.nT + t1];
+            cells[1] = G.cellmap[p1 * G.nT + t2];
+            cells[2] = G.cellmap[p2 * G.nT + t1];
+            cells[3] = G.cellmap[p2 * G.nT + t2];
+            if (cells[0] < 0 || cells[1] < 0 || cells[2] < 0 || cells[3] < 0)
+                flags |= LFLAG_NO_CELL;
+            const double wp1 = (G.Ps[p2] - pres) / (G.Ps[p2] - G.Ps[p1]);
+            const double wp2 = (pres - G.Ps[p1]) / (G.Ps[p2] - G.Ps[p1]);
+            const double wt1 = (G.Ts[t2] - temp) / (G.Ts[t2] - G.Ts[t1]);
+            const double wt2 = (temp - G.Ts[t1]) / (G.Ts[t2] - G.Ts[t1]);
+            wc[0] = wt1 * wp1; wc[1] = wt2 * wp1; wc[2] = wt1 * wp2; wc[3] = wt2 * wp2;
+        }
+    } else {
+        flags |= LFLAG_EXTRAP_P;                                  // smm:1058
+    }
+    if (flags) {
+        atomicOr(a.flags, flags);
+        cells[0] = cells[1] = cells[2] = cells[3] = -1;
+        return;
+    }
+    const double q_part = partition_sum(G.qtab, temp);            // smm:2212
+    const double col = G.iso_ratio * a.column[o];
+    for (int s = 0; s < G.n_sets; s++) {
+        double pop;
+        if (G.lte_unidentified) pop = 1 / q_part;                 // smm:2218
+        else {
+            const double vibt = a.tvib
+                ? a.tvib[(((size_t)m * a.n_sets_max + s) * a.n_los + l) * a.n_steps_max + k]
+                : temp;                                           // smm:2231-2234
+            pop = exp(-a.c2 * G.elev[s] / vibt) / q_part;         // smm:2241
+        }
+        for (int c = 0; c < 4; c++) {
+            const double w = wc[c] * pop * col;
+            if (!isfinite(w)) flags |= LFLAG_NONFINITE;
+            W[s * 4 + c] = w;
+        }
+    }
+    if (flags) atomicOr(a.flags, flags);
+}
+
+struct LosArgs {
+    GasDev gas[MAX_GAS];
+    int n_gas, n_los, n_steps_max, n_sets_max;
+    const int* n_steps;
+    const int* cells;
+    const double* W;
+    long n_grid, pt0, n_pts;
+    const double* i0;     // [n_los][n_pts] or nullptr
+    double* rad;          // [n_los][n_pts]
+    double* tau_out;      // [n_los][n_steps_max][n_pts] (k_los_tau_src)
+    double* src_out;
+    int solo_absorption;
+};
+
+// tau and J of one step for PPT points of one thread
+template <int PPT>
+__device__ __forceinline__ void step_tau_j(const LosArgs& a, int l, int k, long p_first,
+                                           const bool (&ok)[PPT], double (&tau)[PPT],
+                                           double (&J)[PPT]) {
+#pragma unroll
+    for (int i = 0; i < PPT; i++) tau[i] = J[i] = 0.0;
+    for (int m = 0; m < a.n_gas; m++) {
+        const GasDev& G = a.gas[m];
+        const size_t o = ((size_t)m * a.n_los + l) * a.n_steps_max + k;
+        const int4 cells = __ldg(reinterpret_cast<const int4*>(a.cells + o * 4));
+        const double* __restrict__ W = a.W + o * a.n_sets_max * 4;
+        const int cl[4] = {cells.x, cells.y, cells.z, cells.w};
+        const size_t row = (size_t)a.n_grid;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            if (cl[c] < 0) continue;
+            const float* __restrict__ base =
+                G.g32 + (size_t)cl[c] * G.n_sets * 3 * row + (size_t)(a.pt0 + p_first);
+#pragma unroll 4
+            for (int s = 0; s < G.n_sets; s++) {
+                const double w = __ldg(W + s * 4 + c);
+                const float* __restrict__ r0 = base + (size_t)(s * 3) * row;
+#pragma unroll
+                for (int i = 0; i < PPT; i++) {
+                    if (!ok[i]) continue;
+                    const double e = (double)__ldg(r0 + i * 256);              // sp_emission
+                    const double b = (double)__ldg(r0 + row + i * 256);        // ind_emission
+                    const double ab = (double)__ldg(r0 + 2 * row + i * 256);   // absorption
+                    tau[i] = fma(w, ab - b, tau[i]);     // smm:2244-2247
+                    J[i] = fma(w, e, J[i]);              // smm:2248-2249
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ double layer_update(double I, double tau, double J, int solo) {
+    const double em = expm1(-tau);
+    const double t = 1.0 + em;
+    if (solo) return I * t;
+    const double phi = (tau == 0.0) ? 1.0 : -em / tau;
+    return fma(I, t, J * phi);
+}
+
+template <int PPT, bool MATERIALISE>
+__global__ void __launch_bounds__(256) k_los_fused(LosArgs a) {
+    const int l = blockIdx.y;
+    const long p_first = (long)blockIdx.x * (256 * PPT) + threadIdx.x;
+    bool ok[PPT];
+    double I[PPT], tau[PPT], J[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; i++) {
+        ok[i] = p_first + i * 256 < a.n_pts;
+        I[i] = (ok[i] && a.i0) ? a.i0[(size_t)l * a.n_pts + p_first + i * 256] : 0.0;
+    }
+    const int ns = a.n_steps[l];
+    for (int k = 0; k < ns; k++) {
+        step_tau_j<PPT>(a, l, k, p_first, ok, tau, J);
+        if (MATERIALISE) {
+            const size_t o = ((size_t)l * a.n_steps_max + k) * a.n_pts + p_first;
+#pragma unroll
+            for (int i = 0; i < PPT; i++)
+                if (ok[i]) {
+                    __stcs(a.tau_out + o + i * 256, tau[i]);
+                    __stcs(a.src_out + o + i * 256, tau[i] == 0.0 ? 0.0 : J[i] / tau[i]);
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PPT; i++) I[i] = layer_update(I[i], tau[i], J[i], a.solo_absorption);
+        }
+    }
+    if (!MATERIALISE) {
+#pragma unroll
+        for (int i = 0; i < PPT; i++)
+            if (ok[i]) __stcs(a.rad + (size_t)l * a.n_pts + p_first + i * 256, I[i]);
+    }
+}
+
+// K3: I <- I e^-tau + S (1 - e^-tau) over materialised layers; pure HBM streaming.
+// Each thread owns VEC consecutive points and keeps UNROLL steps of loads in flight.
+template <int VEC>
+__global__ void __launch_bounds__(256) k_los_layers(const double* __restrict__ tau,
+                                                    const double* __restrict__ src,
+                                                    const int* __restrict__ n_steps,
+                                                    int n_steps_max, long n_pts,
+                                                    const double* __restrict__ i0, int solo,
+                                                    double* __restrict__ rad) {
+    constexpr int UNROLL = 4;
+    const int l = blockIdx.y;
+    const long p = ((long)blockIdx.x * 256 + threadIdx.x) * VEC;
+    if (p >= n_pts) return;
+    const int nv = (int)min((long)VEC, n_pts - p);
+    double I[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; v++) I[v] = (i0 && v < nv) ? i0[(size_t)l * n_pts + p + v] : 0.0;
+    const int ns = n_steps[l];
+    const double* __restrict__ tp = tau + (size_t)l * n_steps_max * n_pts + p;
+    const double* __restrict__ sp = src + (size_t)l * n_steps_max * n_pts + p;
+    int k = 0;
+    if (VEC == 2 && nv == 2) {
+        for (; k + UNROLL <= ns; k += UNROLL) {
+            double2 t[UNROLL], s[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                t[u] = __ldcs(reinterpret_cast<const double2*>(tp + (size_t)(k + u) * n_pts));
+                s[u] = __ldcs(reinterpret_cast<const double2*>(sp + (size_t)(k + u) * n_pts));
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const double e0 = expm1(-t[u].x), e1 = expm1(-t[u].y);
+                I[0] = solo ? I[0] * (1.0 + e0) : fma(I[0], 1.0 + e0, -s[u].x * e0);
+                I[1] = solo ? I[1] * (1.0 + e1) : fma(I[1], 1.0 + e1, -s[u].y * e1);
+            }
+        }
+    }
+    for (; k < ns; k++) {
+#pragma unroll
+        for (int v = 0; v < VEC; v++) {
+            if (v >= nv) break;
+            const double t = __ldcs(tp + (size_t)k * n_pts + v);
+            const double s = __ldcs(sp + (size_t)k * n_pts + v);
+            const double em = expm1(-t);
+            I[v] = solo ? I[v] * (1.0 + em) : fma(I[v], 1.0 + em, -s * em);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; v++)
+        if (v < nv) __stcs(rad + (size_t)l * n_pts + p + v, I[v]);
+}
+
+}  // namespace
+
+// =============================================================================================
+// host side
+// =============================================================================================
+struct sr_lut {
+    const float* g32 = nullptr;
+    int n_cells = 0, n_sets = 0, mol = 0, iso = 0, lte_unidentified = 0;
+    long n_grid = 0;
+    double iso_ratio = 1.0;
+    sr_consts c{};
+    std::vector<double> pt, Ps, Ts;
+    std::vector<int> cellmap;
+    sr::DevBuf<double> dPs, dTs, dq, delev;
+    sr::DevBuf<int> dmap;
+    // per-call scratch (owned by the first LUT of a call)
+    sr::DevBuf<int> cells, nsteps, flags;
+    sr::DevBuf<double> W, temp, pres, column, tvib;
+};
+
+namespace {
+
+void unique_sorted(const double* v, int n, int stride, std::vector<double>& out) {
+    out.resize(n);
+    for (int i = 0; i < n; i++) out[i] = v[i * stride];
+    std::sort(out.begin(), out.end());
+    out.erase(std::unique(out.begin(), out.end()), out.end());
+}
+
+void host_nearest_two(const std::vector<double>& nodes, double v, int& i1, int& i2) {
+    const int n = (int)nodes.size();
+    int a = 0;
+    for (int i = 1; i < n; i++)
+        if (std::fabs(nodes[i] - v) < std::fabs(nodes[a] - v)) a = i;
+    int b = -1;
+    for (int i = 0; i < n; i++) {
+        if (i == a) continue;
+        if (b < 0 || std::fabs(nodes[i] - v) < std::fabs(nodes[b] - v)) b = i;
+    }
+    i1 = a;
+    i2 = b;
+}
+
+GasDev gas_dev(const sr_lut* L) {
+    GasDev g;
+    g.g32 = L->g32;
+    g.Ps = L->dPs.p;
+    g.Ts = L->dTs.p;
+    g.cellmap = L->dmap.p;
+    g.qtab = L->dq.p;
+    g.elev = L->delev.p;
+    g.nP = (int)L->Ps.size();
+    g.nT = (int)L->Ts.size();
+    g.n_sets = L->n_sets;
+    g.lte_unidentified = L->lte_unidentified;
+    g.iso_ratio = L->iso_ratio;
+    return g;
+}
+
+int lflags_to_status(int f) {
+    if (f & LFLAG_EXTRAP_P) return sr::fail(SR_ERR_LUT, "Extrapolating in P (spect_main_module.py:1058)");
+    if (f & LFLAG_NO_CELL) return sr::fail(SR_ERR_LUT, "LUT couple not found (spect_main_module.py:989-991)");
+    if (f & LFLAG_NONFINITE) return sr::fail(SR_ERR_LUT, "non-finite LOS step weight (T, T_vib or column)");
+    return SR_OK;
+}
+
+// uploads the step tables, runs k_step_weights; scratch lives in luts[0]
+int prepare_steps(sr_lut* const* luts, const sr_los_steps* S, cudaStream_t st, LosArgs& la) {
+    if (!luts || !S || S->n_gas < 1 || S->n_gas > MAX_GAS || S->n_los < 1 || S->n_steps_max < 1 ||
+        !S->n_steps || !S->temp || !S->pres || !S->column)
+        return sr::fail(SR_ERR_ARG, "LOS step tables: bad argument (n_gas must be 1..%d)", MAX_GAS);
+    sr_lut* L0 = luts[0];
+    int n_sets_max = 0;
+    for (int m = 0; m < S->n_gas; m++) {
+        if (!luts[m]) return sr::fail(SR_ERR_ARG, "LOS: missing LUT %d", m);
+        if (luts[m]->n_grid != L0->n_grid) return sr::fail(SR_ERR_ARG, "LOS: LUT grids differ");
+        n_sets_max = std::max(n_sets_max, luts[m]->n_sets);
+    }
+    if (S->tvib && S->n_sets_max < n_sets_max)
+        return sr::fail(SR_ERR_ARG, "LOS: tvib table has n_sets_max=%d < %d", S->n_sets_max, n_sets_max);
+    if (S->tvib) n_sets_max = S->n_sets_max;
+    const size_t nls = (size_t)S->n_los * S->n_steps_max;
+    for (int l = 0; l < S->n_los; l++)
+        if (S->n_steps[l] < 0 || S->n_steps[l] > S->n_steps_max)
+            return sr::fail(SR_ERR_ARG, "LOS %d: n_steps out of range", l);
+    SR_CUDA(cudaStreamSynchronize(st));  // scratch of a previous call on this LUT may be in use
+    SR_CUDA(L0->nsteps.upload(S->n_steps, S->n_los, st));
+    SR_CUDA(L0->temp.upload(S->temp, nls, st));
+    SR_CUDA(L0->pres.upload(S->pres, nls, st));
+    SR_CUDA(L0->column.upload(S->column, nls * S->n_gas, st));
+    if (S->tvib) SR_CUDA(L0->tvib.upload(S->tvib, nls * S->n_gas * n_sets_max, st));
+    SR_CUDA(L0->cells.ensure(nls * S->n_gas * 4));
+    SR_CUDA(L0->W.ensure(nls * S->n_gas * n_sets_max * 4));
+    if (!L0->flags.p) {
+        SR_CUDA(L0->flags.alloc(1));
+        SR_CUDA(cudaMemsetAsync(L0->flags.p, 0, sizeof(int), st));
+    }
+    StepArgs sa;
+    for (int m = 0; m < S->n_gas; m++) sa.gas[m] = gas_dev(luts[m]);
+    sa.n_gas = S->n_gas;
+    sa.n_los = S->n_los;
+    sa.n_steps_max = S->n_steps_max;
+    sa.n_sets_max = n_sets_max;
+    sa.n_steps = L0->nsteps.p;
+    sa.temp = L0->temp.p;
+    sa.pres = L0->pres.p;
+    sa.column = L0->column.p;
+    sa.tvib = S->tvib ? L0->tvib.p : nullptr;
+    sa.cells = L0->cells.p;
+    sa.W = L0->W.p;
+    sa.flags = L0->flags.p;
+    sa.c2 = L0->c.h_cgs * L0->c.c_cgs / L0->c.k_cgs;
+    dim3 grid((S->n_steps_max + 63) / 64, S->n_los, S->n_gas);
+    SR_LAUNCH(k_step_weights, grid, 64, 0, st, sa);
+    for (int m = 0; m < S->n_gas; m++) la.gas[m] = sa.gas[m];
+    la.n_gas = S->n_gas;
+    la.n_los = S->n_los;
+    la.n_steps_max = S->n_steps_max;
+    la.n_sets_max = n_sets_max;
+    la.n_steps = L0->nsteps.p;
+    la.cells = L0->cells.p;
+    la.W = L0->W.p;
+    la.n_grid = L0->n_grid;
+    return SR_OK;
+}
+
+int check_lflags(sr_lut* L0, cudaStream_t st) {
+    int f = 0;
+    SR_CUDA(cudaMemcpyAsync(&f, L0->flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SR_CUDA(cudaStreamSynchronize(st));
+    if (f) SR_CUDA(cudaMemsetAsync(L0->flags.p, 0, sizeof(int), st));
+    return lflags_to_status(f);
+}
+
+}  // namespace
+
+extern "C" {
+
+int sr_lut_create(const float* g32_dev, const double* pt_host, int n_cells, int n_sets,
+                  long n_grid, const double* level_energy_host, int mol, int iso,
+                  double iso_ratio, int lte_unidentified, const sr_consts* consts, sr_lut** out) {
+    if (!g32_dev || !pt_host || n_cells < 1 || n_sets < 1 || n_grid < 1 || !out ||
+        (!lte_unidentified && !level_energy_host))
+        return sr::fail(SR_ERR_ARG, "sr_lut_create: bad argument");
+    double gi, t[TIPS_N], q[TIPS_N];
+    int rc = sr_bd_tips_2003(mol, iso, &gi, t, q);
+    if (rc) return rc;
+    sr_lut* L = new sr_lut();
+    L->g32 = g32_dev;
+    L->n_cells = n_cells;
+    L->n_sets = n_sets;
+    L->n_grid = n_grid;
+    L->mol = mol;
+    L->iso = iso;
+    L->iso_ratio = iso_ratio;
+    L->lte_unidentified = lte_unidentified;
+    if (consts) L->c = *consts; else sr_default_consts(&L->c);
+    L->pt.assign(pt_host, pt_host + 2 * n_cells);
+    unique_sorted(pt_host, n_cells, 2, L->Ps);
+    unique_sorted(pt_host + 1, n_cells, 2, L->Ts);
+    const int nP = (int)L->Ps.size(), nT = (int)L->Ts.size();
+    L->cellmap.assign((size_t)nP * nT, -1);
+    for (int i = n_cells - 1; i >= 0; i--) {  // first occurrence wins, like list.index (smm:993)
+        int ip = (int)(std::lower_bound(L->Ps.begin(), L->Ps.end(), pt_host[2 * i]) - L->Ps.begin());
+        int it = (int)(std::lower_bound(L->Ts.begin(), L->Ts.end(), pt_host[2 * i + 1]) - L->Ts.begin());
+        L->cellmap[(size_t)ip * nT + it] = i;
+    }
+    std::vector<double> elev(n_sets, 0.0);
+    if (!lte_unidentified) elev.assign(level_energy_host, level_energy_host + n_sets);
+    auto body = [&]() -> int {
+        SR_CUDA(L->dPs.upload(L->Ps.data(), nP));
+        SR_CUDA(L->dTs.upload(L->Ts.data(), nT));
+        SR_CUDA(L->dmap.upload(L->cellmap.data(), L->cellmap.size()));
+        SR_CUDA(L->dq.upload(q, TIPS_N));
+        SR_CUDA(L->delev.upload(elev.data(), n_sets));
+        SR_CUDA(cudaDeviceSynchronize());
+        return SR_OK;
+    };
+    rc = body();
+    if (rc) { delete L; return rc; }
+    *out = L;
+    return SR_OK;
+}
+
+int sr_lut_destroy(sr_lut* lut) {
+    delete lut;
+    return SR_OK;
+}
+
+int sr_lut_weights(const double* pt_host, int n_cells, double pres, double temp, int cell[4],
+                   double w[4]) {
+    if (!pt_host || n_cells < 1 || !cell || !w) return sr::fail(SR_ERR_ARG, "sr_lut_weights: bad argument");
+    std::vector<double> Ps, Ts;
+    unique_sorted(pt_host, n_cells, 2, Ps);
+    unique_sorted(pt_host + 1, n_cells, 2, Ts);
+    auto find = [&](double p, double t) {
+        for (int i = 0; i < n_cells; i++)
+            if (pt_host[2 * i] == p && pt_host[2 * i + 1] == t) return i;
+        return -1;
+    };
+    for (int i = 0; i < 4; i++) { cell[i] = -1; w[i] = 0.0; }
+    if (Ts.size() < 2) return sr::fail(SR_ERR_LUT, "LUT has fewer than two temperatures");
+    if (pres <= Ps.front()) {
+        int ta, tb;
+        host_nearest_two(Ts, temp, ta, tb);
+        cell[0] = find(Ps[0], Ts[ta]);
+        cell[1] = find(Ps[0], Ts[tb]);
+        if (cell[0] < 0 || cell[1] < 0) return lflags_to_status(LFLAG_NO_CELL);
+        w[0] = (Ts[tb] - temp) / (Ts[tb] - Ts[ta]);
+        w[1] = (temp - Ts[ta]) / (Ts[tb] - Ts[ta]);
+    } else if (pres <= Ps.back()) {
+        if (Ps.size() < 2) return lflags_to_status(LFLAG_NO_CELL);
+        int p1, p2, t1, t2;
+        host_nearest_two(Ps, pres, p1, p2);
+        host_nearest_two(Ts, temp, t1, t2);
+        cell[0] = find(Ps[p1], Ts[t1]);
+        cell[1] = find(Ps[p1], Ts[t2]);
+        cell[2] = find(Ps[p2], Ts[t1]);
+        cell[3] = find(Ps[p2], Ts[t2]);
+        for (int i = 0; i < 4; i++)
+            if (cell[i] < 0) return lflags_to_status(LFLAG_NO_CELL);
+        const double wp1 = (Ps[p2] - pres) / (Ps[p2] - Ps[p1]), wp2 = (pres - Ps[p1]) / (Ps[p2] - Ps[p1]);
+        const double wt1 = (Ts[t2] - temp) / (Ts[t2] - Ts[t1]), wt2 = (temp - Ts[t1]) / (Ts[t2] - Ts[t1]);
+        w[0] = wt1 * wp1; w[1] = wt2 * wp1; w[2] = wt1 * wp2; w[3] = wt2 * wp2;
+    } else {
+        return lflags_to_status(LFLAG_EXTRAP_P);
+    }
+    return SR_OK;
+}
+
+int sr_los_rt_layers_dev(const double* tau, const double* src, const int* n_steps, int n_los,
+                         int n_steps_max, long n_pts, const double* i0, int solo_absorption,
+                         double* rad, void* stream) {
+    if (!tau || !src || !n_steps || !rad || n_los < 1 || n_steps_max < 1 || n_pts < 1)
+        return sr::fail(SR_ERR_ARG, "sr_los_rt_layers_dev: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec2 = (n_pts % 2 == 0) && ((uintptr_t)tau % 16 == 0) && ((uintptr_t)src % 16 == 0);
+    if (vec2) {
+        dim3 grid((unsigned)((n_pts / 2 + 255) / 256), n_los);
+        SR_LAUNCH(k_los_layers<2>, grid, 256, 0, st, tau, src, n_steps, n_steps_max, n_pts, i0,
+                  solo_absorption, rad);
+    } else {
+        dim3 grid((unsigned)((n_pts + 255) / 256), n_los);
+        SR_LAUNCH(k_los_layers<1>, grid, 256, 0, st, tau, src, n_steps, n_steps_max, n_pts, i0,
+                  solo_absorption, rad);
+    }
+    return SR_OK;
+}
+
+static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
+                      const double* i0_dev, int solo, double* rad_dev, double* tau_dev,
+                      double* src_dev, cudaStream_t st) {
+    LosArgs la;
+    int rc = prepare_steps(luts, steps, st, la);
+    if (rc) return rc;
+    if (pt0 < 0 || n_pts < 1 || pt0 + n_pts > la.n_grid)
+        return sr::fail(SR_ERR_ARG, "LOS: point range [%ld,%ld) outside the LUT grid", pt0, pt0 + n_pts);
+    la.pt0 = pt0;
+    la.n_pts = n_pts;
+    la.i0 = i0_dev;
+    la.rad = rad_dev;
+    la.tau_out = tau_dev;
+    la.src_out = src_dev;
+    la.solo_absorption = solo;
+    constexpr int PPT = 2;
+    dim3 grid((unsigned)((n_pts + 256 * PPT - 1) / (256 * PPT)), steps->n_los);
+    if (tau_dev) SR_LAUNCH((k_los_fused<PPT, true>), grid, 256, 0, st, la);
+    else SR_LAUNCH((k_los_fused<PPT, false>), grid, 256, 0, st, la);
+    return SR_OK;
+}
+
+int sr_los_rt_lut_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
+                      const double* i0_dev, int solo_absorption, double* rad_dev, void* stream) {
+    if (!rad_dev) return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_dev: bad argument");
+    return los_launch(luts, steps, pt0, n_pts, i0_dev, solo_absorption, rad_dev, nullptr, nullptr,
+                      (cudaStream_t)stream);
+}
+
+int sr_los_tau_src_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
+                       double* tau_dev, double* src_dev, void* stream) {
+    if (!tau_dev || !src_dev) return sr::fail(SR_ERR_ARG, "sr_los_tau_src_dev: bad argument");
+    return los_launch(luts, steps, pt0, n_pts, nullptr, 0, nullptr, tau_dev, src_dev,
+                      (cudaStream_t)stream);
+}
+
+int sr_los_check(sr_lut* const* luts, void* stream) {
+    if (!luts || !luts[0] || !luts[0]->flags.p) return SR_OK;
+    return check_lflags(luts[0], (cudaStream_t)stream);
+}
+
+int sr_los_rt_lut_host(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
+                       const double* i0_host, int solo_absorption, double* rad_host) {
+    if (!rad_host || !steps) return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_host: bad argument");
+    const size_t n = (size_t)steps->n_los * n_pts;
+    sr::DevBuf<double> rad, i0;
+    SR_CUDA(rad.alloc(n));
+    if (i0_host) SR_CUDA(i0.upload(i0_host, n));
+    int rc = los_launch(luts, steps, pt0, n_pts, i0_host ? i0.p : nullptr, solo_absorption, rad.p,
+                        nullptr, nullptr, 0);
+    if (rc) return rc;
+    rc = check_lflags(luts[0], 0);
+    if (rc) return rc;
+    SR_CUDA(cudaMemcpy(rad_host, rad.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return SR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,326 @@
+"""Host-side handles over the Tier-2 C ABI (include/spectrobot.h).
+
+PyTorch is used for what it is good at here: owning device memory and streams.  All arithmetic
+of the hot path happens inside libspectrobot.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import IMXSIG, as_f64, as_i32, check, dptr, iptr, lib
+
+CTYPES = ('sp_emission', 'ind_emission', 'absorption')   # spect_classes.py:313
+
+_LINE_FIELDS = ("freq", "a_coeff", "air_broad", "t_dep", "e_lower", "g_up", "g_lo", "e_vib_up",
+                "e_vib_lo")
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("spectrobot_b200 needs a CUDA device (no CPU fallback)")
+    return torch
+
+
+def _stream_ptr(stream=None):
+    torch = _torch()
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def line_window_offsets(grid):
+    """Window offsets of PrepareCalcShapes (spect_classes.py:1445-1446): built from the ACTUAL
+    grid step grid[1]-grid[0], and required to have exactly imxsig points (humliv_bb's f2py
+    signature fixes the length, lineshape.f:236)."""
+    sp_step = grid[1] - grid[0]
+    lin = np.arange(-IMXSIG * sp_step / 2, IMXSIG * sp_step / 2, sp_step, dtype=float)
+    if len(lin) != IMXSIG:
+        raise ValueError("line window has %d points; humliv_bb needs exactly %d (imxsig)"
+                         % (len(lin), IMXSIG))
+    return lin
+
+
+class LineSet(object):
+    """Device-resident line table of one isotopologue bound to one spectral grid.
+
+    lines: dict of equal-length arrays (freq, a_coeff, air_broad, t_dep, e_lower, g_up, g_lo,
+    e_vib_up, e_vib_lo float64; up_set, lo_set int32), see sr_lines in spectrobot.h.
+    """
+
+    def __init__(self, lines, grid, MM, n_sets, consts=None, lin_grid=None):
+        self._h = C.c_void_p()
+        self.grid = as_f64(grid)
+        self.n_grid = len(self.grid)
+        self.n_sets = int(n_sets)
+        self.MM = float(MM)
+        self.lin_grid = as_f64(line_window_offsets(self.grid) if lin_grid is None else lin_grid)
+        if len(self.lin_grid) != IMXSIG:
+            raise ValueError("lin_grid must have %d points" % IMXSIG)
+        keep = [as_f64(lines[k]) for k in _LINE_FIELDS]
+        up = as_i32(lines["up_set"])
+        lo = as_i32(lines["lo_set"])
+        n = len(up)
+        for a in keep:
+            if len(a) != n:
+                raise ValueError("line arrays have different lengths")
+        st = _lib.sr_lines()
+        st.n_lines = n
+        for name, a in zip(_LINE_FIELDS, keep):
+            setattr(st, name, dptr(a))
+        st.up_set = iptr(up)
+        st.lo_set = iptr(lo)
+        self.consts = consts if consts is not None else _lib.python_consts()
+        self.n_lines = n
+        check(lib().sr_lineset_create(C.byref(st), dptr(self.grid), self.n_grid,
+                                      dptr(self.lin_grid), self.n_sets, self.MM,
+                                      C.byref(self.consts), C.byref(self._h)))
+        self.n_active = int(lib().sr_lineset_n_active(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().sr_lineset_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def centres(self):
+        """closest_grid index of every input line (-1 for lines dropped by the level filter)."""
+        out = np.empty(self.n_lines, dtype=np.int32)
+        check(lib().sr_lineset_centres(self._h, iptr(out)))
+        return out
+
+    def order(self):
+        out = np.empty(self.n_active, dtype=np.int32)
+        check(lib().sr_lineset_order(self._h, iptr(out)))
+        return out
+
+    def cells_elems(self, n_cells):
+        return int(n_cells) * self.n_sets * 3 * self.n_grid
+
+    def gcoeff_cells(self, PTcouples, out=None, stream=None, check_status=True):
+        """[n_cells, n_sets, 3, n_grid] float64 CUDA tensor of G-coefficient spectra."""
+        torch = _torch()
+        pt = as_f64(np.asarray(PTcouples, dtype=float).reshape(-1, 2))
+        n_cells = pt.shape[0]
+        if out is None:
+            out = torch.empty((n_cells, self.n_sets, 3, self.n_grid), dtype=torch.float64,
+                              device="cuda")
+        assert out.is_cuda and out.dtype == torch.float64 and out.is_contiguous()
+        assert out.numel() == self.cells_elems(n_cells)
+        sp = _stream_ptr(stream)
+        check(lib().sr_gcoeff_cells_dev(self._h, dptr(pt), n_cells, C.c_void_p(out.data_ptr()),
+                                        sp))
+        if check_status:
+            check(lib().sr_lineset_check(self._h, sp))
+        return out
+
+    def gcoeff_cells_f32(self, PTcouples, out=None, stream=None):
+        """Same as gcoeff_cells but stored as float32 (the compressed LUT,
+        spect_main_module.py:1676); needs only one cell of FP64 scratch."""
+        torch = _torch()
+        pt = as_f64(np.asarray(PTcouples, dtype=float).reshape(-1, 2))
+        n_cells = pt.shape[0]
+        if out is None:
+            out = torch.empty((n_cells, self.n_sets, 3, self.n_grid), dtype=torch.float32,
+                              device="cuda")
+        scratch = torch.empty((self.n_sets, 3, self.n_grid), dtype=torch.float64, device="cuda")
+        sp = _stream_ptr(stream)
+        check(lib().sr_gcoeff_cells_dev_f32(self._h, dptr(pt), n_cells,
+                                            C.c_void_p(out.data_ptr()),
+                                            C.c_void_p(scratch.data_ptr()), sp))
+        check(lib().sr_lineset_check(self._h, sp))
+        return out
+
+    def gcoeff_cells_host(self, PTcouples, out=None):
+        """Host-buffer entry point (copies inside): numpy [n_cells, n_sets, 3, n_grid]."""
+        pt = as_f64(np.asarray(PTcouples, dtype=float).reshape(-1, 2))
+        n_cells = pt.shape[0]
+        if out is None:
+            out = np.empty((n_cells, self.n_sets, 3, self.n_grid))
+        check(lib().sr_gcoeff_cells_host(self._h, dptr(pt), n_cells, dptr(out)))
+        return out
+
+    def line_shapes(self, Pres, Temp):
+        """Per-line normalised shapes [n_active, 13010] and G coefficients [n_active, 3] (CUDA
+        tensors, internal sorted order; see order())."""
+        torch = _torch()
+        shapes = torch.empty((self.n_active, IMXSIG), dtype=torch.float64, device="cuda")
+        g = torch.empty((self.n_active, 3), dtype=torch.float64, device="cuda")
+        check(lib().sr_line_shapes_dev(self._h, float(Pres), float(Temp),
+                                       C.c_void_p(shapes.data_ptr()), C.c_void_p(g.data_ptr()),
+                                       _stream_ptr()))
+        return shapes, g
+
+
+class Lut(object):
+    """Float32 LUT of one isotopologue resident on the device (sr_lut in spectrobot.h).
+
+    g32: CUDA float32 tensor [n_cells, n_sets, 3, n_grid] (kept alive by this object);
+    PTcouples: [[P_hPa, T_K], ...]; level_energies: per set (cm-1), None for an LTE isotopologue
+    whose lines are not assigned to levels (single set 'all', pop = 1/Q).
+    """
+
+    def __init__(self, g32, PTcouples, mol, iso, iso_ratio, level_energies=None, consts=None):
+        torch = _torch()
+        assert g32.is_cuda and g32.dtype == torch.float32 and g32.is_contiguous() and g32.dim() == 4
+        self.g32 = g32
+        self.pt = as_f64(np.asarray(PTcouples, dtype=float).reshape(-1, 2))
+        n_cells, n_sets, three, n_grid = g32.shape
+        assert three == 3 and n_cells == self.pt.shape[0]
+        self.n_cells, self.n_sets, self.n_grid = n_cells, n_sets, n_grid
+        self.mol, self.iso, self.iso_ratio = int(mol), int(iso), float(iso_ratio)
+        self.lte_unidentified = level_energies is None
+        self.level_energies = None if level_energies is None else as_f64(level_energies)
+        if self.level_energies is not None and len(self.level_energies) != n_sets:
+            raise ValueError("level_energies must have one entry per set")
+        self.consts = consts if consts is not None else _lib.python_consts()
+        self._h = C.c_void_p()
+        check(lib().sr_lut_create(C.c_void_p(g32.data_ptr()), dptr(self.pt), n_cells, n_sets,
+                                  n_grid,
+                                  None if self.level_energies is None else dptr(self.level_energies),
+                                  self.mol, self.iso, self.iso_ratio, int(self.lte_unidentified),
+                                  C.byref(self.consts), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().sr_lut_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class LosSteps(object):
+    """Step tables of a LOS batch (sr_los_steps in spectrobot.h), steps ordered far end ->
+    observer.  n_steps [n_los]; temp, pres [n_los, n_steps_max]; column [n_gas, n_los,
+    n_steps_max]; tvib [n_gas, n_sets_max, n_los, n_steps_max] or None (LTE)."""
+
+    def __init__(self, n_steps, temp, pres, column, tvib=None):
+        self.n_steps = as_i32(n_steps)
+        self.temp = as_f64(temp)
+        self.pres = as_f64(pres)
+        self.column = as_f64(column)
+        self.tvib = None if tvib is None else as_f64(tvib)
+        self.n_los, self.n_steps_max = self.temp.shape
+        if self.column.ndim == 2:
+            self.column = self.column[None]
+        self.n_gas = self.column.shape[0]
+        assert self.pres.shape == self.temp.shape and len(self.n_steps) == self.n_los
+        assert self.column.shape == (self.n_gas, self.n_los, self.n_steps_max)
+        self.n_sets_max = 0
+        if self.tvib is not None:
+            assert self.tvib.ndim == 4 and self.tvib.shape[0] == self.n_gas
+            assert self.tvib.shape[2:] == (self.n_los, self.n_steps_max)
+            self.n_sets_max = self.tvib.shape[1]
+
+    def struct(self):
+        st = _lib.sr_los_steps()
+        st.n_los, st.n_steps_max, st.n_gas, st.n_sets_max = (self.n_los, self.n_steps_max,
+                                                              self.n_gas, self.n_sets_max)
+        st.n_steps = iptr(self.n_steps)
+        st.temp = dptr(self.temp)
+        st.pres = dptr(self.pres)
+        st.column = dptr(self.column)
+        st.tvib = None if self.tvib is None else dptr(self.tvib)
+        return st
+
+    def subset(self, sl):
+        return LosSteps(self.n_steps[sl], self.temp[sl], self.pres[sl], self.column[:, sl],
+                        None if self.tvib is None else self.tvib[:, :, sl])
+
+
+def _lut_array(luts):
+    arr = (C.c_void_p * len(luts))(*[l._h for l in luts])
+    return arr
+
+
+def los_rt_lut(luts, steps, pt0=0, n_pts=None, i0=None, solo_absorption=False, out=None,
+               stream=None, check_status=True):
+    """Fused K3a+K3: radiances [n_los, n_pts] (CUDA float64 tensor) from device-resident LUTs."""
+    torch = _torch()
+    if n_pts is None:
+        n_pts = luts[0].n_grid - pt0
+    if out is None:
+        out = torch.empty((steps.n_los, n_pts), dtype=torch.float64, device="cuda")
+    arr = _lut_array(luts)
+    st = steps.struct()
+    sp = _stream_ptr(stream)
+    check(lib().sr_los_rt_lut_dev(arr, C.byref(st), int(pt0), int(n_pts),
+                                  None if i0 is None else C.c_void_p(i0.data_ptr()),
+                                  int(bool(solo_absorption)), C.c_void_p(out.data_ptr()), sp))
+    if check_status:
+        check(lib().sr_los_check(arr, sp))
+    return out
+
+
+def los_rt_lut_host(luts, steps, pt0=0, n_pts=None, i0=None, solo_absorption=False, out=None):
+    """Host-buffer entry point (copies inside): numpy [n_los, n_pts]."""
+    if n_pts is None:
+        n_pts = luts[0].n_grid - pt0
+    if out is None:
+        out = np.empty((steps.n_los, n_pts))
+    arr = _lut_array(luts)
+    st = steps.struct()
+    i0a = None if i0 is None else as_f64(i0)
+    check(lib().sr_los_rt_lut_host(arr, C.byref(st), int(pt0), int(n_pts),
+                                   None if i0a is None else dptr(i0a),
+                                   int(bool(solo_absorption)), dptr(out)))
+    return out
+
+
+def los_tau_src(luts, steps, pt0=0, n_pts=None, stream=None):
+    """K3a alone: materialised (tau, S) CUDA tensors [n_los, n_steps_max, n_pts]."""
+    torch = _torch()
+    if n_pts is None:
+        n_pts = luts[0].n_grid - pt0
+    shape = (steps.n_los, steps.n_steps_max, n_pts)
+    tau = torch.zeros(shape, dtype=torch.float64, device="cuda")
+    src = torch.zeros(shape, dtype=torch.float64, device="cuda")
+    arr = _lut_array(luts)
+    st = steps.struct()
+    sp = _stream_ptr(stream)
+    check(lib().sr_los_tau_src_dev(arr, C.byref(st), int(pt0), int(n_pts),
+                                   C.c_void_p(tau.data_ptr()), C.c_void_p(src.data_ptr()), sp))
+    check(lib().sr_los_check(arr, sp))
+    return tau, src
+
+
+def los_rt_layers(tau, src, n_steps, i0=None, solo_absorption=False, out=None, stream=None):
+    """K3 alone on materialised layers: tau, src CUDA float64 [n_los, n_steps_max, n_pts];
+    n_steps CUDA int32 [n_los] -> radiances [n_los, n_pts]."""
+    torch = _torch()
+    n_los, n_steps_max, n_pts = tau.shape
+    assert src.shape == tau.shape and tau.is_contiguous() and src.is_contiguous()
+    assert n_steps.is_cuda and n_steps.dtype == torch.int32
+    if out is None:
+        out = torch.empty((n_los, n_pts), dtype=torch.float64, device="cuda")
+    check(lib().sr_los_rt_layers_dev(C.c_void_p(tau.data_ptr()), C.c_void_p(src.data_ptr()),
+                                     C.c_void_p(n_steps.data_ptr()), n_los, n_steps_max, n_pts,
+                                     None if i0 is None else C.c_void_p(i0.data_ptr()),
+                                     int(bool(solo_absorption)), C.c_void_p(out.data_ptr()),
+                                     _stream_ptr(stream)))
+    return out
+
+
+def lut_weights(PTcouples, Pres, Temp):
+    """LutSet.calculate's cell choice (spect_main_module.py:997-1066): (cells[4], weights[4])."""
+    pt = as_f64(np.asarray(PTcouples, dtype=float).reshape(-1, 2))
+    cell = np.empty(4, dtype=np.int32)
+    w = np.empty(4)
+    check(lib().sr_lut_weights(dptr(pt), pt.shape[0], float(Pres), float(Temp), iptr(cell),
+                               dptr(w)))
+    return cell, w
+
+
+def fp64_peak(iters=20000):
+    v = C.c_double()
+    check(lib().sr_fp64_peak(int(iters), C.byref(v)))
+    return v.value
