@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SpectRobot hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement on host cores
+
+Workload (BASELINE.json configs[1]): CH4 3.3 um non-LTE limb radiances, spectral grid
+[2850,3450] cm-1 at 5e-4 (1 200 001 points), 12 vibrational levels, 3e4 synthetic lines, float32
+(P,T) LUT built by the K2 kernel, a block of synthetic VIMS limb lines of sight (tangent heights
+350-1050 km, SZA 30-80 deg, 3 LOS per pixel).
+
+A "step" is one pass of the LOS integral over the resident LOS block:
+  value     LOS radiances/s of K3 (recursion over layer optical depths and source functions that are
+            already resident in HBM), CUDA-event timed, max over ranks
+  e2e       the same metric through the reference-facing host call (radtran_fast's contract: host
+            step tables in, host hi-res radiances out; sr_los_rt_lut_host), copies inside
+  roofline  K3 kernel against the measured HBM copy bandwidth (16 B per LOS*step*point + 8 B per
+            LOS*point)
+Extra objects report the other two parts of BASELINE.json's metric: "voigt" (K1 line*gridpoint
+evals/s, FP64 roofline) and "lut_build" (K2 wall time of the whole LUT), and "fused" (K3a+K3 from
+the LUT with device-resident inputs).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_GRID_FULL = 1200001
+W0, W1 = 2850.0, 3450.0
+N_LEVELS = 12
+N_LINES = 30000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--los-block", type=int, default=36, help="LOS per rank in the K3 block")
+    ap.add_argument("--e2e-los", type=int, default=12, help="LOS per host call of the e2e leg")
+    ap.add_argument("--lines", type=int, default=N_LINES)
+    ap.add_argument("--small", action="store_true", help="tiny sizes (CI / debugging only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------
+def make_workload(args, rank, n_los):
+    from spectrobot_b200 import synthetic as S
+    w0, w1 = (2990.0, 3010.0) if args.small else (W0, W1)
+    grid = S.spectral_grid(w0, w1)
+    n_lines = 600 if args.small else args.lines
+    lines = S.line_table(n_lines, w0, w1, n_levels=N_LEVELS)
+    atm = S.titan_atmosphere()
+    rng = np.random.default_rng(S.SEED + 1000 * rank)
+    n_pix = (n_los + 2) // 3
+    tg = rng.uniform(350.0, 1050.0, n_pix)
+    band = rng.integers(0, 7, n_pix)
+    sza = rng.uniform(30.0, 80.0, n_pix)
+    # 3 LOS per pixel (low, centre, up: spect_main_module.py:3091-3096), +-12 km about the centre
+    tgs = np.repeat(tg, 3)[:n_los] + np.tile([-12.0, 0.0, 12.0], n_pix)[:n_los]
+    st = S.limb_los_steps(tgs, np.repeat(band, 3)[:n_los], np.repeat(sza, 3)[:n_los], atm,
+                          lines["level_energies"])
+    # LUT cells must cover every rank's LOS block: use the envelope of the whole tangent range
+    env = S.limb_los_steps([338.0, 1062.0] * 7, list(range(7)) * 2, [55.0] * 14, atm,
+                           lines["level_energies"])
+    pmin = min(st["pres"][st["pres"] > 1e-6].min(), env["pres"][env["pres"] > 1e-6].min())
+    pmax = max(st["pres"].max(), env["pres"].max())
+    tmin = min(st["temp"].min(), env["temp"].min())
+    tmax = max(st["temp"].max(), env["temp"].max())
+    cells = S.rect_cells(pmin * 0.9, pmax * 1.1, tmin, tmax)
+    return dict(grid=grid, lines=lines, st=st, cells=cells, S=S)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4)
+                          if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm (oracle): used as cpu_baseline of our arm and as --impl reference
+# --------------------------------------------------------------------------------------------
+def cpu_los_sample(args, wl, seconds, threads):
+    """Times the CPU restatement of the LOS path (LUT interpolation + populations + layer
+    recursion, oracle/sr_oracle.c orc_los_rt) on a bounded sample of the workload: a few LOS of
+    the block on a contiguous range of grid points, LUT rows for that range built by the CPU
+    restatement of the cell builder from the lines centred inside the range.
+    Returns (LOS-equivalents per second, description)."""
+    from oracle import cpu_oracle as O
+    S = wl["S"]
+    st, grid, lines = wl["st"], wl["grid"], wl["lines"]
+    n_pts = 4096 if args.small else 16384
+    pt0 = (len(grid) // 2 // 1024) * 1024
+    sub = grid[pt0:pt0 + n_pts]
+    inside = (lines["freq"] > sub[0]) & (lines["freq"] < sub[-1])
+    sub_lines = {k: (v[inside] if isinstance(v, np.ndarray) and v.shape[:1] == inside.shape else v)
+                 for k, v in lines.items()}
+    n_los = min(2, st["temp"].shape[0])
+    need = set()
+    for l in range(n_los):
+        for k in range(st["n_steps"][l]):
+            c, _ = O.lut_weights(wl["cells"], st["pres"][l, k], st["temp"][l, k])
+            need.update(int(x) for x in c if x >= 0)
+    lin = O.line_window_offsets(grid)
+    g32 = np.zeros((len(wl["cells"]), N_LEVELS, 3, n_pts), dtype=np.float32)
+    for c in sorted(need):
+        P, T = wl["cells"][c]
+        g32[c] = O.gcoeff_cell(sub_lines, sub, T, P, S.CH4_MM, N_LEVELS, n_threads=threads,
+                               lin_grid=lin).astype(np.float32)
+    lut = dict(g32=g32, pt=np.array(wl["cells"]), level_energy=lines["level_energies"], mol=6,
+               iso=1, iso_ratio=S.CH4_RATIO, lte_unidentified=False)
+    sl = slice(0, n_los)
+    kw = dict(n_steps=st["n_steps"][sl], temp=st["temp"][sl], pres=st["pres"][sl],
+              column=st["column"][:, sl], tvib=st["tvib"][:, :, sl], n_threads=threads)
+    O.los_rt([lut], **kw)                                   # warm-up
+    reps, t_used = 0, 0.0
+    while t_used < seconds and reps < 50:
+        t0 = time.perf_counter()
+        O.los_rt([lut], **kw)
+        t_used += time.perf_counter() - t0
+        reps += 1
+    per = t_used / reps
+    los_equiv = n_los * n_pts / float(len(grid))
+    desc = ("%d LOS x %d of %d grid points, %d steps/LOS avg, %d threads, %d reps; "
+            "CPU restatement (oracle) of LUT interpolation + level populations + layer recursion"
+            % (n_los, n_pts, len(grid), int(st["n_steps"][sl].mean()), threads, reps))
+    return los_equiv / per, per, desc
+
+
+def cpu_voigt_sample(args, wl, threads):
+    """CPU restatement of one LUT cell (humliv_bb + G coefficients + line sum) on a line sample."""
+    from oracle import cpu_oracle as O
+    S = wl["S"]
+    grid, lines = wl["grid"], wl["lines"]
+    n = min(len(lines["freq"]), 200 if args.small else 4000)
+    sub_lines = {k: (v[:n] if isinstance(v, np.ndarray) and v.shape[:1] == lines["freq"].shape else v)
+                 for k, v in lines.items()}
+    t0 = time.perf_counter()
+    O.gcoeff_cell(sub_lines, grid, 160.0, 0.05, S.CH4_MM, N_LEVELS, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return n * 13010 / dt, "%d lines x 13010 points, one (P,T) cell, %d threads" % (n, threads)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    wl = make_workload(args, 0, max(2, min(args.los_block, 6)))
+    vals, per = [], []
+    for i in range(args.warmup + args.steps):
+        v, p, desc = cpu_los_sample(args, wl, seconds=2.0, threads=threads)
+        if i >= args.warmup:
+            vals.append(v)
+            per.append(p)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "LOS radiances/s", "value": value, "unit": "LOS/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * float(np.mean(per)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, wl),
+        "cpu_baseline": {"value": value, "unit": "LOS/s", "cores": threads, "kind": "port",
+                         "sample": desc},
+        "e2e": {"value": value, "unit": "LOS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference (Fortran 77 + Python 2, spect_base_module missing) cannot be built "
+                "or run here; this arm times the C restatement in oracle/ on all host threads",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, wl):
+    return {"workload": "CH4 3.3um non-LTE limb LOS radiances (BASELINE configs[1], "
+                        "radtran_3D_ch4.py shape)",
+            "grid": "[%g,%g] cm-1 step 5e-4 (%d points)" % (wl["grid"][0], wl["grid"][-1],
+                                                           len(wl["grid"])),
+            "n_levels": N_LEVELS, "n_lines": int(len(wl["lines"]["freq"])),
+            "lut_cells": len(wl["cells"]), "los_per_rank": int(wl["st"]["temp"].shape[0]),
+            "steps_per_los_mean": float(wl["st"]["n_steps"].mean()),
+            "l2": "inputs larger than L2 (tau/S block streamed once per step)",
+            "small": bool(args.small)}
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from spectrobot_b200 import engine
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    engine.lib().sr_set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = engine.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n_los = 6 if args.small else args.los_block
+    wl = make_workload(args, rank, n_los)
+    S, grid, lines, st, cells = wl["S"], wl["grid"], wl["lines"], wl["st"], wl["cells"]
+    n_grid, n_cells = len(grid), len(cells)
+    ls = engine.LineSet(lines, grid, S.CH4_MM, N_LEVELS)
+
+    # ---- K1: one cell, evals/s --------------------------------------------------------------
+    cell_buf = torch.empty((1, N_LEVELS, 3, n_grid), dtype=torch.float64, device="cuda")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        ls.gcoeff_cells([[0.05, 160.0]], out=cell_buf)
+    k1_ms = []
+    for i in range(5):
+        torch.cuda.synchronize()
+        ev0.record()
+        ls.gcoeff_cells([[0.05 * (1 + i), 160.0]], out=cell_buf, check_status=False)
+        ev1.record()
+        torch.cuda.synchronize()
+        k1_ms.append(ev0.elapsed_time(ev1))
+    k1_t = float(np.median(k1_ms)) * 1e-3
+    evals = ls.n_active * 13010.0
+    fp64_peak = engine.fp64_peak(40000)
+    voigt = {"metric": "Voigt line*gridpoint evals/s", "value": evals / k1_t, "unit": "evals/s",
+             "ms_per_cell": 1e3 * k1_t, "lines": int(ls.n_active),
+             "roofline": {"bound": "fp64", "achieved": 15.0 * evals / k1_t / 1e12,
+                          "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                          "frac": 15.0 * evals / k1_t / fp64_peak, "traffic": None,
+                          "note": "15 FP64 flop per eval (SURVEY 8d) over the DFMA rate measured "
+                                  "live by sr_fp64_peak"}}
+    del cell_buf
+
+    # ---- K2: LUT build (cells sharded over ranks, all_gather) --------------------------------
+    my_cells = list(range(rank, n_cells, world))
+    g32 = torch.empty((n_cells, N_LEVELS, 3, n_grid), dtype=torch.float32, device="cuda")
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    if my_cells:
+        mine = ls.gcoeff_cells_f32([cells[c] for c in my_cells])
+    ev1.record()
+    torch.cuda.synchronize()
+    build_dev_s = ev0.elapsed_time(ev1) * 1e-3
+    if world > 1:
+        # cells are independent: the only exchange is the final gather of the LUT (NCCL)
+        for src in range(world):
+            idx = list(range(src, n_cells, world))
+            if not idx:
+                continue
+            buf = mine if src == rank else torch.empty((len(idx), N_LEVELS, 3, n_grid),
+                                                        dtype=torch.float32, device="cuda")
+            dist.broadcast(buf, src=src)
+            g32[idx] = buf
+            del buf
+    else:
+        g32[my_cells] = mine
+    del mine
+    barrier()
+    build_wall_s = max_over_ranks(time.perf_counter() - t0)
+    lut_build = {"metric": "CH4 LUT build time", "value": build_wall_s, "unit": "s",
+                 "cells": n_cells, "device_s_per_rank": max_over_ranks(build_dev_s),
+                 "evals_per_s": n_cells * evals / build_wall_s, "includes": "float32 cast + gather"}
+    lut = engine.Lut(g32, cells, 6, 1, S.CH4_RATIO, level_energies=lines["level_energies"])
+    steps = engine.LosSteps(st["n_steps"], st["temp"], st["pres"], st["column"], st["tvib"])
+
+    # ---- K3a: materialise tau/S of the block (resident inputs of K3) -------------------------
+    tau, src = engine.los_tau_src([lut], steps)
+    nst = torch.tensor(st["n_steps"], dtype=torch.int32, device="cuda")
+    rad = torch.empty((n_los, n_grid), dtype=torch.float64, device="cuda")
+    step_pts = float(st["n_steps"].sum()) * n_grid
+    k3_bytes = 16.0 * step_pts + 8.0 * n_los * n_grid
+
+    sampler = ClockSampler(local)
+    for _ in range(args.warmup):
+        engine.los_rt_layers(tau, src, nst, out=rad)
+    barrier()
+    l0 = lib.sr_kernel_launch_count()
+    sampler.start()
+    ev0.record()
+    for _ in range(args.steps):
+        engine.los_rt_layers(tau, src, nst, out=rad)
+    ev1.record()
+    barrier()
+    k3_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    launches = lib.sr_kernel_launch_count() - l0
+    value = world * n_los / (k3_ms * 1e-3)
+    rad_k3 = rad.clone()
+
+    # ---- fused K3a+K3 from the LUT, device-resident ------------------------------------------
+    for _ in range(2):
+        engine.los_rt_lut([lut], steps, out=rad)
+    barrier()
+    ev0.record()
+    n_f = max(1, min(args.steps, 3))
+    for _ in range(n_f):
+        engine.los_rt_lut([lut], steps, out=rad, check_status=False)
+    ev1.record()
+    barrier()
+    fused_ms = max_over_ranks(ev0.elapsed_time(ev1)) / n_f
+    agree = float(((rad - rad_k3).abs() / rad_k3.abs().clamp_min(1e-300)).max().item())
+    del tau, src
+
+    # ---- e2e: reference-facing host call (host step tables in, host radiances out) ------------
+    n_e = min(n_los, 3 if args.small else args.e2e_los)
+    sub = steps.subset(slice(0, n_e))
+    host_out = torch.empty((n_e, n_grid), dtype=torch.float64).pin_memory().numpy()
+    engine.los_rt_lut_host([lut], sub, out=host_out)
+    barrier()
+    t0 = time.perf_counter()
+    n_h = max(1, min(args.steps, 3))
+    for _ in range(n_h):
+        engine.los_rt_lut_host([lut], sub, out=host_out)
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / n_h)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    h2d = int(sub.n_steps.nbytes + sub.temp.nbytes + sub.pres.nbytes + sub.column.nbytes +
+              sub.tvib.nbytes)
+    d2h = int(host_out.nbytes)
+
+    peaks = measured_peaks()
+    hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+    achieved = k3_bytes / (k3_ms * 1e-3) / 1e9
+    line = {
+        "metric": "LOS radiances/s", "value": value, "unit": "LOS/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": k3_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args, wl),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": None, "kernel": "k_los_layers",
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks
+                     else "fallback 6650 GB/s (of fallback)",
+                     "algorithmic_bytes_per_launch": k3_bytes},
+        "e2e": {"value": world * n_e / e2e_s, "unit": "LOS/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "los_per_call": n_e,
+                "path": "sr_los_rt_lut_host: LUT interpolation + populations + layer recursion, "
+                        "host step tables -> host hi-res radiances"},
+        "fused": {"value": world * n_los / (fused_ms * 1e-3), "unit": "LOS/s",
+                  "ms_per_step": fused_ms, "step_points_per_s": world * step_pts / (fused_ms * 1e-3),
+                  "max_rel_diff_vs_k3": agree},
+        "voigt": voigt, "lut_build": lut_build,
+        "gpu_launches": int(launches), "clocks": sampler.summary(),
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, per, desc = cpu_los_sample(args, wl, seconds=args.cpu_seconds, threads=threads)
+        line["cpu_baseline"] = {"value": v, "unit": "LOS/s", "cores": threads, "kind": "port",
+                                "sample": desc}
+        ve, vdesc = cpu_voigt_sample(args, wl, threads)
+        line["voigt"]["cpu_baseline"] = {"value": ve, "unit": "evals/s", "cores": threads,
+                                         "kind": "port", "sample": vdesc}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

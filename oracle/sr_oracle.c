@@ -757,10 +757,10 @@ static int orc_abs_emi(const orc_lut* L, long n_grid, double pres, double temp,
     return 0;
 }
 
-/* DESIGN.md 6.4 layer update: I <- I e^-tau + J phi(tau), phi = (1-e^-tau)/tau (1 at 0) */
+/* DESIGN.md 6.4 layer update: I <- I exp(-tau) + J phi(tau), phi = -expm1(-tau)/tau (1 at 0) */
 static inline double layer_update(double I, double tau, double J, int solo_absorption) {
     double em = expm1(-tau);
-    double t = 1.0 + em;
+    double t = exp(-tau);
     if (solo_absorption) return I * t;
     double phi = (tau == 0.0) ? 1.0 : -em / tau;
     return I * t + J * phi;
@@ -835,8 +835,8 @@ void orc_los_layers(const double* tau, const double* src, const int* n_steps, in
             double I = i0 ? i0[(size_t)l * n_pts + i] : 0.0;
             for (int k = 0; k < n_steps[l]; k++) {
                 size_t o = ((size_t)l * n_steps_max + k) * n_pts + i;
-                double em = expm1(-tau[o]);
-                I = solo_absorption ? I * (1.0 + em) : I * (1.0 + em) + src[o] * (-em);
+                double em = expm1(-tau[o]), t = exp(-tau[o]);
+                I = solo_absorption ? I * t : I * t + src[o] * (-em);
             }
             rad[(size_t)l * n_pts + i] = I;
         }

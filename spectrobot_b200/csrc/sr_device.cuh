@@ -126,4 +126,37 @@ __device__ __forceinline__ double humliv_reg1_fast(double u, double c2) {
 
 __device__ __forceinline__ long long f_nint(double x) { return llround(x); }  // Fortran NINT
 
+// exp(x) and expm1(x) from ONE range reduction and ONE polynomial (layer update of the LOS
+// recursion needs both: the transmission exp(-tau) must stay accurate when tau is large, the
+// emission weight 1-exp(-tau) when tau is tiny).
+//   x = n ln2 + r, |r| <= ln2/2;  p = expm1(r) (Taylor to r^13, |err| < 5e-18 |r|)
+//   exp(x) = 2^n (1 + p);  expm1(x) = 2^n p + (2^n - 1)
+__device__ __forceinline__ void exp_pair(double x, double& ex, double& em) {
+    const double n = rint(x * 1.4426950408889634);
+    if (!(n > -1000.0 && n < 1000.0)) {   // |x| > ~693 or NaN: rare, take the library path
+        ex = exp(x);
+        em = expm1(x);
+        return;
+    }
+    double r = fma(n, -6.93147180369123816490e-01, x);   // ln2 hi
+    r = fma(n, -1.90821492927058770002e-10, r);          // ln2 lo
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p * r, r, r);                                // expm1(r)
+    const int ni = (int)n;
+    const double s = __hiloint2double((ni + 1023) << 20, 0);   // 2^n
+    ex = fma(s, p, s);
+    em = (ni == 0) ? p : fma(s, p, s - 1.0);
+}
+
 }  // namespace srdev

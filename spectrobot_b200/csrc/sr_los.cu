@@ -20,6 +20,7 @@
 #include <cmath>
 #include <vector>
 #include "sr_common.h"
+#include "sr_device.cuh"
 
 namespace {
 
@@ -204,9 +205,10 @@ __device__ __forceinline__ void step_tau_j(const LosArgs& a, int l, int k, long 
     }
 }
 
+// I <- I exp(-tau) + J phi(tau), phi = (1 - exp(-tau))/tau (1 at tau = 0)
 __device__ __forceinline__ double layer_update(double I, double tau, double J, int solo) {
-    const double em = expm1(-tau);
-    const double t = 1.0 + em;
+    double t, em;
+    srdev::exp_pair(-tau, t, em);
     if (solo) return I * t;
     const double phi = (tau == 0.0) ? 1.0 : -em / tau;
     return fma(I, t, J * phi);
@@ -246,56 +248,58 @@ __global__ void __launch_bounds__(256) k_los_fused(LosArgs a) {
     }
 }
 
-// K3: I <- I e^-tau + S (1 - e^-tau) over materialised layers; pure HBM streaming.
-// Each thread owns VEC consecutive points and keeps UNROLL steps of loads in flight.
-template <int VEC>
+// K3: I <- I exp(-tau) + S (1 - exp(-tau)) over materialised layers; pure HBM streaming.
+// Each thread owns PPT points (stride 256, so every warp load is one coalesced 256-byte row
+// segment for any n_pts parity) and keeps UNROLL steps x PPT points x 2 arrays of loads in flight.
+template <int PPT, int UNROLL>
 __global__ void __launch_bounds__(256) k_los_layers(const double* __restrict__ tau,
                                                     const double* __restrict__ src,
                                                     const int* __restrict__ n_steps,
                                                     int n_steps_max, long n_pts,
                                                     const double* __restrict__ i0, int solo,
                                                     double* __restrict__ rad) {
-    constexpr int UNROLL = 4;
     const int l = blockIdx.y;
-    const long p = ((long)blockIdx.x * 256 + threadIdx.x) * VEC;
-    if (p >= n_pts) return;
-    const int nv = (int)min((long)VEC, n_pts - p);
-    double I[VEC];
+    const long p0 = (long)blockIdx.x * (256 * PPT) + threadIdx.x;
+    if (p0 >= n_pts) return;
+    bool ok[PPT];
+    double I[PPT];
 #pragma unroll
-    for (int v = 0; v < VEC; v++) I[v] = (i0 && v < nv) ? i0[(size_t)l * n_pts + p + v] : 0.0;
+    for (int i = 0; i < PPT; i++) {
+        ok[i] = p0 + i * 256 < n_pts;
+        I[i] = (i0 && ok[i]) ? i0[(size_t)l * n_pts + p0 + i * 256] : 0.0;
+    }
     const int ns = n_steps[l];
-    const double* __restrict__ tp = tau + (size_t)l * n_steps_max * n_pts + p;
-    const double* __restrict__ sp = src + (size_t)l * n_steps_max * n_pts + p;
+    const double* __restrict__ tp = tau + (size_t)l * n_steps_max * n_pts + p0;
+    const double* __restrict__ sp = src + (size_t)l * n_steps_max * n_pts + p0;
+    auto update = [&](int i, double t, double s) {
+        double ex, em;
+        srdev::exp_pair(-t, ex, em);
+        I[i] = solo ? I[i] * ex : fma(I[i], ex, -s * em);
+    };
     int k = 0;
-    if (VEC == 2 && nv == 2) {
-        for (; k + UNROLL <= ns; k += UNROLL) {
-            double2 t[UNROLL], s[UNROLL];
+    for (; k + UNROLL <= ns; k += UNROLL) {
+        double t[UNROLL][PPT], s[UNROLL][PPT];
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                t[u] = __ldcs(reinterpret_cast<const double2*>(tp + (size_t)(k + u) * n_pts));
-                s[u] = __ldcs(reinterpret_cast<const double2*>(sp + (size_t)(k + u) * n_pts));
+        for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+            for (int i = 0; i < PPT; i++) {
+                const size_t o = (size_t)(k + u) * n_pts + i * 256;
+                t[u][i] = ok[i] ? __ldcs(tp + o) : 0.0;
+                s[u][i] = ok[i] ? __ldcs(sp + o) : 0.0;
             }
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++) {
-                const double e0 = expm1(-t[u].x), e1 = expm1(-t[u].y);
-                I[0] = solo ? I[0] * (1.0 + e0) : fma(I[0], 1.0 + e0, -s[u].x * e0);
-                I[1] = solo ? I[1] * (1.0 + e1) : fma(I[1], 1.0 + e1, -s[u].y * e1);
-            }
-        }
-    }
-    for (; k < ns; k++) {
+        for (int u = 0; u < UNROLL; u++)
 #pragma unroll
-        for (int v = 0; v < VEC; v++) {
-            if (v >= nv) break;
-            const double t = __ldcs(tp + (size_t)k * n_pts + v);
-            const double s = __ldcs(sp + (size_t)k * n_pts + v);
-            const double em = expm1(-t);
-            I[v] = solo ? I[v] * (1.0 + em) : fma(I[v], 1.0 + em, -s * em);
-        }
+            for (int i = 0; i < PPT; i++) update(i, t[u][i], s[u][i]);
     }
+    for (; k < ns; k++)
 #pragma unroll
-    for (int v = 0; v < VEC; v++)
-        if (v < nv) __stcs(rad + (size_t)l * n_pts + p + v, I[v]);
+        for (int i = 0; i < PPT; i++)
+            if (ok[i]) update(i, __ldcs(tp + (size_t)k * n_pts + i * 256),
+                              __ldcs(sp + (size_t)k * n_pts + i * 256));
+#pragma unroll
+    for (int i = 0; i < PPT; i++)
+        if (ok[i]) __stcs(rad + (size_t)l * n_pts + p0 + i * 256, I[i]);
 }
 
 }  // namespace
@@ -534,16 +538,10 @@ int sr_los_rt_layers_dev(const double* tau, const double* src, const int* n_step
     if (!tau || !src || !n_steps || !rad || n_los < 1 || n_steps_max < 1 || n_pts < 1)
         return sr::fail(SR_ERR_ARG, "sr_los_rt_layers_dev: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    const bool vec2 = (n_pts % 2 == 0) && ((uintptr_t)tau % 16 == 0) && ((uintptr_t)src % 16 == 0);
-    if (vec2) {
-        dim3 grid((unsigned)((n_pts / 2 + 255) / 256), n_los);
-        SR_LAUNCH(k_los_layers<2>, grid, 256, 0, st, tau, src, n_steps, n_steps_max, n_pts, i0,
-                  solo_absorption, rad);
-    } else {
-        dim3 grid((unsigned)((n_pts + 255) / 256), n_los);
-        SR_LAUNCH(k_los_layers<1>, grid, 256, 0, st, tau, src, n_steps, n_steps_max, n_pts, i0,
-                  solo_absorption, rad);
-    }
+    constexpr int PPT = 2, UNROLL = 8;
+    dim3 grid((unsigned)((n_pts + 256 * PPT - 1) / (256 * PPT)), n_los);
+    SR_LAUNCH((k_los_layers<PPT, UNROLL>), grid, 256, 0, st, tau, src, n_steps, n_steps_max, n_pts,
+              i0, solo_absorption, rad);
     return SR_OK;
 }
 

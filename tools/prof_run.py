@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Small driver for ncu captures of single kernels (see profiles/README.md for the commands).
+
+    python tools/prof_run.py k1      # K1/K2 tile kernel: one CH4 LUT cell, 3e4 lines, 800 001 points
+    python tools/prof_run.py k3      # K3 recursion over materialised layers
+    python tools/prof_run.py fused   # K3a+K3 fused from the LUT
+Prints CUDA-event timings so the same command is meaningful without ncu.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+from spectrobot_b200 import engine, synthetic as S  # noqa: E402
+
+
+def timed(fn, n=3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = []
+    for _ in range(n):
+        torch.cuda.synchronize()
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out.append(e0.elapsed_time(e1))
+    return out
+
+
+def k1(n_lines=30000, n_lev=12, w0=2825.0, w1=3225.0):
+    g = S.spectral_grid(w0, w1)
+    lines = S.line_table(n_lines, w0, w1, n_levels=n_lev)
+    ls = engine.LineSet(lines, g, S.CH4_MM, n_lev)
+    out = torch.empty((1, n_lev, 3, len(g)), dtype=torch.float64, device="cuda")
+    for P, T in ((1e-4, 150.0), (0.05, 160.0), (2.5, 175.0)):
+        ms = timed(lambda: ls.gcoeff_cells([[P, T]], out=out, check_status=False))
+        print("k1 P=%g T=%g: %s ms -> %.3e evals/s" % (P, T, ["%.3f" % m for m in ms],
+                                                       ls.n_active * 13010 / (min(ms) * 1e-3)))
+
+
+def los(mode, n_los=8):
+    w0, w1 = 2850.0, 3450.0
+    g = S.spectral_grid(w0, w1)
+    n_lev = 12
+    lines = S.line_table(30000, w0, w1, n_levels=n_lev)
+    atm = S.titan_atmosphere()
+    tg = np.linspace(360.0, 1040.0, n_los)
+    st = S.limb_los_steps(tg, [3] * n_los, [50.0] * n_los, atm, lines["level_energies"])
+    cells = S.rect_cells(st["pres"][st["pres"] > 1e-6].min() * 0.9, st["pres"].max() * 1.1,
+                         st["temp"].min(), st["temp"].max())
+    ls = engine.LineSet(lines, g, S.CH4_MM, n_lev)
+    g32 = ls.gcoeff_cells_f32(cells)
+    lut = engine.Lut(g32, cells, 6, 1, S.CH4_RATIO, level_energies=lines["level_energies"])
+    steps = engine.LosSteps(st["n_steps"], st["temp"], st["pres"], st["column"], st["tvib"])
+    sp = float(st["n_steps"].sum()) * len(g)
+    if mode == "k3":
+        tau, src = engine.los_tau_src([lut], steps)
+        nst = torch.tensor(st["n_steps"], dtype=torch.int32, device="cuda")
+        rad = torch.empty((n_los, len(g)), dtype=torch.float64, device="cuda")
+        ms = timed(lambda: engine.los_rt_layers(tau, src, nst, out=rad), 5)
+        print("k3: %s ms -> %.1f GB/s" % (["%.3f" % m for m in ms],
+                                          (16 * sp + 8 * n_los * len(g)) / (min(ms) * 1e-3) / 1e9))
+    else:
+        rad = torch.empty((n_los, len(g)), dtype=torch.float64, device="cuda")
+        ms = timed(lambda: engine.los_rt_lut([lut], steps, out=rad, check_status=False), 3)
+        print("fused: %s ms -> %.3e step-points/s" % (["%.3f" % m for m in ms], sp / (min(ms) * 1e-3)))
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1] if len(sys.argv) > 1 else "k1"
+    if mode == "k1":
+        k1()
+    else:
+        los(mode)
