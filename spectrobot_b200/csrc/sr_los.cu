@@ -18,6 +18,7 @@
 //   k_los_layers    K3 alone: HBM-streaming recursion over materialised tau/S
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 #include "sr_common.h"
 #include "sr_device.cuh"
@@ -538,10 +539,25 @@ int sr_los_rt_layers_dev(const double* tau, const double* src, const int* n_step
     if (!tau || !src || !n_steps || !rad || n_los < 1 || n_steps_max < 1 || n_pts < 1)
         return sr::fail(SR_ERR_ARG, "sr_los_rt_layers_dev: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    constexpr int PPT = 2, UNROLL = 8;
-    dim3 grid((unsigned)((n_pts + 256 * PPT - 1) / (256 * PPT)), n_los);
-    SR_LAUNCH((k_los_layers<PPT, UNROLL>), grid, 256, 0, st, tau, src, n_steps, n_steps_max, n_pts,
-              i0, solo_absorption, rad);
+    // measured on B200 (tools/tune.py): (PPT=1, UNROLL=4) at 38 registers streams at the
+    // measured copy bandwidth; wider variants lose occupancy
+    int cfg = 5;
+    if (const char* e = getenv("SR_K3_CFG")) cfg = atoi(e);   // tuning aid
+#define SR_K3_LAUNCH(PPT, UNROLL)                                                             \
+    {                                                                                          \
+        dim3 grid((unsigned)((n_pts + 256 * PPT - 1) / (256 * PPT)), n_los);                   \
+        SR_LAUNCH((k_los_layers<PPT, UNROLL>), grid, 256, 0, st, tau, src, n_steps,            \
+                  n_steps_max, n_pts, i0, solo_absorption, rad);                               \
+    }
+    switch (cfg) {
+        case 1: SR_K3_LAUNCH(1, 8) break;
+        case 2: SR_K3_LAUNCH(2, 4) break;
+        case 3: SR_K3_LAUNCH(1, 16) break;
+        case 4: SR_K3_LAUNCH(4, 4) break;
+        case 5: SR_K3_LAUNCH(1, 4) break;
+        default: SR_K3_LAUNCH(2, 8) break;
+    }
+#undef SR_K3_LAUNCH
     return SR_OK;
 }
 

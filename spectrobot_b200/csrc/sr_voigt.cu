@@ -9,18 +9,23 @@
 //   LookUpTable.make / LutSet.add_PT loops   spect_main_module.py:753-774, 1122-1168
 //
 // Data layout in HBM
-//   line table      SoA doubles/ints, sorted by (group=(upper set, lower set), centre index)
-//   LineCell rec    [cell][line] 128-byte records: per-(line,cell) widths, region boundaries and
-//                   G coefficients, written by k_line_cell_params, read by the tile kernel
-//   out             [cell][set][ctype][n_grid] doubles, each element written exactly once
+//   line table   SoA doubles/ints, sorted by (group = (upper set, lower set), centre index)
+//   LineCell     [cell][line] 128 B: widths, region boundaries, G coefficients of one (line, cell)
+//   LineRec      [cell][line] 112 B: the far-wing (region 1) form of the same line in ABSOLUTE grid
+//                coordinates; contiguous runs are TMA-bulk-copied into shared memory
+//   core         [cell][line][CORE_STRIDE] K(x,y) of the window points il..ir (regions 2/3/4)
+//   out          [cell][set][ctype][n_grid] doubles, each element written exactly once
 //
-// Kernel k_voigt_tile: one CTA owns TP = 256*PPT consecutive grid points of one cell and keeps
-// the n_sets*3 output rows of that tile in shared memory.  It walks the lines whose 13010-point
-// window touches the tile, group by group; every thread accumulates the three G-weighted sums of
-// its PPT points in FP64 registers and flushes them to the shared tile when the group changes.
-// ~98% of the (line, point) pairs are far-wing (region 1) and take the branch-free 10-FP64-op
-// path; pairs near the line centre take the general path (regions 2/3/4).
+// Kernels
+//   k_line_cell_params  one thread per (cell, line): everything that is per line, not per point
+//   k_core_eval         one warp per (cell, line): the ~250 centre points (divergent complex
+//                       rational code, exp, cos) into the core buffer
+//   k_voigt_tile        one CTA per (tile of TP grid points, cell): far-wing evaluation of every
+//                       line whose 13010-point window touches the tile (10 FP64 ops + 1 MUFU per
+//                       line*point), FP64 register accumulation per group, shared-memory tile of
+//                       all n_sets*3 output rows, plus the gather of the buffered centre values
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 #include <vector>
 #include "sr_common.h"
@@ -30,9 +35,9 @@ namespace {
 
 constexpr int N_WIN = SR_IMXSIG;       // 13010
 constexpr int HALF = SR_IMXSIG / 2;    // 6505: window index of the centre point (0-based)
-constexpr int THREADS = 256;
-constexpr int CHUNK = 128;             // lines staged per step
 constexpr int MAX_GROUPS = 1024;
+constexpr int CORE_STRIDE = 512;       // buffered non-region-1 points per (line, cell)
+constexpr int REC_CAP = 576;           // LineRec slots in shared memory (63 KB)
 constexpr double HPA_TO_ATM = 0.00098692326671601;  // spect_classes.py:40
 constexpr double T_REF = 296.0;                      // spect_classes.py:39
 
@@ -56,16 +61,17 @@ struct __align__(16) LineCell {
 };
 static_assert(sizeof(LineCell) == 128, "LineCell must be 128 bytes");
 
-struct __align__(16) Staged {
-    double A, B, C, c2;  // u(p) = A + B p + C p^2 for the fast region-1 path
-    double g1[3];        // gs * b4
-    int type;            // 0 skip, 1 fast region 1, 2 general
-    int grp;
-    int line;            // sorted line index
-    int j0_first;        // 0-based window index of tile point 0
+// Far-wing record in absolute grid coordinates: for grid point P (0-based index into the
+// spectral grid)  x = b{L,R} + P*xs,  u = x^2 + c1,  contribution g{0,1,2} * reg1_fast(u, c2).
+//   left wing  : Pwin_lo <= P <= PL_end        right wing : PR_beg <= P <= Pwin_hi
+//   centre (regions 2/3/4, from the core buffer): PL_end < P < PR_beg, core index P - PL_end - 1
+struct __align__(16) LineRec {
+    double xs, bL, bR, c1, c2, g0, g1, g2;   // g = gs * b4 (far wing)
+    double gs0, gs1, gs2;                     // G/fac (centre values from the core buffer)
+    int Pwin_lo, PL_end, PR_beg, Pwin_hi;
     int pad[2];
 };
-static_assert(sizeof(Staged) == 80, "Staged must be 80 bytes");
+static_assert(sizeof(LineRec) == 112, "LineRec must be 112 bytes");
 
 struct LineArrays {
     const double *freq, *a_coeff, *air, *tdep, *e_lower, *g_up, *g_lo, *evu, *evl;
@@ -106,6 +112,9 @@ struct ParamsArgs {
     const double* lin;   // window offsets [N_WIN]
     const double* pt;    // [n_cells][2]
     LineCell* rec;       // [n_cells][n_lines]
+    LineRec* lrec;       // [n_cells][n_lines]
+    int* il_min;         // [n_cells] min il over the lines of the cell (memset 0x7f before)
+    int* ir_max;         // [n_cells] max ir (memset 0 before)
     int* flags;          // [1] OR of all record flags
     int n_lines, n_cells;
     double mm;
@@ -173,7 +182,7 @@ __global__ void k_line_cell_params(ParamsArgs a) {
     int ir2 = ir;
     if (dR + ry >= 5.5) ir2 = ir - (int)max(srdev::f_nint((dR - ry - 5.5) / xs), 0LL);
     // geometry the tile kernel relies on (always true for a window centred on the line)
-    if (!(il2 <= ir && ir2 >= il && il2 >= il && ir2 <= ir && il2 < N_WIN && ir2 > 1))
+    if (!(il2 <= ir && ir2 >= il && il2 >= il && ir2 <= ir && il2 < N_WIN && ir2 > 1 && il <= ir))
         flags |= FLAG_GEOMETRY;
     il2 = min(max(il2, 1), N_WIN);
     ir2 = min(max(ir2, 1), N_WIN);
@@ -196,6 +205,30 @@ __global__ void k_line_cell_params(ParamsArgs a) {
     r.flags = flags;
     r.pad = 0;
     a.rec[(size_t)cell * a.n_lines + l] = r;
+    {
+        // absolute-index form: window index j0 = P - (ind - HALF)
+        const int w0 = a.L.ind[l] - HALF;
+        LineRec f;
+        f.xs = xs;
+        f.bL = fma(-(double)w0, xs, r.baseL1);
+        f.bR = fma(-(double)w0, xs, r.baseR1);
+        f.c1 = r.c1;
+        f.c2 = r.c2;
+        f.g0 = r.gs[0] * r.b4;
+        f.g1 = r.gs[1] * r.b4;
+        f.g2 = r.gs[2] * r.b4;
+        f.gs0 = r.gs[0];
+        f.gs1 = r.gs[1];
+        f.gs2 = r.gs[2];
+        f.pad[0] = f.pad[1] = 0;
+        f.Pwin_lo = w0;
+        f.Pwin_hi = w0 + N_WIN - 1;
+        f.PL_end = w0 + il - 2;   // last region-1-left point (== Pwin_lo - 1 when il == 1)
+        f.PR_beg = w0 + ir;       // first region-1-right point (== Pwin_hi + 1 when ir == N)
+        a.lrec[(size_t)cell * a.n_lines + l] = f;
+    }
+    atomicMin(a.il_min + cell, il);
+    atomicMax(a.ir_max + cell, ir);
     if (flags) atomicOr(a.flags, flags);
 }
 
@@ -235,11 +268,32 @@ __device__ __noinline__ double eval_window_point(const LineCell* __restrict__ rc
     return 0.0;  // never written by the Fortran (cannot happen for a centred window)
 }
 
+// Regions 2/3/4 of every (cell, line): one warp per line evaluates the window points il..ir
+// (everything that is not pure far wing, ~250 points at Titan pressures) into the core buffer,
+// so that the tile kernel never runs the divergent complex-rational code itself.
+__global__ void __launch_bounds__(256) k_core_eval(const LineCell* __restrict__ rec,
+                                                   const double* __restrict__ nu0,
+                                                   const double* __restrict__ gc,
+                                                   const double* __restrict__ lin, int n_lines,
+                                                   double* __restrict__ core) {
+    const int line = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int cell = blockIdx.y;
+    if (line >= n_lines) return;
+    const LineCell* rc = rec + (size_t)cell * n_lines + line;
+    const int il = rc->il, ir = rc->ir;
+    if (ir - il + 1 > CORE_STRIDE) return;   // wide centre: evaluated inline by the tile kernel
+    const double f = nu0[line], g = gc[line];
+    double* __restrict__ dst = core + ((size_t)cell * n_lines + line) * CORE_STRIDE;
+    for (int j1 = il + (threadIdx.x & 31); j1 <= ir; j1 += 32)
+        dst[j1 - il] = eval_window_point(rc, j1, f, g, lin);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1/K2 tile kernel
 // ---------------------------------------------------------------------------------------------
 struct TileArgs {
     const LineCell* rec;     // [n_cells][n_lines]
+    const LineRec* lrec;     // [n_cells][n_lines]
     const double* nu0;       // sorted line arrays
     const double* gc;
     const int* ind;
@@ -247,63 +301,170 @@ struct TileArgs {
     const int* grp_up;       // [n_groups]
     const int* grp_lo;
     const double* lin;       // [N_WIN]
+    const double* core;      // [n_cells][n_lines][CORE_STRIDE] K of the points il..ir
+    const int* il_min;       // [n_cells]
+    const int* ir_max;       // [n_cells]
     double* out;             // [n_cells][n_sets][3][n_grid]
     long n_grid;
     int n_lines, n_sets, n_groups;
 };
 
-template <int PPT>
-__global__ void __launch_bounds__(THREADS, 1) k_voigt_tile(TileArgs a) {
-    constexpr int TP = THREADS * PPT;
+// mbarrier / TMA bulk-copy helpers (sm_90+ PTX; SASS: SYNCS / UBLKCP)
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes,
+                                         unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Tile kernel.  One CTA owns TP = NT*PPT consecutive grid points of one cell.
+//   phase 0  per group (upper set, lower set): the lines whose window touches the tile (binary
+//            search on the sorted centre index) and the split
+//               edgeR | wingR | centre | wingL | edgeL
+//            wingR / wingL are GUARANTEED (from the cell-wide min il / max ir) to see the whole
+//            tile in one far wing of the line; edge lines are cut by their window end, centre
+//            lines by their own regions 2/3/4;
+//   phase 1  thread g issues the TMA bulk copy (cp.async.bulk + mbarrier) of group g's LineRec
+//            run into shared memory; the output tile is zeroed while the copies land;
+//   phase 2  far-wing evaluation: wing runs with a branch-free fixed-trip-count loop (two lines x
+//            PPT points = independent FP64 chains per thread), edge/centre runs with the same loop
+//            plus integer window predicates; FP64 register accumulation per group, flushed into
+//            the shared output tile when the group changes;
+//   phase 3  centre gather: buffered K of regions 2/3/4 (k_core_eval) added into the tile;
+//   phase 4  coalesced store of the n_sets*3 rows.
+template <int NT, int PPT>
+__global__ void __launch_bounds__(NT, 1) k_voigt_tile(TileArgs a) {
+    constexpr int TP = NT * PPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* acc_s = reinterpret_cast<double*>(smem_raw);                      // [n_sets*3][TP]
-    Staged* stage = reinterpret_cast<Staged*>(acc_s + (size_t)a.n_sets * 3 * TP);   // [2][CHUNK]
-    int* g_first = reinterpret_cast<int*>(stage + 2 * CHUNK);                 // [n_groups]
-    int* g_cum = g_first + a.n_groups;                                        // [n_groups+1]
+    double* acc_s = reinterpret_cast<double*>(smem_raw);                          // [n_sets*3][TP]
+    LineRec* recbuf = reinterpret_cast<LineRec*>(acc_s + (size_t)a.n_sets * 3 * TP);   // [REC_CAP]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(recbuf + REC_CAP);
+    int* g_rng = reinterpret_cast<int*>(mbar + 2);          // [n_groups][10] lo a b c d hi cs ce up lo
+    int* cum = g_rng + 10 * a.n_groups;                      // [n_groups+1] slot of group start
 
     const int tid = threadIdx.x;
     const int cell = blockIdx.y;
     const long tile0 = (long)blockIdx.x * TP;
     const LineCell* __restrict__ rec = a.rec + (size_t)cell * a.n_lines;
+    const LineRec* __restrict__ lrec = a.lrec + (size_t)cell * a.n_lines;
+    const double* __restrict__ core = a.core + (size_t)cell * a.n_lines * CORE_STRIDE;
 
-    for (int i = tid; i < a.n_sets * 3 * TP; i += THREADS) acc_s[i] = 0.0;
-
-    // lines of each group whose window [ind-HALF, ind+HALF-1] touches [tile0, tile0+TP-1]
-    const long ind_lo = tile0 - (HALF - 1), ind_hi = tile0 + TP - 1 + HALF;
-    for (int g = tid; g < a.n_groups; g += THREADS) {
-        int b = a.grp_begin[g], e = a.grp_begin[g + 1];
-        int lo = b, hi = e;
-        while (lo < hi) { int m = (lo + hi) >> 1; if (a.ind[m] < ind_lo) lo = m + 1; else hi = m; }
-        int first = lo;
-        hi = e;
-        while (lo < hi) { int m = (lo + hi) >> 1; if (a.ind[m] <= ind_hi) lo = m + 1; else hi = m; }
-        g_first[g] = first;
-        g_cum[g + 1] = lo - first;
+    // ---- phase 0: ranges --------------------------------------------------------------------
+    // Eight lower_bound searches per group over the sorted centre indices, run in lock step so
+    // that their (L2-latency-bound) probes overlap.
+    const int il_min = a.il_min[cell], ir_max = a.ir_max[cell];
+    long thr[8];
+    thr[0] = tile0 - (HALF - 1);                  // lo : window reaches the tile
+    thr[1] = tile0 + HALF + TP - N_WIN;           // a  : window end beyond the tile (wingR start)
+    thr[2] = tile0 + HALF - ir_max + 1;           // b  : wingR end  (tile start beyond every ir)
+    thr[3] = tile0 + HALF + TP - il_min + 1;      // c  : wingL start (tile end before every il)
+    thr[4] = tile0 + HALF + 1;                    // d  : wingL end  (window start before the tile)
+    thr[5] = tile0 + TP + HALF;                   // hi : window starts beyond the tile
+    thr[6] = thr[2];                              // centre values can reach the tile from here ...
+    thr[7] = thr[3];                              // ... to here
+    for (int g = tid; g < a.n_groups; g += NT) {
+        const int gb = a.grp_begin[g], ge = a.grp_begin[g + 1];
+        int lo8[8], hi8[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) { lo8[q] = gb; hi8[q] = ge; }
+        for (int span = ge - gb; span > 0; span >>= 1) {   // ceil(log2(n+1)) lock-step rounds
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (lo8[q] < hi8[q]) {
+                    const int m = (lo8[q] + hi8[q]) >> 1;
+                    if (__ldg(a.ind + m) < thr[q]) lo8[q] = m + 1; else hi8[q] = m;
+                }
+            }
+        }
+        const int lo = lo8[0], hi = max(lo8[5], lo);
+        int ra = min(max(lo8[1], lo), hi), rb = min(max(lo8[2], ra), hi);
+        int rc = min(max(lo8[3], rb), hi), rd = min(max(lo8[4], rc), hi);
+        if (il_min <= 1) { rc = hi; rd = hi; }
+        int* r = g_rng + 10 * g;
+        r[0] = lo; r[1] = ra; r[2] = rb; r[3] = rc; r[4] = rd; r[5] = hi;
+        r[6] = min(max(lo8[6], lo), hi);
+        r[7] = (il_min <= 1) ? hi : min(max(lo8[7], r[6]), hi);
+        r[8] = a.grp_up[g];
+        r[9] = a.grp_lo[g];
     }
+    if (tid == 0) mbar_init(mbar, NT);
     __syncthreads();
     if (tid == 0) {
         int run = 0;
-        g_cum[0] = 0;
-        for (int g = 0; g < a.n_groups; g++) { run += g_cum[g + 1]; g_cum[g + 1] = run; }
+        cum[0] = 0;
+        for (int g = 0; g < a.n_groups; g++) { run += g_rng[10 * g + 5] - g_rng[10 * g]; cum[g + 1] = run; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int n_tot = g_cum[a.n_groups];
-    const int n_chunks = (n_tot + CHUNK - 1) / CHUNK;
+    const int n_tot = cum[a.n_groups];
+    const int n_rounds = (n_tot + REC_CAP - 1) / REC_CAP;
 
-    double pd[PPT], acc0[PPT], acc1[PPT], acc2[PPT];
+    // ---- phase 1: TMA bulk copies of round r (every thread arrives exactly once per round) ----
+    auto issue_round = [&](int r) {
+        const int r0 = r * REC_CAP, r1 = min(n_tot, r0 + REC_CAP);
+        unsigned bytes = 0;
+        for (int g = tid; g < a.n_groups; g += NT) {
+            const int s0 = max(cum[g], r0), s1 = min(cum[g + 1], r1);
+            if (s1 > s0) bytes += (unsigned)(s1 - s0) * (unsigned)sizeof(LineRec);
+        }
+        if (bytes) mbar_arrive_expect_tx(mbar, bytes); else mbar_arrive(mbar);
+        for (int g = tid; g < a.n_groups; g += NT) {
+            const int s0 = max(cum[g], r0), s1 = min(cum[g + 1], r1);
+            if (s1 > s0)
+                bulk_g2s(recbuf + (s0 - r0), lrec + g_rng[10 * g] + (s0 - cum[g]),
+                         (unsigned)(s1 - s0) * (unsigned)sizeof(LineRec), mbar);
+        }
+    };
+    if (n_rounds > 0) issue_round(0);
+
+    for (int i = tid; i < a.n_sets * 3 * TP; i += NT) acc_s[i] = 0.0;
+
+    double Pd[PPT], acc0[PPT], acc1[PPT], acc2[PPT];
+    int Pi[PPT];
 #pragma unroll
     for (int k = 0; k < PPT; k++) {
-        pd[k] = (double)(tid + k * THREADS);
+        Pi[k] = (int)tile0 + tid + k * NT;
+        Pd[k] = (double)Pi[k];
         acc0[k] = acc1[k] = acc2[k] = 0.0;
     }
-    int cur_grp = -1;
+    int cur_g = -1;
+    __syncthreads();   // tile zeroed before the first flush
 
-    auto flush = [&](int grp) {
-        if (grp < 0) return;
-        const int up = a.grp_up[grp], lo = a.grp_lo[grp];
+    auto flush = [&](int g) {
+        if (g < 0) return;
+        const int up = g_rng[10 * g + 8], lo = g_rng[10 * g + 9];
 #pragma unroll
         for (int k = 0; k < PPT; k++) {
-            const int p = tid + k * THREADS;
+            const int p = tid + k * NT;
             acc_s[(up * 3 + 0) * TP + p] += acc0[k];
             acc_s[(up * 3 + 1) * TP + p] += acc1[k];
             acc_s[(lo * 3 + 2) * TP + p] += acc2[k];
@@ -311,92 +472,150 @@ __global__ void __launch_bounds__(THREADS, 1) k_voigt_tile(TileArgs a) {
         }
     };
 
-    // staging: slot n of the tile's line list -> Staged record (threads 0..CHUNK-1)
-    auto stage_slot = [&](int n, Staged& s) {
-        s.type = 0;
-        if (n >= n_tot) return;
-        int lo = 0, hi = a.n_groups;  // find g with g_cum[g] <= n < g_cum[g+1]
-        while (hi - lo > 1) { int m = (lo + hi) >> 1; if (g_cum[m] <= n) lo = m; else hi = m; }
-        const int g = lo;
-        const int line = g_first[g] + (n - g_cum[g]);
-        const LineCell* rc = rec + line;
-        const int j0_first = (int)(tile0 - ((long)a.ind[line] - HALF));
-        s.grp = g;
-        s.line = line;
-        s.j0_first = j0_first;
-        const double4 q0 = *reinterpret_cast<const double4*>(&rc->xs);       // xs c1 c2 b4
-        const int2 ilr = *reinterpret_cast<const int2*>(&rc->il);
-        const int j1_first = j0_first + 1, j1_last = j0_first + TP;
-        double base;
-        bool fast = false;
-        if (ilr.x > 1 && j1_first >= 1 && j1_last <= ilr.x - 1) { base = rc->baseL1; fast = true; }
-        else if (j1_first >= ilr.y + 1 && j1_last <= N_WIN) { base = rc->baseR1; fast = true; }
-        if (fast) {
-            const double xoff = fma((double)j0_first, q0.x, base);
-            s.A = fma(xoff, xoff, q0.y);
-            s.B = 2.0 * xoff * q0.x;
-            s.C = q0.x * q0.x;
-            s.c2 = q0.z;
-            s.g1[0] = rc->gs[0] * q0.w;
-            s.g1[1] = rc->gs[1] * q0.w;
-            s.g1[2] = rc->gs[2] * q0.w;
-            s.type = 1;
-        } else {
-            s.type = 2;
+    // whole tile in one wing of every line of the run: no predicates, two lines per iteration
+    auto wing_run = [&](const LineRec* __restrict__ fr, int n, bool right) {
+        int i = 0;
+        for (; i + 2 <= n; i += 2) {
+            const LineRec& f0 = fr[i];
+            const LineRec& f1 = fr[i + 1];
+            const double xs0 = f0.xs, xs1 = f1.xs;
+            const double bs0 = right ? f0.bR : f0.bL, bs1 = right ? f1.bR : f1.bL;
+            const double c10 = f0.c1, c20 = f0.c2, c11 = f1.c1, c21 = f1.c2;
+            const double a0 = f0.g0, a1 = f0.g1, a2 = f0.g2, b0 = f1.g0, b1 = f1.g1, b2 = f1.g2;
+#pragma unroll
+            for (int k = 0; k < PPT; k++) {
+                const double x0 = fma(Pd[k], xs0, bs0);
+                const double x1 = fma(Pd[k], xs1, bs1);
+                const double k0 = srdev::humliv_reg1_fast(fma(x0, x0, c10), c20);
+                const double k1 = srdev::humliv_reg1_fast(fma(x1, x1, c11), c21);
+                acc0[k] = fma(a0, k0, acc0[k]);
+                acc1[k] = fma(a1, k0, acc1[k]);
+                acc2[k] = fma(a2, k0, acc2[k]);
+                acc0[k] = fma(b0, k1, acc0[k]);
+                acc1[k] = fma(b1, k1, acc1[k]);
+                acc2[k] = fma(b2, k1, acc2[k]);
+            }
+        }
+        if (i < n) {
+            const LineRec& f0 = fr[i];
+            const double xs0 = f0.xs, bs0 = right ? f0.bR : f0.bL, c10 = f0.c1, c20 = f0.c2;
+            const double a0 = f0.g0, a1 = f0.g1, a2 = f0.g2;
+#pragma unroll
+            for (int k = 0; k < PPT; k++) {
+                const double x0 = fma(Pd[k], xs0, bs0);
+                const double k0 = srdev::humliv_reg1_fast(fma(x0, x0, c10), c20);
+                acc0[k] = fma(a0, k0, acc0[k]);
+                acc1[k] = fma(a1, k0, acc1[k]);
+                acc2[k] = fma(a2, k0, acc2[k]);
+            }
         }
     };
-
-    Staged pre;
-    if (tid < CHUNK) stage_slot(tid, pre);
-    for (int c = 0; c < n_chunks; c++) {
-        Staged* buf = stage + (c & 1) * CHUNK;
-        if (tid < CHUNK) buf[tid] = pre;
-        __syncthreads();
-        if (tid < CHUNK && c + 1 < n_chunks) stage_slot((c + 1) * CHUNK + tid, pre);
-        const int n_here = min(CHUNK, n_tot - c * CHUNK);
-        for (int i = 0; i < n_here; i++) {
-            const Staged& s = buf[i];
-            const int grp = s.grp;
-            if (grp != cur_grp) { flush(cur_grp); cur_grp = grp; }
-            if (s.type == 1) {
-                const double A = s.A, B = s.B, C = s.C, c2 = s.c2;
-                const double g0 = s.g1[0], g1 = s.g1[1], g2 = s.g1[2];
+    // lines cut by their window end or by their own centre: same math, per-point predicates
+    auto pred_run = [&](const LineRec* __restrict__ fr, int n) {
+        for (int i = 0; i < n; i++) {
+            const LineRec& f = fr[i];
+            const double xs = f.xs, bL = f.bL, bR = f.bR, c1 = f.c1, c2 = f.c2;
+            const double a0 = f.g0, a1 = f.g1, a2 = f.g2;
+            const int wlo = f.Pwin_lo, le = f.PL_end, rb = f.PR_beg, whi = f.Pwin_hi;
 #pragma unroll
-                for (int k = 0; k < PPT; k++) {
-                    const double u = fma(fma(C, pd[k], B), pd[k], A);
-                    const double kp = srdev::humliv_reg1_fast(u, c2);
-                    acc0[k] = fma(g0, kp, acc0[k]);
-                    acc1[k] = fma(g1, kp, acc1[k]);
-                    acc2[k] = fma(g2, kp, acc2[k]);
-                }
-            } else {
-                const int line = s.line;
-                const LineCell* rc = rec + line;
-                const double nu0 = a.nu0[line], gc = a.gc[line];
-                const double g0 = rc->gs[0], g1 = rc->gs[1], g2 = rc->gs[2];
-#pragma unroll
-                for (int k = 0; k < PPT; k++) {
-                    const int j1 = s.j0_first + tid + k * THREADS + 1;
-                    if (j1 >= 1 && j1 <= N_WIN) {
-                        const double v = eval_window_point(rc, j1, nu0, gc, a.lin);
-                        acc0[k] = fma(g0, v, acc0[k]);
-                        acc1[k] = fma(g1, v, acc1[k]);
-                        acc2[k] = fma(g2, v, acc2[k]);
-                    }
+            for (int k = 0; k < PPT; k++) {
+                const int P = Pi[k];
+                const bool inL = P >= wlo && P <= le, inR = P >= rb && P <= whi;
+                if (inL || inR) {
+                    const double x = fma(Pd[k], xs, inL ? bL : bR);
+                    const double kp = srdev::humliv_reg1_fast(fma(x, x, c1), c2);
+                    acc0[k] = fma(a0, kp, acc0[k]);
+                    acc1[k] = fma(a1, kp, acc1[k]);
+                    acc2[k] = fma(a2, kp, acc2[k]);
                 }
             }
         }
+    };
+    // K of regions 2/3/4 of one line at this thread's points (0 outside PL_end < P < PR_beg)
+    auto centre_load = [&](const LineRec& f, int line, double (&v)[PPT]) {
+        const int le = f.PL_end, rb = f.PR_beg;
+#pragma unroll
+        for (int k = 0; k < PPT; k++) {
+            const int P = Pi[k];
+            v[k] = 0.0;
+            if (P > le && P < rb) {
+                if (rb - le - 1 <= CORE_STRIDE)
+                    v[k] = __ldg(core + (size_t)line * CORE_STRIDE + (P - le - 1));
+                else
+                    v[k] = eval_window_point(rec + line, P - f.Pwin_lo + 1, a.nu0[line],
+                                             a.gc[line], a.lin);
+            }
+        }
+    };
+    auto centre_add = [&](const LineRec& f, const double (&v)[PPT]) {
+        const double s0 = f.gs0, s1 = f.gs1, s2 = f.gs2;
+#pragma unroll
+        for (int k = 0; k < PPT; k++) {
+            acc0[k] = fma(s0, v[k], acc0[k]);
+            acc1[k] = fma(s1, v[k], acc1[k]);
+            acc2[k] = fma(s2, v[k], acc2[k]);
+        }
+    };
+
+    // ---- phase 2: per group: centre prefetch, far-wing runs, centre accumulate -------------------
+    constexpr int NPRE = 4;
+    for (int r = 0; r < n_rounds; r++) {
+        mbar_wait(mbar, r & 1);
+        const int r0 = r * REC_CAP, r1 = min(n_tot, r0 + REC_CAP);
+        int g;
+        {
+            int lo = 0, hi = a.n_groups;   // first group with cum[g+1] > r0
+            while (hi - lo > 1) { int m = (lo + hi) >> 1; if (cum[m] <= r0) lo = m; else hi = m; }
+            g = lo;
+        }
+        for (; g < a.n_groups && cum[g] < r1; g++) {
+            const int* rr = g_rng + 10 * g;
+            if (rr[5] == rr[0]) continue;
+            if (g != cur_g) { flush(cur_g); cur_g = g; }
+            const int base = cum[g] - rr[0];   // slot = base + line
+            // centre values of this group's lines: issue the (L2) loads before the wing math
+            const int q0 = max(base + rr[6], r0), q1 = min(base + rr[7], r1);
+            const int n_c = max(q1 - q0, 0);
+            double v[NPRE][PPT];
+#pragma unroll
+            for (int q = 0; q < NPRE; q++)
+                if (q < n_c) centre_load(recbuf[q0 - r0 + q], q0 + q - base, v[q]);
+#pragma unroll
+            for (int part = 0; part < 5; part++) {
+                const int s0 = max(base + rr[part], r0), s1 = min(base + rr[part + 1], r1);
+                if (s1 <= s0) continue;
+                const LineRec* fr = recbuf + (s0 - r0);
+                if (part == 1) wing_run(fr, s1 - s0, true);
+                else if (part == 3) wing_run(fr, s1 - s0, false);
+                else pred_run(fr, s1 - s0);
+            }
+#pragma unroll
+            for (int q = 0; q < NPRE; q++)
+                if (q < n_c) centre_add(recbuf[q0 - r0 + q], v[q]);
+            for (int qb = NPRE; qb < n_c; qb += NPRE) {   // further batches: loads first, then adds
+#pragma unroll
+                for (int q = 0; q < NPRE; q++)
+                    if (qb + q < n_c) centre_load(recbuf[q0 - r0 + qb + q], q0 + qb + q - base, v[q]);
+#pragma unroll
+                for (int q = 0; q < NPRE; q++)
+                    if (qb + q < n_c) centre_add(recbuf[q0 - r0 + qb + q], v[q]);
+            }
+        }
+        if (r + 1 < n_rounds) {
+            __syncthreads();          // everyone is done reading recbuf
+            issue_round(r + 1);
+        }
     }
-    flush(cur_grp);
+    flush(cur_g);
     __syncthreads();
 
-    // write the tile: every output element exactly once, coalesced
+    // ---- phase 4: write the tile: every output element exactly once, coalesced -------------------
     const int n_rows = a.n_sets * 3;
     double* __restrict__ out = a.out + (size_t)cell * n_rows * a.n_grid;
     for (int row = 0; row < n_rows; row++) {
 #pragma unroll
         for (int k = 0; k < PPT; k++) {
-            const int p = tid + k * THREADS;
+            const int p = tid + k * NT;
             const long s = tile0 + p;
             if (s < a.n_grid) __stcs(out + (size_t)row * a.n_grid + s, acc_s[row * TP + p]);
         }
@@ -445,9 +664,10 @@ struct sr_lineset {
     double mm = 0.0;
     sr_consts c{};
     sr::DevBuf<double> grid, lin, freq, a_coeff, air, tdep, e_lower, g_up, g_lo, evu, evl, gc;
-    sr::DevBuf<int> ind, grp_begin, grp_up, grp_lo, flags;
+    sr::DevBuf<int> ind, grp_begin, grp_up, grp_lo, flags, il_min, ir_max;
     sr::DevBuf<LineCell> rec;
-    sr::DevBuf<double> pt, facs;
+    sr::DevBuf<LineRec> lrec;
+    sr::DevBuf<double> pt, facs, core;
     std::vector<int> order;    // sorted position -> input line
     std::vector<int> ind_in;   // input line -> centre index (-1 dropped)
     int max_cells_per_batch = 1;
@@ -455,27 +675,50 @@ struct sr_lineset {
 
 namespace {
 
-template <int PPT>
-size_t tile_smem(int n_sets, int n_groups) {
-    return (size_t)n_sets * 3 * THREADS * PPT * sizeof(double) + 2 * CHUNK * sizeof(Staged) +
-           (size_t)(2 * n_groups + 1) * sizeof(int) + 16;
+size_t tile_smem(int tp, int n_sets, int n_groups) {
+    return (size_t)n_sets * 3 * tp * sizeof(double) + REC_CAP * sizeof(LineRec) + 16 +
+           (size_t)(10 * n_groups + n_groups + 1) * sizeof(int) + 16;
 }
 
-int pick_ppt(int n_sets, int n_groups, size_t smem_max) {
-    if (tile_smem<4>(n_sets, n_groups) <= smem_max && n_sets <= 3) return 4;
-    if (tile_smem<2>(n_sets, n_groups) <= smem_max) return 2;
-    if (tile_smem<1>(n_sets, n_groups) <= smem_max) return 1;
-    return 0;
-}
-
-template <int PPT>
-int launch_tile(const TileArgs& ta, int n_cells, size_t smem, cudaStream_t st) {
-    SR_CUDA(cudaFuncSetAttribute(k_voigt_tile<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-    const int TP = THREADS * PPT;
+template <int NT, int PPT>
+int launch_tile(const TileArgs& ta, int n_cells, cudaStream_t st) {
+    const size_t smem = tile_smem(NT * PPT, ta.n_sets, ta.n_groups);
+    SR_CUDA(cudaFuncSetAttribute(k_voigt_tile<NT, PPT>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int TP = NT * PPT;
     dim3 grid((unsigned)((ta.n_grid + TP - 1) / TP), (unsigned)n_cells);
-    SR_LAUNCH(k_voigt_tile<PPT>, grid, THREADS, smem, st, ta);
+    SR_LAUNCH((k_voigt_tile<NT, PPT>), grid, NT, smem, st, ta);
     return SR_OK;
+}
+
+// tile configurations (threads, points per thread); SR_K1_CFG=<index> forces one (tuning aid)
+struct TileCfg { int nt, ppt; };
+constexpr TileCfg kTileCfgs[] = {{256, 4}, {256, 2}, {512, 1}, {256, 1}, {128, 4}, {128, 2}, {512, 2}};
+
+int pick_cfg(int n_sets, int n_groups, size_t smem_max) {
+    if (const char* e = getenv("SR_K1_CFG")) {
+        int i = atoi(e);
+        if (i >= 0 && i < (int)(sizeof(kTileCfgs) / sizeof(kTileCfgs[0])) &&
+            tile_smem(kTileCfgs[i].nt * kTileCfgs[i].ppt, n_sets, n_groups) <= smem_max)
+            return i;
+    }
+    if (tile_smem(1024, n_sets, n_groups) <= smem_max) return 6;
+    if (tile_smem(512, n_sets, n_groups) <= smem_max) return 1;
+    if (tile_smem(256, n_sets, n_groups) <= smem_max) return 3;
+    return -1;
+}
+
+int launch_cfg(int cfg, const TileArgs& ta, int n_cells, cudaStream_t st) {
+    switch (cfg) {
+        case 0: return launch_tile<256, 4>(ta, n_cells, st);
+        case 1: return launch_tile<256, 2>(ta, n_cells, st);
+        case 2: return launch_tile<512, 1>(ta, n_cells, st);
+        case 3: return launch_tile<256, 1>(ta, n_cells, st);
+        case 4: return launch_tile<128, 4>(ta, n_cells, st);
+        case 5: return launch_tile<128, 2>(ta, n_cells, st);
+        case 6: return launch_tile<512, 2>(ta, n_cells, st);
+    }
+    return sr::fail(SR_ERR_ARG, "bad tile configuration");
 }
 
 int flags_to_status(int f) {
@@ -537,8 +780,6 @@ int sr_lineset_create(const sr_lines* lines, const double* grid, long n_grid,
     const int n_act = (int)act.size();
     ls->n_act = n_act;
     cudaStream_t st = 0;
-    int rc = SR_OK;
-    auto guard = [&](int code) { if (code != SR_OK && rc == SR_OK) rc = code; return code; };
     auto body = [&]() -> int {
         SR_CUDA(ls->grid.upload(grid, (size_t)n_grid, st));
         SR_CUDA(ls->lin.upload(lin_grid, N_WIN, st));
@@ -561,7 +802,9 @@ int sr_lineset_create(const sr_lines* lines, const double* grid, long n_grid,
         // sort by (group, centre index, input position)
         std::vector<int> perm(n_act);
         std::iota(perm.begin(), perm.end(), 0);
-        auto key = [&](int i) { return (long long)lines->up_set[act[i]] * n_sets + lines->lo_set[act[i]]; };
+        auto key = [&](int i) {
+            return (long long)lines->up_set[act[i]] * n_sets + lines->lo_set[act[i]];
+        };
         std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) {
             long long kx = key(x), ky = key(y);
             if (kx != ky) return kx < ky;
@@ -593,20 +836,21 @@ int sr_lineset_create(const sr_lines* lines, const double* grid, long n_grid,
             SR_CUDA(cudaStreamSynchronize(st));  // tmp is reused
             return SR_OK;
         };
-        if (guard(up_sorted(lines->freq, ls->freq))) return rc;
-        if (guard(up_sorted(lines->a_coeff, ls->a_coeff))) return rc;
-        if (guard(up_sorted(lines->air_broad, ls->air))) return rc;
-        if (guard(up_sorted(lines->t_dep, ls->tdep))) return rc;
-        if (guard(up_sorted(lines->e_lower, ls->e_lower))) return rc;
-        if (guard(up_sorted(lines->g_up, ls->g_up))) return rc;
-        if (guard(up_sorted(lines->g_lo, ls->g_lo))) return rc;
-        if (guard(up_sorted(lines->e_vib_up, ls->evu))) return rc;
-        if (guard(up_sorted(lines->e_vib_lo, ls->evl))) return rc;
+        int rc;
+        if ((rc = up_sorted(lines->freq, ls->freq))) return rc;
+        if ((rc = up_sorted(lines->a_coeff, ls->a_coeff))) return rc;
+        if ((rc = up_sorted(lines->air_broad, ls->air))) return rc;
+        if ((rc = up_sorted(lines->t_dep, ls->tdep))) return rc;
+        if ((rc = up_sorted(lines->e_lower, ls->e_lower))) return rc;
+        if ((rc = up_sorted(lines->g_up, ls->g_up))) return rc;
+        if ((rc = up_sorted(lines->g_lo, ls->g_lo))) return rc;
+        if ((rc = up_sorted(lines->e_vib_up, ls->evu))) return rc;
+        if ((rc = up_sorted(lines->e_vib_lo, ls->evl))) return rc;
         SR_CUDA(ls->ind.upload(sind.data(), n_act, st));
         SR_CUDA(ls->grp_begin.upload(gb.data(), gb.size(), st));
         SR_CUDA(ls->grp_up.upload(gu.data(), gu.size(), st));
         SR_CUDA(ls->grp_lo.upload(gl.data(), gl.size(), st));
-        // gc in sorted order
+        // ind / gc in sorted order
         SR_LAUNCH(k_closest_grid, (n_act + 255) / 256, 256, 0, st, ls->grid.p, n_grid,
                   ls->freq.p, n_act, ls->ind.p, ls->gc.p);
         SR_CUDA(cudaStreamSynchronize(st));
@@ -614,9 +858,11 @@ int sr_lineset_create(const sr_lines* lines, const double* grid, long n_grid,
     };
     int code = body();
     if (code != SR_OK) { delete ls; return code; }
-    // cells per batch: keep the LineCell table under ~2 GiB
-    size_t per_cell = (size_t)std::max(n_act, 1) * sizeof(LineCell);
-    ls->max_cells_per_batch = (int)std::max<size_t>(1, std::min<size_t>(4096, ((size_t)2 << 30) / per_cell));
+    // cells per batch: keep the per-(line,cell) tables under ~6 GiB
+    size_t per_cell = (size_t)std::max(n_act, 1) *
+                      (sizeof(LineCell) + sizeof(LineRec) + CORE_STRIDE * sizeof(double));
+    ls->max_cells_per_batch =
+        (int)std::max<size_t>(1, std::min<size_t>(4096, ((size_t)6 << 30) / per_cell));
     *out = ls;
     return SR_OK;
 }
@@ -645,12 +891,20 @@ static int run_params(sr_lineset* ls, const double* pt_host, int n_cells, cudaSt
     SR_CUDA(cudaMemcpyAsync(ls->pt.p, pt_host, sizeof(double) * 2 * n_cells,
                             cudaMemcpyHostToDevice, st));
     SR_CUDA(ls->rec.ensure((size_t)n_cells * ls->n_act));
+    SR_CUDA(ls->lrec.ensure((size_t)n_cells * ls->n_act));
+    SR_CUDA(ls->il_min.ensure(n_cells));
+    SR_CUDA(ls->ir_max.ensure(n_cells));
+    SR_CUDA(cudaMemsetAsync(ls->il_min.p, 0x7f, sizeof(int) * n_cells, st));
+    SR_CUDA(cudaMemsetAsync(ls->ir_max.p, 0, sizeof(int) * n_cells, st));
     ParamsArgs pa;
     pa.L = {ls->freq.p, ls->a_coeff.p, ls->air.p, ls->tdep.p, ls->e_lower.p, ls->g_up.p,
             ls->g_lo.p, ls->evu.p, ls->evl.p, ls->gc.p, ls->ind.p};
     pa.lin = ls->lin.p;
     pa.pt = ls->pt.p;
     pa.rec = ls->rec.p;
+    pa.lrec = ls->lrec.p;
+    pa.il_min = ls->il_min.p;
+    pa.ir_max = ls->ir_max.p;
     pa.flags = ls->flags.p;
     pa.n_lines = ls->n_act;
     pa.n_cells = n_cells;
@@ -678,17 +932,24 @@ int sr_gcoeff_cells_dev(sr_lineset* ls, const double* pt_host, int n_cells, doub
     int dev = 0, smem_max = 0;
     SR_CUDA(cudaGetDevice(&dev));
     SR_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const int ppt = pick_ppt(ls->n_sets, ls->n_groups, (size_t)smem_max);
-    if (ppt == 0)
+    const int cfg = pick_cfg(ls->n_sets, ls->n_groups, (size_t)smem_max);
+    if (cfg < 0)
         return sr::fail(SR_ERR_LIMIT, "n_sets = %d needs more than %d bytes of shared memory",
                         ls->n_sets, smem_max);
     for (int c0 = 0; c0 < n_cells; c0 += ls->max_cells_per_batch) {
         const int nb = std::min(ls->max_cells_per_batch, n_cells - c0);
-        if (c0 > 0) SR_CUDA(cudaStreamSynchronize(st));  // rec/pt buffers are reused per batch
+        if (c0 > 0) SR_CUDA(cudaStreamSynchronize(st));  // per-batch tables are reused
         int code = run_params(ls, pt_host + 2 * c0, nb, st);
         if (code) return code;
+        SR_CUDA(ls->core.ensure((size_t)nb * ls->n_act * CORE_STRIDE));
+        {
+            dim3 cgrid((ls->n_act + 7) / 8, nb);
+            SR_LAUNCH(k_core_eval, cgrid, 256, 0, st, ls->rec.p, ls->freq.p, ls->gc.p, ls->lin.p,
+                      ls->n_act, ls->core.p);
+        }
         TileArgs ta;
         ta.rec = ls->rec.p;
+        ta.lrec = ls->lrec.p;
         ta.nu0 = ls->freq.p;
         ta.gc = ls->gc.p;
         ta.ind = ls->ind.p;
@@ -696,14 +957,15 @@ int sr_gcoeff_cells_dev(sr_lineset* ls, const double* pt_host, int n_cells, doub
         ta.grp_up = ls->grp_up.p;
         ta.grp_lo = ls->grp_lo.p;
         ta.lin = ls->lin.p;
+        ta.core = ls->core.p;
+        ta.il_min = ls->il_min.p;
+        ta.ir_max = ls->ir_max.p;
         ta.out = out_dev + (size_t)c0 * cell_elems;
         ta.n_grid = ls->n_grid;
         ta.n_lines = ls->n_act;
         ta.n_sets = ls->n_sets;
         ta.n_groups = ls->n_groups;
-        if (ppt == 4) code = launch_tile<4>(ta, nb, tile_smem<4>(ls->n_sets, ls->n_groups), st);
-        else if (ppt == 2) code = launch_tile<2>(ta, nb, tile_smem<2>(ls->n_sets, ls->n_groups), st);
-        else code = launch_tile<1>(ta, nb, tile_smem<1>(ls->n_sets, ls->n_groups), st);
+        code = launch_cfg(cfg, ta, nb, st);
         if (code) return code;
     }
     return SR_OK;
@@ -727,7 +989,8 @@ int sr_gcoeff_cells_host(sr_lineset* ls, const double* pt_host, int n_cells, dou
     if (!ls || !out_host) return sr::fail(SR_ERR_ARG, "sr_gcoeff_cells_host: bad argument");
     const size_t cell_elems = (size_t)ls->n_sets * 3 * ls->n_grid;
     // stream the result out in slabs of cells so the device buffer stays bounded (~4 GiB)
-    const int slab = (int)std::max<size_t>(1, std::min<size_t>(n_cells, ((size_t)4 << 30) / (cell_elems * sizeof(double))));
+    const int slab = (int)std::max<size_t>(
+        1, std::min<size_t>(n_cells, ((size_t)4 << 30) / (cell_elems * sizeof(double))));
     sr::DevBuf<double> buf;
     SR_CUDA(buf.alloc(cell_elems * slab));
     for (int c0 = 0; c0 < n_cells; c0 += slab) {
