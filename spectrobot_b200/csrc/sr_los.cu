@@ -36,6 +36,10 @@ struct GasDev {
     const int* cellmap;     // [nP][nT] -> cell index or -1
     const double* qtab;     // [119] TIPS Q(T) row
     const double* elev;     // [n_sets] level energies (cm-1)
+    const int* rowlist;     // [3][n_sets] sets whose (set, ctype) LUT row is non-zero somewhere, per
+                            // ctype (all-zero spectra are None in the reference and skipped,
+                            // smm:1674-1679, 2244-2249)
+    int n_rows[3];          // list lengths: sp_emission, ind_emission, absorption
     int nP, nT, n_sets, lte_unidentified;
     double iso_ratio;
 };
@@ -155,6 +159,20 @@ __global__ void k_step_weights(StepArgs a) {
     if (flags) atomicOr(a.flags, flags);
 }
 
+// which LUT rows (set, ctype) hold any non-zero value (over all cells and grid points)
+__global__ void k_row_nonzero(const float* __restrict__ g32, int n_cells, int n_sets, long n_grid,
+                              int* __restrict__ rowmask) {
+    const int r = blockIdx.y;                 // (cell, set, ctype) row
+    const int s = (r / 3) % n_sets, ct = r % 3;
+    const float* __restrict__ p = g32 + (size_t)r * n_grid;
+    bool nz = false;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_grid;
+         i += (long)gridDim.x * blockDim.x)
+        nz |= (p[i] != 0.0f);
+    if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(rowmask + s, 1 << ct);
+    (void)n_cells;
+}
+
 struct LosArgs {
     GasDev gas[MAX_GAS];
     int n_gas, n_los, n_steps_max, n_sets_max;
@@ -188,18 +206,24 @@ __device__ __forceinline__ void step_tau_j(const LosArgs& a, int l, int k, long 
             if (cl[c] < 0) continue;
             const float* __restrict__ base =
                 G.g32 + (size_t)cl[c] * G.n_sets * 3 * row + (size_t)(a.pt0 + p_first);
-#pragma unroll 4
-            for (int s = 0; s < G.n_sets; s++) {
-                const double w = __ldg(W + s * 4 + c);
-                const float* __restrict__ r0 = base + (size_t)(s * 3) * row;
+            // one branch-free loop per ctype over the non-zero rows (independent coalesced loads)
 #pragma unroll
-                for (int i = 0; i < PPT; i++) {
-                    if (!ok[i]) continue;
-                    const double e = (double)__ldg(r0 + i * 256);              // sp_emission
-                    const double b = (double)__ldg(r0 + row + i * 256);        // ind_emission
-                    const double ab = (double)__ldg(r0 + 2 * row + i * 256);   // absorption
-                    tau[i] = fma(w, ab - b, tau[i]);     // smm:2244-2247
-                    J[i] = fma(w, e, J[i]);              // smm:2248-2249
+            for (int ct = 0; ct < 3; ct++) {
+                const int* __restrict__ list = G.rowlist + ct * G.n_sets;
+                const int n = G.n_rows[ct];
+#pragma unroll 4
+                for (int j = 0; j < n; j++) {
+                    const int s = __ldg(list + j);
+                    double w = __ldg(W + s * 4 + c);
+                    if (ct == 1) w = -w;                 // abs_coeff -= G_ind*pop, smm:2246-2247
+                    const float* __restrict__ r0 = base + (size_t)(s * 3 + ct) * row;
+#pragma unroll
+                    for (int i = 0; i < PPT; i++) {
+                        if (!ok[i]) continue;
+                        const double v = (double)__ldg(r0 + i * 256);
+                        if (ct == 0) J[i] = fma(w, v, J[i]);        // smm:2248-2249
+                        else tau[i] = fma(w, v, tau[i]);            // smm:2244-2247
+                    }
                 }
             }
         }
@@ -216,9 +240,15 @@ __device__ __forceinline__ double layer_update(double I, double tau, double J, i
 }
 
 template <int PPT, bool MATERIALISE>
-__global__ void __launch_bounds__(256) k_los_fused(LosArgs a) {
-    const int l = blockIdx.y;
-    const long p_first = (long)blockIdx.x * (256 * PPT) + threadIdx.x;
+__global__ void __launch_bounds__(1024) k_los_fused(LosArgs a) {
+    // blockDim = (256, G): G consecutive LOS (the 3 LOS of a pixel are neighbours in the batch and
+    // cross nearly the same (P,T) cells) share one wavenumber tile, so that the LUT rows one of
+    // them pulls from L2 are L1 hits for the others.
+    // grid = (LOS groups, wavenumber tiles): all LOS of one wavenumber tile are scheduled next to
+    // each other, so the LUT rows of that tile are read from HBM once and then served by L2
+    const int l = blockIdx.x * blockDim.y + threadIdx.y;
+    if (l >= a.n_los) return;
+    const long p_first = (long)blockIdx.y * (256 * PPT) + threadIdx.x;
     bool ok[PPT];
     double I[PPT], tau[PPT], J[PPT];
 #pragma unroll
@@ -317,7 +347,9 @@ struct sr_lut {
     std::vector<double> pt, Ps, Ts;
     std::vector<int> cellmap;
     sr::DevBuf<double> dPs, dTs, dq, delev;
-    sr::DevBuf<int> dmap;
+    sr::DevBuf<int> dmap, drowmask, drowlist;
+    int n_rows[3] = {0, 0, 0};
+    sr::DevBuf<double> ws_rad, ws_i0;   // workspace of the host-buffer entry point
     // per-call scratch (owned by the first LUT of a call)
     sr::DevBuf<int> cells, nsteps, flags;
     sr::DevBuf<double> W, temp, pres, column, tvib;
@@ -354,6 +386,8 @@ GasDev gas_dev(const sr_lut* L) {
     g.cellmap = L->dmap.p;
     g.qtab = L->dq.p;
     g.elev = L->delev.p;
+    g.rowlist = L->drowlist.p;
+    for (int ct = 0; ct < 3; ct++) g.n_rows[ct] = L->n_rows[ct];
     g.nP = (int)L->Ps.size();
     g.nT = (int)L->Ts.size();
     g.n_sets = L->n_sets;
@@ -478,6 +512,22 @@ int sr_lut_create(const float* g32_dev, const double* pt_host, int n_cells, int 
         SR_CUDA(L->dmap.upload(L->cellmap.data(), L->cellmap.size()));
         SR_CUDA(L->dq.upload(q, TIPS_N));
         SR_CUDA(L->delev.upload(elev.data(), n_sets));
+        SR_CUDA(L->drowmask.alloc(n_sets));
+        SR_CUDA(cudaMemset(L->drowmask.p, 0, sizeof(int) * n_sets));
+        {
+            dim3 grid(8, (unsigned)(n_cells * n_sets * 3));
+            SR_LAUNCH(k_row_nonzero, grid, 256, 0, 0, g32_dev, n_cells, n_sets, n_grid,
+                      L->drowmask.p);
+        }
+        std::vector<int> mask(n_sets), list(3 * (size_t)n_sets, 0);
+        SR_CUDA(cudaMemcpy(mask.data(), L->drowmask.p, sizeof(int) * n_sets, cudaMemcpyDeviceToHost));
+        for (int ct = 0; ct < 3; ct++) {
+            int n = 0;
+            for (int s2 = 0; s2 < n_sets; s2++)
+                if (mask[s2] & (1 << ct)) list[(size_t)ct * n_sets + n++] = s2;
+            L->n_rows[ct] = n;
+        }
+        SR_CUDA(L->drowlist.upload(list.data(), list.size()));
         SR_CUDA(cudaDeviceSynchronize());
         return SR_OK;
     };
@@ -576,10 +626,19 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
     la.tau_out = tau_dev;
     la.src_out = src_dev;
     la.solo_absorption = solo;
-    constexpr int PPT = 2;
-    dim3 grid((unsigned)((n_pts + 256 * PPT - 1) / (256 * PPT)), steps->n_los);
-    if (tau_dev) SR_LAUNCH((k_los_fused<PPT, true>), grid, 256, 0, st, la);
-    else SR_LAUNCH((k_los_fused<PPT, false>), grid, 256, 0, st, la);
+    int G = 2, ppt = 4;   // measured on B200 (tools/tune.py fused)
+    if (const char* e = getenv("SR_LOS_G")) G = std::max(1, std::min(4, atoi(e)));     // tuning aids
+    if (const char* e = getenv("SR_LOS_PPT")) ppt = atoi(e);
+    dim3 block(256, G);
+#define SR_FUSED(PPT)                                                                          \
+    {                                                                                          \
+        dim3 grid((unsigned)((steps->n_los + G - 1) / G),                                      \
+                  (unsigned)((n_pts + 256 * PPT - 1) / (256 * PPT)));                          \
+        if (tau_dev) SR_LAUNCH((k_los_fused<PPT, true>), grid, block, 0, st, la);              \
+        else SR_LAUNCH((k_los_fused<PPT, false>), grid, block, 0, st, la);                     \
+    }
+    if (ppt == 1) SR_FUSED(1) else if (ppt == 4) SR_FUSED(4) else SR_FUSED(2)
+#undef SR_FUSED
     return SR_OK;
 }
 
@@ -606,15 +665,16 @@ int sr_los_rt_lut_host(sr_lut* const* luts, const sr_los_steps* steps, long pt0,
                        const double* i0_host, int solo_absorption, double* rad_host) {
     if (!rad_host || !steps) return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_host: bad argument");
     const size_t n = (size_t)steps->n_los * n_pts;
-    sr::DevBuf<double> rad, i0;
-    SR_CUDA(rad.alloc(n));
-    if (i0_host) SR_CUDA(i0.upload(i0_host, n));
-    int rc = los_launch(luts, steps, pt0, n_pts, i0_host ? i0.p : nullptr, solo_absorption, rad.p,
-                        nullptr, nullptr, 0);
+    if (!luts || !luts[0]) return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_host: missing LUT");
+    sr_lut* L0 = luts[0];
+    SR_CUDA(L0->ws_rad.ensure(n));      // grow-only workspace: no cudaMalloc/cudaFree per call
+    if (i0_host) SR_CUDA(L0->ws_i0.upload(i0_host, n));
+    int rc = los_launch(luts, steps, pt0, n_pts, i0_host ? L0->ws_i0.p : nullptr, solo_absorption,
+                        L0->ws_rad.p, nullptr, nullptr, 0);
     if (rc) return rc;
-    rc = check_lflags(luts[0], 0);
+    rc = check_lflags(L0, 0);
     if (rc) return rc;
-    SR_CUDA(cudaMemcpy(rad_host, rad.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    SR_CUDA(cudaMemcpy(rad_host, L0->ws_rad.p, n * sizeof(double), cudaMemcpyDeviceToHost));
     return SR_OK;
 }
 

@@ -58,5 +58,38 @@ def k3(n_los=8):
         ms = timed(lambda: engine.los_rt_layers(tau, src, nst, out=rad), 5)
         print("k3 cfg %s: %.3f ms -> %.1f GB/s" % (cfg, min(ms), (16 * sp + 8 * n_los * len(g)) / (min(ms) * 1e-3) / 1e9))
 
+def fused(n_los=int(os.environ.get("TUNE_NLOS", "12"))):
+    w0, w1 = 2850.0, 3450.0
+    g = S.spectral_grid(w0, w1); n_lev = 12
+    lines = S.line_table(3000, w0, w1, n_levels=n_lev)
+    atm = S.titan_atmosphere()
+    tg = np.repeat(np.linspace(400.0, 1000.0, n_los // 3), 3) + np.tile([-12.0, 0.0, 12.0], n_los // 3)
+    st = S.limb_los_steps(tg, [3] * n_los, [50.0] * n_los, atm, lines["level_energies"])
+    cells = S.rect_cells(st["pres"][st["pres"] > 1e-6].min() * 0.9, st["pres"].max() * 1.1, st["temp"].min(), st["temp"].max())
+    ls = engine.LineSet(lines, g, S.CH4_MM, n_lev)
+    g32 = ls.gcoeff_cells_f32(cells)
+    lut = engine.Lut(g32, cells, 6, 1, S.CH4_RATIO, level_energies=lines["level_energies"])
+    steps = engine.LosSteps(st["n_steps"], st["temp"], st["pres"], st["column"], st["tvib"])
+    sp = float(st["n_steps"].sum()) * len(g)
+    rad = torch.empty((n_los, len(g)), dtype=torch.float64, device="cuda")
+    ref = None
+    for G in ("1", "2", "3", "4"):
+        for ppt in ("1", "2", "4"):
+            os.environ["SR_LOS_G"] = G; os.environ["SR_LOS_PPT"] = ppt
+            ms = timed(lambda: engine.los_rt_lut([lut], steps, out=rad, check_status=False), 3)
+            if ref is None: ref = rad.clone()
+            print("fused G %s ppt %s: %.3f ms -> %.3e step-points/s (same %s)" % (G, ppt, min(ms), sp / (min(ms) * 1e-3), bool((rad == ref).all())))
+    import time
+    host = torch.empty((n_los, len(g)), dtype=torch.float64).pin_memory().numpy()
+    for _ in range(3):
+        t0 = time.perf_counter(); engine.los_rt_lut_host([lut], steps, out=host); t1 = time.perf_counter()
+        print("host call %d LOS: %.1f ms" % (n_los, 1e3 * (t1 - t0)))
+    pag = np.empty((n_los, len(g)))
+    t0 = time.perf_counter(); engine.los_rt_lut_host([lut], steps, out=pag); print("host call pageable out: %.1f ms" % (1e3 * (time.perf_counter() - t0)))
+
+
 if __name__ == "__main__":
-    k1(); k3()
+    what = sys.argv[1:] or ["k1", "k3", "fused"]
+    if "k1" in what: k1()
+    if "k3" in what: k3()
+    if "fused" in what: fused()
