@@ -1,0 +1,527 @@
+"""Minimal `spect_base_module` (sbm) for the hot path.
+
+The reference imports `spect_base_module as sbm` everywhere, but the module is NOT part of the
+reference tree, so nothing here can be checked against the original.  This file provides
+the surface the hot path needs, inferred from the call sites, with the
+semantics published in DESIGN.md section 6:
+
+  helpers      isclose, weight, rad, find_molec_metadata, extract_quanta_HITRAN, vibtemp_to_ratio,
+               hydro_P, read_inputs, check_free_space
+  atmosphere   AtmGrid, AtmProfile (1-D in altitude or 2-D latitude-band x altitude), Titan
+  molecules    Molec, IsoMolec, Level
+  geometry     Coords, LineOfSight (ray / spherical-shell intersections, radtran steps with
+               Curtis-Godson columns through the `curgods` drop-in, radtran_fast on the GPU),
+               VIMSPixel
+Geometry and step construction are host-side set-up; the per-point arithmetic of
+the LOS integral runs in libspectrobot.so.
+"""
+import copy
+import json
+import math as mt
+import os
+
+import numpy as np
+
+from . import curgods
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_MOLPARAM = None
+
+kb_hpa = 1.38065e-19      # spect_classes.py:34 (P in hPa, n in cm-3)
+c_R = 8.31446             # spect_classes.py:35
+c_G = 6.67408e-11         # spect_classes.py:36
+T_ref = 296.0
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------
+def isclose(a, b, rtol=1.e-9, atol=0.0):
+    """Scalar/array closeness (call sites spect_classes.py:933,1359; spect_main_module.py:1425)."""
+    return np.isclose(a, b, rtol=rtol, atol=atol)
+
+
+def weight(v, v1, v2, itype='lin'):
+    """(w1, w2) such that value(v) = w1*value(v1) + w2*value(v2) (spect_classes.py:1365)."""
+    if itype == 'lin':
+        return (v2 - v) / (v2 - v1), (v - v1) / (v2 - v1)
+    if itype == 'exp':
+        return weight(mt.log(v), mt.log(v1), mt.log(v2), 'lin')
+    raise ValueError('unknown interpolation type ' + str(itype))
+
+
+def rad(deg):
+    return deg * mt.pi / 180.0
+
+
+def _molparam():
+    global _MOLPARAM
+    if _MOLPARAM is None:
+        _MOLPARAM = json.load(open(os.path.join(_HERE, "data", "molparam.json")))
+    return _MOLPARAM
+
+
+def find_molec_metadata(mol, iso):
+    """HITRAN isotopologue metadata from molparam.txt: iso_MM, iso_ratio, Q296, gj, mol_name
+    (call sites spect_classes.py:179,233,270,301)."""
+    m = _molparam()[str(int(mol))]
+    e = m["isos"][int(iso) - 1]
+    return {'mol_name': m["name"], 'iso_name': str(e["code"]), 'iso_MM': e["iso_MM"],
+            'iso_ratio': e["iso_ratio"], 'Q296': e["Q296"], 'gj': e["gj"]}
+
+
+def extract_quanta_HITRAN(mol, iso, lev_string):
+    """(minimal_string, quanta, symmetry): the vibrational quanta part of a HITRAN global-quanta
+    string, without the symmetry label (spect_classes.py:346-351, 1251)."""
+    toks = str(lev_string).split()
+    quanta = []
+    sym = ''
+    for t in toks:
+        try:
+            quanta.append(int(t))
+        except ValueError:
+            sym = t
+            break
+    return ' '.join(str(q) for q in quanta), quanta, sym
+
+
+def vibtemp_to_ratio(energy, T_vib, T):
+    """Ratio of the non-LTE to the LTE population of a level (spect_classes.py:280-281)."""
+    from .spect_classes import c2
+    return np.exp(-c2 * energy * (1.0 / T_vib - 1.0 / T))
+
+
+def hydro_P(z_km, temp, MM, P0=1467.0, R_km=2575.0, M_kg=1.3452e23):
+    """Hydrostatic pressure profile (titanatm.py:32)."""
+    z = np.asarray(z_km, dtype=float)
+    g = c_G * M_kg / ((R_km + z) * 1e3) ** 2
+    H = c_R * np.asarray(temp, dtype=float) / (MM * 1e-3 * g) / 1e3
+    integ = np.concatenate([[0.0], np.cumsum(0.5 * (1 / H[1:] + 1 / H[:-1]) * np.diff(z))])
+    return P0 * np.exp(-integ)
+
+
+def read_inputs(nomefile, key_strings, n_lines=None, itype=None, defaults=None, verbose=False):
+    """Parser of the `[key]\\nvalue` input files (inputs_spect_robot_SAMPLE.in;
+    radtran_3D_ch4.py:45-49)."""
+    txt = [ln.rstrip('\n') for ln in open(nomefile)]
+    out = dict()
+    for i, key in enumerate(key_strings):
+        val = None
+        for j, ln in enumerate(txt):
+            if ln.strip() == '[' + key + ']' and j + 1 < len(txt):
+                val = txt[j + 1].strip()
+        if val is None and defaults is not None:
+            val = defaults.get(key) if isinstance(defaults, dict) else defaults[i]
+        if val is not None and itype is not None and itype[i] is not None and isinstance(val, str):
+            cast = itype[i]
+            val = (val.lower() in ('true', '1', 't')) if cast is bool else cast(val)
+        out[key] = val
+        if verbose:
+            print(key, val)
+    return out
+
+
+def check_free_space(path):
+    st = os.statvfs(path)
+    return st.f_bavail * st.f_frsize / 1.e9
+
+
+# ---------------------------------------------------------------------------------------------
+# atmosphere
+# ---------------------------------------------------------------------------------------------
+class AtmGrid(object):
+    def __init__(self, names, coords):
+        if isinstance(names, str):
+            names, coords = [names], [coords]
+        self.names = list(names)
+        self.coords = dict((n, np.asarray(c, dtype=float)) for n, c in zip(names, coords))
+        self.grid = [self.coords[n] for n in self.names]
+        self.n_dim = len(self.names)
+
+
+class AtmProfile(object):
+    """Profiles on an AtmGrid ('alt' or ('lat', 'alt')); lat coordinates are band EDGES for the
+    2-D case (box interpolation in latitude, linear / log-linear in altitude)."""
+
+    def __init__(self, grid, values, profname, interp):
+        self.grid = grid
+        self.names = []
+        self.interp = dict()
+        self.values = dict()
+        self.add_profile(values, profname, interp)
+
+    def add_profile(self, values, profname, interp='lin'):
+        self.names.append(profname)
+        self.values[profname] = np.asarray(values, dtype=float)
+        self.interp[profname] = interp if isinstance(interp, str) else interp[-1]
+        setattr(self, profname, self.values[profname])
+
+    def get(self, name):
+        return self.values[name]
+
+    def _band(self, lat):
+        if self.grid.n_dim == 1:
+            return None
+        edges = self.grid.coords['lat']
+        return int(np.clip(np.searchsorted(edges, lat, side='right') - 1, 0, len(edges) - 2))
+
+    def calc(self, point, profname=None):
+        lat, lon, alt = point.Spherical() if hasattr(point, 'Spherical') else point
+        names = [profname] if profname is not None else self.names
+        res = dict()
+        z = self.grid.coords['alt']
+        b = self._band(lat)
+        for n in names:
+            v = self.values[n] if b is None else self.values[n][b]
+            if self.interp[n] == 'exp':
+                res[n] = float(np.exp(np.interp(alt, z, np.log(v))))
+            elif self.interp[n] == 'box':
+                res[n] = float(v[int(np.clip(np.searchsorted(z, alt, side='right') - 1, 0, len(z) - 1))])
+            else:
+                res[n] = float(np.interp(alt, z, v))
+        return res[profname] if profname is not None else res
+
+    def profile_1d(self, name, lat=0.0):
+        b = self._band(lat)
+        return self.values[name] if b is None else self.values[name][b]
+
+
+def AtmProfZeros(grid, profname, interp):
+    shape = tuple(len(g) - (1 if n == 'lat' else 0) for n, g in zip(grid.names, grid.grid))
+    return AtmProfile(grid, np.zeros(shape), profname, interp)
+
+
+class Level(object):
+    def __init__(self, levstring, energy, degen=None, simmetry=None):
+        self.lev_string = levstring
+        self.energy = float(energy)
+        self.degen = degen
+        self.simmetry = simmetry or []
+        self.vibtemp = None
+        self.local_vibtemp = []
+
+    def minimal_level_string(self):
+        return extract_quanta_HITRAN(None, None, self.lev_string)[0]
+
+    def get_quanta(self):
+        m, q, s = extract_quanta_HITRAN(None, None, self.lev_string)
+        return q, s
+
+    def equiv(self, string):
+        return extract_quanta_HITRAN(None, None, string)[0] == self.minimal_level_string()
+
+    def add_vibtemp(self, profile):
+        self.vibtemp = profile
+
+    def add_local_vibtemp(self, temp):
+        self.local_vibtemp.append(temp)
+
+
+class IsoMolec(object):
+    def __init__(self, mol, iso, MM=None, ratio=None, LTE=True):
+        self.mol, self.iso = int(mol), int(iso)
+        md = find_molec_metadata(mol, iso)
+        self.MM = md['iso_MM'] if MM is None else MM
+        self.ratio = md['iso_ratio'] if ratio is None else ratio
+        self.mol_name = md['mol_name']
+        self.is_in_LTE = LTE
+        self.levels = []
+        self.n_lev = 0
+
+    def add_levels(self, lev_strings, energies, vibtemps=None, degeneracies=None, simmetries=None):
+        for i, (ls_, en) in enumerate(zip(lev_strings, energies)):
+            name = 'lev_{:02d}'.format(self.n_lev)
+            lev = Level(ls_, en)
+            if vibtemps is not None and vibtemps[i] is not None:
+                lev.add_vibtemp(vibtemps[i])
+                self.is_in_LTE = False
+            setattr(self, name, lev)
+            self.levels.append(name)
+            self.n_lev += 1
+
+    def has_level(self, lev_string):
+        for lev in self.levels:
+            if getattr(self, lev).equiv(lev_string):
+                return True, lev
+        return False, None
+
+    def erase_level(self, lev):
+        self.levels.remove(lev)
+        delattr(self, lev)
+
+    def level_energies(self):
+        return np.array([getattr(self, lev).energy for lev in self.levels])
+
+
+class Molec(object):
+    def __init__(self, mol, name, MM=None):
+        self.mol, self.name, self.MM = int(mol), name, MM
+        self.all_iso = []
+        self.iso_N = 0
+        self.abundance = None
+
+    def add_iso(self, num, MM=None, ratio=None, LTE=True):
+        nam = 'iso_{:1d}'.format(num)
+        setattr(self, nam, IsoMolec(self.mol, num, MM=MM, ratio=ratio, LTE=LTE))
+        self.all_iso.append(nam)
+        self.iso_N += 1
+        return getattr(self, nam)
+
+    def add_clim(self, profile):
+        self.abundance = profile
+
+    def link_to_atmos(self, atmosphere):
+        self.atmosphere = atmosphere
+
+
+class Planet(object):
+    def __init__(self, name, radius, atm_extension):
+        self.name, self.radius, self.atm_extension = name, float(radius), float(atm_extension)
+        self.gases = dict()
+        self.atmosphere = None
+
+    def add_atmosphere(self, atmosphere):
+        self.atmosphere = atmosphere
+
+    def add_gas(self, gas):
+        self.gases[gas.name] = gas
+        gas.link_to_atmos(self.atmosphere)
+
+
+class Titan(Planet):
+    def __init__(self, atm_extension=1500.0):
+        Planet.__init__(self, 'Titan', 2575.0, atm_extension)
+        self.mass = 1.3452e23
+
+
+# ---------------------------------------------------------------------------------------------
+# geometry
+# ---------------------------------------------------------------------------------------------
+class Coords(object):
+    """Point in planetocentric coordinates: 'Spherical' = (lat deg, lon deg, alt km above R) or
+    'Cartesian' = (x, y, z) km (spect_robot.py:24-27)."""
+
+    def __init__(self, vec, s_ref='Spherical', R=2575.0):
+        self.R = R
+        v = np.asarray(vec, dtype=float)
+        if s_ref == 'Spherical':
+            lat, lon, alt = v
+            r = R + alt
+            self.cart = np.array([r * mt.cos(rad(lat)) * mt.cos(rad(lon)),
+                                  r * mt.cos(rad(lat)) * mt.sin(rad(lon)), r * mt.sin(rad(lat))])
+        else:
+            self.cart = v.copy()
+
+    def Cartesian(self):
+        return self.cart.copy()
+
+    def Spherical(self):
+        x, y, z = self.cart
+        r = mt.sqrt(x * x + y * y + z * z)
+        return np.array([mt.degrees(mt.asin(z / r)), mt.degrees(mt.atan2(y, x)), r - self.R])
+
+    def distance(self, other):
+        return float(np.linalg.norm(self.cart - other.cart))
+
+
+class LineOfSight(object):
+    """Straight ray from `start` (observer) through `second_point`."""
+
+    def __init__(self, start, second_point, tag=None):
+        self.starting_point = start
+        self.second_point = second_point
+        d = second_point.Cartesian() - start.Cartesian()
+        self.direction = d / np.linalg.norm(d)
+        self.tag = tag
+        self.intersections = None
+        self.szas = None
+        self.radtran_steps = None
+        self.involved_retparams = dict()
+
+    def details(self):
+        print('LOS from {} towards {}'.format(self.starting_point.Spherical(),
+                                              self.second_point.Spherical()))
+
+    def _s_tangent(self):
+        return float(-np.dot(self.starting_point.Cartesian(), self.direction))
+
+    def get_tangent_point(self):
+        p = self.starting_point.Cartesian() + self._s_tangent() * self.direction
+        return Coords(p, s_ref='Cartesian', R=self.starting_point.R)
+
+    def get_tangent_altitude(self):
+        return float(self.get_tangent_point().Spherical()[2])
+
+    @property
+    def tangent_altitude(self):
+        return self.get_tangent_altitude()
+
+    def calc_atm_intersections(self, planet, delta_x=5.0, start_from_TOA=True,
+                               stop_at_second_point=False, LOS_order='radtran'):
+        """Points along the ray inside the atmosphere, every delta_x km.  LOS_order 'radtran':
+        from the far end towards the observer (order of the layer recursion); 'photon': same
+        ordering (photons travel towards the observer)."""
+        o = self.starting_point.Cartesian()
+        st = self._s_tangent()
+        rt = float(np.linalg.norm(o + st * self.direction))
+        r_top = planet.radius + planet.atm_extension
+        if rt >= r_top:
+            self.intersections = []
+            self._s = np.zeros(0)
+            return self.intersections
+        half = mt.sqrt(r_top ** 2 - rt ** 2)
+        s_near, s_far = st - half, st + half
+        if rt < planet.radius:                       # ray hits the surface: stop there
+            s_far = st - mt.sqrt(planet.radius ** 2 - rt ** 2)
+        # samples anchored on the tangent point, so that no two ADJACENT samples sit at the same
+        # altitude (curgod_fort_* divide by log(nd2/nd1), curgods.f:17)
+        kmax = int(mt.floor(half / delta_x - 1e-9))
+        inner = st + delta_x * np.arange(kmax, -kmax - 1, -1)
+        inner = inner[(inner < s_far - 1e-6) & (inner > s_near + 1e-6)]
+        s = np.concatenate([[s_far], inner, [s_near]])
+        self._s = s
+        self.intersections = [Coords(o + si * self.direction, s_ref='Cartesian', R=planet.radius)
+                              for si in s]
+        return self.intersections
+
+    def calc_SZA_along_los(self, planet, sub_solar_point):
+        sun = sub_solar_point.Cartesian()
+        sun = sun / np.linalg.norm(sun)
+        self.szas = np.array([mt.degrees(mt.acos(np.clip(np.dot(p.Cartesian(), sun) /
+                                                         np.linalg.norm(p.Cartesian()), -1, 1)))
+                              for p in self.intersections])
+        return self.szas
+
+    def calc_along_LOS(self, atmosphere, profname=None, set_attr=False, set_attr_name=None):
+        vals = np.array([atmosphere.calc(p, profname=profname) for p in self.intersections])
+        if set_attr:
+            setattr(self, set_attr_name or profname, vals)
+        return vals
+
+    def calc_radtran_steps(self, planet, lines=None, queue=None, calc_derivatives=False,
+                           bayes_set=None, max_T_variation=5.0, max_Plog_variation=1.0,
+                           max_opt_depth=None):
+        """Merge the intersection points into radtran steps: consecutive points are
+        merged while T varies by < max_T_variation and ln P by < max_Plog_variation; every step
+        gets air-weighted Curtis-Godson T and P (curgod_fort_1/4), the gas columns (curgod_fort_2)
+        and the column-weighted vibrational temperature of every level (curgod_fort_3)."""
+        pts = self.intersections
+        n = len(pts)
+        atm = planet.atmosphere
+        T = np.array([atm.calc(p, 'temp') for p in pts])
+        P = np.array([atm.calc(p, 'pres') for p in pts])
+        nd = P / (kb_hpa * T)
+        x = (self._s[0] - self._s) * 1.e5                       # path length from the far end, cm
+        lnP = np.log(P)
+        bounds, i0 = [], 0
+        for i in range(1, n):
+            seg = slice(i0, i + 1)
+            if (T[seg].max() - T[seg].min() > max_T_variation or
+                    lnP[seg].max() - lnP[seg].min() > max_Plog_variation) and i - i0 >= 2:
+                bounds.append((i0, i - 1))
+                i0 = i - 1
+        if n >= 2:
+            bounds.append((i0, n - 1))
+        steps = []
+        gas_isos = [(g, iso) for g in sorted(planet.gases) for iso in planet.gases[g].all_iso]
+        for a, e in bounds:
+            sl = slice(a, e + 1)
+            npnt = e - a + 1
+            ones = np.ones(npnt)
+            air = curgods.curgod_fort_1(nd[sl], x[sl], npnt)
+            st = {'range': (a, e), 'air_column': air,
+                  'temp': curgods.curgod_fort_4(nd[sl], ones, T[sl], x[sl], npnt) / air,
+                  'pres': curgods.curgod_fort_4(nd[sl], ones, P[sl], x[sl], npnt) / air,
+                  'columns': dict(), 'vibtemps': dict(),
+                  'sza': None if self.szas is None else float(np.mean(self.szas[sl]))}
+            for g in sorted(planet.gases):
+                gas = planet.gases[g]
+                vmr = np.array([gas.abundance.calc(p, 'vmr') for p in pts[a:e + 1]])
+                col = curgods.curgod_fort_2(nd[sl], vmr, x[sl], npnt)
+                st['columns'][g] = col
+                for iso in gas.all_iso:
+                    im = getattr(gas, iso)
+                    for lev in im.levels:
+                        L = getattr(im, lev)
+                        if L.vibtemp is None:
+                            tv = st['temp']
+                        else:
+                            tvp = np.array([L.vibtemp.calc(p, 'vibtemp') for p in pts[a:e + 1]])
+                            tv = curgods.curgod_fort_3(nd[sl], vmr, tvp, x[sl], npnt) / col
+                        st['vibtemps'][(g, iso, lev)] = tv
+            steps.append(st)
+        self.radtran_steps = {'step': steps, 'gas_isos': gas_isos,
+                              'opt': dict(max_T_variation=max_T_variation,
+                                          max_Plog_variation=max_Plog_variation)}
+        if queue is not None:
+            queue.put(self)
+        return self
+
+    def step_tables(self, planet, n_steps_max=None):
+        """Arrays for the C ABI (sr_los_steps) from self.radtran_steps, one gas-iso per LUT."""
+        steps = self.radtran_steps['step']
+        gi = self.radtran_steps['gas_isos']
+        ns = len(steps)
+        nmax = ns if n_steps_max is None else n_steps_max
+        n_lev = max([len(getattr(planet.gases[g], iso).levels) for g, iso in gi] + [1])
+        temp = np.full(nmax, 100.0)
+        pres = np.full(nmax, 1.e-6)
+        col = np.zeros((len(gi), nmax))
+        tvib = np.full((len(gi), n_lev, nmax), 100.0)
+        for k, st in enumerate(steps):
+            temp[k], pres[k] = st['temp'], st['pres']
+            for m, (g, iso) in enumerate(gi):
+                col[m, k] = st['columns'][g]
+                im = getattr(planet.gases[g], iso)
+                for j, lev in enumerate(im.levels):
+                    tvib[m, j, k] = st['vibtemps'][(g, iso, lev)]
+        return ns, temp, pres, col, tvib
+
+    def radtran_fast(self, sp_grid, planet, queue=None, cartLUTs=None, cartDROP=None,
+                     calc_derivatives=False, bayes_set=None, LUTS=None, radtran_opt=None,
+                     store_abscoeff=False, track_levels=None, solo_absorption=False,
+                     initial_intensity=None):
+        """Hi-res radiance of this LOS on sp_grid from device-resident LUTs (one-LOS batch through
+        the same C ABI entry point smm.radtrans uses for whole batches).  Returns
+        [SpectralIntensity, {}, bayes_set] like the reference (spect_main_module.py:3214-3228)."""
+        from . import spect_main_module as smm
+        rads = smm.los_batch_radiances([self], sp_grid, planet, LUTS,
+                                       solo_absorption=solo_absorption,
+                                       initial_intensity=initial_intensity)
+        out = [rads[0], dict(), copy.deepcopy(bayes_set)]
+        if calc_derivatives:
+            raise NotImplementedError('analytic Jacobians are a "next" row (SURVEY 8f #2)')
+        if queue is not None:
+            queue.put(out)
+        return out
+
+
+class VIMSPixel(object):
+    """Synthetic VIMS limb pixel: observer position + tangent geometry; three LOS per pixel
+    (low, centre, up: spect_main_module.py:3091-3096)."""
+
+    def __init__(self, keys, values):
+        for k, v in zip(keys, values):
+            setattr(self, k, v)
+        self.pixel_rot = getattr(self, 'pixel_rot', 0.0)
+        self.fov_km = getattr(self, 'fov_km', 24.0)       # full vertical extent of the pixel
+        self.observation = getattr(self, 'observation', None)
+
+    def Spacecraft(self):
+        return Coords([self.sub_obs_lat, self.sub_obs_lon, self.dist], s_ref='Spherical')
+
+    def _los_at(self, alt):
+        tg = Coords([self.limb_tg_lat, self.limb_tg_lon, alt], s_ref='Spherical')
+        return LineOfSight(self.Spacecraft(), tg)
+
+    def LOS(self):
+        return self._los_at(self.limb_tg_alt)
+
+    def low_LOS(self):
+        return self._los_at(self.limb_tg_alt - self.fov_km / 2.0)
+
+    def up_LOS(self):
+        return self._los_at(self.limb_tg_alt + self.fov_km / 2.0)
+
+    def sub_solar_point(self):
+        return Coords([self.sub_solar_lat, self.sub_solar_lon, 0.0], s_ref='Spherical')
