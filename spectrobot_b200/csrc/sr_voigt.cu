@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <numeric>
+#include <type_traits>
 #include <vector>
 #include "sr_common.h"
 #include "sr_device.cuh"
@@ -37,9 +38,6 @@ constexpr int N_WIN = SR_IMXSIG;       // 13010
 constexpr int HALF = SR_IMXSIG / 2;    // 6505: window index of the centre point (0-based)
 constexpr int MAX_GROUPS = 1024;
 constexpr int CORE_STRIDE = 512;       // buffered non-region-1 points per (line, cell)
-constexpr int REC_CAP = 256;           // LineRec slots in shared memory (28 KB)
-constexpr int GR = 12;                 // ints per group in the tile kernel's range table
-constexpr int MAX_CHUNKS = 8;
 constexpr double HPA_TO_ATM = 0.00098692326671601;  // spect_classes.py:40
 constexpr double T_REF = 296.0;                      // spect_classes.py:39
 
@@ -115,8 +113,6 @@ struct ParamsArgs {
     const double* pt;    // [n_cells][2]
     LineCell* rec;       // [n_cells][n_lines]
     LineRec* lrec;       // [n_cells][n_lines]
-    int* il_min;         // [n_cells] min il over the lines of the cell (memset 0x7f before)
-    int* ir_max;         // [n_cells] max ir (memset 0 before)
     int* flags;          // [1] OR of all record flags
     int n_lines, n_cells;
     double mm;
@@ -229,8 +225,6 @@ __global__ void k_line_cell_params(ParamsArgs a) {
         f.PR_beg = w0 + ir;       // first region-1-right point (== Pwin_hi + 1 when ir == N)
         a.lrec[(size_t)cell * a.n_lines + l] = f;
     }
-    atomicMin(a.il_min + cell, il);
-    atomicMax(a.ir_max + cell, ir);
     if (flags) atomicOr(a.flags, flags);
 }
 
@@ -291,275 +285,185 @@ __global__ void __launch_bounds__(256) k_core_eval(const LineCell* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1/K2 tile kernel
+// K1/K2 tile kernel (v5)
 // ---------------------------------------------------------------------------------------------
+// One far wing of one line restricted to nothing: for grid point P (absolute index)
+//   x = b + P*xs,  u = x^2 + c1,  contribution g{0,1,2} * reg1_fast(u, c2)  iff  lo <= P <= lo+len
+struct __align__(16) HalfRec {
+    double xs, b, c1, c2, g0, g1, g2;
+    int lo;
+    unsigned len;
+};
+static_assert(sizeof(HalfRec) == 64, "HalfRec must be 64 bytes");
+// Centre (regions 2/3/4) of one line: buffered K at core[line][P - le - 1] for le < P <= le + n
+struct __align__(16) CentreRec {
+    double gs0, gs1, gs2;
+    int le, n, line, pad;
+};
+static_assert(sizeof(CentreRec) == 48, "CentreRec must be 48 bytes");
+
 struct TileArgs {
     const LineCell* rec;     // [n_cells][n_lines]
     const LineRec* lrec;     // [n_cells][n_lines]
     const double* nu0;       // sorted line arrays
     const double* gc;
-    const int* ind;
-    const int* grp_begin;    // [n_groups+1] offsets into the sorted line arrays
-    const int* grp_up;       // [n_groups]
-    const int* grp_lo;
     const double* lin;       // [N_WIN]
     const double* core;      // [n_cells][n_lines][CORE_STRIDE] K of the points il..ir
-    const int* il_min;       // [n_cells]
-    const int* ir_max;       // [n_cells]
-    double* out;             // [n_cells][n_sets][3][n_grid]
+    const int* tile_rng;     // [n_tiles][n_groups][2] lines whose window touches the tile
+    const int* grp_upidx;    // [n_groups] index of the group's upper set in up_list
+    const int* grp_loslot;   // [n_groups] index of the group's lower set in lo_list
+    const int* up_list;      // [n_up] distinct upper sets, ascending (groups are sorted by them)
+    const int* lo_list;      // [n_lo] distinct lower sets
+    const int* zero_rows;    // [n_zero] rows (set*3+ctype) that no line feeds
+    void* out;               // [n_cells][n_sets][3][n_grid] double (or float when F32)
     long n_grid;
-    int n_lines, n_sets, n_groups;
-    // group chunks: a CTA handles one (tile, chunk of groups) and keeps only the output rows its
-    // groups feed in shared memory (compact row numbering per chunk)
-    const int* chunk_gbeg;   // [n_chunks+1] group ranges
-    const int* grp_slot;     // [n_groups][3] compact rows: sp, ind (upper set), abs (lower set)
-    const int* chunk_rows;   // [n_chunks][max_rows] global row (set*3+ctype) or -1
-    const int* chunk_shared; // [n_chunks][max_rows] 1 = row also fed by another chunk: atomic add
-    int n_chunks, max_rows;  //                          onto the pre-zeroed output row
+    int n_lines, n_sets, n_groups, n_up, n_lo, n_zero;
 };
 
-// mbarrier / TMA bulk-copy helpers (sm_90+ PTX; SASS: SYNCS / UBLKCP)
-__device__ __forceinline__ unsigned smem_u32(const void* p) {
-    return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes,
-                                         unsigned long long* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-            "r"(smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-
-// Tile kernel.  One CTA owns TP = NT*PPT consecutive grid points of one cell.
-//   phase 0  per group (upper set, lower set): the lines whose window touches the tile (binary
-//            search on the sorted centre index) and the split
-//               edgeR | wingR | centre | wingL | edgeL
-//            wingR / wingL are GUARANTEED (from the cell-wide min il / max ir) to see the whole
-//            tile in one far wing of the line; edge lines are cut by their window end, centre
-//            lines by their own regions 2/3/4;
-//   phase 1  thread g issues the TMA bulk copy (cp.async.bulk + mbarrier) of group g's LineRec
-//            run into shared memory; the output tile is zeroed while the copies land;
-//   phase 2  far-wing evaluation: wing runs with a branch-free fixed-trip-count loop (two lines x
-//            PPT points = independent FP64 chains per thread), edge/centre runs with the same loop
-//            plus integer window predicates; FP64 register accumulation per group, flushed into
-//            the shared output tile when the group changes;
-//   phase 3  centre gather: buffered K of regions 2/3/4 (k_core_eval) added into the tile;
-//   phase 4  coalesced store of the n_sets*3 rows.
-template <int NT, int PPT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
+// Tile kernel.  One CTA owns TP = NT*PPT consecutive grid points of one cell; thread t owns the
+// points tile0 + t + k*NT.  Lines are sorted by (upper set, lower set, centre index).
+//   prologue   the candidate line range of every group for this tile (precomputed once per line
+//              set: it depends only on the centre indices) -> flat candidate list;
+//   rounds     NT candidates per round: thread i loads candidate i's LineRec, keeps the far wings
+//              (left, right) and the centre that actually intersect the tile, and a block-wide
+//              scan compacts them into HalfRec / CentreRec lists in shared memory;
+//   compute    one flat loop over the half records of a group: 10 FP64 instructions + one
+//              MUFU.RCP64H per line*point, ONE unsigned compare as window predicate, three FP64
+//              register accumulators (sp_emission, ind_emission of the upper set; absorption of the
+//              lower set); buffered centre values are prefetched before the wing loop;
+//   rows       sp/ind accumulators live in registers until the upper set changes and are then
+//              written straight to global memory; absorption accumulators are parked in a
+//              thread-private shared-memory slot per lower set.  Every output element is written
+//              exactly once, by exactly one thread: no atomics, no zero-fill pass.
+template <int NT, int PPT, bool F32>
+__global__ void __launch_bounds__(NT, NT >= 256 ? 2 : 3) k_voigt_tile(TileArgs a) {
     constexpr int TP = NT * PPT;
-    const int chunk = blockIdx.y % a.n_chunks, cell = blockIdx.y / a.n_chunks;
-    const int gb0 = a.chunk_gbeg[chunk], n_grp = a.chunk_gbeg[chunk + 1] - gb0;
+    constexpr int NW = NT / 32;
+    const int cell = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tile0 = blockIdx.x * TP, tile_last = tile0 + TP - 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* acc_s = reinterpret_cast<double*>(smem_raw);                          // [max_rows][TP]
-    LineRec* recbuf = reinterpret_cast<LineRec*>(acc_s + (size_t)a.max_rows * TP);      // [REC_CAP]
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(recbuf + REC_CAP);
-    int* g_rng = reinterpret_cast<int*>(mbar + 2);   // [n_grp][GR] lo a b c d hi cs ce | 3 row slots
-    int* cum = g_rng + GR * n_grp;                   // [n_grp+1] slot of group start
+    double* abs_s = reinterpret_cast<double*>(smem_raw);                  // [n_lo][PPT][NT]
+    HalfRec* hbuf = reinterpret_cast<HalfRec*>(abs_s + (size_t)a.n_lo * TP);   // [2*NT]
+    CentreRec* cbuf = reinterpret_cast<CentreRec*>(hbuf + 2 * NT);             // [NT]
+    int* pre = reinterpret_cast<int*>(cbuf + NT);                              // [NT+1] h | c<<16
+    int* wsum = pre + NT + 1;                                                  // [NW]
+    int* cum = wsum + NW;                                                      // [n_groups+1]
+    int* glo = cum + a.n_groups + 1;                                           // [n_groups]
+    int* gup = glo + a.n_groups;                                               // [n_groups]
+    int* gsl = gup + a.n_groups;                                               // [n_groups]
 
-    const int tid = threadIdx.x;
-    const long tile0 = (long)blockIdx.x * TP;
     const LineCell* __restrict__ rec = a.rec + (size_t)cell * a.n_lines;
     const LineRec* __restrict__ lrec = a.lrec + (size_t)cell * a.n_lines;
     const double* __restrict__ core = a.core + (size_t)cell * a.n_lines * CORE_STRIDE;
 
-    // ---- phase 0: ranges --------------------------------------------------------------------
-    // Eight lower_bound searches per group over the sorted centre indices, run in lock step so
-    // that their (L2-latency-bound) probes overlap.
-    const int il_min = a.il_min[cell], ir_max = a.ir_max[cell];
-    long thr[8];
-    thr[0] = tile0 - (HALF - 1);                  // lo : window reaches the tile
-    thr[1] = tile0 + HALF + TP - N_WIN;           // a  : window end beyond the tile (wingR start)
-    thr[2] = tile0 + HALF - ir_max + 1;           // b  : wingR end  (tile start beyond every ir)
-    thr[3] = tile0 + HALF + TP - il_min + 1;      // c  : wingL start (tile end before every il)
-    thr[4] = tile0 + HALF + 1;                    // d  : wingL end  (window start before the tile)
-    thr[5] = tile0 + TP + HALF;                   // hi : window starts beyond the tile
-    thr[6] = thr[2];                              // centre values can reach the tile from here ...
-    thr[7] = thr[3];                              // ... to here
-    for (int g = tid; g < n_grp; g += NT) {
-        const int gb = a.grp_begin[gb0 + g], ge = a.grp_begin[gb0 + g + 1];
-        int lo8[8], hi8[8];
+    // ---- prologue: candidate ranges -> prefix sums (warp 0) ------------------------------------
+    {
+        const int* __restrict__ rng = a.tile_rng + (size_t)blockIdx.x * a.n_groups * 2;
+        for (int g = tid; g < a.n_groups; g += NT) {
+            const int2 r = __ldg(reinterpret_cast<const int2*>(rng) + g);
+            glo[g] = r.x;
+            cum[g + 1] = r.y - r.x;
+            gup[g] = __ldg(a.grp_upidx + g);
+            gsl[g] = __ldg(a.grp_loslot + g);
+        }
+        __syncthreads();
+        if (wid == 0) {
+            int carry = 0;
+            for (int g0 = 0; g0 < a.n_groups; g0 += 32) {
+                const int g = g0 + lane;
+                int v = g < a.n_groups ? cum[g + 1] : 0;
 #pragma unroll
-        for (int q = 0; q < 8; q++) { lo8[q] = gb; hi8[q] = ge; }
-        for (int span = ge - gb; span > 0; span >>= 1) {   // ceil(log2(n+1)) lock-step rounds
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                if (lo8[q] < hi8[q]) {
-                    const int m = (lo8[q] + hi8[q]) >> 1;
-                    if (__ldg(a.ind + m) < thr[q]) lo8[q] = m + 1; else hi8[q] = m;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, v, d);
+                    if (lane >= d) v += t;
                 }
+                if (g < a.n_groups) cum[g + 1] = carry + v;
+                carry += __shfl_sync(0xffffffffu, v, 31);
             }
+            if (lane == 0) cum[0] = 0;
         }
-        const int lo = lo8[0], hi = max(lo8[5], lo);
-        int ra = min(max(lo8[1], lo), hi), rb = min(max(lo8[2], ra), hi);
-        int rc = min(max(lo8[3], rb), hi), rd = min(max(lo8[4], rc), hi);
-        if (il_min <= 1) { rc = hi; rd = hi; }
-        int* r = g_rng + GR * g;
-        r[0] = lo; r[1] = ra; r[2] = rb; r[3] = rc; r[4] = rd; r[5] = hi;
-        r[6] = min(max(lo8[6], lo), hi);
-        r[7] = (il_min <= 1) ? hi : min(max(lo8[7], r[6]), hi);
-        r[8] = a.grp_slot[3 * (gb0 + g)];
-        r[9] = a.grp_slot[3 * (gb0 + g) + 1];
-        r[10] = a.grp_slot[3 * (gb0 + g) + 2];
+        for (int i = 0; i < a.n_lo * PPT; i++) abs_s[i * NT + tid] = 0.0;   // own slots only
+        __syncthreads();
     }
-    if (tid == 0) mbar_init(mbar, NT);
-    __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        cum[0] = 0;
-        for (int g = 0; g < n_grp; g++) { run += g_rng[GR * g + 5] - g_rng[GR * g]; cum[g + 1] = run; }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int n_tot = cum[n_grp];
-    const int n_rounds = (n_tot + REC_CAP - 1) / REC_CAP;
-
-    // ---- phase 1: TMA bulk copies of round r (every thread arrives exactly once per round) ----
-    auto issue_round = [&](int r) {
-        const int r0 = r * REC_CAP, r1 = min(n_tot, r0 + REC_CAP);
-        unsigned bytes = 0;
-        for (int g = tid; g < n_grp; g += NT) {
-            const int s0 = max(cum[g], r0), s1 = min(cum[g + 1], r1);
-            if (s1 > s0) bytes += (unsigned)(s1 - s0) * (unsigned)sizeof(LineRec);
-        }
-        if (bytes) mbar_arrive_expect_tx(mbar, bytes); else mbar_arrive(mbar);
-        for (int g = tid; g < n_grp; g += NT) {
-            const int s0 = max(cum[g], r0), s1 = min(cum[g + 1], r1);
-            if (s1 > s0)
-                bulk_g2s(recbuf + (s0 - r0), lrec + g_rng[GR * g] + (s0 - cum[g]),
-                         (unsigned)(s1 - s0) * (unsigned)sizeof(LineRec), mbar);
-        }
-    };
-    if (n_rounds > 0) issue_round(0);
-
-    for (int i = tid; i < a.max_rows * TP; i += NT) acc_s[i] = 0.0;
+    const int n_tot = cum[a.n_groups];
 
     double Pd[PPT], acc0[PPT], acc1[PPT], acc2[PPT];
-    int Pi[PPT];
 #pragma unroll
     for (int k = 0; k < PPT; k++) {
-        Pi[k] = (int)tile0 + tid + k * NT;
-        Pd[k] = (double)Pi[k];
+        Pd[k] = (double)(tile0 + tid + k * NT);
+        asm volatile("" : "+d"(Pd[k]));   // keep in registers (no I2F.F64 rematerialisation: XU pipe)
         acc0[k] = acc1[k] = acc2[k] = 0.0;
     }
-    int cur_g = -1;
-    __syncthreads();   // tile zeroed before the first flush
+    const int P0 = tile0 + tid;
+    int cur_g = -1, cur_up = -1, stored_up = 0;
+    const size_t rows_cell = (size_t)a.n_sets * 3;
 
-    auto flush = [&](int g) {
-        if (g < 0) return;
-        const int r0 = g_rng[GR * g + 8], r1 = g_rng[GR * g + 9], r2 = g_rng[GR * g + 10];
+    auto store_row = [&](int row, const double (&v)[PPT]) {
+        const size_t o = ((size_t)cell * rows_cell + row) * (size_t)a.n_grid + P0;
 #pragma unroll
         for (int k = 0; k < PPT; k++) {
-            const int p = tid + k * NT;
-            acc_s[r0 * TP + p] += acc0[k];
-            acc_s[r1 * TP + p] += acc1[k];
-            acc_s[r2 * TP + p] += acc2[k];
-            acc0[k] = acc1[k] = acc2[k] = 0.0;
-        }
-    };
-
-    // whole tile in one wing of every line of the run: no predicates, two lines per iteration
-    auto wing_run = [&](const LineRec* __restrict__ fr, int n, bool right) {
-        int i = 0;
-        for (; i + 2 <= n; i += 2) {
-            const LineRec& f0 = fr[i];
-            const LineRec& f1 = fr[i + 1];
-            const double xs0 = f0.xs, xs1 = f1.xs;
-            const double bs0 = right ? f0.bR : f0.bL, bs1 = right ? f1.bR : f1.bL;
-            const double c10 = f0.c1, c20 = f0.c2, c11 = f1.c1, c21 = f1.c2;
-            const double a0 = f0.g0, a1 = f0.g1, a2 = f0.g2, b0 = f1.g0, b1 = f1.g1, b2 = f1.g2;
-#pragma unroll
-            for (int k = 0; k < PPT; k++) {
-                const double x0 = fma(Pd[k], xs0, bs0);
-                const double x1 = fma(Pd[k], xs1, bs1);
-                const double k0 = srdev::humliv_reg1_fast(fma(x0, x0, c10), c20);
-                const double k1 = srdev::humliv_reg1_fast(fma(x1, x1, c11), c21);
-                acc0[k] = fma(a0, k0, acc0[k]);
-                acc1[k] = fma(a1, k0, acc1[k]);
-                acc2[k] = fma(a2, k0, acc2[k]);
-                acc0[k] = fma(b0, k1, acc0[k]);
-                acc1[k] = fma(b1, k1, acc1[k]);
-                acc2[k] = fma(b2, k1, acc2[k]);
-            }
-        }
-        if (i < n) {
-            const LineRec& f0 = fr[i];
-            const double xs0 = f0.xs, bs0 = right ? f0.bR : f0.bL, c10 = f0.c1, c20 = f0.c2;
-            const double a0 = f0.g0, a1 = f0.g1, a2 = f0.g2;
-#pragma unroll
-            for (int k = 0; k < PPT; k++) {
-                const double x0 = fma(Pd[k], xs0, bs0);
-                const double k0 = srdev::humliv_reg1_fast(fma(x0, x0, c10), c20);
-                acc0[k] = fma(a0, k0, acc0[k]);
-                acc1[k] = fma(a1, k0, acc1[k]);
-                acc2[k] = fma(a2, k0, acc2[k]);
+            if ((long)P0 + k * NT < a.n_grid) {
+                if (F32) __stcs(reinterpret_cast<float*>(a.out) + o + k * NT, (float)v[k]);
+                else __stcs(reinterpret_cast<double*>(a.out) + o + k * NT, v[k]);
             }
         }
     };
-    // lines cut by their window end or by their own centre: same math, per-point predicates
-    auto pred_run = [&](const LineRec* __restrict__ fr, int n) {
-        for (int i = 0; i < n; i++) {
-            const LineRec& f = fr[i];
-            const double xs = f.xs, bL = f.bL, bR = f.bR, c1 = f.c1, c2 = f.c2;
-            const double a0 = f.g0, a1 = f.g1, a2 = f.g2;
-            const int wlo = f.Pwin_lo, le = f.PL_end, rb = f.PR_beg, whi = f.Pwin_hi;
+    const double zero_v[PPT] = {};
+    // write sp/ind of upper-set index ui (and zero rows of the upper sets skipped since the last)
+    auto store_up = [&](int ui) {
+        for (; stored_up < ui; stored_up++) {
+            const int s = __ldg(a.up_list + stored_up);
+            store_row(s * 3 + 0, zero_v);
+            store_row(s * 3 + 1, zero_v);
+        }
+        const int s = __ldg(a.up_list + ui);
+        store_row(s * 3 + 0, acc0);
+        store_row(s * 3 + 1, acc1);
+        stored_up = ui + 1;
 #pragma unroll
-            for (int k = 0; k < PPT; k++) {
-                const int P = Pi[k];
-                const bool inL = P >= wlo && P <= le, inR = P >= rb && P <= whi;
-                if (inL || inR) {
-                    const double x = fma(Pd[k], xs, inL ? bL : bR);
-                    const double kp = srdev::humliv_reg1_fast(fma(x, x, c1), c2);
-                    acc0[k] = fma(a0, kp, acc0[k]);
-                    acc1[k] = fma(a1, kp, acc1[k]);
-                    acc2[k] = fma(a2, kp, acc2[k]);
+        for (int k = 0; k < PPT; k++) acc0[k] = acc1[k] = 0.0;
+    };
+    auto park_abs = [&](int slot) {
+#pragma unroll
+        for (int k = 0; k < PPT; k++) {
+            abs_s[(slot * PPT + k) * NT + tid] += acc2[k];
+            acc2[k] = 0.0;
+        }
+    };
+    // FULL: the whole tile lies inside this wing (no predicate at all)
+    auto half_eval = [&](const HalfRec& h, auto full) {
+        constexpr bool FULL = decltype(full)::value;
+        const double xs = h.xs, b = h.b, c1 = h.c1, c2 = h.c2, g0 = h.g0, g1 = h.g1, g2 = h.g2;
+        const int lo = h.lo;
+        const unsigned len = h.len;
+#pragma unroll
+        for (int k = 0; k < PPT; k++) {
+            const double x = fma(Pd[k], xs, b);
+            double kp = srdev::humliv_reg1_fast(fma(x, x, c1), c2);
+            if (!FULL) kp = ((unsigned)(P0 + k * NT - lo) <= len) ? kp : 0.0;   // one compare
+            acc0[k] = fma(g0, kp, acc0[k]);
+            acc1[k] = fma(g1, kp, acc1[k]);
+            acc2[k] = fma(g2, kp, acc2[k]);
+        }
+    };
+    auto centre_load = [&](const CentreRec& c, double (&v)[PPT]) {
+#pragma unroll
+        for (int k = 0; k < PPT; k++) {
+            const int d = P0 + k * NT - c.le - 1;
+            v[k] = 0.0;
+            if ((unsigned)d < (unsigned)c.n) {
+                if (c.n <= CORE_STRIDE) v[k] = __ldg(core + (size_t)c.line * CORE_STRIDE + d);
+                else {
+                    const int w0 = __ldg(&lrec[c.line].Pwin_lo);
+                    v[k] = eval_window_point(rec + c.line, P0 + k * NT - w0 + 1, a.nu0[c.line],
+                                             a.gc[c.line], a.lin);
                 }
             }
         }
     };
-    // K of regions 2/3/4 of one line at this thread's points (0 outside PL_end < P < PR_beg)
-    auto centre_load = [&](const LineRec& f, int line, double (&v)[PPT]) {
-        const int le = f.PL_end, rb = f.PR_beg;
-#pragma unroll
-        for (int k = 0; k < PPT; k++) {
-            const int P = Pi[k];
-            v[k] = 0.0;
-            if (P > le && P < rb) {
-                if (rb - le - 1 <= CORE_STRIDE)
-                    v[k] = __ldg(core + (size_t)line * CORE_STRIDE + (P - le - 1));
-                else
-                    v[k] = eval_window_point(rec + line, P - f.Pwin_lo + 1, a.nu0[line],
-                                             a.gc[line], a.lin);
-            }
-        }
-    };
-    auto centre_add = [&](const LineRec& f, const double (&v)[PPT]) {
-        const double s0 = f.gs0, s1 = f.gs1, s2 = f.gs2;
+    auto centre_add = [&](const CentreRec& c, const double (&v)[PPT]) {
+        const double s0 = c.gs0, s1 = c.gs1, s2 = c.gs2;
 #pragma unroll
         for (int k = 0; k < PPT; k++) {
             acc0[k] = fma(s0, v[k], acc0[k]);
@@ -568,88 +472,140 @@ __global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
         }
     };
 
-    // ---- phase 2: per group: centre prefetch, far-wing runs, centre accumulate -------------------
-    constexpr int NPRE = (PPT >= 4) ? 2 : 4;
-    for (int r = 0; r < n_rounds; r++) {
-        mbar_wait(mbar, r & 1);
-        const int r0 = r * REC_CAP, r1 = min(n_tot, r0 + REC_CAP);
-        int g;
+    int g_run = 0;   // first group that may still have candidates (uniform)
+    for (int r0 = 0; r0 < n_tot; r0 += NT) {
+        const int r1 = min(n_tot, r0 + NT);
+        // ---- loader: candidate r0+tid -> half / centre records ------------------------------
         {
-            int lo = 0, hi = n_grp;   // first group with cum[g+1] > r0
-            while (hi - lo > 1) { int m = (lo + hi) >> 1; if (cum[m] <= r0) lo = m; else hi = m; }
-            g = lo;
-        }
-        for (; g < n_grp && cum[g] < r1; g++) {
-            const int* rr = g_rng + GR * g;
-            if (rr[5] == rr[0]) continue;
-            if (g != cur_g) { flush(cur_g); cur_g = g; }
-            const int base = cum[g] - rr[0];   // slot = base + line
-            // centre values of this group's lines: issue the (L2) loads before the wing math
-            const int q0 = max(base + rr[6], r0), q1 = min(base + rr[7], r1);
-            const int n_c = max(q1 - q0, 0);
-            double v[NPRE][PPT];
+            const int f = r0 + tid;
+            int packed = 0, nL = 0, nR = 0, nC = 0, fL = 0, fR = 0, line = 0;
+            LineRec R;
+            if (f < r1) {
+                int lo = g_run, hi = a.n_groups;   // largest g with cum[g] <= f
+                while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (cum[m] <= f) lo = m; else hi = m; }
+                line = glo[lo] + (f - cum[lo]);
+                const int4* src = reinterpret_cast<const int4*>(lrec + line);
+                int4* dst = reinterpret_cast<int4*>(&R);
 #pragma unroll
-            for (int q = 0; q < NPRE; q++)
-                if (q < n_c) centre_load(recbuf[q0 - r0 + q], q0 + q - base, v[q]);
-#pragma unroll
-            for (int part = 0; part < 5; part++) {
-                const int s0 = max(base + rr[part], r0), s1 = min(base + rr[part + 1], r1);
-                if (s1 <= s0) continue;
-                const LineRec* fr = recbuf + (s0 - r0);
-                if (part == 1) wing_run(fr, s1 - s0, true);
-                else if (part == 3) wing_run(fr, s1 - s0, false);
-                else pred_run(fr, s1 - s0);
+                for (int q = 0; q < (int)(sizeof(LineRec) / 16); q++) dst[q] = __ldg(src + q);
+                nL = (R.PL_end >= R.Pwin_lo && R.Pwin_lo <= tile_last && R.PL_end >= tile0) ? 1 : 0;
+                nR = (R.Pwin_hi >= R.PR_beg && R.PR_beg <= tile_last && R.Pwin_hi >= tile0) ? 1 : 0;
+                nC = (R.PR_beg - R.PL_end > 1 && R.PL_end < tile_last && R.PR_beg > tile0) ? 1 : 0;
+                fL = nL && R.Pwin_lo <= tile0 && R.PL_end >= tile_last;
+                fR = nR && R.PR_beg <= tile0 && R.Pwin_hi >= tile_last;
+                // fields: full halves | partial halves << 11 | centres << 22
+                packed = (fL + fR) | ((nL + nR - fL - fR) << 11) | (nC << 22);
             }
+            int v = packed;
 #pragma unroll
-            for (int q = 0; q < NPRE; q++)
-                if (q < n_c) centre_add(recbuf[q0 - r0 + q], v[q]);
-            for (int qb = NPRE; qb < n_c; qb += NPRE) {   // further batches: loads first, then adds
-#pragma unroll
-                for (int q = 0; q < NPRE; q++)
-                    if (qb + q < n_c) centre_load(recbuf[q0 - r0 + qb + q], q0 + qb + q - base, v[q]);
-#pragma unroll
-                for (int q = 0; q < NPRE; q++)
-                    if (qb + q < n_c) centre_add(recbuf[q0 - r0 + qb + q], v[q]);
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v += t;
             }
+            if (lane == 31) wsum[wid] = v;
+            __syncthreads();   // also: every warp is done reading the previous round's records
+            int base = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) base += (w < wid) ? wsum[w] : 0;
+            const int ex = base + v - packed;
+            pre[tid] = ex;
+            if (tid == NT - 1) pre[NT] = ex + packed;
+            // full halves fill hbuf from the front, partial halves from the back
+            int pf = ex & 0x7ff, pp = 2 * NT - 1 - ((ex >> 11) & 0x7ff);
+            const int pc = ex >> 22;
+            if (nL) {
+                HalfRec h;
+                h.xs = R.xs; h.b = R.bL; h.c1 = R.c1; h.c2 = R.c2; h.g0 = R.g0; h.g1 = R.g1; h.g2 = R.g2;
+                h.lo = R.Pwin_lo; h.len = (unsigned)(R.PL_end - R.Pwin_lo);
+                if (fL) hbuf[pf++] = h; else hbuf[pp--] = h;
+            }
+            if (nR) {
+                HalfRec h;
+                h.xs = R.xs; h.b = R.bR; h.c1 = R.c1; h.c2 = R.c2; h.g0 = R.g0; h.g1 = R.g1; h.g2 = R.g2;
+                h.lo = R.PR_beg; h.len = (unsigned)(R.Pwin_hi - R.PR_beg);
+                if (fR) hbuf[pf] = h; else hbuf[pp] = h;
+            }
+            if (nC) {
+                CentreRec c;
+                c.gs0 = R.gs0; c.gs1 = R.gs1; c.gs2 = R.gs2;
+                c.le = R.PL_end; c.n = R.PR_beg - R.PL_end - 1; c.line = line; c.pad = 0;
+                cbuf[pc] = c;
+            }
+            __syncthreads();
         }
-        if (r + 1 < n_rounds) {
-            __syncthreads();          // everyone is done reading recbuf
-            issue_round(r + 1);
+        // ---- compute: the groups that have candidates in this round ---------------------------
+        while (cum[g_run + 1] <= r0) g_run++;
+        for (int g = g_run; g < a.n_groups && cum[g] < r1; g++) {
+            const int sa = max(cum[g], r0) - r0, sb = min(cum[g + 1], r1) - r0;
+            if (sb <= sa) continue;
+            if (g != cur_g) {
+                if (cur_g >= 0) {
+                    park_abs(gsl[cur_g]);
+                    if (gup[g] != cur_up) store_up(cur_up);
+                }
+                cur_g = g;
+                cur_up = gup[g];
+            }
+            const int pa = pre[sa], pb = pre[sb];
+            const int fa = pa & 0x7ff, fb = pb & 0x7ff;
+            const int qa = (pa >> 11) & 0x7ff, qb = (pb >> 11) & 0x7ff, ca = pa >> 22, cb = pb >> 22;
+            // buffered centre values: issue the (L2/HBM) loads before the wing math
+            double v[2][PPT];
+            const int n_c = cb - ca;
+            if (n_c > 0) centre_load(cbuf[ca], v[0]);
+            if (n_c > 1) centre_load(cbuf[ca + 1], v[1]);
+            int h = fa;
+            for (; h + 2 <= fb; h += 2) {
+                half_eval(hbuf[h], std::true_type{});
+                half_eval(hbuf[h + 1], std::true_type{});
+            }
+            if (h < fb) half_eval(hbuf[h], std::true_type{});
+            for (int q = qa; q < qb; q++) half_eval(hbuf[2 * NT - 1 - q], std::false_type{});
+            if (n_c > 0) centre_add(cbuf[ca], v[0]);
+            if (n_c > 1) centre_add(cbuf[ca + 1], v[1]);
+            for (int c = ca + 2; c < cb; c++) {
+                centre_load(cbuf[c], v[0]);
+                centre_add(cbuf[c], v[0]);
+            }
         }
     }
-    flush(cur_g);
-    __syncthreads();
-
-    // ---- phase 4: write the tile, coalesced.  Rows fed by this chunk only: plain store (every
-    // element written exactly once).  Rows shared with other chunks: FP64 atomic add onto the
-    // row zeroed by k_zero_rows.
-    double* __restrict__ out = a.out + (size_t)cell * a.n_sets * 3 * a.n_grid;
-    for (int slot = 0; slot < a.max_rows; slot++) {
-        const int row = a.chunk_rows[chunk * a.max_rows + slot];
-        if (row < 0) continue;
-        const bool shared = a.chunk_shared[chunk * a.max_rows + slot] != 0;
-#pragma unroll
-        for (int k = 0; k < PPT; k++) {
-            const int p = tid + k * NT;
-            const long s = tile0 + p;
-            if (s < a.n_grid) {
-                double* dst = out + (size_t)row * a.n_grid + s;
-                const double val = acc_s[slot * TP + p];
-                if (shared) atomicAdd(dst, val); else __stcs(dst, val);
-            }
-        }
+    // ---- epilogue: last group, remaining upper sets, absorption rows, empty rows -----------------
+    if (cur_g >= 0) {
+        park_abs(gsl[cur_g]);
+        store_up(cur_up);
     }
+    for (; stored_up < a.n_up; stored_up++) {
+        const int s = __ldg(a.up_list + stored_up);
+        store_row(s * 3 + 0, zero_v);
+        store_row(s * 3 + 1, zero_v);
+    }
+    for (int j = 0; j < a.n_lo; j++) {
+        double v[PPT];
+#pragma unroll
+        for (int k = 0; k < PPT; k++) v[k] = abs_s[(j * PPT + k) * NT + tid];
+        store_row(__ldg(a.lo_list + j) * 3 + 2, v);
+    }
+    for (int j = 0; j < a.n_zero; j++) store_row(__ldg(a.zero_rows + j), zero_v);
 }
 
-// zero the output rows that no chunk owns exclusively (shared rows and rows without any line)
-__global__ void k_zero_rows(double* __restrict__ out, const int* __restrict__ rows, int n_rows_z,
-                            int n_rows_cell, long n_grid) {
-    const int cell = blockIdx.z, row = rows[blockIdx.y];
-    double* dst = out + ((size_t)cell * n_rows_cell + row) * n_grid;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_grid;
-         i += (long)gridDim.x * blockDim.x)
-        dst[i] = 0.0;
-    (void)n_rows_z;
+// candidate line range of every (tile, group): lines whose 13010-point window touches the tile.
+// Depends only on the centre indices, so it is built once per line set (and tile size).
+__global__ void k_tile_ranges(const int* __restrict__ ind, const int* __restrict__ grp_begin,
+                              int n_groups, int n_tiles, int tp, int* __restrict__ rng) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tiles * n_groups) return;
+    const int t = i / n_groups, g = i % n_groups;
+    const long tile0 = (long)t * tp;
+    const long t_lo = tile0 - (HALF - 1);        // window reaches the tile: ind + HALF - 1 >= tile0
+    const long t_hi = tile0 + tp + HALF;         // window starts beyond the tile: ind - HALF >= tile0+tp
+    const int gb = grp_begin[g], ge = grp_begin[g + 1];
+    int lo = gb, hi = ge;
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (ind[m] < t_lo) lo = m + 1; else hi = m; }
+    const int first = lo;
+    hi = ge;
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (ind[m] < t_hi) lo = m + 1; else hi = m; }
+    rng[2 * i] = first;
+    rng[2 * i + 1] = lo;
 }
 
 // per-line shapes (MakeShapeLine keep_memory): one CTA per line, general evaluator
@@ -676,12 +632,6 @@ __global__ void k_line_fac(const double* __restrict__ nu0, int n_lines, double t
     facs[l] = dw * k.sqrt_pi_ln2;
 }
 
-__global__ void k_f64_to_f32(const double* __restrict__ in, float* __restrict__ out, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) out[i] = (float)in[i];   // numpy astype(float32): round-to-nearest
-}
-
 }  // namespace
 
 // =============================================================================================
@@ -694,12 +644,13 @@ struct sr_lineset {
     double mm = 0.0;
     sr_consts c{};
     sr::DevBuf<double> grid, lin, freq, a_coeff, air, tdep, e_lower, g_up, g_lo, evu, evl, gc;
-    sr::DevBuf<int> ind, grp_begin, grp_up, grp_lo, flags, il_min, ir_max;
+    sr::DevBuf<int> ind, grp_begin, grp_up, grp_lo, flags;
     sr::DevBuf<LineCell> rec;
     sr::DevBuf<LineRec> lrec;
     sr::DevBuf<double> pt, facs, core;
-    sr::DevBuf<int> chunk_gbeg, grp_slot, chunk_rows, chunk_shared, zero_rows;
-    int n_chunks = 1, max_rows = 1, max_grp = 1, n_zero_rows = 0;
+    sr::DevBuf<int> grp_upidx, grp_loslot, up_list, lo_list, zero_rows, tile_rng;
+    int n_up = 0, n_lo = 0, n_zero_rows = 0;
+    int cfg = 0, tile_nt = 256, tile_ppt = 4, n_tiles = 0;   // tile geometry of the range table
     std::vector<int> order;    // sorted position -> input line
     std::vector<int> ind_in;   // input line -> centre index (-1 dropped)
     int max_cells_per_batch = 1;
@@ -707,112 +658,54 @@ struct sr_lineset {
 
 namespace {
 
-size_t tile_smem(int tp, int max_rows, int max_grp) {
-    return (size_t)max_rows * tp * sizeof(double) + REC_CAP * sizeof(LineRec) + 16 +
-           (size_t)(GR * max_grp + max_grp + 1) * sizeof(int) + 16;
+size_t tile_smem(int nt, int ppt, int n_lo, int n_groups) {
+    return (size_t)n_lo * nt * ppt * sizeof(double) + (size_t)2 * nt * sizeof(HalfRec) +
+           (size_t)nt * sizeof(CentreRec) +
+           (size_t)(nt + 1 + nt / 32 + 4 * n_groups + 1) * sizeof(int) + 16;
 }
 
-template <int NT, int PPT, int MINB>
-int launch_tile(const TileArgs& ta, int n_cells, int max_grp, cudaStream_t st) {
-    const size_t smem = tile_smem(NT * PPT, ta.max_rows, max_grp);
-    SR_CUDA(cudaFuncSetAttribute(k_voigt_tile<NT, PPT, MINB>,
+template <int NT, int PPT, bool F32>
+int launch_tile(const TileArgs& ta, int n_cells, cudaStream_t st) {
+    const size_t smem = tile_smem(NT, PPT, ta.n_lo, ta.n_groups);
+    SR_CUDA(cudaFuncSetAttribute(k_voigt_tile<NT, PPT, F32>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int TP = NT * PPT;
-    dim3 grid((unsigned)((ta.n_grid + TP - 1) / TP), (unsigned)(n_cells * ta.n_chunks));
-    SR_LAUNCH((k_voigt_tile<NT, PPT, MINB>), grid, NT, smem, st, ta);
+    dim3 grid((unsigned)((ta.n_grid + TP - 1) / TP), (unsigned)n_cells);
+    SR_LAUNCH((k_voigt_tile<NT, PPT, F32>), grid, NT, smem, st, ta);
     return SR_OK;
 }
 
-// tile configurations (threads, points per thread, min CTAs per SM); SR_K1_CFG=<index> forces one
-struct TileCfg { int nt, ppt, minb; };
-constexpr TileCfg kTileCfgs[] = {{256, 4, 2}, {256, 2, 2}, {256, 4, 1}, {256, 2, 1}, {256, 1, 1},
-                                 {512, 2, 1}, {128, 4, 2}};
+// tile geometries (threads, points per thread): the first whose absorption rows fit in shared
+// memory twice per SM is used; SR_K1_CFG=<index> forces one (tuning aid)
+struct TileCfg { int nt, ppt; };
+constexpr TileCfg kTileCfgs[] = {{256, 4}, {256, 2}, {128, 2}, {256, 1}, {128, 4}};
 constexpr int kNumCfgs = (int)(sizeof(kTileCfgs) / sizeof(kTileCfgs[0]));
 
-bool cfg_fits(int i, int max_rows, int max_grp, size_t smem_max, size_t smem_sm) {
-    const size_t need = tile_smem(kTileCfgs[i].nt * kTileCfgs[i].ppt, max_rows, max_grp);
-    if (need > smem_max) return false;
-    return kTileCfgs[i].minb * (need + 1024) <= smem_sm;
-}
-
-int pick_cfg(int max_rows, int max_grp, size_t smem_max, size_t smem_sm) {
+int pick_cfg(int n_lo, int n_groups, size_t smem_max) {
     if (const char* e = getenv("SR_K1_CFG")) {
-        int i = atoi(e);
-        if (i >= 0 && i < kNumCfgs && cfg_fits(i, max_rows, max_grp, smem_max, smem_sm)) return i;
+        const int i = atoi(e);
+        if (i >= 0 && i < kNumCfgs &&
+            tile_smem(kTileCfgs[i].nt, kTileCfgs[i].ppt, n_lo, n_groups) <= smem_max)
+            return i;
     }
-    for (int i = 0; i < 5; i++)
-        if (cfg_fits(i, max_rows, max_grp, smem_max, smem_sm)) return i;
+    for (int i = 0; i < 4; i++)      // two CTAs per SM
+        if (2 * (tile_smem(kTileCfgs[i].nt, kTileCfgs[i].ppt, n_lo, n_groups) + 1024) <= (size_t)228 * 1024)
+            return i;
+    for (int i = 0; i < 4; i++)      // one CTA per SM
+        if (tile_smem(kTileCfgs[i].nt, kTileCfgs[i].ppt, n_lo, n_groups) <= smem_max) return i;
     return -1;
 }
 
-int launch_cfg(int cfg, const TileArgs& ta, int n_cells, int max_grp, cudaStream_t st) {
+template <bool F32>
+int launch_cfg(int cfg, const TileArgs& ta, int n_cells, cudaStream_t st) {
     switch (cfg) {
-        case 0: return launch_tile<256, 4, 2>(ta, n_cells, max_grp, st);
-        case 1: return launch_tile<256, 2, 2>(ta, n_cells, max_grp, st);
-        case 2: return launch_tile<256, 4, 1>(ta, n_cells, max_grp, st);
-        case 3: return launch_tile<256, 2, 1>(ta, n_cells, max_grp, st);
-        case 4: return launch_tile<256, 1, 1>(ta, n_cells, max_grp, st);
-        case 5: return launch_tile<512, 2, 1>(ta, n_cells, max_grp, st);
-        case 6: return launch_tile<128, 4, 2>(ta, n_cells, max_grp, st);
+        case 0: return launch_tile<256, 4, F32>(ta, n_cells, st);
+        case 1: return launch_tile<256, 2, F32>(ta, n_cells, st);
+        case 2: return launch_tile<128, 2, F32>(ta, n_cells, st);
+        case 3: return launch_tile<256, 1, F32>(ta, n_cells, st);
+        case 4: return launch_tile<128, 4, F32>(ta, n_cells, st);
     }
     return sr::fail(SR_ERR_ARG, "bad tile configuration");
-}
-
-// Partition the (sorted) groups into n_chunks contiguous chunks of similar line count and build
-// the compact row tables of every chunk.  Returns max rows per chunk.
-struct ChunkPlan {
-    int n_chunks = 1, max_rows = 0, max_grp = 0;
-    std::vector<int> gbeg, slot, rows, shared, zero_rows;
-};
-
-ChunkPlan plan_chunks(int n_chunks, int n_sets, const std::vector<int>& gb,
-                      const std::vector<int>& gu, const std::vector<int>& gl) {
-    ChunkPlan P;
-    const int n_groups = (int)gu.size();
-    n_chunks = std::max(1, std::min(n_chunks, std::max(n_groups, 1)));
-    P.n_chunks = n_chunks;
-    const int n_lines = n_groups ? gb[n_groups] : 0;
-    P.gbeg.assign(n_chunks + 1, n_groups);
-    P.gbeg[0] = 0;
-    {
-        int g = 0;
-        for (int c = 0; c < n_chunks; c++) {
-            P.gbeg[c] = g;
-            const long target = (long)n_lines * (c + 1) / n_chunks;
-            const int g_min = g + 1, g_max = n_groups - (n_chunks - 1 - c);
-            while (g < g_max && (g < g_min || gb[g + 1] <= target)) g++;
-        }
-        P.gbeg[n_chunks] = n_groups;
-    }
-    const int n_rows = n_sets * 3;
-    std::vector<std::vector<int>> rowlist(n_chunks);
-    std::vector<int> users(n_rows, 0);
-    P.slot.assign(3 * std::max(n_groups, 1), 0);
-    for (int c = 0; c < n_chunks; c++) {
-        std::vector<int> map(n_rows, -1);
-        auto get = [&](int row) {
-            if (map[row] < 0) { map[row] = (int)rowlist[c].size(); rowlist[c].push_back(row); users[row]++; }
-            return map[row];
-        };
-        for (int g = P.gbeg[c]; g < P.gbeg[c + 1]; g++) {
-            P.slot[3 * g + 0] = get(gu[g] * 3 + 0);
-            P.slot[3 * g + 1] = get(gu[g] * 3 + 1);
-            P.slot[3 * g + 2] = get(gl[g] * 3 + 2);
-        }
-        P.max_rows = std::max(P.max_rows, (int)rowlist[c].size());
-        P.max_grp = std::max(P.max_grp, P.gbeg[c + 1] - P.gbeg[c]);
-    }
-    P.max_rows = std::max(P.max_rows, 1);
-    P.rows.assign((size_t)n_chunks * P.max_rows, -1);
-    P.shared.assign((size_t)n_chunks * P.max_rows, 0);
-    for (int c = 0; c < n_chunks; c++)
-        for (size_t i = 0; i < rowlist[c].size(); i++) {
-            P.rows[(size_t)c * P.max_rows + i] = rowlist[c][i];
-            P.shared[(size_t)c * P.max_rows + i] = users[rowlist[c][i]] > 1;
-        }
-    for (int row = 0; row < n_rows; row++)
-        if (users[row] != 1) P.zero_rows.push_back(row);   // shared rows and rows without lines
-    return P;
 }
 
 int flags_to_status(int f) {
@@ -945,35 +838,52 @@ int sr_lineset_create(const sr_lines* lines, const double* grid, long n_grid,
         SR_CUDA(ls->grp_up.upload(gu.data(), gu.size(), st));
         SR_CUDA(ls->grp_lo.upload(gl.data(), gl.size(), st));
         {
-            // smallest chunk count whose tile (1024 points) fits twice per SM; else fewest rows
-            int want = 0;
-            if (const char* e = getenv("SR_K1_CHUNKS")) want = atoi(e);
-            ChunkPlan best;
-            bool have = false;
-            for (int c = 1; c <= MAX_CHUNKS; c++) {
-                if (want > 0 && c != want) continue;
-                ChunkPlan P = plan_chunks(c, n_sets, gb, gu, gl);
-                if (!have || P.max_rows < best.max_rows) { best = P; have = true; }
-                if (want > 0 || 2 * (tile_smem(1024, P.max_rows, P.max_grp) + 1024) <= (size_t)228 * 1024) {
-                    best = P;
-                    break;
-                }
-                if (P.n_chunks < c) break;
+            // distinct upper / lower sets (groups are sorted by upper set, then lower set) and the
+            // rows no line feeds
+            std::vector<int> up_list, lo_list, upidx(ls->n_groups), loslot(ls->n_groups), zrows;
+            std::vector<int> lo_of(n_sets, -1), up_seen(n_sets, 0);
+            for (int g = 0; g < ls->n_groups; g++) {
+                if (up_list.empty() || up_list.back() != gu[g]) up_list.push_back(gu[g]);
+                upidx[g] = (int)up_list.size() - 1;
+                up_seen[gu[g]] = 1;
+                if (lo_of[gl[g]] < 0) { lo_of[gl[g]] = (int)lo_list.size(); lo_list.push_back(gl[g]); }
+                loslot[g] = lo_of[gl[g]];
             }
-            ls->n_chunks = best.n_chunks;
-            ls->max_rows = best.max_rows;
-            ls->max_grp = best.max_grp;
-            ls->n_zero_rows = (int)best.zero_rows.size();
-            SR_CUDA(ls->chunk_gbeg.upload(best.gbeg.data(), best.gbeg.size(), st));
-            SR_CUDA(ls->grp_slot.upload(best.slot.data(), best.slot.size(), st));
-            SR_CUDA(ls->chunk_rows.upload(best.rows.data(), best.rows.size(), st));
-            SR_CUDA(ls->chunk_shared.upload(best.shared.data(), best.shared.size(), st));
-            if (ls->n_zero_rows) SR_CUDA(ls->zero_rows.upload(best.zero_rows.data(), best.zero_rows.size(), st));
+            for (int s2 = 0; s2 < n_sets; s2++) {
+                if (!up_seen[s2]) { zrows.push_back(s2 * 3 + 0); zrows.push_back(s2 * 3 + 1); }
+                if (lo_of[s2] < 0) zrows.push_back(s2 * 3 + 2);
+            }
+            ls->n_up = (int)up_list.size();
+            ls->n_lo = (int)lo_list.size();
+            ls->n_zero_rows = (int)zrows.size();
+            SR_CUDA(ls->grp_upidx.upload(upidx.data(), upidx.size(), st));
+            SR_CUDA(ls->grp_loslot.upload(loslot.data(), loslot.size(), st));
+            SR_CUDA(ls->up_list.upload(up_list.data(), up_list.size(), st));
+            SR_CUDA(ls->lo_list.upload(lo_list.data(), lo_list.size(), st));
+            if (ls->n_zero_rows) SR_CUDA(ls->zero_rows.upload(zrows.data(), zrows.size(), st));
             SR_CUDA(cudaStreamSynchronize(st));
         }
         // ind / gc in sorted order
         SR_LAUNCH(k_closest_grid, (n_act + 255) / 256, 256, 0, st, ls->grid.p, n_grid,
                   ls->freq.p, n_act, ls->ind.p, ls->gc.p);
+        // tile geometry + candidate line ranges per (tile, group)
+        int smem_max = 0;
+        SR_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin,
+                                       ls->device));
+        ls->cfg = pick_cfg(ls->n_lo, ls->n_groups, (size_t)smem_max);
+        if (ls->cfg < 0)
+            return sr::fail(SR_ERR_LIMIT, "%d lower levels x %d level pairs need more than %d bytes "
+                            "of shared memory per tile", ls->n_lo, ls->n_groups, smem_max);
+        ls->tile_nt = kTileCfgs[ls->cfg].nt;
+        ls->tile_ppt = kTileCfgs[ls->cfg].ppt;
+        const int tp = ls->tile_nt * ls->tile_ppt;
+        ls->n_tiles = (int)((n_grid + tp - 1) / tp);
+        SR_CUDA(ls->tile_rng.alloc((size_t)ls->n_tiles * ls->n_groups * 2));
+        {
+            const int n = ls->n_tiles * ls->n_groups;
+            SR_LAUNCH(k_tile_ranges, (n + 255) / 256, 256, 0, st, ls->ind.p, ls->grp_begin.p,
+                      ls->n_groups, ls->n_tiles, tp, ls->tile_rng.p);
+        }
         SR_CUDA(cudaStreamSynchronize(st));
         return SR_OK;
     };
@@ -1013,10 +923,6 @@ static int run_params(sr_lineset* ls, const double* pt_host, int n_cells, cudaSt
                             cudaMemcpyHostToDevice, st));
     SR_CUDA(ls->rec.ensure((size_t)n_cells * ls->n_act));
     SR_CUDA(ls->lrec.ensure((size_t)n_cells * ls->n_act));
-    SR_CUDA(ls->il_min.ensure(n_cells));
-    SR_CUDA(ls->ir_max.ensure(n_cells));
-    SR_CUDA(cudaMemsetAsync(ls->il_min.p, 0x7f, sizeof(int) * n_cells, st));
-    SR_CUDA(cudaMemsetAsync(ls->ir_max.p, 0, sizeof(int) * n_cells, st));
     ParamsArgs pa;
     pa.L = {ls->freq.p, ls->a_coeff.p, ls->air.p, ls->tdep.p, ls->e_lower.p, ls->g_up.p,
             ls->g_lo.p, ls->evu.p, ls->evl.p, ls->gc.p, ls->ind.p};
@@ -1024,8 +930,6 @@ static int run_params(sr_lineset* ls, const double* pt_host, int n_cells, cudaSt
     pa.pt = ls->pt.p;
     pa.rec = ls->rec.p;
     pa.lrec = ls->lrec.p;
-    pa.il_min = ls->il_min.p;
-    pa.ir_max = ls->ir_max.p;
     pa.flags = ls->flags.p;
     pa.n_lines = ls->n_act;
     pa.n_cells = n_cells;
@@ -1036,28 +940,18 @@ static int run_params(sr_lineset* ls, const double* pt_host, int n_cells, cudaSt
     return SR_OK;
 }
 
-int sr_gcoeff_cells_dev(sr_lineset* ls, const double* pt_host, int n_cells, double* out_dev,
-                        void* stream) {
-    if (!ls || !pt_host || n_cells < 0 || !out_dev)
-        return sr::fail(SR_ERR_ARG, "sr_gcoeff_cells_dev: bad argument");
-    cudaStream_t st = (cudaStream_t)stream;
+static int gcoeff_cells_impl(sr_lineset* ls, const double* pt_host, int n_cells, void* out_dev,
+                             bool f32, cudaStream_t st) {
     for (int i = 0; i < n_cells; i++)
         if (!(pt_host[2 * i] >= 0.0) || !(pt_host[2 * i + 1] > 0.0))
             return sr::fail(SR_ERR_ARG, "cell %d: P=%g hPa T=%g K", i, pt_host[2 * i],
                             pt_host[2 * i + 1]);
     const size_t cell_elems = (size_t)ls->n_sets * 3 * ls->n_grid;
+    const size_t esz = f32 ? sizeof(float) : sizeof(double);
     if (ls->n_act == 0) {
-        SR_CUDA(cudaMemsetAsync(out_dev, 0, cell_elems * n_cells * sizeof(double), st));
+        SR_CUDA(cudaMemsetAsync(out_dev, 0, cell_elems * n_cells * esz, st));
         return SR_OK;
     }
-    int dev = 0, smem_max = 0, smem_sm = 0;
-    SR_CUDA(cudaGetDevice(&dev));
-    SR_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    SR_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-    const int cfg = pick_cfg(ls->max_rows, ls->max_grp, (size_t)smem_max, (size_t)smem_sm);
-    if (cfg < 0)
-        return sr::fail(SR_ERR_LIMIT, "%d output rows per chunk need more than %d bytes of shared "
-                        "memory", ls->max_rows, smem_max);
     for (int c0 = 0; c0 < n_cells; c0 += ls->max_cells_per_batch) {
         const int nb = std::min(ls->max_cells_per_batch, n_cells - c0);
         if (c0 > 0) SR_CUDA(cudaStreamSynchronize(st));  // per-batch tables are reused
@@ -1074,34 +968,33 @@ int sr_gcoeff_cells_dev(sr_lineset* ls, const double* pt_host, int n_cells, doub
         ta.lrec = ls->lrec.p;
         ta.nu0 = ls->freq.p;
         ta.gc = ls->gc.p;
-        ta.ind = ls->ind.p;
-        ta.grp_begin = ls->grp_begin.p;
-        ta.grp_up = ls->grp_up.p;
-        ta.grp_lo = ls->grp_lo.p;
         ta.lin = ls->lin.p;
         ta.core = ls->core.p;
-        ta.il_min = ls->il_min.p;
-        ta.ir_max = ls->ir_max.p;
-        ta.out = out_dev + (size_t)c0 * cell_elems;
+        ta.tile_rng = ls->tile_rng.p;
+        ta.grp_upidx = ls->grp_upidx.p;
+        ta.grp_loslot = ls->grp_loslot.p;
+        ta.up_list = ls->up_list.p;
+        ta.lo_list = ls->lo_list.p;
+        ta.zero_rows = ls->zero_rows.p;
+        ta.out = (char*)out_dev + (size_t)c0 * cell_elems * esz;
         ta.n_grid = ls->n_grid;
         ta.n_lines = ls->n_act;
         ta.n_sets = ls->n_sets;
         ta.n_groups = ls->n_groups;
-        ta.chunk_gbeg = ls->chunk_gbeg.p;
-        ta.grp_slot = ls->grp_slot.p;
-        ta.chunk_rows = ls->chunk_rows.p;
-        ta.chunk_shared = ls->chunk_shared.p;
-        ta.n_chunks = ls->n_chunks;
-        ta.max_rows = ls->max_rows;
-        if (ls->n_zero_rows) {
-            dim3 zgrid(148, ls->n_zero_rows, nb);
-            SR_LAUNCH(k_zero_rows, zgrid, 256, 0, st, ta.out, ls->zero_rows.p, ls->n_zero_rows,
-                      ls->n_sets * 3, ls->n_grid);
-        }
-        code = launch_cfg(cfg, ta, nb, ls->max_grp, st);
+        ta.n_up = ls->n_up;
+        ta.n_lo = ls->n_lo;
+        ta.n_zero = ls->n_zero_rows;
+        code = f32 ? launch_cfg<true>(ls->cfg, ta, nb, st) : launch_cfg<false>(ls->cfg, ta, nb, st);
         if (code) return code;
     }
     return SR_OK;
+}
+
+int sr_gcoeff_cells_dev(sr_lineset* ls, const double* pt_host, int n_cells, double* out_dev,
+                        void* stream) {
+    if (!ls || !pt_host || n_cells < 0 || !out_dev)
+        return sr::fail(SR_ERR_ARG, "sr_gcoeff_cells_dev: bad argument");
+    return gcoeff_cells_impl(ls, pt_host, n_cells, out_dev, false, (cudaStream_t)stream);
 }
 
 // sync + translate the device flag word into a status (humliv_bb's STOP conditions etc.)
@@ -1140,18 +1033,10 @@ int sr_gcoeff_cells_host(sr_lineset* ls, const double* pt_host, int n_cells, dou
 
 int sr_gcoeff_cells_dev_f32(sr_lineset* ls, const double* pt_host, int n_cells, float* out32_dev,
                             double* scratch_dev, void* stream) {
-    if (!ls || !out32_dev || !scratch_dev)
+    if (!ls || !pt_host || n_cells < 0 || !out32_dev)
         return sr::fail(SR_ERR_ARG, "sr_gcoeff_cells_dev_f32: bad argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t cell_elems = (size_t)ls->n_sets * 3 * ls->n_grid;
-    // scratch_dev holds ONE cell in FP64; cells are converted one by one
-    for (int c = 0; c < n_cells; c++) {
-        int code = sr_gcoeff_cells_dev(ls, pt_host + 2 * c, 1, scratch_dev, stream);
-        if (code) return code;
-        SR_LAUNCH(k_f64_to_f32, 148 * 8, 256, 0, st, scratch_dev,
-                  out32_dev + (size_t)c * cell_elems, cell_elems);
-    }
-    return SR_OK;
+    (void)scratch_dev;   // the tile kernel rounds to float32 (numpy astype) in its store
+    return gcoeff_cells_impl(ls, pt_host, n_cells, out32_dev, true, (cudaStream_t)stream);
 }
 
 int sr_line_shapes_dev(sr_lineset* ls, double pres_hpa, double temp, double* shapes_dev,
