@@ -263,29 +263,37 @@ def run_ours(args):
     n_grid, n_cells = len(grid), len(cells)
     ls = engine.LineSet(lines, grid, S.CH4_MM, N_LEVELS)
 
-    # ---- K1: one cell, evals/s --------------------------------------------------------------
-    cell_buf = torch.empty((1, N_LEVELS, 3, n_grid), dtype=torch.float64, device="cuda")
+    # ---- K1: evals/s per (P,T) cell; cells are launched in batches like the LUT builder does ----
+    n_k1 = 2 if args.small else 8
+    cell_buf = torch.empty((n_k1, N_LEVELS, 3, n_grid), dtype=torch.float64, device="cuda")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(3):
-        ls.gcoeff_cells([[0.05, 160.0]], out=cell_buf)
-    k1_ms = []
-    for i in range(5):
-        torch.cuda.synchronize()
-        ev0.record()
-        ls.gcoeff_cells([[0.05 * (1 + i), 160.0]], out=cell_buf, check_status=False)
-        ev1.record()
-        torch.cuda.synchronize()
-        k1_ms.append(ev0.elapsed_time(ev1))
-    k1_t = float(np.median(k1_ms)) * 1e-3
+
+    def k1_time(n_c, reps=5):
+        ms = []
+        for i in range(reps + 2):
+            pts = [[0.05 * (1 + i + j), 150.0 + 2.0 * j] for j in range(n_c)]
+            torch.cuda.synchronize()
+            ev0.record()
+            ls.gcoeff_cells(pts, out=cell_buf[:n_c], check_status=(i < 2))
+            ev1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ms.append(ev0.elapsed_time(ev1))
+        return float(np.median(ms)) * 1e-3
+
+    k1_single = k1_time(1)
+    k1_t = k1_time(n_k1) / n_k1
     evals = ls.n_active * 13010.0
     fp64_peak = engine.fp64_peak(40000)
     voigt = {"metric": "Voigt line*gridpoint evals/s", "value": evals / k1_t, "unit": "evals/s",
-             "ms_per_cell": 1e3 * k1_t, "lines": int(ls.n_active),
+             "ms_per_cell": 1e3 * k1_t, "cells_per_launch": n_k1,
+             "ms_single_cell_launch": 1e3 * k1_single, "lines": int(ls.n_active),
              "roofline": {"bound": "fp64", "achieved": 15.0 * evals / k1_t / 1e12,
                           "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                           "frac": 15.0 * evals / k1_t / fp64_peak, "traffic": None,
                           "note": "15 FP64 flop per eval (SURVEY 8d) over the DFMA rate measured "
-                                  "live by sr_fp64_peak"}}
+                                  "live by sr_fp64_peak; time includes k_line_cell_params, "
+                                  "k_core_eval and k_voigt_tile"}}
     del cell_buf
 
     # ---- K2: LUT build (cells sharded over ranks, all_gather) --------------------------------

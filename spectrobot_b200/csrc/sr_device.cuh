@@ -78,8 +78,6 @@ static __device__ __noinline__ double humliv_core(double rx, double ry) {
         return c_div_re(num, den);
     }
 }
-#undef SRF
-
 // region 2 (lineshape.f:492-522), x2 = x*x
 static __device__ __noinline__ double humliv_reg2(double x2, double ry) {
     double ry2 = ry * ry;
@@ -93,6 +91,90 @@ static __device__ __noinline__ double humliv_reg2(double x2, double ry) {
     double h = 4. * ry2 - 6.;
     return (a + x2 * (b + x2 * (c + d * x2))) / (e + x2 * (f + x2 * (g + x2 * (h + x2))));
 }
+
+// ---- variants for the batched centre kernel (k_core_eval) ------------------------------------
+// Same formulas; the Horner steps are written as FMA pairs (r - c*n and r + c*n in 4 instructions
+// instead of 6), the quotient's real part as (n.d)/(d.d) with one division instead of Smith's two,
+// and the region-2 coefficients are hoisted out of the point loop.  Differences from the forms
+// above are rounding-level (<= a few 1e-16 of the largest term).
+struct reg2_coef { double a, b, c, d, e, f, g, h; };
+__device__ __forceinline__ reg2_coef humliv_reg2_coefs(double ry) {
+    const double ry2 = ry * ry;
+    reg2_coef k;
+    k.a = ry * (1.0578555 + ry2 * (4.6545642 + ry2 * (3.1030428 + 0.5641896 * ry2)));
+    k.b = ry * (2.9619954 + ry2 * (0.5641896 + 1.6925688 * ry2));
+    k.c = ry * (-2.5388532 + ry2 * 1.6925688);
+    k.d = ry * 0.5641896;
+    k.e = 0.5625 + ry2 * (4.5 + ry2 * (10.5 + ry2 * (6. + ry2)));
+    k.f = -4.5 + ry2 * (9. + ry2 * (6. + 4. * ry2));
+    k.g = 10.5 + ry2 * (-6. + 6. * ry2);
+    k.h = 4. * ry2 - 6.;
+    return k;
+}
+__device__ __forceinline__ double humliv_reg2_eval(const reg2_coef& k, double x2) {
+    return (k.a + x2 * (k.b + x2 * (k.c + k.d * x2))) /
+           (k.e + x2 * (k.f + x2 * (k.g + x2 * (k.h + x2))));
+}
+// n <- r - c*n
+__device__ __forceinline__ cplx h_rsub(double r, cplx c, cplx n) {
+    cplx o;
+    o.re = fma(-c.re, n.re, fma(c.im, n.im, r));
+    o.im = -fma(c.re, n.im, c.im * n.re);
+    return o;
+}
+// n <- r + c*n
+__device__ __forceinline__ cplx h_radd(double r, cplx c, cplx n) {
+    cplx o;
+    o.re = fma(c.re, n.re, fma(-c.im, n.im, r));
+    o.im = fma(c.re, n.im, c.im * n.re);
+    return o;
+}
+__device__ __forceinline__ double c_div_re_direct(cplx a, cplx b) {
+    return fma(a.re, b.re, a.im * b.im) / fma(b.re, b.re, b.im * b.im);
+}
+__device__ __forceinline__ double humliv_core_fast(double rx, double ry) {
+    const double r2 = 0.195 * rx - 0.176;
+    cplx c2;
+    c2.re = (double)__double2float_rn(ry);
+    c2.im = (double)__double2float_rn(-rx);
+    if (ry < r2) {  // region 4
+        const cplx c1 = c_mul(c2, c2);
+        cplx num;
+        num.re = c1.re * SRF(.56419);
+        num.im = c1.im * SRF(.56419);
+        num = c_r_sub(SRF(1.320522), num);
+        num = h_rsub(SRF(35.76683), c1, num);
+        num = h_rsub(SRF(219.0313), c1, num);
+        num = h_rsub(SRF(1540.787), c1, num);
+        num = h_rsub(SRF(3321.9905), c1, num);
+        num = h_rsub(SRF(36183.31), c1, num);
+        num = c_mul(c2, num);
+        cplx den = c_r_sub(SRF(1.841439), c1);
+        den = h_rsub(SRF(61.57037), c1, den);
+        den = h_rsub(SRF(364.2191), c1, den);
+        den = h_rsub(SRF(2186.181), c1, den);
+        den = h_rsub(SRF(9022.228), c1, den);
+        den = h_rsub(SRF(24322.84), c1, den);
+        den = h_rsub(SRF(32066.6), c1, den);
+        return exp(c1.re) * cos(c1.im) - c_div_re_direct(num, den);
+    } else {  // region 3
+        cplx num;
+        num.re = c2.re * SRF(.5642236);
+        num.im = c2.im * SRF(.5642236);
+        num = c_add_r(SRF(3.778987), num);
+        num = h_radd(SRF(11.96482), c2, num);
+        num = h_radd(SRF(20.20933), c2, num);
+        num = h_radd(SRF(16.4955), c2, num);
+        cplx den = c_add_r(SRF(6.699398), c2);
+        den = h_radd(SRF(21.69274), c2, den);
+        den = h_radd(SRF(39.27121), c2, den);
+        den = h_radd(SRF(38.82363), c2, den);
+        den = h_radd(SRF(16.4955), c2, den);
+        return c_div_re_direct(num, den);
+    }
+}
+
+#undef SRF
 
 // region 1 exactly as written in the Fortran (lineshape.f:456-477); used by the Tier-1 drop-in
 __device__ __forceinline__ double humliv_reg1(double x2, double ry) {
@@ -118,6 +200,15 @@ __device__ __forceinline__ double rcp_approx(double x) {
 __device__ __forceinline__ double humliv_reg1_fast(double u, double c2) {
     double den = fma(u, u, c2);
     double w = u + 1.0;
+    double r0 = rcp_approx(den);
+    double e = fma(-den, r0, 1.0);
+    double t = w * r0;
+    return fma(t, e, t);
+}
+
+// same with w = u + 1 supplied by the caller (computed in parallel with u)
+__device__ __forceinline__ double humliv_reg1_uw(double u, double w, double c2) {
+    double den = fma(u, u, c2);
     double r0 = rcp_approx(den);
     double e = fma(-den, r0, 1.0);
     double t = w * r0;

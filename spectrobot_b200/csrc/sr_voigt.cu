@@ -280,8 +280,36 @@ __global__ void __launch_bounds__(256) k_core_eval(const LineCell* __restrict__ 
     if (ir - il + 1 > CORE_STRIDE) return;   // wide centre: evaluated inline by the tile kernel
     const double f = nu0[line], g = gc[line];
     double* __restrict__ dst = core + ((size_t)cell * n_lines + line) * CORE_STRIDE;
-    for (int j1 = il + (threadIdx.x & 31); j1 <= ir; j1 += 32)
-        dst[j1 - il] = eval_window_point(rc, j1, f, g, lin);
+    // same precedence as eval_window_point (last writer of lineshape.f:455-562 wins)
+    const int il2 = rc->il2, ir2 = rc->ir2;
+    const int core_lo = (il2 > il) ? il2 + 1 : il, core_hi = (ir2 < ir) ? ir2 - 1 : ir;
+    const double ry = rc->ry, dwp = rc->dwp, xs = rc->xs;
+    const double bL2 = rc->baseL2, bR2 = rc->baseR2, bL1 = rc->baseL1, bR1 = rc->baseR1;
+    const double c1 = rc->c1, c2 = rc->c2, b4 = rc->b4;
+    const srdev::reg2_coef k2 = srdev::humliv_reg2_coefs(ry);
+    for (int j1 = il + (threadIdx.x & 31); j1 <= ir; j1 += 32) {
+        const double j0 = (double)(j1 - 1);
+        double v;
+        if (j1 >= core_lo && j1 <= core_hi) {
+            const double x = lin[j1 - 1] + g;               // spect_classes.py:1455
+            v = srdev::humliv_core_fast(fabs(x - f) / dwp, ry);   // lineshape.f:527
+        } else if (ir2 < ir && j1 >= ir2) {
+            const double x = fma(j0, xs, bR2);
+            v = srdev::humliv_reg2_eval(k2, x * x);
+        } else if (il2 > il && j1 <= il2) {
+            const double x = fma(j0, xs, bL2);
+            v = srdev::humliv_reg2_eval(k2, x * x);
+        } else if (ir < N_WIN && j1 >= ir) {
+            const double x = fma(j0, xs, bR1);
+            v = b4 * srdev::humliv_reg1_fast(fma(x, x, c1), c2);
+        } else if (il > 1 && j1 <= il) {
+            const double x = fma(j0, xs, bL1);
+            v = b4 * srdev::humliv_reg1_fast(fma(x, x, c1), c2);
+        } else {
+            v = 0.0;
+        }
+        dst[j1 - il] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -335,8 +363,8 @@ struct TileArgs {
 //              written straight to global memory; absorption accumulators are parked in a
 //              thread-private shared-memory slot per lower set.  Every output element is written
 //              exactly once, by exactly one thread: no atomics, no zero-fill pass.
-template <int NT, int PPT, bool F32>
-__global__ void __launch_bounds__(NT, NT >= 256 ? 2 : 3) k_voigt_tile(TileArgs a) {
+template <int NT, int PPT, bool F32, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
     constexpr int TP = NT * PPT;
     constexpr int NW = NT / 32;
     const int cell = blockIdx.y;
@@ -431,17 +459,24 @@ __global__ void __launch_bounds__(NT, NT >= 256 ? 2 : 3) k_voigt_tile(TileArgs a
             acc2[k] = 0.0;
         }
     };
-    // FULL: the whole tile lies inside this wing (no predicate at all)
+    // FULL: the whole tile lies inside this wing (no predicate at all).  Partial records skip the
+    // 32-point segments of this warp that lie completely outside the wing (warp-uniform branch).
     auto half_eval = [&](const HalfRec& h, auto full) {
         constexpr bool FULL = decltype(full)::value;
         const double xs = h.xs, b = h.b, c1 = h.c1, c2 = h.c2, g0 = h.g0, g1 = h.g1, g2 = h.g2;
+        const double c1p = c1 + 1.0;   // w = u + 1 straight from x (shorter dependency chain)
         const int lo = h.lo;
         const unsigned len = h.len;
 #pragma unroll
         for (int k = 0; k < PPT; k++) {
+            bool in = true;
+            if (!FULL) {
+                in = (unsigned)(P0 + k * NT - lo) <= len;   // one compare
+                if (!__any_sync(0xffffffffu, in)) continue;
+            }
             const double x = fma(Pd[k], xs, b);
-            double kp = srdev::humliv_reg1_fast(fma(x, x, c1), c2);
-            if (!FULL) kp = ((unsigned)(P0 + k * NT - lo) <= len) ? kp : 0.0;   // one compare
+            double kp = srdev::humliv_reg1_uw(fma(x, x, c1), fma(x, x, c1p), c2);
+            if (!FULL) kp = in ? kp : 0.0;
             acc0[k] = fma(g0, kp, acc0[k]);
             acc1[k] = fma(g1, kp, acc1[k]);
             acc2[k] = fma(g2, kp, acc2[k]);
@@ -530,6 +565,13 @@ __global__ void __launch_bounds__(NT, NT >= 256 ? 2 : 3) k_voigt_tile(TileArgs a
                 c.gs0 = R.gs0; c.gs1 = R.gs1; c.gs2 = R.gs2;
                 c.le = R.PL_end; c.n = R.PR_beg - R.PL_end - 1; c.line = line; c.pad = 0;
                 cbuf[pc] = c;
+                // pull the slice of buffered centre values this tile will gather towards the SM
+                if (c.n <= CORE_STRIDE) {
+                    const int d0 = max(tile0 - c.le - 1, 0) & ~15, d1 = min(c.n, tile_last - c.le);
+                    const double* src = core + (size_t)line * CORE_STRIDE;
+                    for (int d = d0; d < d1; d += 16)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(src + d));
+                }
             }
             __syncthreads();
         }
@@ -664,21 +706,21 @@ size_t tile_smem(int nt, int ppt, int n_lo, int n_groups) {
            (size_t)(nt + 1 + nt / 32 + 4 * n_groups + 1) * sizeof(int) + 16;
 }
 
-template <int NT, int PPT, bool F32>
+template <int NT, int PPT, bool F32, int MINB>
 int launch_tile(const TileArgs& ta, int n_cells, cudaStream_t st) {
     const size_t smem = tile_smem(NT, PPT, ta.n_lo, ta.n_groups);
-    SR_CUDA(cudaFuncSetAttribute(k_voigt_tile<NT, PPT, F32>,
+    SR_CUDA(cudaFuncSetAttribute(k_voigt_tile<NT, PPT, F32, MINB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int TP = NT * PPT;
     dim3 grid((unsigned)((ta.n_grid + TP - 1) / TP), (unsigned)n_cells);
-    SR_LAUNCH((k_voigt_tile<NT, PPT, F32>), grid, NT, smem, st, ta);
+    SR_LAUNCH((k_voigt_tile<NT, PPT, F32, MINB>), grid, NT, smem, st, ta);
     return SR_OK;
 }
 
 // tile geometries (threads, points per thread): the first whose absorption rows fit in shared
 // memory twice per SM is used; SR_K1_CFG=<index> forces one (tuning aid)
 struct TileCfg { int nt, ppt; };
-constexpr TileCfg kTileCfgs[] = {{256, 4}, {256, 2}, {128, 2}, {256, 1}, {128, 4}};
+constexpr TileCfg kTileCfgs[] = {{128, 4}, {256, 4}, {256, 2}, {128, 2}, {256, 1}, {128, 4}, {64, 8}, {64, 4}};
 constexpr int kNumCfgs = (int)(sizeof(kTileCfgs) / sizeof(kTileCfgs[0]));
 
 int pick_cfg(int n_lo, int n_groups, size_t smem_max) {
@@ -688,10 +730,12 @@ int pick_cfg(int n_lo, int n_groups, size_t smem_max) {
             tile_smem(kTileCfgs[i].nt, kTileCfgs[i].ppt, n_lo, n_groups) <= smem_max)
             return i;
     }
-    for (int i = 0; i < 4; i++)      // two CTAs per SM
+    if (2 * (tile_smem(kTileCfgs[5].nt, kTileCfgs[5].ppt, n_lo, n_groups) + 1024) <= (size_t)228 * 1024)
+        return 5;                    // measured best on B200 (tools/tune.py k1): 128 thr x 4 pts, 4 CTAs/SM
+    for (int i = 0; i < 5; i++)      // at least two CTAs per SM
         if (2 * (tile_smem(kTileCfgs[i].nt, kTileCfgs[i].ppt, n_lo, n_groups) + 1024) <= (size_t)228 * 1024)
             return i;
-    for (int i = 0; i < 4; i++)      // one CTA per SM
+    for (int i = 0; i < 5; i++)      // one CTA per SM
         if (tile_smem(kTileCfgs[i].nt, kTileCfgs[i].ppt, n_lo, n_groups) <= smem_max) return i;
     return -1;
 }
@@ -699,11 +743,14 @@ int pick_cfg(int n_lo, int n_groups, size_t smem_max) {
 template <bool F32>
 int launch_cfg(int cfg, const TileArgs& ta, int n_cells, cudaStream_t st) {
     switch (cfg) {
-        case 0: return launch_tile<256, 4, F32>(ta, n_cells, st);
-        case 1: return launch_tile<256, 2, F32>(ta, n_cells, st);
-        case 2: return launch_tile<128, 2, F32>(ta, n_cells, st);
-        case 3: return launch_tile<256, 1, F32>(ta, n_cells, st);
-        case 4: return launch_tile<128, 4, F32>(ta, n_cells, st);
+        case 0: return launch_tile<128, 4, F32, 3>(ta, n_cells, st);
+        case 1: return launch_tile<256, 4, F32, 2>(ta, n_cells, st);
+        case 2: return launch_tile<256, 2, F32, 2>(ta, n_cells, st);
+        case 3: return launch_tile<128, 2, F32, 3>(ta, n_cells, st);
+        case 4: return launch_tile<256, 1, F32, 2>(ta, n_cells, st);
+        case 5: return launch_tile<128, 4, F32, 4>(ta, n_cells, st);
+        case 6: return launch_tile<64, 8, F32, 4>(ta, n_cells, st);
+        case 7: return launch_tile<64, 4, F32, 6>(ta, n_cells, st);
     }
     return sr::fail(SR_ERR_ARG, "bad tile configuration");
 }

@@ -14,7 +14,7 @@ def k1():
     lines = S.line_table(30000, w0, w1, n_levels=n_lev)
     cells = [[1e-4, 150.0], [0.05, 160.0], [0.5, 170.0], [2.5, 175.0]]
     ref = None
-    for cfg in ("0", "1", "2", "3", "4"):
+    for cfg in ("0", "5", "6", "7"):
         os.environ["SR_K1_CFG"] = cfg       # read at LineSet creation (tile geometry)
         ls = engine.LineSet(lines, g, S.CH4_MM, n_lev)
         out = torch.empty((4, n_lev, 3, len(g)), dtype=torch.float64, device="cuda")
@@ -27,7 +27,7 @@ def k1():
         print("k1 cfg %s: %.3f ms / 4 cells -> %.3e evals/s (max rel diff %.1e)" % (cfg, min(ms), 4 * ls.n_active * 13010 / (min(ms) * 1e-3), d))
         del ls, out
     lines1 = S.line_table(30000, w0, w1, n_levels=1)
-    for cfg in ("0", "1", "4"):
+    for cfg in ("0", "1"):
         os.environ["SR_K1_CFG"] = cfg
         ls1 = engine.LineSet(lines1, g, 27.99, 1)
         out1 = torch.empty((4, 1, 3, len(g)), dtype=torch.float64, device="cuda")
