@@ -193,10 +193,34 @@ int sr_los_check(sr_lut* const* luts, void* stream);
 int sr_los_tau_src_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
                        double* tau_dev, double* src_dev, void* stream);
 
+/* make_abscoeff_LUTS_fast [spect_main_module.py:2134-2299]: per (LOS, step, point)
+ * abs = sum_gas column*ratio*sum_lev (G_abs - G_ind)*pop and emi = sum_gas column*ratio*sum_lev
+ * G_sp*pop, [n_los][n_steps_max][n_pts] each (device).  With column = 1/ratio these are the
+ * reference's absorption / emission coefficients of the isotopologue. */
+int sr_los_abs_emi_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
+                       double* abs_dev, double* emi_dev, void* stream);
+
 /* LutSet.calculate(P,T) [spect_main_module.py:997-1066]: the (up to) 4 cells and weights the
  * reference's nearest-node bilinear rule picks.  Host helper (index logic only). */
 int sr_lut_weights(const double* pt_host, int n_cells, double pres, double temp, int cell[4],
                    double w[4]);
+
+/* ===========================================================================================
+ * Tier 2 -- instrument convolution of hi-res spectra to low-res channels
+ * SpectralIntensity.hires_to_lowres -> convolve_to_grid_from_irregular
+ * [spect_classes.py:1180-1191, 883-918, gaussian :1926, conv_single :1162]
+ * =========================================================================================*/
+
+/* spec: [n_spec][n_pts] spectra on the common ascending (possibly irregular) grid[n_pts];
+ * channel c integrates spec * N(centre[c], width[c]) with the trapezoid rule over the grid points
+ * within +-n_sigma*width[c] (reference default n_sigma = 5); out: [n_spec][n_chan].
+ * _dev: every pointer is a DEVICE pointer, asynchronous on `stream`.  _host: HOST pointers. */
+int sr_convolve_lowres_dev(const double* grid_dev, long n_pts, const double* spec_dev, int n_spec,
+                           const double* centre_dev, const double* width_dev, int n_chan,
+                           double n_sigma, double* out_dev, void* stream);
+int sr_convolve_lowres_host(const double* grid, long n_pts, const double* spec, int n_spec,
+                            const double* centre, const double* width, int n_chan,
+                            double n_sigma, double* out);
 
 /* FP64 FMA micro-benchmark used by bench.py for the K1/K2 roofline denominator: runs
  * `iters` dependent-chain FMAs per thread on a full grid and returns achieved FLOP/s. */

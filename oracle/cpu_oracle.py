@@ -462,3 +462,22 @@ def gcoeff_cell(lines, grid, T, P, MM, n_sets, n_threads=1, lin_grid=None):
     if rc:
         raise RuntimeError("gcoeff_cell: humliv_bb status %d" % rc)
     return out
+
+
+def convolve_to_grid_from_irregular(grid, spectrum, new_grid, spectral_widths, n_sigma=5.):
+    """Literal NumPy restatement of SpectralObject.convolve_to_grid_from_irregular
+    (spect_classes.py:883-918) with gaussian (:1926-1934) and conv_single (:1162-1164)."""
+    grid = np.asarray(grid, dtype=float)
+    spectrum = np.asarray(spectrum, dtype=float)
+    out = np.zeros(len(new_grid), dtype=float)
+    for num, (freq, wid) in enumerate(zip(new_grid, spectral_widths)):
+        ok_po = (grid >= freq - n_sigma * wid) & (grid <= freq + n_sigma * wid)
+        lin_grid_ok = grid[ok_po]
+        spect_old = spectrum[ok_po]
+        if len(spect_old) == 0:
+            out[num] = 0.0
+            continue
+        fac = 1 / (wid * np.sqrt(2. * np.pi))
+        gauss = fac * np.exp(-0.5 * ((lin_grid_ok - freq) / wid) ** 2)
+        out[num] = np.trapezoid(spect_old * gauss, x=lin_grid_ok)
+    return out

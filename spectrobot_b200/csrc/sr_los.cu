@@ -185,6 +185,7 @@ struct LosArgs {
     double* tau_out;      // [n_los][n_steps_max][n_pts] (k_los_tau_src)
     double* src_out;
     int solo_absorption;
+    int emit_j;           // k_los_tau_src: write J (emission coefficient x column) instead of S = J/tau
 };
 
 // tau and J of one step for PPT points of one thread
@@ -265,7 +266,8 @@ __global__ void __launch_bounds__(1024) k_los_fused(LosArgs a) {
             for (int i = 0; i < PPT; i++)
                 if (ok[i]) {
                     __stcs(a.tau_out + o + i * 256, tau[i]);
-                    __stcs(a.src_out + o + i * 256, tau[i] == 0.0 ? 0.0 : J[i] / tau[i]);
+                    __stcs(a.src_out + o + i * 256,
+                           a.emit_j ? J[i] : (tau[i] == 0.0 ? 0.0 : J[i] / tau[i]));
                 }
         } else {
 #pragma unroll
@@ -613,7 +615,7 @@ int sr_los_rt_layers_dev(const double* tau, const double* src, const int* n_step
 
 static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
                       const double* i0_dev, int solo, double* rad_dev, double* tau_dev,
-                      double* src_dev, cudaStream_t st) {
+                      double* src_dev, cudaStream_t st, int emit_j = 0) {
     LosArgs la;
     int rc = prepare_steps(luts, steps, st, la);
     if (rc) return rc;
@@ -626,6 +628,7 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
     la.tau_out = tau_dev;
     la.src_out = src_dev;
     la.solo_absorption = solo;
+    la.emit_j = emit_j;
     int G = 2, ppt = 4;   // measured on B200 (tools/tune.py fused)
     if (const char* e = getenv("SR_LOS_G")) G = std::max(1, std::min(4, atoi(e)));     // tuning aids
     if (const char* e = getenv("SR_LOS_PPT")) ppt = atoi(e);
@@ -654,6 +657,13 @@ int sr_los_tau_src_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0,
     if (!tau_dev || !src_dev) return sr::fail(SR_ERR_ARG, "sr_los_tau_src_dev: bad argument");
     return los_launch(luts, steps, pt0, n_pts, nullptr, 0, nullptr, tau_dev, src_dev,
                       (cudaStream_t)stream);
+}
+
+int sr_los_abs_emi_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
+                       double* abs_dev, double* emi_dev, void* stream) {
+    if (!abs_dev || !emi_dev) return sr::fail(SR_ERR_ARG, "sr_los_abs_emi_dev: bad argument");
+    return los_launch(luts, steps, pt0, n_pts, nullptr, 0, nullptr, abs_dev, emi_dev,
+                      (cudaStream_t)stream, 1);
 }
 
 int sr_los_check(sr_lut* const* luts, void* stream) {

@@ -293,6 +293,31 @@ def los_tau_src(luts, steps, pt0=0, n_pts=None, stream=None):
     return tau, src
 
 
+def los_abs_emi(luts, steps, pt0=0, n_pts=None, stream=None):
+    """make_abscoeff_LUTS_fast on the device: (abs, emi) CUDA tensors [n_los, n_steps_max, n_pts]
+    (coefficients x column x isotopic ratio)."""
+    torch = _torch()
+    if n_pts is None:
+        n_pts = luts[0].n_grid - pt0
+    shape = (steps.n_los, steps.n_steps_max, n_pts)
+    a = torch.zeros(shape, dtype=torch.float64, device="cuda")
+    e = torch.zeros(shape, dtype=torch.float64, device="cuda")
+    arr = _lut_array(luts)
+    st = steps.struct()
+    sp = _stream_ptr(stream)
+    check(lib().sr_los_abs_emi_dev(arr, C.byref(st), int(pt0), int(n_pts),
+                                   C.c_void_p(a.data_ptr()), C.c_void_p(e.data_ptr()), sp))
+    check(lib().sr_los_check(arr, sp))
+    return a, e
+
+
+def partition_sum(mol, iso, temp=296.0):
+    """CalcPartitionSum (spect_classes.py:1692-1710) from the library's TIPS tables."""
+    q = C.c_double()
+    check(lib().sr_partition_sum(int(mol), int(iso), float(temp), C.byref(q)))
+    return q.value
+
+
 def los_rt_layers(tau, src, n_steps, i0=None, solo_absorption=False, out=None, stream=None):
     """K3 alone on materialised layers: tau, src CUDA float64 [n_los, n_steps_max, n_pts];
     n_steps CUDA int32 [n_los] -> radiances [n_los, n_pts]."""
@@ -318,6 +343,39 @@ def lut_weights(PTcouples, Pres, Temp):
     check(lib().sr_lut_weights(dptr(pt), pt.shape[0], float(Pres), float(Temp), iptr(cell),
                                dptr(w)))
     return cell, w
+
+
+def convolve_lowres(grid, spec, centres, widths, n_sigma=5.0, out=None, stream=None):
+    """Instrument convolution on the device (spect_classes.py:883-918): grid [n_pts] and spec
+    [n_spec, n_pts] CUDA float64 tensors, channel centres/widths (array-likes or CUDA tensors) ->
+    CUDA float64 [n_spec, n_chan]."""
+    torch = _torch()
+    if spec.dim() == 1:
+        spec = spec[None]
+    assert spec.is_cuda and spec.dtype == torch.float64 and spec.is_contiguous()
+    assert grid.is_cuda and grid.dtype == torch.float64 and grid.numel() == spec.shape[1]
+    c = centres if torch.is_tensor(centres) else torch.as_tensor(as_f64(centres), device="cuda")
+    w = widths if torch.is_tensor(widths) else torch.as_tensor(as_f64(widths), device="cuda")
+    assert c.numel() == w.numel()
+    if out is None:
+        out = torch.empty((spec.shape[0], c.numel()), dtype=torch.float64, device="cuda")
+    check(lib().sr_convolve_lowres_dev(C.c_void_p(grid.data_ptr()), spec.shape[1],
+                                       C.c_void_p(spec.data_ptr()), spec.shape[0],
+                                       C.c_void_p(c.data_ptr()), C.c_void_p(w.data_ptr()),
+                                       c.numel(), float(n_sigma), C.c_void_p(out.data_ptr()),
+                                       _stream_ptr(stream)))
+    return out
+
+
+def convolve_lowres_host(grid, spec, centres, widths, n_sigma=5.0):
+    """Host-buffer form of convolve_lowres: numpy in, numpy [n_spec, n_chan] out."""
+    grid = as_f64(grid)
+    spec = np.atleast_2d(as_f64(spec))
+    c, w = as_f64(centres), as_f64(widths)
+    out = np.empty((spec.shape[0], len(c)))
+    check(lib().sr_convolve_lowres_host(dptr(grid), len(grid), dptr(spec), spec.shape[0], dptr(c),
+                                        dptr(w), len(c), float(n_sigma), dptr(out)))
+    return out
 
 
 def fp64_peak(iters=20000):

@@ -1,0 +1,495 @@
+"""`spect_main_module` for the hot path, Python 3, backed by libspectrobot.so.
+
+Keeps the reference's names and call signatures for the forward-model chain:
+
+    prepare_spe_grid, calc_PT_couples_atmosphere, LutSet, LookUpTable, makeLUT_nonLTE_Gcoeffs,
+    check_and_build_allluts, make_abscoeff_LUTS_fast, radtrans
+
+Differences in HOW, not in WHAT: LookUpTable.make builds every (P,T) cell x level x ctype with one
+batched GPU call and keeps the LUT resident on the device as float32 (the reference's compressed
+LUT, smm:1676); radtrans runs all lines of sight of a wavenumber chunk in one launch instead of one
+forked process per LOS, and reduces each chunk to the instrument channels on the device.  The
+retrieval algebra, FOV integration and the observation readers are out of scope.
+"""
+import copy
+import math as mt
+import os
+import pickle
+import time
+
+import numpy as np
+
+from . import engine
+from . import spect_base_module as sbm
+from . import spect_classes as spcl
+
+n_threads = 8
+CTYPES = spcl.CTYPES
+
+
+def date_stamp():
+    t = time.localtime()
+    return '_{:d}-{}-{:d}'.format(t.tm_mday, time.strftime('%b', t), t.tm_year)
+
+
+def lut_name(mol, iso, LTE):
+    """LUT_molMM_isoI_{LTE|nonLTE} (smm:659-680)."""
+    return 'LUT_mol{:02d}_iso{:1d}_{}'.format(mol, iso, 'LTE' if LTE else 'nonLTE')
+
+
+def prepare_spe_grid(wn_range, sp_step=5.e-4, units='cm_1'):
+    """Zero spectrum on np.arange(w0, w1 + step/2, step) (smm:1262-1272)."""
+    grid = spcl.SpectralGrid(np.arange(wn_range[0], wn_range[1] + sp_step / 2, sp_step,
+                                       dtype=float), units=units)
+    return spcl.SpectralObject(np.zeros(len(grid.grid)), grid, units=units)
+
+
+# ---------------------------------------------------------------------------------------------
+# (P,T) cells of the LUT
+# ---------------------------------------------------------------------------------------------
+def calc_PT_couples_atmosphere(lines, molecs, atmosphere, pres_step_log=0.4, temp_step=5.0,
+                               max_pres=None, thres=0.01, add_lowpres=True):
+    """The [P_hPa, T_K] cells a LUT needs for `atmosphere` (smm:1746-1844).
+
+    ln P on multiples of pres_step_log between the lowest atmospheric pressure and max_pres; for
+    every pressure the temperature range found within +-1 pressure level, widened by one
+    temp_step on both sides and rounded to the temp_step ladder; cells where the Lorentz width of
+    the broadest line is below thres x Doppler width collapse onto two pressures (the largest such
+    pressure and, with add_lowpres, the lowest ladder pressure)."""
+    atm_p = np.asarray(atmosphere.pres, dtype=float)
+    atm_t = np.asarray(atmosphere.temp, dtype=float)
+    top = mt.log(np.max(atm_p)) if max_pres is None else mt.log(max_pres)
+    n_hi = mt.ceil(top / pres_step_log)
+    n_lo = mt.floor(mt.log(np.min(atm_p)) / pres_step_log)
+    ln_lo, ln_hi = n_lo * pres_step_log, n_hi * pres_step_log
+    pressures = np.exp(ln_lo + np.arange(0, (ln_hi - ln_lo) + 0.5 * pres_step_log, pres_step_log))
+
+    def t_range(mask):
+        t = atm_t[mask]
+        return [np.min(t), np.max(t)]
+
+    temps = [t_range(atm_p <= pressures[1])]
+    for p0, p2 in zip(pressures[:-2], pressures[2:]):
+        temps.append(t_range((atm_p >= p0) & (atm_p <= p2)))
+    temps.append(t_range((atm_p >= pressures[-2]) & (atm_p <= pressures[-1])))
+
+    couples = []
+    for pres, (t_min, t_max) in zip(pressures, temps):
+        t_0 = (np.floor(t_min / temp_step) - 1) * temp_step
+        t_1 = (np.ceil(t_max / temp_step) + 1) * temp_step
+        couples += [[pres, temp] for temp in np.arange(t_0, t_1 + 0.5 * temp_step, temp_step)]
+
+    if not isinstance(molecs, (list, tuple)):
+        molecs = [molecs]
+    mms = []
+    for mol in molecs:
+        if isinstance(mol, sbm.Molec):
+            mms += [getattr(mol, isom).MM for isom in mol.all_iso]
+        elif isinstance(mol, sbm.IsoMolec):
+            mms.append(mol.MM)
+    broadest = lines[int(np.argmax(np.array([lin.Air_broad for lin in lines])))]
+
+    kept, doppler_temps, pres_0 = [], [], 1.e-8
+    for pres, temp in couples:
+        dw, lw, _ = broadest.CheckWidths(temp, pres, min(mms))
+        if lw < thres * dw:
+            pres_0 = max(pres_0, pres)
+            if temp not in doppler_temps:
+                doppler_temps.append(temp)
+        else:
+            kept.append([pres, temp])
+    for temp in doppler_temps:
+        kept.insert(0, [pres_0, temp])
+    if add_lowpres:
+        for temp in doppler_temps:
+            kept.insert(0, [mt.exp(ln_lo), temp])
+    return kept
+
+
+# ---------------------------------------------------------------------------------------------
+# LUT classes
+# ---------------------------------------------------------------------------------------------
+class LutSet(object):
+    """All (P,T) cells of one vibrational level (or of 'all' lines for an LTE isotopologue), three
+    ctypes each (smm:841-1176).  The numbers live in the parent LookUpTable's device tensor;
+    `sets` materialises host SpectralGcoeff objects on demand (calculate())."""
+
+    def __init__(self, mol, iso, MM, level=None, filename=None):
+        self.mol, self.iso, self.MM = mol, iso, MM
+        self.level = copy.deepcopy(level)
+        self.unidentified_lines = level is None
+        self.filename = filename
+        self.filenames = [filename]
+        self.sets = []
+        self.spectral_grid = None
+        self.PTcouples = None
+        self._table = None     # (LookUpTable, set index) once built on the device
+
+    def find(self, Pres, Temp):
+        """Index of [Pres, Temp] in PTcouples (smm:985-995)."""
+        if [Pres, Temp] not in self.PTcouples:
+            raise ValueError('{} couple not found!'.format([Pres, Temp]))
+        return self.PTcouples.index([Pres, Temp])
+
+    def _host_sets(self):
+        if not self.sets and self._table is not None:
+            lut, s = self._table
+            g = lut.g32[:, s].cpu().numpy()
+            lev_str = '' if self.unidentified_lines else self.level.minimal_level_string()
+            for c, (P, T) in enumerate(self.PTcouples):
+                d = dict()
+                for k, ctype in enumerate(CTYPES):
+                    # all-zero spectra are stored as None by split_and_compress_LUTS (smm:1674-1679)
+                    d[ctype] = None if not np.any(g[c, k]) else spcl.SpectralGcoeff(
+                        ctype, self.spectral_grid, self.mol, self.iso, self.MM, lev_str,
+                        unidentified_lines=self.unidentified_lines,
+                        spectrum=g[c, k].astype(np.float64), Pres=P, Temp=T)
+                self.sets.append(d)
+        return self.sets
+
+    def free_memory(self):
+        self.sets = []
+
+    def calculate(self, Pres, Temp):
+        """{ctype: SpectralGcoeff} interpolated to (Pres, Temp) with the reference's rule
+        (smm:997-1066): nearest and second-nearest node in P and in T, linear in P then in T; at or
+        below the lowest pressure node only T is interpolated; above the highest: ValueError."""
+        sets = self._host_sets()
+        Ps = np.unique(np.array([PT[0] for PT in self.PTcouples]))
+        Ts = np.unique(np.array([PT[1] for PT in self.PTcouples]))
+        t_near = np.argsort(np.abs(Ts - Temp), kind='stable')
+        T1, T2 = Ts[np.argmin(np.abs(Ts - Temp))], Ts[t_near[1]]
+        out = dict()
+        if Pres <= np.min(Ps):
+            a, b = sets[self.find(np.min(Ps), T1)], sets[self.find(np.min(Ps), T2)]
+            for ctype in CTYPES:
+                out[ctype] = None if a[ctype] is None or b[ctype] is None else \
+                    a[ctype].interpolate(b[ctype], Temp=Temp)
+        elif Pres <= np.max(Ps):
+            P1 = Ps[np.argmin(np.abs(Ps - Pres))]
+            P2 = Ps[np.argsort(np.abs(Ps - Pres), kind='stable')[1]]
+            c11, c12 = sets[self.find(P1, T1)], sets[self.find(P1, T2)]
+            c21, c22 = sets[self.find(P2, T1)], sets[self.find(P2, T2)]
+            for ctype in CTYPES:
+                if any(c[ctype] is None for c in (c11, c12, c21, c22)):
+                    out[ctype] = None
+                    continue
+                lo = c11[ctype].interpolate(c21[ctype], Pres=Pres)
+                hi = c12[ctype].interpolate(c22[ctype], Pres=Pres)
+                out[ctype] = lo.interpolate(hi, Temp=Temp)
+        else:
+            raise ValueError('Extrapolating in P')
+        return out
+
+    def add_PT(self, spectral_grid, lines, Pres, Temp, keep_memory=False, control=True,
+               n_threads=n_threads):
+        """One (P,T) cell from lines that already carry shapes and G coefficients
+        (calc_shapes_lines), through BuildCoeff -> sum_all_lines (smm:1122-1168).  The batched
+        builder is LookUpTable.make; this method is the reference-shaped single-cell form."""
+        if self.spectral_grid is None:
+            self.spectral_grid = copy.deepcopy(spectral_grid)
+        if self.PTcouples is None:
+            self.PTcouples = []
+        lev_str = '' if self.unidentified_lines else self.level.minimal_level_string()
+        set_ = dict()
+        for ctype in CTYPES:
+            co = spcl.SpectralGcoeff(ctype, spectral_grid, self.mol, self.iso, self.MM, lev_str,
+                                     unidentified_lines=self.unidentified_lines)
+            co.BuildCoeff(lines, Temp, Pres, preCalc_shapes=True, n_threads=n_threads)
+            set_[ctype] = co
+        if keep_memory:
+            self.sets.append(set_)
+            self.PTcouples.append([Pres, Temp])
+        return set_
+
+
+class LookUpTable(object):
+    """Look-up table of one isotopologue (smm:682-838): one LutSet per vibrational level for a
+    non-LTE isotopologue, a single set 'all' for an LTE one."""
+
+    def __init__(self, isomolec, wn_range, LTE):
+        self.tag = lut_name(isomolec.mol, isomolec.iso, LTE)
+        self.wn_range = copy.deepcopy(wn_range)
+        self.mol, self.iso, self.MM = isomolec.mol, isomolec.iso, isomolec.MM
+        self.isomolec = copy.deepcopy(isomolec)
+        self.sets = dict()
+        self.PTcouples = []
+        self.LTE = LTE
+        self.g32 = None           # CUDA float32 [n_cells][n_sets][3][n_grid]
+        self._dev = None
+
+    def set_names(self):
+        return list(self.isomolec.levels) if not self.LTE else ['all']
+
+    def make(self, spectral_grid, lines, PTcouples, export_levels=True, cartLUTs=None,
+             control=True, n_threads=n_threads, cells=None):
+        """Builds every cell of the LUT on the GPU (smm:718-788).  `cells` optionally restricts
+        the build to a subset of PTcouples indices (multi-GPU sharding: parallel.shard_cells);
+        the other cells are left zero until parallel.gather_lut fills them."""
+        import torch
+        self.PTcouples = [list(map(float, pt)) for pt in PTcouples]
+        self.spectral_grid = copy.deepcopy(spectral_grid)
+        lines = [lin for lin in lines if lin.Mol == self.mol and lin.Iso == self.iso]
+        tab = spcl.line_table(lines, None if self.LTE else self.isomolec)
+        names = self.set_names()
+        n_sets = tab["n_sets"]
+        if n_sets != len(names):
+            raise ValueError('isotopologue {} has no levels but LTE is False'.format(self.tag))
+        grid = self.spectral_grid.grid
+        self.g32 = torch.zeros((len(self.PTcouples), n_sets, 3, len(grid)), dtype=torch.float32,
+                               device="cuda")
+        idx = list(range(len(self.PTcouples))) if cells is None else list(cells)
+        if idx:
+            ls = engine.LineSet(tab, grid, self.MM, n_sets)
+            sub = ls.gcoeff_cells_f32([self.PTcouples[i] for i in idx])
+            self.g32[torch.as_tensor(idx, device="cuda")] = sub
+            ls.close()
+        for s, nam in enumerate(names):
+            level = None if self.LTE else getattr(self.isomolec, nam)
+            st = LutSet(self.mol, self.iso, self.MM, level=level)
+            st.PTcouples = self.PTcouples
+            st.spectral_grid = self.spectral_grid
+            st._table = (self, s)
+            self.sets[nam] = st
+        self._dev = None
+        if cartLUTs is not None and export_levels:
+            self.export(os.path.join(cartLUTs, self.tag + date_stamp() + '.pic'))
+        return self
+
+    def device_lut(self):
+        """engine.Lut handle over the resident float32 table."""
+        if self._dev is None:
+            energies = None if self.LTE else self.isomolec.level_energies()
+            self._dev = engine.Lut(self.g32, self.PTcouples, self.mol, self.iso,
+                                   self.isomolec.ratio, level_energies=energies)
+        return self._dev
+
+    def find_lev(self, lev_string):
+        for lev, st in self.sets.items():
+            if st.level is not None and st.level.equiv(lev_string):
+                return True, lev
+        return False, None
+
+    def merge(self, LUT):
+        """Concatenate the cells of another LUT of the same isotopologue and range (smm:699-716)."""
+        import torch
+        if self.wn_range != LUT.wn_range:
+            raise ValueError('Incompatible LUTs, different wn_ranges: {} {}'.format(
+                self.wn_range, LUT.wn_range))
+        self.PTcouples += LUT.PTcouples
+        self.g32 = torch.cat([self.g32, LUT.g32], dim=0)
+        for st in self.sets.values():
+            st.PTcouples = self.PTcouples
+            st.free_memory()
+        self._dev = None
+
+    def export(self, filename):
+        """Header (PTcouples) first, then the table, like the reference's per-level files
+        (smm:880-892): resumable by check_LUT_exists()."""
+        with open(filename, 'wb') as f:
+            pickle.dump(self.PTcouples, f, protocol=-1)
+            pickle.dump(dict(tag=self.tag, wn_range=self.wn_range, mol=self.mol, iso=self.iso,
+                             LTE=self.LTE, sets=self.set_names(),
+                             grid=self.spectral_grid.grid, g32=self.g32.cpu().numpy()), f,
+                        protocol=-1)
+        self.filename = filename
+        return filename
+
+
+def check_LUT_exists(PTcouples, cartLUTs, mol, iso, LTE):
+    """(missing cells, files holding the others): reads only the PTcouples header of the LUT
+    files of this isotopologue found in cartLUTs (smm:1390-1456)."""
+    tag = lut_name(mol, iso, LTE)
+    have, files = [], []
+    if cartLUTs is not None and os.path.isdir(cartLUTs):
+        for fn in sorted(os.listdir(cartLUTs)):
+            if fn.startswith(tag) and fn.endswith('.pic'):
+                with open(os.path.join(cartLUTs, fn), 'rb') as f:
+                    pts = pickle.load(f)
+                have += [list(map(float, pt)) for pt in pts]
+                files.append(os.path.join(cartLUTs, fn))
+    missing = [list(map(float, pt)) for pt in PTcouples
+               if not any(sbm.isclose(pt[0], h[0]) and sbm.isclose(pt[1], h[1]) for h in have)]
+    return missing, files
+
+
+def makeLUT_nonLTE_Gcoeffs(spectral_grid, lines, isomolec, LTE=True, atmosphere=None,
+                           cartLUTs=None, n_threads=n_threads, test=False, PTcouples=None,
+                           LUTopt=dict()):
+    """Build the LUT of one isotopologue (smm:1847-1877)."""
+    if PTcouples is None:
+        PTcouples = calc_PT_couples_atmosphere(lines, isomolec, atmosphere, **LUTopt)
+    if test:
+        PTcouples = PTcouples[:2]
+    wn_range = [spectral_grid.grid[0], spectral_grid.grid[-1]]
+    LUT = LookUpTable(isomolec, wn_range, LTE)
+    LUT.make(spectral_grid, lines, PTcouples, cartLUTs=cartLUTs, n_threads=n_threads)
+    return LUT
+
+
+def check_and_build_allluts(inputs, sp_grid, lines, molecs, atmosphere=None, PTcouples=None,
+                            LUTopt=dict(), check_wn_range=True):
+    """{(mol_name, iso): LookUpTable} for every isotopologue of `molecs` that has lines in the
+    range (None otherwise, smm:1459-1510)."""
+    if PTcouples is None:
+        PTcouples = calc_PT_couples_atmosphere(lines, list(molecs), atmosphere, **LUTopt)
+    cart = inputs.get('cart_LUTS') if isinstance(inputs, dict) else None
+    allLUTs = dict()
+    for molec in molecs:
+        for isoname in molec.all_iso:
+            isomol = getattr(molec, isoname)
+            mine = [lin for lin in lines if lin.Mol == isomol.mol and lin.Iso == isomol.iso]
+            if not mine:
+                allLUTs[(isomol.mol_name, isomol.iso)] = None
+                continue
+            LTE = isomol.is_in_LTE or len(isomol.levels) == 0
+            allLUTs[(isomol.mol_name, isomol.iso)] = makeLUT_nonLTE_Gcoeffs(
+                sp_grid, mine, isomol, LTE=LTE, cartLUTs=cart, PTcouples=PTcouples)
+    return allLUTs
+
+
+# ---------------------------------------------------------------------------------------------
+# absorption / emission coefficients and the LOS integral
+# ---------------------------------------------------------------------------------------------
+def make_abscoeff_LUTS_fast(spectral_grid, isomolec, Temps, Press, LTE=True, tagLOS=None,
+                            allLUTs=None, cartDROP=None, store_in_memory=False, track_levels=None,
+                            time_control=False):
+    """Absorption and emission coefficients of one isotopologue at the LOS steps (Temps, Press)
+    from the LUT (smm:2134-2299): lists of SpectralObject, one per step.  Vibrational
+    temperatures are read from Level.local_vibtemp[step] when LTE is False."""
+    LUT = allLUTs[(isomolec.mol_name, isomolec.iso)]
+    if LUT is None:
+        return None, None
+    Temps, Press = np.atleast_1d(Temps).astype(float), np.atleast_1d(Press).astype(float)
+    n = len(Temps)
+    n_sets = len(LUT.set_names())
+    tvib = None
+    if not LUT.LTE:
+        tvib = np.empty((1, n_sets, 1, n))
+        for s, lev in enumerate(isomolec.levels):
+            L = getattr(isomolec, lev)
+            tvib[0, s, 0] = Temps if LTE else np.asarray(L.local_vibtemp[:n], dtype=float)
+    # unit column per unit isotopic ratio: tau = abs coefficient, J = emission coefficient
+    steps = engine.LosSteps([n], Temps[None], Press[None],
+                            np.full((1, 1, n), 1.0 / LUT.isomolec.ratio), tvib)
+    a, e = engine.los_abs_emi([LUT.device_lut()], steps)
+    a, e = a.cpu().numpy()[0], e.cpu().numpy()[0]
+    abs_c = [spcl.SpectralObject(a[k], spectral_grid, link_grid=True) for k in range(n)]
+    emi_c = [spcl.SpectralObject(e[k], spectral_grid, link_grid=True) for k in range(n)]
+    return abs_c, emi_c
+
+
+def los_step_tables(loss, planet):
+    """engine.LosSteps of a list of sbm.LineOfSight that went through calc_radtran_steps."""
+    gi = loss[0].radtran_steps['gas_isos']
+    nmax = max(len(l.radtran_steps['step']) for l in loss)
+    tabs = [l.step_tables(planet, n_steps_max=nmax) for l in loss]
+    n_steps = np.array([t[0] for t in tabs], dtype=np.int32)
+    temp = np.stack([t[1] for t in tabs])
+    pres = np.stack([t[2] for t in tabs])
+    col = np.stack([t[3] for t in tabs], axis=1)            # [gas][los][step]
+    tvib = np.stack([t[4] for t in tabs], axis=2)           # [gas][set][los][step]
+    return gi, engine.LosSteps(n_steps, temp, pres, col, tvib)
+
+
+def los_batch_radiances(loss, sp_grid, planet, LUTS, solo_absorption=False,
+                        initial_intensity=None, lowres=None, pt0=0, n_pts=None):
+    """Radiances of a batch of lines of sight in ONE launch sequence.
+
+    loss: sbm.LineOfSight objects with radtran_steps; LUTS: {(mol_name, iso): LookUpTable}.
+    Returns a list of hi-res SpectralIntensity on sp_grid[pt0:pt0+n_pts], or, with
+    lowres = (channel centres, channel widths) in the units of sp_grid, the CUDA tensor
+    [n_los][n_chan] convolved on the device (hires_to_lowres)."""
+    import torch
+    gi, steps = los_step_tables(loss, planet)
+    luts, keep = [], []
+    for m, (g, iso) in enumerate(gi):
+        im = getattr(planet.gases[g], iso)
+        L = LUTS.get((im.mol_name, im.iso))
+        if L is not None:
+            luts.append(L.device_lut())
+            keep.append(m)
+    if not luts:
+        raise ValueError('no LUT for any gas of the planet in this spectral range')
+    if len(keep) != len(gi):
+        steps = engine.LosSteps(steps.n_steps, steps.temp, steps.pres, steps.column[keep],
+                                steps.tvib[keep])
+    grid = sp_grid.grid if hasattr(sp_grid, 'grid') else np.asarray(sp_grid)
+    n_pts = len(grid) - pt0 if n_pts is None else n_pts
+    i0 = None
+    if initial_intensity is not None:
+        i0 = torch.as_tensor(np.broadcast_to(np.asarray(initial_intensity, dtype=float),
+                                             (len(loss), n_pts)).copy(), device="cuda")
+    rad = engine.los_rt_lut(luts, steps, pt0=pt0, n_pts=n_pts, i0=i0,
+                            solo_absorption=solo_absorption)
+    if lowres is not None:
+        gdev = torch.as_tensor(np.ascontiguousarray(grid[pt0:pt0 + n_pts]), device="cuda")
+        return engine.convolve_lowres(gdev, rad, lowres[0], lowres[1])
+    rad = rad.cpu().numpy()
+    units = getattr(sp_grid, 'units', 'cm_1')
+    sub = spcl.SpectralGrid(grid[pt0:pt0 + n_pts], units=units)
+    return [spcl.SpectralIntensity(rad[i], sub) for i in range(len(loss))]
+
+
+def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_opt=dict(),
+             save_hires=True, save_lowres=True, LUTopt=dict(), test=False, use_tangent_sza=False,
+             group_observations=False, invert_LOS_direction=False, nome_inv='1',
+             track_levels=None, alt_step_sims=50., alt_first_los=None):
+    """Forward model for a list of pixels (smm:2990-3287), batched on the GPU.
+
+    Three lines of sight per pixel (low, centre, up; :3091-3096) -> radtran steps (host,
+    Curtis-Godson through the `curgods` drop-in) -> per wavenumber chunk ONE launch for all LOS,
+    reduced to the instrument channels on the device -> low-res spectra summed over chunks.
+    Returns (sims, radtrans, single_rads): `radtrans` = {LOS tag: low-res SpectralIntensity};
+    `sims` = per pixel the mean of its three LOS (the reference's FOV_integr_1D spline/quad
+    integration is out of scope); single_rads = {} (per-gas tracking is not
+    part of the hot path)."""
+    import torch
+    pixels = sorted(pixels, key=lambda p: p.limb_tg_alt)
+    if sp_gri is None:
+        if wn_range is None:
+            raise ValueError('radtrans needs wn_range or sp_gri')
+        sp_gri = prepare_spe_grid(wn_range).spectral_grid
+    LUTopt = dict(LUTopt)
+    if 'max_pres' not in LUTopt:
+        LUTopt['max_pres'] = max(planet.atmosphere.calc(p.low_LOS().get_tangent_point(), 'pres')
+                                 for p in pixels)
+    gases = list(planet.gases.values())
+    PT = calc_PT_couples_atmosphere(lines, gases, planet.atmosphere, **LUTopt)
+    LUTS = check_and_build_allluts(inputs, sp_gri, lines, gases, PTcouples=PT, LUTopt=LUTopt)
+
+    sim_LOSs = []
+    for pix in pixels:
+        sim_LOSs += [pix.low_LOS(), pix.LOS(), pix.up_LOS()]
+    for num, los in enumerate(sim_LOSs):
+        los.tag = 'LOS{:03d}'.format(num)
+        los.calc_atm_intersections(planet)
+        pix = pixels[num // 3]
+        if hasattr(pix, 'sub_solar_point'):
+            los.calc_SZA_along_los(planet, pix.sub_solar_point())
+        los.calc_radtran_steps(planet, lines, **radtran_opt)
+
+    obs = pixels[0].observation
+    centres, widths = obs.spectral_grid.grid, obs.bands.spectrum
+    n_grid = len(sp_gri.grid)
+    n_split = int(inputs.get('n_split', 1)) if isinstance(inputs, dict) else 1
+    chunk = int(mt.ceil(n_grid / float(max(n_split, 1))))
+    low = torch.zeros((len(sim_LOSs), len(centres)), dtype=torch.float64, device="cuda")
+    hi_res = dict()
+    for pt0 in range(0, n_grid, chunk):
+        npt = min(chunk, n_grid - pt0)
+        # neighbouring chunks share their boundary point so that the trapezoid rule of the
+        # instrument convolution sees every hi-res interval exactly once
+        ext = npt + (1 if pt0 + npt < n_grid else 0)
+        low += los_batch_radiances(sim_LOSs, sp_gri, planet, LUTS, lowres=(centres, widths),
+                                   pt0=pt0, n_pts=ext)
+    low = low.cpu().numpy()
+    radtrans_out = dict()
+    for i, los in enumerate(sim_LOSs):
+        radtrans_out[los.tag] = spcl.SpectralIntensity(low[i], obs.spectral_grid)
+    sims = [spcl.SpectralIntensity(low[3 * k:3 * k + 3].mean(axis=0), obs.spectral_grid)
+            for k in range(len(pixels))]
+    if isinstance(inputs, dict) and inputs.get('out_dir') and save_lowres:
+        with open(os.path.join(inputs['out_dir'], 'lowres_radtran_{}.pic'.format(nome_inv)), 'wb') as f:
+            pickle.dump([sims, radtrans_out], f, protocol=-1)
+    return sims, radtrans_out, dict()

@@ -228,3 +228,83 @@ def rect_cells(p_lo, p_hi, t_lo, t_hi, pres_step_log=1.0, temp_step=5.0):
 def fixed_cells():
     """The 5-cell check set of spect_main_Titan.py:212-213: T=175 K, P in 1e-3..10 hPa."""
     return [[p, 175.0] for p in (1e-3, 1e-2, 0.1, 1.0, 10.0)]
+
+
+# ---------------------------------------------------------------------------------------------
+# object-level synthetic inputs for the spect_classes / spect_main_module API
+# ---------------------------------------------------------------------------------------------
+def level_strings(n_levels):
+    """HITRAN-like global-quanta strings 'v1 v2 v3 v4 sym', one per synthetic level."""
+    return ['%d %d 0 0 1A1' % (i // 4, i % 4) for i in range(n_levels)]
+
+
+def spect_lines(tab, mol=6, iso=1):
+    """List of spect_classes.SpectLine from a line_table() dict; unlinked lines (up_set < 0) get
+    level strings that match no level of the synthetic isotopologue."""
+    from . import spect_classes as spcl
+    strings = level_strings(int(tab["n_sets"]))
+    out = []
+    for i in range(len(tab["freq"])):
+        u, l = int(tab["up_set"][i]), int(tab["lo_set"][i])
+        d = dict(Mol=mol, Iso=iso, Freq=float(tab["freq"][i]), Strength=float(tab["strength"][i]),
+                 A_coeff=float(tab["a_coeff"][i]), Air_broad=float(tab["air_broad"][i]),
+                 Self_broad=0.0, E_lower=float(tab["e_lower"][i]),
+                 T_dep_broad=float(tab["t_dep"][i]), P_shift=float(tab["p_shift"][i]),
+                 Up_lev_str=strings[u] if u >= 0 else '9 9 9 9 1A1',
+                 Lo_lev_str=strings[l] if l >= 0 else '9 9 9 8 1A1', Q_num_up='', Q_num_lo='',
+                 others='', g_up=float(tab["g_up"][i]), g_lo=float(tab["g_lo"][i]))
+        out.append(spcl.SpectLine(d))
+    return out
+
+
+def titan_planet(level_energies=None, n_bands=1, vmr=0.015, nonlte=True, sza_deg=60.0):
+    """sbm.Titan with the synthetic atmosphere, CH4 (iso 1) and, when nonlte, one vibrational
+    level per entry of level_energies carrying a vibrational-temperature profile."""
+    from . import spect_base_module as sbm
+    atm = titan_atmosphere(n_bands=max(n_bands, 1))
+    planet = sbm.Titan(1500.0)
+    if n_bands <= 1:
+        grid = sbm.AtmGrid('alt', atm["z"])
+        sel = lambda a: a[0]
+    else:
+        grid = sbm.AtmGrid(['lat', 'alt'], [atm["lat_edges"], atm["z"]])
+        sel = lambda a: a
+    prof = sbm.AtmProfile(grid, sel(atm["temp"]), 'temp', 'lin')
+    prof.add_profile(sel(atm["pres"]), 'pres', 'exp')
+    planet.add_atmosphere(prof)
+    ch4 = sbm.Molec(6, 'CH4')
+    im = ch4.add_iso(1, MM=CH4_MM, ratio=CH4_RATIO, LTE=not nonlte)
+    ch4.add_clim(sbm.AtmProfile(grid, np.full_like(sel(atm["temp"]), vmr), 'vmr', 'lin'))
+    if level_energies is not None:
+        tv = [vib_temperatures(atm["z"], atm["temp"][b], level_energies, sza_deg)
+              for b in range(max(n_bands, 1))]
+        profs = []
+        for i in range(len(level_energies)):
+            v = tv[0][i] if n_bands <= 1 else np.stack([t[i] for t in tv])
+            profs.append(sbm.AtmProfile(grid, v, 'vibtemp', 'lin') if nonlte else None)
+        im.add_levels(level_strings(len(level_energies)), level_energies, vibtemps=profs)
+        im.is_in_LTE = not nonlte
+    planet.add_gas(ch4)
+    return planet
+
+
+def vims_pixels(tangent_km, lat=10.0, lon=0.0, dist=1.e5, channels=None, widths=None,
+                units='cm_1'):
+    """sbm.VIMSPixel list looking at the limb at the given tangent altitudes, with an (empty)
+    observation that defines the instrument channels."""
+    from . import spect_base_module as sbm
+    from . import spect_classes as spcl
+    out = []
+    for ht in tangent_km:
+        obs = None
+        if channels is not None:
+            obs = spcl.SpectralIntensity(np.zeros(len(channels)), spcl.SpectralGrid(channels, units=units))
+            obs.bands = spcl.SpectralObject(np.asarray(widths, dtype=float), obs.spectral_grid)
+            obs.mask = np.ones(len(channels))
+            obs.noise = None
+        keys = ['sub_obs_lat', 'sub_obs_lon', 'dist', 'limb_tg_lat', 'limb_tg_lon', 'limb_tg_alt',
+                'limb_tg_sza', 'sub_solar_lat', 'sub_solar_lon', 'observation', 'pixel_rot']
+        # observer on the equatorial plane 90 deg away in longitude: the ray grazes the limb
+        vals = [lat, lon + 90.0, dist, lat, lon, float(ht), 60.0, 0.0, lon - 60.0, obs, 0.0]
+        out.append(sbm.VIMSPixel(keys, vals))
+    return out

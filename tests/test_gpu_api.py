@@ -1,0 +1,136 @@
+"""GPU tests of the reference-shaped Python API (spect_classes / spect_main_module /
+spect_base_module) against the oracle: the per-line path (calc_shapes_lines -> BuildCoeff ->
+sum_all_lines), the batched LUT builder, the coefficient assembly, the instrument convolution and
+the radtrans driver."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL_XS, TOL_RAD = 1e-6, 1e-5
+
+
+@pytest.fixture(scope="module")
+def world():
+    import torch
+    from spectrobot_b200 import engine, spect_base_module as sbm, spect_classes as spcl
+    from spectrobot_b200 import spect_main_module as smm, synthetic as S
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    tab = S.line_table(160, 2993.0, 3007.0, n_levels=5, seed=21, frac_unlinked=0.05)
+    lines = S.spect_lines(tab)
+    planet = S.titan_planet(tab["level_energies"])
+    sp = smm.prepare_spe_grid([2996.0, 3004.0]).spectral_grid
+    return dict(torch=torch, engine=engine, sbm=sbm, spcl=spcl, smm=smm, S=S, tab=tab,
+                lines=lines, planet=planet, sp=sp, im=planet.gases['CH4'].iso_1)
+
+
+def test_reference_shaped_cell_path_matches_batched_builder_and_oracle(world, oracle):
+    """calc_shapes_lines + SpectralGcoeff.BuildCoeff(preCalc_shapes=True) (the reference's
+    LutSet.add_PT path through humliv_bb/sum_all_lines) == LookUpTable.make == oracle."""
+    spcl, smm, S, im, sp = world["spcl"], world["smm"], world["S"], world["im"], world["sp"]
+    P, T = 0.02, 158.0
+    proc = spcl.calc_shapes_lines(sp, world["lines"], T, P, im)
+    assert len(proc) == int(np.sum(world["tab"]["up_set"] >= 0))
+    assert abs(proc[0].shape.integrate() - 1.0) < 2e-3           # "integral(shape)=1", spcl:1994
+    ref = oracle.gcoeff_cell(world["tab"], sp.grid, T, P, S.CH4_MM, 5)
+    lut = smm.LookUpTable(im, [2996.0, 3004.0], LTE=False)
+    lut.make(sp, world["lines"], [[P, T], [P, T + 5.0]])
+    g32 = lut.g32.cpu().numpy()
+    for s, lev in enumerate(im.levels):
+        st = smm.LutSet(6, 1, im.MM, level=getattr(im, lev))
+        set_ = st.add_PT(sp, proc, P, T, keep_memory=True)
+        for k, ct in enumerate(spcl.CTYPES):
+            got = set_[ct].spectrum
+            if np.max(np.abs(ref[s, k])) == 0.0:
+                assert np.all(got == 0.0)
+                continue
+            assert rel_err(got, ref[s, k]) < TOL_XS, (lev, ct)
+            assert rel_err(g32[0, s, k], ref[s, k].astype(np.float32)) < 2e-7, (lev, ct)
+
+
+def test_make_abscoeff_LUTS_fast_matches_literal_restatement(world, oracle):
+    smm, spcl, im, sp = world["smm"], world["spcl"], world["im"], world["sp"]
+    PT = [[p, float(t)] for p in (1e-3, 1e-2, 1e-1) for t in (150., 155., 160., 165.)]
+    lut = smm.LookUpTable(im, [2996.0, 3004.0], LTE=False)
+    lut.make(sp, world["lines"], PT)
+    Temps, Press = [152.3, 158.8, 163.0], [5e-4, 3e-3, 0.04]
+    tv = np.array([[t + 3.0 * s for t in Temps] for s in range(5)])
+    for s, lev in enumerate(im.levels):
+        getattr(im, lev).local_vibtemp = list(tv[s])
+    allL = {(im.mol_name, im.iso): lut}
+    a, e = smm.make_abscoeff_LUTS_fast(sp, im, Temps, Press, LTE=False, allLUTs=allL)
+    olut = dict(g32=lut.g32.cpu().numpy(), pt=np.array(PT), level_energy=im.level_energies(),
+                mol=6, iso=1, lte_unidentified=False)
+    ra, re = oracle.make_abscoeff_LUTS_fast(olut, Temps, Press, tvib=tv)
+    for k in range(3):
+        assert rel_err(a[k].spectrum, ra[k]) < 1e-9
+        assert rel_err(e[k].spectrum, re[k]) < 1e-9
+    # the host LutSet.calculate path gives the same interpolated G coefficients
+    Gco = lut.sets['lev_00'].calculate(Press[1], Temps[1])
+    assert Gco['sp_emission'] is None                  # level 0 is never an upper level
+    sets = [olut["g32"][c, 0, 2].astype(float) for c in range(len(PT))]
+    assert np.array_equal(Gco['absorption'].spectrum,
+                          oracle.LutSet_calculate(PT, sets, Press[1], Temps[1]))
+
+
+def test_convolve_lowres_matches_reference_formula(world, oracle):
+    eng, spcl = world["engine"], world["spcl"]
+    rng = np.random.default_rng(9)
+    x = np.sort(np.concatenate([np.arange(3000.0, 3010.0, 5e-4), rng.uniform(3000.0, 3010.0, 500)]))
+    y = rng.uniform(0.0, 1.0, (3, len(x))) * np.exp(-((x - 3004.0) / 2.0) ** 2)
+    centres = np.array([2990.0, 3000.2, 3003.0, 3005.5, 3009.9, 3010.0 + 5e-4 * 0.4])
+    widths = np.array([0.5, 0.3, 0.8, 0.05, 0.4, 1e-5])
+    got = eng.convolve_lowres_host(x, y, centres, widths)
+    for s in range(3):
+        ref = oracle.convolve_to_grid_from_irregular(x, y[s], centres, widths)
+        assert got[s, 0] == 0.0 and ref[0] == 0.0               # no hi-res point in the window
+        assert rel_err(got[s], ref, floor_rel=1e-12) < 1e-12
+    so = spcl.SpectralIntensity(y[0], spcl.SpectralGrid(x, units='cm_1'))
+    obs = spcl.SpectralIntensity(np.zeros(6), spcl.SpectralGrid(centres, units='cm_1'))
+    low = so.hires_to_lowres(obs, spectral_widths=list(widths))
+    assert np.array_equal(low.spectrum, got[0])
+
+
+def test_radtrans_driver_matches_oracle_pipeline(world, oracle):
+    """smm.radtrans: pixels -> 3 LOS -> Curtis-Godson steps -> batched GPU radiances in two
+    wavenumber chunks -> low-res channels; checked against the oracle run on the same step tables
+    followed by the literal convolution."""
+    smm, S, planet, sp, sbm = world["smm"], world["S"], world["planet"], world["sp"], world["sbm"]
+    centres = np.linspace(2997.0, 3003.0, 7)
+    widths = np.full(7, 0.6)
+    pixels = S.vims_pixels([450.0, 700.0], channels=centres, widths=widths)
+    inputs = dict(n_split=2, cart_LUTS=None, out_dir=None, n_threads=8)
+    LUTopt = dict(pres_step_log=1.0, temp_step=5.0)
+    sims, rt, single = smm.radtrans(inputs, planet, world["lines"], pixels, sp_gri=sp,
+                                    radtran_opt=dict(max_T_variation=5., max_Plog_variation=1.),
+                                    LUTopt=LUTopt)
+    assert len(sims) == 2 and len(rt) == 6 and single == {}
+    # oracle: rebuild the same LOS, steps and LUT cells; hi-res on the CPU, then convolve
+    pix = sorted(pixels, key=lambda p: p.limb_tg_alt)
+    loss = []
+    for p in pix:
+        loss += [p.low_LOS(), p.LOS(), p.up_LOS()]
+    for los in loss:
+        los.calc_atm_intersections(planet)
+        los.calc_radtran_steps(planet, None, max_T_variation=5., max_Plog_variation=1.)
+    gi, steps = smm.los_step_tables(loss, planet)
+    max_p = max(planet.atmosphere.calc(p.low_LOS().get_tangent_point(), 'pres') for p in pix)
+    PT = smm.calc_PT_couples_atmosphere(world["lines"], list(planet.gases.values()),
+                                        planet.atmosphere, max_pres=max_p, **LUTopt)
+    lut = smm.LookUpTable(world["im"], [2996.0, 3004.0], LTE=False)
+    lut.make(sp, world["lines"], PT)
+    olut = dict(g32=lut.g32.cpu().numpy(), pt=np.array(PT),
+                level_energy=world["im"].level_energies(), mol=6, iso=1,
+                iso_ratio=S.CH4_RATIO, lte_unidentified=False)
+    hi = oracle.los_rt([olut], steps.n_steps, steps.temp, steps.pres, steps.column, steps.tvib)
+    assert hi.max() > 0
+    for i, los in enumerate(loss):
+        ref = oracle.convolve_to_grid_from_irregular(sp.grid, hi[i], centres, widths)
+        got = rt['LOS%03d' % i].spectrum
+        assert rel_err(got, ref, floor_rel=1e-9) < TOL_RAD, i
+    assert np.allclose(sims[0].spectrum, np.mean([rt['LOS%03d' % i].spectrum for i in range(3)], axis=0))
+    # single-LOS reference-shaped call gives the same hi-res spectrum as the batch
+    one = loss[1].radtran_fast(sp, planet, LUTS={(world["im"].mol_name, 1): lut})
+    assert rel_err(one[0].spectrum, hi[1]) < TOL_RAD
