@@ -297,30 +297,19 @@ def run_ours(args):
     del cell_buf
 
     # ---- K2: LUT build (cells sharded over ranks, all_gather) --------------------------------
-    my_cells = list(range(rank, n_cells, world))
+    from spectrobot_b200 import parallel
+    my_cells = parallel.shard_cells(n_cells, rank, world)
     g32 = torch.empty((n_cells, N_LEVELS, 3, n_grid), dtype=torch.float32, device="cuda")
     barrier()
     t0 = time.perf_counter()
     ev0.record()
     if my_cells:
-        mine = ls.gcoeff_cells_f32([cells[c] for c in my_cells])
+        g32[my_cells] = ls.gcoeff_cells_f32([cells[c] for c in my_cells])
     ev1.record()
     torch.cuda.synchronize()
     build_dev_s = ev0.elapsed_time(ev1) * 1e-3
-    if world > 1:
-        # cells are independent: the only exchange is the final gather of the LUT (NCCL)
-        for src in range(world):
-            idx = list(range(src, n_cells, world))
-            if not idx:
-                continue
-            buf = mine if src == rank else torch.empty((len(idx), N_LEVELS, 3, n_grid),
-                                                        dtype=torch.float32, device="cuda")
-            dist.broadcast(buf, src=src)
-            g32[idx] = buf
-            del buf
-    else:
-        g32[my_cells] = mine
-    del mine
+    # cells are independent: the only exchange is the final gather of the LUT (NCCL broadcasts)
+    parallel.gather_lut(g32, n_cells, rank, world)
     barrier()
     build_wall_s = max_over_ranks(time.perf_counter() - t0)
     lut_build = {"metric": "CH4 LUT build time", "value": build_wall_s, "unit": "s",

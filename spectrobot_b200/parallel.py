@@ -1,0 +1,124 @@
+"""Multi-GPU partitioning of the hot path: one process per GPU, `torch.distributed` for the
+plumbing (NCCL on the GPUs; the same code runs on gloo/CPU tensors in the tests).
+
+The path shards where the reference itself fans out over processes:
+
+  LUT cells    independent (`for [Pres,Temp] in PTcouples`, spect_main_module.py:753) -> round-robin
+               over ranks, no collective on the data path, one gather of the float32 LUT at the end
+               if every rank needs the whole table (gather_lut);
+  LOS batch    independent (one forked process per LOS in the reference, spect_main_module.py:
+               3202-3221) -> contiguous blocks per rank, gather of the (low-res) spectra (gather_rows);
+  one huge line list (config 5)  the sum over lines is linear (lineshape.f:17-23) -> lines split by
+               index, all_reduce(SUM, fp64) of the partial [set][3][n_grid] spectra (allreduce_spectra).
+"""
+import os
+
+import numpy as np
+
+
+def world():
+    """(rank, world_size, local_rank) from the torchrun environment (1 process: 0, 1, 0)."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def init(backend=None):
+    """Initialise torch.distributed from the environment (no-op for a single process)."""
+    import torch
+    import torch.distributed as dist
+    rank, n, local = world()
+    if n == 1 or dist.is_initialized():
+        return rank, n, local
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+        from . import engine
+        engine.lib().sr_set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group(backend)
+    return rank, n, local
+
+
+def shard_cells(n_cells, rank, n_ranks):
+    """Indices of the (P,T) cells rank builds: round-robin, so that the pressure ladder (and with it
+    the slightly different per-cell cost) is spread evenly."""
+    return list(range(rank, n_cells, n_ranks))
+
+
+def shard_range(n, rank, n_ranks):
+    """Contiguous [begin, end) block of n items for rank (sizes differ by at most one)."""
+    base, extra = divmod(n, n_ranks)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def shard_los(n_los, rank, n_ranks):
+    return shard_range(n_los, rank, n_ranks)
+
+
+def shard_lines(n_lines, rank, n_ranks):
+    """Lines are split by index; with a frequency-sorted list every rank gets a contiguous
+    wavenumber interval, but the result does not depend on that (the sum is linear)."""
+    return shard_range(n_lines, rank, n_ranks)
+
+
+def gather_lut(g32, n_cells, rank, n_ranks):
+    """Complete a LUT tensor [n_cells, ...] in which every rank has filled shard_cells(rank):
+    the owner of each block broadcasts it (every cell crosses NVLink once per receiver)."""
+    import torch.distributed as dist
+    if n_ranks == 1:
+        return g32
+    for src in range(n_ranks):
+        idx = shard_cells(n_cells, src, n_ranks)
+        if not idx:
+            continue
+        buf = g32[idx].contiguous()
+        dist.broadcast(buf, src=src)
+        if src != rank:
+            g32[idx] = buf
+    return g32
+
+
+def gather_rows(local, n_total, rank, n_ranks):
+    """All ranks' row blocks (shard_range partition of n_total rows) -> [n_total, ...] on every
+    rank."""
+    import torch
+    import torch.distributed as dist
+    if n_ranks == 1:
+        return local
+    sizes = [shard_range(n_total, r, n_ranks) for r in range(n_ranks)]
+    nmax = max(e - b for b, e in sizes)
+    pad = torch.zeros((nmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(n_ranks)]
+    dist.all_gather(parts, pad)
+    return torch.cat([p[:e - b] for p, (b, e) in zip(parts, sizes)], dim=0)
+
+
+def allreduce_spectra(t):
+    """In-place sum of partial cross-section spectra over the ranks (line-sharded K1)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def subset_lines(tab, begin, end):
+    """Rows [begin, end) of a line-table dict (see spect_classes.line_table / synthetic)."""
+    n = len(tab["freq"])
+    return {k: (v[begin:end] if isinstance(v, np.ndarray) and v.shape[:1] == (n,) else v)
+            for k, v in tab.items()}
+
+
+def gcoeff_cells_line_sharded(tab, grid, MM, n_sets, PTcouples):
+    """Cross-sections of a line list too large for one GPU's time budget: every rank evaluates its
+    share of the lines for ALL cells, then one all_reduce sums the partial spectra."""
+    from . import engine
+    rank, n, _ = world()
+    b, e = shard_lines(len(tab["freq"]), rank, n)
+    ls = engine.LineSet(subset_lines(tab, b, e), grid, MM, n_sets)
+    out = ls.gcoeff_cells(PTcouples)
+    ls.close()
+    return allreduce_spectra(out)

@@ -1,0 +1,83 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU partitioning logic (spectrobot_b200/parallel.py):
+cell sharding + LUT gather, LOS sharding + row gather, line sharding + all_reduce."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from spectrobot_b200 import parallel
+
+
+def test_shard_arithmetic():
+    for n in (0, 1, 7, 273, 30000):
+        for w in (1, 2, 3, 8):
+            cells = sorted(sum((parallel.shard_cells(n, r, w) for r in range(w)), []))
+            assert cells == list(range(n))
+            rng = [parallel.shard_range(n, r, w) for r in range(w)]
+            assert rng[0][0] == 0 and rng[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(rng[:-1], rng[1:]))
+            sizes = [e - b for b, e in rng]
+            assert max(sizes) - min(sizes) <= 1
+    tab = dict(freq=np.arange(10.0), up_set=np.arange(10), n_sets=3, level_energies=np.zeros(3))
+    sub = parallel.subset_lines(tab, 2, 5)
+    assert list(sub["freq"]) == [2.0, 3.0, 4.0] and sub["n_sets"] == 3 and len(sub["level_energies"]) == 3
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, n, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(n), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=n)
+    try:
+        r, w, _ = parallel.world()
+        assert (r, w) == (rank, n)
+        # LUT cells: every rank fills its own cells, gather completes the table
+        n_cells = 7
+        full = torch.arange(n_cells * 6, dtype=torch.float32).reshape(n_cells, 2, 3)
+        mine = torch.zeros_like(full)
+        idx = parallel.shard_cells(n_cells, rank, n)
+        mine[idx] = full[idx]
+        got = parallel.gather_lut(mine, n_cells, rank, n)
+        ok_lut = bool(torch.equal(got, full))
+        # LOS rows: contiguous blocks, unequal sizes
+        n_los = 5
+        rows = torch.arange(n_los * 4, dtype=torch.float64).reshape(n_los, 4)
+        b, e = parallel.shard_los(n_los, rank, n)
+        ok_rows = bool(torch.equal(parallel.gather_rows(rows[b:e].clone(), n_los, rank, n), rows))
+        # line-sharded partial spectra: the sum over ranks equals the full sum
+        rng = np.random.default_rng(3)
+        contrib = torch.as_tensor(rng.uniform(size=(11, 2, 3, 16)))
+        b, e = parallel.shard_lines(11, rank, n)
+        part = contrib[b:e].sum(dim=0)
+        parallel.allreduce_spectra(part)
+        ok_sum = bool(torch.allclose(part, contrib.sum(dim=0), rtol=1e-14, atol=0))
+        q.put((rank, ok_lut, ok_rows, ok_sum))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world_size_2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1]
+    for r in res:
+        assert r[1] and r[2] and r[3], r
