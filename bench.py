@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--los-block", type=int, default=36, help="LOS per rank in the K3 block")
-    ap.add_argument("--e2e-los", type=int, default=12, help="LOS per host call of the e2e leg")
+    ap.add_argument("--e2e-los", type=int, default=36, help="LOS per host call of the e2e leg")
     ap.add_argument("--lines", type=int, default=N_LINES)
     ap.add_argument("--small", action="store_true", help="tiny sizes (CI / debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -233,6 +233,9 @@ def workload_config(args, wl):
 # our arm
 # --------------------------------------------------------------------------------------------
 def run_ours(args):
+    # only the JSON line may go to stdout (NCCL prints its version banner there)
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from spectrobot_b200 import engine
@@ -405,7 +408,7 @@ def run_ours(args):
         line["voigt"]["cpu_baseline"] = {"value": ve, "unit": "evals/s", "cores": threads,
                                          "kind": "port", "sample": vdesc}
     if rank == 0:
-        print(json.dumps(line))
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

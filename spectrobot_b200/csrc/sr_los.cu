@@ -281,6 +281,131 @@ __global__ void __launch_bounds__(1024) k_los_fused(LosArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3a as a grouped, register-tiled product (v2).  The (LOS, step) pairs of a batch are grouped by
+// the LUT cells their interpolation uses ("quad": up to 4 cells per gas).  One CTA takes PB pairs
+// of one quad and a tile of grid points: every needed LUT row is read (and converted from
+// float32) ONCE per CTA and used for all PB pairs, with the PB combined weights of the row
+// broadcast from shared memory -> PB*PPT FP64 FMAs per PPT loads + PB/2 LDS.128.
+//   tau[pair][p] = sum_rows w_abs/ind[pair][row] * G[row][p],  J[pair][p] = sum_rows w_sp * G
+// Output goes to the [los][step][point] layer arrays that k_los_layers then streams.
+// ---------------------------------------------------------------------------------------------
+constexpr int GEMM_PB = 8;        // pairs per CTA
+constexpr int GEMM_NT = 256;
+constexpr int GEMM_MAXJ = 8 * 4 * 3 * 16;   // rows of one quad program (capacity check on the host)
+
+struct ProgEntry {                // one LUT row of a quad program
+    long long roff;               // address of the row's first element (float*) on the device
+    int gas;                      // which LUT
+    int widx;                     // set*4 + cell slot: index into the pair's weight block
+    int neg;                      // 1: subtract (ind_emission row), 0: add
+    int pad;
+};
+
+struct GemmArgs {
+    const ProgEntry* prog;        // [n_groups][max_j]
+    const int* grp_ntau;          // [n_groups] rows feeding tau (abs, ind); they come first
+    const int* grp_ntot;          // [n_groups] all rows (tau rows, then sp_emission rows)
+    const int* chunk_grp;         // [n_chunks]
+    const int* chunk_pair;        // [n_chunks][PB] pair index los*n_steps_max+step, -1 = padding
+    const double* W;              // [n_gas][n_los*n_steps_max][n_sets_max*4]
+    long n_pairs_tot;             // n_los*n_steps_max
+    int n_sets_max, max_j;
+    long pt0, n_pts;
+    double* tau_out;              // [n_los*n_steps_max][n_pts]
+    double* src_out;
+    int mode;                     // 0: src = S = J/tau, 1: src = J
+};
+
+template <int PPT>
+__global__ void __launch_bounds__(GEMM_NT, 2) k_los_gemm(GemmArgs a) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    double* wj = reinterpret_cast<double*>(gsm);                          // [max_j][PB]
+    long long* roff = reinterpret_cast<long long*>(wj + (size_t)a.max_j * GEMM_PB);   // [max_j]
+    __shared__ int pair_s[GEMM_PB];
+    const int chunk = blockIdx.y, tid = threadIdx.x;
+    const int grp = a.chunk_grp[chunk];
+    const int n_tau = a.grp_ntau[grp], n_tot = a.grp_ntot[grp];
+    const ProgEntry* __restrict__ prog = a.prog + (size_t)grp * a.max_j;
+    if (tid < GEMM_PB) pair_s[tid] = a.chunk_pair[chunk * GEMM_PB + tid];
+    __syncthreads();
+    const size_t wstride = (size_t)a.n_sets_max * 4;
+    for (int e = tid; e < n_tot * GEMM_PB; e += GEMM_NT) {
+        const int j = e / GEMM_PB, i = e % GEMM_PB;
+        const ProgEntry pe = prog[j];
+        const int pr = pair_s[i];
+        double w = 0.0;
+        if (pr >= 0) w = a.W[((size_t)pe.gas * a.n_pairs_tot + pr) * wstride + pe.widx];
+        wj[j * GEMM_PB + i] = pe.neg ? -w : w;
+        if (i == 0) roff[j] = pe.roff;
+    }
+    __syncthreads();
+    const long p_first = (long)blockIdx.x * (GEMM_NT * PPT) + tid;
+    bool ok[PPT];
+#pragma unroll
+    for (int q = 0; q < PPT; q++) ok[q] = p_first + q * GEMM_NT < a.n_pts;
+    double tau[GEMM_PB][PPT], J[GEMM_PB][PPT];
+#pragma unroll
+    for (int i = 0; i < GEMM_PB; i++)
+#pragma unroll
+        for (int q = 0; q < PPT; q++) tau[i][q] = J[i][q] = 0.0;
+    const long pbase = a.pt0 + p_first;
+    // rows j0..j1 into acc, U rows per batch, the next batch's loads issued before this batch's
+    // FMAs (software pipelining: 2*U*PPT loads in flight per thread)
+    auto rows = [&](int j0, int j1, double (&acc)[GEMM_PB][PPT]) {
+        constexpr int U = 4;
+        float g[U][PPT], gn[U][PPT];
+        auto load = [&](int j, float (&dst)[U][PPT]) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const bool live = j + u < j1;
+                const float* __restrict__ r =
+                    reinterpret_cast<const float*>(roff[live ? j + u : j0]) + pbase;
+#pragma unroll
+                for (int q = 0; q < PPT; q++)
+                    dst[u][q] = (live && ok[q]) ? __ldg(r + q * GEMM_NT) : 0.0f;
+            }
+        };
+        if (j0 < j1) load(j0, gn);
+        for (int j = j0; j < j1; j += U) {
+#pragma unroll
+            for (int u = 0; u < U; u++)
+#pragma unroll
+                for (int q = 0; q < PPT; q++) g[u][q] = gn[u][q];
+            if (j + U < j1) load(j + U, gn);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (j + u >= j1) break;
+                double gd[PPT];
+#pragma unroll
+                for (int q = 0; q < PPT; q++) gd[q] = (double)g[u][q];
+                const double* __restrict__ w = wj + (j + u) * GEMM_PB;
+#pragma unroll
+                for (int i = 0; i < GEMM_PB; i++) {
+                    const double wi = w[i];
+#pragma unroll
+                    for (int q = 0; q < PPT; q++) acc[i][q] = fma(wi, gd[q], acc[i][q]);
+                }
+            }
+        }
+    };
+    rows(0, n_tau, tau);
+    rows(n_tau, n_tot, J);
+#pragma unroll
+    for (int i = 0; i < GEMM_PB; i++) {
+        const int pr = pair_s[i];
+        if (pr < 0) continue;
+        const size_t o = (size_t)pr * a.n_pts + p_first;
+#pragma unroll
+        for (int q = 0; q < PPT; q++) {
+            if (!ok[q]) continue;
+            __stcs(a.tau_out + o + q * GEMM_NT, tau[i][q]);
+            const double sv = a.mode ? J[i][q] : (tau[i][q] == 0.0 ? 0.0 : J[i][q] / tau[i][q]);
+            __stcs(a.src_out + o + q * GEMM_NT, sv);
+        }
+    }
+}
+
 // K3: I <- I exp(-tau) + S (1 - exp(-tau)) over materialised layers; pure HBM streaming.
 // Each thread owns PPT points (stride 256, so every warp load is one coalesced 256-byte row
 // segment for any n_pts parity) and keeps UNROLL steps x PPT points x 2 arrays of loads in flight.
@@ -290,7 +415,8 @@ __global__ void __launch_bounds__(256) k_los_layers(const double* __restrict__ t
                                                     const int* __restrict__ n_steps,
                                                     int n_steps_max, long n_pts,
                                                     const double* __restrict__ i0, int solo,
-                                                    double* __restrict__ rad) {
+                                                    double* __restrict__ rad, int src_is_j,
+                                                    long io_stride, long io_off) {
     const int l = blockIdx.y;
     const long p0 = (long)blockIdx.x * (256 * PPT) + threadIdx.x;
     if (p0 >= n_pts) return;
@@ -299,7 +425,7 @@ __global__ void __launch_bounds__(256) k_los_layers(const double* __restrict__ t
 #pragma unroll
     for (int i = 0; i < PPT; i++) {
         ok[i] = p0 + i * 256 < n_pts;
-        I[i] = (i0 && ok[i]) ? i0[(size_t)l * n_pts + p0 + i * 256] : 0.0;
+        I[i] = (i0 && ok[i]) ? i0[(size_t)l * io_stride + io_off + p0 + i * 256] : 0.0;
     }
     const int ns = n_steps[l];
     const double* __restrict__ tp = tau + (size_t)l * n_steps_max * n_pts + p0;
@@ -307,7 +433,12 @@ __global__ void __launch_bounds__(256) k_los_layers(const double* __restrict__ t
     auto update = [&](int i, double t, double s) {
         double ex, em;
         srdev::exp_pair(-t, ex, em);
-        I[i] = solo ? I[i] * ex : fma(I[i], ex, -s * em);
+        if (src_is_j) {   // s = J: I <- I e^-tau + J phi(tau), phi = (1 - e^-tau)/tau
+            const double phi = (t == 0.0) ? 1.0 : -em / t;
+            I[i] = solo ? I[i] * ex : fma(I[i], ex, s * phi);
+        } else {
+            I[i] = solo ? I[i] * ex : fma(I[i], ex, -s * em);
+        }
     };
     int k = 0;
     for (; k + UNROLL <= ns; k += UNROLL) {
@@ -332,7 +463,7 @@ __global__ void __launch_bounds__(256) k_los_layers(const double* __restrict__ t
                               __ldcs(sp + (size_t)k * n_pts + i * 256));
 #pragma unroll
     for (int i = 0; i < PPT; i++)
-        if (ok[i]) __stcs(rad + (size_t)l * n_pts + p0 + i * 256, I[i]);
+        if (ok[i]) __stcs(rad + (size_t)l * io_stride + io_off + p0 + i * 256, I[i]);
 }
 
 }  // namespace
@@ -352,6 +483,9 @@ struct sr_lut {
     sr::DevBuf<int> dmap, drowmask, drowlist;
     int n_rows[3] = {0, 0, 0};
     sr::DevBuf<double> ws_rad, ws_i0;   // workspace of the host-buffer entry point
+    sr::DevBuf<double> ws_tau, ws_src;  // layer scratch of the grouped K3a -> K3 path
+    sr::DevBuf<char> g_prog;            // quad row programs / chunk tables of the current call
+    sr::DevBuf<int> g_ntau, g_ntot, g_cgrp, g_cpair;
     // per-call scratch (owned by the first LUT of a call)
     sr::DevBuf<int> cells, nsteps, flags;
     sr::DevBuf<double> W, temp, pres, column, tvib;
@@ -585,12 +719,11 @@ int sr_lut_weights(const double* pt_host, int n_cells, double pres, double temp,
     return SR_OK;
 }
 
-int sr_los_rt_layers_dev(const double* tau, const double* src, const int* n_steps, int n_los,
+static int layers_launch(const double* tau, const double* src, const int* n_steps, int n_los,
                          int n_steps_max, long n_pts, const double* i0, int solo_absorption,
-                         double* rad, void* stream) {
-    if (!tau || !src || !n_steps || !rad || n_los < 1 || n_steps_max < 1 || n_pts < 1)
-        return sr::fail(SR_ERR_ARG, "sr_los_rt_layers_dev: bad argument");
-    cudaStream_t st = (cudaStream_t)stream;
+                         double* rad, cudaStream_t st, int src_is_j, long io_stride = -1,
+                         long io_off = 0) {
+    if (io_stride < 0) io_stride = n_pts;   // rad / i0 rows: [n_los][io_stride], window at io_off
     // measured on B200 (tools/tune.py): (PPT=1, UNROLL=4) at 38 registers streams at the
     // measured copy bandwidth; wider variants lose occupancy
     int cfg = 5;
@@ -599,7 +732,7 @@ int sr_los_rt_layers_dev(const double* tau, const double* src, const int* n_step
     {                                                                                          \
         dim3 grid((unsigned)((n_pts + 256 * PPT - 1) / (256 * PPT)), n_los);                   \
         SR_LAUNCH((k_los_layers<PPT, UNROLL>), grid, 256, 0, st, tau, src, n_steps,            \
-                  n_steps_max, n_pts, i0, solo_absorption, rad);                               \
+                  n_steps_max, n_pts, i0, solo_absorption, rad, src_is_j, io_stride, io_off);  \
     }
     switch (cfg) {
         case 1: SR_K3_LAUNCH(1, 8) break;
@@ -613,6 +746,126 @@ int sr_los_rt_layers_dev(const double* tau, const double* src, const int* n_step
     return SR_OK;
 }
 
+int sr_los_rt_layers_dev(const double* tau, const double* src, const int* n_steps, int n_los,
+                         int n_steps_max, long n_pts, const double* i0, int solo_absorption,
+                         double* rad, void* stream) {
+    if (!tau || !src || !n_steps || !rad || n_los < 1 || n_steps_max < 1 || n_pts < 1)
+        return sr::fail(SR_ERR_ARG, "sr_los_rt_layers_dev: bad argument");
+    return layers_launch(tau, src, n_steps, n_los, n_steps_max, n_pts, i0, solo_absorption, rad,
+                         (cudaStream_t)stream, 0);
+}
+
+// Host side of the grouped K3a: choose the LUT cells of every (LOS, step) pair with the
+// reference's rule (same code as sr_lut_weights), group the pairs by their cells, build one row
+// program per group and PB-pair chunks.
+struct GemmPlan {
+    std::vector<ProgEntry> prog;
+    std::vector<int> ntau, ntot, chunk_grp, chunk_pair;
+    int max_j = 0, n_groups = 0, n_chunks = 0;
+};
+
+static int cells_of(const sr_lut* L, double pres, double temp, int cell[4]) {
+    for (int i = 0; i < 4; i++) cell[i] = -1;
+    const std::vector<double>&Ps = L->Ps, &Ts = L->Ts;
+    const int nT = (int)Ts.size();
+    if (nT < 2) return lflags_to_status(LFLAG_NO_CELL);
+    if (pres <= Ps.front()) {
+        int ta, tb;
+        host_nearest_two(Ts, temp, ta, tb);
+        cell[0] = L->cellmap[ta];
+        cell[1] = L->cellmap[tb];
+        if (cell[0] < 0 || cell[1] < 0) return lflags_to_status(LFLAG_NO_CELL);
+    } else if (pres <= Ps.back()) {
+        if (Ps.size() < 2) return lflags_to_status(LFLAG_NO_CELL);
+        int p1, p2, t1, t2;
+        host_nearest_two(Ps, pres, p1, p2);
+        host_nearest_two(Ts, temp, t1, t2);
+        cell[0] = L->cellmap[(size_t)p1 * nT + t1];
+        cell[1] = L->cellmap[(size_t)p1 * nT + t2];
+        cell[2] = L->cellmap[(size_t)p2 * nT + t1];
+        cell[3] = L->cellmap[(size_t)p2 * nT + t2];
+        for (int i = 0; i < 4; i++)
+            if (cell[i] < 0) return lflags_to_status(LFLAG_NO_CELL);
+    } else {
+        return lflags_to_status(LFLAG_EXTRAP_P);
+    }
+    return SR_OK;
+}
+
+static int build_plan(sr_lut* const* luts, const sr_los_steps* S, GemmPlan& P) {
+    const int n_gas = S->n_gas;
+    const size_t nmax = (size_t)S->n_steps_max;
+    struct Key { std::vector<int> c; int pair; };
+    std::vector<Key> keys;
+    for (int l = 0; l < S->n_los; l++)
+        for (int k = 0; k < S->n_steps[l]; k++) {
+            Key key;
+            key.pair = (int)(l * nmax + k);
+            key.c.resize((size_t)n_gas * 4);
+            for (int m = 0; m < n_gas; m++) {
+                int rc = cells_of(luts[m], S->pres[l * nmax + k], S->temp[l * nmax + k],
+                                  key.c.data() + 4 * m);
+                if (rc) return rc;
+            }
+            keys.push_back(std::move(key));
+        }
+    std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.c < b.c; });
+    // row lists per gas and ctype (all-zero spectra are skipped like the reference's None entries)
+    std::vector<std::vector<int>> rl((size_t)n_gas * 3);
+    for (int m = 0; m < n_gas; m++) {
+        std::vector<int> list(3 * (size_t)luts[m]->n_sets);
+        if (cudaMemcpy(list.data(), luts[m]->drowlist.p, list.size() * sizeof(int),
+                       cudaMemcpyDeviceToHost) != cudaSuccess)
+            return sr::fail(SR_ERR_CUDA, "LOS: cannot read the LUT row lists");
+        for (int ct = 0; ct < 3; ct++)
+            rl[(size_t)m * 3 + ct].assign(list.begin() + (size_t)ct * luts[m]->n_sets,
+                                          list.begin() + (size_t)ct * luts[m]->n_sets + luts[m]->n_rows[ct]);
+    }
+    int max_j = 0;
+    for (int m = 0; m < n_gas; m++)
+        max_j += 4 * (luts[m]->n_rows[0] + luts[m]->n_rows[1] + luts[m]->n_rows[2]);
+    P.max_j = std::max(max_j, 1);
+    size_t i = 0;
+    while (i < keys.size()) {
+        size_t e = i;
+        while (e < keys.size() && keys[e].c == keys[i].c) e++;
+        const int grp = P.n_groups++;
+        P.prog.resize((size_t)P.n_groups * P.max_j);
+        ProgEntry* pr = P.prog.data() + (size_t)grp * P.max_j;
+        int nj = 0;
+        for (int pass = 0; pass < 2; pass++) {          // pass 0: tau rows (abs +, ind -); 1: J rows
+            for (int m = 0; m < n_gas; m++) {
+                const sr_lut* L = luts[m];
+                for (int c = 0; c < 4; c++) {
+                    const int cell = keys[i].c[(size_t)m * 4 + c];
+                    if (cell < 0) continue;
+                    for (int ct = (pass == 0 ? 1 : 0); ct <= (pass == 0 ? 2 : 0); ct++)
+                        for (int s : rl[(size_t)m * 3 + ct]) {
+                            ProgEntry pe;
+                            pe.roff = (long long)(L->g32 + (((size_t)cell * L->n_sets + s) * 3 + ct) *
+                                                               (size_t)L->n_grid);
+                            pe.gas = m;
+                            pe.widx = s * 4 + c;
+                            pe.neg = (ct == 1);
+                            pe.pad = 0;
+                            pr[nj++] = pe;
+                        }
+                }
+            }
+            if (pass == 0) P.ntau.push_back(nj);
+        }
+        P.ntot.push_back(nj);
+        for (size_t q = i; q < e; q += GEMM_PB) {
+            P.chunk_grp.push_back(grp);
+            for (int t = 0; t < GEMM_PB; t++)
+                P.chunk_pair.push_back(q + t < e ? keys[q + t].pair : -1);
+            P.n_chunks++;
+        }
+        i = e;
+    }
+    return SR_OK;
+}
+
 static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
                       const double* i0_dev, int solo, double* rad_dev, double* tau_dev,
                       double* src_dev, cudaStream_t st, int emit_j = 0) {
@@ -621,18 +874,22 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
     if (rc) return rc;
     if (pt0 < 0 || n_pts < 1 || pt0 + n_pts > la.n_grid)
         return sr::fail(SR_ERR_ARG, "LOS: point range [%ld,%ld) outside the LUT grid", pt0, pt0 + n_pts);
-    la.pt0 = pt0;
-    la.n_pts = n_pts;
-    la.i0 = i0_dev;
-    la.rad = rad_dev;
-    la.tau_out = tau_dev;
-    la.src_out = src_dev;
-    la.solo_absorption = solo;
-    la.emit_j = emit_j;
-    int G = 2, ppt = 4;   // measured on B200 (tools/tune.py fused)
-    if (const char* e = getenv("SR_LOS_G")) G = std::max(1, std::min(4, atoi(e)));     // tuning aids
-    if (const char* e = getenv("SR_LOS_PPT")) ppt = atoi(e);
-    dim3 block(256, G);
+    sr_lut* L0 = luts[0];
+    int ver = 2;
+    if (const char* e = getenv("SR_LOS_VER")) ver = atoi(e);   // 1 = thread-per-point fused kernel
+    if (ver == 1) {
+        la.pt0 = pt0;
+        la.n_pts = n_pts;
+        la.i0 = i0_dev;
+        la.rad = rad_dev;
+        la.tau_out = tau_dev;
+        la.src_out = src_dev;
+        la.solo_absorption = solo;
+        la.emit_j = emit_j;
+        int G = 2, ppt = 4;   // measured on B200 (tools/tune.py fused)
+        if (const char* e = getenv("SR_LOS_G")) G = std::max(1, std::min(4, atoi(e)));
+        if (const char* e = getenv("SR_LOS_PPT")) ppt = atoi(e);
+        dim3 block(256, G);
 #define SR_FUSED(PPT)                                                                          \
     {                                                                                          \
         dim3 grid((unsigned)((steps->n_los + G - 1) / G),                                      \
@@ -640,8 +897,75 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         if (tau_dev) SR_LAUNCH((k_los_fused<PPT, true>), grid, block, 0, st, la);              \
         else SR_LAUNCH((k_los_fused<PPT, false>), grid, block, 0, st, la);                     \
     }
-    if (ppt == 1) SR_FUSED(1) else if (ppt == 4) SR_FUSED(4) else SR_FUSED(2)
+        if (ppt == 1) SR_FUSED(1) else if (ppt == 4) SR_FUSED(4) else SR_FUSED(2)
 #undef SR_FUSED
+        return SR_OK;
+    }
+    // ---- v2: grouped product into layer arrays, then the streaming recursion -----------------
+    GemmPlan P;
+    rc = build_plan(luts, steps, P);
+    if (rc) return rc;
+    if (P.n_chunks == 0) {   // no step at all: radiance = initial intensity
+        if (rad_dev) {
+            if (i0_dev) SR_CUDA(cudaMemcpyAsync(rad_dev, i0_dev, sizeof(double) * steps->n_los * n_pts,
+                                                cudaMemcpyDeviceToDevice, st));
+            else SR_CUDA(cudaMemsetAsync(rad_dev, 0, sizeof(double) * steps->n_los * n_pts, st));
+        }
+        return SR_OK;
+    }
+    if (P.max_j > GEMM_MAXJ)
+        return sr::fail(SR_ERR_LIMIT, "LOS: %d LUT rows per cell quad (limit %d)", P.max_j, GEMM_MAXJ);
+    SR_CUDA(L0->g_prog.upload(reinterpret_cast<const char*>(P.prog.data()),
+                              P.prog.size() * sizeof(ProgEntry), st));
+    SR_CUDA(L0->g_ntau.upload(P.ntau.data(), P.ntau.size(), st));
+    SR_CUDA(L0->g_ntot.upload(P.ntot.data(), P.ntot.size(), st));
+    SR_CUDA(L0->g_cgrp.upload(P.chunk_grp.data(), P.chunk_grp.size(), st));
+    SR_CUDA(L0->g_cpair.upload(P.chunk_pair.data(), P.chunk_pair.size(), st));
+    SR_CUDA(cudaStreamSynchronize(st));   // the plan vectors die with this frame
+    GemmArgs ga;
+    ga.prog = reinterpret_cast<const ProgEntry*>(L0->g_prog.p);
+    ga.grp_ntau = L0->g_ntau.p;
+    ga.grp_ntot = L0->g_ntot.p;
+    ga.chunk_grp = L0->g_cgrp.p;
+    ga.chunk_pair = L0->g_cpair.p;
+    ga.W = la.W;
+    ga.n_pairs_tot = (long)steps->n_los * steps->n_steps_max;
+    ga.n_sets_max = la.n_sets_max;
+    ga.max_j = P.max_j;
+    const size_t smem = (size_t)P.max_j * (GEMM_PB * sizeof(double) + sizeof(long long)) + 16;
+    constexpr int PPT = 2;
+    SR_CUDA(cudaFuncSetAttribute(k_los_gemm<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long n_pairs = (long)steps->n_los * steps->n_steps_max;
+    if (tau_dev) {   // materialise for the caller: [los][step][n_pts]
+        ga.pt0 = pt0;
+        ga.n_pts = n_pts;
+        ga.tau_out = tau_dev;
+        ga.src_out = src_dev;
+        ga.mode = emit_j;
+        dim3 grid((unsigned)((n_pts + GEMM_NT * PPT - 1) / (GEMM_NT * PPT)), (unsigned)P.n_chunks);
+        SR_LAUNCH((k_los_gemm<PPT>), grid, GEMM_NT, smem, st, ga);
+        return SR_OK;
+    }
+    // radiances: wavenumber chunks sized so that the layer scratch stays below ~6 GiB
+    long chunk_pts = (long)std::max<size_t>(((size_t)6 << 30) / ((size_t)n_pairs * 16), 4096);
+    if (const char* e = getenv("SR_LOS_CHUNK")) chunk_pts = std::max(256L, atol(e));
+    chunk_pts = std::min(chunk_pts, n_pts);
+    SR_CUDA(L0->ws_tau.ensure((size_t)n_pairs * chunk_pts));
+    SR_CUDA(L0->ws_src.ensure((size_t)n_pairs * chunk_pts));
+    for (long c0 = 0; c0 < n_pts; c0 += chunk_pts) {
+        const long np = std::min(chunk_pts, n_pts - c0);
+        ga.pt0 = pt0 + c0;
+        ga.n_pts = np;
+        ga.tau_out = L0->ws_tau.p;
+        ga.src_out = L0->ws_src.p;
+        ga.mode = 1;
+        dim3 grid((unsigned)((np + GEMM_NT * PPT - 1) / (GEMM_NT * PPT)), (unsigned)P.n_chunks);
+        SR_LAUNCH((k_los_gemm<PPT>), grid, GEMM_NT, smem, st, ga);
+        // radiances (and i0) rows have stride n_pts; this chunk is the window [c0, c0+np)
+        rc = layers_launch(L0->ws_tau.p, L0->ws_src.p, la.n_steps, steps->n_los,
+                           steps->n_steps_max, np, i0_dev, solo, rad_dev, st, 1, n_pts, c0);
+        if (rc) return rc;
+    }
     return SR_OK;
 }
 

@@ -42,7 +42,7 @@ def k1(n_lines=30000, n_lev=12, w0=2825.0, w1=3225.0):
                                                        ls.n_active * 13010 / (min(ms) * 1e-3)))
 
 
-def los(mode, n_los=8):
+def los(mode, n_los=int(os.environ.get("SR_PROF_NLOS", "8"))):
     w0, w1 = 2850.0, 3450.0
     g = S.spectral_grid(w0, w1)
     n_lev = 12
