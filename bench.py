@@ -47,7 +47,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--los-block", type=int, default=36, help="LOS per rank in the K3 block")
-    ap.add_argument("--e2e-los", type=int, default=36, help="LOS per host call of the e2e leg")
+    ap.add_argument("--e2e-los", type=int, default=360, help="LOS per host call of the e2e leg")
+    ap.add_argument("--fused-los", type=int, default=360,
+                    help="LOS per rank of the device-resident K3a+K3 leg")
     ap.add_argument("--lines", type=int, default=N_LINES)
     ap.add_argument("--small", action="store_true", help="tiny sizes (CI / debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -224,6 +226,7 @@ def workload_config(args, wl):
                                                            len(wl["grid"])),
             "n_levels": N_LEVELS, "n_lines": int(len(wl["lines"]["freq"])),
             "lut_cells": len(wl["cells"]), "los_per_rank": int(wl["st"]["temp"].shape[0]),
+            "e2e_los_per_call": int(args.e2e_los), "fused_los_per_rank": int(args.fused_los),
             "steps_per_los_mean": float(wl["st"]["n_steps"].mean()),
             "l2": "inputs larger than L2 (tau/S block streamed once per step)",
             "small": bool(args.small)}
@@ -261,8 +264,14 @@ def run_ours(args):
         return float(t.item())
 
     n_los = 6 if args.small else args.los_block
-    wl = make_workload(args, rank, n_los)
-    S, grid, lines, st, cells = wl["S"], wl["grid"], wl["lines"], wl["st"], wl["cells"]
+    n_fused = 12 if args.small else max(args.fused_los, n_los)
+    n_e = 9 if args.small else max(1, args.e2e_los)
+    n_big = max(n_los, n_fused, n_e)
+    wl = make_workload(args, rank, n_big)     # the K3 block is the first n_los LOS of the batch
+    S, grid, lines, st_all, cells = wl["S"], wl["grid"], wl["lines"], wl["st"], wl["cells"]
+    st = {k: (v[..., :n_los, :] if k in ("temp", "pres", "column", "tvib") else v[:n_los])
+          for k, v in st_all.items()}
+    wl["st"] = st
     n_grid, n_cells = len(grid), len(cells)
     ls = engine.LineSet(lines, grid, S.CH4_MM, N_LEVELS)
 
@@ -306,8 +315,9 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     ev0.record()
-    if my_cells:
-        g32[my_cells] = ls.gcoeff_cells_f32([cells[c] for c in my_cells])
+    if my_cells:   # contiguous block per rank, written in place
+        ls.gcoeff_cells_f32([cells[c] for c in my_cells],
+                            out=g32[my_cells[0]:my_cells[0] + len(my_cells)])
     ev1.record()
     torch.cuda.synchronize()
     build_dev_s = ev0.elapsed_time(ev1) * 1e-3
@@ -319,7 +329,9 @@ def run_ours(args):
                  "cells": n_cells, "device_s_per_rank": max_over_ranks(build_dev_s),
                  "evals_per_s": n_cells * evals / build_wall_s, "includes": "float32 cast + gather"}
     lut = engine.Lut(g32, cells, 6, 1, S.CH4_RATIO, level_energies=lines["level_energies"])
-    steps = engine.LosSteps(st["n_steps"], st["temp"], st["pres"], st["column"], st["tvib"])
+    steps_all = engine.LosSteps(st_all["n_steps"], st_all["temp"], st_all["pres"],
+                                st_all["column"], st_all["tvib"])
+    steps = steps_all.subset(slice(0, n_los))
 
     # ---- K3a: materialise tau/S of the block (resident inputs of K3) -------------------------
     tau, src = engine.los_tau_src([lut], steps)
@@ -343,25 +355,28 @@ def run_ours(args):
     launches = lib.sr_kernel_launch_count() - l0
     value = world * n_los / (k3_ms * 1e-3)
     rad_k3 = rad.clone()
+    del tau, src
 
-    # ---- fused K3a+K3 from the LUT, device-resident ------------------------------------------
+    # ---- K3a+K3 from the LUT, device-resident (grouped tensor-path product + recursion) -------
+    steps_f = steps_all.subset(slice(0, n_fused))
+    rad_f = torch.empty((n_fused, n_grid), dtype=torch.float64, device="cuda")
     for _ in range(2):
-        engine.los_rt_lut([lut], steps, out=rad)
+        engine.los_rt_lut([lut], steps_f, out=rad_f)
     barrier()
     ev0.record()
     n_f = max(1, min(args.steps, 3))
     for _ in range(n_f):
-        engine.los_rt_lut([lut], steps, out=rad, check_status=False)
+        engine.los_rt_lut([lut], steps_f, out=rad_f, check_status=False)
     ev1.record()
     barrier()
     fused_ms = max_over_ranks(ev0.elapsed_time(ev1)) / n_f
-    agree = float(((rad - rad_k3).abs() / rad_k3.abs().clamp_min(1e-300)).max().item())
-    del tau, src
+    agree = float(((rad_f[:n_los] - rad_k3).abs() / rad_k3.abs().clamp_min(1e-300)).max().item())
+    fused_step_pts = float(st_all["n_steps"][:n_fused].sum()) * n_grid
+    del rad_f
 
     # ---- e2e: reference-facing host call (host step tables in, host radiances out) ------------
-    n_e = min(n_los, 3 if args.small else args.e2e_los)
-    sub = steps.subset(slice(0, n_e))
-    host_out = torch.empty((n_e, n_grid), dtype=torch.float64).pin_memory().numpy()
+    sub = steps_all.subset(slice(0, n_e))
+    host_out = torch.empty((n_e, n_grid), dtype=torch.float64, pin_memory=True).numpy()
     engine.los_rt_lut_host([lut], sub, out=host_out)
     barrier()
     t0 = time.perf_counter()
@@ -393,8 +408,9 @@ def run_ours(args):
                 "d2h_bytes_per_step": d2h, "los_per_call": n_e,
                 "path": "sr_los_rt_lut_host: LUT interpolation + populations + layer recursion, "
                         "host step tables -> host hi-res radiances"},
-        "fused": {"value": world * n_los / (fused_ms * 1e-3), "unit": "LOS/s",
-                  "ms_per_step": fused_ms, "step_points_per_s": world * step_pts / (fused_ms * 1e-3),
+        "fused": {"value": world * n_fused / (fused_ms * 1e-3), "unit": "LOS/s",
+                  "los_per_rank": n_fused, "ms_per_step": fused_ms,
+                  "step_points_per_s": world * fused_step_pts / (fused_ms * 1e-3),
                   "max_rel_diff_vs_k3": agree},
         "voigt": voigt, "lut_build": lut_build,
         "gpu_launches": int(launches), "clocks": sampler.summary(),

@@ -19,6 +19,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
+#include <map>
 #include <vector>
 #include "sr_common.h"
 #include "sr_device.cuh"
@@ -281,129 +283,171 @@ __global__ void __launch_bounds__(1024) k_los_fused(LosArgs a) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// K3a as a grouped, register-tiled product (v2).  The (LOS, step) pairs of a batch are grouped by
-// the LUT cells their interpolation uses ("quad": up to 4 cells per gas).  One CTA takes PB pairs
-// of one quad and a tile of grid points: every needed LUT row is read (and converted from
-// float32) ONCE per CTA and used for all PB pairs, with the PB combined weights of the row
-// broadcast from shared memory -> PB*PPT FP64 FMAs per PPT loads + PB/2 LDS.128.
+// One LUT row of a quad program (K3a, grouped product): the (LOS, step) pairs of a batch are
+// grouped by the LUT cells their interpolation uses ("quad": up to 4 cells per gas); every needed
+// LUT row is read once per CTA and used for all pairs of the chunk:
 //   tau[pair][p] = sum_rows w_abs/ind[pair][row] * G[row][p],  J[pair][p] = sum_rows w_sp * G
 // Output goes to the [los][step][point] layer arrays that k_los_layers then streams.
-// ---------------------------------------------------------------------------------------------
-constexpr int GEMM_PB = 8;        // pairs per CTA
-constexpr int GEMM_NT = 256;
 constexpr int GEMM_MAXJ = 8 * 4 * 3 * 16;   // rows of one quad program (capacity check on the host)
 
-struct ProgEntry {                // one LUT row of a quad program
+struct ProgEntry {
     long long roff;               // address of the row's first element (float*) on the device
-    int gas;                      // which LUT
+    int gas;                      // which LUT (-1: zero-weight padding row)
     int widx;                     // set*4 + cell slot: index into the pair's weight block
     int neg;                      // 1: subtract (ind_emission row), 0: add
     int pad;
 };
 
-struct GemmArgs {
-    const ProgEntry* prog;        // [n_groups][max_j]
-    const int* grp_ntau;          // [n_groups] rows feeding tau (abs, ind); they come first
-    const int* grp_ntot;          // [n_groups] all rows (tau rows, then sp_emission rows)
+// ---------------------------------------------------------------------------------------------
+// K3a on the FP64 tensor path (v3).  Same grouping as v2, but the per-CTA product
+//   C[16 pairs][points] += A[16 pairs][rows] * B[rows][points]
+// is issued as DMMA.8x8x4 (mma.sync.m8n8k4.f64): one warp instruction does the work of 8 DFMA
+// warp instructions on the same FP64 pipe (tools/ubench/ub_dmma.cu: 37 TFLOP/s with ILP 1), so the
+// pipe is fed with ~1.4 issue slots per 16 pipe cycles instead of ~1.5 per 2.
+//   A fragment  lane -> W[pair = lane>>2][row j0 + (lane&3)]: packed once per call in fragment order
+//               by k_pack_wfrag, copied to shared memory per CTA (one conflict-free LDS.64 per use)
+//   B fragment  lane -> G[row j0 + (lane&3)][point 8i + (lane>>2)]: one float per lane straight from
+//               the LUT (4 rows x 32 B per warp load), converted to double in registers
+//   C fragment  lane -> pair lane>>2, points 8i + 2(lane&3) + {0,1}
+// One warp owns 16 pairs x 8*NB points; the second 8-pair M block is skipped when the chunk has
+// at most 8 pairs.  Rows are processed in two passes (tau rows, then emission rows) over the same
+// accumulators; program rows are padded to multiples of 4 with zero weights.
+// ---------------------------------------------------------------------------------------------
+constexpr int MMA_PB = 16;
+constexpr int MMA_NT = 128;
+
+struct MmaArgs {
+    const long long* rowptr;      // [n_groups][max_jp] device address of each program row
+    const int* grp_ntau;          // [n_groups] tau rows, padded to a multiple of 4
+    const int* grp_ntot;          // [n_groups] all rows (padded tau rows + padded emission rows)
     const int* chunk_grp;         // [n_chunks]
-    const int* chunk_pair;        // [n_chunks][PB] pair index los*n_steps_max+step, -1 = padding
-    const double* W;              // [n_gas][n_los*n_steps_max][n_sets_max*4]
-    long n_pairs_tot;             // n_los*n_steps_max
-    int n_sets_max, max_j;
+    const int* chunk_pair;        // [n_chunks][16] global pair index los*n_steps_max+step, -1 = padding
+    const double* wfrag;          // [n_chunks][max_jp/4][2][32] fragment-ordered weights
+    int max_jp, chunk0;
+    long pair_base;               // first pair of the LOS block (rows of tau_out/src_out are local)
     long pt0, n_pts;
-    double* tau_out;              // [n_los*n_steps_max][n_pts]
+    double* tau_out;              // [pairs of the block][n_pts]
     double* src_out;
     int mode;                     // 0: src = S = J/tau, 1: src = J
 };
 
-template <int PPT>
-__global__ void __launch_bounds__(GEMM_NT, 2) k_los_gemm(GemmArgs a) {
-    extern __shared__ __align__(16) unsigned char gsm[];
-    double* wj = reinterpret_cast<double*>(gsm);                          // [max_j][PB]
-    long long* roff = reinterpret_cast<long long*>(wj + (size_t)a.max_j * GEMM_PB);   // [max_j]
-    __shared__ int pair_s[GEMM_PB];
-    const int chunk = blockIdx.y, tid = threadIdx.x;
+struct PackArgs {
+    const ProgEntry* prog;        // [n_groups][max_jp] (gas < 0: padding row)
+    const int* grp_ntot;
+    const int* chunk_grp;
+    const int* chunk_pair;
+    const double* W;              // [n_gas][n_pairs_tot][n_sets_max*4]
+    double* wfrag;
+    long n_pairs_tot;
+    int n_sets_max, max_jp, n_chunks;
+};
+
+__global__ void k_pack_wfrag(PackArgs a) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long per_chunk = (long)a.max_jp * MMA_PB;
+    if (e >= per_chunk * a.n_chunks) return;
+    const int chunk = (int)(e / per_chunk);
+    const int r = (int)(e % per_chunk), j = r / MMA_PB, slot = r % MMA_PB;
+    const int grp = a.chunk_grp[chunk];
+    if (j >= a.grp_ntot[grp]) return;
+    const ProgEntry pe = a.prog[(size_t)grp * a.max_jp + j];
+    const int pr = a.chunk_pair[chunk * MMA_PB + slot];
+    double w = 0.0;
+    if (pr >= 0 && pe.gas >= 0)
+        w = a.W[((size_t)pe.gas * a.n_pairs_tot + pr) * ((size_t)a.n_sets_max * 4) + pe.widx];
+    if (pe.neg) w = -w;
+    const int kb = j >> 2, kq = j & 3, mb = slot >> 3, row = slot & 7;
+    a.wfrag[(((size_t)chunk * (a.max_jp >> 2) + kb) * 2 + mb) * 32 + row * 4 + kq] = w;
+}
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+template <int NB>
+__global__ void __launch_bounds__(MMA_NT, 4) k_los_mma(MmaArgs a) {
+    extern __shared__ __align__(16) unsigned char msm[];
+    double* wA = reinterpret_cast<double*>(msm);                                   // [kb][2][32]
+    long long* rps = reinterpret_cast<long long*>(wA + (size_t)a.max_jp * MMA_PB);   // [max_jp]
+    __shared__ int pair_s[MMA_PB];
+    const int chunk = a.chunk0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int grp = a.chunk_grp[chunk];
     const int n_tau = a.grp_ntau[grp], n_tot = a.grp_ntot[grp];
-    const ProgEntry* __restrict__ prog = a.prog + (size_t)grp * a.max_j;
-    if (tid < GEMM_PB) pair_s[tid] = a.chunk_pair[chunk * GEMM_PB + tid];
-    __syncthreads();
-    const size_t wstride = (size_t)a.n_sets_max * 4;
-    for (int e = tid; e < n_tot * GEMM_PB; e += GEMM_NT) {
-        const int j = e / GEMM_PB, i = e % GEMM_PB;
-        const ProgEntry pe = prog[j];
-        const int pr = pair_s[i];
-        double w = 0.0;
-        if (pr >= 0) w = a.W[((size_t)pe.gas * a.n_pairs_tot + pr) * wstride + pe.widx];
-        wj[j * GEMM_PB + i] = pe.neg ? -w : w;
-        if (i == 0) roff[j] = pe.roff;
+    if (tid < MMA_PB) pair_s[tid] = a.chunk_pair[chunk * MMA_PB + tid];
+    {
+        const double2* __restrict__ wsrc =
+            reinterpret_cast<const double2*>(a.wfrag + (size_t)chunk * a.max_jp * MMA_PB);
+        double2* wdst = reinterpret_cast<double2*>(wA);
+        for (int e = tid; e < n_tot * (MMA_PB / 2); e += MMA_NT) wdst[e] = __ldg(wsrc + e);
+        const long long* __restrict__ rsrc = a.rowptr + (size_t)grp * a.max_jp;
+        for (int e = tid; e < n_tot; e += MMA_NT) rps[e] = __ldg(rsrc + e);
     }
     __syncthreads();
-    const long p_first = (long)blockIdx.x * (GEMM_NT * PPT) + tid;
-    bool ok[PPT];
+    const bool two = pair_s[8] >= 0;
+    const int kq = lane & 3, nq = lane >> 2;
+    const long p_warp = (long)blockIdx.y * ((MMA_NT / 32) * 8 * NB) + wid * (8 * NB);
+    if (p_warp >= a.n_pts) return;
+    const long pl = p_warp + nq;
+    bool okb[NB];
 #pragma unroll
-    for (int q = 0; q < PPT; q++) ok[q] = p_first + q * GEMM_NT < a.n_pts;
-    double tau[GEMM_PB][PPT], J[GEMM_PB][PPT];
+    for (int i = 0; i < NB; i++) okb[i] = pl + 8 * i < a.n_pts;
+    double C0[NB][2], C1[NB][2];
+    auto pass = [&](int j0, int j1) {
 #pragma unroll
-    for (int i = 0; i < GEMM_PB; i++)
+        for (int i = 0; i < NB; i++) C0[i][0] = C0[i][1] = C1[i][0] = C1[i][1] = 0.0;
+        float g[NB], gn[NB];
+        auto load = [&](int j, float (&dst)[NB]) {
+            const float* __restrict__ r = reinterpret_cast<const float*>(rps[j + kq]) + a.pt0 + pl;
 #pragma unroll
-        for (int q = 0; q < PPT; q++) tau[i][q] = J[i][q] = 0.0;
-    const long pbase = a.pt0 + p_first;
-    // rows j0..j1 into acc, U rows per batch, the next batch's loads issued before this batch's
-    // FMAs (software pipelining: 2*U*PPT loads in flight per thread)
-    auto rows = [&](int j0, int j1, double (&acc)[GEMM_PB][PPT]) {
-        constexpr int U = 4;
-        float g[U][PPT], gn[U][PPT];
-        auto load = [&](int j, float (&dst)[U][PPT]) {
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const bool live = j + u < j1;
-                const float* __restrict__ r =
-                    reinterpret_cast<const float*>(roff[live ? j + u : j0]) + pbase;
-#pragma unroll
-                for (int q = 0; q < PPT; q++)
-                    dst[u][q] = (live && ok[q]) ? __ldg(r + q * GEMM_NT) : 0.0f;
-            }
+            for (int i = 0; i < NB; i++) dst[i] = okb[i] ? __ldg(r + 8 * i) : 0.0f;
         };
         if (j0 < j1) load(j0, gn);
-        for (int j = j0; j < j1; j += U) {
+        for (int j = j0; j < j1; j += 4) {
 #pragma unroll
-            for (int u = 0; u < U; u++)
+            for (int i = 0; i < NB; i++) g[i] = gn[i];
+            if (j + 4 < j1) load(j + 4, gn);
+            const double a0 = wA[(j >> 2) * 64 + lane];
+            if (two) {
+                const double a1 = wA[(j >> 2) * 64 + 32 + lane];
 #pragma unroll
-                for (int q = 0; q < PPT; q++) g[u][q] = gn[u][q];
-            if (j + U < j1) load(j + U, gn);
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                if (j + u >= j1) break;
-                double gd[PPT];
-#pragma unroll
-                for (int q = 0; q < PPT; q++) gd[q] = (double)g[u][q];
-                const double* __restrict__ w = wj + (j + u) * GEMM_PB;
-#pragma unroll
-                for (int i = 0; i < GEMM_PB; i++) {
-                    const double wi = w[i];
-#pragma unroll
-                    for (int q = 0; q < PPT; q++) acc[i][q] = fma(wi, gd[q], acc[i][q]);
+                for (int i = 0; i < NB; i++) {
+                    const double b = (double)g[i];
+                    dmma884(C0[i], a0, b);
+                    dmma884(C1[i], a1, b);
                 }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NB; i++) dmma884(C0[i], a0, (double)g[i]);
             }
         }
     };
-    rows(0, n_tau, tau);
-    rows(n_tau, n_tot, J);
+    // C fragment -> rows of out: pair slot mb*8 + nq, points p_warp + 8i + 2kq + {0,1}
+    auto store = [&](double* __restrict__ out, bool as_src) {
 #pragma unroll
-    for (int i = 0; i < GEMM_PB; i++) {
-        const int pr = pair_s[i];
-        if (pr < 0) continue;
-        const size_t o = (size_t)pr * a.n_pts + p_first;
+        for (int mb = 0; mb < 2; mb++) {
+            if (mb == 1 && !two) break;
+            const int pr = pair_s[mb * 8 + nq];
+            if (pr < 0) continue;
+            const size_t o = (size_t)(pr - a.pair_base) * a.n_pts + p_warp + 2 * kq;
 #pragma unroll
-        for (int q = 0; q < PPT; q++) {
-            if (!ok[q]) continue;
-            __stcs(a.tau_out + o + q * GEMM_NT, tau[i][q]);
-            const double sv = a.mode ? J[i][q] : (tau[i][q] == 0.0 ? 0.0 : J[i][q] / tau[i][q]);
-            __stcs(a.src_out + o + q * GEMM_NT, sv);
+            for (int i = 0; i < NB; i++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    if (p_warp + 8 * i + 2 * kq + e >= a.n_pts) continue;
+                    double v = mb ? C1[i][e] : C0[i][e];
+                    if (as_src && a.mode == 0) {   // S = J/tau (tau was written by this very lane)
+                        const double t = a.tau_out[o + 8 * i + e];
+                        v = (t == 0.0) ? 0.0 : v / t;
+                    }
+                    __stcs(out + o + 8 * i + e, v);
+                }
         }
-    }
+    };
+    pass(0, n_tau);
+    store(a.tau_out, false);
+    pass(n_tau, n_tot);
+    store(a.src_out, true);
 }
 
 // K3: I <- I exp(-tau) + S (1 - exp(-tau)) over materialised layers; pure HBM streaming.
@@ -482,10 +526,14 @@ struct sr_lut {
     sr::DevBuf<double> dPs, dTs, dq, delev;
     sr::DevBuf<int> dmap, drowmask, drowlist;
     int n_rows[3] = {0, 0, 0};
-    sr::DevBuf<double> ws_rad, ws_i0;   // workspace of the host-buffer entry point
+    sr::DevBuf<double> ws_rad[2], ws_i0;   // workspace of the host-buffer entry point
     sr::DevBuf<double> ws_tau, ws_src;  // layer scratch of the grouped K3a -> K3 path
     sr::DevBuf<char> g_prog;            // quad row programs / chunk tables of the current call
+    sr::DevBuf<long long> g_rowptr;
+    sr::DevBuf<double> g_wfrag;
     sr::DevBuf<int> g_ntau, g_ntot, g_cgrp, g_cpair;
+    cudaStream_t copy_stream = nullptr; // device -> host copies of the host-buffer entry point
+    ~sr_lut() { if (copy_stream) cudaStreamDestroy(copy_stream); }
     // per-call scratch (owned by the first LUT of a call)
     sr::DevBuf<int> cells, nsteps, flags;
     sr::DevBuf<double> W, temp, pres, column, tvib;
@@ -756,12 +804,23 @@ int sr_los_rt_layers_dev(const double* tau, const double* src, const int* n_step
 }
 
 // Host side of the grouped K3a: choose the LUT cells of every (LOS, step) pair with the
-// reference's rule (same code as sr_lut_weights), group the pairs by their cells, build one row
-// program per group and PB-pair chunks.
+// reference's rule (same code as sr_lut_weights), group the pairs by their cells ("quads"),
+// build one row program per quad and 16-pair chunks.  Large batches are cut into LOS blocks so
+// that the layer scratch stays bounded; quads (row programs) are shared by all blocks.
+constexpr int KEY_LEN = 4 * MAX_GAS;
+struct QuadKey {
+    int c[KEY_LEN];
+    bool operator<(const QuadKey& o) const { return memcmp(c, o.c, sizeof(c)) < 0; }
+    bool operator==(const QuadKey& o) const { return memcmp(c, o.c, sizeof(c)) == 0; }
+};
+
 struct GemmPlan {
-    std::vector<ProgEntry> prog;
-    std::vector<int> ntau, ntot, chunk_grp, chunk_pair;
-    int max_j = 0, n_groups = 0, n_chunks = 0;
+    std::vector<ProgEntry> prog;        // [n_groups][max_jp], padding rows have gas = -1
+    std::vector<long long> rowptr;      // [n_groups][max_jp]
+    std::vector<int> ntau, ntot;        // per group, multiples of 4
+    std::vector<int> chunk_grp, chunk_pair;
+    std::vector<int> blk_los, blk_chunk;   // [n_blocks+1] LOS / chunk range of each LOS block
+    int max_jp = 4, n_groups = 0, n_chunks = 0;
 };
 
 static int cells_of(const sr_lut* L, double pres, double temp, int cell[4]) {
@@ -792,26 +851,13 @@ static int cells_of(const sr_lut* L, double pres, double temp, int cell[4]) {
     return SR_OK;
 }
 
-static int build_plan(sr_lut* const* luts, const sr_los_steps* S, GemmPlan& P) {
+// nl_block: LOS per block (the last block may be shorter)
+static int build_plan(sr_lut* const* luts, const sr_los_steps* S, int nl_block, GemmPlan& P) {
     const int n_gas = S->n_gas;
     const size_t nmax = (size_t)S->n_steps_max;
-    struct Key { std::vector<int> c; int pair; };
-    std::vector<Key> keys;
-    for (int l = 0; l < S->n_los; l++)
-        for (int k = 0; k < S->n_steps[l]; k++) {
-            Key key;
-            key.pair = (int)(l * nmax + k);
-            key.c.resize((size_t)n_gas * 4);
-            for (int m = 0; m < n_gas; m++) {
-                int rc = cells_of(luts[m], S->pres[l * nmax + k], S->temp[l * nmax + k],
-                                  key.c.data() + 4 * m);
-                if (rc) return rc;
-            }
-            keys.push_back(std::move(key));
-        }
-    std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.c < b.c; });
     // row lists per gas and ctype (all-zero spectra are skipped like the reference's None entries)
     std::vector<std::vector<int>> rl((size_t)n_gas * 3);
+    int max_j_tau = 0, max_j_src = 0;
     for (int m = 0; m < n_gas; m++) {
         std::vector<int> list(3 * (size_t)luts[m]->n_sets);
         if (cudaMemcpy(list.data(), luts[m]->drowlist.p, list.size() * sizeof(int),
@@ -820,64 +866,122 @@ static int build_plan(sr_lut* const* luts, const sr_los_steps* S, GemmPlan& P) {
         for (int ct = 0; ct < 3; ct++)
             rl[(size_t)m * 3 + ct].assign(list.begin() + (size_t)ct * luts[m]->n_sets,
                                           list.begin() + (size_t)ct * luts[m]->n_sets + luts[m]->n_rows[ct]);
+        max_j_tau += 4 * (luts[m]->n_rows[1] + luts[m]->n_rows[2]);
+        max_j_src += 4 * luts[m]->n_rows[0];
     }
-    int max_j = 0;
-    for (int m = 0; m < n_gas; m++)
-        max_j += 4 * (luts[m]->n_rows[0] + luts[m]->n_rows[1] + luts[m]->n_rows[2]);
-    P.max_j = std::max(max_j, 1);
-    size_t i = 0;
-    while (i < keys.size()) {
-        size_t e = i;
-        while (e < keys.size() && keys[e].c == keys[i].c) e++;
-        const int grp = P.n_groups++;
-        P.prog.resize((size_t)P.n_groups * P.max_j);
-        ProgEntry* pr = P.prog.data() + (size_t)grp * P.max_j;
-        int nj = 0;
-        for (int pass = 0; pass < 2; pass++) {          // pass 0: tau rows (abs +, ind -); 1: J rows
-            for (int m = 0; m < n_gas; m++) {
-                const sr_lut* L = luts[m];
-                for (int c = 0; c < 4; c++) {
-                    const int cell = keys[i].c[(size_t)m * 4 + c];
-                    if (cell < 0) continue;
-                    for (int ct = (pass == 0 ? 1 : 0); ct <= (pass == 0 ? 2 : 0); ct++)
-                        for (int s : rl[(size_t)m * 3 + ct]) {
-                            ProgEntry pe;
-                            pe.roff = (long long)(L->g32 + (((size_t)cell * L->n_sets + s) * 3 + ct) *
-                                                               (size_t)L->n_grid);
-                            pe.gas = m;
-                            pe.widx = s * 4 + c;
-                            pe.neg = (ct == 1);
-                            pe.pad = 0;
-                            pr[nj++] = pe;
-                        }
+    P.max_jp = std::max(4, (max_j_tau + 3) / 4 * 4 + (max_j_src + 3) / 4 * 4);
+    struct Item { QuadKey key; int pair; };
+    std::map<QuadKey, int> group_of;
+    std::vector<Item> items;
+    P.blk_los.push_back(0);
+    P.blk_chunk.push_back(0);
+    for (int l0 = 0; l0 < S->n_los; l0 += nl_block) {
+        const int l1 = std::min(S->n_los, l0 + nl_block);
+        items.clear();
+        for (int l = l0; l < l1; l++)
+            for (int k = 0; k < S->n_steps[l]; k++) {
+                Item it;
+                memset(it.key.c, 0xff, sizeof(it.key.c));
+                it.pair = (int)(l * nmax + k);
+                for (int m = 0; m < n_gas; m++) {
+                    int rc = cells_of(luts[m], S->pres[l * nmax + k], S->temp[l * nmax + k],
+                                      it.key.c + 4 * m);
+                    if (rc) return rc;
                 }
+                items.push_back(it);
             }
-            if (pass == 0) P.ntau.push_back(nj);
+        std::stable_sort(items.begin(), items.end(),
+                         [](const Item& a, const Item& b) { return a.key < b.key; });
+        size_t i = 0;
+        while (i < items.size()) {
+            size_t e = i;
+            while (e < items.size() && items[e].key == items[i].key) e++;
+            int grp;
+            auto f = group_of.find(items[i].key);
+            if (f != group_of.end()) grp = f->second;
+            else {
+                grp = P.n_groups++;
+                group_of.emplace(items[i].key, grp);
+                P.prog.resize((size_t)P.n_groups * P.max_jp);
+                ProgEntry* pr = P.prog.data() + (size_t)grp * P.max_jp;
+                int nj = 0;
+                for (int pass = 0; pass < 2; pass++) {      // pass 0: tau rows (abs +, ind -); 1: J rows
+                    const int nj0 = nj;
+                    for (int m = 0; m < n_gas; m++) {
+                        const sr_lut* L = luts[m];
+                        for (int c = 0; c < 4; c++) {
+                            const int cell = items[i].key.c[m * 4 + c];
+                            if (cell < 0) continue;
+                            for (int ct = (pass == 0 ? 1 : 0); ct <= (pass == 0 ? 2 : 0); ct++)
+                                for (int s : rl[(size_t)m * 3 + ct]) {
+                                    ProgEntry pe;
+                                    pe.roff = (long long)(L->g32 + (((size_t)cell * L->n_sets + s) * 3 + ct) *
+                                                                       (size_t)L->n_grid);
+                                    pe.gas = m;
+                                    pe.widx = s * 4 + c;
+                                    pe.neg = (ct == 1);
+                                    pe.pad = 0;
+                                    pr[nj++] = pe;
+                                }
+                        }
+                    }
+                    while ((nj - nj0) % 4) {                // zero-weight padding rows
+                        ProgEntry pe;
+                        pe.roff = (long long)luts[0]->g32;
+                        pe.gas = -1;
+                        pe.widx = 0;
+                        pe.neg = 0;
+                        pe.pad = 0;
+                        pr[nj++] = pe;
+                    }
+                    if (pass == 0) P.ntau.push_back(nj);
+                }
+                P.ntot.push_back(nj);
+            }
+            for (size_t q = i; q < e; q += MMA_PB) {
+                P.chunk_grp.push_back(grp);
+                for (int t = 0; t < MMA_PB; t++)
+                    P.chunk_pair.push_back(q + t < e ? items[q + t].pair : -1);
+                P.n_chunks++;
+            }
+            i = e;
         }
-        P.ntot.push_back(nj);
-        for (size_t q = i; q < e; q += GEMM_PB) {
-            P.chunk_grp.push_back(grp);
-            for (int t = 0; t < GEMM_PB; t++)
-                P.chunk_pair.push_back(q + t < e ? keys[q + t].pair : -1);
-            P.n_chunks++;
-        }
-        i = e;
+        P.blk_los.push_back(l1);
+        P.blk_chunk.push_back(P.n_chunks);
     }
+    P.rowptr.resize(P.prog.size());
+    for (size_t q = 0; q < P.prog.size(); q++) P.rowptr[q] = P.prog[q].roff;
     return SR_OK;
 }
 
+// host-buffer sink of los_launch: radiances leave the device block by block, chunk by chunk, on a
+// second stream while the next chunk is computed
+struct HostSink {
+    double* rad_host;
+    const double* i0_host;
+};
+
 static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
                       const double* i0_dev, int solo, double* rad_dev, double* tau_dev,
-                      double* src_dev, cudaStream_t st, int emit_j = 0) {
+                      double* src_dev, cudaStream_t st, int emit_j = 0, HostSink* sink = nullptr) {
     LosArgs la;
     int rc = prepare_steps(luts, steps, st, la);
     if (rc) return rc;
     if (pt0 < 0 || n_pts < 1 || pt0 + n_pts > la.n_grid)
         return sr::fail(SR_ERR_ARG, "LOS: point range [%ld,%ld) outside the LUT grid", pt0, pt0 + n_pts);
     sr_lut* L0 = luts[0];
-    int ver = 2;
+    const int n_los = steps->n_los;
+    const size_t nmax = (size_t)steps->n_steps_max;
+    int ver = 3;
     if (const char* e = getenv("SR_LOS_VER")) ver = atoi(e);   // 1 = thread-per-point fused kernel
     if (ver == 1) {
+        if (sink) {   // plain path: whole batch on the device, then one copy
+            const size_t n = (size_t)n_los * n_pts;
+            SR_CUDA(L0->ws_rad[0].ensure(n));
+            if (sink->i0_host) SR_CUDA(L0->ws_i0.upload(sink->i0_host, n, st));
+            i0_dev = sink->i0_host ? L0->ws_i0.p : nullptr;
+            rad_dev = L0->ws_rad[0].p;
+        }
         la.pt0 = pt0;
         la.n_pts = n_pts;
         la.i0 = i0_dev;
@@ -892,82 +996,170 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         dim3 block(256, G);
 #define SR_FUSED(PPT)                                                                          \
     {                                                                                          \
-        dim3 grid((unsigned)((steps->n_los + G - 1) / G),                                      \
+        dim3 grid((unsigned)((n_los + G - 1) / G),                                             \
                   (unsigned)((n_pts + 256 * PPT - 1) / (256 * PPT)));                          \
         if (tau_dev) SR_LAUNCH((k_los_fused<PPT, true>), grid, block, 0, st, la);              \
         else SR_LAUNCH((k_los_fused<PPT, false>), grid, block, 0, st, la);                     \
     }
         if (ppt == 1) SR_FUSED(1) else if (ppt == 4) SR_FUSED(4) else SR_FUSED(2)
 #undef SR_FUSED
-        return SR_OK;
-    }
-    // ---- v2: grouped product into layer arrays, then the streaming recursion -----------------
-    GemmPlan P;
-    rc = build_plan(luts, steps, P);
-    if (rc) return rc;
-    if (P.n_chunks == 0) {   // no step at all: radiance = initial intensity
-        if (rad_dev) {
-            if (i0_dev) SR_CUDA(cudaMemcpyAsync(rad_dev, i0_dev, sizeof(double) * steps->n_los * n_pts,
-                                                cudaMemcpyDeviceToDevice, st));
-            else SR_CUDA(cudaMemsetAsync(rad_dev, 0, sizeof(double) * steps->n_los * n_pts, st));
+        if (sink) {
+            SR_CUDA(cudaStreamSynchronize(st));
+            SR_CUDA(cudaMemcpy(sink->rad_host, rad_dev, (size_t)n_los * n_pts * sizeof(double),
+                               cudaMemcpyDeviceToHost));
         }
         return SR_OK;
     }
-    if (P.max_j > GEMM_MAXJ)
-        return sr::fail(SR_ERR_LIMIT, "LOS: %d LUT rows per cell quad (limit %d)", P.max_j, GEMM_MAXJ);
-    SR_CUDA(L0->g_prog.upload(reinterpret_cast<const char*>(P.prog.data()),
-                              P.prog.size() * sizeof(ProgEntry), st));
-    SR_CUDA(L0->g_ntau.upload(P.ntau.data(), P.ntau.size(), st));
-    SR_CUDA(L0->g_ntot.upload(P.ntot.data(), P.ntot.size(), st));
-    SR_CUDA(L0->g_cgrp.upload(P.chunk_grp.data(), P.chunk_grp.size(), st));
-    SR_CUDA(L0->g_cpair.upload(P.chunk_pair.data(), P.chunk_pair.size(), st));
-    SR_CUDA(cudaStreamSynchronize(st));   // the plan vectors die with this frame
-    GemmArgs ga;
-    ga.prog = reinterpret_cast<const ProgEntry*>(L0->g_prog.p);
-    ga.grp_ntau = L0->g_ntau.p;
-    ga.grp_ntot = L0->g_ntot.p;
-    ga.chunk_grp = L0->g_cgrp.p;
-    ga.chunk_pair = L0->g_cpair.p;
-    ga.W = la.W;
-    ga.n_pairs_tot = (long)steps->n_los * steps->n_steps_max;
-    ga.n_sets_max = la.n_sets_max;
-    ga.max_j = P.max_j;
-    const size_t smem = (size_t)P.max_j * (GEMM_PB * sizeof(double) + sizeof(long long)) + 16;
-    constexpr int PPT = 2;
-    SR_CUDA(cudaFuncSetAttribute(k_los_gemm<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long n_pairs = (long)steps->n_los * steps->n_steps_max;
-    if (tau_dev) {   // materialise for the caller: [los][step][n_pts]
-        ga.pt0 = pt0;
-        ga.n_pts = n_pts;
-        ga.tau_out = tau_dev;
-        ga.src_out = src_dev;
-        ga.mode = emit_j;
-        dim3 grid((unsigned)((n_pts + GEMM_NT * PPT - 1) / (GEMM_NT * PPT)), (unsigned)P.n_chunks);
-        SR_LAUNCH((k_los_gemm<PPT>), grid, GEMM_NT, smem, st, ga);
+    // ---- v3: grouped tensor-path product into layer arrays, then the streaming recursion ------
+    // blocking: the layer scratch (16 B per pair and point) stays below the budget
+    size_t budget = (size_t)8 << 30;
+    if (const char* e = getenv("SR_LOS_SCRATCH_MB")) budget = (size_t)std::max(1L, atol(e)) << 20;
+    long chunk_pts = n_pts;
+    int nl_block = n_los;
+    if (!tau_dev) {
+        const long min_chunk = std::min<long>(n_pts, 65536);
+        if ((size_t)n_los * nmax * 16 * (size_t)min_chunk <= budget) {
+            chunk_pts = (long)(budget / ((size_t)n_los * nmax * 16));
+        } else {
+            chunk_pts = min_chunk;
+            nl_block = (int)std::max<size_t>(1, budget / (nmax * 16 * (size_t)chunk_pts));
+        }
+        if (const char* e = getenv("SR_LOS_CHUNK")) chunk_pts = std::max(256L, atol(e));
+        if (const char* e = getenv("SR_LOS_BLOCK")) nl_block = std::max(1, atoi(e));
+        chunk_pts = std::min(chunk_pts, n_pts);
+        if (chunk_pts < n_pts) chunk_pts = std::max(256L, chunk_pts / 256 * 256);
+        nl_block = std::min(nl_block, n_los);
+    }
+    GemmPlan P;
+    rc = build_plan(luts, steps, nl_block, P);
+    if (rc) return rc;
+    const int n_blocks = (int)P.blk_los.size() - 1;
+    if (P.max_jp > GEMM_MAXJ)
+        return sr::fail(SR_ERR_LIMIT, "LOS: %d LUT rows per cell quad (limit %d)", P.max_jp, GEMM_MAXJ);
+    const size_t smem = (size_t)P.max_jp * (MMA_PB * sizeof(double) + sizeof(long long)) + 16;
+    constexpr int NB = 8;
+    constexpr int TILE = (MMA_NT / 32) * 8 * NB;
+    MmaArgs ma;
+    if (P.n_chunks > 0) {
+        SR_CUDA(L0->g_prog.upload(reinterpret_cast<const char*>(P.prog.data()),
+                                  P.prog.size() * sizeof(ProgEntry), st));
+        SR_CUDA(L0->g_rowptr.upload(P.rowptr.data(), P.rowptr.size(), st));
+        SR_CUDA(L0->g_ntau.upload(P.ntau.data(), P.ntau.size(), st));
+        SR_CUDA(L0->g_ntot.upload(P.ntot.data(), P.ntot.size(), st));
+        SR_CUDA(L0->g_cgrp.upload(P.chunk_grp.data(), P.chunk_grp.size(), st));
+        SR_CUDA(L0->g_cpair.upload(P.chunk_pair.data(), P.chunk_pair.size(), st));
+        SR_CUDA(L0->g_wfrag.ensure((size_t)P.n_chunks * P.max_jp * MMA_PB));
+        PackArgs pa;
+        pa.prog = reinterpret_cast<const ProgEntry*>(L0->g_prog.p);
+        pa.grp_ntot = L0->g_ntot.p;
+        pa.chunk_grp = L0->g_cgrp.p;
+        pa.chunk_pair = L0->g_cpair.p;
+        pa.W = la.W;
+        pa.wfrag = L0->g_wfrag.p;
+        pa.n_pairs_tot = (long)n_los * (long)nmax;
+        pa.n_sets_max = la.n_sets_max;
+        pa.max_jp = P.max_jp;
+        pa.n_chunks = P.n_chunks;
+        const long n_el = (long)P.n_chunks * P.max_jp * MMA_PB;
+        SR_LAUNCH(k_pack_wfrag, (unsigned)((n_el + 255) / 256), 256, 0, st, pa);
+        SR_CUDA(cudaFuncSetAttribute(k_los_mma<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ma.rowptr = L0->g_rowptr.p;
+        ma.grp_ntau = L0->g_ntau.p;
+        ma.grp_ntot = L0->g_ntot.p;
+        ma.chunk_grp = L0->g_cgrp.p;
+        ma.chunk_pair = L0->g_cpair.p;
+        ma.wfrag = L0->g_wfrag.p;
+        ma.max_jp = P.max_jp;
+    }
+    if (tau_dev) {   // materialise for the caller: [los][step][n_pts]; rows without a step stay as they are
+        if (P.n_chunks == 0) return SR_OK;
+        ma.chunk0 = 0;
+        ma.pair_base = 0;
+        ma.pt0 = pt0;
+        ma.n_pts = n_pts;
+        ma.tau_out = tau_dev;
+        ma.src_out = src_dev;
+        ma.mode = emit_j;
+        dim3 grid((unsigned)P.n_chunks, (unsigned)((n_pts + TILE - 1) / TILE));
+        SR_LAUNCH((k_los_mma<NB>), grid, MMA_NT, smem, st, ma);
         return SR_OK;
     }
-    // radiances: wavenumber chunks sized so that the layer scratch stays below ~6 GiB
-    long chunk_pts = (long)std::max<size_t>(((size_t)6 << 30) / ((size_t)n_pairs * 16), 4096);
-    if (const char* e = getenv("SR_LOS_CHUNK")) chunk_pts = std::max(256L, atol(e));
-    chunk_pts = std::min(chunk_pts, n_pts);
-    SR_CUDA(L0->ws_tau.ensure((size_t)n_pairs * chunk_pts));
-    SR_CUDA(L0->ws_src.ensure((size_t)n_pairs * chunk_pts));
-    for (long c0 = 0; c0 < n_pts; c0 += chunk_pts) {
-        const long np = std::min(chunk_pts, n_pts - c0);
-        ga.pt0 = pt0 + c0;
-        ga.n_pts = np;
-        ga.tau_out = L0->ws_tau.p;
-        ga.src_out = L0->ws_src.p;
-        ga.mode = 1;
-        dim3 grid((unsigned)((np + GEMM_NT * PPT - 1) / (GEMM_NT * PPT)), (unsigned)P.n_chunks);
-        SR_LAUNCH((k_los_gemm<PPT>), grid, GEMM_NT, smem, st, ga);
-        // radiances (and i0) rows have stride n_pts; this chunk is the window [c0, c0+np)
-        rc = layers_launch(L0->ws_tau.p, L0->ws_src.p, la.n_steps, steps->n_los,
-                           steps->n_steps_max, np, i0_dev, solo, rad_dev, st, 1, n_pts, c0);
-        if (rc) return rc;
+    const size_t blk_pairs = (size_t)nl_block * nmax;
+    SR_CUDA(L0->ws_tau.ensure(blk_pairs * chunk_pts));
+    SR_CUDA(L0->ws_src.ensure(blk_pairs * chunk_pts));
+    cudaEvent_t buf_free[2] = {nullptr, nullptr};
+    if (sink) {
+        if (!L0->copy_stream)
+            SR_CUDA(cudaStreamCreateWithFlags(&L0->copy_stream, cudaStreamNonBlocking));
+        const int n_buf = n_blocks > 1 ? 2 : 1;
+        for (int b = 0; b < n_buf; b++) SR_CUDA(L0->ws_rad[b].ensure((size_t)nl_block * n_pts));
+        if (sink->i0_host) SR_CUDA(L0->ws_i0.ensure((size_t)nl_block * n_pts));
     }
-    return SR_OK;
+    int status = SR_OK;
+    auto body = [&]() -> int {
+        for (int b = 0; b < n_blocks; b++) {
+            const int l0 = P.blk_los[b], nl = P.blk_los[b + 1] - l0;
+            const int c_lo = P.blk_chunk[b], n_ch = P.blk_chunk[b + 1] - c_lo;
+            double* rad_blk = rad_dev ? rad_dev + (size_t)l0 * n_pts : nullptr;
+            const double* i0_blk = i0_dev ? i0_dev + (size_t)l0 * n_pts : nullptr;
+            if (sink) {
+                rad_blk = L0->ws_rad[b & 1].p;
+                if (buf_free[b & 1]) {   // the copies of block b-2 must have left this buffer
+                    SR_CUDA(cudaStreamWaitEvent(st, buf_free[b & 1], 0));
+                    SR_CUDA(cudaEventDestroy(buf_free[b & 1]));
+                    buf_free[b & 1] = nullptr;
+                }
+                i0_blk = nullptr;
+                if (sink->i0_host) {
+                    SR_CUDA(cudaMemcpyAsync(L0->ws_i0.p, sink->i0_host + (size_t)l0 * n_pts,
+                                            (size_t)nl * n_pts * sizeof(double),
+                                            cudaMemcpyHostToDevice, st));
+                    i0_blk = L0->ws_i0.p;
+                }
+            }
+            for (long c0 = 0; c0 < n_pts; c0 += chunk_pts) {
+                const long np = std::min(chunk_pts, n_pts - c0);
+                if (n_ch > 0) {
+                    ma.chunk0 = c_lo;
+                    ma.pair_base = (long)l0 * (long)nmax;
+                    ma.pt0 = pt0 + c0;
+                    ma.n_pts = np;
+                    ma.tau_out = L0->ws_tau.p;
+                    ma.src_out = L0->ws_src.p;
+                    ma.mode = 1;
+                    dim3 grid((unsigned)n_ch, (unsigned)((np + TILE - 1) / TILE));
+                    SR_LAUNCH((k_los_mma<NB>), grid, MMA_NT, smem, st, ma);
+                }
+                // radiances (and i0) rows have stride n_pts; this chunk is the window [c0, c0+np)
+                int code = layers_launch(L0->ws_tau.p, L0->ws_src.p, la.n_steps + l0, nl,
+                                         steps->n_steps_max, np, i0_blk, solo, rad_blk, st, 1, n_pts, c0);
+                if (code) return code;
+                if (sink) {
+                    cudaEvent_t ev;
+                    SR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                    SR_CUDA(cudaEventRecord(ev, st));
+                    SR_CUDA(cudaStreamWaitEvent(L0->copy_stream, ev, 0));
+                    SR_CUDA(cudaEventDestroy(ev));
+                    SR_CUDA(cudaMemcpy2DAsync(sink->rad_host + (size_t)l0 * n_pts + c0,
+                                              (size_t)n_pts * sizeof(double), rad_blk + c0,
+                                              (size_t)n_pts * sizeof(double), (size_t)np * sizeof(double),
+                                              (size_t)nl, cudaMemcpyDeviceToHost, L0->copy_stream));
+                }
+            }
+            if (sink && n_blocks > 1) {
+                SR_CUDA(cudaEventCreateWithFlags(&buf_free[b & 1], cudaEventDisableTiming));
+                SR_CUDA(cudaEventRecord(buf_free[b & 1], L0->copy_stream));
+            }
+        }
+        if (sink) SR_CUDA(cudaStreamSynchronize(L0->copy_stream));
+        return SR_OK;
+    };
+    status = body();
+    for (int b = 0; b < 2; b++)
+        if (buf_free[b]) cudaEventDestroy(buf_free[b]);
+    return status;
 }
+
 
 int sr_los_rt_lut_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
                       const double* i0_dev, int solo_absorption, double* rad_dev, void* stream) {
@@ -998,18 +1190,15 @@ int sr_los_check(sr_lut* const* luts, void* stream) {
 int sr_los_rt_lut_host(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
                        const double* i0_host, int solo_absorption, double* rad_host) {
     if (!rad_host || !steps) return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_host: bad argument");
-    const size_t n = (size_t)steps->n_los * n_pts;
     if (!luts || !luts[0]) return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_host: missing LUT");
     sr_lut* L0 = luts[0];
-    SR_CUDA(L0->ws_rad.ensure(n));      // grow-only workspace: no cudaMalloc/cudaFree per call
-    if (i0_host) SR_CUDA(L0->ws_i0.upload(i0_host, n));
-    int rc = los_launch(luts, steps, pt0, n_pts, i0_host ? L0->ws_i0.p : nullptr, solo_absorption,
-                        L0->ws_rad.p, nullptr, nullptr, 0);
+    // grow-only workspaces inside the LUT handle: no cudaMalloc/cudaFree per call; the radiances
+    // are copied out per (LOS block, wavenumber chunk) while the next chunk is computed
+    HostSink sink{rad_host, i0_host};
+    int rc = los_launch(luts, steps, pt0, n_pts, nullptr, solo_absorption, nullptr, nullptr, nullptr,
+                        0, 0, &sink);
     if (rc) return rc;
-    rc = check_lflags(L0, 0);
-    if (rc) return rc;
-    SR_CUDA(cudaMemcpy(rad_host, L0->ws_rad.p, n * sizeof(double), cudaMemcpyDeviceToHost));
-    return SR_OK;
+    return check_lflags(L0, 0);
 }
 
 }  // extern "C"

@@ -121,18 +121,18 @@ class LineSet(object):
 
     def gcoeff_cells_f32(self, PTcouples, out=None, stream=None):
         """Same as gcoeff_cells but stored as float32 (the compressed LUT,
-        spect_main_module.py:1676); needs only one cell of FP64 scratch."""
+        spect_main_module.py:1676); the tile kernel rounds in its store, no FP64 copy exists."""
         torch = _torch()
         pt = as_f64(np.asarray(PTcouples, dtype=float).reshape(-1, 2))
         n_cells = pt.shape[0]
         if out is None:
             out = torch.empty((n_cells, self.n_sets, 3, self.n_grid), dtype=torch.float32,
                               device="cuda")
-        scratch = torch.empty((self.n_sets, 3, self.n_grid), dtype=torch.float64, device="cuda")
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
+        assert out.numel() == self.cells_elems(n_cells)
         sp = _stream_ptr(stream)
         check(lib().sr_gcoeff_cells_dev_f32(self._h, dptr(pt), n_cells,
-                                            C.c_void_p(out.data_ptr()),
-                                            C.c_void_p(scratch.data_ptr()), sp))
+                                            C.c_void_p(out.data_ptr()), None, sp))
         check(lib().sr_lineset_check(self._h, sp))
         return out
 

@@ -3,8 +3,8 @@ plumbing (NCCL on the GPUs; the same code runs on gloo/CPU tensors in the tests)
 
 The path shards where the reference itself fans out over processes:
 
-  LUT cells    independent (`for [Pres,Temp] in PTcouples`, spect_main_module.py:753) -> round-robin
-               over ranks, no collective on the data path, one gather of the float32 LUT at the end
+  LUT cells    independent (`for [Pres,Temp] in PTcouples`, spect_main_module.py:753) -> contiguous
+               blocks over ranks, no collective on the data path, one gather of the float32 LUT at the end
                if every rank needs the whole table (gather_lut);
   LOS batch    independent (one forked process per LOS in the reference, spect_main_module.py:
                3202-3221) -> contiguous blocks per rank, gather of the (low-res) spectra (gather_rows);
@@ -42,9 +42,11 @@ def init(backend=None):
 
 
 def shard_cells(n_cells, rank, n_ranks):
-    """Indices of the (P,T) cells rank builds: round-robin, so that the pressure ladder (and with it
-    the slightly different per-cell cost) is spread evenly."""
-    return list(range(rank, n_cells, n_ranks))
+    """Indices of the (P,T) cells rank builds: one contiguous block per rank (the per-cell cost is
+    uniform to ~2 % across the pressure ladder), so that a rank writes its cells straight into its
+    slice of the LUT tensor and the gather moves contiguous memory."""
+    b, e = shard_range(n_cells, rank, n_ranks)
+    return list(range(b, e))
 
 
 def shard_range(n, rank, n_ranks):
@@ -71,13 +73,9 @@ def gather_lut(g32, n_cells, rank, n_ranks):
     if n_ranks == 1:
         return g32
     for src in range(n_ranks):
-        idx = shard_cells(n_cells, src, n_ranks)
-        if not idx:
-            continue
-        buf = g32[idx].contiguous()
-        dist.broadcast(buf, src=src)
-        if src != rank:
-            g32[idx] = buf
+        b, e = shard_range(n_cells, src, n_ranks)
+        if e > b:
+            dist.broadcast(g32[b:e], src=src)   # contiguous view: received in place
     return g32
 
 

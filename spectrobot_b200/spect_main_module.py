@@ -241,8 +241,12 @@ class LookUpTable(object):
         idx = list(range(len(self.PTcouples))) if cells is None else list(cells)
         if idx:
             ls = engine.LineSet(tab, grid, self.MM, n_sets)
-            sub = ls.gcoeff_cells_f32([self.PTcouples[i] for i in idx])
-            self.g32[torch.as_tensor(idx, device="cuda")] = sub
+            if idx == list(range(idx[0], idx[0] + len(idx))):   # contiguous: built in place
+                ls.gcoeff_cells_f32([self.PTcouples[i] for i in idx],
+                                    out=self.g32[idx[0]:idx[0] + len(idx)])
+            else:
+                sub = ls.gcoeff_cells_f32([self.PTcouples[i] for i in idx])
+                self.g32[torch.as_tensor(idx, device="cuda")] = sub
             ls.close()
         for s, nam in enumerate(names):
             level = None if self.LTE else getattr(self.isomolec, nam)

@@ -67,6 +67,28 @@ def test_fused_radiances_parity(case, oracle):
     assert np.array_equal(sub, got[:, 1001:1778])
 
 
+def test_los_blocking_and_chunking_are_invisible(case, monkeypatch):
+    """LOS blocks / wavenumber chunks of the scratch (large batches) and the overlapped copies of
+    the host entry point must not change a single bit; the thread-per-point kernel (SR_LOS_VER=1)
+    agrees with the tensor-path product to rounding."""
+    eng = case["engine"]
+    base = eng.los_rt_lut([case["lut"]], case["steps"]).cpu().numpy()
+    monkeypatch.setenv("SR_LOS_BLOCK", "4")
+    monkeypatch.setenv("SR_LOS_CHUNK", "768")
+    got = eng.los_rt_lut([case["lut"]], case["steps"]).cpu().numpy()
+    assert np.array_equal(got, base)
+    got_h = eng.los_rt_lut_host([case["lut"]], case["steps"])
+    assert np.array_equal(got_h, base)
+    monkeypatch.setenv("SR_LOS_BLOCK", "1")
+    got_h = eng.los_rt_lut_host([case["lut"]], case["steps"], pt0=5, n_pts=3001)
+    assert np.array_equal(got_h, base[:, 5:3006])
+    monkeypatch.delenv("SR_LOS_BLOCK")
+    monkeypatch.delenv("SR_LOS_CHUNK")
+    monkeypatch.setenv("SR_LOS_VER", "1")
+    v1 = eng.los_rt_lut([case["lut"]], case["steps"]).cpu().numpy()
+    assert rel_err(v1, base) < 1e-12
+
+
 def test_materialised_layers_parity(case, oracle):
     eng, st, torch = case["engine"], case["st"], case["torch"]
     ref, tau_ref, src_ref = oracle.los_rt([case["olut"]], st["n_steps"], st["temp"], st["pres"],
