@@ -311,7 +311,7 @@ def run_ours(args):
     # ---- K2: LUT build (cells sharded over ranks, all_gather) --------------------------------
     from spectrobot_b200 import parallel
     my_cells = parallel.shard_cells(n_cells, rank, world)
-    g32 = torch.empty((n_cells, N_LEVELS, 3, n_grid), dtype=torch.float32, device="cuda")
+    g32 = engine.lut_tensor(n_cells, N_LEVELS, n_grid)
     barrier()
     t0 = time.perf_counter()
     ev0.record()

@@ -136,6 +136,12 @@ int sr_lineset_check(sr_lineset* ls, void* stream);
  * spect_main_module.py:1676 via spect_classes.py:732). out32_dev: [n_cells][n_sets][3][n_grid]. */
 int sr_gcoeff_cells_dev_f32(sr_lineset* ls, const double* pt_host, int n_cells, float* out32_dev,
                             double* scratch_dev, void* stream);
+/* Same with padded rows: out32_dev is [n_cells][n_sets][3][row_stride] floats, row_stride >=
+ * n_grid; only the first n_grid elements of a row are written.  A row stride that is a multiple
+ * of 32 floats keeps every LUT row 128-byte aligned, which lets the LOS kernels read the table
+ * with 16-byte vector loads. */
+int sr_gcoeff_cells_dev_f32_ld(sr_lineset* ls, const double* pt_host, int n_cells,
+                               float* out32_dev, long row_stride, void* stream);
 
 /* Per-line normalised shapes of one cell (MakeShapeLine with keep_memory, spect_classes.py:174):
  * shapes_dev [n_active][SR_IMXSIG] in the lineset's internal (sorted) line order, and the three
@@ -167,6 +173,12 @@ typedef struct sr_lut sr_lut;
 int sr_lut_create(const float* g32_dev, const double* pt_host, int n_cells, int n_sets,
                   long n_grid, const double* level_energy_host, int mol, int iso,
                   double iso_ratio, int lte_unidentified, const sr_consts* consts, sr_lut** out);
+/* Same for a table with padded rows, [n_cells][n_sets][3][row_stride] (see
+ * sr_gcoeff_cells_dev_f32_ld); the padding elements must be finite. */
+int sr_lut_create_ld(const float* g32_dev, long row_stride, const double* pt_host, int n_cells,
+                     int n_sets, long n_grid, const double* level_energy_host, int mol, int iso,
+                     double iso_ratio, int lte_unidentified, const sr_consts* consts,
+                     sr_lut** out);
 int sr_lut_destroy(sr_lut* lut);
 
 /* Step tables of a LOS batch (HOST arrays, steps ordered far end -> observer):

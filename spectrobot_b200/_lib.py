@@ -72,11 +72,15 @@ SIGNATURES = {
     "sr_gcoeff_cells_dev": (C.c_int, [_vp, _dp, C.c_int, _vp, _vp]),
     "sr_gcoeff_cells_host": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "sr_gcoeff_cells_dev_f32": (C.c_int, [_vp, _dp, C.c_int, _vp, _vp, _vp]),
+    "sr_gcoeff_cells_dev_f32_ld": (C.c_int, [_vp, _dp, C.c_int, _vp, C.c_long, _vp]),
     "sr_line_shapes_dev": (C.c_int, [_vp, C.c_double, C.c_double, _vp, _vp, _vp]),
     "sr_los_rt_layers_dev": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_long, _vp, C.c_int,
                                        _vp, _vp]),
     "sr_lut_create": (C.c_int, [_vp, _dp, C.c_int, C.c_int, C.c_long, _dp, C.c_int, C.c_int,
                                 C.c_double, C.c_int, C.POINTER(sr_consts), C.POINTER(_vp)]),
+    "sr_lut_create_ld": (C.c_int, [_vp, C.c_long, _dp, C.c_int, C.c_int, C.c_long, _dp, C.c_int,
+                                   C.c_int, C.c_double, C.c_int, C.POINTER(sr_consts),
+                                   C.POINTER(_vp)]),
     "sr_lut_destroy": (C.c_int, [_vp]),
     "sr_los_rt_lut_dev": (C.c_int, [C.POINTER(_vp), C.POINTER(sr_los_steps), C.c_long, C.c_long,
                                     _vp, C.c_int, _vp, _vp]),

@@ -43,6 +43,7 @@ struct GasDev {
                             // smm:1674-1679, 2244-2249)
     int n_rows[3];          // list lengths: sp_emission, ind_emission, absorption
     int nP, nT, n_sets, lte_unidentified;
+    long row_stride;        // floats between consecutive LUT rows (>= n_grid)
     double iso_ratio;
 };
 
@@ -163,10 +164,10 @@ __global__ void k_step_weights(StepArgs a) {
 
 // which LUT rows (set, ctype) hold any non-zero value (over all cells and grid points)
 __global__ void k_row_nonzero(const float* __restrict__ g32, int n_cells, int n_sets, long n_grid,
-                              int* __restrict__ rowmask) {
+                              long row_stride, int* __restrict__ rowmask) {
     const int r = blockIdx.y;                 // (cell, set, ctype) row
     const int s = (r / 3) % n_sets, ct = r % 3;
-    const float* __restrict__ p = g32 + (size_t)r * n_grid;
+    const float* __restrict__ p = g32 + (size_t)r * row_stride;
     bool nz = false;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_grid;
          i += (long)gridDim.x * blockDim.x)
@@ -203,7 +204,7 @@ __device__ __forceinline__ void step_tau_j(const LosArgs& a, int l, int k, long 
         const int4 cells = __ldg(reinterpret_cast<const int4*>(a.cells + o * 4));
         const double* __restrict__ W = a.W + o * a.n_sets_max * 4;
         const int cl[4] = {cells.x, cells.y, cells.z, cells.w};
-        const size_t row = (size_t)a.n_grid;
+        const size_t row = (size_t)G.row_stride;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             if (cl[c] < 0) continue;
@@ -326,7 +327,8 @@ struct MmaArgs {
     int max_jp, chunk0;
     long pair_base;               // first pair of the LOS block (rows of tau_out/src_out are local)
     long pt0, n_pts;
-    double* tau_out;              // [pairs of the block][n_pts]
+    long ld_out;                  // stride of the output rows (>= n_pts)
+    double* tau_out;              // [pairs of the block][ld_out]
     double* src_out;
     int mode;                     // 0: src = S = J/tau, 1: src = J
 };
@@ -365,7 +367,13 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-template <int NB>
+// VEC: every LUT row and the point window are 16-byte aligned (padded LUT rows, pt0 % 4 == 0) and
+// the output rows have a stride that is a multiple of 4 -> one LDG.128 per lane brings 4 points of
+// one row (a warp load = 4 rows x 128 contiguous bytes), and each lane ends up with 8 consecutive
+// points of one pair, written as 16-byte vectors.  Point <-> fragment maps:
+//   VEC    B(v,i): point 32v + 4(lane>>2) + i         C(v,i)[e]: point 32v + 8(lane&3) + 4e + i
+//   scalar B(i)  : point 8i + (lane>>2)               C(i)[e]  : point 8i + 2(lane&3) + e
+template <int NB, bool VEC>
 __global__ void __launch_bounds__(MMA_NT, 4) k_los_mma(MmaArgs a) {
     extern __shared__ __align__(16) unsigned char msm[];
     double* wA = reinterpret_cast<double*>(msm);                                   // [kb][2][32]
@@ -388,60 +396,94 @@ __global__ void __launch_bounds__(MMA_NT, 4) k_los_mma(MmaArgs a) {
     const int kq = lane & 3, nq = lane >> 2;
     const long p_warp = (long)blockIdx.y * ((MMA_NT / 32) * 8 * NB) + wid * (8 * NB);
     if (p_warp >= a.n_pts) return;
-    const long pl = p_warp + nq;
-    bool okb[NB];
+    struct Frag { float v[NB]; };
+    auto load = [&](int j, Frag& f) {
+        const float* __restrict__ r = reinterpret_cast<const float*>(rps[j + kq]) + a.pt0 + p_warp;
+        if (VEC) {
 #pragma unroll
-    for (int i = 0; i < NB; i++) okb[i] = pl + 8 * i < a.n_pts;
+            for (int v = 0; v < NB / 4; v++) {
+                const int p = 32 * v + 4 * nq;
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p_warp + p < a.n_pts) q = __ldg(reinterpret_cast<const float4*>(r + p));
+                f.v[4 * v + 0] = q.x; f.v[4 * v + 1] = q.y; f.v[4 * v + 2] = q.z; f.v[4 * v + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NB; i++)
+                f.v[i] = (p_warp + 8 * i + nq < a.n_pts) ? __ldg(r + 8 * i + nq) : 0.0f;
+        }
+    };
     double C0[NB][2], C1[NB][2];
+    // rows [j0, j1) into the accumulators; B fragments are fetched two k-steps ahead
     auto pass = [&](int j0, int j1) {
 #pragma unroll
         for (int i = 0; i < NB; i++) C0[i][0] = C0[i][1] = C1[i][0] = C1[i][1] = 0.0;
-        float g[NB], gn[NB];
-        auto load = [&](int j, float (&dst)[NB]) {
-            const float* __restrict__ r = reinterpret_cast<const float*>(rps[j + kq]) + a.pt0 + pl;
-#pragma unroll
-            for (int i = 0; i < NB; i++) dst[i] = okb[i] ? __ldg(r + 8 * i) : 0.0f;
-        };
-        if (j0 < j1) load(j0, gn);
+        Frag g, g1, g2;
+        if (j0 < j1) load(j0, g1);
+        if (j0 + 4 < j1) load(j0 + 4, g2);
         for (int j = j0; j < j1; j += 4) {
-#pragma unroll
-            for (int i = 0; i < NB; i++) g[i] = gn[i];
-            if (j + 4 < j1) load(j + 4, gn);
+            g = g1;
+            g1 = g2;
+            if (j + 8 < j1) load(j + 8, g2);
             const double a0 = wA[(j >> 2) * 64 + lane];
             if (two) {
                 const double a1 = wA[(j >> 2) * 64 + 32 + lane];
 #pragma unroll
                 for (int i = 0; i < NB; i++) {
-                    const double b = (double)g[i];
+                    const double b = (double)g.v[i];
                     dmma884(C0[i], a0, b);
                     dmma884(C1[i], a1, b);
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < NB; i++) dmma884(C0[i], a0, (double)g[i]);
+                for (int i = 0; i < NB; i++) dmma884(C0[i], a0, (double)g.v[i]);
             }
         }
     };
-    // C fragment -> rows of out: pair slot mb*8 + nq, points p_warp + 8i + 2kq + {0,1}
     auto store = [&](double* __restrict__ out, bool as_src) {
 #pragma unroll
         for (int mb = 0; mb < 2; mb++) {
             if (mb == 1 && !two) break;
             const int pr = pair_s[mb * 8 + nq];
             if (pr < 0) continue;
-            const size_t o = (size_t)(pr - a.pair_base) * a.n_pts + p_warp + 2 * kq;
+            double* __restrict__ o = out + (size_t)(pr - a.pair_base) * a.ld_out + p_warp;
+            const double* __restrict__ t_in =
+                a.tau_out + (size_t)(pr - a.pair_base) * a.ld_out + p_warp;
+            const bool divide = as_src && a.mode == 0;   // S = J/tau (tau written by this very lane)
+            if (VEC) {
 #pragma unroll
-            for (int i = 0; i < NB; i++)
+                for (int v = 0; v < NB / 4; v++)
 #pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    if (p_warp + 8 * i + 2 * kq + e >= a.n_pts) continue;
-                    double v = mb ? C1[i][e] : C0[i][e];
-                    if (as_src && a.mode == 0) {   // S = J/tau (tau was written by this very lane)
-                        const double t = a.tau_out[o + 8 * i + e];
-                        v = (t == 0.0) ? 0.0 : v / t;
+                    for (int e = 0; e < 2; e++) {
+                        const int off = 32 * v + 8 * kq + 4 * e;
+                        if (p_warp + off >= a.n_pts) continue;   // rows are padded to ld_out
+                        double x[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            x[i] = mb ? C1[4 * v + i][e] : C0[4 * v + i][e];
+                            if (divide) {
+                                const double t = t_in[off + i];
+                                x[i] = (t == 0.0) ? 0.0 : x[i] / t;
+                            }
+                        }
+                        __stcs(reinterpret_cast<double2*>(o + off), make_double2(x[0], x[1]));
+                        __stcs(reinterpret_cast<double2*>(o + off + 2), make_double2(x[2], x[3]));
                     }
-                    __stcs(out + o + 8 * i + e, v);
-                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NB; i++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int off = 8 * i + 2 * kq + e;
+                        if (p_warp + off >= a.n_pts) continue;
+                        double x = mb ? C1[i][e] : C0[i][e];
+                        if (divide) {
+                            const double t = t_in[off];
+                            x = (t == 0.0) ? 0.0 : x / t;
+                        }
+                        __stcs(o + off, x);
+                    }
+            }
         }
     };
     pass(0, n_tau);
@@ -460,7 +502,7 @@ __global__ void __launch_bounds__(256) k_los_layers(const double* __restrict__ t
                                                     int n_steps_max, long n_pts,
                                                     const double* __restrict__ i0, int solo,
                                                     double* __restrict__ rad, int src_is_j,
-                                                    long io_stride, long io_off) {
+                                                    long io_stride, long io_off, long lay_stride) {
     const int l = blockIdx.y;
     const long p0 = (long)blockIdx.x * (256 * PPT) + threadIdx.x;
     if (p0 >= n_pts) return;
@@ -472,8 +514,8 @@ __global__ void __launch_bounds__(256) k_los_layers(const double* __restrict__ t
         I[i] = (i0 && ok[i]) ? i0[(size_t)l * io_stride + io_off + p0 + i * 256] : 0.0;
     }
     const int ns = n_steps[l];
-    const double* __restrict__ tp = tau + (size_t)l * n_steps_max * n_pts + p0;
-    const double* __restrict__ sp = src + (size_t)l * n_steps_max * n_pts + p0;
+    const double* __restrict__ tp = tau + (size_t)l * n_steps_max * lay_stride + p0;
+    const double* __restrict__ sp = src + (size_t)l * n_steps_max * lay_stride + p0;
     auto update = [&](int i, double t, double s) {
         double ex, em;
         srdev::exp_pair(-t, ex, em);
@@ -491,7 +533,7 @@ __global__ void __launch_bounds__(256) k_los_layers(const double* __restrict__ t
         for (int u = 0; u < UNROLL; u++)
 #pragma unroll
             for (int i = 0; i < PPT; i++) {
-                const size_t o = (size_t)(k + u) * n_pts + i * 256;
+                const size_t o = (size_t)(k + u) * lay_stride + i * 256;
                 t[u][i] = ok[i] ? __ldcs(tp + o) : 0.0;
                 s[u][i] = ok[i] ? __ldcs(sp + o) : 0.0;
             }
@@ -503,8 +545,8 @@ __global__ void __launch_bounds__(256) k_los_layers(const double* __restrict__ t
     for (; k < ns; k++)
 #pragma unroll
         for (int i = 0; i < PPT; i++)
-            if (ok[i]) update(i, __ldcs(tp + (size_t)k * n_pts + i * 256),
-                              __ldcs(sp + (size_t)k * n_pts + i * 256));
+            if (ok[i]) update(i, __ldcs(tp + (size_t)k * lay_stride + i * 256),
+                              __ldcs(sp + (size_t)k * lay_stride + i * 256));
 #pragma unroll
     for (int i = 0; i < PPT; i++)
         if (ok[i]) __stcs(rad + (size_t)l * io_stride + io_off + p0 + i * 256, I[i]);
@@ -518,7 +560,7 @@ __global__ void __launch_bounds__(256) k_los_layers(const double* __restrict__ t
 struct sr_lut {
     const float* g32 = nullptr;
     int n_cells = 0, n_sets = 0, mol = 0, iso = 0, lte_unidentified = 0;
-    long n_grid = 0;
+    long n_grid = 0, row_stride = 0;
     double iso_ratio = 1.0;
     sr_consts c{};
     std::vector<double> pt, Ps, Ts;
@@ -576,6 +618,7 @@ GasDev gas_dev(const sr_lut* L) {
     g.nT = (int)L->Ts.size();
     g.n_sets = L->n_sets;
     g.lte_unidentified = L->lte_unidentified;
+    g.row_stride = L->row_stride;
     g.iso_ratio = L->iso_ratio;
     return g;
 }
@@ -662,8 +705,16 @@ extern "C" {
 int sr_lut_create(const float* g32_dev, const double* pt_host, int n_cells, int n_sets,
                   long n_grid, const double* level_energy_host, int mol, int iso,
                   double iso_ratio, int lte_unidentified, const sr_consts* consts, sr_lut** out) {
+    return sr_lut_create_ld(g32_dev, n_grid, pt_host, n_cells, n_sets, n_grid, level_energy_host,
+                            mol, iso, iso_ratio, lte_unidentified, consts, out);
+}
+
+int sr_lut_create_ld(const float* g32_dev, long row_stride, const double* pt_host, int n_cells,
+                     int n_sets, long n_grid, const double* level_energy_host, int mol, int iso,
+                     double iso_ratio, int lte_unidentified, const sr_consts* consts,
+                     sr_lut** out) {
     if (!g32_dev || !pt_host || n_cells < 1 || n_sets < 1 || n_grid < 1 || !out ||
-        (!lte_unidentified && !level_energy_host))
+        row_stride < n_grid || (!lte_unidentified && !level_energy_host))
         return sr::fail(SR_ERR_ARG, "sr_lut_create: bad argument");
     double gi, t[TIPS_N], q[TIPS_N];
     int rc = sr_bd_tips_2003(mol, iso, &gi, t, q);
@@ -673,6 +724,7 @@ int sr_lut_create(const float* g32_dev, const double* pt_host, int n_cells, int 
     L->n_cells = n_cells;
     L->n_sets = n_sets;
     L->n_grid = n_grid;
+    L->row_stride = row_stride;
     L->mol = mol;
     L->iso = iso;
     L->iso_ratio = iso_ratio;
@@ -700,7 +752,7 @@ int sr_lut_create(const float* g32_dev, const double* pt_host, int n_cells, int 
         SR_CUDA(cudaMemset(L->drowmask.p, 0, sizeof(int) * n_sets));
         {
             dim3 grid(8, (unsigned)(n_cells * n_sets * 3));
-            SR_LAUNCH(k_row_nonzero, grid, 256, 0, 0, g32_dev, n_cells, n_sets, n_grid,
+            SR_LAUNCH(k_row_nonzero, grid, 256, 0, 0, g32_dev, n_cells, n_sets, n_grid, row_stride,
                       L->drowmask.p);
         }
         std::vector<int> mask(n_sets), list(3 * (size_t)n_sets, 0);
@@ -770,8 +822,9 @@ int sr_lut_weights(const double* pt_host, int n_cells, double pres, double temp,
 static int layers_launch(const double* tau, const double* src, const int* n_steps, int n_los,
                          int n_steps_max, long n_pts, const double* i0, int solo_absorption,
                          double* rad, cudaStream_t st, int src_is_j, long io_stride = -1,
-                         long io_off = 0) {
+                         long io_off = 0, long lay_stride = -1) {
     if (io_stride < 0) io_stride = n_pts;   // rad / i0 rows: [n_los][io_stride], window at io_off
+    if (lay_stride < 0) lay_stride = n_pts; // tau / src rows: [n_los][n_steps_max][lay_stride]
     // measured on B200 (tools/tune.py): (PPT=1, UNROLL=4) at 38 registers streams at the
     // measured copy bandwidth; wider variants lose occupancy
     int cfg = 5;
@@ -780,7 +833,8 @@ static int layers_launch(const double* tau, const double* src, const int* n_step
     {                                                                                          \
         dim3 grid((unsigned)((n_pts + 256 * PPT - 1) / (256 * PPT)), n_los);                   \
         SR_LAUNCH((k_los_layers<PPT, UNROLL>), grid, 256, 0, st, tau, src, n_steps,            \
-                  n_steps_max, n_pts, i0, solo_absorption, rad, src_is_j, io_stride, io_off);  \
+                  n_steps_max, n_pts, i0, solo_absorption, rad, src_is_j, io_stride, io_off,   \
+                  lay_stride);                                                                 \
     }
     switch (cfg) {
         case 1: SR_K3_LAUNCH(1, 8) break;
@@ -916,7 +970,7 @@ static int build_plan(sr_lut* const* luts, const sr_los_steps* S, int nl_block, 
                                 for (int s : rl[(size_t)m * 3 + ct]) {
                                     ProgEntry pe;
                                     pe.roff = (long long)(L->g32 + (((size_t)cell * L->n_sets + s) * 3 + ct) *
-                                                                       (size_t)L->n_grid);
+                                                                       (size_t)L->row_stride);
                                     pe.gas = m;
                                     pe.widx = s * 4 + c;
                                     pe.neg = (ct == 1);
@@ -1040,6 +1094,10 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
     constexpr int NB = 8;
     constexpr int TILE = (MMA_NT / 32) * 8 * NB;
     MmaArgs ma;
+    bool rows_aligned = true;   // every LUT row starts on a 16-byte boundary
+    for (int m = 0; m < steps->n_gas; m++)
+        rows_aligned = rows_aligned && luts[m]->row_stride % 4 == 0 && (size_t)luts[m]->g32 % 16 == 0;
+    if (const char* e = getenv("SR_LOS_NOVEC")) rows_aligned = rows_aligned && atoi(e) == 0;
     if (P.n_chunks > 0) {
         SR_CUDA(L0->g_prog.upload(reinterpret_cast<const char*>(P.prog.data()),
                                   P.prog.size() * sizeof(ProgEntry), st));
@@ -1062,7 +1120,8 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         pa.n_chunks = P.n_chunks;
         const long n_el = (long)P.n_chunks * P.max_jp * MMA_PB;
         SR_LAUNCH(k_pack_wfrag, (unsigned)((n_el + 255) / 256), 256, 0, st, pa);
-        SR_CUDA(cudaFuncSetAttribute(k_los_mma<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SR_CUDA(cudaFuncSetAttribute(k_los_mma<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SR_CUDA(cudaFuncSetAttribute(k_los_mma<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ma.rowptr = L0->g_rowptr.p;
         ma.grp_ntau = L0->g_ntau.p;
         ma.grp_ntot = L0->g_ntot.p;
@@ -1077,16 +1136,21 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         ma.pair_base = 0;
         ma.pt0 = pt0;
         ma.n_pts = n_pts;
+        ma.ld_out = n_pts;
         ma.tau_out = tau_dev;
         ma.src_out = src_dev;
         ma.mode = emit_j;
         dim3 grid((unsigned)P.n_chunks, (unsigned)((n_pts + TILE - 1) / TILE));
-        SR_LAUNCH((k_los_mma<NB>), grid, MMA_NT, smem, st, ma);
+        const bool vec = rows_aligned && pt0 % 4 == 0 && n_pts % 4 == 0 &&
+                         ((size_t)tau_dev | (size_t)src_dev) % 16 == 0;
+        if (vec) SR_LAUNCH((k_los_mma<NB, true>), grid, MMA_NT, smem, st, ma);
+        else SR_LAUNCH((k_los_mma<NB, false>), grid, MMA_NT, smem, st, ma);
         return SR_OK;
     }
     const size_t blk_pairs = (size_t)nl_block * nmax;
-    SR_CUDA(L0->ws_tau.ensure(blk_pairs * chunk_pts));
-    SR_CUDA(L0->ws_src.ensure(blk_pairs * chunk_pts));
+    const long ld_lay = (chunk_pts + 3) / 4 * 4;   // scratch rows: 32-byte aligned for any chunk size
+    SR_CUDA(L0->ws_tau.ensure(blk_pairs * ld_lay));
+    SR_CUDA(L0->ws_src.ensure(blk_pairs * ld_lay));
     cudaEvent_t buf_free[2] = {nullptr, nullptr};
     if (sink) {
         if (!L0->copy_stream)
@@ -1124,15 +1188,20 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
                     ma.pair_base = (long)l0 * (long)nmax;
                     ma.pt0 = pt0 + c0;
                     ma.n_pts = np;
+                    ma.ld_out = ld_lay;
                     ma.tau_out = L0->ws_tau.p;
                     ma.src_out = L0->ws_src.p;
                     ma.mode = 1;
                     dim3 grid((unsigned)n_ch, (unsigned)((np + TILE - 1) / TILE));
-                    SR_LAUNCH((k_los_mma<NB>), grid, MMA_NT, smem, st, ma);
+                    if (rows_aligned && (pt0 + c0) % 4 == 0)
+                        SR_LAUNCH((k_los_mma<NB, true>), grid, MMA_NT, smem, st, ma);
+                    else
+                        SR_LAUNCH((k_los_mma<NB, false>), grid, MMA_NT, smem, st, ma);
                 }
                 // radiances (and i0) rows have stride n_pts; this chunk is the window [c0, c0+np)
                 int code = layers_launch(L0->ws_tau.p, L0->ws_src.p, la.n_steps + l0, nl,
-                                         steps->n_steps_max, np, i0_blk, solo, rad_blk, st, 1, n_pts, c0);
+                                         steps->n_steps_max, np, i0_blk, solo, rad_blk, st, 1, n_pts, c0,
+                                         ld_lay);
                 if (code) return code;
                 if (sink) {
                     cudaEvent_t ev;

@@ -345,6 +345,7 @@ struct TileArgs {
     const int* zero_rows;    // [n_zero] rows (set*3+ctype) that no line feeds
     void* out;               // [n_cells][n_sets][3][n_grid] double (or float when F32)
     long n_grid;
+    long row_stride;         // elements between consecutive output rows (>= n_grid)
     int n_lines, n_sets, n_groups, n_up, n_lo, n_zero;
 };
 
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
     const size_t rows_cell = (size_t)a.n_sets * 3;
 
     auto store_row = [&](int row, const double (&v)[PPT]) {
-        const size_t o = ((size_t)cell * rows_cell + row) * (size_t)a.n_grid + P0;
+        const size_t o = ((size_t)cell * rows_cell + row) * (size_t)a.row_stride + P0;
 #pragma unroll
         for (int k = 0; k < PPT; k++) {
             if ((long)P0 + k * NT < a.n_grid) {
@@ -988,12 +989,15 @@ static int run_params(sr_lineset* ls, const double* pt_host, int n_cells, cudaSt
 }
 
 static int gcoeff_cells_impl(sr_lineset* ls, const double* pt_host, int n_cells, void* out_dev,
-                             bool f32, cudaStream_t st) {
+                             bool f32, cudaStream_t st, long row_stride = 0) {
+    if (row_stride == 0) row_stride = ls->n_grid;
+    if (row_stride < ls->n_grid)
+        return sr::fail(SR_ERR_ARG, "row stride %ld < n_grid %ld", row_stride, ls->n_grid);
     for (int i = 0; i < n_cells; i++)
         if (!(pt_host[2 * i] >= 0.0) || !(pt_host[2 * i + 1] > 0.0))
             return sr::fail(SR_ERR_ARG, "cell %d: P=%g hPa T=%g K", i, pt_host[2 * i],
                             pt_host[2 * i + 1]);
-    const size_t cell_elems = (size_t)ls->n_sets * 3 * ls->n_grid;
+    const size_t cell_elems = (size_t)ls->n_sets * 3 * row_stride;
     const size_t esz = f32 ? sizeof(float) : sizeof(double);
     if (ls->n_act == 0) {
         SR_CUDA(cudaMemsetAsync(out_dev, 0, cell_elems * n_cells * esz, st));
@@ -1025,6 +1029,7 @@ static int gcoeff_cells_impl(sr_lineset* ls, const double* pt_host, int n_cells,
         ta.zero_rows = ls->zero_rows.p;
         ta.out = (char*)out_dev + (size_t)c0 * cell_elems * esz;
         ta.n_grid = ls->n_grid;
+        ta.row_stride = row_stride;
         ta.n_lines = ls->n_act;
         ta.n_sets = ls->n_sets;
         ta.n_groups = ls->n_groups;
@@ -1084,6 +1089,13 @@ int sr_gcoeff_cells_dev_f32(sr_lineset* ls, const double* pt_host, int n_cells, 
         return sr::fail(SR_ERR_ARG, "sr_gcoeff_cells_dev_f32: bad argument");
     (void)scratch_dev;   // the tile kernel rounds to float32 (numpy astype) in its store
     return gcoeff_cells_impl(ls, pt_host, n_cells, out32_dev, true, (cudaStream_t)stream);
+}
+
+int sr_gcoeff_cells_dev_f32_ld(sr_lineset* ls, const double* pt_host, int n_cells,
+                               float* out32_dev, long row_stride, void* stream) {
+    if (!ls || !pt_host || n_cells < 0 || !out32_dev)
+        return sr::fail(SR_ERR_ARG, "sr_gcoeff_cells_dev_f32_ld: bad argument");
+    return gcoeff_cells_impl(ls, pt_host, n_cells, out32_dev, true, (cudaStream_t)stream, row_stride);
 }
 
 int sr_line_shapes_dev(sr_lineset* ls, double pres_hpa, double temp, double* shapes_dev,

@@ -121,18 +121,20 @@ class LineSet(object):
 
     def gcoeff_cells_f32(self, PTcouples, out=None, stream=None):
         """Same as gcoeff_cells but stored as float32 (the compressed LUT,
-        spect_main_module.py:1676); the tile kernel rounds in its store, no FP64 copy exists."""
+        spect_main_module.py:1676); the tile kernel rounds in its store, no FP64 copy exists.
+        The result is a [n_cells, n_sets, 3, n_grid] view of a table whose rows are padded to a
+        multiple of 32 floats (lut_tensor): 128-byte aligned rows for the LOS kernels.  `out` may
+        be such a view (or a dim-0 slice of one) or a plain contiguous tensor."""
         torch = _torch()
         pt = as_f64(np.asarray(PTcouples, dtype=float).reshape(-1, 2))
         n_cells = pt.shape[0]
         if out is None:
-            out = torch.empty((n_cells, self.n_sets, 3, self.n_grid), dtype=torch.float32,
-                              device="cuda")
-        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
-        assert out.numel() == self.cells_elems(n_cells)
+            out = lut_tensor(n_cells, self.n_sets, self.n_grid)
+        rs = lut_row_stride(out)
+        assert tuple(out.shape) == (n_cells, self.n_sets, 3, self.n_grid)
         sp = _stream_ptr(stream)
-        check(lib().sr_gcoeff_cells_dev_f32(self._h, dptr(pt), n_cells,
-                                            C.c_void_p(out.data_ptr()), None, sp))
+        check(lib().sr_gcoeff_cells_dev_f32_ld(self._h, dptr(pt), n_cells,
+                                               C.c_void_p(out.data_ptr()), rs, sp))
         check(lib().sr_lineset_check(self._h, sp))
         return out
 
@@ -157,6 +159,64 @@ class LineSet(object):
         return shapes, g
 
 
+def lut_tensor(n_cells, n_sets, n_grid, zero=False):
+    """Float32 LUT storage [n_cells, n_sets, 3, n_grid] as a view of a row-padded CUDA tensor
+    (row stride = n_grid rounded up to 32 floats; the padding is zero)."""
+    torch = _torch()
+    rs = (int(n_grid) + 31) // 32 * 32
+    alloc = torch.zeros if zero else torch.empty
+    base = alloc((int(n_cells), int(n_sets), 3, rs), dtype=torch.float32, device="cuda")
+    if not zero and rs > n_grid:
+        base[..., n_grid:].zero_()
+    return base[..., :n_grid]
+
+
+def lut_from_host(arr):
+    """Row-padded device LUT (see lut_tensor) from a host array [n_cells, n_sets, 3, n_grid]."""
+    torch = _torch()
+    arr = np.asarray(arr, dtype=np.float32)
+    out = lut_tensor(arr.shape[0], arr.shape[1], arr.shape[3])
+    out.copy_(torch.from_numpy(np.ascontiguousarray(arr)))
+    return out
+
+
+def lut_cat(tables):
+    """Concatenate LUT tensors along the cell axis, keeping the padded-row layout."""
+    torch = _torch()
+    n = sum(t.shape[0] for t in tables)
+    out = lut_tensor(n, tables[0].shape[1], tables[0].shape[3])
+    c = 0
+    for t in tables:
+        out[c:c + t.shape[0]].copy_(t)
+        c += t.shape[0]
+    return out
+
+
+def lut_row_stride(g32):
+    """Row stride (floats) of a LUT tensor: a contiguous [n_cells, n_sets, 3, n_grid] tensor or a
+    view over padded rows as made by lut_tensor."""
+    torch = _torch()
+    assert g32.is_cuda and g32.dtype == torch.float32 and g32.dim() == 4 and g32.shape[2] == 3
+    n_cells, n_sets, _, n_grid = g32.shape
+    rs = g32.stride(2) if n_grid > 1 else n_grid
+    ok = g32.stride(3) == 1 and rs >= n_grid and g32.stride(1) == 3 * rs and \
+        (n_cells == 1 or g32.stride(0) == n_sets * 3 * rs)
+    if not ok:
+        raise ValueError("LUT tensor must be [n_cells, n_sets, 3, n_grid] with unit point stride "
+                         "and uniformly padded rows (strides %s)" % (g32.stride(),))
+    return int(rs)
+
+
+def lut_padded(g32):
+    """The contiguous row-padded tensor behind a LUT view (for collectives, which need
+    contiguous memory)."""
+    torch = _torch()
+    rs = lut_row_stride(g32)
+    n_cells, n_sets, _, _ = g32.shape
+    return torch.as_strided(g32, (n_cells, n_sets, 3, rs), (n_sets * 3 * rs, 3 * rs, rs, 1),
+                            g32.storage_offset())
+
+
 class Lut(object):
     """Float32 LUT of one isotopologue resident on the device (sr_lut in spectrobot.h).
 
@@ -166,8 +226,7 @@ class Lut(object):
     """
 
     def __init__(self, g32, PTcouples, mol, iso, iso_ratio, level_energies=None, consts=None):
-        torch = _torch()
-        assert g32.is_cuda and g32.dtype == torch.float32 and g32.is_contiguous() and g32.dim() == 4
+        rs = lut_row_stride(g32)
         self.g32 = g32
         self.pt = as_f64(np.asarray(PTcouples, dtype=float).reshape(-1, 2))
         n_cells, n_sets, three, n_grid = g32.shape
@@ -180,11 +239,11 @@ class Lut(object):
             raise ValueError("level_energies must have one entry per set")
         self.consts = consts if consts is not None else _lib.python_consts()
         self._h = C.c_void_p()
-        check(lib().sr_lut_create(C.c_void_p(g32.data_ptr()), dptr(self.pt), n_cells, n_sets,
-                                  n_grid,
-                                  None if self.level_energies is None else dptr(self.level_energies),
-                                  self.mol, self.iso, self.iso_ratio, int(self.lte_unidentified),
-                                  C.byref(self.consts), C.byref(self._h)))
+        check(lib().sr_lut_create_ld(
+            C.c_void_p(g32.data_ptr()), rs, dptr(self.pt), n_cells, n_sets, n_grid,
+            None if self.level_energies is None else dptr(self.level_energies),
+            self.mol, self.iso, self.iso_ratio, int(self.lte_unidentified),
+            C.byref(self.consts), C.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

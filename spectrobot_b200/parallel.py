@@ -72,10 +72,14 @@ def gather_lut(g32, n_cells, rank, n_ranks):
     import torch.distributed as dist
     if n_ranks == 1:
         return g32
+    buf = g32
+    if g32.is_cuda and not g32.is_contiguous():   # row-padded LUT view: send the padded rows
+        from . import engine
+        buf = engine.lut_padded(g32)
     for src in range(n_ranks):
         b, e = shard_range(n_cells, src, n_ranks)
         if e > b:
-            dist.broadcast(g32[b:e], src=src)   # contiguous view: received in place
+            dist.broadcast(buf[b:e], src=src)   # contiguous slice: received in place
     return g32
 
 

@@ -236,8 +236,7 @@ class LookUpTable(object):
         if n_sets != len(names):
             raise ValueError('isotopologue {} has no levels but LTE is False'.format(self.tag))
         grid = self.spectral_grid.grid
-        self.g32 = torch.zeros((len(self.PTcouples), n_sets, 3, len(grid)), dtype=torch.float32,
-                               device="cuda")
+        self.g32 = engine.lut_tensor(len(self.PTcouples), n_sets, len(grid), zero=True)
         idx = list(range(len(self.PTcouples))) if cells is None else list(cells)
         if idx:
             ls = engine.LineSet(tab, grid, self.MM, n_sets)
@@ -281,7 +280,7 @@ class LookUpTable(object):
             raise ValueError('Incompatible LUTs, different wn_ranges: {} {}'.format(
                 self.wn_range, LUT.wn_range))
         self.PTcouples += LUT.PTcouples
-        self.g32 = torch.cat([self.g32, LUT.g32], dim=0)
+        self.g32 = engine.lut_cat([self.g32, LUT.g32])
         for st in self.sets.values():
             st.PTcouples = self.PTcouples
             st.free_memory()
