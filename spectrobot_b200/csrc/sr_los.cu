@@ -299,6 +299,78 @@ struct ProgEntry {
     int pad;
 };
 
+// K3: I <- I exp(-tau) + S (1 - exp(-tau)) over materialised layers; pure HBM streaming.
+// A work item is (LOS, tile of NT*PPT points): each thread owns PPT points (stride NT, so every
+// warp load is one coalesced 256-byte row segment for any n_pts parity) and keeps UNROLL steps x
+// PPT points x 2 arrays of loads in flight.
+struct RecArgs {
+    const double* tau;        // [n_los][n_steps_max][lay_stride]
+    const double* src;
+    const int* n_steps;       // [n_los]
+    const double* i0;         // [n_los][io_stride] window at io_off, or nullptr
+    double* rad;              // [n_los][io_stride] window at io_off
+    long n_pts, io_stride, io_off, lay_stride;
+    long n_work;              // n_los * n_tiles (0: nothing to do)
+    int n_steps_max, n_tiles, solo, src_is_j;
+};
+
+template <int PPT, int UNROLL, int NT>
+__device__ __forceinline__ void layers_item(const RecArgs& r, long w) {
+    const int l = (int)(w / r.n_tiles);
+    const long p0 = (long)(w % r.n_tiles) * (NT * PPT) + threadIdx.x;
+    if (p0 >= r.n_pts) return;
+    bool ok[PPT];
+    double I[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; i++) {
+        ok[i] = p0 + i * NT < r.n_pts;
+        I[i] = (r.i0 && ok[i]) ? r.i0[(size_t)l * r.io_stride + r.io_off + p0 + i * NT] : 0.0;
+    }
+    const int ns = r.n_steps[l];
+    const long ls = r.lay_stride;
+    const double* __restrict__ tp = r.tau + (size_t)l * r.n_steps_max * ls + p0;
+    const double* __restrict__ sp = r.src + (size_t)l * r.n_steps_max * ls + p0;
+    const int solo = r.solo, src_is_j = r.src_is_j;
+    auto update = [&](int i, double t, double s) {
+        double ex, em;
+        srdev::exp_pair(-t, ex, em);
+        if (src_is_j) {   // s = J: I <- I e^-tau + J phi(tau), phi = (1 - e^-tau)/tau (DESIGN 6.4)
+            const double phi = (t == 0.0) ? 1.0 : -em / t;
+            I[i] = solo ? I[i] * ex : fma(I[i], ex, s * phi);
+        } else {
+            I[i] = solo ? I[i] * ex : fma(I[i], ex, -s * em);
+        }
+    };
+    int k = 0;
+    for (; k + UNROLL <= ns; k += UNROLL) {
+        double t[UNROLL][PPT], s[UNROLL][PPT];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+            for (int i = 0; i < PPT; i++) {
+                const size_t o = (size_t)(k + u) * ls + i * NT;
+                t[u][i] = ok[i] ? __ldcs(tp + o) : 0.0;
+                s[u][i] = ok[i] ? __ldcs(sp + o) : 0.0;
+            }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+            for (int i = 0; i < PPT; i++) update(i, t[u][i], s[u][i]);
+    }
+    for (; k < ns; k++)
+#pragma unroll
+        for (int i = 0; i < PPT; i++)
+            if (ok[i]) update(i, __ldcs(tp + (size_t)k * ls + i * NT), __ldcs(sp + (size_t)k * ls + i * NT));
+#pragma unroll
+    for (int i = 0; i < PPT; i++)
+        if (ok[i]) __stcs(r.rad + (size_t)l * r.io_stride + r.io_off + p0 + i * NT, I[i]);
+}
+
+template <int PPT, int UNROLL>
+__global__ void __launch_bounds__(256) k_los_layers(RecArgs r) {
+    for (long w = blockIdx.x; w < r.n_work; w += gridDim.x) layers_item<PPT, UNROLL, 256>(r, w);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3a on the FP64 tensor path (v3).  Same grouping as v2, but the per-CTA product
 //   C[16 pairs][points] += A[16 pairs][rows] * B[rows][points]
@@ -327,6 +399,7 @@ struct MmaArgs {
     int max_jp, chunk0;
     long pair_base;               // first pair of the LOS block (rows of tau_out/src_out are local)
     long pt0, n_pts;
+    long ld_min;                  // smallest LUT row stride: loads are clamped below it
     long ld_out;                  // stride of the output rows (>= n_pts)
     double* tau_out;              // [pairs of the block][ld_out]
     double* src_out;
@@ -371,10 +444,31 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 // the output rows have a stride that is a multiple of 4 -> one LDG.128 per lane brings 4 points of
 // one row (a warp load = 4 rows x 128 contiguous bytes), and each lane ends up with 8 consecutive
 // points of one pair, written as 16-byte vectors.  Point <-> fragment maps:
-//   VEC    B(v,i): point 32v + 4(lane>>2) + i         C(v,i)[e]: point 32v + 8(lane&3) + 4e + i
+//   VEC    B(v,i): point 32v + pn(lane>>2) + i, pn(n) = 4(n>>1) + 16(n&1)
+//          C(v,i)[e]: point 32v + 16e + 4(lane&3) + i   (n = 2(lane&3) + e)
+//          -> a store instruction (v,e) writes 32 B per lane, 128 contiguous bytes per pair row
 //   scalar B(i)  : point 8i + (lane>>2)               C(i)[e]  : point 8i + 2(lane&3) + e
-template <int NB, bool VEC>
-__global__ void __launch_bounds__(MMA_NT, 4) k_los_mma(MmaArgs a) {
+// one 32-byte streaming store (a full sector per lane)
+__device__ __forceinline__ void st_cs_v4(double* p, const double (&x)[4]) {
+    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]),
+                 "d"(x[3]) : "memory");
+}
+
+// LUT row loads: LD = 0 read-only path (ld.global.nc), 1 streaming (ld.global.cs), 2 no L1
+// allocation (tuning aid, SR_MMA_LD)
+template <int LD>
+__device__ __forceinline__ float4 ld_row4(const float* p) {
+    float4 q;
+    if (LD == 1) q = __ldcs(reinterpret_cast<const float4*>(p));
+    else if (LD == 2)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "l"(p));
+    else q = __ldg(reinterpret_cast<const float4*>(p));
+    return q;
+}
+
+template <int NB, bool VEC, int MINB, int LD>
+__global__ void __launch_bounds__(MMA_NT, MINB) k_los_mma(MmaArgs a) {
     extern __shared__ __align__(16) unsigned char msm[];
     double* wA = reinterpret_cast<double*>(msm);                                   // [kb][2][32]
     long long* rps = reinterpret_cast<long long*>(wA + (size_t)a.max_jp * MMA_PB);   // [max_jp]
@@ -397,49 +491,76 @@ __global__ void __launch_bounds__(MMA_NT, 4) k_los_mma(MmaArgs a) {
     const long p_warp = (long)blockIdx.y * ((MMA_NT / 32) * 8 * NB) + wid * (8 * NB);
     if (p_warp >= a.n_pts) return;
     struct Frag { float v[NB]; };
+    // per-lane point offsets inside a LUT row; lanes beyond the point window re-read the last
+    // valid vector of the row (their columns are never stored), so every load is unconditional
+    long loff[VEC ? NB / 4 : NB];
+    if (VEC) {
+#pragma unroll
+        for (int v = 0; v < NB / 4; v++)
+            loff[v] = min(a.pt0 + p_warp + 32 * v + 4 * (nq >> 1) + 16 * (nq & 1), a.ld_min - 4);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NB; i++) loff[i] = min(a.pt0 + p_warp + 8 * i + nq, a.ld_min - 1);
+    }
     auto load = [&](int j, Frag& f) {
-        const float* __restrict__ r = reinterpret_cast<const float*>(rps[j + kq]) + a.pt0 + p_warp;
+        const float* __restrict__ r = reinterpret_cast<const float*>(rps[j + kq]);
         if (VEC) {
 #pragma unroll
             for (int v = 0; v < NB / 4; v++) {
-                const int p = 32 * v + 4 * nq;
-                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p_warp + p < a.n_pts) q = __ldg(reinterpret_cast<const float4*>(r + p));
+                const float4 q = ld_row4<LD>(r + loff[v]);
                 f.v[4 * v + 0] = q.x; f.v[4 * v + 1] = q.y; f.v[4 * v + 2] = q.z; f.v[4 * v + 3] = q.w;
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < NB; i++)
-                f.v[i] = (p_warp + 8 * i + nq < a.n_pts) ? __ldg(r + 8 * i + nq) : 0.0f;
+            for (int i = 0; i < NB; i++) f.v[i] = __ldg(r + loff[i]);
         }
     };
     double C0[NB][2], C1[NB][2];
-    // rows [j0, j1) into the accumulators; B fragments are fetched two k-steps ahead
+    // rows [j0, j1) into the accumulators.  Three B-fragment buffers rotate without register
+    // copies: a buffer is refilled (rows j+12.., clamped to the last k-step of the pass) right
+    // after its values have been converted, so every load has two full k-steps (>= 32 DMMA) to
+    // arrive.  The main loop has no conditional code around the buffers (a merge point would make
+    // the compiler copy the freshly loaded registers, i.e. wait for the load at once).
+    auto mma_step = [&](int j, const double (&b)[NB]) {
+        const double a0 = wA[(j >> 2) * 64 + lane];
+        if (two) {
+            const double a1 = wA[(j >> 2) * 64 + 32 + lane];
+#pragma unroll
+            for (int i = 0; i < NB; i++) {
+                dmma884(C0[i], a0, b[i]);
+                dmma884(C1[i], a1, b[i]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NB; i++) dmma884(C0[i], a0, b[i]);
+        }
+    };
+#define SR_KSTEP(J, F, RELOAD)                                        \
+    {                                                                 \
+        double b_[NB];                                                \
+        _Pragma("unroll") for (int i = 0; i < NB; i++) b_[i] = (double)F.v[i]; \
+        if (RELOAD) load(min((J) + 12, j1 - 4), F);                   \
+        mma_step((J), b_);                                            \
+    }
     auto pass = [&](int j0, int j1) {
 #pragma unroll
         for (int i = 0; i < NB; i++) C0[i][0] = C0[i][1] = C1[i][0] = C1[i][1] = 0.0;
-        Frag g, g1, g2;
-        if (j0 < j1) load(j0, g1);
-        if (j0 + 4 < j1) load(j0 + 4, g2);
-        for (int j = j0; j < j1; j += 4) {
-            g = g1;
-            g1 = g2;
-            if (j + 8 < j1) load(j + 8, g2);
-            const double a0 = wA[(j >> 2) * 64 + lane];
-            if (two) {
-                const double a1 = wA[(j >> 2) * 64 + 32 + lane];
-#pragma unroll
-                for (int i = 0; i < NB; i++) {
-                    const double b = (double)g.v[i];
-                    dmma884(C0[i], a0, b);
-                    dmma884(C1[i], a1, b);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < NB; i++) dmma884(C0[i], a0, (double)g.v[i]);
-            }
+        if (j0 >= j1) return;
+        Frag f0, f1, f2;
+        load(j0, f0);
+        load(min(j0 + 4, j1 - 4), f1);
+        load(min(j0 + 8, j1 - 4), f2);
+        int j = j0;
+#pragma unroll 1
+        for (; j + 12 <= j1; j += 12) {
+            SR_KSTEP(j, f0, true)
+            SR_KSTEP(j + 4, f1, true)
+            SR_KSTEP(j + 8, f2, true)
         }
+        if (j < j1) SR_KSTEP(j, f0, false)
+        if (j + 4 < j1) SR_KSTEP(j + 4, f1, false)
     };
+#undef SR_KSTEP
     auto store = [&](double* __restrict__ out, bool as_src) {
 #pragma unroll
         for (int mb = 0; mb < 2; mb++) {
@@ -455,7 +576,7 @@ __global__ void __launch_bounds__(MMA_NT, 4) k_los_mma(MmaArgs a) {
                 for (int v = 0; v < NB / 4; v++)
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
-                        const int off = 32 * v + 8 * kq + 4 * e;
+                        const int off = 32 * v + 16 * e + 4 * kq;
                         if (p_warp + off >= a.n_pts) continue;   // rows are padded to ld_out
                         double x[4];
 #pragma unroll
@@ -466,8 +587,7 @@ __global__ void __launch_bounds__(MMA_NT, 4) k_los_mma(MmaArgs a) {
                                 x[i] = (t == 0.0) ? 0.0 : x[i] / t;
                             }
                         }
-                        __stcs(reinterpret_cast<double2*>(o + off), make_double2(x[0], x[1]));
-                        __stcs(reinterpret_cast<double2*>(o + off + 2), make_double2(x[2], x[3]));
+                        st_cs_v4(o + off, x);
                     }
             } else {
 #pragma unroll
@@ -490,66 +610,6 @@ __global__ void __launch_bounds__(MMA_NT, 4) k_los_mma(MmaArgs a) {
     store(a.tau_out, false);
     pass(n_tau, n_tot);
     store(a.src_out, true);
-}
-
-// K3: I <- I exp(-tau) + S (1 - exp(-tau)) over materialised layers; pure HBM streaming.
-// Each thread owns PPT points (stride 256, so every warp load is one coalesced 256-byte row
-// segment for any n_pts parity) and keeps UNROLL steps x PPT points x 2 arrays of loads in flight.
-template <int PPT, int UNROLL>
-__global__ void __launch_bounds__(256) k_los_layers(const double* __restrict__ tau,
-                                                    const double* __restrict__ src,
-                                                    const int* __restrict__ n_steps,
-                                                    int n_steps_max, long n_pts,
-                                                    const double* __restrict__ i0, int solo,
-                                                    double* __restrict__ rad, int src_is_j,
-                                                    long io_stride, long io_off, long lay_stride) {
-    const int l = blockIdx.y;
-    const long p0 = (long)blockIdx.x * (256 * PPT) + threadIdx.x;
-    if (p0 >= n_pts) return;
-    bool ok[PPT];
-    double I[PPT];
-#pragma unroll
-    for (int i = 0; i < PPT; i++) {
-        ok[i] = p0 + i * 256 < n_pts;
-        I[i] = (i0 && ok[i]) ? i0[(size_t)l * io_stride + io_off + p0 + i * 256] : 0.0;
-    }
-    const int ns = n_steps[l];
-    const double* __restrict__ tp = tau + (size_t)l * n_steps_max * lay_stride + p0;
-    const double* __restrict__ sp = src + (size_t)l * n_steps_max * lay_stride + p0;
-    auto update = [&](int i, double t, double s) {
-        double ex, em;
-        srdev::exp_pair(-t, ex, em);
-        if (src_is_j) {   // s = J: I <- I e^-tau + J phi(tau), phi = (1 - e^-tau)/tau (DESIGN 6.4)
-            const double phi = (t == 0.0) ? 1.0 : -em / t;
-            I[i] = solo ? I[i] * ex : fma(I[i], ex, s * phi);
-        } else {
-            I[i] = solo ? I[i] * ex : fma(I[i], ex, -s * em);
-        }
-    };
-    int k = 0;
-    for (; k + UNROLL <= ns; k += UNROLL) {
-        double t[UNROLL][PPT], s[UNROLL][PPT];
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++)
-#pragma unroll
-            for (int i = 0; i < PPT; i++) {
-                const size_t o = (size_t)(k + u) * lay_stride + i * 256;
-                t[u][i] = ok[i] ? __ldcs(tp + o) : 0.0;
-                s[u][i] = ok[i] ? __ldcs(sp + o) : 0.0;
-            }
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++)
-#pragma unroll
-            for (int i = 0; i < PPT; i++) update(i, t[u][i], s[u][i]);
-    }
-    for (; k < ns; k++)
-#pragma unroll
-        for (int i = 0; i < PPT; i++)
-            if (ok[i]) update(i, __ldcs(tp + (size_t)k * lay_stride + i * 256),
-                              __ldcs(sp + (size_t)k * lay_stride + i * 256));
-#pragma unroll
-    for (int i = 0; i < PPT; i++)
-        if (ok[i]) __stcs(rad + (size_t)l * io_stride + io_off + p0 + i * 256, I[i]);
 }
 
 }  // namespace
@@ -819,22 +879,42 @@ int sr_lut_weights(const double* pt_host, int n_cells, double pres, double temp,
     return SR_OK;
 }
 
+static RecArgs rec_args(const double* tau, const double* src, const int* n_steps, int n_los,
+                        int n_steps_max, long n_pts, const double* i0, int solo_absorption,
+                        double* rad, int src_is_j, long io_stride, long io_off, long lay_stride,
+                        int tile_pts) {
+    RecArgs r;
+    r.tau = tau;
+    r.src = src;
+    r.n_steps = n_steps;
+    r.i0 = i0;
+    r.rad = rad;
+    r.n_pts = n_pts;
+    r.io_stride = io_stride < 0 ? n_pts : io_stride;   // rad / i0 rows: [n_los][io_stride], window at io_off
+    r.io_off = io_off;
+    r.lay_stride = lay_stride < 0 ? n_pts : lay_stride;   // tau / src rows: [n_los][n_steps_max][lay_stride]
+    r.n_steps_max = n_steps_max;
+    r.n_tiles = (int)((n_pts + tile_pts - 1) / tile_pts);
+    r.n_work = (long)r.n_tiles * n_los;
+    r.solo = solo_absorption;
+    r.src_is_j = src_is_j;
+    return r;
+}
+
 static int layers_launch(const double* tau, const double* src, const int* n_steps, int n_los,
                          int n_steps_max, long n_pts, const double* i0, int solo_absorption,
                          double* rad, cudaStream_t st, int src_is_j, long io_stride = -1,
                          long io_off = 0, long lay_stride = -1) {
-    if (io_stride < 0) io_stride = n_pts;   // rad / i0 rows: [n_los][io_stride], window at io_off
-    if (lay_stride < 0) lay_stride = n_pts; // tau / src rows: [n_los][n_steps_max][lay_stride]
     // measured on B200 (tools/tune.py): (PPT=1, UNROLL=4) at 38 registers streams at the
     // measured copy bandwidth; wider variants lose occupancy
     int cfg = 5;
     if (const char* e = getenv("SR_K3_CFG")) cfg = atoi(e);   // tuning aid
 #define SR_K3_LAUNCH(PPT, UNROLL)                                                             \
     {                                                                                          \
-        dim3 grid((unsigned)((n_pts + 256 * PPT - 1) / (256 * PPT)), n_los);                   \
-        SR_LAUNCH((k_los_layers<PPT, UNROLL>), grid, 256, 0, st, tau, src, n_steps,            \
-                  n_steps_max, n_pts, i0, solo_absorption, rad, src_is_j, io_stride, io_off,   \
-                  lay_stride);                                                                 \
+        const RecArgs r = rec_args(tau, src, n_steps, n_los, n_steps_max, n_pts, i0,           \
+                                   solo_absorption, rad, src_is_j, io_stride, io_off,          \
+                                   lay_stride, 256 * PPT);                                     \
+        SR_LAUNCH((k_los_layers<PPT, UNROLL>), (unsigned)r.n_work, 256, 0, st, r);             \
     }
     switch (cfg) {
         case 1: SR_K3_LAUNCH(1, 8) break;
@@ -1004,9 +1084,39 @@ static int build_plan(sr_lut* const* luts, const sr_los_steps* S, int nl_block, 
         P.blk_chunk.push_back(P.n_chunks);
     }
     P.rowptr.resize(P.prog.size());
-    for (size_t q = 0; q < P.prog.size(); q++) P.rowptr[q] = P.prog[q].roff;
+    const bool same_row = getenv("SR_MMA_SAMEROW") != nullptr;   // timing experiment only (wrong results)
+    for (size_t q = 0; q < P.prog.size(); q++)
+        P.rowptr[q] = same_row ? (long long)luts[0]->g32 : P.prog[q].roff;
     return SR_OK;
 }
+
+}  // extern "C"
+
+constexpr int MMA_NB = 8;   // 8-point N blocks per warp: 64 points per warp, 256 per CTA
+
+template <bool VEC, int MINB, int LD>
+static int mma_launch_t(dim3 grid, size_t smem, cudaStream_t st, const MmaArgs& ma) {
+    SR_CUDA(cudaFuncSetAttribute(k_los_mma<MMA_NB, VEC, MINB, LD>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SR_LAUNCH((k_los_mma<MMA_NB, VEC, MINB, LD>), grid, MMA_NT, smem, st, ma);
+    return SR_OK;
+}
+
+static int mma_launch(bool vec, dim3 grid, size_t smem, cudaStream_t st, const MmaArgs& ma) {
+    static const int minb = getenv("SR_MMA_MINB") ? atoi(getenv("SR_MMA_MINB")) : 4;   // tuning aids
+    static const int ld = getenv("SR_MMA_LD") ? atoi(getenv("SR_MMA_LD")) : 0;
+    if (!vec) return mma_launch_t<false, 3, 0>(grid, smem, st, ma);
+    if (minb == 3) {
+        if (ld == 1) return mma_launch_t<true, 3, 1>(grid, smem, st, ma);
+        if (ld == 2) return mma_launch_t<true, 3, 2>(grid, smem, st, ma);
+        return mma_launch_t<true, 3, 0>(grid, smem, st, ma);
+    }
+    if (ld == 1) return mma_launch_t<true, 4, 1>(grid, smem, st, ma);
+    if (ld == 2) return mma_launch_t<true, 4, 2>(grid, smem, st, ma);
+    return mma_launch_t<true, 4, 0>(grid, smem, st, ma);
+}
+
+extern "C" {
 
 // host-buffer sink of los_launch: radiances leave the device block by block, chunk by chunk, on a
 // second stream while the next chunk is computed
@@ -1091,12 +1201,14 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
     if (P.max_jp > GEMM_MAXJ)
         return sr::fail(SR_ERR_LIMIT, "LOS: %d LUT rows per cell quad (limit %d)", P.max_jp, GEMM_MAXJ);
     const size_t smem = (size_t)P.max_jp * (MMA_PB * sizeof(double) + sizeof(long long)) + 16;
-    constexpr int NB = 8;
-    constexpr int TILE = (MMA_NT / 32) * 8 * NB;
+    constexpr int TILE = (MMA_NT / 32) * 8 * MMA_NB;
     MmaArgs ma;
     bool rows_aligned = true;   // every LUT row starts on a 16-byte boundary
-    for (int m = 0; m < steps->n_gas; m++)
+    ma.ld_min = luts[0]->row_stride;
+    for (int m = 0; m < steps->n_gas; m++) {
         rows_aligned = rows_aligned && luts[m]->row_stride % 4 == 0 && (size_t)luts[m]->g32 % 16 == 0;
+        ma.ld_min = std::min(ma.ld_min, luts[m]->row_stride);
+    }
     if (const char* e = getenv("SR_LOS_NOVEC")) rows_aligned = rows_aligned && atoi(e) == 0;
     if (P.n_chunks > 0) {
         SR_CUDA(L0->g_prog.upload(reinterpret_cast<const char*>(P.prog.data()),
@@ -1120,8 +1232,6 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         pa.n_chunks = P.n_chunks;
         const long n_el = (long)P.n_chunks * P.max_jp * MMA_PB;
         SR_LAUNCH(k_pack_wfrag, (unsigned)((n_el + 255) / 256), 256, 0, st, pa);
-        SR_CUDA(cudaFuncSetAttribute(k_los_mma<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SR_CUDA(cudaFuncSetAttribute(k_los_mma<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ma.rowptr = L0->g_rowptr.p;
         ma.grp_ntau = L0->g_ntau.p;
         ma.grp_ntot = L0->g_ntot.p;
@@ -1142,16 +1252,18 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         ma.mode = emit_j;
         dim3 grid((unsigned)P.n_chunks, (unsigned)((n_pts + TILE - 1) / TILE));
         const bool vec = rows_aligned && pt0 % 4 == 0 && n_pts % 4 == 0 &&
-                         ((size_t)tau_dev | (size_t)src_dev) % 16 == 0;
-        if (vec) SR_LAUNCH((k_los_mma<NB, true>), grid, MMA_NT, smem, st, ma);
-        else SR_LAUNCH((k_los_mma<NB, false>), grid, MMA_NT, smem, st, ma);
-        return SR_OK;
+                         ((size_t)tau_dev | (size_t)src_dev) % 32 == 0;
+        return mma_launch(vec, grid, smem, st, ma);
     }
+    // Per (LOS block, wavenumber chunk): product into the layer scratch, then the streaming
+    // recursion.  (Running the two concurrently - second stream, persistent recursion CTAs, or
+    // recursion items inside the product CTAs - was measured slower on B200: the product keeps
+    // the whole register file busy and the recursion needs >= 4 CTAs per SM of loads in flight.)
     const size_t blk_pairs = (size_t)nl_block * nmax;
     const long ld_lay = (chunk_pts + 3) / 4 * 4;   // scratch rows: 32-byte aligned for any chunk size
     SR_CUDA(L0->ws_tau.ensure(blk_pairs * ld_lay));
     SR_CUDA(L0->ws_src.ensure(blk_pairs * ld_lay));
-    cudaEvent_t buf_free[2] = {nullptr, nullptr};
+    cudaEvent_t buf_free[2] = {nullptr, nullptr};   // host sink: copies of a radiance buffer done
     if (sink) {
         if (!L0->copy_stream)
             SR_CUDA(cudaStreamCreateWithFlags(&L0->copy_stream, cudaStreamNonBlocking));
@@ -1193,10 +1305,8 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
                     ma.src_out = L0->ws_src.p;
                     ma.mode = 1;
                     dim3 grid((unsigned)n_ch, (unsigned)((np + TILE - 1) / TILE));
-                    if (rows_aligned && (pt0 + c0) % 4 == 0)
-                        SR_LAUNCH((k_los_mma<NB, true>), grid, MMA_NT, smem, st, ma);
-                    else
-                        SR_LAUNCH((k_los_mma<NB, false>), grid, MMA_NT, smem, st, ma);
+                    int code = mma_launch(rows_aligned && (pt0 + c0) % 4 == 0, grid, smem, st, ma);
+                    if (code) return code;
                 }
                 // radiances (and i0) rows have stride n_pts; this chunk is the window [c0, c0+np)
                 int code = layers_launch(L0->ws_tau.p, L0->ws_src.p, la.n_steps + l0, nl,
@@ -1228,7 +1338,6 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         if (buf_free[b]) cudaEventDestroy(buf_free[b]);
     return status;
 }
-
 
 int sr_los_rt_lut_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
                       const double* i0_dev, int solo_absorption, double* rad_dev, void* stream) {
