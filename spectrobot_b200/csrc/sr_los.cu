@@ -300,7 +300,7 @@ struct ProgEntry {
 };
 
 // K3: I <- I exp(-tau) + S (1 - exp(-tau)) over materialised layers; pure HBM streaming.
-// A work item is (LOS, tile of NT*PPT points): each thread owns PPT points (stride NT, so every
+// A CTA is (LOS, tile of NT*PPT points): each thread owns PPT points (stride NT, so every
 // warp load is one coalesced 256-byte row segment for any n_pts parity) and keeps UNROLL steps x
 // PPT points x 2 arrays of loads in flight.
 struct RecArgs {
@@ -315,9 +315,8 @@ struct RecArgs {
 };
 
 template <int PPT, int UNROLL, int NT>
-__device__ __forceinline__ void layers_item(const RecArgs& r, long w) {
-    const int l = (int)(w / r.n_tiles);
-    const long p0 = (long)(w % r.n_tiles) * (NT * PPT) + threadIdx.x;
+__device__ __forceinline__ void layers_item(const RecArgs& r, int l, int tile) {
+    const long p0 = (long)tile * (NT * PPT) + threadIdx.x;
     if (p0 >= r.n_pts) return;
     bool ok[PPT];
     double I[PPT];
@@ -367,8 +366,8 @@ __device__ __forceinline__ void layers_item(const RecArgs& r, long w) {
 }
 
 template <int PPT, int UNROLL>
-__global__ void __launch_bounds__(256) k_los_layers(RecArgs r) {
-    for (long w = blockIdx.x; w < r.n_work; w += gridDim.x) layers_item<PPT, UNROLL, 256>(r, w);
+__global__ void __launch_bounds__(256, 6) k_los_layers(const __grid_constant__ RecArgs r) {
+    layers_item<PPT, UNROLL, 256>(r, (int)blockIdx.y, (int)blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -914,7 +913,8 @@ static int layers_launch(const double* tau, const double* src, const int* n_step
         const RecArgs r = rec_args(tau, src, n_steps, n_los, n_steps_max, n_pts, i0,           \
                                    solo_absorption, rad, src_is_j, io_stride, io_off,          \
                                    lay_stride, 256 * PPT);                                     \
-        SR_LAUNCH((k_los_layers<PPT, UNROLL>), (unsigned)r.n_work, 256, 0, st, r);             \
+        SR_LAUNCH((k_los_layers<PPT, UNROLL>), dim3((unsigned)r.n_tiles, (unsigned)n_los), 256, \
+                  0, st, r);                                                                   \
     }
     switch (cfg) {
         case 1: SR_K3_LAUNCH(1, 8) break;
