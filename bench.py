@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--e2e-los", type=int, default=360, help="LOS per host call of the e2e leg")
     ap.add_argument("--fused-los", type=int, default=360,
                     help="LOS per rank of the device-resident K3a+K3 leg")
+    ap.add_argument("--batch-pixels", type=int, default=10000,
+                    help="pixels (3 LOS each) of the low-res batch leg, whole job; 0 disables it")
     ap.add_argument("--lines", type=int, default=N_LINES)
     ap.add_argument("--small", action="store_true", help="tiny sizes (CI / debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -60,12 +62,12 @@ def parse():
 # --------------------------------------------------------------------------------------------
 # workload
 # --------------------------------------------------------------------------------------------
-def make_workload(args, rank, n_los):
+def make_workload(args, rank, n_los, want_lines=True):
     from spectrobot_b200 import synthetic as S
     w0, w1 = (2990.0, 3010.0) if args.small else (W0, W1)
     grid = S.spectral_grid(w0, w1)
     n_lines = 600 if args.small else args.lines
-    lines = S.line_table(n_lines, w0, w1, n_levels=N_LEVELS)
+    lines = S.line_table(n_lines if want_lines else 10, w0, w1, n_levels=N_LEVELS)
     atm = S.titan_atmosphere()
     rng = np.random.default_rng(S.SEED + 1000 * rank)
     n_pix = (n_los + 2) // 3
@@ -321,13 +323,21 @@ def run_ours(args):
     ev1.record()
     torch.cuda.synchronize()
     build_dev_s = ev0.elapsed_time(ev1) * 1e-3
-    # cells are independent: the only exchange is the final gather of the LUT (NCCL broadcasts)
+    build_wall_s = max_over_ranks(time.perf_counter() - t0)
+    # cells are independent (no collective on the build itself); the LOS leg below wants the whole
+    # table on every rank, so the cell blocks are exchanged once over NVLink (NCCL broadcasts)
+    barrier()
+    t1 = time.perf_counter()
     parallel.gather_lut(g32, n_cells, rank, world)
     barrier()
-    build_wall_s = max_over_ranks(time.perf_counter() - t0)
+    gather_s = max_over_ranks(time.perf_counter() - t1)
     lut_build = {"metric": "CH4 LUT build time", "value": build_wall_s, "unit": "s",
-                 "cells": n_cells, "device_s_per_rank": max_over_ranks(build_dev_s),
-                 "evals_per_s": n_cells * evals / build_wall_s, "includes": "float32 cast + gather"}
+                 "cells": n_cells, "cells_per_rank": len(my_cells),
+                 "device_s_per_rank": max_over_ranks(build_dev_s),
+                 "evals_per_s": n_cells * evals / build_wall_s,
+                 "includes": "per-cell parameters, core evaluation, tile kernel with float32 store",
+                 "replicate_gather_s": gather_s if world > 1 else 0.0,
+                 "lut_bytes": int(n_cells) * N_LEVELS * 3 * n_grid * 4}
     lut = engine.Lut(g32, cells, 6, 1, S.CH4_RATIO, level_energies=lines["level_energies"])
     steps_all = engine.LosSteps(st_all["n_steps"], st_all["temp"], st_all["pres"],
                                 st_all["column"], st_all["tvib"])
@@ -391,6 +401,41 @@ def run_ours(args):
               sub.tvib.nbytes)
     d2h = int(host_out.nbytes)
 
+    # ---- batch: the north_star batch (10^4 pixels x 3 LOS), reduced to VIMS-like channels -------
+    batch = None
+    n_pix = 40 if args.small else args.batch_pixels
+    if n_pix > 0:
+        del host_out
+        p0, p1 = parallel.shard_range(n_pix, rank, world)      # pixels are split over the ranks
+        n_b = 3 * (p1 - p0)
+        n_uni = min(n_b, 6 if args.small else 6000)            # distinct synthetic geometries
+        wl_b = make_workload(args, 100 + rank, n_uni, want_lines=False)
+        sb_ = wl_b["st"]
+        reps_ = (n_b + n_uni - 1) // n_uni
+        tile = lambda v, ax: np.concatenate([v] * reps_, axis=ax).take(range(n_b), axis=ax)
+        steps_b = engine.LosSteps(tile(sb_["n_steps"], 0), tile(sb_["temp"], 0), tile(sb_["pres"], 0),
+                                  tile(sb_["column"], 1), tile(sb_["tvib"], 2))
+        centres = np.linspace(grid[0] + 10.0, grid[-1] - 10.0, 36)   # ~16 nm sampling at 3.3 um
+        widths = np.full(36, 6.2)                                    # sigma of a 14.6 cm-1 FWHM
+        gdev = torch.as_tensor(grid, device="cuda")
+        cdev, wdev = torch.as_tensor(centres, device="cuda"), torch.as_tensor(widths, device="cuda")
+        warm = steps_b.subset(slice(0, min(n_b, 256)))
+        engine.los_rt_lut_lowres([lut], warm, gdev, cdev, wdev)      # workspaces, first-call costs
+        barrier()
+        t0 = time.perf_counter()
+        low = engine.los_rt_lut_lowres([lut], steps_b, gdev, cdev, wdev)
+        low_host = low.cpu().numpy()                                  # the call's result leaves the device
+        barrier()
+        batch_s = max_over_ranks(time.perf_counter() - t0)
+        batch = {"pixels": n_pix, "los": 3 * n_pix, "seconds": batch_s,
+                 "value": 3 * n_pix / batch_s, "unit": "LOS/s", "channels": 36,
+                 "d2h_bytes": int(low_host.nbytes), "distinct_geometries_per_rank": int(n_uni),
+                 "finite": bool(np.isfinite(low_host).all()),
+                 "path": "sr_los_rt_lut_lowres_dev: step tables on the host in, low-res channel "
+                         "radiances out (wall clock incl. host planning and copies); hi-res radiances "
+                         "exist per LOS block on the device only"}
+        del low, steps_b
+
     peaks = measured_peaks()
     hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
     achieved = k3_bytes / (k3_ms * 1e-3) / 1e9
@@ -412,7 +457,7 @@ def run_ours(args):
                   "los_per_rank": n_fused, "ms_per_step": fused_ms,
                   "step_points_per_s": world * fused_step_pts / (fused_ms * 1e-3),
                   "max_rel_diff_vs_k3": agree},
-        "voigt": voigt, "lut_build": lut_build,
+        "batch": batch, "voigt": voigt, "lut_build": lut_build,
         "gpu_launches": int(launches), "clocks": sampler.summary(),
     }
     if rank == 0 and not args.no_cpu_baseline:

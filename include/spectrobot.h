@@ -198,6 +198,18 @@ int sr_los_rt_lut_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
                       const double* i0_dev, int solo_absorption, double* rad_dev, void* stream);
 int sr_los_rt_lut_host(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
                        const double* i0_host, int solo_absorption, double* rad_host);
+/* Same, reduced to the instrument's low-resolution channels on the device (radtrans ->
+ * hires_to_lowres, spect_main_module.py:3342-3374, spect_classes.py:1180-1191): the batch is
+ * processed in LOS blocks, each block's hi-res radiances are convolved (see
+ * sr_convolve_lowres_dev) and only low_dev [n_los][n_chan] is kept, so a 10^4-pixel batch never
+ * materialises its 288 GB of hi-res output.  grid_dev: the n_pts spectral grid points of the
+ * window [pt0, pt0+n_pts); centre_dev / width_dev: [n_chan] channel centres and Gaussian widths
+ * in the units of the grid (device).  i0_dev: [n_los][n_pts] or NULL. */
+int sr_los_rt_lut_lowres_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
+                             const double* grid_dev, const double* centre_dev,
+                             const double* width_dev, int n_chan, double n_sigma,
+                             const double* i0_dev, int solo_absorption, double* low_dev,
+                             void* stream);
 /* Synchronise `stream` and report LUT-interpolation errors (SR_ERR_LUT) raised by the
  * asynchronous LOS calls that used luts[0] since the last check. */
 int sr_los_check(sr_lut* const* luts, void* stream);

@@ -84,6 +84,9 @@ SIGNATURES = {
     "sr_lut_destroy": (C.c_int, [_vp]),
     "sr_los_rt_lut_dev": (C.c_int, [C.POINTER(_vp), C.POINTER(sr_los_steps), C.c_long, C.c_long,
                                     _vp, C.c_int, _vp, _vp]),
+    "sr_los_rt_lut_lowres_dev": (C.c_int, [C.POINTER(_vp), C.POINTER(sr_los_steps), C.c_long,
+                                           C.c_long, _vp, _vp, _vp, C.c_int, C.c_double, _vp,
+                                           C.c_int, _vp, _vp]),
     "sr_los_rt_lut_host": (C.c_int, [C.POINTER(_vp), C.POINTER(sr_los_steps), C.c_long, C.c_long,
                                      _dp, C.c_int, _dp]),
     "sr_los_tau_src_dev": (C.c_int, [C.POINTER(_vp), C.POINTER(sr_los_steps), C.c_long, C.c_long,

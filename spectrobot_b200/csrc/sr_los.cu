@@ -92,10 +92,7 @@ __device__ double partition_sum(const double* __restrict__ q, double temp) {
     return acc;
 }
 
-__global__ void k_step_weights(StepArgs a) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int l = blockIdx.y, m = blockIdx.z;
-    if (k >= a.n_steps_max) return;
+__device__ void step_weights_one(const StepArgs& a, int k, int l, int m) {
     const GasDev& G = a.gas[m];
     const size_t sk = (size_t)l * a.n_steps_max + k;
     const size_t o = ((size_t)m * a.n_los + l) * a.n_steps_max + k;
@@ -160,6 +157,12 @@ __global__ void k_step_weights(StepArgs a) {
         }
     }
     if (flags) atomicOr(a.flags, flags);
+}
+
+__global__ void k_step_weights(const __grid_constant__ StepArgs a) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n_steps_max) return;
+    for (int l = blockIdx.y; l < a.n_los; l += gridDim.y) step_weights_one(a, k, l, blockIdx.z);
 }
 
 // which LUT rows (set, ctype) hold any non-zero value (over all cells and grid points)
@@ -735,7 +738,7 @@ int prepare_steps(sr_lut* const* luts, const sr_los_steps* S, cudaStream_t st, L
     sa.W = L0->W.p;
     sa.flags = L0->flags.p;
     sa.c2 = L0->c.h_cgs * L0->c.c_cgs / L0->c.k_cgs;
-    dim3 grid((S->n_steps_max + 63) / 64, S->n_los, S->n_gas);
+    dim3 grid((S->n_steps_max + 63) / 64, std::min(S->n_los, 65535), S->n_gas);
     SR_LAUNCH(k_step_weights, grid, 64, 0, st, sa);
     for (int m = 0; m < S->n_gas; m++) la.gas[m] = sa.gas[m];
     la.n_gas = S->n_gas;
@@ -1125,9 +1128,21 @@ struct HostSink {
     const double* i0_host;
 };
 
+// low-resolution sink: every LOS block is reduced to the instrument channels on the device
+// (k_convolve_lowres over the block's full point window) and only [n_los][n_chan] survives
+struct LowSink {
+    const double* grid_dev;     // the spectral grid points of the window [pt0, pt0+n_pts)
+    const double* centre_dev;
+    const double* width_dev;
+    int n_chan;
+    double n_sigma;
+    double* low_dev;            // [n_los][n_chan]
+};
+
 static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
                       const double* i0_dev, int solo, double* rad_dev, double* tau_dev,
-                      double* src_dev, cudaStream_t st, int emit_j = 0, HostSink* sink = nullptr) {
+                      double* src_dev, cudaStream_t st, int emit_j = 0, HostSink* sink = nullptr,
+                      LowSink* low = nullptr) {
     LosArgs la;
     int rc = prepare_steps(luts, steps, st, la);
     if (rc) return rc;
@@ -1192,7 +1207,10 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         if (const char* e = getenv("SR_LOS_BLOCK")) nl_block = std::max(1, atoi(e));
         chunk_pts = std::min(chunk_pts, n_pts);
         if (chunk_pts < n_pts) chunk_pts = std::max(256L, chunk_pts / 256 * 256);
-        nl_block = std::min(nl_block, n_los);
+        if (low || sink)   // the block's radiances [nl_block][n_pts] live in a workspace (<= 4 GiB)
+            nl_block = (int)std::min<size_t>((size_t)nl_block,
+                                             std::max<size_t>(1, ((size_t)4 << 30) / ((size_t)n_pts * 8)));
+        nl_block = std::min(std::min(nl_block, n_los), 65535);   // blockIdx.y of the recursion
     }
     GemmPlan P;
     rc = build_plan(luts, steps, nl_block, P);
@@ -1271,6 +1289,7 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         for (int b = 0; b < n_buf; b++) SR_CUDA(L0->ws_rad[b].ensure((size_t)nl_block * n_pts));
         if (sink->i0_host) SR_CUDA(L0->ws_i0.ensure((size_t)nl_block * n_pts));
     }
+    if (low) SR_CUDA(L0->ws_rad[0].ensure((size_t)nl_block * n_pts));
     int status = SR_OK;
     auto body = [&]() -> int {
         for (int b = 0; b < n_blocks; b++) {
@@ -1278,6 +1297,7 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
             const int c_lo = P.blk_chunk[b], n_ch = P.blk_chunk[b + 1] - c_lo;
             double* rad_blk = rad_dev ? rad_dev + (size_t)l0 * n_pts : nullptr;
             const double* i0_blk = i0_dev ? i0_dev + (size_t)l0 * n_pts : nullptr;
+            if (low) rad_blk = L0->ws_rad[0].p;
             if (sink) {
                 rad_blk = L0->ws_rad[b & 1].p;
                 if (buf_free[b & 1]) {   // the copies of block b-2 must have left this buffer
@@ -1329,6 +1349,12 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
                 SR_CUDA(cudaEventCreateWithFlags(&buf_free[b & 1], cudaEventDisableTiming));
                 SR_CUDA(cudaEventRecord(buf_free[b & 1], L0->copy_stream));
             }
+            if (low) {
+                int code = sr_convolve_lowres_dev(low->grid_dev, n_pts, rad_blk, nl, low->centre_dev,
+                                                  low->width_dev, low->n_chan, low->n_sigma,
+                                                  low->low_dev + (size_t)l0 * low->n_chan, st);
+                if (code) return code;
+            }
         }
         if (sink) SR_CUDA(cudaStreamSynchronize(L0->copy_stream));
         return SR_OK;
@@ -1344,6 +1370,20 @@ int sr_los_rt_lut_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
     if (!rad_dev) return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_dev: bad argument");
     return los_launch(luts, steps, pt0, n_pts, i0_dev, solo_absorption, rad_dev, nullptr, nullptr,
                       (cudaStream_t)stream);
+}
+
+int sr_los_rt_lut_lowres_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
+                             const double* grid_dev, const double* centre_dev,
+                             const double* width_dev, int n_chan, double n_sigma,
+                             const double* i0_dev, int solo_absorption, double* low_dev,
+                             void* stream) {
+    if (!grid_dev || !centre_dev || !width_dev || !low_dev || n_chan < 1 || !(n_sigma > 0.0))
+        return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_lowres_dev: bad argument");
+    if (getenv("SR_LOS_VER") && atoi(getenv("SR_LOS_VER")) == 1)
+        return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_lowres_dev needs the grouped LOS path");
+    LowSink low{grid_dev, centre_dev, width_dev, n_chan, n_sigma, low_dev};
+    return los_launch(luts, steps, pt0, n_pts, i0_dev, solo_absorption, nullptr, nullptr, nullptr,
+                      (cudaStream_t)stream, 0, nullptr, &low);
 }
 
 int sr_los_tau_src_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,

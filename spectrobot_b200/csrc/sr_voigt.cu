@@ -721,7 +721,8 @@ int launch_tile(const TileArgs& ta, int n_cells, cudaStream_t st) {
 // tile geometries (threads, points per thread): the first whose absorption rows fit in shared
 // memory twice per SM is used; SR_K1_CFG=<index> forces one (tuning aid)
 struct TileCfg { int nt, ppt; };
-constexpr TileCfg kTileCfgs[] = {{128, 4}, {256, 4}, {256, 2}, {128, 2}, {256, 1}, {128, 4}, {64, 8}, {64, 4}};
+constexpr TileCfg kTileCfgs[] = {{128, 4}, {256, 4}, {256, 2}, {128, 2}, {256, 1}, {128, 4}, {64, 8}, {64, 4},
+                                 {128, 8}, {128, 8}, {128, 6}};
 constexpr int kNumCfgs = (int)(sizeof(kTileCfgs) / sizeof(kTileCfgs[0]));
 
 int pick_cfg(int n_lo, int n_groups, size_t smem_max) {
@@ -752,6 +753,9 @@ int launch_cfg(int cfg, const TileArgs& ta, int n_cells, cudaStream_t st) {
         case 5: return launch_tile<128, 4, F32, 4>(ta, n_cells, st);
         case 6: return launch_tile<64, 8, F32, 4>(ta, n_cells, st);
         case 7: return launch_tile<64, 4, F32, 6>(ta, n_cells, st);
+        case 8: return launch_tile<128, 8, F32, 4>(ta, n_cells, st);
+        case 9: return launch_tile<128, 8, F32, 3>(ta, n_cells, st);
+        case 10: return launch_tile<128, 6, F32, 4>(ta, n_cells, st);
     }
     return sr::fail(SR_ERR_ARG, "bad tile configuration");
 }

@@ -320,6 +320,35 @@ def los_rt_lut(luts, steps, pt0=0, n_pts=None, i0=None, solo_absorption=False, o
     return out
 
 
+def los_rt_lut_lowres(luts, steps, grid, centres, widths, pt0=0, n_pts=None, n_sigma=5.0, i0=None,
+                      solo_absorption=False, out=None, stream=None, check_status=True):
+    """K3a+K3 + instrument convolution: low-res spectra [n_los, n_chan] (CUDA float64) of a batch
+    of any size; the hi-res radiances only ever exist per LOS block on the device.  grid: CUDA
+    float64 tensor with the WHOLE spectral grid of the LUTs; centres/widths: channel definition in
+    the units of the grid (array-likes or CUDA tensors)."""
+    torch = _torch()
+    if n_pts is None:
+        n_pts = luts[0].n_grid - pt0
+    assert grid.is_cuda and grid.dtype == torch.float64 and grid.numel() == luts[0].n_grid
+    c = centres if torch.is_tensor(centres) else torch.as_tensor(as_f64(centres), device="cuda")
+    w = widths if torch.is_tensor(widths) else torch.as_tensor(as_f64(widths), device="cuda")
+    assert c.numel() == w.numel()
+    if out is None:
+        out = torch.empty((steps.n_los, c.numel()), dtype=torch.float64, device="cuda")
+    arr = _lut_array(luts)
+    st = steps.struct()
+    sp = _stream_ptr(stream)
+    gwin = grid[pt0:pt0 + n_pts]
+    check(lib().sr_los_rt_lut_lowres_dev(arr, C.byref(st), int(pt0), int(n_pts),
+                                         C.c_void_p(gwin.data_ptr()), C.c_void_p(c.data_ptr()),
+                                         C.c_void_p(w.data_ptr()), c.numel(), float(n_sigma),
+                                         None if i0 is None else C.c_void_p(i0.data_ptr()),
+                                         int(bool(solo_absorption)), C.c_void_p(out.data_ptr()), sp))
+    if check_status:
+        check(lib().sr_los_check(arr, sp))
+    return out
+
+
 def los_rt_lut_host(luts, steps, pt0=0, n_pts=None, i0=None, solo_absorption=False, out=None):
     """Host-buffer entry point (copies inside): numpy [n_los, n_pts]."""
     if n_pts is None:

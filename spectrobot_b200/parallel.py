@@ -76,10 +76,13 @@ def gather_lut(g32, n_cells, rank, n_ranks):
     if g32.is_cuda and not g32.is_contiguous():   # row-padded LUT view: send the padded rows
         from . import engine
         buf = engine.lut_padded(g32)
+    work = []
     for src in range(n_ranks):
         b, e = shard_range(n_cells, src, n_ranks)
-        if e > b:
-            dist.broadcast(buf[b:e], src=src)   # contiguous slice: received in place
+        if e > b:   # contiguous slice, received in place; all owners send at the same time
+            work.append(dist.broadcast(buf[b:e], src=src, async_op=True))
+    for w in work:
+        w.wait()
     return g32
 
 

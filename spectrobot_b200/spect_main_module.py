@@ -423,11 +423,12 @@ def los_batch_radiances(loss, sp_grid, planet, LUTS, solo_absorption=False,
     if initial_intensity is not None:
         i0 = torch.as_tensor(np.broadcast_to(np.asarray(initial_intensity, dtype=float),
                                              (len(loss), n_pts)).copy(), device="cuda")
+    if lowres is not None:   # LOS blocks are reduced to the channels on the device, batch of any size
+        gdev = torch.as_tensor(np.ascontiguousarray(grid, dtype=float), device="cuda")
+        return engine.los_rt_lut_lowres(luts, steps, gdev, lowres[0], lowres[1], pt0=pt0,
+                                        n_pts=n_pts, i0=i0, solo_absorption=solo_absorption)
     rad = engine.los_rt_lut(luts, steps, pt0=pt0, n_pts=n_pts, i0=i0,
                             solo_absorption=solo_absorption)
-    if lowres is not None:
-        gdev = torch.as_tensor(np.ascontiguousarray(grid[pt0:pt0 + n_pts]), device="cuda")
-        return engine.convolve_lowres(gdev, rad, lowres[0], lowres[1])
     rad = rad.cpu().numpy()
     units = getattr(sp_grid, 'units', 'cm_1')
     sub = spcl.SpectralGrid(grid[pt0:pt0 + n_pts], units=units)
@@ -441,8 +442,8 @@ def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_
     """Forward model for a list of pixels (smm:2990-3287), batched on the GPU.
 
     Three lines of sight per pixel (low, centre, up; :3091-3096) -> radtran steps (host,
-    Curtis-Godson through the `curgods` drop-in) -> per wavenumber chunk ONE launch for all LOS,
-    reduced to the instrument channels on the device -> low-res spectra summed over chunks.
+    Curtis-Godson through the `curgods` drop-in) -> ONE library call for all LOS
+    (engine.los_rt_lut_lowres), reduced to the instrument channels on the device.
     Returns (sims, radtrans, single_rads): `radtrans` = {LOS tag: low-res SpectralIntensity};
     `sims` = per pixel the mean of its three LOS (the reference's FOV_integr_1D spline/quad
     integration is out of scope); single_rads = {} (per-gas tracking is not
@@ -474,18 +475,9 @@ def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_
 
     obs = pixels[0].observation
     centres, widths = obs.spectral_grid.grid, obs.bands.spectrum
-    n_grid = len(sp_gri.grid)
-    n_split = int(inputs.get('n_split', 1)) if isinstance(inputs, dict) else 1
-    chunk = int(mt.ceil(n_grid / float(max(n_split, 1))))
-    low = torch.zeros((len(sim_LOSs), len(centres)), dtype=torch.float64, device="cuda")
-    hi_res = dict()
-    for pt0 in range(0, n_grid, chunk):
-        npt = min(chunk, n_grid - pt0)
-        # neighbouring chunks share their boundary point so that the trapezoid rule of the
-        # instrument convolution sees every hi-res interval exactly once
-        ext = npt + (1 if pt0 + npt < n_grid else 0)
-        low += los_batch_radiances(sim_LOSs, sp_gri, planet, LUTS, lowres=(centres, widths),
-                                   pt0=pt0, n_pts=ext)
+    # one call for the whole batch and range: the library cuts it into LOS blocks x wavenumber
+    # chunks itself (the reference's n_split loop, smm:3190, was a host-memory workaround)
+    low = los_batch_radiances(sim_LOSs, sp_gri, planet, LUTS, lowres=(centres, widths))
     low = low.cpu().numpy()
     radtrans_out = dict()
     for i, los in enumerate(sim_LOSs):

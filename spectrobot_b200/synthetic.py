@@ -174,12 +174,20 @@ def limb_los_steps(tangent_km, bands, szas, atm, level_energies, max_T_variation
         nd = np.exp(np.interp(zz, z, np.log(atm["ndens"][b]))) * vmr
         steps = []
         i0 = 0
+        # running extremes of T and ln P over the samples i0..i of the open step
+        tl = th = T[0]
+        pl = ph = lnP[0]
         for i in range(1, len(s)):
-            seg = slice(i0, i + 1)
-            if (T[seg].max() - T[seg].min() > max_T_variation or
-                    lnP[seg].max() - lnP[seg].min() > max_Plog_variation) and i - i0 >= 2:
+            ti, pi = T[i], lnP[i]
+            tl2, th2 = (ti if ti < tl else tl), (ti if ti > th else th)
+            pl2, ph2 = (pi if pi < pl else pl), (pi if pi > ph else ph)
+            if (th2 - tl2 > max_T_variation or ph2 - pl2 > max_Plog_variation) and i - i0 >= 2:
                 steps.append((i0, i - 1))
                 i0 = i - 1
+                tl, th = min(T[i0], ti), max(T[i0], ti)
+                pl, ph = min(lnP[i0], pi), max(lnP[i0], pi)
+            else:
+                tl, th, pl, ph = tl2, th2, pl2, ph2
         steps.append((i0, len(s) - 1))
         rows = []
         for a, e in steps:

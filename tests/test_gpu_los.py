@@ -89,6 +89,37 @@ def test_los_blocking_and_chunking_are_invisible(case, monkeypatch):
     assert rel_err(v1, base) < 1e-12
 
 
+def test_lowres_fused_matches_hires_then_convolve(case, oracle, monkeypatch):
+    """sr_los_rt_lut_lowres_dev (LOS blocks reduced to the channels on the device) = hi-res
+    radiances followed by the instrument convolution, and both match the CPU restatement of
+    convolve_to_grid_from_irregular (spect_classes.py:883-918) on the oracle's radiances."""
+    eng, st, torch = case["engine"], case["st"], case["torch"]
+    g = case["grid"]
+    gdev = torch.as_tensor(g, device="cuda")
+    centres = np.linspace(g[0] + 0.3, g[-1] - 0.3, 7)
+    widths = np.full(7, 0.08)
+    hi = eng.los_rt_lut([case["lut"]], case["steps"])
+    ref = eng.convolve_lowres(gdev, hi, centres, widths).cpu().numpy()
+    got = eng.los_rt_lut_lowres([case["lut"]], case["steps"], gdev, centres, widths).cpu().numpy()
+    assert np.array_equal(got, ref)
+    monkeypatch.setenv("SR_LOS_BLOCK", "4")          # 6 LOS -> blocks of 4 + 2
+    monkeypatch.setenv("SR_LOS_CHUNK", "1024")
+    got_b = eng.los_rt_lut_lowres([case["lut"]], case["steps"], gdev, centres, widths).cpu().numpy()
+    assert np.array_equal(got_b, ref)
+    monkeypatch.delenv("SR_LOS_BLOCK")
+    monkeypatch.delenv("SR_LOS_CHUNK")
+    rad = oracle.los_rt([case["olut"]], st["n_steps"], st["temp"], st["pres"], st["column"],
+                        st["tvib"])
+    cpu = np.stack([oracle.convolve_to_grid_from_irregular(g, rad[i], centres, widths) for i in range(len(rad))])
+    assert rel_err(got, cpu) < TOL_RAD
+    # a sub-window of the grid
+    sub = eng.los_rt_lut_lowres([case["lut"]], case["steps"], gdev, centres[2:4], widths[2:4],
+                                pt0=1000, n_pts=3000).cpu().numpy()
+    ref_sub = eng.convolve_lowres(gdev[1000:4000].contiguous(), hi[:, 1000:4000].contiguous(),
+                                  centres[2:4], widths[2:4]).cpu().numpy()
+    assert np.array_equal(sub, ref_sub)
+
+
 def test_materialised_layers_parity(case, oracle):
     eng, st, torch = case["engine"], case["st"], case["torch"]
     ref, tau_ref, src_ref = oracle.los_rt([case["olut"]], st["n_steps"], st["temp"], st["pres"],

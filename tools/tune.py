@@ -12,26 +12,26 @@ def k1():
     w0, w1, n_lev = 2825.0, 3225.0, 12
     g = S.spectral_grid(w0, w1)
     lines = S.line_table(30000, w0, w1, n_levels=n_lev)
-    cells = [[1e-4, 150.0], [0.05, 160.0], [0.5, 170.0], [2.5, 175.0]]
+    cells = [[1e-4 * (1 + j), 150.0 + j] for j in range(8)]
     ref = None
-    for cfg in ("0", "5", "6", "7"):
+    for cfg in os.environ.get("SR_TUNE_CFGS", "0,5,6,7").split(","):
         os.environ["SR_K1_CFG"] = cfg       # read at LineSet creation (tile geometry)
         ls = engine.LineSet(lines, g, S.CH4_MM, n_lev)
-        out = torch.empty((4, n_lev, 3, len(g)), dtype=torch.float64, device="cuda")
+        out = torch.empty((8, n_lev, 3, len(g)), dtype=torch.float64, device="cuda")
         try:
             ms = timed(lambda: ls.gcoeff_cells(cells, out=out, check_status=False), 3)
         except Exception as e:
             print("k1 cfg", cfg, "failed", e); continue
         if ref is None: ref = out.clone()
         d = float(((out - ref).abs() / ref.abs().clamp_min(1e-300)).max())
-        print("k1 cfg %s: %.3f ms / 4 cells -> %.3e evals/s (max rel diff %.1e)" % (cfg, min(ms), 4 * ls.n_active * 13010 / (min(ms) * 1e-3), d))
+        print("k1 cfg %s: %.3f ms / 8 cells -> %.3e evals/s (max rel diff %.1e)" % (cfg, min(ms), 8 * ls.n_active * 13010 / (min(ms) * 1e-3), d))
         del ls, out
     lines1 = S.line_table(30000, w0, w1, n_levels=1)
     for cfg in ("0", "1"):
         os.environ["SR_K1_CFG"] = cfg
         ls1 = engine.LineSet(lines1, g, 27.99, 1)
         out1 = torch.empty((4, 1, 3, len(g)), dtype=torch.float64, device="cuda")
-        ms = timed(lambda: ls1.gcoeff_cells(cells, out=out1, check_status=False), 3)
+        ms = timed(lambda: ls1.gcoeff_cells(cells[:4], out=out1, check_status=False), 3)
         print("k1 LTE cfg %s: %.3f ms / 4 cells -> %.3e evals/s" % (cfg, min(ms), 4 * ls1.n_active * 13010 / (min(ms) * 1e-3)))
     os.environ.pop("SR_K1_CFG", None)
 
