@@ -481,3 +481,25 @@ def convolve_to_grid_from_irregular(grid, spectrum, new_grid, spectral_widths, n
         gauss = fac * np.exp(-0.5 * ((lin_grid_ok - freq) / wid) ** 2)
         out[num] = np.trapezoid(spect_old * gauss, x=lin_grid_ok)
     return out
+
+
+def FOV_integr_1D(spectra, grid, pixel_rot=0.0):
+    """Literal restatement of FOV_integr_1D (spect_main_module.py:3342-3374): RectBivariateSpline
+    (kx=ky=2) through the low / centre / up LOS spectra and scipy quad of spline*trapezoid response
+    for every wavenumber.  spectra: [3][n]; returns [n]."""
+    from scipy import integrate
+    from scipy.interpolate import RectBivariateSpline as spline2D
+    pixel_rot = abs(np.pi * pixel_rot / 180.0)
+    dmax = np.sqrt(2.) / 2. * np.cos(np.pi / 4 - pixel_rot)
+    delta = dmax - np.sin(pixel_rot)
+    esse = 1 / np.cos(pixel_rot)
+    x_integ = np.array([-dmax, 0, dmax])
+    intens_spl = spline2D(x_integ, np.asarray(grid, dtype=float), np.asarray(spectra, dtype=float),
+                          kx=2, ky=2)
+
+    def integrand(x, ww):
+        if abs(x) <= delta:
+            return intens_spl(x, ww)[0, 0] * esse
+        return intens_spl(x, ww)[0, 0] * esse * abs(dmax - abs(x)) / (dmax - delta)
+
+    return np.array([integrate.quad(integrand, -dmax, dmax, args=(ww,))[0] for ww in grid])

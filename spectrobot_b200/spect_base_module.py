@@ -121,6 +121,23 @@ def read_inputs(nomefile, key_strings, n_lines=None, itype=None, defaults=None, 
     return out
 
 
+def trova_spip(ifile, hasha='#', read_past=False):
+    """Advances an open text file to the line after the next one starting with `hasha` (the
+    "#"-delimited headers of the gbb-style input files; surface inferred from the call sites
+    spect_classes.py:1558 and Appendix C of SURVEY.md).  Returns False at end of file."""
+    while True:
+        line = ifile.readline()
+        if not line:
+            return False
+        if line.lstrip().startswith(hasha):
+            if read_past:
+                ifile.readline()
+            return True
+
+
+find_spip = trova_spip
+
+
 def check_free_space(path):
     st = os.statvfs(path)
     return st.f_bavail * st.f_frsize / 1.e9

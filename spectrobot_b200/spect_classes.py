@@ -11,8 +11,8 @@ code written against the reference keeps working:
 What differs is where the arithmetic runs: per-line Python loops, fork/Queue fan-out and the three
 f2py modules are replaced by batched calls into the CUDA library (engine.LineSet), and the level
 book-keeping by string comparison (spect_classes.py:1304-1313) is resolved once into integer set
-ids (`line_table`).  Unit conversions, plotting, `degrade_grid*` and the database readers are out of
-scope.
+ids (`line_table`).  `read_line_database` parses HITRAN / "gbb" fixed-width files (SURVEY 8f row
+3).  Unit conversions, plotting and `degrade_grid*` are out of scope.
 """
 import copy
 import math as mt
@@ -275,6 +275,156 @@ class SpectLine(object):
 # ---------------------------------------------------------------------------------------------
 # line list -> device line table
 # ---------------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------
+# line database reader (reference: spect_classes.py:1532-1601) and statistical weights (:1604-1678)
+# ---------------------------------------------------------------------------------------------
+DB_FORMATS = {
+    # field widths of one record, names, converters (reference :1546-1553)
+    'gbb': ((2, 1, 12, 10, 10, 6, 6, 10, 4, 8, 15, 15, 15, 15), cose),
+    'HITRAN': ((2, 1, 12, 10, 10, 5, 5, 10, 4, 8, 15, 15, 15, 15, 19, 7, 7), cose_hit),
+}
+_DB_NUMERIC = ('Freq', 'Strength', 'A_coeff', 'Air_broad', 'Self_broad', 'E_lower', 'T_dep_broad',
+               'P_shift', 'g_up', 'g_lo')
+
+
+def parse_line_record(text, db_format='HITRAN'):
+    """One fixed-width record -> dict of the reference's field names.  Numbers as np.genfromtxt
+    reads them (blank -> nan for floats, -1 for ints), strings kept with their padding."""
+    widths, names = DB_FORMATS[db_format]
+    rec, pos = dict(), 0
+    for w, nam in zip(widths, names):
+        tok = text[pos:pos + w]
+        pos += w
+        if nam in ('Mol', 'Iso'):
+            try:
+                rec[nam] = int(tok)
+            except ValueError:
+                rec[nam] = -1
+        elif nam in _DB_NUMERIC:
+            try:
+                rec[nam] = float(tok)
+            except ValueError:
+                rec[nam] = float('nan')
+        else:
+            rec[nam] = tok
+    return rec
+
+
+def read_line_database(nome_sp, mol=None, iso=None, up_lev=None, down_lev=None,
+                       fraction_to_keep=None, db_format='HITRAN', freq_range=None, n_skip=0,
+                       link_to_isomolecs=None, verbose=False):
+    """List of SpectLine from a HITRAN2012 (160-character) or "gbb" (MAKE_MW) line file, with the
+    reference's selection rules (:1532-1601): optional (mol, iso, upper/lower level string)
+    filter, frequency window on a frequency-sorted file (stops at the first line beyond it), zero
+    air/self widths replaced by 0.05 / 0.07, and the `fraction_to_keep` strength cut."""
+    if db_format not in DB_FORMATS:
+        raise ValueError('Allowed values for db_format: {}, {}'.format('gbb', 'HITRAN'))
+    linee_ok = []
+    with open(nome_sp, 'r') as infi:
+        if n_skip == -1:
+            sbm.trova_spip(infi)
+        else:
+            for _ in range(n_skip):
+                infi.readline()
+        for text in infi:
+            text = text.rstrip('\r\n')
+            if not text.strip():
+                continue
+            linea = parse_line_record(text, db_format)
+            if verbose:
+                print(linea['Mol'], linea['Iso'], linea['Freq'])
+            if freq_range is not None:
+                if linea['Freq'] < freq_range[0]:
+                    continue
+                if linea['Freq'] > freq_range[1]:
+                    break
+            if ((linea['Mol'] == mol or mol is None) and (linea['Iso'] == iso or iso is None) and
+                    (linea['Up_lev_str'] == up_lev or up_lev is None) and
+                    (linea['Lo_lev_str'] == down_lev or down_lev is None)):
+                line = SpectLine(linea)
+                if line.Air_broad == 0.0:
+                    line.Air_broad = 0.05
+                if line.Self_broad == 0.0:
+                    line.Self_broad = 0.07
+                if link_to_isomolecs is not None:
+                    found = [m for m in link_to_isomolecs
+                             if m.mol == line.Mol and m.iso == line.Iso]
+                    if len(found) > 1:
+                        raise ValueError('Multiple isotopologues corresponding to line!')
+                    if found:
+                        line.LinkToMolec(found[0])
+                linee_ok.append(line)
+    if fraction_to_keep is not None and linee_ok:
+        essesss = np.sort(np.array([lin.Strength for lin in linee_ok]))
+        essort = essesss[int(fraction_to_keep * (len(linee_ok) - 1))]
+        return [lin for lin in linee_ok if lin.Strength >= essort]
+    return linee_ok
+
+
+def format_line_record(line, db_format='HITRAN'):
+    """Inverse of parse_line_record for a SpectLine / dict (used to write test and synthetic
+    databases in the HITRAN2012 layout)."""
+    get = (lambda k: line[k]) if isinstance(line, dict) else (lambda k: getattr(line, k))
+    fmt = {'Mol': '{:2d}', 'Iso': '{:1d}', 'Freq': '{:12.6f}', 'Strength': '{:10.3E}',
+           'A_coeff': '{:10.3E}', 'E_lower': '{:10.4f}', 'T_dep_broad': '{:4.2f}',
+           'P_shift': '{:8.5f}', 'g_up': '{:7.1f}', 'g_lo': '{:7.1f}'}
+    wid = 5 if db_format == 'HITRAN' else 6
+    fmt['Air_broad'] = '{:%d.4f}' % wid
+    fmt['Self_broad'] = '{:%d.3f}' % wid
+    widths, names = DB_FORMATS[db_format]
+    out = ''
+    for w, nam in zip(widths, names):
+        v = get(nam)
+        if nam in fmt:
+            tok = fmt[nam].format(v)
+            if nam in ('Air_broad', 'Self_broad') and tok.startswith('0.'):
+                tok = tok[1:] if len(tok) > w else tok      # HITRAN writes .0700
+        else:
+            tok = '' if v is None else str(v)
+        out += tok[:w].rjust(w) if nam in fmt else tok[:w].ljust(w)
+    return out
+
+
+def calc_stat_weights_CH4(Q_num_up, Q_num_lo, formato='HITRAN'):
+    """g = gi*gs*(2J+1) with gs = 5, 2, 3 for the A, E, F symmetry species of CH4 (:1604-1635)."""
+    gs = dict(A=5, E=2, F=3)
+    if formato == 'HITRAN':
+        J_up, state_up = int(Q_num_up[2:5]), Q_num_up[5]
+        J_lo, state_lo = int(Q_num_lo[2:5]), Q_num_lo[5]
+    elif formato == 'hot_bands':
+        J_up, J_lo = int(Q_num_up.split()[0]), int(Q_num_lo.split()[0])
+        state_up, state_lo = Q_num_up.split()[1][0], Q_num_lo.split()[1][0]
+    else:
+        raise ValueError('formato {} not recognized'.format(formato))
+    return gs[state_up] * (2 * J_up + 1), gs[state_lo] * (2 * J_lo + 1)
+
+
+def calc_stat_weights_linear_molec(gi, gs, Q_num_up, Q_num_lo, formato='HITRAN'):
+    """g = gi*gs*(2J+1) of a linear molecule from the branch symbol and lower-state J of the
+    HITRAN local quanta, or from both J of a GEISA record (:1639-1678)."""
+    def to_int(tok):
+        try:
+            return int(tok)
+        except ValueError:
+            return int(tok[:-1])
+    if formato == 'HITRAN':
+        coso = Q_num_lo.split()
+        J, br = to_int(coso[1]), coso[0]
+        q_lo = gs * gi * (2 * J + 1)
+        if br == 'Q':
+            q_up = gs * gi * (2 * J + 1)
+        elif br == 'P':
+            q_up = gs * gi * (2 * (J - 1) + 1)
+        else:
+            q_up = gs * gi * (2 * (J + 1) + 1)
+    elif formato == 'GEISA':
+        J_up, J_lo = to_int(Q_num_up.split()[0]), to_int(Q_num_lo.split()[0])
+        q_up, q_lo = gs * gi * (2 * J_up + 1), gs * gi * (2 * J_lo + 1)
+    else:
+        raise ValueError('formato {} not recognized'.format(formato))
+    return q_up, q_lo
+
+
 def line_table(lines, isomolec=None):
     """Arrays for engine.LineSet from a list of SpectLine and an sbm.IsoMolec.
 

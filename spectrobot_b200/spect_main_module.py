@@ -8,8 +8,10 @@ Keeps the reference's names and call signatures for the forward-model chain (SUR
 Differences in HOW, not in WHAT: LookUpTable.make builds every (P,T) cell x level x ctype with one
 batched GPU call and keeps the LUT resident on the device as float32 (the reference's compressed
 LUT, smm:1676); radtrans runs all lines of sight of a wavenumber chunk in one launch instead of one
-forked process per LOS, and reduces each chunk to the instrument channels on the device.  The
-retrieval algebra, FOV integration and the observation readers are out of scope.
+forked process per LOS, and reduces each LOS block to the instrument channels on the device;
+FOV_integr_1D integrates the three LOS of a pixel in closed form.  LUT files can be written and
+read in the reference's per-level pickle stream (LookUpTable.export_levels / import_levels).  The
+retrieval algebra and the observation readers are out of scope.
 """
 import copy
 import math as mt
@@ -286,6 +288,76 @@ class LookUpTable(object):
             st.free_memory()
         self._dev = None
 
+    def export_levels(self, cartLUTs, stamp=None, dtype=np.float64):
+        """Writes the table in the reference's on-disk form (smm:726-788, 880-892, 1122-1161): one
+        pickle stream per vibrational level (`<tag>_<lev><date>.pic`, `_alllev` for an LTE
+        isotopologue) holding the PTcouples header and then, per cell, the dict
+        {ctype: SpectralGcoeff} with the grid erased.  Returns {set name: filename}."""
+        stamp = date_stamp() if stamp is None else stamp
+        names = self.set_names()
+        host = self.g32.cpu().numpy()
+        files = dict()
+        for s, nam in enumerate(names):
+            st = self.sets[nam]
+            fn = os.path.join(cartLUTs, self.tag + ('_alllev' if self.LTE else '_' + nam) + stamp + '.pic')
+            lev_string = '' if st.level is None else st.level.minimal_level_string()
+            with open(fn, 'wb') as f:
+                pickle.dump(self.PTcouples, f, protocol=-1)
+                for c, (P, T) in enumerate(self.PTcouples):
+                    set_ = dict()
+                    for k, ct in enumerate(CTYPES):
+                        gigi = spcl.SpectralGcoeff(ct, self.spectral_grid, self.mol, self.iso, self.MM,
+                                                   lev_string, unidentified_lines=st.unidentified_lines,
+                                                   spectrum=host[c, s, k].astype(dtype), Pres=P, Temp=T)
+                        gigi.erase_grid()
+                        set_[ct] = gigi
+                    pickle.dump(set_, f, protocol=-1)
+            st.filename = fn
+            st.filenames = [fn]
+            files[nam] = fn
+        return files
+
+    def import_levels(self, files, spectral_grid):
+        """Reads per-level streams written by export_levels (or by the reference's
+        LookUpTable.make / LutSet.add_PT; see read_lutset_stream) back into the resident float32
+        table.  files: {set name: filename or list of filenames}; cells of several files are
+        concatenated like LutSet.load_from_files (smm:923-956)."""
+        self.spectral_grid = copy.deepcopy(spectral_grid)
+        names = self.set_names()
+        n_grid = len(spectral_grid.grid)
+        table, pts = None, None
+        for s, nam in enumerate(names):
+            fl = files[nam]
+            fl = [fl] if isinstance(fl, str) else list(fl)
+            pt_s, rows = [], []
+            for fn in fl:
+                pt_f, sets_f = read_lutset_stream(fn)
+                pt_s += pt_f
+                rows += sets_f
+            if pts is None:
+                pts = pt_s
+                table = np.zeros((len(pts), len(names), 3, n_grid), dtype=np.float32)
+            elif pt_s != pts:
+                raise ValueError('LUT files of {} hold different PTcouples'.format(nam))
+            for c, set_ in enumerate(rows):
+                for k, ct in enumerate(CTYPES):
+                    spe = set_[ct]
+                    spe = spe.spectrum if hasattr(spe, 'spectrum') else spe
+                    if spe is not None:                      # None: all-zero spectrum (smm:1674-1679)
+                        table[c, s, k] = np.asarray(spe, dtype=np.float32)
+            level = None if self.LTE else getattr(self.isomolec, nam)
+            st = LutSet(self.mol, self.iso, self.MM, level=level, filename=fl[0])
+            st.filenames = fl
+            st.spectral_grid = self.spectral_grid
+            st._table = (self, s)
+            self.sets[nam] = st
+        self.PTcouples = [list(map(float, pt)) for pt in pts]
+        for st in self.sets.values():
+            st.PTcouples = self.PTcouples
+        self.g32 = engine.lut_from_host(table)
+        self._dev = None
+        return self
+
     def export(self, filename):
         """Header (PTcouples) first, then the table, like the reference's per-level files
         (smm:880-892): resumable by check_LUT_exists()."""
@@ -297,6 +369,32 @@ class LookUpTable(object):
                         protocol=-1)
         self.filename = filename
         return filename
+
+
+class _RefUnpickler(pickle.Unpickler):
+    """Resolves the reference's top-level module names (`spect_classes`, `spect_main_module`,
+    `spect_base_module`) to this package, so that pickles written by the reference load here."""
+
+    def find_class(self, module, name):
+        if module in ('spect_classes', 'spect_main_module', 'spect_base_module'):
+            module = __package__ + '.' + module
+        return pickle.Unpickler.find_class(self, module, name)
+
+
+def read_lutset_stream(filename):
+    """(PTcouples, [ {ctype: SpectralGcoeff}, ... ]) of one per-level LUT stream (smm:900-921):
+    the header, then one dict per cell until the stream ends (a build that was interrupted
+    leaves fewer cells than the header announces; only the complete ones are returned)."""
+    with open(filename, 'rb') as f:
+        # every pickle.dump of the writer is a stream of its own (fresh memo): one Unpickler each
+        pts = [list(map(float, pt)) for pt in _RefUnpickler(f, encoding='latin1').load()]
+        sets = []
+        for _ in pts:
+            try:
+                sets.append(_RefUnpickler(f, encoding='latin1').load())
+            except (EOFError, pickle.UnpicklingError):
+                break
+    return pts[:len(sets)], sets
 
 
 def check_LUT_exists(PTcouples, cartLUTs, mol, iso, LTE):
@@ -435,6 +533,43 @@ def los_batch_radiances(loss, sp_grid, planet, LUTS, solo_absorption=False,
     return [spcl.SpectralIntensity(rad[i], sub) for i in range(len(loss))]
 
 
+def fov_weights(pixel_rot=0.0):
+    """(dmax, W0, W2) of FOV_integr_1D (smm:3342-3374): the pixel response across the limb is a
+    trapezoid w(x) = esse for |x| <= delta, esse*(dmax-|x|)/(dmax-delta) beyond, on [-dmax, dmax]
+    (pixel_rot in degrees).  W0 = int w dx, W2 = int x^2 w dx."""
+    rot = abs(sbm.rad(pixel_rot))
+    dmax = np.sqrt(2.) / 2. * np.cos(np.pi / 4 - rot)
+    delta = dmax - np.sin(rot)
+    esse = 1 / np.cos(rot)
+    W0 = dmax + delta
+    W2 = 2. * delta ** 3 / 3.
+    if dmax - delta > 0.0:
+        W2 += 2. * (dmax ** 4 / 12. - dmax * delta ** 3 / 3. + delta ** 4 / 4.) / (dmax - delta)
+    return dmax, esse * W0, esse * W2
+
+
+def fov_integrate(low, pixel_rot=0.0):
+    """FOV integration of [..., 3, n_chan] low / centre / up LOS spectra -> [..., n_chan].
+
+    The reference builds RectBivariateSpline(x = [-dmax, 0, dmax], wavenumbers, kx=2, ky=2) and
+    integrates spline(x, ww)*w(x) with scipy quad for every channel (smm:3342-3374).  With three
+    nodes and kx = 2 the spline is, at every grid wavenumber, THE parabola through the three LOS
+    values, so the integral has the closed form  y1*W0 + (y0 + y2 - 2*y1)/(2 dmax^2) * W2  (the odd
+    term integrates to zero against the even weight); quad only approximates it (~1e-8)."""
+    low = np.asarray(low, dtype=float)
+    dmax, W0, W2 = fov_weights(pixel_rot)
+    y0, y1, y2 = low[..., 0, :], low[..., 1, :], low[..., 2, :]
+    return y1 * W0 + (y0 + y2 - 2. * y1) / (2. * dmax ** 2) * W2
+
+
+def FOV_integr_1D(radtrans, pixel_rot=0.0):
+    """Reference signature (smm:3342): three SpectralIntensity (low, centre, up LOS) -> the
+    FOV-integrated SpectralIntensity."""
+    integ_rad = copy.deepcopy(radtrans[0])
+    integ_rad.spectrum = fov_integrate(np.array([rad.spectrum for rad in radtrans]), pixel_rot)
+    return integ_rad
+
+
 def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_opt=dict(),
              save_hires=True, save_lowres=True, LUTopt=dict(), test=False, use_tangent_sza=False,
              group_observations=False, invert_LOS_direction=False, nome_inv='1',
@@ -445,9 +580,9 @@ def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_
     Curtis-Godson through the `curgods` drop-in) -> ONE library call for all LOS
     (engine.los_rt_lut_lowres), reduced to the instrument channels on the device.
     Returns (sims, radtrans, single_rads): `radtrans` = {LOS tag: low-res SpectralIntensity};
-    `sims` = per pixel the mean of its three LOS (the reference's FOV_integr_1D spline/quad
-    integration is out of scope); single_rads = {} (per-gas tracking is not
-    part of the hot path)."""
+    `sims` = per pixel the FOV integral of its three LOS (FOV_integr_1D, :3273-3277; the
+    group_observations altitude-ladder variant is not implemented); single_rads = {} (per-gas
+    tracking is not part of the hot path)."""
     import torch
     pixels = sorted(pixels, key=lambda p: p.limb_tg_alt)
     if sp_gri is None:
@@ -482,8 +617,9 @@ def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_
     radtrans_out = dict()
     for i, los in enumerate(sim_LOSs):
         radtrans_out[los.tag] = spcl.SpectralIntensity(low[i], obs.spectral_grid)
-    sims = [spcl.SpectralIntensity(low[3 * k:3 * k + 3].mean(axis=0), obs.spectral_grid)
-            for k in range(len(pixels))]
+    sims = [spcl.SpectralIntensity(fov_integrate(low[3 * k:3 * k + 3],
+                                                 getattr(pixels[k], 'pixel_rot', 0.0) or 0.0),
+                                   obs.spectral_grid) for k in range(len(pixels))]
     if isinstance(inputs, dict) and inputs.get('out_dir') and save_lowres:
         with open(os.path.join(inputs['out_dir'], 'lowres_radtran_{}.pic'.format(nome_inv)), 'wb') as f:
             pickle.dump([sims, radtrans_out], f, protocol=-1)

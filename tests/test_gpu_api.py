@@ -130,7 +130,29 @@ def test_radtrans_driver_matches_oracle_pipeline(world, oracle):
         ref = oracle.convolve_to_grid_from_irregular(sp.grid, hi[i], centres, widths)
         got = rt['LOS%03d' % i].spectrum
         assert rel_err(got, ref, floor_rel=1e-9) < TOL_RAD, i
-    assert np.allclose(sims[0].spectrum, np.mean([rt['LOS%03d' % i].spectrum for i in range(3)], axis=0))
+    # sims: FOV integral of the pixel's three LOS (FOV_integr_1D, smm:3273-3277) against the
+    # literal spline + quad restatement
+    three = np.array([rt['LOS%03d' % i].spectrum for i in range(3)])
+    rot = getattr(pix[0], 'pixel_rot', 0.0) or 0.0
+    assert np.allclose(sims[0].spectrum, oracle.FOV_integr_1D(three, centres, rot), rtol=2e-7, atol=0)
     # single-LOS reference-shaped call gives the same hi-res spectrum as the batch
     one = loss[1].radtran_fast(sp, planet, LUTS={(world["im"].mol_name, 1): lut})
     assert rel_err(one[0].spectrum, hi[1]) < TOL_RAD
+
+
+def test_lut_level_files_round_trip_through_the_device(world, tmp_path):
+    """LookUpTable.make -> export_levels (reference per-level pickle streams) -> import_levels
+    into a fresh table: identical float32 numbers, and the reloaded table drives the LOS path."""
+    smm, im, sp, eng = world["smm"], world["im"], world["sp"], world["engine"]
+    PT = [[p, float(t)] for p in (1e-3, 1e-2) for t in (150., 155., 160.)]
+    lut = smm.LookUpTable(im, [2996.0, 3004.0], LTE=False)
+    lut.make(sp, world["lines"], PT)
+    files = lut.export_levels(str(tmp_path), stamp='_rt')
+    back = smm.LookUpTable(im, [2996.0, 3004.0], LTE=False).import_levels(files, sp)
+    assert back.PTcouples == lut.PTcouples
+    assert np.array_equal(back.g32.cpu().numpy(), lut.g32.cpu().numpy())
+    assert eng.lut_row_stride(back.g32) % 32 == 0
+    steps = eng.LosSteps([2], [[152.0, 157.0]], [[2e-3, 5e-3]], [[[1e17, 2e17]]], None)
+    a = eng.los_rt_lut([lut.device_lut()], steps).cpu().numpy()
+    b = eng.los_rt_lut([back.device_lut()], steps).cpu().numpy()
+    assert a.max() > 0 and np.array_equal(a, b)

@@ -170,3 +170,139 @@ def test_prepare_spe_grid_is_numpy_arange():
     assert len(g) == 1200001
     assert np.array_equal(g, np.arange(2850.0, 3450.0 + 2.5e-4, 5e-4))
     assert g[-1] != 2850.0 + 1200000 * 5e-4            # the grid drifts
+
+
+def test_fov_integration_closed_form_matches_spline_quad(oracle):
+    """fov_integrate (closed form) against the literal RectBivariateSpline + quad restatement of
+    FOV_integr_1D (spect_main_module.py:3342-3374), incl. a rotated pixel."""
+    rng = np.random.default_rng(3)
+    grid = np.linspace(2900.0, 3400.0, 9)
+    spectra = rng.uniform(0.5, 2.0, (3, 9)) * np.array([[1.0], [1.3], [0.8]])
+    for rot in (0.0, 12.5, -30.0, 44.0):
+        got = smm.fov_integrate(spectra, rot)
+        ref = oracle.FOV_integr_1D(spectra, grid, rot)
+        assert np.allclose(got, ref, rtol=2e-7, atol=0), rot
+    # a flat field integrates to itself (unit-area response), any rotation
+    flat = np.ones((3, 4)) * 2.5
+    assert np.allclose(smm.fov_integrate(flat, 17.0), 2.5, rtol=1e-14)
+    sg = spcl.SpectralGrid(grid, units='cm_1')
+    rads = [spcl.SpectralIntensity(spectra[i], sg) for i in range(3)]
+    out = smm.FOV_integr_1D(rads, 12.5)
+    assert np.array_equal(out.spectrum, smm.fov_integrate(spectra, 12.5))
+
+
+def test_read_line_database_hitran_and_gbb(tmp_path, world):
+    """read_line_database (spect_classes.py:1532-1601) on files written in the HITRAN2012
+    160-character and the 'gbb' layouts: field round trip, selection rules, default widths."""
+    lines = world["lines"][:40]
+    lines[3].Air_broad = 0.0                       # -> 0.05 on reading (:1578-1581)
+    for fmt in ('HITRAN', 'gbb'):
+        fn = tmp_path / ('db_%s.par' % fmt)
+        with open(fn, 'w') as f:
+            f.write("header to skip\n")
+            for lin in lines:
+                f.write(spcl.format_line_record(lin, fmt) + "\n")
+        if fmt == 'HITRAN':
+            assert all(len(l.rstrip("\n")) == 160 for l in open(fn).readlines()[1:])
+        got = spcl.read_line_database(str(fn), db_format=fmt, n_skip=1)
+        assert len(got) == len(lines)
+        for a, b in zip(got, lines):
+            assert a.Mol == b.Mol and a.Iso == b.Iso
+            assert a.Freq == pytest.approx(b.Freq, abs=6e-7)
+            assert a.Strength == pytest.approx(b.Strength, rel=6e-4)
+            assert a.A_coeff == pytest.approx(b.A_coeff, rel=6e-4)
+            assert a.E_lower == pytest.approx(b.E_lower, abs=6e-5)
+            assert a.T_dep_broad == pytest.approx(b.T_dep_broad, abs=6e-3)
+            assert a.Up_lev_str.strip() == b.Up_lev_str.strip()
+            assert a.Self_broad == 0.07
+            if fmt == 'HITRAN':
+                assert a.g_up == b.g_up and a.g_lo == b.g_lo
+        assert got[3].Air_broad == 0.05
+        # frequency window on the sorted file, molecule filter, strength cut
+        f0, f1 = lines[10].Freq - 1e-4, lines[20].Freq + 1e-4
+        sub = spcl.read_line_database(str(fn), db_format=fmt, n_skip=1, freq_range=[f0, f1])
+        assert len(sub) == 11
+        assert spcl.read_line_database(str(fn), mol=5, db_format=fmt, n_skip=1) == []
+        kept = spcl.read_line_database(str(fn), db_format=fmt, n_skip=1, fraction_to_keep=0.5)
+        assert 0 < len(kept) < len(lines)
+        thr = np.sort([g.Strength for g in got])[int(0.5 * (len(got) - 1))]     # (:1592-1594)
+        assert min(k.Strength for k in kept) == thr and len(kept) == sum(g.Strength >= thr for g in got)
+    # level linking while reading
+    im = world["planet"].gases['CH4'].iso_1
+    fn = tmp_path / 'db_HITRAN.par'
+    linked = spcl.read_line_database(str(fn), db_format='HITRAN', n_skip=1, link_to_isomolecs=[im])
+    assert any(l.Up_lev_id is not None for l in linked)
+    with pytest.raises(ValueError):
+        spcl.read_line_database(str(fn), db_format='GEISA')
+
+
+def test_stat_weights():
+    assert spcl.calc_stat_weights_CH4('    7F2 21', '    6F1  3') == (3 * 15, 3 * 13)
+    assert spcl.calc_stat_weights_CH4('  12 A1', '  11 A2', formato='hot_bands') == (5 * 25, 5 * 23)
+    assert spcl.calc_stat_weights_linear_molec(6, 1, '', ' P 10') == (6 * 19, 6 * 21)
+    assert spcl.calc_stat_weights_linear_molec(6, 1, '', ' R 10e') == (6 * 23, 6 * 21)
+    assert spcl.calc_stat_weights_linear_molec(1, 1, '', ' Q  4') == (9, 9)
+    assert spcl.calc_stat_weights_linear_molec(6, 1, ' 11', ' 10e', formato='GEISA') == (6 * 23, 6 * 21)
+
+
+def test_lut_level_streams_round_trip_and_reference_module_names(tmp_path):
+    """export_levels writes the reference's per-level pickle stream (PTcouples header + one
+    {ctype: SpectralGcoeff} per cell, smm:880-892, 1122-1161); read_lutset_stream reads it back,
+    also when the classes were pickled under the reference's top-level module names."""
+    import pickle
+    import sys
+    import types
+    import torch
+    rng = np.random.default_rng(9)
+    im = sbm.IsoMolec(6, 1, LTE=False)
+    im.add_levels(S.level_strings(2), [0.0, 1310.76])
+    grid = spcl.SpectralGrid(np.linspace(3000.0, 3000.1, 33), units='cm_1')
+    PT = [[0.01, 150.0], [0.01, 155.0], [0.1, 150.0]]
+    lut = smm.LookUpTable(im, [3000.0, 3000.1], LTE=False)
+    lut.PTcouples, lut.spectral_grid = PT, grid
+    g = rng.uniform(0.5, 1.5, (3, 2, 3, 33)).astype(np.float32)
+    lut.g32 = torch.as_tensor(g)
+    for s, nam in enumerate(im.levels):
+        st = smm.LutSet(6, 1, im.MM, level=getattr(im, nam))
+        st.PTcouples, st.spectral_grid, st._table = PT, grid, (lut, s)
+        lut.sets[nam] = st
+    files = lut.export_levels(str(tmp_path), stamp='_test')
+    assert sorted(files) == sorted(im.levels)
+    for s, nam in enumerate(im.levels):
+        assert files[nam].endswith('LUT_mol06_iso1_nonLTE_%s_test.pic' % nam)
+        pts, sets = smm.read_lutset_stream(files[nam])
+        assert pts == PT and len(sets) == 3
+        for c in range(3):
+            for k, ct in enumerate(spcl.CTYPES):
+                gc = sets[c][ct]
+                assert gc.spectral_grid is None and gc.ctype == ct           # erase_grid (:1143)
+                assert gc.temp == PT[c][1] and gc.pres == PT[c][0]
+                assert np.array_equal(np.asarray(gc.spectrum, dtype=np.float32), g[c, s, k])
+    # a truncated stream (interrupted build) yields the complete cells only
+    raw = open(files[im.levels[0]], 'rb').read()
+    cut = tmp_path / 'cut.pic'
+    cut.write_bytes(raw[:int(len(raw) * 0.6)])
+    pts, sets = smm.read_lutset_stream(str(cut))
+    assert 0 < len(sets) < 3 and pts == PT[:len(sets)]
+    # classes pickled under the reference's module name `spect_classes`
+    fake = types.ModuleType('spect_classes')
+
+    class SpectralGcoeff(object):
+        pass
+    SpectralGcoeff.__module__ = 'spect_classes'
+    SpectralGcoeff.__qualname__ = 'SpectralGcoeff'
+    fake.SpectralGcoeff = SpectralGcoeff
+    sys.modules['spect_classes'] = fake
+    try:
+        obj = SpectralGcoeff()
+        obj.spectrum, obj.ctype, obj.temp, obj.pres = np.arange(33.0), 'absorption', 150.0, 0.01
+        ref_file = tmp_path / 'ref.pic'
+        with open(ref_file, 'wb') as f:
+            pickle.dump([[0.01, 150.0]], f, protocol=2)
+            pickle.dump({'absorption': obj, 'sp_emission': obj, 'ind_emission': obj}, f, protocol=2)
+    finally:
+        del sys.modules['spect_classes']
+    pts, sets = smm.read_lutset_stream(str(ref_file))
+    assert pts == [[0.01, 150.0]]
+    assert isinstance(sets[0]['absorption'], spcl.SpectralGcoeff)
+    assert np.array_equal(sets[0]['absorption'].spectrum, np.arange(33.0))
