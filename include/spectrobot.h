@@ -217,6 +217,44 @@ int sr_los_check(sr_lut* const* luts, void* stream);
 int sr_los_tau_src_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
                        double* tau_dev, double* src_dev, void* stream);
 
+/* -------------------------------------------------------------------------------------------
+ * Analytic Jacobians: d radiance / d retrieval parameter, the `hires_deriv`
+ * spectra the reference's retrieval collects per LOS and parameter
+ * [callers spect_main_module.py:2758, 2837, 2867-2881; RetParam / maskgrid :600-656; the
+ *  computation itself is in the missing spect_base_module.radtran_fast - DESIGN.md 6.5 is the
+ *  specification implemented here].
+ * A parameter p is a VMR node of ONE gas: it changes step k only through that gas' column u_k,
+ *   dfrac[los][step][p] = (d u_k / d p) / u_k      (0 where the node's mask does not reach)
+ * with the step's Curtis-Godson T and P held fixed.
+ * ----------------------------------------------------------------------------------------- */
+
+/* K3 + Jacobians over materialised layers, all DEVICE pointers.  tau, emi: [n_los][n_steps_max]
+ * [n_pts] optical depth and emission (coefficient x column, the outputs of sr_los_abs_emi_dev)
+ * of the whole mixture; tau_g, emi_g: the same for the retrieved gas alone, or both NULL when
+ * that gas is the only absorber; dfrac [n_los][n_steps_max][n_par]; rad [n_los][n_pts];
+ * jac [n_los][n_par][n_pts].  n_los <= 65535. */
+int sr_los_rt_layers_jac_dev(const double* tau, const double* emi, const double* tau_g,
+                             const double* emi_g, const double* dfrac, int n_par,
+                             const int* n_steps, int n_los, int n_steps_max, long n_pts,
+                             const double* i0, int solo_absorption, double* rad, double* jac,
+                             void* stream);
+/* Fused from the LUTs.  gas_in_jac[n_gas] (HOST ints, NULL = all): which LUTs (isotopologues)
+ * belong to the retrieved gas; dfrac_host [n_los][n_steps_max][n_par] (HOST).
+ * rad_dev [n_los][n_pts], jac_dev [n_los][n_par][n_pts] (device). */
+int sr_los_rt_lut_jac_dev(sr_lut* const* luts, const sr_los_steps* steps, int n_par,
+                          const int* gas_in_jac, const double* dfrac_host, long pt0, long n_pts,
+                          const double* i0_dev, int solo_absorption, double* rad_dev,
+                          double* jac_dev, void* stream);
+/* Same, radiances and derivatives reduced to the instrument channels on the device
+ * (par_mod.hires_deriv.hires_to_lowres, spect_main_module.py:2874): low_dev [n_los][n_chan],
+ * jac_low_dev [n_los][n_par][n_chan]; other arguments as sr_los_rt_lut_lowres_dev. */
+int sr_los_rt_lut_jac_lowres_dev(sr_lut* const* luts, const sr_los_steps* steps, int n_par,
+                                 const int* gas_in_jac, const double* dfrac_host, long pt0,
+                                 long n_pts, const double* grid_dev, const double* centre_dev,
+                                 const double* width_dev, int n_chan, double n_sigma,
+                                 const double* i0_dev, int solo_absorption, double* low_dev,
+                                 double* jac_low_dev, void* stream);
+
 /* make_abscoeff_LUTS_fast [spect_main_module.py:2134-2299]: per (LOS, step, point)
  * abs = sum_gas column*ratio*sum_lev (G_abs - G_ind)*pop and emi = sum_gas column*ratio*sum_lev
  * G_sp*pop, [n_los][n_steps_max][n_pts] each (device).  With column = 1/ratio these are the

@@ -441,6 +441,35 @@ def los_layers(tau, src, n_steps, i0=None, solo_absorption=False):
     return rad
 
 
+def los_layers_jac(tau, emi, dfrac, n_steps, tau_g=None, emi_g=None, i0=None,
+                   solo_absorption=False):
+    """CPU radiances + analytic Jacobians of the layer recursion in closed-sum form
+    (orc_los_layers_jac): (rad [n_los, n_pts], jac [n_los, n_par, n_pts])."""
+    tau, pt_ = _d(tau)
+    emi, pe = _d(emi)
+    dfrac, pf = _d(dfrac)
+    n_steps, pn = _i(n_steps)
+    n_los, n_steps_max, n_pts = tau.shape
+    n_par = dfrac.shape[2]
+    ptg = peg = None
+    if tau_g is not None:
+        tau_g, ptg = _d(tau_g)
+        emi_g, peg = _d(emi_g)
+    i0p = None
+    if i0 is not None:
+        i0, i0p = _d(i0)
+    rad = np.empty((n_los, n_pts))
+    jac = np.empty((n_los, n_par, n_pts))
+    L = lib()
+    L.orc_los_layers_jac.restype = None
+    L.orc_los_layers_jac.argtypes = [_dp, _dp, _dp, _dp, _dp, C.c_int, _ip, C.c_int, C.c_int,
+                                     C.c_long, _dp, C.c_int, _dp, _dp]
+    L.orc_los_layers_jac(pt_, pe, ptg, peg, pf, n_par, pn, n_los, n_steps_max, n_pts, i0p,
+                         int(bool(solo_absorption)), rad.ctypes.data_as(_dp),
+                         jac.ctypes.data_as(_dp))
+    return rad, jac
+
+
 def gcoeff_cell(lines, grid, T, P, MM, n_sets, n_threads=1, lin_grid=None):
     """One LUT cell on the CPU: out[n_sets, 3, n_grid] (see orc_gcoeff_cell).
 

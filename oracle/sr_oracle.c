@@ -841,3 +841,71 @@ void orc_los_layers(const double* tau, const double* src, const int* n_steps, in
             rad[(size_t)l * n_pts + i] = I;
         }
 }
+
+/* Analytic Jacobians of the layer recursion, written in the closed "sum over
+ * layers" form rather than as the recursion the CUDA kernel runs, so that the two are independent:
+ *   I_N = I_0 T(1..N) + sum_k J_k phi_k T(k+1..N),           T(a..b) = exp(-sum_{a..b} tau)
+ *   dI_N/dp = sum_k f_kp [ (J_g,k phi_k + J_k phi'_k tau_g,k) T(k+1..N)
+ *                          - tau_g,k ( I_0 T(1..N) + sum_{j<k} J_j phi_j T(j+1..N) ) ]
+ * tau/emi: whole mixture, tau_g/emi_g: the retrieved gas alone (NULL = same arrays);
+ * dfrac [n_los][n_steps_max][n_par]; jac [n_los][n_par][n_pts]. */
+static double orc_phi(double t) { return (t == 0.0) ? 1.0 : -expm1(-t) / t; }
+static double orc_dphi(double t) {
+    if (fabs(t) < 0.02) {   /* series of d/dt (1-e^-t)/t */
+        double s = 0.0, term = 1.0;   /* sum_{n>=1} n (-1)^n t^(n-1) / (n+1)! */
+        double fact = 1.0;            /* (n+1)! built incrementally */
+        for (int n = 1; n <= 12; n++) {
+            fact *= (double)(n + 1);
+            s += (n % 2 ? -1.0 : 1.0) * (double)n * term / fact;
+            term *= t;
+        }
+        return s;
+    }
+    return (exp(-t) - orc_phi(t)) / t;
+}
+
+void orc_los_layers_jac(const double* tau, const double* emi, const double* tau_g,
+                        const double* emi_g, const double* dfrac, int n_par, const int* n_steps,
+                        int n_los, int n_steps_max, long n_pts, const double* i0,
+                        int solo_absorption, double* rad, double* jac) {
+    if (!tau_g) { tau_g = tau; emi_g = emi; }
+    double* below = (double*)malloc(sizeof(double) * (n_steps_max + 1));
+    for (int l = 0; l < n_los; l++)
+        for (long i = 0; i < n_pts; i++) {
+            const int ns = n_steps[l];
+            const size_t base = (size_t)l * n_steps_max * n_pts + i;
+            const double I0 = i0 ? i0[(size_t)l * n_pts + i] : 0.0;
+            /* suffix optical depths: od[k] = sum_{j>k} tau_j */
+            double total = 0.0;
+            for (int k = 0; k < ns; k++) total += tau[base + (size_t)k * n_pts];
+            /* below[k] = I_0 T(1..N) + sum_{j<k} J_j phi_j T(j+1..N) */
+            double acc = I0 * exp(-total), run = 0.0;
+            for (int k = 0; k < ns; k++) {
+                const double t = tau[base + (size_t)k * n_pts];
+                below[k] = acc;
+                run += t;
+                if (!solo_absorption)
+                    acc += emi[base + (size_t)k * n_pts] * orc_phi(t) * exp(-(total - run));
+            }
+            rad[(size_t)l * n_pts + i] = acc;
+            for (int p = 0; p < n_par; p++) {
+                double d = 0.0;
+                run = 0.0;
+                for (int k = 0; k < ns; k++) {
+                    const double t = tau[base + (size_t)k * n_pts];
+                    const double tg = tau_g[base + (size_t)k * n_pts];
+                    run += t;
+                    const double f = dfrac[((size_t)l * n_steps_max + k) * n_par + p];
+                    if (f == 0.0) continue;
+                    double own = 0.0;
+                    if (!solo_absorption)
+                        own = (emi_g[base + (size_t)k * n_pts] * orc_phi(t) +
+                               emi[base + (size_t)k * n_pts] * orc_dphi(t) * tg) *
+                              exp(-(total - run));
+                    d += f * (own - tg * below[k]);
+                }
+                jac[((size_t)l * n_par + p) * n_pts + i] = d;
+            }
+        }
+    free(below);
+}

@@ -93,6 +93,13 @@ SIGNATURES = {
                                      _vp, _vp, _vp]),
     "sr_los_abs_emi_dev": (C.c_int, [C.POINTER(_vp), C.POINTER(sr_los_steps), C.c_long, C.c_long,
                                      _vp, _vp, _vp]),
+    "sr_los_rt_layers_jac_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int,
+                                           C.c_long, _vp, C.c_int, _vp, _vp, _vp]),
+    "sr_los_rt_lut_jac_dev": (C.c_int, [C.POINTER(_vp), C.POINTER(sr_los_steps), C.c_int, _ip, _dp,
+                                        C.c_long, C.c_long, _vp, C.c_int, _vp, _vp, _vp]),
+    "sr_los_rt_lut_jac_lowres_dev": (C.c_int, [C.POINTER(_vp), C.POINTER(sr_los_steps), C.c_int,
+                                               _ip, _dp, C.c_long, C.c_long, _vp, _vp, _vp,
+                                               C.c_int, C.c_double, _vp, C.c_int, _vp, _vp, _vp]),
     "sr_los_check": (C.c_int, [C.POINTER(_vp), _vp]),
     "sr_lut_weights": (C.c_int, [_dp, C.c_int, C.c_double, C.c_double, _ip, _dp]),
     "sr_convolve_lowres_dev": (C.c_int, [_vp, C.c_long, _vp, C.c_int, _vp, _vp, C.c_int,

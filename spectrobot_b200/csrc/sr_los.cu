@@ -374,6 +374,98 @@ __global__ void __launch_bounds__(256, 6) k_los_layers(const __grid_constant__ R
 }
 
 // ---------------------------------------------------------------------------------------------
+// K3 with analytic Jacobians (callers spect_main_module.py:2758, 2837,
+// 2867-2881: `calc_derivatives=True`, `par.hires_deriv`).  A retrieval parameter p (a VMR node of
+// one gas, RetParam.maskgrid :600-656) changes step k only through the gas column:
+//   d tau_k / dp = tau_g,k * f_kp,   d J_k / dp = J_g,k * f_kp,   f_kp = (d u_k/dp) / u_k
+// (tau_g, J_g: the layers of the retrieved gas alone; T and P of the step are held fixed).
+// Differentiating the layer update I_k = I_{k-1} e^-tau + J phi(tau):
+//   D_p,k = D_p,k-1 e^-tau_k + f_kp * B_k
+//   B_k   = -I_{k-1} e^-tau tau_g + J_g phi + J phi'(tau) tau_g,   phi' = (e^-tau - phi)/tau
+// which collapses to B_k = e^-tau (J - I_{k-1} tau) when the retrieved gas is the only absorber.
+// One thread per grid point keeps I and NP derivative accumulators in registers and streams the
+// layers once; more than NP parameters -> blockIdx.z chunks, each re-streaming the layers.
+// ---------------------------------------------------------------------------------------------
+struct JacArgs {
+    RecArgs r;                // forward part; src is J (emission coefficient x column)
+    const double* tau_g;      // layers of the retrieved gas alone (MULTI only)
+    const double* src_g;
+    const double* dfrac;      // [n_los][n_steps_max][n_par]
+    double* jac;              // [n_los][n_par][io_stride], window at io_off
+    int n_par;
+};
+
+// phi'(t) for phi(t) = (1 - e^-t)/t, given ex = e^-t and phi
+__device__ __forceinline__ double dphi(double t, double ex, double phi) {
+    if (t < 0.05)   // Taylor series: the closed form cancels like eps/t
+        return fma(t, fma(t, fma(t, fma(t, fma(t, 1.0 / 840.0, -1.0 / 144.0), 1.0 / 30.0), -0.125),
+                          1.0 / 3.0), -0.5);
+    return (ex - phi) / t;
+}
+
+template <int NP, bool MULTI>
+__global__ void __launch_bounds__(256, 2) k_los_layers_jac(const __grid_constant__ JacArgs a) {
+    const RecArgs& r = a.r;
+    const int l = blockIdx.y, pz = blockIdx.z * NP;
+    const long p = (long)blockIdx.x * 256 + threadIdx.x;
+    if (p >= r.n_pts) return;
+    double I = r.i0 ? r.i0[(size_t)l * r.io_stride + r.io_off + p] : 0.0;
+    double D[NP];
+#pragma unroll
+    for (int q = 0; q < NP; q++) D[q] = 0.0;
+    const int ns = r.n_steps[l], solo = r.solo;
+    const long ls = r.lay_stride;
+    const size_t lay0 = (size_t)l * r.n_steps_max * ls + p;
+    const double* __restrict__ tp = r.tau + lay0;
+    const double* __restrict__ sp = r.src + lay0;
+    const double* __restrict__ tgp = MULTI ? a.tau_g + lay0 : nullptr;
+    const double* __restrict__ sgp = MULTI ? a.src_g + lay0 : nullptr;
+    const double* __restrict__ fr = a.dfrac + (size_t)l * r.n_steps_max * a.n_par + pz;
+    const int npar = min(NP, a.n_par - pz);
+    constexpr int U = 4;
+    for (int k0 = 0; k0 < ns; k0 += U) {
+        double t[U], s[U], tg[U], sg[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool ok = k0 + u < ns;
+            const size_t o = (size_t)(k0 + u) * ls;
+            t[u] = ok ? __ldcs(tp + o) : 0.0;
+            s[u] = ok ? __ldcs(sp + o) : 0.0;
+            if (MULTI) {
+                tg[u] = ok ? __ldcs(tgp + o) : 0.0;
+                sg[u] = ok ? __ldcs(sgp + o) : 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (k0 + u >= ns) break;
+            double ex, em;
+            srdev::exp_pair(-t[u], ex, em);
+            const double phi = (t[u] == 0.0) ? 1.0 : -em / t[u];
+            double B;
+            if (MULTI) {
+                const double a0 = -I * ex * tg[u];
+                B = solo ? a0 : fma(s[u] * dphi(t[u], ex, phi), tg[u], fma(sg[u], phi, a0));
+            } else {
+                B = solo ? -I * ex * t[u] : ex * fma(-I, t[u], s[u]);
+            }
+            I = solo ? I * ex : fma(I, ex, s[u] * phi);
+            const double* __restrict__ f = fr + (size_t)(k0 + u) * a.n_par;
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                const double fq = q < npar ? __ldg(f + q) : 0.0;   // uniform over the CTA
+                D[q] = fma(D[q], ex, fq * B);
+            }
+        }
+    }
+    if (blockIdx.z == 0) __stcs(r.rad + (size_t)l * r.io_stride + r.io_off + p, I);
+#pragma unroll
+    for (int q = 0; q < NP; q++)
+        if (q < npar)
+            __stcs(a.jac + ((size_t)l * a.n_par + pz + q) * r.io_stride + r.io_off + p, D[q]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K3a on the FP64 tensor path (v3).  Same grouping as v2, but the per-CTA product
 //   C[16 pairs][points] += A[16 pairs][rows] * B[rows][points]
 // is issued as DMMA.8x8x4 (mma.sync.m8n8k4.f64): one warp instruction does the work of 8 DFMA
@@ -417,6 +509,7 @@ struct PackArgs {
     double* wfrag;
     long n_pairs_tot;
     int n_sets_max, max_jp, n_chunks;
+    unsigned gas_mask;            // LUTs whose weights are packed (the others get 0)
 };
 
 __global__ void k_pack_wfrag(PackArgs a) {
@@ -430,7 +523,7 @@ __global__ void k_pack_wfrag(PackArgs a) {
     const ProgEntry pe = a.prog[(size_t)grp * a.max_jp + j];
     const int pr = a.chunk_pair[chunk * MMA_PB + slot];
     double w = 0.0;
-    if (pr >= 0 && pe.gas >= 0)
+    if (pr >= 0 && pe.gas >= 0 && ((a.gas_mask >> pe.gas) & 1u))
         w = a.W[((size_t)pe.gas * a.n_pairs_tot + pr) * ((size_t)a.n_sets_max * 4) + pe.widx];
     if (pe.neg) w = -w;
     const int kb = j >> 2, kq = j & 3, mb = slot >> 3, row = slot & 7;
@@ -632,6 +725,7 @@ struct sr_lut {
     int n_rows[3] = {0, 0, 0};
     sr::DevBuf<double> ws_rad[2], ws_i0;   // workspace of the host-buffer entry point
     sr::DevBuf<double> ws_tau, ws_src;  // layer scratch of the grouped K3a -> K3 path
+    sr::DevBuf<double> ws_tau_g, ws_src_g, ws_jac, g_wfrag_g, g_dfrac;   // Jacobian path
     sr::DevBuf<char> g_prog;            // quad row programs / chunk tables of the current call
     sr::DevBuf<long long> g_rowptr;
     sr::DevBuf<double> g_wfrag;
@@ -940,6 +1034,44 @@ int sr_los_rt_layers_dev(const double* tau, const double* src, const int* n_step
                          (cudaStream_t)stream, 0);
 }
 
+// K3 + Jacobians.  tau_g/src_g == nullptr: the retrieved gas is the only absorber.
+static int layers_jac_launch(const double* tau, const double* src, const double* tau_g,
+                             const double* src_g, const double* dfrac, int n_par,
+                             const int* n_steps, int n_los, int n_steps_max, long n_pts,
+                             const double* i0, int solo, double* rad, double* jac, cudaStream_t st,
+                             long io_stride = -1, long io_off = 0, long lay_stride = -1) {
+    JacArgs a;
+    a.r = rec_args(tau, src, n_steps, n_los, n_steps_max, n_pts, i0, solo, rad, 1, io_stride,
+                   io_off, lay_stride, 256);
+    a.tau_g = tau_g;
+    a.src_g = src_g;
+    a.dfrac = dfrac;
+    a.jac = jac;
+    a.n_par = n_par;
+    const bool multi = tau_g != nullptr;
+#define SR_JAC(NP)                                                                             \
+    {                                                                                          \
+        dim3 grid((unsigned)a.r.n_tiles, (unsigned)n_los, (unsigned)((n_par + NP - 1) / NP));  \
+        if (multi) SR_LAUNCH((k_los_layers_jac<NP, true>), grid, 256, 0, st, a);               \
+        else SR_LAUNCH((k_los_layers_jac<NP, false>), grid, 256, 0, st, a);                    \
+    }
+    if (n_par <= 4) SR_JAC(4) else if (n_par <= 8) SR_JAC(8) else SR_JAC(16)
+#undef SR_JAC
+    return SR_OK;
+}
+
+int sr_los_rt_layers_jac_dev(const double* tau, const double* emi, const double* tau_g,
+                             const double* emi_g, const double* dfrac, int n_par,
+                             const int* n_steps, int n_los, int n_steps_max, long n_pts,
+                             const double* i0, int solo_absorption, double* rad, double* jac,
+                             void* stream) {
+    if (!tau || !emi || !dfrac || !n_steps || !rad || !jac || n_los < 1 || n_los > 65535 ||
+        n_steps_max < 1 || n_pts < 1 || n_par < 1 || (tau_g == nullptr) != (emi_g == nullptr))
+        return sr::fail(SR_ERR_ARG, "sr_los_rt_layers_jac_dev: bad argument");
+    return layers_jac_launch(tau, emi, tau_g, emi_g, dfrac, n_par, n_steps, n_los, n_steps_max,
+                             n_pts, i0, solo_absorption, rad, jac, (cudaStream_t)stream);
+}
+
 // Host side of the grouped K3a: choose the LUT cells of every (LOS, step) pair with the
 // reference's rule (same code as sr_lut_weights), group the pairs by their cells ("quads"),
 // build one row program per quad and 16-pair chunks.  Large batches are cut into LOS blocks so
@@ -1139,10 +1271,19 @@ struct LowSink {
     double* low_dev;            // [n_los][n_chan]
 };
 
+// analytic Jacobians of the batch (k_los_layers_jac)
+struct JacSpec {
+    int n_par;
+    unsigned gas_mask;          // bit m: LUT m belongs to the retrieved gas
+    const double* dfrac_host;   // [n_los][n_steps_max][n_par]
+    double* jac_dev;            // hi-res [n_los][n_par][n_pts], or
+    double* jac_low_dev;        // low-res [n_los][n_par][n_chan] (with a LowSink)
+};
+
 static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
                       const double* i0_dev, int solo, double* rad_dev, double* tau_dev,
                       double* src_dev, cudaStream_t st, int emit_j = 0, HostSink* sink = nullptr,
-                      LowSink* low = nullptr) {
+                      LowSink* low = nullptr, JacSpec* jac = nullptr) {
     LosArgs la;
     int rc = prepare_steps(luts, steps, st, la);
     if (rc) return rc;
@@ -1153,6 +1294,10 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
     const size_t nmax = (size_t)steps->n_steps_max;
     int ver = 3;
     if (const char* e = getenv("SR_LOS_VER")) ver = atoi(e);   // 1 = thread-per-point fused kernel
+    if (jac && (ver == 1 || sink || tau_dev))
+        return sr::fail(SR_ERR_ARG, "LOS Jacobians need the grouped LOS path with device outputs");
+    const unsigned all_gas = (steps->n_gas >= 32) ? ~0u : ((1u << steps->n_gas) - 1u);
+    const bool jac_multi = jac && (jac->gas_mask & all_gas) != all_gas;
     if (ver == 1) {
         if (sink) {   // plain path: whole batch on the device, then one copy
             const size_t n = (size_t)n_los * n_pts;
@@ -1197,11 +1342,12 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
     int nl_block = n_los;
     if (!tau_dev) {
         const long min_chunk = std::min<long>(n_pts, 65536);
-        if ((size_t)n_los * nmax * 16 * (size_t)min_chunk <= budget) {
-            chunk_pts = (long)(budget / ((size_t)n_los * nmax * 16));
+        const size_t lay_b = jac_multi ? 32 : 16;   // scratch bytes per (pair, point)
+        if ((size_t)n_los * nmax * lay_b * (size_t)min_chunk <= budget) {
+            chunk_pts = (long)(budget / ((size_t)n_los * nmax * lay_b));
         } else {
             chunk_pts = min_chunk;
-            nl_block = (int)std::max<size_t>(1, budget / (nmax * 16 * (size_t)chunk_pts));
+            nl_block = (int)std::max<size_t>(1, budget / (nmax * lay_b * (size_t)chunk_pts));
         }
         if (const char* e = getenv("SR_LOS_CHUNK")) chunk_pts = std::max(256L, atol(e));
         if (const char* e = getenv("SR_LOS_BLOCK")) nl_block = std::max(1, atoi(e));
@@ -1210,6 +1356,10 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         if (low || sink)   // the block's radiances [nl_block][n_pts] live in a workspace (<= 4 GiB)
             nl_block = (int)std::min<size_t>((size_t)nl_block,
                                              std::max<size_t>(1, ((size_t)4 << 30) / ((size_t)n_pts * 8)));
+        if (low && jac)    // ... and so do its derivatives [nl_block][n_par][n_pts] (<= 8 GiB)
+            nl_block = (int)std::min<size_t>(
+                (size_t)nl_block,
+                std::max<size_t>(1, ((size_t)8 << 30) / ((size_t)n_pts * 8 * (size_t)jac->n_par)));
         nl_block = std::min(std::min(nl_block, n_los), 65535);   // blockIdx.y of the recursion
     }
     GemmPlan P;
@@ -1248,8 +1398,15 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         pa.n_sets_max = la.n_sets_max;
         pa.max_jp = P.max_jp;
         pa.n_chunks = P.n_chunks;
+        pa.gas_mask = ~0u;
         const long n_el = (long)P.n_chunks * P.max_jp * MMA_PB;
         SR_LAUNCH(k_pack_wfrag, (unsigned)((n_el + 255) / 256), 256, 0, st, pa);
+        if (jac_multi) {   // second weight set: the retrieved gas alone
+            SR_CUDA(L0->g_wfrag_g.ensure((size_t)P.n_chunks * P.max_jp * MMA_PB));
+            pa.wfrag = L0->g_wfrag_g.p;
+            pa.gas_mask = jac->gas_mask;
+            SR_LAUNCH(k_pack_wfrag, (unsigned)((n_el + 255) / 256), 256, 0, st, pa);
+        }
         ma.rowptr = L0->g_rowptr.p;
         ma.grp_ntau = L0->g_ntau.p;
         ma.grp_ntot = L0->g_ntot.p;
@@ -1290,6 +1447,14 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         if (sink->i0_host) SR_CUDA(L0->ws_i0.ensure((size_t)nl_block * n_pts));
     }
     if (low) SR_CUDA(L0->ws_rad[0].ensure((size_t)nl_block * n_pts));
+    if (jac) {
+        SR_CUDA(L0->g_dfrac.upload(jac->dfrac_host, (size_t)n_los * nmax * jac->n_par, st));
+        if (jac_multi) {
+            SR_CUDA(L0->ws_tau_g.ensure(blk_pairs * ld_lay));
+            SR_CUDA(L0->ws_src_g.ensure(blk_pairs * ld_lay));
+        }
+        if (low) SR_CUDA(L0->ws_jac.ensure((size_t)nl_block * jac->n_par * n_pts));
+    }
     int status = SR_OK;
     auto body = [&]() -> int {
         for (int b = 0; b < n_blocks; b++) {
@@ -1325,13 +1490,33 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
                     ma.src_out = L0->ws_src.p;
                     ma.mode = 1;
                     dim3 grid((unsigned)n_ch, (unsigned)((np + TILE - 1) / TILE));
+                    ma.wfrag = L0->g_wfrag.p;
                     int code = mma_launch(rows_aligned && (pt0 + c0) % 4 == 0, grid, smem, st, ma);
                     if (code) return code;
+                    if (jac_multi) {
+                        ma.wfrag = L0->g_wfrag_g.p;
+                        ma.tau_out = L0->ws_tau_g.p;
+                        ma.src_out = L0->ws_src_g.p;
+                        code = mma_launch(rows_aligned && (pt0 + c0) % 4 == 0, grid, smem, st, ma);
+                        if (code) return code;
+                    }
                 }
                 // radiances (and i0) rows have stride n_pts; this chunk is the window [c0, c0+np)
-                int code = layers_launch(L0->ws_tau.p, L0->ws_src.p, la.n_steps + l0, nl,
-                                         steps->n_steps_max, np, i0_blk, solo, rad_blk, st, 1, n_pts, c0,
-                                         ld_lay);
+                int code;
+                if (jac) {
+                    double* jac_blk = low ? L0->ws_jac.p
+                                          : jac->jac_dev + (size_t)l0 * jac->n_par * n_pts;
+                    code = layers_jac_launch(L0->ws_tau.p, L0->ws_src.p,
+                                             jac_multi ? L0->ws_tau_g.p : nullptr,
+                                             jac_multi ? L0->ws_src_g.p : nullptr,
+                                             L0->g_dfrac.p + (size_t)l0 * nmax * jac->n_par,
+                                             jac->n_par, la.n_steps + l0, nl, steps->n_steps_max, np,
+                                             i0_blk, solo, rad_blk, jac_blk, st, n_pts, c0, ld_lay);
+                } else {
+                    code = layers_launch(L0->ws_tau.p, L0->ws_src.p, la.n_steps + l0, nl,
+                                         steps->n_steps_max, np, i0_blk, solo, rad_blk, st, 1, n_pts,
+                                         c0, ld_lay);
+                }
                 if (code) return code;
                 if (sink) {
                     cudaEvent_t ev;
@@ -1354,6 +1539,14 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
                                                   low->width_dev, low->n_chan, low->n_sigma,
                                                   low->low_dev + (size_t)l0 * low->n_chan, st);
                 if (code) return code;
+                if (jac) {
+                    code = sr_convolve_lowres_dev(low->grid_dev, n_pts, L0->ws_jac.p, nl * jac->n_par,
+                                                  low->centre_dev, low->width_dev, low->n_chan,
+                                                  low->n_sigma,
+                                                  jac->jac_low_dev + (size_t)l0 * jac->n_par * low->n_chan,
+                                                  st);
+                    if (code) return code;
+                }
             }
         }
         if (sink) SR_CUDA(cudaStreamSynchronize(L0->copy_stream));
@@ -1384,6 +1577,51 @@ int sr_los_rt_lut_lowres_dev(sr_lut* const* luts, const sr_los_steps* steps, lon
     LowSink low{grid_dev, centre_dev, width_dev, n_chan, n_sigma, low_dev};
     return los_launch(luts, steps, pt0, n_pts, i0_dev, solo_absorption, nullptr, nullptr, nullptr,
                       (cudaStream_t)stream, 0, nullptr, &low);
+}
+
+static int jac_spec(const sr_los_steps* steps, int n_par, const int* gas_in_jac,
+                    const double* dfrac_host, JacSpec& j) {
+    if (!steps || n_par < 1 || !dfrac_host || steps->n_gas < 1 || steps->n_gas > MAX_GAS)
+        return sr::fail(SR_ERR_ARG, "LOS Jacobians: bad argument");
+    j.n_par = n_par;
+    j.dfrac_host = dfrac_host;
+    j.gas_mask = 0;
+    for (int m = 0; m < steps->n_gas; m++)
+        if (!gas_in_jac || gas_in_jac[m]) j.gas_mask |= 1u << m;
+    if (!j.gas_mask) return sr::fail(SR_ERR_ARG, "LOS Jacobians: no LUT belongs to the retrieved gas");
+    j.jac_dev = j.jac_low_dev = nullptr;
+    return SR_OK;
+}
+
+int sr_los_rt_lut_jac_dev(sr_lut* const* luts, const sr_los_steps* steps, int n_par,
+                          const int* gas_in_jac, const double* dfrac_host, long pt0, long n_pts,
+                          const double* i0_dev, int solo_absorption, double* rad_dev,
+                          double* jac_dev, void* stream) {
+    if (!rad_dev || !jac_dev) return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_jac_dev: bad argument");
+    JacSpec j;
+    int rc = jac_spec(steps, n_par, gas_in_jac, dfrac_host, j);
+    if (rc) return rc;
+    j.jac_dev = jac_dev;
+    return los_launch(luts, steps, pt0, n_pts, i0_dev, solo_absorption, rad_dev, nullptr, nullptr,
+                      (cudaStream_t)stream, 0, nullptr, nullptr, &j);
+}
+
+int sr_los_rt_lut_jac_lowres_dev(sr_lut* const* luts, const sr_los_steps* steps, int n_par,
+                                 const int* gas_in_jac, const double* dfrac_host, long pt0,
+                                 long n_pts, const double* grid_dev, const double* centre_dev,
+                                 const double* width_dev, int n_chan, double n_sigma,
+                                 const double* i0_dev, int solo_absorption, double* low_dev,
+                                 double* jac_low_dev, void* stream) {
+    if (!grid_dev || !centre_dev || !width_dev || !low_dev || !jac_low_dev || n_chan < 1 ||
+        !(n_sigma > 0.0))
+        return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_jac_lowres_dev: bad argument");
+    JacSpec j;
+    int rc = jac_spec(steps, n_par, gas_in_jac, dfrac_host, j);
+    if (rc) return rc;
+    j.jac_low_dev = jac_low_dev;
+    LowSink low{grid_dev, centre_dev, width_dev, n_chan, n_sigma, low_dev};
+    return los_launch(luts, steps, pt0, n_pts, i0_dev, solo_absorption, nullptr, nullptr, nullptr,
+                      (cudaStream_t)stream, 0, nullptr, &low, &j);
 }
 
 int sr_los_tau_src_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,

@@ -399,6 +399,91 @@ def los_abs_emi(luts, steps, pt0=0, n_pts=None, stream=None):
     return a, e
 
 
+def _jac_args(steps, dfrac, gas_in_jac):
+    dfrac = as_f64(dfrac)
+    assert dfrac.ndim == 3 and dfrac.shape[:2] == (steps.n_los, steps.n_steps_max)
+    gij = None if gas_in_jac is None else as_i32(gas_in_jac)
+    assert gij is None or len(gij) == steps.n_gas
+    return dfrac, gij
+
+
+def los_rt_lut_jac(luts, steps, dfrac, gas_in_jac=None, pt0=0, n_pts=None, i0=None,
+                   solo_absorption=False, stream=None, check_status=True):
+    """Fused K3a+K3 with analytic Jacobians: (rad [n_los, n_pts], jac [n_los, n_par, n_pts]) CUDA
+    float64 tensors.  dfrac [n_los, n_steps_max, n_par] = (d column / d parameter) / column of the
+    retrieved gas per step; gas_in_jac [n_gas]: which LUTs belong to that gas (None = all)."""
+    torch = _torch()
+    if n_pts is None:
+        n_pts = luts[0].n_grid - pt0
+    dfrac, gij = _jac_args(steps, dfrac, gas_in_jac)
+    n_par = dfrac.shape[2]
+    rad = torch.empty((steps.n_los, n_pts), dtype=torch.float64, device="cuda")
+    jac = torch.empty((steps.n_los, n_par, n_pts), dtype=torch.float64, device="cuda")
+    arr = _lut_array(luts)
+    st = steps.struct()
+    sp = _stream_ptr(stream)
+    check(lib().sr_los_rt_lut_jac_dev(arr, C.byref(st), n_par, None if gij is None else iptr(gij),
+                                      dptr(dfrac), int(pt0), int(n_pts),
+                                      None if i0 is None else C.c_void_p(i0.data_ptr()),
+                                      int(bool(solo_absorption)), C.c_void_p(rad.data_ptr()),
+                                      C.c_void_p(jac.data_ptr()), sp))
+    if check_status:
+        check(lib().sr_los_check(arr, sp))
+    return rad, jac
+
+
+def los_rt_lut_jac_lowres(luts, steps, dfrac, grid, centres, widths, gas_in_jac=None, pt0=0,
+                          n_pts=None, n_sigma=5.0, i0=None, solo_absorption=False, stream=None,
+                          check_status=True):
+    """Same, reduced to the instrument channels on the device: (low [n_los, n_chan],
+    jac_low [n_los, n_par, n_chan]); see los_rt_lut_lowres for grid / centres / widths."""
+    torch = _torch()
+    if n_pts is None:
+        n_pts = luts[0].n_grid - pt0
+    dfrac, gij = _jac_args(steps, dfrac, gas_in_jac)
+    n_par = dfrac.shape[2]
+    assert grid.is_cuda and grid.dtype == torch.float64 and grid.numel() == luts[0].n_grid
+    c = centres if torch.is_tensor(centres) else torch.as_tensor(as_f64(centres), device="cuda")
+    w = widths if torch.is_tensor(widths) else torch.as_tensor(as_f64(widths), device="cuda")
+    assert c.numel() == w.numel()
+    low = torch.empty((steps.n_los, c.numel()), dtype=torch.float64, device="cuda")
+    jlow = torch.empty((steps.n_los, n_par, c.numel()), dtype=torch.float64, device="cuda")
+    arr = _lut_array(luts)
+    st = steps.struct()
+    sp = _stream_ptr(stream)
+    gwin = grid[pt0:pt0 + n_pts]
+    check(lib().sr_los_rt_lut_jac_lowres_dev(
+        arr, C.byref(st), n_par, None if gij is None else iptr(gij), dptr(dfrac), int(pt0),
+        int(n_pts), C.c_void_p(gwin.data_ptr()), C.c_void_p(c.data_ptr()),
+        C.c_void_p(w.data_ptr()), c.numel(), float(n_sigma),
+        None if i0 is None else C.c_void_p(i0.data_ptr()), int(bool(solo_absorption)),
+        C.c_void_p(low.data_ptr()), C.c_void_p(jlow.data_ptr()), sp))
+    if check_status:
+        check(lib().sr_los_check(arr, sp))
+    return low, jlow
+
+
+def los_rt_layers_jac(tau, emi, dfrac, n_steps, tau_g=None, emi_g=None, i0=None,
+                      solo_absorption=False, stream=None):
+    """K3 + Jacobians on materialised layers (tau, emi from los_abs_emi; tau_g, emi_g the retrieved
+    gas alone or None): CUDA tensors -> (rad [n_los, n_pts], jac [n_los, n_par, n_pts])."""
+    torch = _torch()
+    n_los, n_steps_max, n_pts = tau.shape
+    assert emi.shape == tau.shape and tau.is_contiguous() and emi.is_contiguous()
+    assert dfrac.is_cuda and dfrac.dtype == torch.float64 and dfrac.is_contiguous()
+    assert dfrac.shape[:2] == (n_los, n_steps_max)
+    assert (tau_g is None) == (emi_g is None)
+    n_par = dfrac.shape[2]
+    rad = torch.empty((n_los, n_pts), dtype=torch.float64, device="cuda")
+    jac = torch.empty((n_los, n_par, n_pts), dtype=torch.float64, device="cuda")
+    vp = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
+    check(lib().sr_los_rt_layers_jac_dev(vp(tau), vp(emi), vp(tau_g), vp(emi_g), vp(dfrac), n_par,
+                                         vp(n_steps), n_los, n_steps_max, n_pts, vp(i0),
+                                         int(bool(solo_absorption)), vp(rad), vp(jac),
+                                         _stream_ptr(stream)))
+    return rad, jac
+
+
 def partition_sum(mol, iso, temp=296.0):
     """CalcPartitionSum (spect_classes.py:1692-1710) from the library's TIPS tables."""
     q = C.c_double()

@@ -42,6 +42,19 @@ def k1(n_lines=30000, n_lev=12, w0=2825.0, w1=3225.0):
                                                        ls.n_active * 13010 / (min(ms) * 1e-3)))
 
 
+def k1b(n_c=8):
+    """the bench's K1 measurement: 8 cells per launch on the [2850,3450] grid"""
+    w0, w1, n_lev = 2850.0, 3450.0, 12
+    g = S.spectral_grid(w0, w1)
+    lines = S.line_table(30000, w0, w1, n_levels=n_lev)
+    ls = engine.LineSet(lines, g, S.CH4_MM, n_lev)
+    out = torch.empty((n_c, n_lev, 3, len(g)), dtype=torch.float64, device="cuda")
+    pts = [[0.05 * (3 + j), 150.0 + 2.0 * j] for j in range(n_c)]
+    ms = timed(lambda: ls.gcoeff_cells(pts, out=out, check_status=False), 5)
+    print("k1b %d cells: %s ms -> %.3e evals/s" % (n_c, ["%.3f" % m for m in ms],
+                                                   n_c * ls.n_active * 13010 / (min(ms) * 1e-3)))
+
+
 def los(mode, n_los=int(os.environ.get("SR_PROF_NLOS", "8"))):
     w0, w1 = 2850.0, 3450.0
     g = S.spectral_grid(w0, w1)
@@ -74,5 +87,7 @@ if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "k1"
     if mode == "k1":
         k1()
+    elif mode == "k1b":
+        k1b()
     else:
         los(mode)
