@@ -198,9 +198,40 @@ class AtmProfile(object):
                 res[n] = float(np.interp(alt, z, v))
         return res[profname] if profname is not None else res
 
+    def __iadd__(self, other):
+        """prof += maskgrid*value (RetSet.profile, smm:483-489): adds the other profile's single
+        field to every field of this one."""
+        add = other.values[other.names[0]]
+        for n in self.names:
+            self.values[n] = self.values[n] + add
+            setattr(self, n, self.values[n])
+        return self
+
     def profile_1d(self, name, lat=0.0):
         b = self._band(lat)
         return self.values[name] if b is None else self.values[name][b]
+
+
+class AtmGridMask(object):
+    """Weight of one retrieval parameter over the atmosphere grid (smm:348-350: built by
+    alt_triangle on an 'alt' AtmGrid; 1-D altitude masks only here)."""
+
+    def __init__(self, grid, mask, interp='lin'):
+        self.grid = grid
+        self.mask = np.asarray(mask, dtype=float)
+        self.interp = {'mask': interp if isinstance(interp, str) else interp[-1]}
+
+    def calc(self, point, profname=None):
+        lat, lon, alt = point.Spherical() if hasattr(point, 'Spherical') else point
+        z = self.grid.coords['alt']
+        if self.interp['mask'] == 'box':
+            return float(self.mask[int(np.clip(np.searchsorted(z, alt, side='right') - 1, 0, len(z) - 1))])
+        return float(np.interp(alt, z, self.mask))
+
+    def __mul__(self, value):
+        return AtmProfile(self.grid, self.mask * float(value), 'mask', self.interp['mask'])
+
+    __rmul__ = __mul__
 
 
 def AtmProfZeros(grid, profname, interp):
@@ -441,6 +472,14 @@ class LineOfSight(object):
             bounds.append((i0, n - 1))
         steps = []
         gas_isos = [(g, iso) for g in sorted(planet.gases) for iso in planet.gases[g].all_iso]
+        # retrieval parameters that are VMR nodes of a gas of this planet: the
+        # column of a step depends on parameter p through d u/dp = int n * mask_p ds
+        jac_pars = []
+        if calc_derivatives and bayes_set is not None:
+            for par in bayes_set.params():
+                self.involved_retparams[(par.nameset, par.key)] = False
+                if par.nameset in planet.gases:
+                    jac_pars.append((par, np.array([par.maskgrid.calc(p) for p in pts])))
         for a, e in bounds:
             sl = slice(a, e + 1)
             npnt = e - a + 1
@@ -466,6 +505,14 @@ class LineOfSight(object):
                             tvp = np.array([L.vibtemp.calc(p, 'vibtemp') for p in pts[a:e + 1]])
                             tv = curgods.curgod_fort_3(nd[sl], vmr, tvp, x[sl], npnt) / col
                         st['vibtemps'][(g, iso, lev)] = tv
+            if jac_pars:
+                st['dcolumns'] = dict()
+                for par, mvals in jac_pars:
+                    m = mvals[sl]
+                    d = curgods.curgod_fort_2(nd[sl], m, x[sl], npnt) if np.any(m != 0.0) else 0.0
+                    st['dcolumns'][(par.nameset, par.key)] = d
+                    if d != 0.0:
+                        self.involved_retparams[(par.nameset, par.key)] = True
             steps.append(st)
         self.radtran_steps = {'step': steps, 'gas_isos': gas_isos,
                               'opt': dict(max_T_variation=max_T_variation,
@@ -507,7 +554,14 @@ class LineOfSight(object):
                                        initial_intensity=initial_intensity)
         out = [rads[0], dict(), copy.deepcopy(bayes_set)]
         if calc_derivatives:
-            raise NotImplementedError('analytic Jacobians are a "next" row (SURVEY 8f #2)')
+            # hi-res derivative spectra of this LOS, attached to the copy of the parameter set
+            # like the reference does (par_mod.hires_deriv, spect_main_module.py:2867-2874)
+            rad, jac = smm.los_batch_jacobians([self], sp_grid, planet, LUTS, bayes_set,
+                                               solo_absorption=solo_absorption,
+                                               initial_intensity=initial_intensity)
+            out[0] = rad[0]
+            for par, der in zip(out[2].params(), jac[0]):
+                par.add_hires_deriv(der)
         if queue is not None:
             queue.put(out)
         return out

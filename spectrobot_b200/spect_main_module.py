@@ -480,6 +480,191 @@ def make_abscoeff_LUTS_fast(spectral_grid, isomolec, Temps, Press, LTE=True, tag
     return abs_c, emi_c
 
 
+# ---------------------------------------------------------------------------------------------
+# parameter space of the retrieval (smm:161-296, 319-352, 442-656): only what the forward model
+# and its Jacobians need - the update / regularisation algebra is out of scope
+# ---------------------------------------------------------------------------------------------
+def alt_triangle(alt_grid, node_alt, step=None, node_lo=None, node_up=None, first=False,
+                 last=False):
+    """Triangular weight of one altitude node on alt_grid (smm:319-352), as an sbm.AtmGridMask.
+    first / last: constant 1 below / above the node."""
+    if step is not None:
+        node_lo, node_up = node_alt - step, node_alt + step
+    alt_grid = np.asarray(alt_grid, dtype=float)
+    cos = np.zeros(len(alt_grid))
+    up = None if node_up is None else 1.0 - (alt_grid - node_alt) / (node_up - node_alt)
+    lo = None if node_lo is None else 1.0 - (node_alt - alt_grid) / (node_alt - node_lo)
+    if first:
+        cos = np.where(alt_grid < node_alt, 1.0, np.where(alt_grid < node_up, up, 0.0))
+    elif last:
+        cos = np.where(alt_grid > node_alt, 1.0, np.where(alt_grid > node_lo, lo, 0.0))
+    else:
+        inside = (alt_grid >= node_lo) & (alt_grid <= node_up)
+        cos = np.where(inside, np.where(alt_grid >= node_alt, up, lo), 0.0)
+    return sbm.AtmGridMask(sbm.AtmGrid('alt', alt_grid), cos, 'lin')
+
+
+class RetParam(object):
+    """A single parameter of the parameter space (smm:600-656)."""
+
+    def __init__(self, nameset, key, maskgrid, apriori, apriori_err, first_guess=None,
+                 constrain_positive=True):
+        self.nameset = nameset
+        self.key = key
+        self.maskgrid = copy.deepcopy(maskgrid)
+        self.value = apriori if first_guess is None else first_guess
+        self.apriori = apriori
+        self.apriori_err = apriori_err
+        self.derivatives = []
+        self.old_values = []
+        self.constrain_positive = constrain_positive
+        self.not_involved = False
+        self.is_used = False
+        self.hires_deriv = None
+
+    def set_not_involved(self):
+        self.not_involved = True
+
+    def set_used(self):
+        self.is_used = True
+
+    def set_involved(self):
+        self.not_involved = False
+
+    def update_par(self, delta_par):
+        self.old_values.append(self.value)
+        new_value = self.value + delta_par
+        if self.constrain_positive:
+            while new_value <= 0.0:
+                delta_par /= 2
+                new_value = self.value + delta_par
+        self.value = new_value
+
+    def add_hires_deriv(self, derivative):
+        self.hires_deriv = copy.deepcopy(derivative)
+
+    def erase_hires_deriv(self):
+        self.hires_deriv = None
+
+    def store_deriv(self, derivative, num):
+        try:
+            self.derivatives[num] = copy.deepcopy(derivative)
+        except IndexError:
+            self.derivatives.append(copy.deepcopy(derivative))
+
+
+class RetSet(object):
+    """Parameters of one quantity, e.g. the VMR profile of a gas (smm:259-283); `name` is the
+    gas name for a VMR set."""
+
+    def __init__(self, name, params):
+        self.name = name
+        self.set = [copy.deepcopy(par) for par in params]
+        self.n_par = len(self.set)
+
+    def items(self):
+        return zip([par.key for par in self.set], self.set)
+
+    def keys(self):
+        return [par.key for par in self.set]
+
+    def profile(self):
+        """sum_p maskgrid_p * value_p (smm:483-489) as an AtmProfile named 'vmr' (and self.name)."""
+        grid = self.set[0].maskgrid.grid
+        prof = sbm.AtmProfZeros(grid, 'vmr', self.set[0].maskgrid.interp['mask'])
+        for par in self.set:
+            prof += par.maskgrid * par.value
+        prof.add_profile(prof.values['vmr'], self.name, prof.interp['vmr'])
+        return prof
+
+
+class LinearProfile_1D_new(RetSet):
+    """Profile through linear interpolation of altitude nodes (smm:442-489)."""
+
+    def __init__(self, name, alt_grid, alt_nodes, apriori_prof, apriori_prof_err,
+                 first_guess_prof=None):
+        self.name = name
+        self.set = []
+        self.n_par = len(alt_nodes)
+        self.alts = list(alt_nodes)
+        z = alt_grid.grid[0] if hasattr(alt_grid, 'grid') else np.asarray(alt_grid, dtype=float)
+        if first_guess_prof is None:
+            first_guess_prof = apriori_prof
+        n = len(alt_nodes)
+        for i in range(n):
+            if i == 0:
+                mask = alt_triangle(z, alt_nodes[0], node_up=alt_nodes[1], first=True)
+            elif i == n - 1:
+                mask = alt_triangle(z, alt_nodes[-1], node_lo=alt_nodes[-2], last=True)
+            else:
+                mask = alt_triangle(z, alt_nodes[i], node_up=alt_nodes[i + 1], node_lo=alt_nodes[i - 1])
+            self.set.append(RetParam(name, alt_nodes[i], mask, apriori_prof[i], apriori_prof_err[i],
+                                     first_guess=first_guess_prof[i]))
+
+    def check_involved(self, parkey, coord_range):
+        indp = self.alts.index(parkey)
+        if indp == len(self.alts) - 1:
+            return True
+        return not coord_range['alt'][0] > self.alts[indp + 1]
+
+
+class LinearProfile_1D(LinearProfile_1D_new):
+    """Same with the reference's older signature taking the atmosphere (smm:563-597)."""
+
+    def __init__(self, name, atmosphere, alt_nodes, apriori_prof, apriori_prof_err,
+                 first_guess_prof=None):
+        LinearProfile_1D_new.__init__(self, name, atmosphere.grid.coords['alt'], alt_nodes,
+                                      apriori_prof, apriori_prof_err, first_guess_prof)
+        self.orig_atmosphere = atmosphere
+
+
+class BayesSet(object):
+    """The full parameter space that drives the forward model (smm:161-257)."""
+
+    def __init__(self, tag=None):
+        self.tag = tag
+        self.sets = dict()
+        self.n_tot = 0
+        self.order = []
+        self.old_params = []
+
+    def add_set(self, set_):
+        self.sets[set_.name] = copy.deepcopy(set_)
+        self.n_tot += set_.n_par
+        self.order.append(set_.name)
+
+    def values(self):
+        return [par.value for par in self.params()]
+
+    def params(self):
+        return [par for nam in self.order for par in self.sets[nam].set]
+
+    def n_used_par(self):
+        return sum([par.is_used for par in self.params()])
+
+    def param_vector(self):
+        return np.array([par.value for par in self.params()])
+
+    def apriori_vector(self):
+        return np.array([par.apriori for par in self.params()])
+
+    def VCM_apriori(self):
+        return np.diag(np.array([par.apriori_err for par in self.params()], dtype=float) ** 2)
+
+    def build_jacobian(self, masks=None):
+        """[n_obs_points x n_tot] from the per-pixel derivative spectra stored on the parameters
+        (smm:197-222)."""
+        masktot = None
+        if masks is not None:
+            masktot = np.concatenate([np.asarray(m) for m in masks]).astype(bool)
+        jac = []
+        for par in self.params():
+            dertot = np.concatenate([np.asarray(der.spectrum, dtype=float) for der in par.derivatives])
+            jac.append(dertot if masktot is None else dertot[masktot])
+        self.jacobian = np.array(jac).T
+        return self.jacobian
+
+
 def los_step_tables(loss, planet):
     """engine.LosSteps of a list of sbm.LineOfSight that went through calc_radtran_steps."""
     gi = loss[0].radtran_steps['gas_isos']
@@ -531,6 +716,85 @@ def los_batch_radiances(loss, sp_grid, planet, LUTS, solo_absorption=False,
     units = getattr(sp_grid, 'units', 'cm_1')
     sub = spcl.SpectralGrid(grid[pt0:pt0 + n_pts], units=units)
     return [spcl.SpectralIntensity(rad[i], sub) for i in range(len(loss))]
+
+
+def los_jac_tables(loss, bayes_set, set_name, n_steps_max):
+    """dfrac [n_los][n_steps_max][n_par] = (d column / d parameter) / column of gas `set_name` for
+    the parameters of bayes_set.sets[set_name], from the `dcolumns` that
+    calc_radtran_steps(calc_derivatives=True, bayes_set=...) stored on every step."""
+    pars = bayes_set.sets[set_name].set
+    dfrac = np.zeros((len(loss), n_steps_max, len(pars)))
+    for l, los in enumerate(loss):
+        for k, st in enumerate(los.radtran_steps['step']):
+            col = st['columns'][set_name]
+            if col == 0.0:
+                continue
+            for q, par in enumerate(pars):
+                dfrac[l, k, q] = st['dcolumns'][(par.nameset, par.key)] / col
+    return dfrac
+
+
+def los_batch_jacobians(loss, sp_grid, planet, LUTS, bayes_set, solo_absorption=False,
+                        initial_intensity=None, lowres=None, pt0=0, n_pts=None):
+    """Radiances AND their derivatives with respect to every parameter of bayes_set for a batch of
+    lines of sight (the `calc_derivatives=True` path of radtran_fast, smm:2837-2881), one fused
+    library call per retrieved gas.  Parameter sets whose name is not a gas of the planet get zero
+    derivatives.  Returns (rad, jac): lists of SpectralIntensity / lists of per-parameter
+    SpectralIntensity (order of bayes_set.params()); with lowres = (centres, widths) the CUDA
+    tensors low [n_los][n_chan], jac_low [n_los][n_tot][n_chan]."""
+    import torch
+    gi, steps = los_step_tables(loss, planet)
+    luts, keep = [], []
+    for m, (g, iso) in enumerate(gi):
+        im = getattr(planet.gases[g], iso)
+        L = LUTS.get((im.mol_name, im.iso))
+        if L is not None:
+            luts.append(L.device_lut())
+            keep.append(m)
+    if not luts:
+        raise ValueError('no LUT for any gas of the planet in this spectral range')
+    if len(keep) != len(gi):
+        steps = engine.LosSteps(steps.n_steps, steps.temp, steps.pres, steps.column[keep],
+                                steps.tvib[keep])
+    grid = sp_grid.grid if hasattr(sp_grid, 'grid') else np.asarray(sp_grid)
+    n_pts = len(grid) - pt0 if n_pts is None else n_pts
+    i0 = None
+    if initial_intensity is not None:
+        i0 = torch.as_tensor(np.broadcast_to(np.asarray(initial_intensity, dtype=float),
+                                             (len(loss), n_pts)).copy(), device="cuda")
+    gdev = None
+    if lowres is not None:
+        gdev = torch.as_tensor(np.ascontiguousarray(grid, dtype=float), device="cuda")
+    n_out = n_pts if lowres is None else len(lowres[0])
+    rad, blocks = None, []
+    for nam in bayes_set.order:
+        n_par = bayes_set.sets[nam].n_par
+        in_jac = [1 if gi[m][0] == nam else 0 for m in keep]
+        if nam not in planet.gases or not any(in_jac):
+            blocks.append(torch.zeros((len(loss), n_par, n_out), dtype=torch.float64, device="cuda"))
+            continue
+        dfrac = los_jac_tables(loss, bayes_set, nam, steps.n_steps_max)
+        if lowres is None:
+            rad, jac = engine.los_rt_lut_jac(luts, steps, dfrac, gas_in_jac=in_jac, pt0=pt0,
+                                             n_pts=n_pts, i0=i0, solo_absorption=solo_absorption)
+        else:
+            rad, jac = engine.los_rt_lut_jac_lowres(luts, steps, dfrac, gdev, lowres[0], lowres[1],
+                                                    gas_in_jac=in_jac, pt0=pt0, n_pts=n_pts, i0=i0,
+                                                    solo_absorption=solo_absorption)
+        blocks.append(jac)
+    if rad is None:   # no parameter touches a gas with a LUT: plain forward model
+        rad = (engine.los_rt_lut(luts, steps, pt0=pt0, n_pts=n_pts, i0=i0,
+                                 solo_absorption=solo_absorption) if lowres is None else
+               engine.los_rt_lut_lowres(luts, steps, gdev, lowres[0], lowres[1], pt0=pt0,
+                                        n_pts=n_pts, i0=i0, solo_absorption=solo_absorption))
+    jac = torch.cat(blocks, dim=1)
+    if lowres is not None:
+        return rad, jac
+    rad, jac = rad.cpu().numpy(), jac.cpu().numpy()
+    sub = spcl.SpectralGrid(grid[pt0:pt0 + n_pts], units=getattr(sp_grid, 'units', 'cm_1'))
+    return ([spcl.SpectralIntensity(rad[i], sub) for i in range(len(loss))],
+            [[spcl.SpectralIntensity(jac[i, q], sub) for q in range(jac.shape[1])]
+             for i in range(len(loss))])
 
 
 def fov_weights(pixel_rot=0.0):
@@ -624,3 +888,79 @@ def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_
         with open(os.path.join(inputs['out_dir'], 'lowres_radtran_{}.pic'.format(nome_inv)), 'wb') as f:
             pickle.dump([sims, radtrans_out], f, protocol=-1)
     return sims, radtrans_out, dict()
+
+
+def inversion_fast_limb(inputs, planet, lines, bayes_set, pixels, wn_range=None, sp_gri=None,
+                        chi_threshold=0.01, max_it=10, lambda_LM=0.1, L1_reg=False,
+                        radtran_opt=dict(), debugfile=None, save_hires=False, save_lowres=True,
+                        LUTopt=dict(), test=False, use_tangent_sza=False, group_observations=False,
+                        nome_inv='1', solo_simulation=False, invert_LOS_direction=False,
+                        alt_step_sims=50., alt_first_los=None, track_levels=None, check_log=None):
+    """ONE forward + Jacobian evaluation of the fast limb retrieval (smm:2598-2956), batched on the
+    GPU: the a-priori / current VMR profiles of bayes_set are installed on the planet (:2626-2627),
+    all lines of sight of all pixels go through the radtran steps with derivative columns and ONE
+    fused library call per retrieved gas returns low-res radiances and derivative spectra; both are
+    FOV-integrated per pixel (:2934-2940) and the derivatives are stored on the parameters
+    (`par.store_deriv`), so that `bayes_set.build_jacobian()` gives the Jacobian the reference's
+    inversion step consumes.  The Levenberg-Marquardt update itself (:2962-2987, `max_it`,
+    `lambda_LM`, `chi_threshold`) is retrieval algebra and out of scope: this
+    function returns after the evaluation.  Returns (sims, radtrans, derivs) with
+    derivs[(LOS tag, nameset, key)] = low-res derivative SpectralIntensity."""
+    pixels = sorted(pixels, key=lambda p: p.limb_tg_alt)
+    if sp_gri is None:
+        if wn_range is None:
+            raise ValueError('inversion_fast_limb needs wn_range or sp_gri')
+        sp_gri = prepare_spe_grid(wn_range).spectral_grid
+    for gas in bayes_set.sets.keys():
+        if gas in planet.gases:
+            planet.gases[gas].add_clim(bayes_set.sets[gas].profile())
+    LUTopt = dict(LUTopt)
+    if 'max_pres' not in LUTopt:
+        LUTopt['max_pres'] = max(planet.atmosphere.calc(p.low_LOS().get_tangent_point(), 'pres')
+                                 for p in pixels)
+    gases = list(planet.gases.values())
+    PT = calc_PT_couples_atmosphere(lines, gases, planet.atmosphere, **LUTopt)
+    LUTS = check_and_build_allluts(inputs, sp_gri, lines, gases, PTcouples=PT, LUTopt=LUTopt)
+
+    sim_LOSs = []
+    for pix in pixels:
+        sim_LOSs += [pix.low_LOS(), pix.LOS(), pix.up_LOS()]
+    for num, los in enumerate(sim_LOSs):
+        los.tag = 'LOS{:02d}'.format(num)
+        los.calc_atm_intersections(planet)
+        pix = pixels[num // 3]
+        if hasattr(pix, 'sub_solar_point'):
+            los.calc_SZA_along_los(planet, pix.sub_solar_point())
+        los.calc_radtran_steps(planet, lines, calc_derivatives=True, bayes_set=bayes_set,
+                               **radtran_opt)
+
+    obs = pixels[0].observation
+    centres, widths = obs.spectral_grid.grid, obs.bands.spectrum
+    low, jlow = los_batch_jacobians(sim_LOSs, sp_gri, planet, LUTS, bayes_set,
+                                    lowres=(centres, widths))
+    low, jlow = low.cpu().numpy(), jlow.cpu().numpy()
+    radtrans_out, derivs = dict(), dict()
+    pars = bayes_set.params()
+    for i, los in enumerate(sim_LOSs):
+        radtrans_out[los.tag] = spcl.SpectralIntensity(low[i], obs.spectral_grid)
+        for q, par in enumerate(pars):
+            if not los.involved_retparams.get((par.nameset, par.key), False):
+                jlow[i, q] = 0.0                                   # zeroder, smm:2871-2872
+            else:
+                par.set_used()
+            derivs[(los.tag, par.nameset, par.key)] = spcl.SpectralIntensity(jlow[i, q],
+                                                                            obs.spectral_grid)
+    sims = []
+    for k, pix in enumerate(pixels):
+        rot = getattr(pix, 'pixel_rot', 0.0) or 0.0
+        sims.append(spcl.SpectralIntensity(fov_integrate(low[3 * k:3 * k + 3], rot),
+                                           obs.spectral_grid))
+        for q, par in enumerate(pars):
+            der = fov_integrate(jlow[3 * k:3 * k + 3, q], rot)
+            par.store_deriv(spcl.SpectralIntensity(der, obs.spectral_grid), num=k)
+    for par in pars:
+        par.hires_deriv = None
+    if isinstance(inputs, dict) and inputs.get('out_dir') and save_lowres:
+        with open(os.path.join(inputs['out_dir'], 'lowres_radtran_{}.pic'.format(nome_inv)), 'wb') as f:
+            pickle.dump([sims, radtrans_out], f, protocol=-1)
+    return sims, radtrans_out, derivs

@@ -156,3 +156,76 @@ def test_lut_level_files_round_trip_through_the_device(world, tmp_path):
     a = eng.los_rt_lut([lut.device_lut()], steps).cpu().numpy()
     b = eng.los_rt_lut([back.device_lut()], steps).cpu().numpy()
     assert a.max() > 0 and np.array_equal(a, b)
+
+
+def _bayes(smm, planet, nodes=(300., 500., 700., 900., 1100.), vmr=0.015):
+    z = planet.atmosphere.grid.coords['alt']
+    prof = smm.LinearProfile_1D_new('CH4', z, list(nodes), [vmr] * len(nodes), [0.3 * vmr] * len(nodes))
+    bs = smm.BayesSet('ch4')
+    bs.add_set(prof)
+    return bs
+
+
+def test_inversion_fast_limb_forward_and_jacobian(world):
+    """smm.inversion_fast_limb (one forward + Jacobian evaluation, smm:2598-2956): the forward part
+    equals smm.radtrans; the derivative columns of the step builder add up to the column
+    (linearity of curgod_fort_2 in the VMR); the FOV-integrated analytic Jacobian matches central
+    finite differences of the whole host path on an LTE planet (where a step's T, P and T_vib do
+    not depend on the VMR)."""
+    smm, S = world["smm"], world["S"]
+    planet = S.titan_planet(world["tab"]["level_energies"], nonlte=False)
+    sp = world["sp"]
+    centres = np.linspace(2997.0, 3003.0, 7)
+    widths = np.full(7, 0.6)
+    inputs = dict(n_split=1, cart_LUTS=None, out_dir=None, n_threads=8)
+    LUTopt = dict(pres_step_log=1.0, temp_step=5.0)
+    opt = dict(max_T_variation=5., max_Plog_variation=1.)
+    bs = _bayes(smm, planet)
+
+    def run(bset):
+        pixels = S.vims_pixels([450.0, 700.0], channels=centres, widths=widths)
+        return smm.inversion_fast_limb(inputs, planet, world["lines"], bset, pixels, sp_gri=sp,
+                                       radtran_opt=opt, LUTopt=dict(LUTopt))
+
+    sims, rt, derivs = run(bs)
+    assert len(sims) == 2 and len(rt) == 6 and len(derivs) == 6 * bs.n_tot
+    pixels = S.vims_pixels([450.0, 700.0], channels=centres, widths=widths)
+    sims_f, rt_f, _ = smm.radtrans(inputs, planet, world["lines"], pixels, sp_gri=sp,
+                                   radtran_opt=opt, LUTopt=dict(LUTopt))
+    for a, b in zip(sims, sims_f):
+        assert rel_err(a.spectrum, b.spectrum) < 1e-12
+    # node at 300 km lies below both tangent heights (first node: mask = 1 below it, so it is
+    # still involved through its triangle up to 500 km); the 1100 km node only feeds the top
+    jac = bs.build_jacobian()
+    assert jac.shape == (2 * 7, bs.n_tot) and np.all(np.isfinite(jac))
+    assert bs.n_used_par() == bs.n_tot
+    # derivative columns: sum_p value_p * d u/d p == u for every step of every LOS
+    pix = sorted(pixels, key=lambda p: p.limb_tg_alt)
+    los = pix[0].LOS()
+    los.calc_atm_intersections(planet)
+    los.calc_radtran_steps(planet, None, calc_derivatives=True, bayes_set=bs, **opt)
+    for st in los.radtran_steps['step']:
+        tot = sum(par.value * st['dcolumns'][(par.nameset, par.key)] for par in bs.params())
+        assert abs(tot - st['columns']['CH4']) <= 1e-10 * st['columns']['CH4']
+    # finite differences of the full host path
+    for q in (1, 2, 3):
+        up, dn = _bayes(smm, planet), _bayes(smm, planet)
+        h = 1e-3 * up.params()[q].value
+        up.params()[q].value += h
+        dn.params()[q].value -= h
+        s_up, _, _ = run(up)
+        s_dn, _, _ = run(dn)
+        for k in range(2):
+            fd = (s_up[k].spectrum - s_dn[k].spectrum) / (2 * h)
+            got = bs.params()[q].derivatives[k].spectrum
+            scale = max(np.abs(fd).max(), np.abs(jac[k * 7:(k + 1) * 7]).max() * 1e-3)
+            assert np.abs(got - fd).max() < 2e-5 * scale, (q, k)
+    # reference-shaped single-LOS call: hires_deriv attached to the returned parameter set
+    max_p = max(planet.atmosphere.calc(p.low_LOS().get_tangent_point(), 'pres') for p in pix)
+    PT = smm.calc_PT_couples_atmosphere(world["lines"], list(planet.gases.values()),
+                                        planet.atmosphere, max_pres=max_p, **LUTopt)
+    LUTS = smm.check_and_build_allluts(inputs, sp, world["lines"], list(planet.gases.values()),
+                                       PTcouples=PT, LUTopt=LUTopt)
+    one = los.radtran_fast(sp, planet, LUTS=LUTS, calc_derivatives=True, bayes_set=bs)
+    assert len(one[2].params()) == bs.n_tot
+    assert one[2].params()[2].hires_deriv.spectrum.shape == one[0].spectrum.shape

@@ -306,3 +306,28 @@ def test_lut_level_streams_round_trip_and_reference_module_names(tmp_path):
     assert pts == [[0.01, 150.0]]
     assert isinstance(sets[0]['absorption'], spcl.SpectralGcoeff)
     assert np.array_equal(sets[0]['absorption'].spectrum, np.arange(33.0))
+
+
+def test_alt_triangle_matches_reference_loop():
+    """Vectorised alt_triangle against the literal per-point loop of smm:319-352."""
+    from spectrobot_b200 import spect_main_module as smm
+    z = np.arange(0.0, 1501.0, 10.0)
+
+    def ref(alt_grid, node_alt, node_lo=None, node_up=None, first=False, last=False):
+        cos = np.zeros(len(alt_grid))
+        for ii, alt in enumerate(alt_grid):
+            if first:
+                cos[ii] = 1.0 if alt < node_alt else (1.0 - (alt - node_alt) / (node_up - node_alt) if alt < node_up else 0.0)
+            elif last:
+                cos[ii] = 1.0 if alt > node_alt else (1.0 - (node_alt - alt) / (node_alt - node_lo) if alt > node_lo else 0.0)
+            elif alt < node_lo or alt > node_up:
+                cos[ii] = 0.0
+            elif alt >= node_alt:
+                cos[ii] = 1.0 - (alt - node_alt) / (node_up - node_alt)
+            else:
+                cos[ii] = 1.0 - (node_alt - alt) / (node_alt - node_lo)
+        return cos
+    assert np.array_equal(smm.alt_triangle(z, 300., node_up=500., first=True).mask, ref(z, 300., node_up=500., first=True))
+    assert np.array_equal(smm.alt_triangle(z, 900., node_lo=700., last=True).mask, ref(z, 900., node_lo=700., last=True))
+    assert np.array_equal(smm.alt_triangle(z, 505., node_lo=300., node_up=700.).mask, ref(z, 505., 300., 700.))
+    assert np.array_equal(smm.alt_triangle(z, 500., step=200.).mask, ref(z, 500., 300., 700.))
