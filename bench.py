@@ -383,6 +383,51 @@ def run_ours(args):
     agree = float(((rad_f[:n_los] - rad_k3).abs() / rad_k3.abs().clamp_min(1e-300)).max().item())
     fused_step_pts = float(st_all["n_steps"][:n_fused].sum()) * n_grid
     del rad_f
+    # algorithmic FP64 work of the grouped product: every (step, point) needs one FMA per non-zero
+    # LUT row of the 4 interpolation cells
+    rows_cell = int((g32[:2] != 0).any(dim=3).any(dim=0).sum().item())
+    fused_flop = 2.0 * 4 * rows_cell * fused_step_pts
+
+    # ---- forward + analytic Jacobians (BASELINE configs[4] shape: every LOS also returns its
+    # derivative spectra for n_par VMR nodes), reduced to the instrument channels on the device ----
+    n_par = 12
+    ns_f = st_all["n_steps"][:n_fused]
+    kk = np.arange(steps_f.n_steps_max)[None, :]
+    node = np.minimum(kk * n_par // np.maximum(ns_f[:, None], 1), n_par - 1)     # triangle masks:
+    wgt = 0.25 + 0.5 * ((kk * 7919) % 97) / 97.0                                 # two nodes per step
+    dfrac = np.zeros((n_fused, steps_f.n_steps_max, n_par))
+    ii = np.arange(n_fused)[:, None].repeat(steps_f.n_steps_max, 1)
+    np.add.at(dfrac, (ii, kk.repeat(n_fused, 0), node), np.broadcast_to(wgt, node.shape))
+    np.add.at(dfrac, (ii, kk.repeat(n_fused, 0), np.minimum(node + 1, n_par - 1)),
+              np.broadcast_to(1.0 - wgt, node.shape))
+    dfrac *= (kk < ns_f[:, None])[:, :, None]
+    j_centres = np.linspace(grid[0] + 10.0, grid[-1] - 10.0, 36)
+    j_widths = np.full(36, 6.2)
+    gdev_j = torch.as_tensor(grid, device="cuda")
+    cj, wj = torch.as_tensor(j_centres, device="cuda"), torch.as_tensor(j_widths, device="cuda")
+    engine.los_rt_lut_lowres([lut], steps_f, gdev_j, cj, wj)
+    low_j, jac_j = engine.los_rt_lut_jac_lowres([lut], steps_f, dfrac, gdev_j, cj, wj)
+    barrier()
+    ev0.record()
+    low_f = engine.los_rt_lut_lowres([lut], steps_f, gdev_j, cj, wj, check_status=False)
+    ev1.record()
+    barrier()
+    fwd_low_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    ev0.record()
+    low_j, jac_j = engine.los_rt_lut_jac_lowres([lut], steps_f, dfrac, gdev_j, cj, wj,
+                                                check_status=False)
+    ev1.record()
+    barrier()
+    jac_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    jacobian = {"value": world * n_fused / (jac_ms * 1e-3), "unit": "LOS/s (radiance + %d derivative "
+                "spectra each)" % n_par, "n_par": n_par, "los_per_rank": n_fused, "ms": jac_ms,
+                "forward_only_ms": fwd_low_ms, "channels": 36,
+                "derivative_spectra_per_s": world * n_fused * n_par / (jac_ms * 1e-3),
+                "radiance_same_as_forward": bool(torch.equal(low_j, low_f)),
+                "finite": bool(torch.isfinite(jac_j).all().item()),
+                "path": "sr_los_rt_lut_jac_lowres_dev (k_los_mma -> k_los_layers_jac -> "
+                        "k_convolve_lowres per LOS block)"}
+    del low_j, jac_j, low_f, dfrac
 
     # ---- e2e: reference-facing host call (host step tables in, host radiances out) ------------
     sub = steps_all.subset(slice(0, n_e))
@@ -456,7 +501,14 @@ def run_ours(args):
         "fused": {"value": world * n_fused / (fused_ms * 1e-3), "unit": "LOS/s",
                   "los_per_rank": n_fused, "ms_per_step": fused_ms,
                   "step_points_per_s": world * fused_step_pts / (fused_ms * 1e-3),
-                  "max_rel_diff_vs_k3": agree},
+                  "max_rel_diff_vs_k3": agree,
+                  "roofline": {"bound": "fp64", "achieved": fused_flop / (fused_ms * 1e-3) / 1e12,
+                               "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                               "frac": fused_flop / (fused_ms * 1e-3) / fp64_peak, "traffic": None,
+                               "kernel": "k_los_mma (+ k_los_layers in the same timed region)",
+                               "note": "2 flop x %d non-zero LUT rows x 4 cells per (step, point); "
+                                       "DFMA rate measured live by sr_fp64_peak" % rows_cell}},
+        "jacobian": jacobian,
         "batch": batch, "voigt": voigt, "lut_build": lut_build,
         "gpu_launches": int(launches), "clocks": sampler.summary(),
     }
