@@ -284,6 +284,45 @@ int sr_convolve_lowres_host(const double* grid, long n_pts, const double* spec, 
                             const double* centre, const double* width, int n_chan,
                             double n_sigma, double* out);
 
+/* ===========================================================================================
+ * Tier 2 -- LOS geometry and radtran steps for a whole batch
+ * LineOfSight.calc_atm_intersections + calc_radtran_steps [callers spect_main_module.py:2746-2767,
+ * 3133-3147; options radtran_3D_ch4.py:200-202, 311; integrals curgods.f:2-98; the methods
+ * themselves are in the reference's missing spect_base_module - DESIGN.md 6.1 is the specification]
+ * =========================================================================================*/
+
+/* Atmosphere on an altitude grid (km, ascending) with n_band latitude boxes (lat_edges[n_band+1]
+ * in degrees, ascending; NULL when n_band == 1).  temp linear, pres log-linear, vmr and tvib
+ * linear in altitude.  One entry of vmr per LUT of the later LOS call (isotopologues of one gas
+ * repeat the profile).  tvib_on[n_gas][n_sets_max]: 1 = the level has its own T_vib profile,
+ * 0 = T_vib is the step temperature, -1 = the gas has no such level (padding, 100 K). */
+typedef struct {
+    int n_band, n_z, n_gas, n_sets_max;
+    const double *lat_edges, *z;
+    const double *temp, *pres;     /* [n_band][n_z], K and hPa */
+    const double *vmr;             /* [n_gas][n_band][n_z] */
+    const double *tvib;            /* [n_gas][n_sets_max][n_band][n_z] or NULL */
+    const int* tvib_on;            /* [n_gas][n_sets_max] (NULL when n_sets_max == 0) */
+    double radius_km, top_km;      /* planet radius, atmosphere extension above it */
+} sr_atmosphere;
+
+/* For n_los rays (origin = observer position, direction = unit vector, planetocentric Cartesian
+ * km): samples every delta_x_km anchored on the tangent point between the atmosphere
+ * intersections (or down to the surface), ordered far end -> observer; consecutive samples are
+ * merged into steps while max T - min T <= max_T_variation and max ln P - min ln P <=
+ * max_Plog_variation; every step gets air-weighted Curtis-Godson T and P, the gas columns
+ * (molecules cm-2) and column-weighted vibrational temperatures.  Outputs are HOST arrays in the
+ * sr_los_steps layout with n_steps_max columns (padding: 100 K, 1e-6 hPa, column 0).
+ * n_par > 0: masks[n_par][n_z] are the altitude weights of retrieval parameters of gas entry
+ * jac_gas; dfrac[n_los][n_steps_max][n_par] = (d column / d parameter) / column for
+ * sr_los_rt_lut_jac_*.  n_steps_needed (optional) returns the largest step count; when it exceeds
+ * n_steps_max the call returns SR_ERR_LIMIT. */
+int sr_los_steps_build(const sr_atmosphere* atm, int n_los, const double* origin,
+                       const double* direction, double delta_x_km, double max_T_variation,
+                       double max_Plog_variation, int n_par, const double* masks, int jac_gas,
+                       int n_steps_max, int* n_steps, double* temp, double* pres, double* column,
+                       double* tvib, double* dfrac, int* n_steps_needed);
+
 /* FP64 FMA micro-benchmark used by bench.py for the K1/K2 roofline denominator: runs
  * `iters` dependent-chain FMAs per thread on a full grid and returns achieved FLOP/s. */
 int sr_fp64_peak(int iters, double* flops_per_s);

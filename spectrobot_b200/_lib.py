@@ -48,6 +48,12 @@ class sr_los_steps(C.Structure):
                 ("column", _dp), ("tvib", _dp)]
 
 
+class sr_atmosphere(C.Structure):
+    _fields_ = [("n_band", C.c_int), ("n_z", C.c_int), ("n_gas", C.c_int), ("n_sets_max", C.c_int),
+                ("lat_edges", _dp), ("z", _dp), ("temp", _dp), ("pres", _dp), ("vmr", _dp),
+                ("tvib", _dp), ("tvib_on", _ip), ("radius_km", C.c_double), ("top_km", C.c_double)]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 SIGNATURES = {
     "sr_version": (C.c_int, []),
@@ -106,6 +112,9 @@ SIGNATURES = {
                                          C.c_double, _vp, _vp]),
     "sr_convolve_lowres_host": (C.c_int, [_dp, C.c_long, _dp, C.c_int, _dp, _dp, C.c_int,
                                           C.c_double, _dp]),
+    "sr_los_steps_build": (C.c_int, [C.POINTER(sr_atmosphere), C.c_int, _dp, _dp, C.c_double,
+                                     C.c_double, C.c_double, C.c_int, _dp, C.c_int, C.c_int, _ip,
+                                     _dp, _dp, _dp, _dp, _dp, _ip]),
     "sr_fp64_peak": (C.c_int, [C.c_int, _dp]),
 }
 

@@ -250,4 +250,43 @@ __device__ __forceinline__ void exp_pair(double x, double& ex, double& em) {
     em = (ni == 0) ? p : fma(s, p, s - 1.0);
 }
 
+// ---------------------------------------------------------------------------------------------
+// One segment of the Curtis-Godson integrals curgod_fort_1..4 (curgods.f:2-98): number density
+// piecewise exponential, vmr (and f in variant 3) piecewise linear, nd*f exponential in variant 4.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double curgod_seg1(double nd0, double nd1, double dx) {   // :14-19
+    const double fu = nd1 / nd0;
+    const double D = log(fu) / dx;
+    return (nd1 - nd0) / D;
+}
+__device__ __forceinline__ double curgod_seg2(double nd0, double nd1, double v0, double v1,
+                                              double dx) {                             // :35-42
+    const double A = nd0 * v0;
+    const double B = nd0 * (v1 - v0) / dx;
+    const double fu = nd1 / nd0;
+    const double D = log(fu) / dx;
+    return (A * D * (fu - 1.) + B * fu * (D * dx - 1.) + B) / (D * D);
+}
+__device__ __forceinline__ double curgod_seg3(double nd0, double nd1, double v0, double v1,
+                                              double f0, double f1, double dx) {       // :58-70
+    const double A = nd0 * v0 * f0;
+    const double cc = (v1 - v0) / dx;
+    const double bb = (f1 - f0) / dx;
+    const double B = nd0 * (v0 * bb + f0 * cc);
+    const double Cc = nd0 * bb * cc;
+    const double fu = nd1 / nd0;
+    const double D = log(fu) / dx;
+    return (fu * (D * (A * D + B * (D * dx - 1.)) + Cc * (D * dx * (D * dx - 2.) + 2.)) +
+            D * (B - A * D) - 2 * Cc) / (D * D * D);
+}
+__device__ __forceinline__ double curgod_seg4(double nd0, double nd1, double v0, double v1,
+                                              double f0, double f1, double dx) {       // :86-94
+    const double A = nd0 * v0 * f0;
+    const double cc = (v1 - v0) / dx;
+    const double B = nd0 * f0 * cc;
+    const double fu = nd1 * f1 / (nd0 * f0);
+    const double D = log(fu) / dx;
+    return (A * D * (fu - 1.) + B * fu * (D * dx - 1.) + B) / (D * D);
+}
+
 }  // namespace srdev

@@ -1,0 +1,357 @@
+// sr_steps.cu -- LOS geometry and radtran-step construction for whole batches on the device
+// (SURVEY 8f row 4).  Replaces, for a batch of lines of sight, the per-LOS host chain
+//   LineOfSight.calc_atm_intersections   (ray / atmosphere-shell intersections, samples every delta_x)
+//   LineOfSight.calc_radtran_steps       (adaptive merge limited by max_T_variation / max_Plog_variation,
+//                                         Curtis-Godson T, P, gas columns, per-level vibrational
+//                                         temperatures; callers spect_main_module.py:2746-2767,
+//                                         3133-3147; radtran_3D_ch4.py:200-202, 311)
+//   curgod_fort_1..4                     curgods.f:2-98
+// The reference's own code for the first two is in the missing spect_base_module; DESIGN.md 6.1 is
+// the specification, spectrobot_b200/spect_base_module.py the host implementation this kernel
+// pair must agree with.
+//
+// Kernels
+//   k_steps_points     one thread per LOS: sample points (far end -> observer), T, P, number
+//                      density per point, greedy merge into steps (bounds per step)
+//   k_steps_integrals  one thread per (LOS, step): air column, Curtis-Godson T and P, gas columns,
+//                      column-weighted vibrational temperatures, parameter derivative columns
+#include <algorithm>
+#include <cmath>
+#include <vector>
+#include "sr_common.h"
+#include "sr_device.cuh"
+
+namespace {
+
+constexpr double KB_HPA = 1.38065e-19;   // spect_classes.py:34 (P in hPa, n in cm-3)
+constexpr int MAX_GAS_ST = 8;
+
+struct AtmDev {
+    int n_band, n_z, n_gas, n_sets_max, n_par, jac_gas;
+    const double* lat_edges;   // [n_band+1] (n_band > 1)
+    const double* z;           // [n_z]
+    const double* temp;        // [n_band][n_z]
+    const double* lnpres;      // [n_band][n_z] log of P (hPa): P is log-linear in z
+    const double* vmr;         // [n_gas][n_band][n_z]
+    const double* tvib;        // [n_gas][n_sets_max][n_band][n_z]
+    const int* tvib_on;        // [n_gas][n_sets_max]: 1 own profile, 0 T_vib = step T, -1 no level
+    const double* masks;       // [n_par][n_z]
+    double radius, top;
+};
+
+// np.interp(x, xp, fp) on an ascending grid, clamped outside
+__device__ __forceinline__ int interp_index(const double* __restrict__ xp, int n, double x) {
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        const int m = (lo + hi) >> 1;
+        if (xp[m] <= x) lo = m; else hi = m;
+    }
+    return lo;
+}
+__device__ __forceinline__ double interp_at(const double* __restrict__ xp, const double* __restrict__ fp,
+                                            int n, int j, double x) {
+    if (x <= xp[0]) return fp[0];
+    if (x >= xp[n - 1]) return fp[n - 1];
+    const double slope = (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j]);
+    return slope * (x - xp[j]) + fp[j];
+}
+
+struct PtArgs {
+    AtmDev A;
+    const double* origin;      // [n_los][3]
+    const double* dir;         // [n_los][3]
+    int n_los, n_pts_max, n_steps_max;
+    double delta_x, max_dT, max_dlnP;
+    // per-point scratch [n_los][n_pts_max]
+    double *T, *P, *nd, *x, *alt;
+    int *band, *jz;
+    int* n_pts;                // [n_los]
+    int* n_steps;              // [n_los] (true count, may exceed n_steps_max)
+    int* bounds;               // [n_los][n_steps_max][2]
+};
+
+__global__ void k_steps_points(PtArgs a) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= a.n_los) return;
+    const double ox = a.origin[3 * l], oy = a.origin[3 * l + 1], oz = a.origin[3 * l + 2];
+    const double dx = a.dir[3 * l], dy = a.dir[3 * l + 1], dz = a.dir[3 * l + 2];
+    const double st = -(ox * dx + oy * dy + oz * dz);
+    const double tx = ox + st * dx, ty = oy + st * dy, tz = oz + st * dz;
+    const double rt = sqrt(tx * tx + ty * ty + tz * tz);
+    const double r_top = a.A.radius + a.A.top;
+    a.n_pts[l] = 0;
+    a.n_steps[l] = 0;
+    if (rt >= r_top) return;
+    const double half = sqrt(r_top * r_top - rt * rt);
+    const double s_near = st - half;
+    double s_far = st + half;
+    if (rt < a.A.radius) s_far = st - sqrt(a.A.radius * a.A.radius - rt * rt);   // hits the surface
+    const int kmax = (int)floor(half / a.delta_x - 1e-9);
+    const size_t o = (size_t)l * a.n_pts_max;
+    int n = 0;
+    double s0 = 0.0;
+    // greedy merge state: current step starts at point i0; running extrema over [i0, i]
+    int i0 = 0, ns = 0;
+    double tmin = 0, tmax = 0, pmin = 0, pmax = 0, t_prev = 0, lp_prev = 0;
+    auto add_point = [&](double s) {
+        const double px = ox + s * dx, py = oy + s * dy, pz = oz + s * dz;
+        const double r = sqrt(px * px + py * py + pz * pz);
+        const double alt = r - a.A.radius;
+        int band = 0;
+        if (a.A.n_band > 1) {
+            const double lat = asin(pz / r) * (180.0 / M_PI);
+            int b = 0;   // searchsorted(edges, lat, 'right') - 1, clipped to [0, n_band-1]
+            while (b + 1 <= a.A.n_band && a.A.lat_edges[b + 1] <= lat) b++;
+            band = min(max(b, 0), a.A.n_band - 1);
+        }
+        const int j = interp_index(a.A.z, a.A.n_z, alt);
+        const double T = interp_at(a.A.z, a.A.temp + (size_t)band * a.A.n_z, a.A.n_z, j, alt);
+        const double lnP = interp_at(a.A.z, a.A.lnpres + (size_t)band * a.A.n_z, a.A.n_z, j, alt);
+        const double P = exp(lnP);
+        if (n == 0) s0 = s;
+        if (n < a.n_pts_max) {
+            a.T[o + n] = T;
+            a.P[o + n] = P;
+            a.nd[o + n] = P / (KB_HPA * T);
+            a.x[o + n] = (s0 - s) * 1.e5;     // path length from the far end, cm
+            a.alt[o + n] = alt;
+            a.band[o + n] = band;
+            a.jz[o + n] = j;
+        }
+        // merge rule of calc_radtran_steps: close the step at i-1 when the range over [i0, i]
+        // exceeds a limit and the step has at least two segments
+        const double lp = log(P);
+        const int i = n;
+        if (i == 0) { tmin = tmax = T; pmin = pmax = lp; }
+        else {
+            tmin = fmin(tmin, T); tmax = fmax(tmax, T);
+            pmin = fmin(pmin, lp); pmax = fmax(pmax, lp);
+            if ((tmax - tmin > a.max_dT || pmax - pmin > a.max_dlnP) && i - i0 >= 2) {
+                if (ns < a.n_steps_max) {
+                    a.bounds[((size_t)l * a.n_steps_max + ns) * 2] = i0;
+                    a.bounds[((size_t)l * a.n_steps_max + ns) * 2 + 1] = i - 1;
+                }
+                ns++;
+                i0 = i - 1;
+                tmin = fmin(t_prev, T); tmax = fmax(t_prev, T);
+                pmin = fmin(lp_prev, lp); pmax = fmax(lp_prev, lp);
+            }
+        }
+        t_prev = T;
+        lp_prev = lp;
+        n++;
+    };
+    add_point(s_far);
+    for (int k = kmax; k >= -kmax; k--) {
+        const double s = st + a.delta_x * (double)k;
+        if (s < s_far - 1e-6 && s > s_near + 1e-6) add_point(s);
+    }
+    add_point(s_near);
+    if (n >= 2) {
+        if (ns < a.n_steps_max) {
+            a.bounds[((size_t)l * a.n_steps_max + ns) * 2] = i0;
+            a.bounds[((size_t)l * a.n_steps_max + ns) * 2 + 1] = n - 1;
+        }
+        ns++;
+    }
+    a.n_pts[l] = n;
+    a.n_steps[l] = ns;
+}
+
+struct IntArgs {
+    AtmDev A;
+    int n_los, n_pts_max, n_steps_max;
+    const double *T, *P, *nd, *x, *alt;
+    const int *band, *jz, *n_steps, *bounds;
+    // outputs, sr_los_steps layout
+    double* temp;     // [n_los][n_steps_max]
+    double* pres;
+    double* column;   // [n_gas][n_los][n_steps_max]
+    double* tvib;     // [n_gas][n_sets_max][n_los][n_steps_max]
+    double* dfrac;    // [n_los][n_steps_max][n_par]
+};
+
+__global__ void k_steps_integrals(IntArgs a) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y;
+    if (k >= a.n_steps_max) return;
+    const AtmDev& A = a.A;
+    const size_t sk = (size_t)l * a.n_steps_max + k;
+    const size_t nls = (size_t)a.n_los * a.n_steps_max;
+    if (k >= min(a.n_steps[l], a.n_steps_max)) {   // padding, as LineOfSight.step_tables fills it
+        a.temp[sk] = 100.0;
+        a.pres[sk] = 1.e-6;
+        for (int m = 0; m < A.n_gas; m++) {
+            a.column[(size_t)m * nls + sk] = 0.0;
+            for (int s = 0; s < A.n_sets_max; s++)
+                a.tvib[((size_t)m * A.n_sets_max + s) * nls + sk] = 100.0;
+        }
+        for (int q = 0; q < A.n_par; q++) a.dfrac[sk * A.n_par + q] = 0.0;
+        return;
+    }
+    const int ia = a.bounds[sk * 2], ie = a.bounds[sk * 2 + 1];
+    const size_t o = (size_t)l * a.n_pts_max;
+    const double* __restrict__ nd = a.nd + o;
+    const double* __restrict__ x = a.x + o;
+    // air column (curgod_fort_1), Curtis-Godson T and P (curgod_fort_4 with vmr = 1)
+    double air = 0.0, ct = 0.0, cp = 0.0;
+    for (int i = ia; i < ie; i++) {
+        const double dx = x[i + 1] - x[i];
+        air += srdev::curgod_seg1(nd[i], nd[i + 1], dx);
+        ct += srdev::curgod_seg4(nd[i], nd[i + 1], 1.0, 1.0, a.T[o + i], a.T[o + i + 1], dx);
+        cp += srdev::curgod_seg4(nd[i], nd[i + 1], 1.0, 1.0, a.P[o + i], a.P[o + i + 1], dx);
+    }
+    const double t_cg = ct / air;
+    a.temp[sk] = t_cg;
+    a.pres[sk] = cp / air;
+    auto prof = [&](const double* __restrict__ table, int i) {   // profile value at sample point i
+        return interp_at(A.z, table + (size_t)a.band[o + i] * A.n_z, A.n_z, a.jz[o + i], a.alt[o + i]);
+    };
+    for (int m = 0; m < A.n_gas; m++) {
+        const double* vt = A.vmr + (size_t)m * A.n_band * A.n_z;
+        double col = 0.0;
+        double v0 = prof(vt, ia);
+        for (int i = ia; i < ie; i++) {
+            const double v1 = prof(vt, i + 1);
+            col += srdev::curgod_seg2(nd[i], nd[i + 1], v0, v1, x[i + 1] - x[i]);
+            v0 = v1;
+        }
+        a.column[(size_t)m * nls + sk] = col;
+        for (int s = 0; s < A.n_sets_max; s++) {
+            const int on = A.tvib_on[m * A.n_sets_max + s];
+            double tv = 100.0;
+            if (on == 0) tv = t_cg;
+            else if (on > 0) {
+                const double* tt = A.tvib + ((size_t)m * A.n_sets_max + s) * A.n_band * A.n_z;
+                double acc = 0.0, w0 = prof(vt, ia), f0 = prof(tt, ia);
+                for (int i = ia; i < ie; i++) {
+                    const double w1 = prof(vt, i + 1), f1 = prof(tt, i + 1);
+                    acc += srdev::curgod_seg3(nd[i], nd[i + 1], w0, w1, f0, f1, x[i + 1] - x[i]);
+                    w0 = w1;
+                    f0 = f1;
+                }
+                tv = acc / col;
+            }
+            a.tvib[((size_t)m * A.n_sets_max + s) * nls + sk] = tv;
+        }
+        if (m == A.jac_gas) {
+            for (int q = 0; q < A.n_par; q++) {
+                const double* mk = A.masks + (size_t)q * A.n_z;
+                double d = 0.0;
+                bool any = false;
+                double m0 = interp_at(A.z, mk, A.n_z, a.jz[o + ia], a.alt[o + ia]);
+                any = m0 != 0.0;
+                for (int i = ia; i < ie; i++) {
+                    const double m1 = interp_at(A.z, mk, A.n_z, a.jz[o + i + 1], a.alt[o + i + 1]);
+                    any = any || m1 != 0.0;
+                    d += srdev::curgod_seg2(nd[i], nd[i + 1], m0, m1, x[i + 1] - x[i]);
+                    m0 = m1;
+                }
+                a.dfrac[sk * A.n_par + q] = (any && col != 0.0) ? d / col : 0.0;
+            }
+        }
+    }
+    if (A.jac_gas < 0 || A.jac_gas >= A.n_gas)
+        for (int q = 0; q < A.n_par; q++) a.dfrac[sk * A.n_par + q] = 0.0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sr_los_steps_build(const sr_atmosphere* atm, int n_los, const double* origin,
+                       const double* direction, double delta_x_km, double max_T_variation,
+                       double max_Plog_variation, int n_par, const double* masks, int jac_gas,
+                       int n_steps_max, int* n_steps, double* temp, double* pres, double* column,
+                       double* tvib, double* dfrac, int* n_steps_needed) {
+    if (!atm || n_los < 1 || !origin || !direction || !(delta_x_km > 0.0) || n_steps_max < 1 ||
+        !n_steps || !temp || !pres || !column || atm->n_band < 1 || atm->n_z < 2 ||
+        atm->n_gas < 1 || atm->n_gas > MAX_GAS_ST || !atm->z || !atm->temp || !atm->pres ||
+        !atm->vmr || (atm->n_band > 1 && !atm->lat_edges) || n_par < 0 ||
+        (n_par > 0 && (!masks || !dfrac)) || (atm->n_sets_max > 0 && (!tvib || !atm->tvib_on)))
+        return sr::fail(SR_ERR_ARG, "sr_los_steps_build: bad argument");
+    const int nb = atm->n_band, nz = atm->n_z, ng = atm->n_gas, nsx = atm->n_sets_max;
+    for (int m = 0; m < ng * nsx; m++)
+        if (atm->tvib_on[m] > 0 && !atm->tvib)
+            return sr::fail(SR_ERR_ARG, "sr_los_steps_build: tvib_on set but no tvib table");
+    cudaStream_t st = 0;
+    std::vector<double> lnp((size_t)nb * nz);
+    for (size_t i = 0; i < lnp.size(); i++) lnp[i] = std::log(atm->pres[i]);
+    sr::DevBuf<double> d_edges, d_z, d_temp, d_lnp, d_vmr, d_tvib, d_masks, d_org, d_dir;
+    sr::DevBuf<int> d_on;
+    if (nb > 1) SR_CUDA(d_edges.upload(atm->lat_edges, nb + 1, st));
+    SR_CUDA(d_z.upload(atm->z, nz, st));
+    SR_CUDA(d_temp.upload(atm->temp, (size_t)nb * nz, st));
+    SR_CUDA(d_lnp.upload(lnp.data(), lnp.size(), st));
+    SR_CUDA(d_vmr.upload(atm->vmr, (size_t)ng * nb * nz, st));
+    if (atm->tvib) SR_CUDA(d_tvib.upload(atm->tvib, (size_t)ng * nsx * nb * nz, st));
+    if (nsx > 0) SR_CUDA(d_on.upload(atm->tvib_on, (size_t)ng * nsx, st));
+    if (n_par > 0) SR_CUDA(d_masks.upload(masks, (size_t)n_par * nz, st));
+    AtmDev A;
+    A.n_band = nb; A.n_z = nz; A.n_gas = ng; A.n_sets_max = nsx; A.n_par = n_par; A.jac_gas = jac_gas;
+    A.lat_edges = d_edges.p; A.z = d_z.p; A.temp = d_temp.p; A.lnpres = d_lnp.p; A.vmr = d_vmr.p;
+    A.tvib = d_tvib.p; A.tvib_on = d_on.p; A.masks = d_masks.p;
+    A.radius = atm->radius_km; A.top = atm->top_km;
+    const double r_top = atm->radius_km + atm->top_km;
+    const int n_pts_max = 2 * (int)std::floor(r_top / delta_x_km) + 3;
+    // LOS blocks bound the per-point scratch (48 B per point) to ~1 GiB
+    const int blk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_los, ((size_t)1 << 30) / ((size_t)n_pts_max * 48)));
+    sr::DevBuf<double> sT, sP, snd, sx, salt, o_temp, o_pres, o_col, o_tvib, o_dfrac;
+    sr::DevBuf<int> sband, sjz, d_npts, d_nsteps, d_bounds;
+    const size_t np = (size_t)blk * n_pts_max;
+    SR_CUDA(sT.alloc(np)); SR_CUDA(sP.alloc(np)); SR_CUDA(snd.alloc(np)); SR_CUDA(sx.alloc(np));
+    SR_CUDA(salt.alloc(np)); SR_CUDA(sband.alloc(np)); SR_CUDA(sjz.alloc(np));
+    SR_CUDA(d_npts.alloc(blk)); SR_CUDA(d_nsteps.alloc(blk));
+    SR_CUDA(d_bounds.alloc((size_t)blk * n_steps_max * 2));
+    const size_t bls = (size_t)blk * n_steps_max;
+    SR_CUDA(o_temp.alloc(bls)); SR_CUDA(o_pres.alloc(bls)); SR_CUDA(o_col.alloc(bls * ng));
+    SR_CUDA(o_tvib.alloc(std::max<size_t>(1, bls * ng * nsx)));
+    SR_CUDA(o_dfrac.alloc(std::max<size_t>(1, bls * n_par)));
+    int needed = 0;
+    std::vector<double> tmp;
+    for (int l0 = 0; l0 < n_los; l0 += blk) {
+        const int nl = std::min(blk, n_los - l0);
+        SR_CUDA(d_org.upload(origin + (size_t)3 * l0, (size_t)3 * nl, st));
+        SR_CUDA(d_dir.upload(direction + (size_t)3 * l0, (size_t)3 * nl, st));
+        PtArgs pa;
+        pa.A = A; pa.origin = d_org.p; pa.dir = d_dir.p;
+        pa.n_los = nl; pa.n_pts_max = n_pts_max; pa.n_steps_max = n_steps_max;
+        pa.delta_x = delta_x_km; pa.max_dT = max_T_variation; pa.max_dlnP = max_Plog_variation;
+        pa.T = sT.p; pa.P = sP.p; pa.nd = snd.p; pa.x = sx.p; pa.alt = salt.p;
+        pa.band = sband.p; pa.jz = sjz.p; pa.n_pts = d_npts.p; pa.n_steps = d_nsteps.p;
+        pa.bounds = d_bounds.p;
+        SR_LAUNCH(k_steps_points, (nl + 63) / 64, 64, 0, st, pa);
+        IntArgs ia;
+        ia.A = A; ia.n_los = nl; ia.n_pts_max = n_pts_max; ia.n_steps_max = n_steps_max;
+        ia.T = sT.p; ia.P = sP.p; ia.nd = snd.p; ia.x = sx.p; ia.alt = salt.p;
+        ia.band = sband.p; ia.jz = sjz.p; ia.n_steps = d_nsteps.p; ia.bounds = d_bounds.p;
+        ia.temp = o_temp.p; ia.pres = o_pres.p; ia.column = o_col.p; ia.tvib = o_tvib.p;
+        ia.dfrac = o_dfrac.p;
+        SR_LAUNCH(k_steps_integrals, dim3((n_steps_max + 63) / 64, nl), 64, 0, st, ia);
+        // copy the block into the caller's [..][n_los][n_steps_max] tables
+        SR_CUDA(cudaMemcpyAsync(n_steps + l0, d_nsteps.p, sizeof(int) * nl, cudaMemcpyDeviceToHost, st));
+        const size_t row = (size_t)nl * n_steps_max;
+        SR_CUDA(cudaMemcpyAsync(temp + (size_t)l0 * n_steps_max, o_temp.p, 8 * row, cudaMemcpyDeviceToHost, st));
+        SR_CUDA(cudaMemcpyAsync(pres + (size_t)l0 * n_steps_max, o_pres.p, 8 * row, cudaMemcpyDeviceToHost, st));
+        for (int m = 0; m < ng; m++) {
+            SR_CUDA(cudaMemcpyAsync(column + ((size_t)m * n_los + l0) * n_steps_max,
+                                    o_col.p + (size_t)m * row, 8 * row, cudaMemcpyDeviceToHost, st));
+            for (int s = 0; s < nsx; s++)
+                SR_CUDA(cudaMemcpyAsync(tvib + (((size_t)m * nsx + s) * n_los + l0) * n_steps_max,
+                                        o_tvib.p + ((size_t)m * nsx + s) * row, 8 * row,
+                                        cudaMemcpyDeviceToHost, st));
+        }
+        if (n_par > 0)
+            SR_CUDA(cudaMemcpyAsync(dfrac + (size_t)l0 * n_steps_max * n_par, o_dfrac.p,
+                                    8 * row * n_par, cudaMemcpyDeviceToHost, st));
+        SR_CUDA(cudaStreamSynchronize(st));
+        for (int l = l0; l < l0 + nl; l++) needed = std::max(needed, n_steps[l]);
+    }
+    if (n_steps_needed) *n_steps_needed = needed;
+    if (needed > n_steps_max)
+        return sr::fail(SR_ERR_LIMIT, "sr_los_steps_build: a line of sight needs %d steps (n_steps_max = %d)",
+                        needed, n_steps_max);
+    return SR_OK;
+}
+
+}  // extern "C"

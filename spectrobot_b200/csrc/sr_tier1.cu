@@ -137,34 +137,16 @@ __global__ void k_curgod(int kind, const double* __restrict__ nd, const double* 
     double res = 0.0;
     for (int i = 0; i < n_p - 1; i++) {
         const double dx = x[o + i + 1] - x[o + i];
-        if (kind == 1) {                                    // curgods.f:14-19
-            const double fu = nd[o + i + 1] / nd[o + i];
-            const double D = log(fu) / dx;
-            res = res + (nd[o + i + 1] - nd[o + i]) / D;
-        } else if (kind == 2) {                             // curgods.f:35-42
-            const double A = nd[o + i] * vmr[o + i];
-            const double B = nd[o + i] * (vmr[o + i + 1] - vmr[o + i]) / dx;
-            const double fu = nd[o + i + 1] / nd[o + i];
-            const double D = log(fu) / dx;
-            res = res + (A * D * (fu - 1.) + B * fu * (D * dx - 1.) + B) / (D * D);
-        } else if (kind == 3) {                             // curgods.f:58-70
-            const double A = nd[o + i] * vmr[o + i] * f[o + i];
-            const double cc = (vmr[o + i + 1] - vmr[o + i]) / dx;
-            const double bb = (f[o + i + 1] - f[o + i]) / dx;
-            const double B = nd[o + i] * (vmr[o + i] * bb + f[o + i] * cc);
-            const double Cc = nd[o + i] * bb * cc;
-            const double fu = nd[o + i + 1] / nd[o + i];
-            const double D = log(fu) / dx;
-            res = res + (fu * (D * (A * D + B * (D * dx - 1.)) + Cc * (D * dx * (D * dx - 2.) + 2.)) +
-                         D * (B - A * D) - 2 * Cc) / (D * D * D);
-        } else {                                            // curgods.f:86-94
-            const double A = nd[o + i] * vmr[o + i] * f[o + i];
-            const double cc = (vmr[o + i + 1] - vmr[o + i]) / dx;
-            const double B = nd[o + i] * f[o + i] * cc;
-            const double fu = nd[o + i + 1] * f[o + i + 1] / (nd[o + i] * f[o + i]);
-            const double D = log(fu) / dx;
-            res = res + (A * D * (fu - 1.) + B * fu * (D * dx - 1.) + B) / (D * D);
-        }
+        if (kind == 1)
+            res = res + srdev::curgod_seg1(nd[o + i], nd[o + i + 1], dx);
+        else if (kind == 2)
+            res = res + srdev::curgod_seg2(nd[o + i], nd[o + i + 1], vmr[o + i], vmr[o + i + 1], dx);
+        else if (kind == 3)
+            res = res + srdev::curgod_seg3(nd[o + i], nd[o + i + 1], vmr[o + i], vmr[o + i + 1],
+                                           f[o + i], f[o + i + 1], dx);
+        else
+            res = res + srdev::curgod_seg4(nd[o + i], nd[o + i + 1], vmr[o + i], vmr[o + i + 1],
+                                           f[o + i], f[o + i + 1], dx);
     }
     res_out[b] = res;
 }

@@ -484,6 +484,85 @@ def los_rt_layers_jac(tau, emi, dfrac, n_steps, tau_g=None, emi_g=None, i0=None,
     return rad, jac
 
 
+class Atmosphere(object):
+    """Atmosphere tables for the device step builder (sr_atmosphere in spectrobot.h).
+
+    z [n_z] km; temp, pres [n_band, n_z] (or [n_z]); vmr [n_gas, n_band, n_z], one entry per LUT of
+    the later LOS call; tvib [n_gas, n_sets_max, n_band, n_z] or None; tvib_on [n_gas, n_sets_max]
+    (1 own profile, 0 T_vib = step temperature, -1 no such level); lat_edges [n_band+1] degrees."""
+
+    def __init__(self, z, temp, pres, vmr, tvib=None, tvib_on=None, lat_edges=None,
+                 radius_km=2575.0, top_km=1500.0):
+        self.z = as_f64(z)
+        nz = len(self.z)
+        self.temp = as_f64(np.asarray(temp, dtype=float).reshape(-1, nz))
+        self.pres = as_f64(np.asarray(pres, dtype=float).reshape(-1, nz))
+        self.n_band = self.temp.shape[0]
+        vmr = np.asarray(vmr, dtype=float)
+        self.vmr = as_f64(vmr.reshape(-1, self.n_band, nz))
+        self.n_gas = self.vmr.shape[0]
+        self.tvib = None
+        self.n_sets_max = 0
+        self.tvib_on = None
+        if tvib_on is not None:
+            self.tvib_on = as_i32(np.asarray(tvib_on).reshape(self.n_gas, -1))
+            self.n_sets_max = self.tvib_on.shape[1]
+        if tvib is not None:
+            self.tvib = as_f64(np.asarray(tvib, dtype=float).reshape(self.n_gas, -1, self.n_band, nz))
+            if self.tvib_on is None:
+                self.n_sets_max = self.tvib.shape[1]
+                self.tvib_on = as_i32(np.ones((self.n_gas, self.n_sets_max)))
+            assert self.tvib.shape[1] == self.n_sets_max
+        self.lat_edges = None if lat_edges is None or self.n_band == 1 else as_f64(lat_edges)
+        assert self.n_band == 1 or len(self.lat_edges) == self.n_band + 1
+        assert self.pres.shape == self.temp.shape
+        self.radius_km, self.top_km = float(radius_km), float(top_km)
+
+    def struct(self):
+        st = _lib.sr_atmosphere()
+        st.n_band, st.n_z, st.n_gas, st.n_sets_max = self.n_band, len(self.z), self.n_gas, self.n_sets_max
+        st.lat_edges = None if self.lat_edges is None else dptr(self.lat_edges)
+        st.z, st.temp, st.pres, st.vmr = dptr(self.z), dptr(self.temp), dptr(self.pres), dptr(self.vmr)
+        st.tvib = None if self.tvib is None else dptr(self.tvib)
+        st.tvib_on = None if self.tvib_on is None else iptr(self.tvib_on)
+        st.radius_km, st.top_km = self.radius_km, self.top_km
+        return st
+
+
+def los_steps_build(atm, origins, directions, delta_x=5.0, max_T_variation=5.0,
+                    max_Plog_variation=1.0, masks=None, jac_gas=-1, n_steps_max=64):
+    """LOS geometry + radtran steps of a whole batch on the device (sr_los_steps_build): rays from
+    origins [n_los, 3] (km, planetocentric Cartesian) along unit directions [n_los, 3].  Returns
+    (LosSteps, dfrac) - dfrac [n_los, n_steps_max, n_par] for the parameter masks [n_par, n_z] of gas
+    entry jac_gas, or None.  The table width grows until every LOS fits."""
+    org, dr = as_f64(origins).reshape(-1, 3), as_f64(directions).reshape(-1, 3)
+    n_los = org.shape[0]
+    assert dr.shape == org.shape
+    mk = None if masks is None else as_f64(np.asarray(masks, dtype=float).reshape(-1, len(atm.z)))
+    n_par = 0 if mk is None else mk.shape[0]
+    st = atm.struct()
+    while True:
+        n_steps = np.zeros(n_los, dtype=np.int32)
+        temp = np.empty((n_los, n_steps_max))
+        pres = np.empty((n_los, n_steps_max))
+        col = np.empty((atm.n_gas, n_los, n_steps_max))
+        tvib = np.empty((atm.n_gas, atm.n_sets_max, n_los, n_steps_max)) if atm.n_sets_max else None
+        dfrac = np.empty((n_los, n_steps_max, n_par)) if n_par else None
+        need = C.c_int(0)
+        rc = lib().sr_los_steps_build(C.byref(st), n_los, dptr(org), dptr(dr), float(delta_x),
+                                      float(max_T_variation), float(max_Plog_variation), n_par,
+                                      None if mk is None else dptr(mk), int(jac_gas),
+                                      int(n_steps_max), iptr(n_steps), dptr(temp), dptr(pres),
+                                      dptr(col), None if tvib is None else dptr(tvib),
+                                      None if dfrac is None else dptr(dfrac), C.byref(need))
+        if rc == _lib.SR_ERR_LIMIT and need.value > n_steps_max:
+            n_steps_max = need.value
+            continue
+        check(rc)
+        break
+    return LosSteps(n_steps, temp, pres, col, tvib), dfrac
+
+
 def partition_sum(mol, iso, temp=296.0):
     """CalcPartitionSum (spect_classes.py:1692-1710) from the library's TIPS tables."""
     q = C.c_double()

@@ -678,8 +678,80 @@ def los_step_tables(loss, planet):
     return gi, engine.LosSteps(n_steps, temp, pres, col, tvib)
 
 
+def planet_atmosphere_tables(planet, gas_isos):
+    """engine.Atmosphere (the tables of sr_atmosphere) from an sbm planet: T (linear), P
+    (log-linear), one VMR profile per (gas, iso) entry and the vibrational-temperature profiles of
+    the levels, all on the atmosphere's altitude grid."""
+    atm = planet.atmosphere
+    z = atm.grid.coords['alt']
+    two_d = atm.grid.n_dim > 1
+    n_band = len(atm.grid.coords['lat']) - 1 if two_d else 1
+
+    def table(prof, name):
+        if not np.array_equal(prof.grid.coords['alt'], z):
+            raise ValueError('profile %s is not on the atmosphere altitude grid' % name)
+        v = np.asarray(prof.values[name], dtype=float)
+        if v.ndim == 1:
+            v = np.broadcast_to(v, (n_band, len(z)))
+        elif v.shape[0] != n_band:
+            raise ValueError('profile %s has %d latitude bands, atmosphere has %d'
+                             % (name, v.shape[0], n_band))
+        return v
+
+    n_lev = max([len(getattr(planet.gases[g], iso).levels) for g, iso in gas_isos] + [0])
+    vmr = np.stack([table(planet.gases[g].abundance, 'vmr') for g, iso in gas_isos])
+    tvib_on = -np.ones((len(gas_isos), n_lev), dtype=np.int32)
+    tvib = np.full((len(gas_isos), n_lev, n_band, len(z)), 100.0)
+    for m, (g, iso) in enumerate(gas_isos):
+        im = getattr(planet.gases[g], iso)
+        for j, lev in enumerate(im.levels):
+            L = getattr(im, lev)
+            if L.vibtemp is None:
+                tvib_on[m, j] = 0
+            else:
+                tvib_on[m, j] = 1
+                tvib[m, j] = table(L.vibtemp, 'vibtemp')
+    return engine.Atmosphere(z, table(atm, 'temp'), table(atm, 'pres'), vmr,
+                             tvib=tvib if n_lev else None, tvib_on=tvib_on if n_lev else None,
+                             lat_edges=atm.grid.coords['lat'] if two_d else None,
+                             radius_km=planet.radius, top_km=planet.atm_extension)
+
+
+def los_step_tables_device(loss, planet, bayes_set=None, set_name=None, delta_x=5.0,
+                           max_T_variation=5.0, max_Plog_variation=1.0, max_opt_depth=None):
+    """calc_atm_intersections + calc_radtran_steps for a whole list of sbm.LineOfSight in ONE
+    library call (sr_los_steps_build).  Returns (gas_isos, engine.LosSteps,
+    dfrac): dfrac [n_los][n_steps_max][n_par] for the parameters of bayes_set.sets[set_name] (a
+    VMR set named like a gas of the planet), else None.  Also fills los.involved_retparams."""
+    gi = [(g, iso) for g in sorted(planet.gases) for iso in planet.gases[g].all_iso]
+    atm = planet_atmosphere_tables(planet, gi)
+    org = np.array([l.starting_point.Cartesian() for l in loss])
+    drc = np.array([l.direction for l in loss])
+    masks, jac_gas, pars = None, -1, []
+    if bayes_set is not None and set_name is not None and set_name in planet.gases:
+        pars = bayes_set.sets[set_name].set
+        z = atm.z
+        masks = np.array([np.interp(z, p.maskgrid.grid.coords['alt'], p.maskgrid.mask) for p in pars])
+        for p in pars:
+            if p.maskgrid.interp['mask'] != 'lin' or not np.array_equal(p.maskgrid.grid.coords['alt'], z):
+                raise ValueError('device step builder: parameter masks must be linear on the '
+                                 'atmosphere altitude grid')
+        jac_gas = [g for g, iso in gi].index(set_name)
+    steps, dfrac = engine.los_steps_build(atm, org, drc, delta_x=delta_x,
+                                          max_T_variation=max_T_variation,
+                                          max_Plog_variation=max_Plog_variation, masks=masks,
+                                          jac_gas=jac_gas)
+    if bayes_set is not None:
+        for l, los in enumerate(loss):
+            for par in bayes_set.params():
+                los.involved_retparams.setdefault((par.nameset, par.key), False)
+            for q, par in enumerate(pars):
+                los.involved_retparams[(par.nameset, par.key)] = bool(np.any(dfrac[l, :, q] != 0.0))
+    return gi, steps, dfrac
+
+
 def los_batch_radiances(loss, sp_grid, planet, LUTS, solo_absorption=False,
-                        initial_intensity=None, lowres=None, pt0=0, n_pts=None):
+                        initial_intensity=None, lowres=None, pt0=0, n_pts=None, tables=None):
     """Radiances of a batch of lines of sight in ONE launch sequence.
 
     loss: sbm.LineOfSight objects with radtran_steps; LUTS: {(mol_name, iso): LookUpTable}.
@@ -687,7 +759,7 @@ def los_batch_radiances(loss, sp_grid, planet, LUTS, solo_absorption=False,
     lowres = (channel centres, channel widths) in the units of sp_grid, the CUDA tensor
     [n_los][n_chan] convolved on the device (hires_to_lowres)."""
     import torch
-    gi, steps = los_step_tables(loss, planet)
+    gi, steps = los_step_tables(loss, planet) if tables is None else tables[:2]
     luts, keep = [], []
     for m, (g, iso) in enumerate(gi):
         im = getattr(planet.gases[g], iso)
@@ -699,7 +771,7 @@ def los_batch_radiances(loss, sp_grid, planet, LUTS, solo_absorption=False,
         raise ValueError('no LUT for any gas of the planet in this spectral range')
     if len(keep) != len(gi):
         steps = engine.LosSteps(steps.n_steps, steps.temp, steps.pres, steps.column[keep],
-                                steps.tvib[keep])
+                                None if steps.tvib is None else steps.tvib[keep])
     grid = sp_grid.grid if hasattr(sp_grid, 'grid') else np.asarray(sp_grid)
     n_pts = len(grid) - pt0 if n_pts is None else n_pts
     i0 = None
@@ -735,7 +807,7 @@ def los_jac_tables(loss, bayes_set, set_name, n_steps_max):
 
 
 def los_batch_jacobians(loss, sp_grid, planet, LUTS, bayes_set, solo_absorption=False,
-                        initial_intensity=None, lowres=None, pt0=0, n_pts=None):
+                        initial_intensity=None, lowres=None, pt0=0, n_pts=None, tables=None):
     """Radiances AND their derivatives with respect to every parameter of bayes_set for a batch of
     lines of sight (the `calc_derivatives=True` path of radtran_fast, smm:2837-2881), one fused
     library call per retrieved gas.  Parameter sets whose name is not a gas of the planet get zero
@@ -743,7 +815,12 @@ def los_batch_jacobians(loss, sp_grid, planet, LUTS, bayes_set, solo_absorption=
     SpectralIntensity (order of bayes_set.params()); with lowres = (centres, widths) the CUDA
     tensors low [n_los][n_chan], jac_low [n_los][n_tot][n_chan]."""
     import torch
-    gi, steps = los_step_tables(loss, planet)
+    # tables: {set name: (gas_isos, LosSteps, dfrac)} from los_step_tables_device, else the step
+    # dictionaries that calc_radtran_steps(calc_derivatives=True) left on every LOS are used
+    if tables is None:
+        gi, steps = los_step_tables(loss, planet)
+    else:
+        gi, steps = list(tables.values())[0][:2]
     luts, keep = [], []
     for m, (g, iso) in enumerate(gi):
         im = getattr(planet.gases[g], iso)
@@ -755,7 +832,7 @@ def los_batch_jacobians(loss, sp_grid, planet, LUTS, bayes_set, solo_absorption=
         raise ValueError('no LUT for any gas of the planet in this spectral range')
     if len(keep) != len(gi):
         steps = engine.LosSteps(steps.n_steps, steps.temp, steps.pres, steps.column[keep],
-                                steps.tvib[keep])
+                                None if steps.tvib is None else steps.tvib[keep])
     grid = sp_grid.grid if hasattr(sp_grid, 'grid') else np.asarray(sp_grid)
     n_pts = len(grid) - pt0 if n_pts is None else n_pts
     i0 = None
@@ -773,7 +850,8 @@ def los_batch_jacobians(loss, sp_grid, planet, LUTS, bayes_set, solo_absorption=
         if nam not in planet.gases or not any(in_jac):
             blocks.append(torch.zeros((len(loss), n_par, n_out), dtype=torch.float64, device="cuda"))
             continue
-        dfrac = los_jac_tables(loss, bayes_set, nam, steps.n_steps_max)
+        dfrac = (los_jac_tables(loss, bayes_set, nam, steps.n_steps_max) if tables is None
+                 else tables[nam][2])
         if lowres is None:
             rad, jac = engine.los_rt_lut_jac(luts, steps, dfrac, gas_in_jac=in_jac, pt0=pt0,
                                              n_pts=n_pts, i0=i0, solo_absorption=solo_absorption)
@@ -866,17 +944,16 @@ def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_
         sim_LOSs += [pix.low_LOS(), pix.LOS(), pix.up_LOS()]
     for num, los in enumerate(sim_LOSs):
         los.tag = 'LOS{:03d}'.format(num)
-        los.calc_atm_intersections(planet)
-        pix = pixels[num // 3]
-        if hasattr(pix, 'sub_solar_point'):
-            los.calc_SZA_along_los(planet, pix.sub_solar_point())
-        los.calc_radtran_steps(planet, lines, **radtran_opt)
+    # geometry + radtran steps of ALL lines of sight in one library call (sr_los_steps_build); the
+    # per-LOS host methods calc_atm_intersections / calc_radtran_steps stay available on sbm
+    tables = los_step_tables_device(sim_LOSs, planet, **radtran_opt)
 
     obs = pixels[0].observation
     centres, widths = obs.spectral_grid.grid, obs.bands.spectrum
     # one call for the whole batch and range: the library cuts it into LOS blocks x wavenumber
     # chunks itself (the reference's n_split loop, smm:3190, was a host-memory workaround)
-    low = los_batch_radiances(sim_LOSs, sp_gri, planet, LUTS, lowres=(centres, widths))
+    low = los_batch_radiances(sim_LOSs, sp_gri, planet, LUTS, lowres=(centres, widths),
+                              tables=tables)
     low = low.cpu().numpy()
     radtrans_out = dict()
     for i, los in enumerate(sim_LOSs):
@@ -927,17 +1004,20 @@ def inversion_fast_limb(inputs, planet, lines, bayes_set, pixels, wn_range=None,
         sim_LOSs += [pix.low_LOS(), pix.LOS(), pix.up_LOS()]
     for num, los in enumerate(sim_LOSs):
         los.tag = 'LOS{:02d}'.format(num)
-        los.calc_atm_intersections(planet)
-        pix = pixels[num // 3]
-        if hasattr(pix, 'sub_solar_point'):
-            los.calc_SZA_along_los(planet, pix.sub_solar_point())
-        los.calc_radtran_steps(planet, lines, calc_derivatives=True, bayes_set=bayes_set,
-                               **radtran_opt)
+    # geometry, radtran steps and derivative columns of all LOS on the device, one call per
+    # retrieved gas (the step tables themselves are identical between the calls)
+    tables = dict()
+    for nam in bayes_set.order:
+        if nam in planet.gases:
+            tables[nam] = los_step_tables_device(sim_LOSs, planet, bayes_set=bayes_set,
+                                                 set_name=nam, **radtran_opt)
+    if not tables:
+        tables[None] = los_step_tables_device(sim_LOSs, planet, bayes_set=bayes_set, **radtran_opt)
 
     obs = pixels[0].observation
     centres, widths = obs.spectral_grid.grid, obs.bands.spectrum
     low, jlow = los_batch_jacobians(sim_LOSs, sp_gri, planet, LUTS, bayes_set,
-                                    lowres=(centres, widths))
+                                    lowres=(centres, widths), tables=tables)
     low, jlow = low.cpu().numpy(), jlow.cpu().numpy()
     radtrans_out, derivs = dict(), dict()
     pars = bayes_set.params()

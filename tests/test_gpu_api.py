@@ -229,3 +229,52 @@ def test_inversion_fast_limb_forward_and_jacobian(world):
     one = los.radtran_fast(sp, planet, LUTS=LUTS, calc_derivatives=True, bayes_set=bs)
     assert len(one[2].params()) == bs.n_tot
     assert one[2].params()[2].hires_deriv.spectrum.shape == one[0].spectrum.shape
+
+
+def test_device_step_builder_matches_host_builder(world):
+    """sr_los_steps_build (geometry + adaptive merge + Curtis-Godson integrals for a whole batch,
+    SURVEY 8f row 4) against sbm.LineOfSight.calc_atm_intersections / calc_radtran_steps run per
+    LOS: same step counts, tables equal to rounding, incl. a 7-band atmosphere, non-LTE
+    vibrational temperatures, a ray that hits the surface, one that misses the atmosphere, and the
+    derivative-column table of a VMR parameter set."""
+    smm, S, sbm = world["smm"], world["S"], world["sbm"]
+    planet = S.titan_planet(world["tab"]["level_energies"], n_bands=7)
+    bs = _bayes(smm, planet)
+    planet.gases['CH4'].add_clim(bs.sets['CH4'].profile())
+    obs = sbm.Coords([5.0, 90.0, 1.0e5], s_ref='Spherical')
+    loss = []
+    for alt, lat in ((-300.0, 12.0), (150.0, -50.0), (420.0, 70.0), (777.7, 28.0), (1200.0, -80.0),
+                     (1499.0, 0.0), (1600.0, 10.0)):
+        loss.append(sbm.LineOfSight(obs, sbm.Coords([lat, 3.0, alt], s_ref='Spherical')))
+    opt = dict(max_T_variation=4.0, max_Plog_variation=0.8)
+    gi, steps, dfrac = smm.los_step_tables_device(loss, planet, bayes_set=bs, set_name='CH4', **opt)
+    assert steps.n_steps[-1] == 0 and steps.n_steps[0] > 0
+    host = []
+    for los in loss[:-1]:
+        los2 = sbm.LineOfSight(los.starting_point, los.second_point)
+        los2.calc_atm_intersections(planet)
+        los2.calc_radtran_steps(planet, None, calc_derivatives=True, bayes_set=bs, **opt)
+        host.append(los2)
+    gi_h, steps_h = smm.los_step_tables(host, planet)
+    assert gi_h == gi
+    nmax = steps_h.n_steps_max
+    assert np.array_equal(steps.n_steps[:-1], steps_h.n_steps) and steps.n_steps_max >= nmax
+    tol = dict(rtol=1e-10, atol=0)
+    assert np.allclose(steps.temp[:-1, :nmax], steps_h.temp, **tol)
+    assert np.allclose(steps.pres[:-1, :nmax], steps_h.pres, **tol)
+    assert np.allclose(steps.column[:, :-1, :nmax], steps_h.column, **tol)
+    assert np.allclose(steps.tvib[:, :, :-1, :nmax], steps_h.tvib, **tol)
+    dfrac_h = smm.los_jac_tables(host, bs, 'CH4', nmax)
+    assert np.allclose(dfrac[:-1, :nmax], dfrac_h, rtol=1e-9, atol=1e-14)
+    assert np.all(dfrac[-1] == 0.0)
+    for l, los in enumerate(host):
+        for par in bs.params():
+            assert loss[l].involved_retparams[(par.nameset, par.key)] == \
+                los.involved_retparams[(par.nameset, par.key)]
+    # a narrow table is widened by the wrapper (SR_ERR_LIMIT -> retry)
+    atm = smm.planet_atmosphere_tables(planet, gi)
+    org = np.array([l.starting_point.Cartesian() for l in loss])
+    drc = np.array([l.direction for l in loss])
+    st2, _ = world["engine"].los_steps_build(atm, org, drc, n_steps_max=2, **opt)
+    assert np.array_equal(st2.n_steps, steps.n_steps)
+    assert np.array_equal(st2.temp[:, :nmax], steps.temp[:, :nmax])
