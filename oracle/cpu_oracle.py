@@ -532,3 +532,94 @@ def FOV_integr_1D(spectra, grid, pixel_rot=0.0):
         return intens_spl(x, ww)[0, 0] * esse * abs(dmax - abs(x)) / (dmax - delta)
 
     return np.array([integrate.quad(integrand, -dmax, dmax, args=(ww,))[0] for ww in grid])
+
+
+def los_steps_build(z, temp, pres, vmr, origins, directions, tvib=None, tvib_on=None,
+                    lat_edges=None, radius=2575.0, top=1500.0, delta_x=5.0, max_T_variation=5.0,
+                    max_Plog_variation=1.0, masks=None, jac_gas=-1):
+    """CPU restatement of the LOS geometry + radtran-step specification with
+    the oracle's own Curtis-Godson integrals (orc_curgod_1..4, curgods.f:2-98).  Array conventions
+    as sr_atmosphere / sr_los_steps_build in include/spectrobot.h.  Returns per LOS a dict with
+    n_steps, temp[], pres[], column[n_gas][], tvib[n_gas][n_sets][], dfrac[][n_par].  Plain
+    Python loops: small cases only."""
+    kb_hpa = 1.38065e-19
+    z = np.asarray(z, dtype=float)
+    temp = np.asarray(temp, dtype=float).reshape(-1, len(z))
+    pres = np.asarray(pres, dtype=float).reshape(-1, len(z))
+    n_band = temp.shape[0]
+    vmr = np.asarray(vmr, dtype=float).reshape(-1, n_band, len(z))
+    n_gas = vmr.shape[0]
+    n_sets = 0 if tvib_on is None else np.asarray(tvib_on).reshape(n_gas, -1).shape[1]
+    if n_sets:
+        tvib_on = np.asarray(tvib_on).reshape(n_gas, n_sets)
+        tvib = None if tvib is None else np.asarray(tvib, dtype=float).reshape(n_gas, n_sets, n_band, len(z))
+    masks = None if masks is None else np.asarray(masks, dtype=float).reshape(-1, len(z))
+    out = []
+    for o, d in zip(np.asarray(origins, dtype=float).reshape(-1, 3),
+                    np.asarray(directions, dtype=float).reshape(-1, 3)):
+        st = -float(np.dot(o, d))
+        rt = float(np.linalg.norm(o + st * d))
+        r_top = radius + top
+        res = dict(n_steps=0, temp=[], pres=[], column=[[] for _ in range(n_gas)],
+                   tvib=[[[] for _ in range(n_sets)] for _ in range(n_gas)], dfrac=[])
+        out.append(res)
+        if rt >= r_top:
+            continue
+        half = mt.sqrt(r_top ** 2 - rt ** 2)
+        s_near, s_far = st - half, st + half
+        if rt < radius:
+            s_far = st - mt.sqrt(radius ** 2 - rt ** 2)
+        kmax = int(mt.floor(half / delta_x - 1e-9))
+        inner = st + delta_x * np.arange(kmax, -kmax - 1, -1)
+        inner = inner[(inner < s_far - 1e-6) & (inner > s_near + 1e-6)]
+        s = np.concatenate([[s_far], inner, [s_near]])
+        pts = o[None, :] + s[:, None] * d[None, :]
+        r = np.sqrt((pts ** 2).sum(axis=1))
+        alt = r - radius
+        band = np.zeros(len(s), dtype=int)
+        if n_band > 1:
+            lat = np.degrees(np.arcsin(pts[:, 2] / r))
+            band = np.clip(np.searchsorted(lat_edges, lat, side='right') - 1, 0, n_band - 1)
+        at = lambda tab: np.array([np.interp(a, z, tab[b]) for a, b in zip(alt, band)])  # noqa: E731
+        T = at(temp)
+        P = np.exp(at(np.log(pres)))
+        nd = P / (kb_hpa * T)
+        x = (s[0] - s) * 1.e5
+        lnP = np.log(P)
+        n = len(s)
+        bounds, i0 = [], 0
+        for i in range(1, n):
+            sl = slice(i0, i + 1)
+            if (T[sl].max() - T[sl].min() > max_T_variation or
+                    lnP[sl].max() - lnP[sl].min() > max_Plog_variation) and i - i0 >= 2:
+                bounds.append((i0, i - 1))
+                i0 = i - 1
+        if n >= 2:
+            bounds.append((i0, n - 1))
+        res["n_steps"] = len(bounds)
+        vm = [at(vmr[m]) for m in range(n_gas)]
+        for a, e in bounds:
+            sl = slice(a, e + 1)
+            ones = np.ones(e - a + 1)
+            air = curgod(1, nd[sl], x[sl])
+            t_cg = curgod(4, nd[sl], ones, T[sl], x[sl]) / air
+            res["temp"].append(t_cg)
+            res["pres"].append(curgod(4, nd[sl], ones, P[sl], x[sl]) / air)
+            for m in range(n_gas):
+                col = curgod(2, nd[sl], vm[m][sl], x[sl])
+                res["column"][m].append(col)
+                for j in range(n_sets):
+                    if tvib_on[m, j] > 0:
+                        tv = curgod(3, nd[sl], vm[m][sl], at(tvib[m, j])[sl], x[sl]) / col
+                    else:
+                        tv = t_cg if tvib_on[m, j] == 0 else 100.0
+                    res["tvib"][m][j].append(tv)
+            if masks is not None:
+                row = []
+                col = res["column"][jac_gas][-1] if 0 <= jac_gas < n_gas else 0.0
+                for q in range(len(masks)):
+                    mk = np.interp(alt[sl], z, masks[q])
+                    dcol = curgod(2, nd[sl], mk, x[sl]) if np.any(mk != 0.0) else 0.0
+                    row.append(dcol / col if col != 0.0 else 0.0)
+                res["dfrac"].append(row)
+    return out

@@ -278,3 +278,55 @@ def test_device_step_builder_matches_host_builder(world):
     st2, _ = world["engine"].los_steps_build(atm, org, drc, n_steps_max=2, **opt)
     assert np.array_equal(st2.n_steps, steps.n_steps)
     assert np.array_equal(st2.temp[:, :nmax], steps.temp[:, :nmax])
+
+
+def test_device_step_builder_matches_oracle(world, oracle):
+    """sr_los_steps_build against the CPU restatement (oracle.los_steps_build: NumPy geometry and
+    merge, the oracle's own C curgod integrals)."""
+    eng, S = world["engine"], world["S"]
+    atm = S.titan_atmosphere()
+    z, nb = atm["z"], len(atm["temp"])
+    energies = world["tab"]["level_energies"]
+    rng = np.random.default_rng(5)
+    vmr = np.stack([np.full((nb, len(z)), 0.015) * (1 + 0.2 * np.sin(z / 150.0)),
+                    np.full((nb, len(z)), 2e-6) * np.exp(-z / 900.0)])
+    tvib = np.stack([np.stack([np.stack(S.vib_temperatures(z, atm["temp"][b], energies, 40.0 + 5 * b))
+                               for b in range(nb)], axis=1)] * 2)           # [gas][set][band][z]
+    tvib_on = np.ones((2, len(energies)), dtype=np.int32)
+    tvib_on[1, 2:] = -1
+    tvib_on[1, 1] = 0
+    masks = np.stack([np.clip(1 - np.abs(z - c) / 200.0, 0, 1) for c in (300., 500., 700.)])
+    n_los = 9
+    th = rng.uniform(-1.2, 1.2, n_los)
+    org = 1.0e5 * np.stack([np.cos(th), np.zeros(n_los), np.sin(th)], axis=1)
+    tgt_alt = np.array([-500., 80., 350., 500., 650., 800., 1000., 1400., 1700.])
+    drc = []
+    for l in range(n_los):     # aim at a point at the wanted tangent altitude, off the origin's meridian
+        t = np.array([-np.sin(th[l]), 0.3, np.cos(th[l])])
+        t /= np.linalg.norm(t)
+        tg = (2575.0 + tgt_alt[l]) * t
+        d = tg - org[l]
+        drc.append(d / np.linalg.norm(d))
+    drc = np.array(drc)
+    A = eng.Atmosphere(z, atm["temp"], atm["pres"], vmr, tvib=tvib, tvib_on=tvib_on,
+                       lat_edges=atm["lat_edges"])
+    opt = dict(delta_x=7.5, max_T_variation=3.0, max_Plog_variation=0.7)
+    steps, dfrac = eng.los_steps_build(A, org, drc, masks=masks, jac_gas=0, **opt)
+    ref = oracle.los_steps_build(z, atm["temp"], atm["pres"], vmr, org, drc, tvib=tvib,
+                                 tvib_on=tvib_on, lat_edges=atm["lat_edges"], masks=masks,
+                                 jac_gas=0, **opt)
+    assert steps.n_steps.max() > 20 and steps.n_steps.min() == 0
+    for l, r in enumerate(ref):
+        n = r["n_steps"]
+        assert steps.n_steps[l] == n, l
+        if n == 0:
+            continue
+        tol = dict(rtol=1e-10, atol=0)
+        assert np.allclose(steps.temp[l, :n], r["temp"], **tol)
+        assert np.allclose(steps.pres[l, :n], r["pres"], **tol)
+        for m in range(2):
+            assert np.allclose(steps.column[m, l, :n], r["column"][m], **tol)
+            for j in range(len(energies)):
+                assert np.allclose(steps.tvib[m, j, l, :n], r["tvib"][m][j], **tol), (l, m, j)
+        assert np.allclose(dfrac[l, :n], np.array(r["dfrac"]), rtol=1e-9, atol=1e-14)
+        assert np.all(steps.column[:, l, n:] == 0.0) and np.all(steps.temp[l, n:] == 100.0)

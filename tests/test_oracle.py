@@ -217,3 +217,35 @@ def test_los_oracle_limits(oracle, S):
     assert thin.any()
     lin = (tau[1, :2] * src[1, :2]).sum(axis=0)
     assert rel_err(rad[1][thin], lin[thin], floor_rel=1e-12) < 1e-5          # thin: I = sum J
+
+
+def test_oracle_step_builder_identities(oracle):
+    """The oracle's LOS step builder pinned by what must hold for any correct one:
+    a horizontal ray is symmetric about its tangent point; the step columns add up to the column of
+    the whole path (additivity of the Curtis-Godson integrals, curgods.f); Curtis-Godson T and P
+    lie inside the range of the step; for a constant VMR the gas column is vmr x air column."""
+    from spectrobot_b200 import synthetic as S
+    atm = S.titan_atmosphere(n_bands=1)
+    z = atm["z"]
+    vmr = np.full((1, 1, len(z)), 0.015)
+    org = np.array([[1.0e5, 0.0, 0.0]])
+    tg = np.array([0.0, 0.0, 2575.0 + 600.0])
+    d = (tg - org[0]) / np.linalg.norm(tg - org[0])
+    fine = oracle.los_steps_build(z, atm["temp"], atm["pres"], vmr, org, [d], max_T_variation=2.0,
+                                  max_Plog_variation=0.3)[0]
+    one = oracle.los_steps_build(z, atm["temp"], atm["pres"], vmr, org, [d], max_T_variation=1e9,
+                                 max_Plog_variation=1e9)[0]
+    assert one["n_steps"] == 1 and fine["n_steps"] > 10
+    col = np.array(fine["column"][0])
+    assert abs(col.sum() - one["column"][0][0]) < 1e-10 * col.sum()
+    assert np.allclose(col, col[::-1], rtol=1e-6)                    # symmetric about the tangent point
+    assert np.allclose(fine["temp"], fine["temp"][::-1], rtol=1e-8)
+    assert min(atm["temp"][0]) <= min(fine["temp"]) and max(fine["temp"]) <= max(atm["temp"][0])
+    assert np.all(np.diff(fine["pres"][:fine["n_steps"] // 2]) > 0)  # inbound half: P rises
+    # tangent altitude above the top: no step; below the surface: the ray stops at the ground
+    miss = oracle.los_steps_build(z, atm["temp"], atm["pres"], vmr, org,
+                                  [(np.array([0, 0, 2575.0 + 1600.0]) - org[0]) / 1.0e5])[0]
+    assert miss["n_steps"] == 0
+    dn = np.array([0.0, 0.0, 2575.0 - 800.0]) - org[0]
+    hit = oracle.los_steps_build(z, atm["temp"], atm["pres"], vmr, org, [dn / np.linalg.norm(dn)])[0]
+    assert hit["n_steps"] > 3 and hit["pres"][0] > 1000.0            # first (far) step is at the surface
