@@ -7,60 +7,117 @@
 // with the trapezoid rule over the (possibly irregular) hi-res grid; a channel that sees no hi-res
 // point is 0 (:903-905).  Doing this on the device turns a LOS from 1.2e6 doubles into ~1e2 before
 // it crosses PCIe.
+#include <algorithm>
 #include <cmath>
 #include "sr_common.h"
 
 namespace {
 
 constexpr int CONV_NT = 256;
-constexpr int CONV_SPB = 4;   // spectra per CTA: the Gaussian weights are computed once for them
+constexpr int CONV_SPB = 8;      // spectra per CTA: the Gaussian weights are computed once for them
+constexpr int CONV_PB = 1024;    // trapezoid segments per CTA
+constexpr int CONV_SLAB = 512;   // spectra per launch pair (bounds the partial-sum workspace)
+constexpr size_t CONV_SMEM = (size_t)(CONV_SPB + 1) * (CONV_PB + 1) * sizeof(double);
 
+// per channel: segments [i0, i1) of the trapezoid rule = hi-res points i0..i1 inside the window
+__global__ void k_convolve_windows(const double* __restrict__ x, long n_pts,
+                                   const double* __restrict__ centre,
+                                   const double* __restrict__ width, int n_chan, double n_sigma,
+                                   long* __restrict__ win) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chan) return;
+    const double f = centre[c], w = width[c];
+    const double lo = f - n_sigma * w, hi = f + n_sigma * w;
+    long a = 0, b = n_pts;   // first index with x >= lo, last index with x <= hi (grid ascending)
+    while (a < b) { const long m = (a + b) >> 1; if (x[m] < lo) a = m + 1; else b = m; }
+    win[2 * c] = a;
+    b = n_pts;
+    while (a < b) { const long m = (a + b) >> 1; if (x[m] <= hi) a = m + 1; else b = m; }
+    win[2 * c + 1] = a - 1;
+}
+
+// One CTA = CONV_PB consecutive trapezoid segments x CONV_SPB spectra, staged ONCE in shared
+// memory (every hi-res value is read from HBM exactly once; the overlapping channel windows
+// re-read it from shared memory), the Gaussian weight of a (channel, point) is computed once per
+// CTA, and the per-block sums go to partial[channel][block][spectrum]; k_convolve_reduce adds the
+// blocks in a fixed order, so the result does not depend on scheduling (no atomics).
+//   sum_i hd_i (y_i g_i + y_{i+1} g_{i+1})  =  sum_p y_p g_p (hd_{p-1} [p > s0] + hd_p [p < s1])
 __global__ void __launch_bounds__(CONV_NT) k_convolve_lowres(
     const double* __restrict__ x, long n_pts, const double* __restrict__ spec, int n_spec,
     const double* __restrict__ centre, const double* __restrict__ width, int n_chan,
-    double n_sigma, double* __restrict__ out) {
-    const int c = blockIdx.x, s0 = blockIdx.y * CONV_SPB;
-    const double f = centre[c], w = width[c];
-    const double lo = f - n_sigma * w, hi = f + n_sigma * w;
-    // first index with x >= lo, last index with x <= hi (grid ascending)
-    long a = 0, b = n_pts;
-    while (a < b) { const long m = (a + b) >> 1; if (x[m] < lo) a = m + 1; else b = m; }
-    const long i0 = a;
-    b = n_pts;
-    while (a < b) { const long m = (a + b) >> 1; if (x[m] <= hi) a = m + 1; else b = m; }
-    const long i1 = a - 1;
-    const double fac = 1.0 / (w * sqrt(2.0 * M_PI));
-    double acc[CONV_SPB];
-#pragma unroll
-    for (int q = 0; q < CONV_SPB; q++) acc[q] = 0.0;
-    // trapezoid segments i .. i+1, i in [i0, i1)
-    for (long i = i0 + threadIdx.x; i < i1; i += CONV_NT) {
-        const double xa = x[i], xb = x[i + 1];
-        const double ta = (xa - f) / w, tb = (xb - f) / w;
-        const double ga = fac * exp(-0.5 * (ta * ta)), gb = fac * exp(-0.5 * (tb * tb));
-        const double hd = (xb - xa) * 0.5;
-#pragma unroll
-        for (int q = 0; q < CONV_SPB; q++) {
-            if (s0 + q < n_spec) {
-                const double* __restrict__ y = spec + (size_t)(s0 + q) * n_pts;
-                acc[q] = fma(hd, fma(y[i], ga, y[i + 1] * gb), acc[q]);
-            }
-        }
-    }
+    const long* __restrict__ win, int n_blocks, double* __restrict__ partial) {
+    const long bstart = (long)blockIdx.x * CONV_PB;
+    const long bend = min(bstart + CONV_PB, n_pts - 1);
+    const int np = (int)(bend - bstart) + 1;          // points bstart .. bend
+    const int sp0 = blockIdx.y * CONV_SPB;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    extern __shared__ __align__(16) double csm[];
+    double* xs = csm;                                  // [CONV_PB + 1]
+    double* ys = csm + CONV_PB + 1;                    // [CONV_SPB][CONV_PB + 1]
     __shared__ double red[CONV_SPB][CONV_NT / 32];
+    // does any channel see this block at all?
+    bool any = false;
+    for (int c = 0; c < n_chan; c++)
+        any = any || min(win[2 * c + 1], bend) > max(win[2 * c], bstart);
+    if (!any) return;                                  // uniform over the CTA
+    for (int i = threadIdx.x; i < np; i += CONV_NT) xs[i] = x[bstart + i];
 #pragma unroll
     for (int q = 0; q < CONV_SPB; q++) {
-        double v = acc[q];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-        if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v;
+        const bool on = sp0 + q < n_spec;
+        const double* __restrict__ y = spec + (size_t)(on ? sp0 + q : sp0) * n_pts + bstart;
+        for (int i = threadIdx.x; i < np; i += CONV_NT)
+            ys[q * (CONV_PB + 1) + i] = on ? __ldcs(y + i) : 0.0;
     }
     __syncthreads();
-    if (threadIdx.x < CONV_SPB && s0 + threadIdx.x < n_spec) {
-        double v = 0.0;
-        for (int k = 0; k < CONV_NT / 32; k++) v += red[threadIdx.x][k];
-        out[(size_t)(s0 + threadIdx.x) * n_chan + c] = v;
+    for (int c = 0; c < n_chan; c++) {
+        const long s0l = max(win[2 * c], bstart), s1l = min(win[2 * c + 1], bend);
+        if (s1l <= s0l) continue;                      // uniform over the CTA
+        const int s0 = (int)(s0l - bstart), s1 = (int)(s1l - bstart);
+        const double f = centre[c], w = width[c];
+        const double fac = 1.0 / (w * sqrt(2.0 * M_PI));
+        double acc[CONV_SPB];
+#pragma unroll
+        for (int q = 0; q < CONV_SPB; q++) acc[q] = 0.0;
+        for (int p = s0 + threadIdx.x; p <= s1; p += CONV_NT) {
+            const double xp = xs[p];
+            double hd = 0.0;
+            if (p > s0) hd += (xp - xs[p - 1]) * 0.5;
+            if (p < s1) hd += (xs[p + 1] - xp) * 0.5;
+            const double t = (xp - f) / w;
+            const double g = fac * exp(-0.5 * (t * t)) * hd;
+#pragma unroll
+            for (int q = 0; q < CONV_SPB; q++) acc[q] = fma(ys[q * (CONV_PB + 1) + p], g, acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < CONV_SPB; q++) {
+            double v = acc[q];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+            if (lane == 0) red[q][wid] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < CONV_SPB && sp0 + threadIdx.x < n_spec) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < CONV_NT / 32; k++) v += red[threadIdx.x][k];
+            partial[((size_t)c * n_blocks + blockIdx.x) * n_spec + sp0 + threadIdx.x] = v;
+        }
+        __syncthreads();
     }
+}
+
+__global__ void k_convolve_reduce(const double* __restrict__ partial, const long* __restrict__ win,
+                                  int n_spec, int n_chan, int n_blocks, long n_pts,
+                                  double* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (s >= n_spec) return;
+    const long i0 = win[2 * c], i1 = min(win[2 * c + 1], n_pts - 1);
+    double v = 0.0;
+    if (i1 > i0) {   // blocks holding the segments [i0, i1)
+        const int b0 = (int)(i0 / CONV_PB), b1 = (int)((i1 - 1) / CONV_PB);
+        for (int b = b0; b <= b1; b++) v += partial[((size_t)c * n_blocks + b) * n_spec + s];
+    }
+    out[(size_t)s * n_chan + c] = v;
 }
 
 }  // namespace
@@ -73,10 +130,48 @@ int sr_convolve_lowres_dev(const double* grid_dev, long n_pts, const double* spe
     if (!grid_dev || !spec_dev || !centre_dev || !width_dev || !out_dev || n_pts < 1 ||
         n_spec < 1 || n_chan < 1 || !(n_sigma > 0.0))
         return sr::fail(SR_ERR_ARG, "sr_convolve_lowres_dev: bad argument");
-    dim3 grid((unsigned)n_chan, (unsigned)((n_spec + CONV_SPB - 1) / CONV_SPB));
-    SR_LAUNCH(k_convolve_lowres, grid, CONV_NT, 0, (cudaStream_t)stream, grid_dev, n_pts, spec_dev,
-              n_spec, centre_dev, width_dev, n_chan, n_sigma, out_dev);
-    return SR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_blocks = (int)std::max<long>(1, (n_pts - 1 + CONV_PB - 1) / CONV_PB);
+    const int slab = std::min(n_spec, CONV_SLAB);
+    // stream-ordered scratch: channel windows + partial sums [n_chan][n_blocks][slab]
+    long* win = nullptr;
+    double* partial = nullptr;
+    SR_CUDA(cudaMallocAsync(&win, sizeof(long) * 2 * n_chan, st));
+    cudaError_t e = cudaMallocAsync(&partial, sizeof(double) * (size_t)n_chan * n_blocks * slab, st);
+    if (e != cudaSuccess) {
+        cudaFreeAsync(win, st);
+        return sr::fail(SR_ERR_CUDA, "sr_convolve_lowres_dev: %s", cudaGetErrorString(e));
+    }
+    auto body = [&]() -> int {
+        static bool once = false;   // keep freed scratch in the stream-ordered pool between calls
+        if (!once) {
+            int dev = 0;
+            cudaMemPool_t pool;
+            unsigned long long keep = ~0ull;
+            if (cudaGetDevice(&dev) == cudaSuccess &&
+                cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            once = true;
+        }
+        SR_CUDA(cudaFuncSetAttribute(k_convolve_lowres, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)CONV_SMEM));
+        SR_LAUNCH(k_convolve_windows, (n_chan + 63) / 64, 64, 0, st, grid_dev, n_pts, centre_dev,
+                  width_dev, n_chan, n_sigma, win);
+        for (int s0 = 0; s0 < n_spec; s0 += slab) {
+            const int ns = std::min(slab, n_spec - s0);
+            dim3 grid((unsigned)n_blocks, (unsigned)((ns + CONV_SPB - 1) / CONV_SPB));
+            SR_LAUNCH(k_convolve_lowres, grid, CONV_NT, CONV_SMEM, st, grid_dev, n_pts,
+                      spec_dev + (size_t)s0 * n_pts, ns, centre_dev, width_dev, n_chan, win,
+                      n_blocks, partial);
+            SR_LAUNCH(k_convolve_reduce, dim3((unsigned)((ns + 127) / 128), (unsigned)n_chan), 128, 0,
+                      st, partial, win, ns, n_chan, n_blocks, n_pts, out_dev + (size_t)s0 * n_chan);
+        }
+        return SR_OK;
+    };
+    const int rc = body();
+    cudaFreeAsync(partial, st);
+    cudaFreeAsync(win, st);
+    return rc;
 }
 
 int sr_convolve_lowres_host(const double* grid, long n_pts, const double* spec, int n_spec,

@@ -408,8 +408,8 @@ __global__ void __launch_bounds__(256, 2) k_los_layers_jac(const __grid_constant
     const RecArgs& r = a.r;
     const int l = blockIdx.y, pz = blockIdx.z * NP;
     const long p = (long)blockIdx.x * 256 + threadIdx.x;
-    if (p >= r.n_pts) return;
-    double I = r.i0 ? r.i0[(size_t)l * r.io_stride + r.io_off + p] : 0.0;
+    const bool live = p < r.n_pts;
+    double I = (r.i0 && live) ? r.i0[(size_t)l * r.io_stride + r.io_off + p] : 0.0;
     double D[NP];
 #pragma unroll
     for (int q = 0; q < NP; q++) D[q] = 0.0;
@@ -420,8 +420,19 @@ __global__ void __launch_bounds__(256, 2) k_los_layers_jac(const __grid_constant
     const double* __restrict__ sp = r.src + lay0;
     const double* __restrict__ tgp = MULTI ? a.tau_g + lay0 : nullptr;
     const double* __restrict__ sgp = MULTI ? a.src_g + lay0 : nullptr;
-    const double* __restrict__ fr = a.dfrac + (size_t)l * r.n_steps_max * a.n_par + pz;
     const int npar = min(NP, a.n_par - pz);
+    // this LOS' rows of the derivative table, zero-padded to NP columns, in shared memory: the
+    // inner loop reads them as broadcast LDS.128 (no per-parameter predicate, no global latency)
+    extern __shared__ __align__(16) double fs[];
+    {
+        const double* __restrict__ fr = a.dfrac + (size_t)l * r.n_steps_max * a.n_par + pz;
+        for (int i = threadIdx.x; i < ns * NP; i += 256) {
+            const int k = i / NP, q = i - k * NP;
+            fs[i] = q < npar ? fr[(size_t)k * a.n_par + q] : 0.0;
+        }
+    }
+    __syncthreads();
+    if (!live) return;
     constexpr int U = 4;
     for (int k0 = 0; k0 < ns; k0 += U) {
         double t[U], s[U], tg[U], sg[U];
@@ -450,11 +461,12 @@ __global__ void __launch_bounds__(256, 2) k_los_layers_jac(const __grid_constant
                 B = solo ? -I * ex * t[u] : ex * fma(-I, t[u], s[u]);
             }
             I = solo ? I * ex : fma(I, ex, s[u] * phi);
-            const double* __restrict__ f = fr + (size_t)(k0 + u) * a.n_par;
+            const double2* __restrict__ f2 = reinterpret_cast<const double2*>(fs + (k0 + u) * NP);
 #pragma unroll
-            for (int q = 0; q < NP; q++) {
-                const double fq = q < npar ? __ldg(f + q) : 0.0;   // uniform over the CTA
-                D[q] = fma(D[q], ex, fq * B);
+            for (int q = 0; q < NP; q += 2) {
+                const double2 fq = f2[q >> 1];
+                D[q] = fma(D[q], ex, fq.x * B);
+                D[q + 1] = fma(D[q + 1], ex, fq.y * B);
             }
         }
     }
@@ -1052,10 +1064,23 @@ static int layers_jac_launch(const double* tau, const double* src, const double*
 #define SR_JAC(NP)                                                                             \
     {                                                                                          \
         dim3 grid((unsigned)a.r.n_tiles, (unsigned)n_los, (unsigned)((n_par + NP - 1) / NP));  \
-        if (multi) SR_LAUNCH((k_los_layers_jac<NP, true>), grid, 256, 0, st, a);               \
-        else SR_LAUNCH((k_los_layers_jac<NP, false>), grid, 256, 0, st, a);                    \
+        const size_t smem = (size_t)n_steps_max * NP * sizeof(double);                         \
+        if (smem > (size_t)200 * 1024)                                                         \
+            return sr::fail(SR_ERR_LIMIT, "LOS Jacobians: %d steps per LOS exceed the shared-memory " \
+                            "table of the derivative kernel", n_steps_max);                    \
+        if (multi) {                                                                           \
+            SR_CUDA(cudaFuncSetAttribute(k_los_layers_jac<NP, true>,                           \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            SR_LAUNCH((k_los_layers_jac<NP, true>), grid, 256, smem, st, a);                   \
+        } else {                                                                               \
+            SR_CUDA(cudaFuncSetAttribute(k_los_layers_jac<NP, false>,                          \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            SR_LAUNCH((k_los_layers_jac<NP, false>), grid, 256, smem, st, a);                  \
+        }                                                                                      \
     }
-    if (n_par <= 4) SR_JAC(4) else if (n_par <= 8) SR_JAC(8) else SR_JAC(16)
+    // the smallest accumulator count that takes all parameters in one pass, else chunks of 16
+    if (n_par <= 4) SR_JAC(4) else if (n_par <= 8) SR_JAC(8) else if (n_par <= 12) SR_JAC(12)
+    else SR_JAC(16)
 #undef SR_JAC
     return SR_OK;
 }
