@@ -1,6 +1,7 @@
 // sr_common.h -- host-side plumbing shared by the translation units of libspectrobot.so
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -58,6 +59,39 @@ struct DevBuf {  // RAII device buffer
     cudaError_t ensure(size_t count) { return count <= n ? cudaSuccess : alloc(count); }
     cudaError_t upload(const T* h, size_t count, cudaStream_t s = 0) {
         cudaError_t e = ensure(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+};
+
+// Stream-ordered scratch (cudaMallocAsync): freed blocks stay in the device's default pool instead
+// of going back to the driver at every synchronisation, so per-call scratch costs no cudaMalloc.
+inline void pool_keep() {
+    static bool once = false;
+    if (once) return;
+    int dev = 0;
+    cudaMemPool_t pool;
+    unsigned long long keep = ~0ull;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    once = true;
+}
+
+template <typename T>
+struct PoolBuf {  // RAII stream-ordered device buffer
+    T* p = nullptr;
+    cudaStream_t st = 0;
+    PoolBuf() = default;
+    PoolBuf(const PoolBuf&) = delete;
+    PoolBuf& operator=(const PoolBuf&) = delete;
+    ~PoolBuf() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t alloc(size_t count, cudaStream_t s) {
+        pool_keep();
+        st = s;
+        return cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), s);
+    }
+    cudaError_t upload(const T* h, size_t count, cudaStream_t s) {
+        cudaError_t e = alloc(count, s);
         if (e != cudaSuccess || count == 0) return e;
         return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
     }

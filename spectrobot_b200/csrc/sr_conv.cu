@@ -136,6 +136,7 @@ int sr_convolve_lowres_dev(const double* grid_dev, long n_pts, const double* spe
     // stream-ordered scratch: channel windows + partial sums [n_chan][n_blocks][slab]
     long* win = nullptr;
     double* partial = nullptr;
+    sr::pool_keep();
     SR_CUDA(cudaMallocAsync(&win, sizeof(long) * 2 * n_chan, st));
     cudaError_t e = cudaMallocAsync(&partial, sizeof(double) * (size_t)n_chan * n_blocks * slab, st);
     if (e != cudaSuccess) {
@@ -143,16 +144,6 @@ int sr_convolve_lowres_dev(const double* grid_dev, long n_pts, const double* spe
         return sr::fail(SR_ERR_CUDA, "sr_convolve_lowres_dev: %s", cudaGetErrorString(e));
     }
     auto body = [&]() -> int {
-        static bool once = false;   // keep freed scratch in the stream-ordered pool between calls
-        if (!once) {
-            int dev = 0;
-            cudaMemPool_t pool;
-            unsigned long long keep = ~0ull;
-            if (cudaGetDevice(&dev) == cudaSuccess &&
-                cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            once = true;
-        }
         SR_CUDA(cudaFuncSetAttribute(k_convolve_lowres, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)CONV_SMEM));
         SR_LAUNCH(k_convolve_windows, (n_chan + 63) / 64, 64, 0, st, grid_dev, n_pts, centre_dev,

@@ -1361,7 +1361,16 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
     }
     // ---- v3: grouped tensor-path product into layer arrays, then the streaming recursion ------
     // blocking: the layer scratch (16 B per pair and point) stays below the budget
-    size_t budget = (size_t)8 << 30;
+    // Bigger LOS blocks mean more (LOS, step) pairs per LUT cell quad, i.e. fuller 16-pair chunks
+    // in the tensor-path product and fewer passes over the LUT, so the budgets follow the free
+    // device memory (a quarter of it for the layer scratch, capped at 32 GiB).
+    size_t mem_free = 0, mem_total = 0;
+    if (cudaMemGetInfo(&mem_free, &mem_total) != cudaSuccess) mem_free = (size_t)32 << 30;
+    mem_free += L0->ws_tau.n * 8 + L0->ws_src.n * 8 + L0->ws_tau_g.n * 8 + L0->ws_src_g.n * 8 +
+                L0->ws_jac.n * 8 + L0->ws_rad[0].n * 8 + L0->ws_rad[1].n * 8;   // our own, reusable
+    size_t budget = std::min<size_t>((size_t)32 << 30, std::max<size_t>((size_t)1 << 30, mem_free / 4));
+    const size_t rad_cap = std::min<size_t>((size_t)8 << 30, std::max<size_t>((size_t)1 << 30, mem_free / 8));
+    const size_t jac_cap = std::min<size_t>((size_t)48 << 30, std::max<size_t>((size_t)1 << 30, mem_free / 3));
     if (const char* e = getenv("SR_LOS_SCRATCH_MB")) budget = (size_t)std::max(1L, atol(e)) << 20;
     long chunk_pts = n_pts;
     int nl_block = n_los;
@@ -1378,13 +1387,13 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         if (const char* e = getenv("SR_LOS_BLOCK")) nl_block = std::max(1, atoi(e));
         chunk_pts = std::min(chunk_pts, n_pts);
         if (chunk_pts < n_pts) chunk_pts = std::max(256L, chunk_pts / 256 * 256);
-        if (low || sink)   // the block's radiances [nl_block][n_pts] live in a workspace (<= 4 GiB)
+        if (low || sink)   // the block's radiances [nl_block][n_pts] live in a workspace (<= 8 GiB)
             nl_block = (int)std::min<size_t>((size_t)nl_block,
-                                             std::max<size_t>(1, ((size_t)4 << 30) / ((size_t)n_pts * 8)));
-        if (low && jac)    // ... and so do its derivatives [nl_block][n_par][n_pts] (<= 8 GiB)
+                                             std::max<size_t>(1, rad_cap / ((size_t)n_pts * 8)));
+        if (low && jac)    // ... and so do its derivatives [nl_block][n_par][n_pts] (<= 48 GiB)
             nl_block = (int)std::min<size_t>(
                 (size_t)nl_block,
-                std::max<size_t>(1, ((size_t)8 << 30) / ((size_t)n_pts * 8 * (size_t)jac->n_par)));
+                std::max<size_t>(1, jac_cap / ((size_t)n_pts * 8 * (size_t)jac->n_par)));
         nl_block = std::min(std::min(nl_block, n_los), 65535);   // blockIdx.y of the recursion
     }
     GemmPlan P;

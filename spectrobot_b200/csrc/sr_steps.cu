@@ -277,8 +277,8 @@ int sr_los_steps_build(const sr_atmosphere* atm, int n_los, const double* origin
     cudaStream_t st = 0;
     std::vector<double> lnp((size_t)nb * nz);
     for (size_t i = 0; i < lnp.size(); i++) lnp[i] = std::log(atm->pres[i]);
-    sr::DevBuf<double> d_edges, d_z, d_temp, d_lnp, d_vmr, d_tvib, d_masks, d_org, d_dir;
-    sr::DevBuf<int> d_on;
+    sr::PoolBuf<double> d_edges, d_z, d_temp, d_lnp, d_vmr, d_tvib, d_masks, d_org, d_dir;
+    sr::PoolBuf<int> d_on;
     if (nb > 1) SR_CUDA(d_edges.upload(atm->lat_edges, nb + 1, st));
     SR_CUDA(d_z.upload(atm->z, nz, st));
     SR_CUDA(d_temp.upload(atm->temp, (size_t)nb * nz, st));
@@ -296,23 +296,28 @@ int sr_los_steps_build(const sr_atmosphere* atm, int n_los, const double* origin
     const int n_pts_max = 2 * (int)std::floor(r_top / delta_x_km) + 3;
     // LOS blocks bound the per-point scratch (48 B per point) to ~1 GiB
     const int blk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_los, ((size_t)1 << 30) / ((size_t)n_pts_max * 48)));
-    sr::DevBuf<double> sT, sP, snd, sx, salt, o_temp, o_pres, o_col, o_tvib, o_dfrac;
-    sr::DevBuf<int> sband, sjz, d_npts, d_nsteps, d_bounds;
+    sr::PoolBuf<double> sT, sP, snd, sx, salt, o_temp, o_pres, o_col, o_tvib, o_dfrac;
+    sr::PoolBuf<int> sband, sjz, d_npts, d_nsteps, d_bounds;
     const size_t np = (size_t)blk * n_pts_max;
-    SR_CUDA(sT.alloc(np)); SR_CUDA(sP.alloc(np)); SR_CUDA(snd.alloc(np)); SR_CUDA(sx.alloc(np));
-    SR_CUDA(salt.alloc(np)); SR_CUDA(sband.alloc(np)); SR_CUDA(sjz.alloc(np));
-    SR_CUDA(d_npts.alloc(blk)); SR_CUDA(d_nsteps.alloc(blk));
-    SR_CUDA(d_bounds.alloc((size_t)blk * n_steps_max * 2));
+    SR_CUDA(sT.alloc(np, st)); SR_CUDA(sP.alloc(np, st)); SR_CUDA(snd.alloc(np, st));
+    SR_CUDA(sx.alloc(np, st)); SR_CUDA(salt.alloc(np, st)); SR_CUDA(sband.alloc(np, st));
+    SR_CUDA(sjz.alloc(np, st));
+    SR_CUDA(d_npts.alloc(blk, st)); SR_CUDA(d_nsteps.alloc(blk, st));
+    SR_CUDA(d_bounds.alloc((size_t)blk * n_steps_max * 2, st));
     const size_t bls = (size_t)blk * n_steps_max;
-    SR_CUDA(o_temp.alloc(bls)); SR_CUDA(o_pres.alloc(bls)); SR_CUDA(o_col.alloc(bls * ng));
-    SR_CUDA(o_tvib.alloc(std::max<size_t>(1, bls * ng * nsx)));
-    SR_CUDA(o_dfrac.alloc(std::max<size_t>(1, bls * n_par)));
+    SR_CUDA(o_temp.alloc(bls, st)); SR_CUDA(o_pres.alloc(bls, st)); SR_CUDA(o_col.alloc(bls * ng, st));
+    SR_CUDA(o_tvib.alloc(bls * ng * nsx, st));
+    SR_CUDA(o_dfrac.alloc(bls * n_par, st));
+    SR_CUDA(d_org.alloc((size_t)3 * blk, st));
+    SR_CUDA(d_dir.alloc((size_t)3 * blk, st));
     int needed = 0;
     std::vector<double> tmp;
     for (int l0 = 0; l0 < n_los; l0 += blk) {
         const int nl = std::min(blk, n_los - l0);
-        SR_CUDA(d_org.upload(origin + (size_t)3 * l0, (size_t)3 * nl, st));
-        SR_CUDA(d_dir.upload(direction + (size_t)3 * l0, (size_t)3 * nl, st));
+        SR_CUDA(cudaMemcpyAsync(d_org.p, origin + (size_t)3 * l0, sizeof(double) * 3 * nl,
+                                cudaMemcpyHostToDevice, st));
+        SR_CUDA(cudaMemcpyAsync(d_dir.p, direction + (size_t)3 * l0, sizeof(double) * 3 * nl,
+                                cudaMemcpyHostToDevice, st));
         PtArgs pa;
         pa.A = A; pa.origin = d_org.p; pa.dir = d_dir.p;
         pa.n_los = nl; pa.n_pts_max = n_pts_max; pa.n_steps_max = n_steps_max;

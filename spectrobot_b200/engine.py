@@ -560,6 +560,12 @@ def los_steps_build(atm, origins, directions, delta_x=5.0, max_T_variation=5.0,
             continue
         check(rc)
         break
+    # trim the tables to the longest LOS: the LOS kernels size their layer scratch by the width
+    w = max(int(n_steps.max()), 1)
+    if w < n_steps_max:
+        temp, pres, col = temp[:, :w], pres[:, :w], col[:, :, :w]
+        tvib = None if tvib is None else tvib[:, :, :, :w]
+        dfrac = None if dfrac is None else dfrac[:, :w]
     return LosSteps(n_steps, temp, pres, col, tvib), dfrac
 
 
