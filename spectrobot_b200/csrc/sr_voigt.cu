@@ -941,11 +941,12 @@ int sr_lineset_create(const sr_lines* lines, const double* grid, long n_grid,
     };
     int code = body();
     if (code != SR_OK) { delete ls; return code; }
-    // cells per batch: keep the per-(line,cell) tables under ~6 GiB
+    // cells per batch: keep the per-(line,cell) tables under ~2 GiB (8 cells per launch already
+    // fill the machine: 2344 tiles x 8 cells on 148 SMs x 4 CTAs)
     size_t per_cell = (size_t)std::max(n_act, 1) *
                       (sizeof(LineCell) + sizeof(LineRec) + CORE_STRIDE * sizeof(double));
     ls->max_cells_per_batch =
-        (int)std::max<size_t>(1, std::min<size_t>(4096, ((size_t)6 << 30) / per_cell));
+        (int)std::max<size_t>(1, std::min<size_t>(4096, ((size_t)2 << 30) / per_cell));
     *out = ls;
     return SR_OK;
 }
@@ -970,11 +971,14 @@ int sr_lineset_order(const sr_lineset* ls, int* order_host) {
 }
 
 static int run_params(sr_lineset* ls, const double* pt_host, int n_cells, cudaStream_t st) {
-    SR_CUDA(ls->pt.ensure((size_t)2 * n_cells));
+    // the per-batch tables are allocated once for a full batch: later (larger) calls never
+    // reallocate them, so consecutive batches need no host synchronisation (stream order suffices)
+    const size_t cap = (size_t)std::max(n_cells, std::min(ls->max_cells_per_batch, 16));
+    SR_CUDA(ls->pt.ensure(2 * cap));
     SR_CUDA(cudaMemcpyAsync(ls->pt.p, pt_host, sizeof(double) * 2 * n_cells,
                             cudaMemcpyHostToDevice, st));
-    SR_CUDA(ls->rec.ensure((size_t)n_cells * ls->n_act));
-    SR_CUDA(ls->lrec.ensure((size_t)n_cells * ls->n_act));
+    SR_CUDA(ls->rec.ensure(cap * ls->n_act));
+    SR_CUDA(ls->lrec.ensure(cap * ls->n_act));
     ParamsArgs pa;
     pa.L = {ls->freq.p, ls->a_coeff.p, ls->air.p, ls->tdep.p, ls->e_lower.p, ls->g_up.p,
             ls->g_lo.p, ls->evu.p, ls->evl.p, ls->gc.p, ls->ind.p};
@@ -1009,10 +1013,12 @@ static int gcoeff_cells_impl(sr_lineset* ls, const double* pt_host, int n_cells,
     }
     for (int c0 = 0; c0 < n_cells; c0 += ls->max_cells_per_batch) {
         const int nb = std::min(ls->max_cells_per_batch, n_cells - c0);
-        if (c0 > 0) SR_CUDA(cudaStreamSynchronize(st));  // per-batch tables are reused
+        // per-batch tables are reused: the kernels of this batch queue behind the previous batch's
+        // tile kernel on the same stream (pt_host is pageable: its copy is staged before return)
         int code = run_params(ls, pt_host + 2 * c0, nb, st);
         if (code) return code;
-        SR_CUDA(ls->core.ensure((size_t)nb * ls->n_act * CORE_STRIDE));
+        SR_CUDA(ls->core.ensure((size_t)std::max(nb, std::min(ls->max_cells_per_batch, 16)) *
+                                ls->n_act * CORE_STRIDE));   // (a growing cudaFree synchronises)
         {
             dim3 cgrid((ls->n_act + 7) / 8, nb);
             SR_LAUNCH(k_core_eval, cgrid, 256, 0, st, ls->rec.p, ls->freq.p, ls->gc.p, ls->lin.p,
