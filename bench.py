@@ -503,6 +503,13 @@ def run_ours(args):
 
     peaks = measured_peaks()
     hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+    traffic = None     # dram__bytes_read + write of this kernel on this workload, one ncu capture
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_k3_bench_traffic.json")))
+        if not args.small and n_los == 36 and n_grid == 1200001:
+            traffic = float(tr["traffic"])
+    except Exception:
+        pass
     achieved = k3_bytes / (k3_ms * 1e-3) / 1e9
     line = {
         "metric": "LOS radiances/s", "value": value, "unit": "LOS/s", "n_gpus": world,
@@ -510,7 +517,9 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, wl),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "kernel": "k_los_layers",
+                     "frac": achieved / hbm_peak, "traffic": traffic, "kernel": "k_los_layers",
+                     "traffic_source": "profiles/r1_k3_bench_traffic.json (ncu --set full, per launch)"
+                     if traffic else None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks
                      else "fallback 6650 GB/s (of fallback)",
                      "algorithmic_bytes_per_launch": k3_bytes},
