@@ -403,8 +403,8 @@ __device__ __forceinline__ double dphi(double t, double ex, double phi) {
     return (ex - phi) / t;
 }
 
-template <int NP, bool MULTI>
-__global__ void __launch_bounds__(256, 2) k_los_layers_jac(const __grid_constant__ JacArgs a) {
+template <int NP, bool MULTI, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_los_layers_jac(const __grid_constant__ JacArgs a) {
     const RecArgs& r = a.r;
     const int l = blockIdx.y, pz = blockIdx.z * NP;
     const long p = (long)blockIdx.x * 256 + threadIdx.x;
@@ -433,7 +433,6 @@ __global__ void __launch_bounds__(256, 2) k_los_layers_jac(const __grid_constant
     }
     __syncthreads();
     if (!live) return;
-    constexpr int U = 4;
     for (int k0 = 0; k0 < ns; k0 += U) {
         double t[U], s[U], tg[U], sg[U];
 #pragma unroll
@@ -1069,15 +1068,24 @@ static int layers_jac_launch(const double* tau, const double* src, const double*
             return sr::fail(SR_ERR_LIMIT, "LOS Jacobians: %d steps per LOS exceed the shared-memory " \
                             "table of the derivative kernel", n_steps_max);                    \
         if (multi) {                                                                           \
-            SR_CUDA(cudaFuncSetAttribute(k_los_layers_jac<NP, true>,                           \
+            SR_CUDA(cudaFuncSetAttribute(k_los_layers_jac<NP, true, 4, 2>,                     \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            SR_LAUNCH((k_los_layers_jac<NP, true>), grid, 256, smem, st, a);                   \
+            SR_LAUNCH((k_los_layers_jac<NP, true, 4, 2>), grid, 256, smem, st, a);             \
+        } else if (jcfg == 1) {                                                                \
+            SR_CUDA(cudaFuncSetAttribute(k_los_layers_jac<NP, false, 2, 3>,                    \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            SR_LAUNCH((k_los_layers_jac<NP, false, 2, 3>), grid, 256, smem, st, a);            \
+        } else if (jcfg == 2) {                                                                \
+            SR_CUDA(cudaFuncSetAttribute(k_los_layers_jac<NP, false, 4, 3>,                    \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            SR_LAUNCH((k_los_layers_jac<NP, false, 4, 3>), grid, 256, smem, st, a);            \
         } else {                                                                               \
-            SR_CUDA(cudaFuncSetAttribute(k_los_layers_jac<NP, false>,                          \
+            SR_CUDA(cudaFuncSetAttribute(k_los_layers_jac<NP, false, 4, 2>,                    \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            SR_LAUNCH((k_los_layers_jac<NP, false>), grid, 256, smem, st, a);                  \
+            SR_LAUNCH((k_los_layers_jac<NP, false, 4, 2>), grid, 256, smem, st, a);            \
         }                                                                                      \
     }
+    static const int jcfg = getenv("SR_JAC_CFG") ? atoi(getenv("SR_JAC_CFG")) : 1;   // tuning aid; 1 (2-step unroll, 3 CTAs/SM) measured best on B200
     // the smallest accumulator count that takes all parameters in one pass, else chunks of 16
     if (n_par <= 4) SR_JAC(4) else if (n_par <= 8) SR_JAC(8) else if (n_par <= 12) SR_JAC(12)
     else SR_JAC(16)
