@@ -90,7 +90,10 @@ def make_workload(args, rank, n_los, want_lines=True):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clocks / throttle reasons sampled during the timed region: NVML in-process (the same
+    counters `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints;
+    spawning nvidia-smi every 0.2 s from every rank perturbs the host-side legs), nvidia-smi as
+    the fallback when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -98,18 +101,44 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         threading.Thread.__init__(self, daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes the visible devices: map through CUDA_VISIBLE_DEVICES if set
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        act = lambda bit: "Active" if r & bit else "Not Active"   # noqa: E731
+        # order of Q: hw_slowdown 0x8, hw_thermal_slowdown 0x40, sw_thermal_slowdown 0x20, sw_power_cap 0x4
+        return [str(sm), str(mx), act(0x8), act(0x40), act(0x20), act(0x4)]
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([t.strip() for t in out.split(",")])
+                if self.nvml is not None:
+                    self.samples.append(self.sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True,
+                                         text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([t.strip() for t in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1 if self.nvml is not None else 0.5)
 
     def summary(self):
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
@@ -119,7 +148,7 @@ class ClockSampler(threading.Thread):
                           if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peaks():
