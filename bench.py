@@ -126,6 +126,7 @@ class ClockSampler(threading.Thread):
         return [str(sm), str(mx), act(0x8), act(0x40), act(0x20), act(0x4)]
 
     def run(self):
+        period = float(os.environ.get("SR_BENCH_SAMPLE_S", "0.5"))   # 10 Hz measurably slows the host legs
         while not self.stop_flag:
             try:
                 if self.nvml is not None:
@@ -138,7 +139,7 @@ class ClockSampler(threading.Thread):
                         self.samples.append([t.strip() for t in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1 if self.nvml is not None else 0.5)
+            time.sleep(period)
 
     def summary(self):
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
@@ -146,7 +147,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for s in self.samples for i in range(4)
                           if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_mhz_min": min(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 

@@ -1377,8 +1377,14 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
     mem_free += L0->ws_tau.n * 8 + L0->ws_src.n * 8 + L0->ws_tau_g.n * 8 + L0->ws_src_g.n * 8 +
                 L0->ws_jac.n * 8 + L0->ws_rad[0].n * 8 + L0->ws_rad[1].n * 8;   // our own, reusable
     size_t budget = std::min<size_t>((size_t)32 << 30, std::max<size_t>((size_t)1 << 30, mem_free / 4));
-    const size_t rad_cap = std::min<size_t>((size_t)8 << 30, std::max<size_t>((size_t)1 << 30, mem_free / 8));
-    const size_t jac_cap = std::min<size_t>((size_t)48 << 30, std::max<size_t>((size_t)1 << 30, mem_free / 3));
+    size_t rad_cap = std::min<size_t>((size_t)8 << 30, std::max<size_t>((size_t)1 << 30, mem_free / 8));
+    size_t jac_cap = std::min<size_t>((size_t)48 << 30, std::max<size_t>((size_t)1 << 30, mem_free / 3));
+    if (L0->ws_rad[0].n * 8 >= rad_cap / 2) rad_cap = std::min(L0->ws_rad[0].n * 8, (size_t)8 << 30);
+    if (L0->ws_jac.n * 8 >= jac_cap / 2) jac_cap = std::min(L0->ws_jac.n * 8, (size_t)48 << 30);
+    // sticky: a workspace that already holds at least half of what a fresh budget would give is
+    // used as it is, so that calls do not reallocate tens of GiB whenever the free memory moves
+    const size_t have = std::min(L0->ws_tau.n, L0->ws_src.n) * 16;
+    if (have >= budget / 2) budget = std::min(have, (size_t)32 << 30);
     if (const char* e = getenv("SR_LOS_SCRATCH_MB")) budget = (size_t)std::max(1L, atol(e)) << 20;
     long chunk_pts = n_pts;
     int nl_block = n_los;
