@@ -403,13 +403,15 @@ def run_ours(args):
     for _ in range(2):
         engine.los_rt_lut([lut], steps_f, out=rad_f)
     barrier()
-    ev0.record()
     n_f = max(1, min(args.steps, 3))
-    for _ in range(n_f):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_f + 1)]
+    evs[0].record()
+    for i in range(n_f):
         engine.los_rt_lut([lut], steps_f, out=rad_f, check_status=False)
-    ev1.record()
+        evs[i + 1].record()
     barrier()
-    fused_ms = max_over_ranks(ev0.elapsed_time(ev1)) / n_f
+    fused_each = [evs[i].elapsed_time(evs[i + 1]) for i in range(n_f)]
+    fused_ms = max_over_ranks(float(np.median(fused_each)))   # median: one call in ~10 catches a host hiccup
     agree = float(((rad_f[:n_los] - rad_k3).abs() / rad_k3.abs().clamp_min(1e-300)).max().item())
     fused_step_pts = float(st_all["n_steps"][:n_fused].sum()) * n_grid
     del rad_f
@@ -438,20 +440,25 @@ def run_ours(args):
     engine.los_rt_lut_lowres([lut], steps_f, gdev_j, cj, wj)
     low_j, jac_j = engine.los_rt_lut_jac_lowres([lut], steps_f, dfrac, gdev_j, cj, wj)
     barrier()
-    ev0.record()
-    low_f = engine.los_rt_lut_lowres([lut], steps_f, gdev_j, cj, wj, check_status=False)
-    ev1.record()
+    fwd_each, jac_each = [], []
+    for _ in range(3):
+        ev0.record()
+        low_f = engine.los_rt_lut_lowres([lut], steps_f, gdev_j, cj, wj, check_status=False)
+        ev1.record()
+        torch.cuda.synchronize()
+        fwd_each.append(ev0.elapsed_time(ev1))
+        ev0.record()
+        low_j, jac_j = engine.los_rt_lut_jac_lowres([lut], steps_f, dfrac, gdev_j, cj, wj,
+                                                    check_status=False)
+        ev1.record()
+        torch.cuda.synchronize()
+        jac_each.append(ev0.elapsed_time(ev1))
     barrier()
-    fwd_low_ms = max_over_ranks(ev0.elapsed_time(ev1))
-    ev0.record()
-    low_j, jac_j = engine.los_rt_lut_jac_lowres([lut], steps_f, dfrac, gdev_j, cj, wj,
-                                                check_status=False)
-    ev1.record()
-    barrier()
-    jac_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    fwd_low_ms = max_over_ranks(float(np.median(fwd_each)))
+    jac_ms = max_over_ranks(float(np.median(jac_each)))
     jacobian = {"value": world * n_fused / (jac_ms * 1e-3), "unit": "LOS/s (radiance + %d derivative "
                 "spectra each)" % n_par, "n_par": n_par, "los_per_rank": n_fused, "ms": jac_ms,
-                "forward_only_ms": fwd_low_ms, "channels": 36,
+                "forward_only_ms": fwd_low_ms, "channels": 36, "ms_each_rank0": jac_each,
                 "derivative_spectra_per_s": world * n_fused * n_par / (jac_ms * 1e-3),
                 "radiance_same_as_forward": bool(torch.equal(low_j, low_f)),
                 "finite": bool(torch.isfinite(jac_j).all().item()),
@@ -464,12 +471,14 @@ def run_ours(args):
     host_out = torch.empty((n_e, n_grid), dtype=torch.float64, pin_memory=True).numpy()
     engine.los_rt_lut_host([lut], sub, out=host_out)
     barrier()
-    t0 = time.perf_counter()
     n_h = max(1, min(args.steps, 3))
+    e2e_each = []
     for _ in range(n_h):
+        t0 = time.perf_counter()
         engine.los_rt_lut_host([lut], sub, out=host_out)
+        e2e_each.append(time.perf_counter() - t0)
     barrier()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / n_h)
+    e2e_s = max_over_ranks(float(np.median(e2e_each)))
     sampler.stop_flag = True
     sampler.join(timeout=2)
     h2d = int(sub.n_steps.nbytes + sub.temp.nbytes + sub.pres.nbytes + sub.column.nbytes +
@@ -554,13 +563,14 @@ def run_ours(args):
                      else "fallback 6650 GB/s (of fallback)",
                      "algorithmic_bytes_per_launch": k3_bytes},
         "e2e": {"value": world * n_e / e2e_s, "unit": "LOS/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "los_per_call": n_e,
+                "d2h_bytes_per_step": d2h, "los_per_call": n_e, "s_each_rank0": e2e_each,
+                "timing": "median of the calls (wall clock around the synchronous host call)",
                 "path": "sr_los_rt_lut_host: LUT interpolation + populations + layer recursion, "
                         "host step tables -> host hi-res radiances"},
         "fused": {"value": world * n_fused / (fused_ms * 1e-3), "unit": "LOS/s",
                   "los_per_rank": n_fused, "ms_per_step": fused_ms,
                   "step_points_per_s": world * fused_step_pts / (fused_ms * 1e-3),
-                  "max_rel_diff_vs_k3": agree,
+                  "max_rel_diff_vs_k3": agree, "ms_each_rank0": fused_each,
                   "roofline": {"bound": "fp64", "achieved": fused_flop / (fused_ms * 1e-3) / 1e12,
                                "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                                "frac": fused_flop / (fused_ms * 1e-3) / fp64_peak, "traffic": None,

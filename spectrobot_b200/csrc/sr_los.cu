@@ -17,6 +17,7 @@
 //   k_los_tau_src   K3a alone: materialises tau and S = J/tau
 //   k_los_layers    K3 alone: HBM-streaming recursion over materialised tau/S
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -1411,8 +1412,14 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         nl_block = std::min(std::min(nl_block, n_los), 65535);   // blockIdx.y of the recursion
     }
     GemmPlan P;
+    static const bool timing = getenv("SR_LOS_TIMING") != nullptr;   // host-side timing to stderr
+    const auto t_plan0 = std::chrono::steady_clock::now();
     rc = build_plan(luts, steps, nl_block, P);
     if (rc) return rc;
+    if (timing)
+        fprintf(stderr, "[sr_los] plan: %d LOS, %d groups, %d chunks, nl_block %d, chunk_pts %ld: %.3f ms\n",
+                n_los, P.n_groups, P.n_chunks, nl_block, chunk_pts,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count());
     const int n_blocks = (int)P.blk_los.size() - 1;
     if (P.max_jp > GEMM_MAXJ)
         return sr::fail(SR_ERR_LIMIT, "LOS: %d LUT rows per cell quad (limit %d)", P.max_jp, GEMM_MAXJ);
