@@ -1253,9 +1253,7 @@ static int build_plan(sr_lut* const* luts, const sr_los_steps* S, int nl_block, 
         P.blk_chunk.push_back(P.n_chunks);
     }
     P.rowptr.resize(P.prog.size());
-    const bool same_row = getenv("SR_MMA_SAMEROW") != nullptr;   // timing experiment only (wrong results)
-    for (size_t q = 0; q < P.prog.size(); q++)
-        P.rowptr[q] = same_row ? (long long)luts[0]->g32 : P.prog[q].roff;
+    for (size_t q = 0; q < P.prog.size(); q++) P.rowptr[q] = P.prog[q].roff;
     return SR_OK;
 }
 
