@@ -9,15 +9,15 @@
 // it crosses PCIe.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include "sr_common.h"
 
 namespace {
 
 constexpr int CONV_NT = 256;
-constexpr int CONV_SPB = 8;      // spectra per CTA: the Gaussian weights are computed once for them
-constexpr int CONV_PB = 1024;    // trapezoid segments per CTA
 constexpr int CONV_SLAB = 512;   // spectra per launch pair (bounds the partial-sum workspace)
-constexpr size_t CONV_SMEM = (size_t)(CONV_SPB + 1) * (CONV_PB + 1) * sizeof(double);
+// CONV_SPB spectra per CTA (the Gaussian weights are computed once for them) x CONV_PB trapezoid
+// segments per CTA are template parameters; (8, 1024) measured best on B200 (SR_CONV_CFG)
 
 // per channel: segments [i0, i1) of the trapezoid rule = hi-res points i0..i1 inside the window
 __global__ void k_convolve_windows(const double* __restrict__ x, long n_pts,
@@ -42,6 +42,7 @@ __global__ void k_convolve_windows(const double* __restrict__ x, long n_pts,
 // CTA, and the per-block sums go to partial[channel][block][spectrum]; k_convolve_reduce adds the
 // blocks in a fixed order, so the result does not depend on scheduling (no atomics).
 //   sum_i hd_i (y_i g_i + y_{i+1} g_{i+1})  =  sum_p y_p g_p (hd_{p-1} [p > s0] + hd_p [p < s1])
+template <int CONV_SPB, int CONV_PB>
 __global__ void __launch_bounds__(CONV_NT) k_convolve_lowres(
     const double* __restrict__ x, long n_pts, const double* __restrict__ spec, int n_spec,
     const double* __restrict__ centre, const double* __restrict__ width, int n_chan,
@@ -60,14 +61,23 @@ __global__ void __launch_bounds__(CONV_NT) k_convolve_lowres(
     for (int c = 0; c < n_chan; c++)
         any = any || min(win[2 * c + 1], bend) > max(win[2 * c], bstart);
     if (!any) return;                                  // uniform over the CTA
-    for (int i = threadIdx.x; i < np; i += CONV_NT) xs[i] = x[bstart + i];
+    // asynchronous global -> shared copies (LDGSTS): every thread has all its 8-byte copies in
+    // flight at once instead of one load per dependent shared-memory store
+    auto cp8 = [](double* dst, const double* src) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+    };
+    for (int i = threadIdx.x; i < np; i += CONV_NT) cp8(xs + i, x + bstart + i);
 #pragma unroll
     for (int q = 0; q < CONV_SPB; q++) {
-        const bool on = sp0 + q < n_spec;
-        const double* __restrict__ y = spec + (size_t)(on ? sp0 + q : sp0) * n_pts + bstart;
-        for (int i = threadIdx.x; i < np; i += CONV_NT)
-            ys[q * (CONV_PB + 1) + i] = on ? __ldcs(y + i) : 0.0;
+        if (sp0 + q < n_spec) {
+            const double* __restrict__ y = spec + (size_t)(sp0 + q) * n_pts + bstart;
+            for (int i = threadIdx.x; i < np; i += CONV_NT) cp8(ys + q * (CONV_PB + 1) + i, y + i);
+        } else {
+            for (int i = threadIdx.x; i < np; i += CONV_NT) ys[q * (CONV_PB + 1) + i] = 0.0;
+        }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     for (int c = 0; c < n_chan; c++) {
         const long s0l = max(win[2 * c], bstart), s1l = min(win[2 * c + 1], bend);
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(CONV_NT) k_convolve_lowres(
 }
 
 __global__ void k_convolve_reduce(const double* __restrict__ partial, const long* __restrict__ win,
-                                  int n_spec, int n_chan, int n_blocks, long n_pts,
+                                  int n_spec, int n_chan, int n_blocks, long n_pts, int CONV_PB,
                                   double* __restrict__ out) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
     if (s >= n_spec) return;
@@ -131,7 +141,10 @@ int sr_convolve_lowres_dev(const double* grid_dev, long n_pts, const double* spe
         n_spec < 1 || n_chan < 1 || !(n_sigma > 0.0))
         return sr::fail(SR_ERR_ARG, "sr_convolve_lowres_dev: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    const int n_blocks = (int)std::max<long>(1, (n_pts - 1 + CONV_PB - 1) / CONV_PB);
+    static const int cfg = getenv("SR_CONV_CFG") ? atoi(getenv("SR_CONV_CFG")) : 0;   // tuning aid
+    const int spb = (cfg == 1 || cfg == 3) ? 4 : 8;
+    const int pb = cfg == 2 ? 512 : (cfg == 3 ? 2048 : 1024);
+    const int n_blocks = (int)std::max<long>(1, (n_pts - 1 + pb - 1) / pb);
     const int slab = std::min(n_spec, CONV_SLAB);
     // stream-ordered scratch: channel windows + partial sums [n_chan][n_blocks][slab]
     long* win = nullptr;
@@ -143,19 +156,28 @@ int sr_convolve_lowres_dev(const double* grid_dev, long n_pts, const double* spe
         cudaFreeAsync(win, st);
         return sr::fail(SR_ERR_CUDA, "sr_convolve_lowres_dev: %s", cudaGetErrorString(e));
     }
+    auto launch = [&](auto kern, int ns, const double* sp, dim3 grid) -> int {
+        const size_t smem = (size_t)(spb + 1) * (pb + 1) * sizeof(double);
+        SR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SR_LAUNCH(kern, grid, CONV_NT, smem, st, grid_dev, n_pts, sp, ns, centre_dev, width_dev, n_chan,
+                  win, n_blocks, partial);
+        return SR_OK;
+    };
     auto body = [&]() -> int {
-        SR_CUDA(cudaFuncSetAttribute(k_convolve_lowres, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)CONV_SMEM));
         SR_LAUNCH(k_convolve_windows, (n_chan + 63) / 64, 64, 0, st, grid_dev, n_pts, centre_dev,
                   width_dev, n_chan, n_sigma, win);
         for (int s0 = 0; s0 < n_spec; s0 += slab) {
             const int ns = std::min(slab, n_spec - s0);
-            dim3 grid((unsigned)n_blocks, (unsigned)((ns + CONV_SPB - 1) / CONV_SPB));
-            SR_LAUNCH(k_convolve_lowres, grid, CONV_NT, CONV_SMEM, st, grid_dev, n_pts,
-                      spec_dev + (size_t)s0 * n_pts, ns, centre_dev, width_dev, n_chan, win,
-                      n_blocks, partial);
+            dim3 grid((unsigned)n_blocks, (unsigned)((ns + spb - 1) / spb));
+            const double* sp = spec_dev + (size_t)s0 * n_pts;
+            int rc;
+            if (cfg == 1) rc = launch(k_convolve_lowres<4, 1024>, ns, sp, grid);
+            else if (cfg == 2) rc = launch(k_convolve_lowres<8, 512>, ns, sp, grid);
+            else if (cfg == 3) rc = launch(k_convolve_lowres<4, 2048>, ns, sp, grid);
+            else rc = launch(k_convolve_lowres<8, 1024>, ns, sp, grid);
+            if (rc) return rc;
             SR_LAUNCH(k_convolve_reduce, dim3((unsigned)((ns + 127) / 128), (unsigned)n_chan), 128, 0,
-                      st, partial, win, ns, n_chan, n_blocks, n_pts, out_dev + (size_t)s0 * n_chan);
+                      st, partial, win, ns, n_chan, n_blocks, n_pts, pb, out_dev + (size_t)s0 * n_chan);
         }
         return SR_OK;
     };

@@ -134,12 +134,27 @@ def batch(n_pix=int(os.environ.get("SR_PROF_NPIX", "1500")), jac=False):
                  t15 - t1, e0.elapsed_time(e1) * 1e-3, n_b / (t2 - t0)))
 
 
+def conv(n_spec=512):
+    g = S.spectral_grid(2850.0, 3450.0)
+    gdev = torch.as_tensor(g, device="cuda")
+    torch.manual_seed(1)
+    spec = torch.rand((n_spec, len(g)), dtype=torch.float64, device="cuda")
+    c = torch.as_tensor(np.linspace(g[0] + 10.0, g[-1] - 10.0, 36), device="cuda")
+    w = torch.as_tensor(np.full(36, 6.2), device="cuda")
+    out = engine.convolve_lowres(gdev, spec, c, w)
+    ms = timed(lambda: engine.convolve_lowres(gdev, spec, c, w, out=out), 5)
+    print("conv %d spectra: %s ms -> %.2f TB/s (checksum %.12e)"
+          % (n_spec, ["%.3f" % m for m in ms], n_spec * len(g) * 8 / (min(ms) * 1e-3) / 1e12, float(out.sum())))
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "k1"
     if mode == "k1":
         k1()
     elif mode == "k1b":
         k1b()
+    elif mode == "conv":
+        conv()
     elif mode == "batch":
         batch()
     elif mode == "batchjac":
