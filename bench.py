@@ -340,6 +340,35 @@ def run_ours(args):
                                   "k_core_eval and k_voigt_tile"}}
     del cell_buf
 
+    # ---- K1 on a million-line list, sharded by line with an all_reduce of the partial spectra
+    # (BASELINE configs[4]); the line table and the per-rank line set are set-up
+    n_big = 20000 if args.small else 1000000
+    big = S.line_table(n_big, grid[0], grid[-1], n_levels=N_LEVELS, seed=20067)
+    from spectrobot_b200 import parallel as _par
+    b0_, b1_ = _par.shard_lines(n_big, rank, world)
+    ls_big = engine.LineSet(_par.subset_lines(big, b0_, b1_), grid, S.CH4_MM, N_LEVELS)
+    xs_big = torch.empty((1, N_LEVELS, 3, n_grid), dtype=torch.float64, device="cuda")
+    big_each = []
+    for i in range(4):
+        barrier()
+        ev0.record()
+        ls_big.gcoeff_cells([[0.02, 155.0]], out=xs_big, check_status=(i == 0))
+        _par.allreduce_spectra(xs_big)
+        ev1.record()
+        barrier()
+        if i > 0:
+            big_each.append(ev0.elapsed_time(ev1))
+    big_ms = max_over_ranks(float(np.median(big_each)))
+    voigt_sharded = {"metric": "Voigt line*gridpoint evals/s, 1e6-line list sharded by line",
+                     "value": n_big * 13010.0 / (big_ms * 1e-3), "unit": "evals/s", "lines": n_big,
+                     "lines_per_rank": int(b1_ - b0_), "ms": big_ms, "scaling": "strong",
+                     "allreduce_bytes": int(xs_big.numel() * 8) if world > 1 else 0,
+                     "roofline_frac_fp64": 15.0 * n_big * 13010.0 / (big_ms * 1e-3) / (world * fp64_peak),
+                     "path": "k_voigt_tile on the rank's lines, then NCCL all_reduce(SUM, fp64) of the "
+                             "[12][3][n_grid] partial spectra"}
+    ls_big.close()
+    del ls_big, xs_big, big
+
     # ---- K2: LUT build (cells sharded over ranks, all_gather) --------------------------------
     from spectrobot_b200 import parallel
     my_cells = parallel.shard_cells(n_cells, rank, world)
@@ -578,7 +607,7 @@ def run_ours(args):
                                "note": "2 flop x %d non-zero LUT rows x 4 cells per (step, point); "
                                        "DFMA rate measured live by sr_fp64_peak" % rows_cell}},
         "jacobian": jacobian,
-        "batch": batch, "voigt": voigt, "lut_build": lut_build,
+        "batch": batch, "voigt": voigt, "voigt_sharded": voigt_sharded, "lut_build": lut_build,
         "gpu_launches": int(launches), "clocks": sampler.summary(),
     }
     if rank == 0 and not args.no_cpu_baseline:
