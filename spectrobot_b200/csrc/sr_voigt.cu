@@ -12,7 +12,7 @@
 //   line table   SoA doubles/ints, sorted by (group = (upper set, lower set), centre index)
 //   LineCell     [cell][line] 128 B: widths, region boundaries, G coefficients of one (line, cell)
 //   LineRec      [cell][line] 112 B: the far-wing (region 1) form of the same line in ABSOLUTE grid
-//                coordinates; contiguous runs are TMA-bulk-copied into shared memory
+//                coordinates; read once per (tile, candidate), compacted into shared memory
 //   core         [cell][line][CORE_STRIDE] K(x,y) of the window points il..ir (regions 2/3/4)
 //   out          [cell][set][ctype][n_grid] doubles, each element written exactly once
 //
