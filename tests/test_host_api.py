@@ -331,3 +331,39 @@ def test_alt_triangle_matches_reference_loop():
     assert np.array_equal(smm.alt_triangle(z, 900., node_lo=700., last=True).mask, ref(z, 900., node_lo=700., last=True))
     assert np.array_equal(smm.alt_triangle(z, 505., node_lo=300., node_up=700.).mask, ref(z, 505., 300., 700.))
     assert np.array_equal(smm.alt_triangle(z, 500., step=200.).mask, ref(z, 500., 300., 700.))
+
+
+def test_retrieval_parameter_space_host_logic():
+    """RetParam / LinearProfile_1D_new / BayesSet (smm:161-296, 442-489, 600-656): the triangle
+    masks form a partition of unity between the first and last node, profile() reproduces a
+    profile that is linear between the nodes, update_par keeps positive parameters positive and
+    build_jacobian stacks the stored per-pixel derivative spectra column by column."""
+    z = np.arange(0.0, 1501.0, 10.0)
+    nodes = [200., 450., 700., 1100.]
+    vals = [1.0e-2, 1.4e-2, 0.9e-2, 2.0e-2]
+    prof = smm.LinearProfile_1D_new('CH4', z, nodes, vals, [1e-3] * 4)
+    tot = sum(p.maskgrid.mask for p in prof.set)
+    assert np.allclose(tot, 1.0, atol=1e-15)
+    got = prof.profile().values['vmr']
+    assert np.allclose(got, np.interp(z, nodes, vals), rtol=1e-14)
+    assert prof.profile().values['CH4'] is not None and prof.keys() == nodes
+    assert prof.check_involved(200., dict(alt=[500., 900.])) is False      # LOS entirely above node 2
+    assert prof.check_involved(450., dict(alt=[500., 900.])) is True
+    bs = smm.BayesSet('t')
+    bs.add_set(prof)
+    assert bs.n_tot == 4 and [p.key for p in bs.params()] == nodes
+    assert np.array_equal(bs.VCM_apriori(), np.diag([1e-6] * 4))
+    p0 = bs.params()[0]
+    p0.update_par(-5.0e-2)                                                # would go negative: halved
+    assert 0.0 < p0.value < 1.0e-2 and p0.old_values == [1.0e-2]
+    grid = spcl.SpectralGrid(np.linspace(3000., 3003., 4), units='cm_1')
+    for q, par in enumerate(bs.params()):
+        for k in range(3):                                                # three pixels
+            par.store_deriv(spcl.SpectralIntensity(np.full(4, 10.0 * q + k), grid), num=k)
+    J = bs.build_jacobian()
+    assert J.shape == (12, 4) and np.array_equal(J[:, 2], np.repeat([20., 21., 22.], 4))
+    masks = [np.array([1, 0, 1, 1]), np.ones(4), np.zeros(4)]
+    assert bs.build_jacobian(masks).shape == (7, 4)
+    assert bs.n_used_par() == 0
+    bs.params()[1].set_used()
+    assert bs.n_used_par() == 1
