@@ -102,11 +102,36 @@ def gather_rows(local, n_total, rank, n_ranks):
     return torch.cat([p[:e - b] for p, (b, e) in zip(parts, sizes)], dim=0)
 
 
-def allreduce_spectra(t):
-    """In-place sum of partial cross-section spectra over the ranks (line-sharded K1)."""
+def fed_rows(tab, n_sets):
+    """(set, ctype) rows of the [n_sets][3] cross-section block that the line list can feed: a
+    line adds to sp_emission / ind_emission of its upper set and to absorption of its lower set
+    (spect_classes.py:1304-1313); every other row is identically zero on every rank."""
+    up, lo = np.asarray(tab["up_set"]), np.asarray(tab["lo_set"])
+    ok = (up >= 0) & (lo >= 0)
+    rows = set()
+    for u in np.unique(up[ok]):
+        rows.update((int(u) * 3 + 0, int(u) * 3 + 1))
+    for l in np.unique(lo[ok]):
+        rows.add(int(l) * 3 + 2)
+    return sorted(r for r in rows if r < 3 * n_sets)
+
+
+def allreduce_spectra(t, rows=None):
+    """In-place sum of partial cross-section spectra [n_cells][n_sets][3][n_grid] over the ranks
+    (line-sharded K1).  rows: the (set*3 + ctype) rows that can be non-zero (fed_rows); only those
+    cross NVLink (packed into one contiguous buffer), the others stay zero."""
+    import torch
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return t
+    if rows is None or len(rows) >= t.shape[1] * t.shape[2]:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+    flat = t.view(t.shape[0], t.shape[1] * t.shape[2], t.shape[3])
+    idx = torch.as_tensor(rows, dtype=torch.long, device=t.device)
+    packed = flat.index_select(1, idx)
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+    flat.index_copy_(1, idx, packed)
     return t
 
 
@@ -126,4 +151,4 @@ def gcoeff_cells_line_sharded(tab, grid, MM, n_sets, PTcouples):
     ls = engine.LineSet(subset_lines(tab, b, e), grid, MM, n_sets)
     out = ls.gcoeff_cells(PTcouples)
     ls.close()
-    return allreduce_spectra(out)
+    return allreduce_spectra(out, rows=fed_rows(tab, n_sets))

@@ -27,6 +27,12 @@ def test_shard_arithmetic():
     assert list(sub["freq"]) == [2.0, 3.0, 4.0] and sub["n_sets"] == 3 and len(sub["level_energies"]) == 3
 
 
+def test_fed_rows():
+    tab = dict(up_set=np.array([1, 1, 2, -1, 3]), lo_set=np.array([0, 0, 0, 0, -1]))
+    # lines 0-2 are linked: upper sets 1, 2 -> sp/ind rows; lower set 0 -> absorption row
+    assert parallel.fed_rows(tab, 4) == [2, 3, 4, 6, 7]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -62,6 +68,15 @@ def _worker(rank, n, port, q):
         part = contrib[b:e].sum(dim=0)
         parallel.allreduce_spectra(part)
         ok_sum = bool(torch.allclose(part, contrib.sum(dim=0), rtol=1e-14, atol=0))
+        # same with the rows the line list can feed (the others are zero on every rank)
+        rows_fed = [0, 1, 5]
+        mask = torch.zeros(6, dtype=torch.float64)
+        mask[rows_fed] = 1.0
+        sparse = contrib.reshape(11, 1, 6, 16) * mask[None, None, :, None]
+        part4 = sparse[b:e].sum(dim=0).reshape(1, 2, 3, 16).clone()
+        parallel.allreduce_spectra(part4, rows=rows_fed)
+        ok_sum = ok_sum and bool(torch.allclose(part4, sparse.sum(dim=0).reshape(1, 2, 3, 16),
+                                                rtol=1e-14, atol=0))
         q.put((rank, ok_lut, ok_rows, ok_sum))
     finally:
         dist.destroy_process_group()
