@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(256, MINB) k_los_layers_jac(const __grid_const
     double D[NP];
 #pragma unroll
     for (int q = 0; q < NP; q++) D[q] = 0.0;
-    const int ns = r.n_steps[l], solo = r.solo;
+    const int ns = min(max(r.n_steps[l], 0), r.n_steps_max), solo = r.solo;   // (table width)
     const long ls = r.lay_stride;
     const size_t lay0 = (size_t)l * r.n_steps_max * ls + p;
     const double* __restrict__ tp = r.tau + lay0;
