@@ -912,6 +912,58 @@ def FOV_integr_1D(radtrans, pixel_rot=0.0):
     return integ_rad
 
 
+def make_group_observations(pixels, alt_step=50., alt_first_los=None):
+    """A ladder of lines of sight with a fixed step in tangent altitude that stands in for the
+    pixels' own LOS (smm:3290-3338): pixels are assumed to share the cube and to have close
+    tangent latitude / longitude / SZA; the ladder runs from alt_first_los (at most the lowest LOS
+    of the lowest pixel) to past the highest LOS of the highest pixel, at the mean tangent
+    latitude / longitude, seen from the first pixel's spacecraft position."""
+    pixels.sort(key=lambda x: x.limb_tg_alt)
+    sim_LOSs = [pix.LOS() for pix in pixels]
+    first_los = pixels[0].low_LOS()
+    if first_los.get_tangent_altitude() > pixels[0].limb_tg_alt:
+        first_los = pixels[0].up_LOS()
+    last_los = pixels[-1].up_LOS()
+    if last_los.get_tangent_altitude() < pixels[-1].limb_tg_alt:
+        last_los = pixels[-1].low_LOS()
+    alt_range = [first_los.get_tangent_altitude(), last_los.get_tangent_altitude()]
+    if alt_first_los is None or alt_first_los > alt_range[0]:
+        alt_first_los = alt_range[0]
+    mea_lat = np.mean([pi.limb_tg_lat for pi in pixels])
+    mea_lon = np.mean([pi.limb_tg_lon for pi in pixels])
+    mea_sza = np.mean([pix.limb_tg_sza for pix in pixels])
+    ssp = pixels[0].sub_solar_point()
+    spacecraft = sim_LOSs[0].starting_point
+    alts = np.arange(alt_first_los, alt_range[1] + alt_step, alt_step)
+    LOS_ok = [sbm.LineOfSight(spacecraft, sbm.Coords([mea_lat, mea_lon, alt], s_ref='Spherical'))
+              for alt in alts]
+    return LOS_ok, alts, [ssp] * len(alts), [mea_sza] * len(alts)
+
+
+def make_radtran_spline(alts, radtrans):
+    """Function of the tangent altitude that interpolates the simulated LOS spectra
+    (smm:3377-3396): the same RectBivariateSpline(alts, grid, spectra, kx=2, ky=2) the reference
+    builds, evaluated on the spectra's own grid."""
+    from scipy.interpolate import RectBivariateSpline as spline2D
+    alts = np.array(alts)
+    spectrums = np.array([rad.spectrum for rad in radtrans])
+    grid = radtrans[0].spectral_grid.grid
+    radsample = radtrans[0]
+    intens_spl = spline2D(alts, grid, spectrums, kx=2, ky=2)
+
+    def radtran_alt(x):
+        res_spe = copy.deepcopy(radsample)
+        res_spe.spectrum = np.array(intens_spl(x, grid)).reshape(-1)
+        return res_spe
+
+    return radtran_alt
+
+
+def _pixel_los_altitudes(pix):
+    return np.array([lin.get_tangent_point().Spherical()[2]
+                     for lin in (pix.low_LOS(), pix.LOS(), pix.up_LOS())])
+
+
 def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_opt=dict(),
              save_hires=True, save_lowres=True, LUTopt=dict(), test=False, use_tangent_sza=False,
              group_observations=False, invert_LOS_direction=False, nome_inv='1',
@@ -922,8 +974,9 @@ def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_
     Curtis-Godson through the `curgods` drop-in) -> ONE library call for all LOS
     (engine.los_rt_lut_lowres), reduced to the instrument channels on the device.
     Returns (sims, radtrans, single_rads): `radtrans` = {LOS tag: low-res SpectralIntensity};
-    `sims` = per pixel the FOV integral of its three LOS (FOV_integr_1D, :3273-3277; the
-    group_observations altitude-ladder variant is not implemented); single_rads = {} (per-gas
+    `sims` = per pixel the FOV integral of its three LOS (FOV_integr_1D, :3273-3277), taken from
+    the pixel's own LOS or, with group_observations, from the altitude ladder of
+    make_group_observations through make_radtran_spline (:3263-3272); single_rads = {} (per-gas
     tracking is not part of the hot path)."""
     import torch
     pixels = sorted(pixels, key=lambda p: p.limb_tg_alt)
@@ -939,9 +992,13 @@ def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_
     PT = calc_PT_couples_atmosphere(lines, gases, planet.atmosphere, **LUTopt)
     LUTS = check_and_build_allluts(inputs, sp_gri, lines, gases, PTcouples=PT, LUTopt=LUTopt)
 
-    sim_LOSs = []
-    for pix in pixels:
-        sim_LOSs += [pix.low_LOS(), pix.LOS(), pix.up_LOS()]
+    if group_observations:   # altitude ladder instead of the pixels' own LOS (smm:3056-3058)
+        sim_LOSs, alts_sim, _, _ = make_group_observations(pixels, alt_step=alt_step_sims,
+                                                           alt_first_los=alt_first_los)
+    else:
+        sim_LOSs = []
+        for pix in pixels:
+            sim_LOSs += [pix.low_LOS(), pix.LOS(), pix.up_LOS()]
     for num, los in enumerate(sim_LOSs):
         los.tag = 'LOS{:03d}'.format(num)
     # geometry + radtran steps of ALL lines of sight in one library call (sr_los_steps_build); the
@@ -958,9 +1015,17 @@ def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_
     radtrans_out = dict()
     for i, los in enumerate(sim_LOSs):
         radtrans_out[los.tag] = spcl.SpectralIntensity(low[i], obs.spectral_grid)
-    sims = [spcl.SpectralIntensity(fov_integrate(low[3 * k:3 * k + 3],
-                                                 getattr(pixels[k], 'pixel_rot', 0.0) or 0.0),
-                                   obs.spectral_grid) for k in range(len(pixels))]
+    if group_observations:   # spectra at the pixels' LOS altitudes from the ladder (smm:3263-3272)
+        radtran_spline = make_radtran_spline(alts_sim, [radtrans_out[los.tag] for los in sim_LOSs])
+        sims = []
+        for pix in pixels:
+            three = np.array([radtran_spline(al).spectrum for al in _pixel_los_altitudes(pix)])
+            sims.append(spcl.SpectralIntensity(
+                fov_integrate(three, getattr(pix, 'pixel_rot', 0.0) or 0.0), obs.spectral_grid))
+    else:
+        sims = [spcl.SpectralIntensity(fov_integrate(low[3 * k:3 * k + 3],
+                                                     getattr(pixels[k], 'pixel_rot', 0.0) or 0.0),
+                                       obs.spectral_grid) for k in range(len(pixels))]
     if isinstance(inputs, dict) and inputs.get('out_dir') and save_lowres:
         with open(os.path.join(inputs['out_dir'], 'lowres_radtran_{}.pic'.format(nome_inv)), 'wb') as f:
             pickle.dump([sims, radtrans_out], f, protocol=-1)
@@ -999,9 +1064,13 @@ def inversion_fast_limb(inputs, planet, lines, bayes_set, pixels, wn_range=None,
     PT = calc_PT_couples_atmosphere(lines, gases, planet.atmosphere, **LUTopt)
     LUTS = check_and_build_allluts(inputs, sp_gri, lines, gases, PTcouples=PT, LUTopt=LUTopt)
 
-    sim_LOSs = []
-    for pix in pixels:
-        sim_LOSs += [pix.low_LOS(), pix.LOS(), pix.up_LOS()]
+    if group_observations:
+        sim_LOSs, alts_sim, _, _ = make_group_observations(pixels, alt_step=alt_step_sims,
+                                                           alt_first_los=alt_first_los)
+    else:
+        sim_LOSs = []
+        for pix in pixels:
+            sim_LOSs += [pix.low_LOS(), pix.LOS(), pix.up_LOS()]
     for num, los in enumerate(sim_LOSs):
         los.tag = 'LOS{:02d}'.format(num)
     # geometry, radtran steps and derivative columns of all LOS on the device, one call per
@@ -1031,13 +1100,23 @@ def inversion_fast_limb(inputs, planet, lines, bayes_set, pixels, wn_range=None,
             derivs[(los.tag, par.nameset, par.key)] = spcl.SpectralIntensity(jlow[i, q],
                                                                             obs.spectral_grid)
     sims = []
+    if group_observations:   # radiances and derivatives interpolated from the ladder (:2904-2929)
+        radtran_spline = make_radtran_spline(alts_sim, [radtrans_out[los.tag] for los in sim_LOSs])
+        deriv_splines = [make_radtran_spline(alts_sim, [derivs[(los.tag, par.nameset, par.key)]
+                                                        for los in sim_LOSs]) for par in pars]
     for k, pix in enumerate(pixels):
         rot = getattr(pix, 'pixel_rot', 0.0) or 0.0
-        sims.append(spcl.SpectralIntensity(fov_integrate(low[3 * k:3 * k + 3], rot),
-                                           obs.spectral_grid))
+        if group_observations:
+            alts_pix = _pixel_los_altitudes(pix)
+            three = np.array([radtran_spline(al).spectrum for al in alts_pix])
+            ders = [np.array([spl(al).spectrum for al in alts_pix]) for spl in deriv_splines]
+        else:
+            three = low[3 * k:3 * k + 3]
+            ders = [jlow[3 * k:3 * k + 3, q] for q in range(len(pars))]
+        sims.append(spcl.SpectralIntensity(fov_integrate(three, rot), obs.spectral_grid))
         for q, par in enumerate(pars):
-            der = fov_integrate(jlow[3 * k:3 * k + 3, q], rot)
-            par.store_deriv(spcl.SpectralIntensity(der, obs.spectral_grid), num=k)
+            par.store_deriv(spcl.SpectralIntensity(fov_integrate(ders[q], rot), obs.spectral_grid),
+                            num=k)
     for par in pars:
         par.hires_deriv = None
     if isinstance(inputs, dict) and inputs.get('out_dir') and save_lowres:

@@ -330,3 +330,30 @@ def test_device_step_builder_matches_oracle(world, oracle):
                 assert np.allclose(steps.tvib[m, j, l, :n], r["tvib"][m][j], **tol), (l, m, j)
         assert np.allclose(dfrac[l, :n], np.array(r["dfrac"]), rtol=1e-9, atol=1e-14)
         assert np.all(steps.column[:, l, n:] == 0.0) and np.all(steps.temp[l, n:] == 100.0)
+
+
+def test_radtrans_group_observations(world):
+    """radtrans(group_observations=True): the pixels' spectra interpolated from a ladder of
+    simulated LOS (smm:3056-3058, 3263-3272) agree with the per-pixel simulation to the accuracy of
+    the quadratic spline on a 12 km ladder, and equal the literal spline + FOV recomputation."""
+    smm, S, planet, sp = world["smm"], world["S"], world["planet"], world["sp"]
+    centres = np.linspace(2997.0, 3003.0, 7)
+    widths = np.full(7, 0.6)
+    inputs = dict(n_split=1, cart_LUTS=None, out_dir=None, n_threads=8)
+    LUTopt = dict(pres_step_log=1.0, temp_step=5.0)
+    opt = dict(max_T_variation=5., max_Plog_variation=1.)
+    mk = lambda: S.vims_pixels([450.0, 520.0, 700.0], channels=centres, widths=widths)   # noqa: E731
+    sims, rt, _ = smm.radtrans(inputs, planet, world["lines"], mk(), sp_gri=sp, radtran_opt=opt,
+                               LUTopt=dict(LUTopt))
+    pix_g = mk()
+    sims_g, rt_g, _ = smm.radtrans(inputs, planet, world["lines"], pix_g, sp_gri=sp, radtran_opt=opt,
+                                   LUTopt=dict(LUTopt), group_observations=True, alt_step_sims=12.,
+                                   alt_first_los=400.)
+    assert len(sims_g) == 3 and len(rt_g) > 20
+    for a, b in zip(sims, sims_g):
+        assert rel_err(b.spectrum, a.spectrum) < 1e-2
+    pix_s = sorted(pix_g, key=lambda p: p.limb_tg_alt)
+    loss, alts, _, _ = smm.make_group_observations(pix_s, alt_step=12., alt_first_los=400.)
+    spl = smm.make_radtran_spline(alts, [rt_g['LOS%03d' % i] for i in range(len(alts))])
+    three = np.array([spl(al).spectrum for al in smm._pixel_los_altitudes(pix_s[1])])
+    assert np.allclose(sims_g[1].spectrum, smm.fov_integrate(three, 0.0), rtol=1e-13)

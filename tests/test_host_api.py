@@ -367,3 +367,26 @@ def test_retrieval_parameter_space_host_logic():
     assert bs.n_used_par() == 0
     bs.params()[1].set_used()
     assert bs.n_used_par() == 1
+
+
+def test_group_observations_ladder_and_spline():
+    """make_group_observations (smm:3290-3338) and make_radtran_spline (smm:3377-3396)."""
+    pixels = S.vims_pixels([700.0, 450.0, 575.0], channels=np.linspace(2997., 3003., 7),
+                           widths=np.full(7, 0.6))
+    loss, alts, ssps, fszas = smm.make_group_observations(pixels, alt_step=50., alt_first_los=300.)
+    assert [p.limb_tg_alt for p in pixels] == [450.0, 575.0, 700.0]           # sorted in place
+    lo = pixels[0].low_LOS().get_tangent_altitude()
+    hi = pixels[-1].up_LOS().get_tangent_altitude()
+    assert alts[0] == 300.0 and alts[0] <= lo and alts[-1] >= hi and np.allclose(np.diff(alts), 50.)
+    assert len(loss) == len(alts) == len(ssps) == len(fszas)
+    for los, a in zip(loss, alts):
+        assert abs(los.get_tangent_altitude() - a) < 1e-6
+    loss2, alts2, _, _ = smm.make_group_observations(pixels, alt_step=50., alt_first_los=900.)
+    assert abs(alts2[0] - lo) < 1e-9                                           # capped at the lowest LOS
+    grid = spcl.SpectralGrid(np.linspace(2997., 3003., 7), units='cm_1')
+    za = np.array([300., 350., 400., 450., 500.])
+    rads = [spcl.SpectralIntensity((1.0 + 0.01 * z) * np.arange(1., 8.), grid) for z in za]
+    spl = smm.make_radtran_spline(za, rads)
+    for z, r in zip(za, rads):
+        assert np.allclose(spl(z).spectrum, r.spectrum, rtol=1e-12)
+    assert np.allclose(spl(437.0).spectrum, (1.0 + 4.37) * np.arange(1., 8.), rtol=1e-12)  # linear in z
