@@ -984,14 +984,6 @@ def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_
         if wn_range is None:
             raise ValueError('radtrans needs wn_range or sp_gri')
         sp_gri = prepare_spe_grid(wn_range).spectral_grid
-    LUTopt = dict(LUTopt)
-    if 'max_pres' not in LUTopt:
-        LUTopt['max_pres'] = max(planet.atmosphere.calc(p.low_LOS().get_tangent_point(), 'pres')
-                                 for p in pixels)
-    gases = list(planet.gases.values())
-    PT = calc_PT_couples_atmosphere(lines, gases, planet.atmosphere, **LUTopt)
-    LUTS = check_and_build_allluts(inputs, sp_gri, lines, gases, PTcouples=PT, LUTopt=LUTopt)
-
     if group_observations:   # altitude ladder instead of the pixels' own LOS (smm:3056-3058)
         sim_LOSs, alts_sim, _, _ = make_group_observations(pixels, alt_step=alt_step_sims,
                                                            alt_first_los=alt_first_los)
@@ -1001,6 +993,17 @@ def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_
             sim_LOSs += [pix.low_LOS(), pix.LOS(), pix.up_LOS()]
     for num, los in enumerate(sim_LOSs):
         los.tag = 'LOS{:03d}'.format(num)
+    LUTopt = dict(LUTopt)
+    if 'max_pres' not in LUTopt:   # the deepest point any simulated LOS reaches (the reference looks
+        # at the pixels' low LOS only, :3010-3024, and stops with 'Extrapolating in P' when the
+        # ladder starts below them)
+        LUTopt['max_pres'] = max([planet.atmosphere.calc(p.low_LOS().get_tangent_point(), 'pres')
+                                  for p in pixels] +
+                                 [planet.atmosphere.calc(sim_LOSs[0].get_tangent_point(), 'pres')])
+    gases = list(planet.gases.values())
+    PT = calc_PT_couples_atmosphere(lines, gases, planet.atmosphere, **LUTopt)
+    LUTS = check_and_build_allluts(inputs, sp_gri, lines, gases, PTcouples=PT, LUTopt=LUTopt)
+
     # geometry + radtran steps of ALL lines of sight in one library call (sr_los_steps_build); the
     # per-LOS host methods calc_atm_intersections / calc_radtran_steps stay available on sbm
     tables = los_step_tables_device(sim_LOSs, planet, **radtran_opt)
@@ -1056,14 +1059,6 @@ def inversion_fast_limb(inputs, planet, lines, bayes_set, pixels, wn_range=None,
     for gas in bayes_set.sets.keys():
         if gas in planet.gases:
             planet.gases[gas].add_clim(bayes_set.sets[gas].profile())
-    LUTopt = dict(LUTopt)
-    if 'max_pres' not in LUTopt:
-        LUTopt['max_pres'] = max(planet.atmosphere.calc(p.low_LOS().get_tangent_point(), 'pres')
-                                 for p in pixels)
-    gases = list(planet.gases.values())
-    PT = calc_PT_couples_atmosphere(lines, gases, planet.atmosphere, **LUTopt)
-    LUTS = check_and_build_allluts(inputs, sp_gri, lines, gases, PTcouples=PT, LUTopt=LUTopt)
-
     if group_observations:
         sim_LOSs, alts_sim, _, _ = make_group_observations(pixels, alt_step=alt_step_sims,
                                                            alt_first_los=alt_first_los)
@@ -1073,6 +1068,15 @@ def inversion_fast_limb(inputs, planet, lines, bayes_set, pixels, wn_range=None,
             sim_LOSs += [pix.low_LOS(), pix.LOS(), pix.up_LOS()]
     for num, los in enumerate(sim_LOSs):
         los.tag = 'LOS{:02d}'.format(num)
+    LUTopt = dict(LUTopt)
+    if 'max_pres' not in LUTopt:   # deepest point of any simulated LOS (see radtrans)
+        LUTopt['max_pres'] = max([planet.atmosphere.calc(p.low_LOS().get_tangent_point(), 'pres')
+                                  for p in pixels] +
+                                 [planet.atmosphere.calc(sim_LOSs[0].get_tangent_point(), 'pres')])
+    gases = list(planet.gases.values())
+    PT = calc_PT_couples_atmosphere(lines, gases, planet.atmosphere, **LUTopt)
+    LUTS = check_and_build_allluts(inputs, sp_gri, lines, gases, PTcouples=PT, LUTopt=LUTopt)
+
     # geometry, radtran steps and derivative columns of all LOS on the device, one call per
     # retrieved gas (the step tables themselves are identical between the calls)
     tables = dict()

@@ -357,3 +357,31 @@ def test_radtrans_group_observations(world):
     spl = smm.make_radtran_spline(alts, [rt_g['LOS%03d' % i] for i in range(len(alts))])
     three = np.array([spl(al).spectrum for al in smm._pixel_los_altitudes(pix_s[1])])
     assert np.allclose(sims_g[1].spectrum, smm.fov_integrate(three, 0.0), rtol=1e-13)
+
+
+def test_inversion_fast_limb_group_observations(world):
+    """The ladder variant of the forward + Jacobian evaluation (smm:2904-2929): radiances and
+    derivative spectra interpolated in altitude agree with the per-pixel evaluation to the accuracy
+    of the spline, and the Jacobian keeps its shape."""
+    smm, S = world["smm"], world["S"]
+    planet = S.titan_planet(world["tab"]["level_energies"], nonlte=False)
+    sp = world["sp"]
+    centres = np.linspace(2997.0, 3003.0, 7)
+    widths = np.full(7, 0.6)
+    inputs = dict(n_split=1, cart_LUTS=None, out_dir=None, n_threads=8)
+    LUTopt = dict(pres_step_log=1.0, temp_step=5.0)
+    opt = dict(max_T_variation=5., max_Plog_variation=1.)
+    mk = lambda: S.vims_pixels([470.0, 650.0], channels=centres, widths=widths)   # noqa: E731
+    bs_a, bs_b = _bayes(smm, planet), _bayes(smm, planet)
+    sims_a, _, _ = smm.inversion_fast_limb(inputs, planet, world["lines"], bs_a, mk(), sp_gri=sp,
+                                           radtran_opt=opt, LUTopt=dict(LUTopt))
+    sims_b, rt_b, _ = smm.inversion_fast_limb(inputs, planet, world["lines"], bs_b, mk(), sp_gri=sp,
+                                              radtran_opt=opt, LUTopt=dict(LUTopt),
+                                              group_observations=True, alt_step_sims=12.)
+    assert len(rt_b) > 15
+    Ja, Jb = bs_a.build_jacobian(), bs_b.build_jacobian()
+    assert Ja.shape == Jb.shape == (14, bs_a.n_tot)
+    for a, b in zip(sims_a, sims_b):
+        assert rel_err(b.spectrum, a.spectrum) < 1e-2
+    scale = np.abs(Ja).max(axis=0, keepdims=True)
+    assert np.all(np.abs(Jb - Ja) <= 2e-2 * scale)
