@@ -209,12 +209,12 @@ def cpu_los_sample(args, wl, seconds, threads):
     return los_equiv / per, per, desc
 
 
-def cpu_voigt_sample(args, wl, threads):
+def cpu_voigt_sample(args, wl, threads, n_sample=None):
     """CPU restatement of one LUT cell (humliv_bb + G coefficients + line sum) on a line sample."""
     from oracle import cpu_oracle as O
     S = wl["S"]
     grid, lines = wl["grid"], wl["lines"]
-    n = min(len(lines["freq"]), 200 if args.small else 4000)
+    n = min(len(lines["freq"]), n_sample or (200 if args.small else 4000))
     sub_lines = {k: (v[:n] if isinstance(v, np.ndarray) and v.shape[:1] == lines["freq"].shape else v)
                  for k, v in lines.items()}
     t0 = time.perf_counter()
@@ -619,6 +619,11 @@ def run_ours(args):
         ve, vdesc = cpu_voigt_sample(args, wl, threads)
         line["voigt"]["cpu_baseline"] = {"value": ve, "unit": "evals/s", "cores": threads,
                                          "kind": "port", "sample": vdesc}
+        v1, v1desc = cpu_voigt_sample(args, wl, 1, n_sample=100 if args.small else 500)
+        line["voigt"]["cpu_baseline_1thread"] = {"value": v1, "unit": "evals/s", "cores": 1,
+                                                 "kind": "port", "sample": v1desc}
+        line["voigt"]["context"] = ("the reference author's own estimate of the Python + f2py path is "
+                                    "~2.2e6 evals/s (spect_main_module.py:791-801; BASELINE.md section 1)")
     if rank == 0:
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
