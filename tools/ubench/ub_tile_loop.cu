@@ -52,7 +52,25 @@ __global__ void __launch_bounds__(NT,MINB) ub(int n_rec,int reps,double* sink){
       hbuf[i].len= left ? (unsigned)(100000+edge) : 1u<<30; }
     __syncthreads();
   }
-  for(int r=0;r<reps;r++){
+  // FP32 evaluation of K, FP64 accumulation (d = P - centre in float, then the same rational)
+  float Pf[PPT];
+  #pragma unroll
+  for(int k=0;k<PPT;k++) Pf[k]=(float)(threadIdx.x+k*NT);
+  auto half_f32=[&](const HalfRec& h){
+    const float xs=(float)h.xs,b=(float)(h.b-300.0),c1=(float)h.c1,c2=(float)h.c2;
+    const double g0=h.g0,g1=h.g1,g2=h.g2;
+    const float c1p=c1+1.0f;
+    #pragma unroll
+    for(int k=0;k<PPT;k++){
+      const float x=fmaf(Pf[k],xs,b);
+      const float u=fmaf(x,x,c1), w=fmaf(x,x,c1p);
+      const float den=fmaf(u,u,c2);
+      float rr; asm("rcp.approx.ftz.f32 %0, %1;":"=f"(rr):"f"(den)); const double kp=(double)(w*rr);
+      acc0[k]=fma(g0,kp,acc0[k]);acc1[k]=fma(g1,kp,acc1[k]);acc2[k]=fma(g2,kp,acc2[k]);
+    }
+  };
+  if(VAR==20){ for(int r=0;r<reps;r++){ int h=0; for(;h+2<=n_rec;h+=2){half_f32(hbuf[h]);half_f32(hbuf[h+1]);} } }
+  for(int r=0;r<reps && VAR!=20;r++){
     if(VAR>=10){ for(int h=0;h<n_rec;h++) half_part(hbuf[h],VAR-10); }
     else if(VAR==0){ int h=0; for(;h+2<=n_rec;h+=2){half_eval(hbuf[h]);half_eval(hbuf[h+1]);} }
     else if(VAR==1){ for(int h=0;h<n_rec;h++) half_eval(hbuf[h]); }
@@ -90,6 +108,9 @@ int main(){
   run<128,4,4,10>(4,nr,reps);  // partial records, per-k vote + branch (the kernel's form); evals/s counts ALL points
   run<128,4,4,11>(4,nr,reps);  // partial records, unconditional evaluation + select
   run<128,4,4,12>(4,nr,reps);  // record-level vote, then unconditional
+  run<128,4,4,20>(4,nr,reps);  // FP32 K, FP64 accumulation
+  run<128,4,6,20>(6,nr,reps);
+  run<128,8,4,20>(4,nr,reps);
   run<128,4,3,0>(3,nr,reps);
   run<128,2,6,0>(6,nr,reps);
   run<128,2,8,0>(8,nr,reps);
