@@ -17,6 +17,7 @@
 //                      column-weighted vibrational temperatures, parameter derivative columns
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 #include "sr_common.h"
 #include "sr_device.cuh"
@@ -295,7 +296,8 @@ int sr_los_steps_build(const sr_atmosphere* atm, int n_los, const double* origin
     const double r_top = atm->radius_km + atm->top_km;
     const int n_pts_max = 2 * (int)std::floor(r_top / delta_x_km) + 3;
     // LOS blocks bound the per-point scratch (48 B per point) to ~1 GiB
-    const int blk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_los, ((size_t)1 << 30) / ((size_t)n_pts_max * 48)));
+    int blk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_los, ((size_t)1 << 30) / ((size_t)n_pts_max * 48)));
+    if (const char* e = getenv("SR_STEPS_BLOCK")) blk = std::max(1, std::min(n_los, atoi(e)));   // test aid
     sr::PoolBuf<double> sT, sP, snd, sx, salt, o_temp, o_pres, o_col, o_tvib, o_dfrac;
     sr::PoolBuf<int> sband, sjz, d_npts, d_nsteps, d_bounds;
     const size_t np = (size_t)blk * n_pts_max;

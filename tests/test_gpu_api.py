@@ -271,6 +271,16 @@ def test_device_step_builder_matches_host_builder(world):
         for par in bs.params():
             assert loss[l].involved_retparams[(par.nameset, par.key)] == \
                 los.involved_retparams[(par.nameset, par.key)]
+    # LOS blocks of the per-point scratch are invisible
+    import os
+    os.environ["SR_STEPS_BLOCK"] = "3"
+    try:
+        _, st_b, df_b = smm.los_step_tables_device(loss, planet, bayes_set=bs, set_name='CH4', **opt)
+    finally:
+        del os.environ["SR_STEPS_BLOCK"]
+    assert np.array_equal(st_b.n_steps, steps.n_steps) and np.array_equal(st_b.temp, steps.temp)
+    assert np.array_equal(st_b.column, steps.column) and np.array_equal(st_b.tvib, steps.tvib)
+    assert np.array_equal(df_b, dfrac)
     # a narrow table is widened by the wrapper (SR_ERR_LIMIT -> retry)
     atm = smm.planet_atmosphere_tables(planet, gi)
     org = np.array([l.starting_point.Cartesian() for l in loss])
