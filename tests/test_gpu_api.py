@@ -395,3 +395,22 @@ def test_inversion_fast_limb_group_observations(world):
         assert rel_err(b.spectrum, a.spectrum) < 1e-2
     scale = np.abs(Ja).max(axis=0, keepdims=True)
     assert np.all(np.abs(Jb - Ja) <= 2e-2 * scale)
+
+
+def test_convolve_lowres_many_spectra(world, oracle):
+    """More spectra than one launch pair of k_convolve_lowres takes (slabs of 512): every spectrum
+    gets the same channels as when it is convolved alone."""
+    eng, torch = world["engine"], world["torch"]
+    rng = np.random.default_rng(12)
+    x = np.arange(3000.0, 3004.0, 5e-4)
+    y = rng.uniform(0.0, 1.0, (700, len(x)))
+    centres = np.linspace(3000.5, 3003.5, 9)
+    widths = np.full(9, 0.2)
+    xd, yd = torch.as_tensor(x, device="cuda"), torch.as_tensor(y, device="cuda")
+    all_ = eng.convolve_lowres(xd, yd, centres, widths).cpu().numpy()
+    for i in (0, 511, 512, 699):
+        one = eng.convolve_lowres(xd, yd[i:i + 1].contiguous(), centres, widths).cpu().numpy()
+        assert np.array_equal(all_[i], one[0]), i
+    for i in (3, 600):
+        ref = oracle.convolve_to_grid_from_irregular(x, y[i], centres, widths)
+        assert rel_err(all_[i], ref, floor_rel=1e-12) < 1e-12
