@@ -947,6 +947,8 @@ int sr_lineset_create(const sr_lines* lines, const double* grid, long n_grid,
                       (sizeof(LineCell) + sizeof(LineRec) + CORE_STRIDE * sizeof(double));
     ls->max_cells_per_batch =
         (int)std::max<size_t>(1, std::min<size_t>(4096, ((size_t)2 << 30) / per_cell));
+    if (const char* e = getenv("SR_K2_BATCH"))   // test aid: cells per batch
+        ls->max_cells_per_batch = std::max(1, atoi(e));
     *out = ls;
     return SR_OK;
 }

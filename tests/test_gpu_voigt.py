@@ -218,3 +218,19 @@ def test_linearity_and_line_sharding_property(sb):
         parts.append(engine.LineSet(sub, g, S.CH4_MM, 12).gcoeff_cells([[0.05, 160.0]]))
     tot = parts[0] + parts[1]
     assert rel_err(tot.cpu().numpy(), whole.cpu().numpy()) < 1e-12
+
+
+def test_cell_batches_are_invisible(sb, monkeypatch):
+    """LUT cells are processed in batches that reuse the per-(line, cell) tables back to back on one
+    stream (no host synchronisation in between): the batch size must not change a bit."""
+    engine, lineshape, S = sb
+    g, lines = _cell_case(S, 300, 2990.0, 3010.0, 6, seed=33)
+    cells = [[10.0 ** (-4 + 0.5 * j), 140.0 + 3.0 * j] for j in range(7)]
+    base = engine.LineSet(lines, g, S.CH4_MM, 6).gcoeff_cells(cells)
+    base32 = engine.LineSet(lines, g, S.CH4_MM, 6).gcoeff_cells_f32(cells)
+    monkeypatch.setenv("SR_K2_BATCH", "2")
+    ls = engine.LineSet(lines, g, S.CH4_MM, 6)
+    import torch
+    assert torch.equal(ls.gcoeff_cells(cells), base)
+    assert torch.equal(ls.gcoeff_cells_f32(cells), base32)
+    assert np.array_equal(ls.gcoeff_cells_host(cells), base.cpu().numpy())
