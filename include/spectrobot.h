@@ -313,8 +313,8 @@ typedef struct {
  * max_Plog_variation; every step gets air-weighted Curtis-Godson T and P, the gas columns
  * (molecules cm-2) and column-weighted vibrational temperatures.  Outputs are HOST arrays in the
  * sr_los_steps layout with n_steps_max columns (padding: 100 K, 1e-6 hPa, column 0).
- * n_par > 0: masks[n_par][n_z] are the altitude weights of retrieval parameters of gas entry
- * jac_gas; dfrac[n_los][n_steps_max][n_par] = (d column / d parameter) / column for
+ * n_par > 0: masks[n_par][n_band][n_z] are the weights (latitude box x altitude, linear in
+ * altitude) of retrieval parameters of gas entry jac_gas; dfrac[n_los][n_steps_max][n_par] = (d column / d parameter) / column for
  * sr_los_rt_lut_jac_*.  n_steps_needed (optional) returns the largest step count; when it exceeds
  * n_steps_max the call returns SR_ERR_LIMIT. */
 int sr_los_steps_build(const sr_atmosphere* atm, int n_los, const double* origin,

@@ -553,7 +553,10 @@ def los_steps_build(z, temp, pres, vmr, origins, directions, tvib=None, tvib_on=
     if n_sets:
         tvib_on = np.asarray(tvib_on).reshape(n_gas, n_sets)
         tvib = None if tvib is None else np.asarray(tvib, dtype=float).reshape(n_gas, n_sets, n_band, len(z))
-    masks = None if masks is None else np.asarray(masks, dtype=float).reshape(-1, len(z))
+    if masks is not None:   # [n_par][n_z] or [n_par][n_band][n_z]
+        masks = np.asarray(masks, dtype=float)
+        if masks.ndim == 2:
+            masks = np.repeat(masks[:, None, :], n_band, axis=1)
     out = []
     for o, d in zip(np.asarray(origins, dtype=float).reshape(-1, 3),
                     np.asarray(directions, dtype=float).reshape(-1, 3)):
@@ -618,7 +621,7 @@ def los_steps_build(z, temp, pres, vmr, origins, directions, tvib=None, tvib_on=
                 row = []
                 col = res["column"][jac_gas][-1] if 0 <= jac_gas < n_gas else 0.0
                 for q in range(len(masks)):
-                    mk = np.interp(alt[sl], z, masks[q])
+                    mk = at(masks[q])[sl]
                     dcol = curgod(2, nd[sl], mk, x[sl]) if np.any(mk != 0.0) else 0.0
                     row.append(dcol / col if col != 0.0 else 0.0)
                 res["dfrac"].append(row)

@@ -36,7 +36,7 @@ struct AtmDev {
     const double* vmr;         // [n_gas][n_band][n_z]
     const double* tvib;        // [n_gas][n_sets_max][n_band][n_z]
     const int* tvib_on;        // [n_gas][n_sets_max]: 1 own profile, 0 T_vib = step T, -1 no level
-    const double* masks;       // [n_par][n_z]
+    const double* masks;       // [n_par][n_band][n_z]
     double radius, top;
 };
 
@@ -237,13 +237,13 @@ __global__ void k_steps_integrals(IntArgs a) {
         }
         if (m == A.jac_gas) {
             for (int q = 0; q < A.n_par; q++) {
-                const double* mk = A.masks + (size_t)q * A.n_z;
+                const double* mk = A.masks + (size_t)q * A.n_band * A.n_z;   // per latitude box
                 double d = 0.0;
                 bool any = false;
-                double m0 = interp_at(A.z, mk, A.n_z, a.jz[o + ia], a.alt[o + ia]);
+                double m0 = prof(mk, ia);
                 any = m0 != 0.0;
                 for (int i = ia; i < ie; i++) {
-                    const double m1 = interp_at(A.z, mk, A.n_z, a.jz[o + i + 1], a.alt[o + i + 1]);
+                    const double m1 = prof(mk, i + 1);
                     any = any || m1 != 0.0;
                     d += srdev::curgod_seg2(nd[i], nd[i + 1], m0, m1, x[i + 1] - x[i]);
                     m0 = m1;
@@ -287,7 +287,7 @@ int sr_los_steps_build(const sr_atmosphere* atm, int n_los, const double* origin
     SR_CUDA(d_vmr.upload(atm->vmr, (size_t)ng * nb * nz, st));
     if (atm->tvib) SR_CUDA(d_tvib.upload(atm->tvib, (size_t)ng * nsx * nb * nz, st));
     if (nsx > 0) SR_CUDA(d_on.upload(atm->tvib_on, (size_t)ng * nsx, st));
-    if (n_par > 0) SR_CUDA(d_masks.upload(masks, (size_t)n_par * nz, st));
+    if (n_par > 0) SR_CUDA(d_masks.upload(masks, (size_t)n_par * nb * nz, st));
     AtmDev A;
     A.n_band = nb; A.n_z = nz; A.n_gas = ng; A.n_sets_max = nsx; A.n_par = n_par; A.jac_gas = jac_gas;
     A.lat_edges = d_edges.p; A.z = d_z.p; A.temp = d_temp.p; A.lnpres = d_lnp.p; A.vmr = d_vmr.p;

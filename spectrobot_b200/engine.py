@@ -533,12 +533,18 @@ def los_steps_build(atm, origins, directions, delta_x=5.0, max_T_variation=5.0,
                     max_Plog_variation=1.0, masks=None, jac_gas=-1, n_steps_max=64):
     """LOS geometry + radtran steps of a whole batch on the device (sr_los_steps_build): rays from
     origins [n_los, 3] (km, planetocentric Cartesian) along unit directions [n_los, 3].  Returns
-    (LosSteps, dfrac) - dfrac [n_los, n_steps_max, n_par] for the parameter masks [n_par, n_z] of gas
-    entry jac_gas, or None.  The table width grows until every LOS fits."""
+    (LosSteps, dfrac) - dfrac [n_los, n_steps_max, n_par] for the parameter masks [n_par, n_z] or
+    [n_par, n_band, n_z] of gas entry jac_gas, or None.  The table width grows until every LOS fits."""
     org, dr = as_f64(origins).reshape(-1, 3), as_f64(directions).reshape(-1, 3)
     n_los = org.shape[0]
     assert dr.shape == org.shape
-    mk = None if masks is None else as_f64(np.asarray(masks, dtype=float).reshape(-1, len(atm.z)))
+    mk = None
+    if masks is not None:   # [n_par, n_z] (same in every latitude box) or [n_par, n_band, n_z]
+        mk = np.asarray(masks, dtype=float)
+        if mk.ndim == 2:
+            mk = np.repeat(mk[:, None, :], atm.n_band, axis=1)
+        assert mk.shape[1:] == (atm.n_band, len(atm.z))
+        mk = as_f64(mk)
     n_par = 0 if mk is None else mk.shape[0]
     st = atm.struct()
     while True:

@@ -213,23 +213,56 @@ class AtmProfile(object):
 
 
 class AtmGridMask(object):
-    """Weight of one retrieval parameter over the atmosphere grid (smm:348-350: built by
-    alt_triangle on an 'alt' AtmGrid; 1-D altitude masks only here)."""
+    """Weight of one retrieval parameter over the atmosphere grid (smm:348-350, 355-374): a
+    triangle in altitude (alt_triangle, linear), a latitude box (lat_box: coords are the box START
+    latitudes, ascending; the last box is open-ended) or their product (merge)."""
 
     def __init__(self, grid, mask, interp='lin'):
         self.grid = grid
         self.mask = np.asarray(mask, dtype=float)
         self.interp = {'mask': interp if isinstance(interp, str) else interp[-1]}
 
+    def _lat_box(self, lat):
+        starts = self.grid.coords['lat']
+        return int(np.clip(np.searchsorted(starts, lat, side='right') - 1, 0, len(starts) - 1))
+
     def calc(self, point, profname=None):
         lat, lon, alt = point.Spherical() if hasattr(point, 'Spherical') else point
+        if self.grid.names == ['lat']:
+            return float(self.mask[self._lat_box(lat)])
+        m = self.mask[self._lat_box(lat)] if self.grid.n_dim > 1 else self.mask
         z = self.grid.coords['alt']
         if self.interp['mask'] == 'box':
-            return float(self.mask[int(np.clip(np.searchsorted(z, alt, side='right') - 1, 0, len(z) - 1))])
-        return float(np.interp(alt, z, self.mask))
+            return float(m[int(np.clip(np.searchsorted(z, alt, side='right') - 1, 0, len(z) - 1))])
+        return float(np.interp(alt, z, m))
+
+    def merge(self, mask2):
+        """Product of an altitude mask and a latitude-box mask -> mask on ('lat', 'alt')
+        (LinearProfile_2D, smm:392-396)."""
+        alt_m, lat_m = (self, mask2) if self.grid.names == ['alt'] else (mask2, self)
+        if alt_m.grid.names != ['alt'] or lat_m.grid.names != ['lat']:
+            raise ValueError('merge needs one altitude mask and one latitude mask')
+        grid = AtmGrid(['lat', 'alt'], [lat_m.grid.coords['lat'], alt_m.grid.coords['alt']])
+        return AtmGridMask(grid, np.outer(lat_m.mask, alt_m.mask), alt_m.interp['mask'])
+
+    def table(self, z, lat_edges=None):
+        """[n_band][n_z] (or [n_z]) weights on the atmosphere's altitude grid and latitude bands:
+        what the device step builder takes.  The latitude boxes must be the atmosphere's bands."""
+        if not np.array_equal(self.grid.coords['alt'], z) or self.interp['mask'] != 'lin':
+            raise ValueError('parameter masks must be linear on the atmosphere altitude grid')
+        if self.grid.n_dim == 1:
+            return self.mask
+        if lat_edges is None or not np.array_equal(self.grid.coords['lat'], np.asarray(lat_edges)[:-1]):
+            raise ValueError('latitude boxes of the parameter masks must start at the atmosphere band edges')
+        return self.mask
 
     def __mul__(self, value):
-        return AtmProfile(self.grid, self.mask * float(value), 'mask', self.interp['mask'])
+        grid = self.grid
+        if grid.n_dim > 1:   # AtmProfile keeps band EDGES as latitude coordinates
+            lat = grid.coords['lat']
+            grid = AtmGrid(['lat', 'alt'], [np.append(lat, 90.0 if lat[-1] < 90.0 else lat[-1] + 1.0),
+                                            grid.coords['alt']])
+        return AtmProfile(grid, self.mask * float(value), 'mask', self.interp['mask'])
 
     __rmul__ = __mul__
 
@@ -237,6 +270,11 @@ class AtmGridMask(object):
 def AtmProfZeros(grid, profname, interp):
     shape = tuple(len(g) - (1 if n == 'lat' else 0) for n, g in zip(grid.names, grid.grid))
     return AtmProfile(grid, np.zeros(shape), profname, interp)
+
+
+def mask_profile_grid(maskgrid):
+    """AtmGrid of the profile a parameter mask spans (latitude coordinates as band edges)."""
+    return (maskgrid * 0.0).grid
 
 
 class Level(object):

@@ -504,6 +504,24 @@ def alt_triangle(alt_grid, node_alt, step=None, node_lo=None, node_up=None, firs
     return sbm.AtmGridMask(sbm.AtmGrid('alt', alt_grid), cos, 'lin')
 
 
+def lat_box(lat_limits, lat_ok):
+    """Latitude mask with a box function (smm:355-374): lat_limits are the START latitudes of the
+    boxes, ascending, the last box is open-ended; 1 in the box that contains lat_ok.  Kept literal:
+    the last box needs lat_ok STRICTLY above its start (:368), so LinearProfile_2D, which passes the
+    box starts themselves, leaves the parameters of its last box with an all-zero mask."""
+    lat_limits = np.asarray(lat_limits, dtype=float)
+    cos = []
+    for lat1, lat2 in zip(lat_limits[:-1], lat_limits[1:]):
+        cos.append(1.0 if lat1 <= lat_ok < lat2 else 0.0)
+    cos.append(1.0 if lat_ok > lat_limits[-1] else 0.0)
+    return sbm.AtmGridMask(sbm.AtmGrid('lat', lat_limits), np.array(cos), 'box')
+
+
+def centre_boxes(lat_limits):
+    """[-90, -60, -30, ...] -> box centres [-75, -45, ...] (smm:377-385)."""
+    return [(la1 + la2) / 2.0 for la1, la2 in zip(lat_limits[:-1], lat_limits[1:])]
+
+
 class RetParam(object):
     """A single parameter of the parameter space (smm:600-656)."""
 
@@ -570,7 +588,7 @@ class RetSet(object):
 
     def profile(self):
         """sum_p maskgrid_p * value_p (smm:483-489) as an AtmProfile named 'vmr' (and self.name)."""
-        grid = self.set[0].maskgrid.grid
+        grid = sbm.mask_profile_grid(self.set[0].maskgrid)
         prof = sbm.AtmProfZeros(grid, 'vmr', self.set[0].maskgrid.interp['mask'])
         for par in self.set:
             prof += par.maskgrid * par.value
@@ -616,6 +634,43 @@ class LinearProfile_1D(LinearProfile_1D_new):
         LinearProfile_1D_new.__init__(self, name, atmosphere.grid.coords['alt'], alt_nodes,
                                       apriori_prof, apriori_prof_err, first_guess_prof)
         self.orig_atmosphere = atmosphere
+
+
+class LinearProfile_2D(RetSet):
+    """Profile linear in altitude between the nodes, with latitude boxes (smm:388-439): one
+    LinearProfile_1D_new per box, every parameter keyed (box start latitude, altitude node) and
+    masked by alt_triangle x lat_box.  lat_limits are the box START latitudes (ascending)."""
+
+    def __init__(self, name, atmosphere, alt_nodes, lat_limits, apriori_profs, apriori_prof_errs,
+                 first_guess_profs=None):
+        self.name = name
+        self.set = []
+        self.n_par = len(alt_nodes) * len(lat_limits)
+        self.alts = list(alt_nodes)
+        self.lats = list(lat_limits)
+        z = atmosphere.grid.coords['alt']
+        if first_guess_profs is None:
+            first_guess_profs = apriori_profs
+        for ap, er, fg, lat in zip(apriori_profs, apriori_prof_errs, first_guess_profs, lat_limits):
+            coso = LinearProfile_1D_new(name, z, alt_nodes, ap, er, first_guess_prof=fg)
+            latbox = lat_box(lat_limits, lat)
+            for cos in coso.set:
+                self.set.append(RetParam(name, (lat, cos.key), cos.maskgrid.merge(latbox),
+                                         cos.apriori, cos.apriori_err, first_guess=cos.value))
+
+    def check_involved(self, parkey, coord_range):
+        indp = self.alts.index(parkey[1])
+        involved = True
+        if indp != len(self.alts) - 1 and coord_range['alt'][0] > self.alts[indp + 1]:
+            involved = False
+        latz = coord_range['lat']
+        indl = self.lats.index(parkey[0])
+        if indl == len(self.lats) - 1:
+            if latz[1] < parkey[0]:
+                involved = False
+        elif latz[1] < parkey[0] or latz[0] > self.lats[indl + 1]:
+            involved = False
+        return involved
 
 
 class BayesSet(object):
@@ -730,12 +785,9 @@ def los_step_tables_device(loss, planet, bayes_set=None, set_name=None, delta_x=
     masks, jac_gas, pars = None, -1, []
     if bayes_set is not None and set_name is not None and set_name in planet.gases:
         pars = bayes_set.sets[set_name].set
-        z = atm.z
-        masks = np.array([np.interp(z, p.maskgrid.grid.coords['alt'], p.maskgrid.mask) for p in pars])
-        for p in pars:
-            if p.maskgrid.interp['mask'] != 'lin' or not np.array_equal(p.maskgrid.grid.coords['alt'], z):
-                raise ValueError('device step builder: parameter masks must be linear on the '
-                                 'atmosphere altitude grid')
+        lat_edges = planet.atmosphere.grid.coords['lat'] if planet.atmosphere.grid.n_dim > 1 else None
+        masks = np.array([np.broadcast_to(p.maskgrid.table(atm.z, lat_edges), (atm.n_band, len(atm.z)))
+                          for p in pars])
         jac_gas = [g for g, iso in gi].index(set_name)
     steps, dfrac = engine.los_steps_build(atm, org, drc, delta_x=delta_x,
                                           max_T_variation=max_T_variation,

@@ -414,3 +414,43 @@ def test_convolve_lowres_many_spectra(world, oracle):
     for i in (3, 600):
         ref = oracle.convolve_to_grid_from_irregular(x, y[i], centres, widths)
         assert rel_err(all_[i], ref, floor_rel=1e-12) < 1e-12
+
+
+def test_device_step_builder_latitude_box_parameters(world):
+    """Parameters with latitude boxes (LinearProfile_2D): the device step builder's derivative
+    table against the per-LOS host builder on the 7-band atmosphere, for rays that cross bands."""
+    smm, S, sbm = world["smm"], world["S"], world["sbm"]
+    planet = S.titan_planet(world["tab"]["level_energies"], n_bands=7)
+    atm = planet.atmosphere
+    starts = list(atm.grid.coords['lat'][:-1])
+    nodes = [300., 550., 800., 1100.]
+    vals = [[0.015 * (1 + 0.1 * b)] * 4 for b in range(7)]
+    prof = smm.LinearProfile_2D('CH4', atm, nodes, starts, vals, [[1e-3] * 4] * 7)
+    bs = smm.BayesSet('3d')
+    bs.add_set(prof)
+    p = prof.profile()
+    p.values['vmr'][6] = p.values['vmr'][5]          # keep the (quirky, empty) last box physical
+    planet.gases['CH4'].add_clim(p)
+    obs = sbm.Coords([20.0, 90.0, 1.0e5], s_ref='Spherical')
+    loss = [sbm.LineOfSight(obs, sbm.Coords([lat, 2.0, alt], s_ref='Spherical'))
+            for alt, lat in ((400.0, 58.0), (650.0, -31.0), (900.0, 74.0), (500.0, 10.0))]
+    opt = dict(max_T_variation=5.0, max_Plog_variation=1.0)
+    gi, steps, dfrac = smm.los_step_tables_device(loss, planet, bayes_set=bs, set_name='CH4', **opt)
+    host = []
+    for los in loss:
+        l2 = sbm.LineOfSight(los.starting_point, los.second_point)
+        l2.calc_atm_intersections(planet)
+        l2.calc_radtran_steps(planet, None, calc_derivatives=True, bayes_set=bs, **opt)
+        host.append(l2)
+    _, steps_h = smm.los_step_tables(host, planet)
+    nmax = steps_h.n_steps_max
+    assert np.array_equal(steps.n_steps, steps_h.n_steps)
+    assert np.allclose(steps.column[:, :, :nmax], steps_h.column, rtol=1e-10, atol=0)
+    dfrac_h = smm.los_jac_tables(host, bs, 'CH4', nmax)
+    assert np.allclose(dfrac[:, :nmax], dfrac_h, rtol=1e-9, atol=1e-14)
+    used_boxes = {bs.params()[q].key[0] for q in range(bs.n_tot) if np.any(dfrac[:, :, q] != 0.0)}
+    assert len(used_boxes) >= 3                        # the rays cross several latitude boxes
+    for l, los in enumerate(host):
+        for par in bs.params():
+            assert loss[l].involved_retparams[(par.nameset, par.key)] == \
+                los.involved_retparams[(par.nameset, par.key)]

@@ -390,3 +390,33 @@ def test_group_observations_ladder_and_spline():
     for z, r in zip(za, rads):
         assert np.allclose(spl(z).spectrum, r.spectrum, rtol=1e-12)
     assert np.allclose(spl(437.0).spectrum, (1.0 + 4.37) * np.arange(1., 8.), rtol=1e-12)  # linear in z
+
+
+def test_latitude_boxes_and_2d_profile():
+    """lat_box / centre_boxes / LinearProfile_2D (smm:355-439) and AtmGridMask.merge: literal box
+    semantics (incl. the strict comparison that empties the last box), parameters keyed
+    (box start, altitude node), profile() = sum of value x mask on (latitude band, altitude)."""
+    lims = [-90., -30., 30., 60.]
+    assert list(smm.lat_box(lims, -90.).mask) == [1., 0., 0., 0.]
+    assert list(smm.lat_box(lims, 45.).mask) == [0., 0., 1., 0.]
+    assert list(smm.lat_box(lims, 60.).mask) == [0., 0., 0., 0.]      # smm:368 uses '>'
+    assert list(smm.lat_box(lims, 61.).mask) == [0., 0., 0., 1.]
+    assert smm.centre_boxes(lims) == [-60., 0., 45.]
+    planet = S.titan_planet(None, n_bands=7)
+    atm = planet.atmosphere
+    starts = list(atm.grid.coords['lat'][:-1])
+    nodes = [300., 600., 900.]
+    vals = [[0.01 * (1 + b), 0.02 * (1 + b), 0.015 * (1 + b)] for b in range(7)]
+    prof = smm.LinearProfile_2D('CH4', atm, nodes, starts, vals, [[1e-3] * 3] * 7)
+    assert prof.n_par == 21 and prof.set[4].key == (-75.0, 600.0)
+    assert prof.set[4].maskgrid.mask.shape == (7, len(atm.grid.coords['alt']))
+    p = prof.profile()
+    z = atm.grid.coords['alt']
+    for b in range(6):
+        assert np.allclose(p.values['vmr'][b], np.interp(z, nodes, vals[b]), rtol=1e-14)
+    assert np.all(p.values['vmr'][6] == 0.0)                           # the literal last-box quirk
+    pt = sbm.Coords([40.0, 0.0, 450.0], s_ref='Spherical')
+    assert abs(p.calc(pt, 'vmr') - sum(q.value * q.maskgrid.calc(pt) for q in prof.set)) < 1e-15
+    assert prof.check_involved((30.0, 600.), dict(alt=[650., 1000.], lat=[35., 50.]))
+    assert not prof.check_involved((60.0, 600.), dict(alt=[650., 1000.], lat=[35., 50.]))
+    assert not prof.check_involved((30.0, 300.), dict(alt=[650., 1000.], lat=[35., 50.]))
