@@ -56,11 +56,34 @@ __global__ void __launch_bounds__(CONV_NT) k_convolve_lowres(
     double* xs = csm;                                  // [CONV_PB + 1]
     double* ys = csm + CONV_PB + 1;                    // [CONV_SPB][CONV_PB + 1]
     __shared__ double red[CONV_SPB][CONV_NT / 32];
-    // does any channel see this block at all?
-    bool any = false;
-    for (int c = 0; c < n_chan; c++)
-        any = any || min(win[2 * c + 1], bend) > max(win[2 * c], bstart);
-    if (!any) return;                                  // uniform over the CTA
+    // the channels whose window reaches into this block, ascending (one test per thread and a
+    // ballot compaction instead of every thread scanning all channels); more than CONV_NT
+    // channels fall back to the scan
+    __shared__ int clist[CONV_NT];
+    __shared__ int wcount[CONV_NT / 32];
+    const bool listed = n_chan <= CONV_NT;
+    int n_list = n_chan;
+    if (listed) {
+        const int t = threadIdx.x;
+        const bool hit = t < n_chan && min(win[2 * t + 1], bend) > max(win[2 * t], bstart);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) wcount[wid] = __popc(m);
+        __syncthreads();
+        int base = 0;
+        n_list = 0;
+#pragma unroll
+        for (int w = 0; w < CONV_NT / 32; w++) {
+            base += w < wid ? wcount[w] : 0;
+            n_list += wcount[w];
+        }
+        if (hit) clist[base + __popc(m & ((1u << lane) - 1u))] = t;
+        if (n_list == 0) return;                       // uniform over the CTA
+    } else {
+        bool any = false;
+        for (int c = 0; c < n_chan; c++)
+            any = any || min(win[2 * c + 1], bend) > max(win[2 * c], bstart);
+        if (!any) return;                              // uniform over the CTA
+    }
     // asynchronous global -> shared copies (LDGSTS): every thread has all its 8-byte copies in
     // flight at once instead of one load per dependent shared-memory store
     auto cp8 = [](double* dst, const double* src) {
@@ -79,7 +102,8 @@ __global__ void __launch_bounds__(CONV_NT) k_convolve_lowres(
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    for (int c = 0; c < n_chan; c++) {
+    for (int ci = 0; ci < n_list; ci++) {              // (clist is published by the barrier above)
+        const int c = listed ? clist[ci] : ci;
         const long s0l = max(win[2 * c], bstart), s1l = min(win[2 * c + 1], bend);
         if (s1l <= s0l) continue;                      // uniform over the CTA
         const int s0 = (int)(s0l - bstart), s1 = (int)(s1l - bstart);
