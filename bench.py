@@ -540,7 +540,7 @@ def run_ours(args):
         A_b = engine.Atmosphere(atm_b["z"], atm_b["temp"], atm_b["pres"],
                                 np.full((1,) + atm_b["temp"].shape, 0.015), tvib=tv_b[None],
                                 lat_edges=atm_b["lat_edges"], radius_km=S.R_TITAN_KM, top_km=1500.0)
-        engine.los_steps_build(A_b, org_b[:64], -east[:64])                     # first-call costs
+        engine.los_steps_build(A_b, org_b, -east)       # warm-up: scratch pool growth, first-touch of host pages
         barrier()
         t0 = time.perf_counter()
         steps_b, _ = engine.los_steps_build(A_b, org_b, -east, delta_x=5.0, max_T_variation=5.0,
