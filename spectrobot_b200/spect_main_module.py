@@ -39,6 +39,16 @@ def lut_name(mol, iso, LTE):
     return 'LUT_mol{:02d}_iso{:1d}_{}'.format(mol, iso, 'LTE' if LTE else 'nonLTE')
 
 
+def lut_name_split(mol, iso, LTE, split):
+    """LUT_csplitNN_molMM_isoI_{LTE|nonLTE} (smm:666-672)."""
+    return 'LUT_csplit{:02d}_mol{:02d}_iso{:1d}_{}'.format(split, mol, iso, 'LTE' if LTE else 'nonLTE')
+
+
+def lut_name_wsplits(mol, iso, LTE, n_split):
+    """LUT_NNsplits_molMM_isoI_{LTE|nonLTE} (smm:674-680)."""
+    return 'LUT_{:02d}splits_mol{:02d}_iso{:1d}_{}'.format(n_split, mol, iso, 'LTE' if LTE else 'nonLTE')
+
+
 def prepare_spe_grid(wn_range, sp_step=5.e-4, units='cm_1'):
     """Zero spectrum on np.arange(w0, w1 + step/2, step) (smm:1262-1272)."""
     grid = spcl.SpectralGrid(np.arange(wn_range[0], wn_range[1] + sp_step / 2, sp_step,
@@ -134,7 +144,7 @@ class LutSet(object):
         return self.PTcouples.index([Pres, Temp])
 
     def _host_sets(self):
-        if not self.sets and self._table is not None:
+        if not self.sets and getattr(self, '_table', None) is not None:
             lut, s = self._table
             g = lut.g32[:, s].cpu().numpy()
             lev_str = '' if self.unidentified_lines else self.level.minimal_level_string()
@@ -358,6 +368,36 @@ class LookUpTable(object):
         self._dev = None
         return self
 
+    def add_split_file(self, filename):
+        if not hasattr(self, 'splitfiles'):
+            self.splitfiles = []
+        self.splitfiles.append(filename)
+
+    def load_split(self, nsp):
+        """Loads wavenumber chunk `nsp` written by split_and_compress_LUTS (here or by the
+        reference, smm:822-838) as THE table of this LUT: the sets, the spectral grid and the
+        resident float32 tensor then cover that chunk only."""
+        split = read_split_file(self.splitfiles[nsp])
+        names = self.set_names()
+        first = split[names[0]]
+        self.spectral_grid = first.spectral_grid
+        self.PTcouples = [list(map(float, pt)) for pt in first.PTcouples]
+        n_grid = len(self.spectral_grid.grid)
+        table = np.zeros((len(self.PTcouples), len(names), 3, n_grid), dtype=np.float32)
+        for s, nam in enumerate(names):
+            st = split[nam]
+            for c, set_ in enumerate(st.sets):
+                for k, ct in enumerate(CTYPES):
+                    if set_[ct] is not None:
+                        table[c, s, k] = set_[ct].spectrum
+                        set_[ct].double_precision()
+                        set_[ct].restore_grid(st.spectral_grid, link_grid=True)
+            st._table = None
+            self.sets[nam] = st
+        self.g32 = engine.lut_from_host(table)
+        self._dev = None
+        return self
+
     def export(self, filename):
         """Header (PTcouples) first, then the table, like the reference's per-level files
         (smm:880-892): resumable by check_LUT_exists()."""
@@ -395,6 +435,73 @@ def read_lutset_stream(filename):
             except (EOFError, pickle.UnpicklingError):
                 break
     return pts[:len(sets)], sets
+
+
+def read_split_file(filename):
+    """{set name: LutSet} of one split / compressed LUT file (smm:1684-1712, read back by
+    LookUpTable.load_split, smm:822-838): one pickle `[set name, LutSet]` per vibrational level
+    ('all' for an LTE isotopologue); the LutSet carries the chunk's SpectralGrid, its PTcouples and
+    per cell {ctype: float32 SpectralGcoeff without grid, or None for an all-zero spectrum}."""
+    out = dict()
+    with open(filename, 'rb') as f:
+        while True:
+            try:
+                nam, st = _RefUnpickler(f, encoding='latin1').load()
+            except EOFError:
+                break
+            out[nam] = st
+    return out
+
+
+def split_and_compress_LUTS(spectral_grid, allLUTs, cartLUTs, n_threads=n_threads, n_split=None,
+                            ram_max=8., dim_tot=20., low_thres=1.e-30):
+    """Writes every LUT as n_split contiguous wavenumber chunks in the reference's split format
+    (smm:1614-1728): chunks of ceil(n_grid/n_split) points, float32, all-zero spectra as None, one
+    file `LUT_csplitNN_...<date>.pic` per chunk.  The LOS path here keeps the whole float32 table
+    resident on the device and does not need the files; they are written for interoperability with
+    the reference's radtrans / load_split.  Returns (allLUTs, n_split, chunk SpectralGrids)."""
+    if n_split is None:
+        n_split = int(np.ceil(dim_tot * n_threads / ram_max))
+    grid = spectral_grid.grid
+    len_split = int(np.ceil(1.0 * len(grid) / n_split))
+    sp_grids = []
+    for nsp in range(n_split):
+        g = copy.deepcopy(spectral_grid)
+        g.grid = grid[nsp * len_split:(nsp + 1) * len_split]
+        sp_grids.append(g)
+    for key, LUT in allLUTs.items():
+        if LUT is None:
+            continue
+        host = LUT.g32.cpu().numpy()
+        LUT.splitfiles = []
+        for nsp, spgri in enumerate(sp_grids):
+            fn = os.path.join(cartLUTs, lut_name_split(LUT.mol, LUT.iso, LUT.LTE, nsp) + date_stamp() + '.pic')
+            lo = nsp * len_split
+            with open(fn, 'wb') as f:
+                for s, nam in enumerate(LUT.set_names()):
+                    src = LUT.sets[nam]
+                    st = LutSet(LUT.mol, LUT.iso, LUT.MM, level=src.level)
+                    st.PTcouples = copy.deepcopy(LUT.PTcouples)
+                    st.spectral_grid = spgri
+                    lev_string = '' if src.level is None else src.level.minimal_level_string()
+                    for c, (P, T) in enumerate(LUT.PTcouples):
+                        d = dict()
+                        for k, ct in enumerate(CTYPES):
+                            spe = host[c, s, k, lo:lo + len(spgri.grid)]
+                            if not spe.max() > 0.0:
+                                d[ct] = None
+                                continue
+                            co = spcl.SpectralGcoeff(ct, spgri, LUT.mol, LUT.iso, LUT.MM, lev_string,
+                                                     unidentified_lines=src.unidentified_lines,
+                                                     spectrum=spe, Pres=P, Temp=T)
+                            co.spectrum = spe.astype(np.float32)
+                            co.erase_grid()
+                            d[ct] = co
+                        st.sets.append(d)
+                    del st._table
+                    pickle.dump([nam, st], f, protocol=-1)
+            LUT.splitfiles.append(fn)
+    return allLUTs, n_split, sp_grids
 
 
 def check_LUT_exists(PTcouples, cartLUTs, mol, iso, LTE):
