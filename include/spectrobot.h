@@ -180,6 +180,12 @@ int sr_lut_create_ld(const float* g32_dev, long row_stride, const double* pt_hos
                      double iso_ratio, int lte_unidentified, const sr_consts* consts,
                      sr_lut** out);
 int sr_lut_destroy(sr_lut* lut);
+/* Bit s of mask: the spontaneous emission of set (level) s contributes to the source function of
+ * the LOS calls that follow (default: all bits set).  Absorption and induced emission are not
+ * affected, so a run with one emitter switched on gives the radiance the observer receives from
+ * that emitter through the whole mixture - the per-gas / per-level `single_rads` of radtrans
+ * (spect_main_module.py:3176-3186, 3242-3246; track_levels :2250-2290).  <= 64 sets. */
+int sr_lut_set_emission_mask(sr_lut* lut, unsigned long long mask);
 
 /* Step tables of a LOS batch (HOST arrays, steps ordered far end -> observer):
  *   n_steps[n_los]; temp, pres [n_los][n_steps_max] (Curtis-Godson T in K, P in hPa);
@@ -273,6 +279,20 @@ int sr_lut_weights(const double* pt_host, int n_cells, double pres, double temp,
  * [spect_classes.py:1180-1191, 883-918, gaussian :1926, conv_single :1162]
  * =========================================================================================*/
 
+/* Low-resolution channels of an instrument.  units says how the channel centres / widths relate to
+ * the hi-res grid: SR_CHAN_SAME_UNITS - same units as the grid; SR_CHAN_NM_FROM_CM1 - grid in cm-1,
+ * channels in nm: the reference first converts the hi-res spectrum to the wavelength axis
+ * (convert_grid_to, spect_classes.py:771-778: grid -> 1e7/grid, spectrum -> spectrum*grid^2*1e-7,
+ * reversed) and convolves there (hires_to_lowres :1180-1191); the kernels do the same per point. */
+#define SR_CHAN_SAME_UNITS  0
+#define SR_CHAN_NM_FROM_CM1 1
+typedef struct {
+    int n_chan;
+    const double *centre_dev, *width_dev;   /* [n_chan], DEVICE pointers */
+    double n_sigma;                         /* window half-width in widths (reference: 5) */
+    int units;
+} sr_channels;
+
 /* spec: [n_spec][n_pts] spectra on the common ascending (possibly irregular) grid[n_pts];
  * channel c integrates spec * N(centre[c], width[c]) with the trapezoid rule over the grid points
  * within +-n_sigma*width[c] (reference default n_sigma = 5); out: [n_spec][n_chan].
@@ -283,6 +303,25 @@ int sr_convolve_lowres_dev(const double* grid_dev, long n_pts, const double* spe
 int sr_convolve_lowres_host(const double* grid, long n_pts, const double* spec, int n_spec,
                             const double* centre, const double* width, int n_chan,
                             double n_sigma, double* out);
+/* Same with a channel set that carries its units (see sr_channels). */
+int sr_convolve_channels_dev(const double* grid_dev, long n_pts, const double* spec_dev, int n_spec,
+                             const sr_channels* ch, double* out_dev, void* stream);
+int sr_convolve_channels_host(const double* grid, long n_pts, const double* spec, int n_spec,
+                              const double* centre, const double* width, int n_chan,
+                              double n_sigma, int units, double* out);
+
+/* sr_los_rt_lut_lowres_dev / sr_los_rt_lut_jac_lowres_dev with a channel set that carries its units
+ * (an observation in nm over a cm-1 hi-res grid, as the reference's VIMS pixels are,
+ * spect_main_module.py:2372): the radiances (and derivative spectra) of every LOS block are
+ * converted per point and convolved on the wavelength axis on the device. */
+int sr_los_rt_lut_channels_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
+                               const double* grid_dev, const sr_channels* ch, const double* i0_dev,
+                               int solo_absorption, double* low_dev, void* stream);
+int sr_los_rt_lut_jac_channels_dev(sr_lut* const* luts, const sr_los_steps* steps, int n_par,
+                                   const int* gas_in_jac, const double* dfrac_host, long pt0,
+                                   long n_pts, const double* grid_dev, const sr_channels* ch,
+                                   const double* i0_dev, int solo_absorption, double* low_dev,
+                                   double* jac_low_dev, void* stream);
 
 /* ===========================================================================================
  * Tier 2 -- LOS geometry and radtran steps for a whole batch
@@ -301,10 +340,41 @@ typedef struct {
     const double *lat_edges, *z;
     const double *temp, *pres;     /* [n_band][n_z], K and hPa */
     const double *vmr;             /* [n_gas][n_band][n_z] */
-    const double *tvib;            /* [n_gas][n_sets_max][n_band][n_z] or NULL */
+    const double *tvib;            /* [n_gas][n_sets_max][n_band][n_sza][n_z] or NULL */
     const int* tvib_on;            /* [n_gas][n_sets_max] (NULL when n_sets_max == 0) */
     double radius_km, top_km;      /* planet radius, atmosphere extension above it */
+    /* Solar-zenith-angle axis of the vibrational temperatures (the reference's 3-D T_vib profiles
+     * are functions of (lat, SZA, alt): radtran_3D_ch4.py:249-250, add_nLTE_molecs_from_tvibmanuel_3D):
+     * n_sza nodes in degrees, ascending; linear between nodes, clamped outside.  n_sza <= 1: no SZA
+     * dependence (sza_nodes may be NULL). */
+    int n_sza;
+    const double* sza_nodes;
 } sr_atmosphere;
+
+/* Rays of a LOS batch.  sun: unit vector from the planet centre towards the Sun per LOS (the
+ * pixel's sub-solar point, spect_main_module.py:3096): the SZA of every sample point is the angle
+ * between its position vector and sun (LineOfSight.calc_SZA_along_los, :3141).  sza_fixed: one SZA
+ * (degrees) used at every point of the LOS instead (use_tangent_sza, :3138-3139).  Both may be
+ * NULL when the atmosphere has no SZA axis. */
+typedef struct {
+    int n_los;
+    const double *origin, *direction;   /* [n_los][3] km, unit vectors */
+    const double *sun;                  /* [n_los][3] or NULL */
+    const double *sza_fixed;            /* [n_los] or NULL */
+} sr_los_rays;
+
+/* Options of calc_atm_intersections / calc_radtran_steps (radtran_3D_ch4.py:200-202, 311;
+ * spect_radtran_test.py:175).  max_opt_depth > 0 adds a third merge limit: a step is closed when
+ * sum_gas sigma_peak[gas] * column_gas over it exceeds max_opt_depth (sigma_peak: the caller's
+ * estimate of the largest absorption cross-section of each gas, cm2 per molecule).  photon_order:
+ * LOS_order='photon' (invert_LOS_direction, spect_main_module.py:3135-3137): samples and steps run
+ * from the observer's side of the atmosphere to the far end, i.e. the layer recursion treats the
+ * observer-side top of the atmosphere as the photons' entry point. */
+typedef struct {
+    double delta_x_km, max_T_variation, max_Plog_variation, max_opt_depth;
+    const double* sigma_peak;           /* [n_gas] or NULL */
+    int photon_order;
+} sr_steps_opt;
 
 /* For n_los rays (origin = observer position, direction = unit vector, planetocentric Cartesian
  * km): samples every delta_x_km anchored on the tangent point between the atmosphere
@@ -322,6 +392,11 @@ int sr_los_steps_build(const sr_atmosphere* atm, int n_los, const double* origin
                        double max_Plog_variation, int n_par, const double* masks, int jac_gas,
                        int n_steps_max, int* n_steps, double* temp, double* pres, double* column,
                        double* tvib, double* dfrac, int* n_steps_needed);
+/* Same with the per-LOS Sun geometry and the full option set. */
+int sr_los_steps_build_rays(const sr_atmosphere* atm, const sr_los_rays* rays, const sr_steps_opt* opt,
+                            int n_par, const double* masks, int jac_gas, int n_steps_max,
+                            int* n_steps, double* temp, double* pres, double* column, double* tvib,
+                            double* dfrac, int* n_steps_needed);
 
 /* FP64 FMA micro-benchmark used by bench.py for the K1/K2 roofline denominator: runs
  * `iters` dependent-chain FMAs per thread on a full grid and returns achieved FLOP/s. */

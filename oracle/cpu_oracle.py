@@ -536,12 +536,16 @@ def FOV_integr_1D(spectra, grid, pixel_rot=0.0):
 
 def los_steps_build(z, temp, pres, vmr, origins, directions, tvib=None, tvib_on=None,
                     lat_edges=None, radius=2575.0, top=1500.0, delta_x=5.0, max_T_variation=5.0,
-                    max_Plog_variation=1.0, masks=None, jac_gas=-1):
+                    max_Plog_variation=1.0, masks=None, jac_gas=-1, sza_nodes=None, sun=None,
+                    sza_fixed=None, photon_order=False, max_opt_depth=None, sigma_peak=None):
     """CPU restatement of the LOS geometry + radtran-step specification with
     the oracle's own Curtis-Godson integrals (orc_curgod_1..4, curgods.f:2-98).  Array conventions
-    as sr_atmosphere / sr_los_steps_build in include/spectrobot.h.  Returns per LOS a dict with
-    n_steps, temp[], pres[], column[n_gas][], tvib[n_gas][n_sets][], dfrac[][n_par].  Plain
-    Python loops: small cases only."""
+    as sr_atmosphere / sr_los_rays / sr_steps_opt in include/spectrobot.h: tvib may carry an SZA
+    axis [n_gas][n_sets][n_band][n_sza][n_z] with sza_nodes (linear between nodes, clamped); the SZA
+    of a sample is the angle between its position and `sun` [n_los][3], or sza_fixed[n_los];
+    photon_order reverses the sample sequence; max_opt_depth closes a step when sum_gas sigma_peak *
+    column exceeds it.  Returns per LOS a dict with n_steps, temp[], pres[], column[n_gas][],
+    tvib[n_gas][n_sets][], dfrac[][n_par].  Plain Python loops: small cases only."""
     kb_hpa = 1.38065e-19
     z = np.asarray(z, dtype=float)
     temp = np.asarray(temp, dtype=float).reshape(-1, len(z))
@@ -552,14 +556,21 @@ def los_steps_build(z, temp, pres, vmr, origins, directions, tvib=None, tvib_on=
     n_sets = 0 if tvib_on is None else np.asarray(tvib_on).reshape(n_gas, -1).shape[1]
     if n_sets:
         tvib_on = np.asarray(tvib_on).reshape(n_gas, n_sets)
-        tvib = None if tvib is None else np.asarray(tvib, dtype=float).reshape(n_gas, n_sets, n_band, len(z))
+        n_sza = 1 if sza_nodes is None else max(len(sza_nodes), 1)
+        tvib = None if tvib is None else np.asarray(tvib, dtype=float).reshape(n_gas, n_sets, n_band,
+                                                                               n_sza, len(z))
     if masks is not None:   # [n_par][n_z] or [n_par][n_band][n_z]
         masks = np.asarray(masks, dtype=float)
         if masks.ndim == 2:
             masks = np.repeat(masks[:, None, :], n_band, axis=1)
     out = []
-    for o, d in zip(np.asarray(origins, dtype=float).reshape(-1, 3),
-                    np.asarray(directions, dtype=float).reshape(-1, 3)):
+    origins = np.asarray(origins, dtype=float).reshape(-1, 3)
+    if sun is not None:
+        sun = np.asarray(sun, dtype=float)
+        sun = np.broadcast_to(sun / np.linalg.norm(sun, axis=-1, keepdims=True), origins.shape)
+    if sza_fixed is not None:
+        sza_fixed = np.broadcast_to(np.asarray(sza_fixed, dtype=float), (len(origins),))
+    for il, (o, d) in enumerate(zip(origins, np.asarray(directions, dtype=float).reshape(-1, 3))):
         st = -float(np.dot(o, d))
         rt = float(np.linalg.norm(o + st * d))
         r_top = radius + top
@@ -576,31 +587,52 @@ def los_steps_build(z, temp, pres, vmr, origins, directions, tvib=None, tvib_on=
         inner = st + delta_x * np.arange(kmax, -kmax - 1, -1)
         inner = inner[(inner < s_far - 1e-6) & (inner > s_near + 1e-6)]
         s = np.concatenate([[s_far], inner, [s_near]])
+        if photon_order:
+            s = s[::-1]
         pts = o[None, :] + s[:, None] * d[None, :]
         r = np.sqrt((pts ** 2).sum(axis=1))
         alt = r - radius
+        sza = np.zeros(len(s))
+        if sza_fixed is not None:
+            sza[:] = sza_fixed[il]
+        elif sun is not None:
+            sza = np.degrees(np.arccos(np.clip(pts @ sun[il] / r, -1.0, 1.0)))
         band = np.zeros(len(s), dtype=int)
         if n_band > 1:
             lat = np.degrees(np.arcsin(pts[:, 2] / r))
             band = np.clip(np.searchsorted(lat_edges, lat, side='right') - 1, 0, n_band - 1)
         at = lambda tab: np.array([np.interp(a, z, tab[b]) for a, b in zip(alt, band)])  # noqa: E731
+
+        def at_sza(tab):   # [n_band][n_sza][n_z]: linear in z, then linear between SZA nodes
+            if tab.shape[1] == 1:
+                return at(tab[:, 0])
+            res = np.empty(len(s))
+            for i, (a, b, sz) in enumerate(zip(alt, band, sza)):
+                col = np.array([np.interp(a, z, tab[b, j]) for j in range(tab.shape[1])])
+                res[i] = np.interp(sz, sza_nodes, col)
+            return res
+
         T = at(temp)
         P = np.exp(at(np.log(pres)))
         nd = P / (kb_hpa * T)
-        x = (s[0] - s) * 1.e5
+        x = np.abs(s[0] - s) * 1.e5
         lnP = np.log(P)
         n = len(s)
+        vm = [at(vmr[m]) for m in range(n_gas)]
         bounds, i0 = [], 0
         for i in range(1, n):
             sl = slice(i0, i + 1)
+            too_thick = False
+            if max_opt_depth is not None and max_opt_depth > 0.0:
+                tau = sum(sigma_peak[m] * curgod(2, nd[sl], vm[m][sl], x[sl]) for m in range(n_gas))
+                too_thick = tau > max_opt_depth
             if (T[sl].max() - T[sl].min() > max_T_variation or
-                    lnP[sl].max() - lnP[sl].min() > max_Plog_variation) and i - i0 >= 2:
+                    lnP[sl].max() - lnP[sl].min() > max_Plog_variation or too_thick) and i - i0 >= 2:
                 bounds.append((i0, i - 1))
                 i0 = i - 1
         if n >= 2:
             bounds.append((i0, n - 1))
         res["n_steps"] = len(bounds)
-        vm = [at(vmr[m]) for m in range(n_gas)]
         for a, e in bounds:
             sl = slice(a, e + 1)
             ones = np.ones(e - a + 1)
@@ -613,7 +645,7 @@ def los_steps_build(z, temp, pres, vmr, origins, directions, tvib=None, tvib_on=
                 res["column"][m].append(col)
                 for j in range(n_sets):
                     if tvib_on[m, j] > 0:
-                        tv = curgod(3, nd[sl], vm[m][sl], at(tvib[m, j])[sl], x[sl]) / col
+                        tv = curgod(3, nd[sl], vm[m][sl], at_sza(tvib[m, j])[sl], x[sl]) / col
                     else:
                         tv = t_cg if tvib_on[m, j] == 0 else 100.0
                     res["tvib"][m][j].append(tv)

@@ -51,8 +51,27 @@ class sr_los_steps(C.Structure):
 class sr_atmosphere(C.Structure):
     _fields_ = [("n_band", C.c_int), ("n_z", C.c_int), ("n_gas", C.c_int), ("n_sets_max", C.c_int),
                 ("lat_edges", _dp), ("z", _dp), ("temp", _dp), ("pres", _dp), ("vmr", _dp),
-                ("tvib", _dp), ("tvib_on", _ip), ("radius_km", C.c_double), ("top_km", C.c_double)]
+                ("tvib", _dp), ("tvib_on", _ip), ("radius_km", C.c_double), ("top_km", C.c_double),
+                ("n_sza", C.c_int), ("sza_nodes", _dp)]
 
+
+class sr_los_rays(C.Structure):
+    _fields_ = [("n_los", C.c_int), ("origin", _dp), ("direction", _dp), ("sun", _dp),
+                ("sza_fixed", _dp)]
+
+
+class sr_steps_opt(C.Structure):
+    _fields_ = [("delta_x_km", C.c_double), ("max_T_variation", C.c_double),
+                ("max_Plog_variation", C.c_double), ("max_opt_depth", C.c_double),
+                ("sigma_peak", _dp), ("photon_order", C.c_int)]
+
+
+class sr_channels(C.Structure):
+    _fields_ = [("n_chan", C.c_int), ("centre_dev", _vp), ("width_dev", _vp),
+                ("n_sigma", C.c_double), ("units", C.c_int)]
+
+
+SR_CHAN_SAME_UNITS, SR_CHAN_NM_FROM_CM1 = 0, 1
 
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 SIGNATURES = {
@@ -88,6 +107,7 @@ SIGNATURES = {
                                    C.c_int, C.c_double, C.c_int, C.POINTER(sr_consts),
                                    C.POINTER(_vp)]),
     "sr_lut_destroy": (C.c_int, [_vp]),
+    "sr_lut_set_emission_mask": (C.c_int, [_vp, C.c_ulonglong]),
     "sr_los_rt_lut_dev": (C.c_int, [C.POINTER(_vp), C.POINTER(sr_los_steps), C.c_long, C.c_long,
                                     _vp, C.c_int, _vp, _vp]),
     "sr_los_rt_lut_lowres_dev": (C.c_int, [C.POINTER(_vp), C.POINTER(sr_los_steps), C.c_long,
@@ -112,9 +132,23 @@ SIGNATURES = {
                                          C.c_double, _vp, _vp]),
     "sr_convolve_lowres_host": (C.c_int, [_dp, C.c_long, _dp, C.c_int, _dp, _dp, C.c_int,
                                           C.c_double, _dp]),
+    "sr_convolve_channels_dev": (C.c_int, [_vp, C.c_long, _vp, C.c_int, C.POINTER(sr_channels), _vp,
+                                           _vp]),
+    "sr_convolve_channels_host": (C.c_int, [_dp, C.c_long, _dp, C.c_int, _dp, _dp, C.c_int,
+                                            C.c_double, C.c_int, _dp]),
+    "sr_los_rt_lut_channels_dev": (C.c_int, [C.POINTER(_vp), C.POINTER(sr_los_steps), C.c_long,
+                                             C.c_long, _vp, C.POINTER(sr_channels), _vp, C.c_int,
+                                             _vp, _vp]),
+    "sr_los_rt_lut_jac_channels_dev": (C.c_int, [C.POINTER(_vp), C.POINTER(sr_los_steps), C.c_int,
+                                                 _ip, _dp, C.c_long, C.c_long, _vp,
+                                                 C.POINTER(sr_channels), _vp, C.c_int, _vp, _vp,
+                                                 _vp]),
     "sr_los_steps_build": (C.c_int, [C.POINTER(sr_atmosphere), C.c_int, _dp, _dp, C.c_double,
                                      C.c_double, C.c_double, C.c_int, _dp, C.c_int, C.c_int, _ip,
                                      _dp, _dp, _dp, _dp, _dp, _ip]),
+    "sr_los_steps_build_rays": (C.c_int, [C.POINTER(sr_atmosphere), C.POINTER(sr_los_rays),
+                                          C.POINTER(sr_steps_opt), C.c_int, _dp, C.c_int, C.c_int,
+                                          _ip, _dp, _dp, _dp, _dp, _dp, _ip]),
     "sr_fp64_peak": (C.c_int, [C.c_int, _dp]),
 }
 

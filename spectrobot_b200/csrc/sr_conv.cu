@@ -20,19 +20,29 @@ constexpr int CONV_SLAB = 512;   // spectra per launch pair (bounds the partial-
 // segments per CTA are template parameters; (8, 1024) measured best on B200 (SR_CONV_CFG)
 
 // per channel: segments [i0, i1) of the trapezoid rule = hi-res points i0..i1 inside the window
+// units == SR_CHAN_NM_FROM_CM1: the grid is in cm-1 and the channels in nm.  The reference converts
+// the hi-res spectrum first (convert_grid_to('nm'), spect_classes.py:771-778: grid -> 1e7/grid,
+// spectrum -> spectrum*grid^2*1e-7, both reversed so that the grid ascends) and convolves on the
+// wavelength axis.  Here the axis is mirrored instead of reversed - abscissa u = -1e7/x ascends with
+// x, the channel sits at -centre - which leaves the Gaussian (even in u - f) and every trapezoid
+// (|du| and the pair of ordinates) unchanged.
+__device__ __forceinline__ double conv_abscissa(double x, int units) {
+    return units == SR_CHAN_NM_FROM_CM1 ? -1.0e7 / x : x;
+}
+
 __global__ void k_convolve_windows(const double* __restrict__ x, long n_pts,
                                    const double* __restrict__ centre,
                                    const double* __restrict__ width, int n_chan, double n_sigma,
-                                   long* __restrict__ win) {
+                                   int units, long* __restrict__ win) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chan) return;
-    const double f = centre[c], w = width[c];
+    const double f = units == SR_CHAN_NM_FROM_CM1 ? -centre[c] : centre[c], w = width[c];
     const double lo = f - n_sigma * w, hi = f + n_sigma * w;
-    long a = 0, b = n_pts;   // first index with x >= lo, last index with x <= hi (grid ascending)
-    while (a < b) { const long m = (a + b) >> 1; if (x[m] < lo) a = m + 1; else b = m; }
+    long a = 0, b = n_pts;   // first index with u >= lo, last index with u <= hi (u ascending)
+    while (a < b) { const long m = (a + b) >> 1; if (conv_abscissa(x[m], units) < lo) a = m + 1; else b = m; }
     win[2 * c] = a;
     b = n_pts;
-    while (a < b) { const long m = (a + b) >> 1; if (x[m] <= hi) a = m + 1; else b = m; }
+    while (a < b) { const long m = (a + b) >> 1; if (conv_abscissa(x[m], units) <= hi) a = m + 1; else b = m; }
     win[2 * c + 1] = a - 1;
 }
 
@@ -46,7 +56,7 @@ template <int CONV_SPB, int CONV_PB>
 __global__ void __launch_bounds__(CONV_NT) k_convolve_lowres(
     const double* __restrict__ x, long n_pts, const double* __restrict__ spec, int n_spec,
     const double* __restrict__ centre, const double* __restrict__ width, int n_chan,
-    const long* __restrict__ win, int n_blocks, double* __restrict__ partial) {
+    const long* __restrict__ win, int n_blocks, int units, double* __restrict__ partial) {
     const long bstart = (long)blockIdx.x * CONV_PB;
     const long bend = min(bstart + CONV_PB, n_pts - 1);
     const int np = (int)(bend - bstart) + 1;          // points bstart .. bend
@@ -102,12 +112,21 @@ __global__ void __launch_bounds__(CONV_NT) k_convolve_lowres(
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
+    if (units == SR_CHAN_NM_FROM_CM1) {   // spectrum per nm on the mirrored wavelength axis
+        for (int i = threadIdx.x; i < np; i += CONV_NT) {
+            const double xv = xs[i], jac = xv * xv * 1.e-7;
+#pragma unroll
+            for (int q = 0; q < CONV_SPB; q++) ys[q * (CONV_PB + 1) + i] *= jac;
+            xs[i] = -1.0e7 / xv;
+        }
+        __syncthreads();
+    }
     for (int ci = 0; ci < n_list; ci++) {              // (clist is published by the barrier above)
         const int c = listed ? clist[ci] : ci;
         const long s0l = max(win[2 * c], bstart), s1l = min(win[2 * c + 1], bend);
         if (s1l <= s0l) continue;                      // uniform over the CTA
         const int s0 = (int)(s0l - bstart), s1 = (int)(s1l - bstart);
-        const double f = centre[c], w = width[c];
+        const double f = units == SR_CHAN_NM_FROM_CM1 ? -centre[c] : centre[c], w = width[c];
         const double fac = 1.0 / (w * sqrt(2.0 * M_PI));
         double acc[CONV_SPB];
 #pragma unroll
@@ -161,9 +180,21 @@ extern "C" {
 int sr_convolve_lowres_dev(const double* grid_dev, long n_pts, const double* spec_dev, int n_spec,
                            const double* centre_dev, const double* width_dev, int n_chan,
                            double n_sigma, double* out_dev, void* stream) {
+    sr_channels ch{n_chan, centre_dev, width_dev, n_sigma, SR_CHAN_SAME_UNITS};
+    return sr_convolve_channels_dev(grid_dev, n_pts, spec_dev, n_spec, &ch, out_dev, stream);
+}
+
+int sr_convolve_channels_dev(const double* grid_dev, long n_pts, const double* spec_dev, int n_spec,
+                             const sr_channels* ch, double* out_dev, void* stream) {
+    if (!ch) return sr::fail(SR_ERR_ARG, "sr_convolve_channels_dev: bad argument");
+    const double* centre_dev = ch->centre_dev;
+    const double* width_dev = ch->width_dev;
+    const int n_chan = ch->n_chan, units = ch->units;
+    const double n_sigma = ch->n_sigma;
     if (!grid_dev || !spec_dev || !centre_dev || !width_dev || !out_dev || n_pts < 1 ||
-        n_spec < 1 || n_chan < 1 || !(n_sigma > 0.0))
-        return sr::fail(SR_ERR_ARG, "sr_convolve_lowres_dev: bad argument");
+        n_spec < 1 || n_chan < 1 || !(n_sigma > 0.0) ||
+        (units != SR_CHAN_SAME_UNITS && units != SR_CHAN_NM_FROM_CM1))
+        return sr::fail(SR_ERR_ARG, "sr_convolve_channels_dev: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     static const int cfg = getenv("SR_CONV_CFG") ? atoi(getenv("SR_CONV_CFG")) : 0;   // tuning aid
     const int spb = (cfg == 1 || cfg == 3) ? 4 : 8;
@@ -184,12 +215,12 @@ int sr_convolve_lowres_dev(const double* grid_dev, long n_pts, const double* spe
         const size_t smem = (size_t)(spb + 1) * (pb + 1) * sizeof(double);
         SR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SR_LAUNCH(kern, grid, CONV_NT, smem, st, grid_dev, n_pts, sp, ns, centre_dev, width_dev, n_chan,
-                  win, n_blocks, partial);
+                  win, n_blocks, units, partial);
         return SR_OK;
     };
     auto body = [&]() -> int {
         SR_LAUNCH(k_convolve_windows, (n_chan + 63) / 64, 64, 0, st, grid_dev, n_pts, centre_dev,
-                  width_dev, n_chan, n_sigma, win);
+                  width_dev, n_chan, n_sigma, units, win);
         for (int s0 = 0; s0 < n_spec; s0 += slab) {
             const int ns = std::min(slab, n_spec - s0);
             dim3 grid((unsigned)n_blocks, (unsigned)((ns + spb - 1) / spb));
@@ -214,6 +245,13 @@ int sr_convolve_lowres_dev(const double* grid_dev, long n_pts, const double* spe
 int sr_convolve_lowres_host(const double* grid, long n_pts, const double* spec, int n_spec,
                             const double* centre, const double* width, int n_chan,
                             double n_sigma, double* out) {
+    return sr_convolve_channels_host(grid, n_pts, spec, n_spec, centre, width, n_chan, n_sigma,
+                                     SR_CHAN_SAME_UNITS, out);
+}
+
+int sr_convolve_channels_host(const double* grid, long n_pts, const double* spec, int n_spec,
+                              const double* centre, const double* width, int n_chan,
+                              double n_sigma, int units, double* out) {
     if (!grid || !spec || !centre || !width || !out || n_pts < 1 || n_spec < 1 || n_chan < 1)
         return sr::fail(SR_ERR_ARG, "sr_convolve_lowres_host: bad argument");
     for (int c = 0; c < n_chan; c++)
@@ -224,8 +262,8 @@ int sr_convolve_lowres_host(const double* grid, long n_pts, const double* spec, 
     SR_CUDA(dc.upload(centre, n_chan));
     SR_CUDA(dw.upload(width, n_chan));
     SR_CUDA(dout.alloc((size_t)n_spec * n_chan));
-    int rc = sr_convolve_lowres_dev(dx.p, n_pts, dy.p, n_spec, dc.p, dw.p, n_chan, n_sigma,
-                                    dout.p, nullptr);
+    sr_channels ch{n_chan, dc.p, dw.p, n_sigma, units};
+    int rc = sr_convolve_channels_dev(dx.p, n_pts, dy.p, n_spec, &ch, dout.p, nullptr);
     if (rc) return rc;
     SR_CUDA(cudaMemcpy(out, dout.p, sizeof(double) * n_spec * n_chan, cudaMemcpyDeviceToHost));
     return SR_OK;

@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <vector>
 #include "sr_common.h"
 #include "sr_device.cuh"
@@ -169,15 +170,16 @@ __global__ void k_step_weights(const __grid_constant__ StepArgs a) {
 // which LUT rows (set, ctype) hold any non-zero value (over all cells and grid points)
 __global__ void k_row_nonzero(const float* __restrict__ g32, int n_cells, int n_sets, long n_grid,
                               long row_stride, int* __restrict__ rowmask) {
-    const int r = blockIdx.y;                 // (cell, set, ctype) row
-    const int s = (r / 3) % n_sets, ct = r % 3;
-    const float* __restrict__ p = g32 + (size_t)r * row_stride;
-    bool nz = false;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_grid;
-         i += (long)gridDim.x * blockDim.x)
-        nz |= (p[i] != 0.0f);
-    if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(rowmask + s, 1 << ct);
-    (void)n_cells;
+    const long n_rows = (long)n_cells * n_sets * 3;
+    for (long r = blockIdx.y; r < n_rows; r += gridDim.y) {   // (cell, set, ctype) row
+        const int s = (int)((r / 3) % n_sets), ct = (int)(r % 3);
+        const float* __restrict__ p = g32 + (size_t)r * row_stride;
+        bool nz = false;
+        for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_grid;
+             i += (long)gridDim.x * blockDim.x)
+            nz |= (p[i] != 0.0f);
+        if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) atomicOr(rowmask + s, 1 << ct);
+    }
 }
 
 struct LosArgs {
@@ -316,6 +318,7 @@ struct RecArgs {
     long n_pts, io_stride, io_off, lay_stride;
     long n_work;              // n_los * n_tiles (0: nothing to do)
     int n_steps_max, n_tiles, solo, src_is_j;
+    int keep;                 // layers were just written and are expected in L2: plain loads
 };
 
 template <int PPT, int UNROLL, int NT>
@@ -334,6 +337,8 @@ __device__ __forceinline__ void layers_item(const RecArgs& r, int l, int tile) {
     const double* __restrict__ tp = r.tau + (size_t)l * r.n_steps_max * ls + p0;
     const double* __restrict__ sp = r.src + (size_t)l * r.n_steps_max * ls + p0;
     const int solo = r.solo, src_is_j = r.src_is_j;
+    const bool keep = r.keep != 0;
+    auto ldl = [&](const double* p) { return keep ? __ldcg(p) : __ldcs(p); };
     auto update = [&](int i, double t, double s) {
         double ex, em;
         srdev::exp_pair(-t, ex, em);
@@ -352,8 +357,8 @@ __device__ __forceinline__ void layers_item(const RecArgs& r, int l, int tile) {
 #pragma unroll
             for (int i = 0; i < PPT; i++) {
                 const size_t o = (size_t)(k + u) * ls + i * NT;
-                t[u][i] = ok[i] ? __ldcs(tp + o) : 0.0;
-                s[u][i] = ok[i] ? __ldcs(sp + o) : 0.0;
+                t[u][i] = ok[i] ? ldl(tp + o) : 0.0;
+                s[u][i] = ok[i] ? ldl(sp + o) : 0.0;
             }
 #pragma unroll
         for (int u = 0; u < UNROLL; u++)
@@ -363,7 +368,7 @@ __device__ __forceinline__ void layers_item(const RecArgs& r, int l, int tile) {
     for (; k < ns; k++)
 #pragma unroll
         for (int i = 0; i < PPT; i++)
-            if (ok[i]) update(i, __ldcs(tp + (size_t)k * ls + i * NT), __ldcs(sp + (size_t)k * ls + i * NT));
+            if (ok[i]) update(i, ldl(tp + (size_t)k * ls + i * NT), ldl(sp + (size_t)k * ls + i * NT));
 #pragma unroll
     for (int i = 0; i < PPT; i++)
         if (ok[i]) __stcs(r.rad + (size_t)l * r.io_stride + r.io_off + p0 + i * NT, I[i]);
@@ -398,7 +403,8 @@ struct JacArgs {
 
 // phi'(t) for phi(t) = (1 - e^-t)/t, given ex = e^-t and phi
 __device__ __forceinline__ double dphi(double t, double ex, double phi) {
-    if (t < 0.05)   // Taylor series: the closed form cancels like eps/t
+    if (fabs(t) < 0.05)   // Taylor series: the closed form cancels like eps/t near 0 (tau < 0 under
+                          // population inversion takes the closed form like tau > 0)
         return fma(t, fma(t, fma(t, fma(t, fma(t, 1.0 / 840.0, -1.0 / 144.0), 1.0 / 30.0), -0.125),
                           1.0 / 3.0), -0.5);
     return (ex - phi) / t;
@@ -510,6 +516,8 @@ struct MmaArgs {
     double* tau_out;              // [pairs of the block][ld_out]
     double* src_out;
     int mode;                     // 0: src = S = J/tau, 1: src = J
+    int keep;                     // 1: the layer rows are read back at once (L2-sized scratch):
+                                  // default-policy stores instead of streaming ones
 };
 
 struct PackArgs {
@@ -522,6 +530,8 @@ struct PackArgs {
     long n_pairs_tot;
     int n_sets_max, max_jp, n_chunks;
     unsigned gas_mask;            // LUTs whose weights are packed (the others get 0)
+    const int* grp_ntau;          // rows [grp_ntau, grp_ntot) of a program are emission rows
+    unsigned long long emis[MAX_GAS];   // per LUT: sets whose spontaneous emission is kept
 };
 
 __global__ void k_pack_wfrag(PackArgs a) {
@@ -535,7 +545,8 @@ __global__ void k_pack_wfrag(PackArgs a) {
     const ProgEntry pe = a.prog[(size_t)grp * a.max_jp + j];
     const int pr = a.chunk_pair[chunk * MMA_PB + slot];
     double w = 0.0;
-    if (pr >= 0 && pe.gas >= 0 && ((a.gas_mask >> pe.gas) & 1u))
+    if (pr >= 0 && pe.gas >= 0 && ((a.gas_mask >> pe.gas) & 1u) &&
+        (j < a.grp_ntau[grp] || ((a.emis[pe.gas] >> (pe.widx >> 2)) & 1ull)))
         w = a.W[((size_t)pe.gas * a.n_pairs_tot + pr) * ((size_t)a.n_sets_max * 4) + pe.widx];
     if (pe.neg) w = -w;
     const int kb = j >> 2, kq = j & 3, mb = slot >> 3, row = slot & 7;
@@ -558,6 +569,10 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 // one 32-byte streaming store (a full sector per lane)
 __device__ __forceinline__ void st_cs_v4(double* p, const double (&x)[4]) {
     asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]),
+                 "d"(x[3]) : "memory");
+}
+__device__ __forceinline__ void st_cg_v4(double* p, const double (&x)[4]) {
+    asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]),
                  "d"(x[3]) : "memory");
 }
 
@@ -694,7 +709,7 @@ __global__ void __launch_bounds__(MMA_NT, MINB) k_los_mma(MmaArgs a) {
                                 x[i] = (t == 0.0) ? 0.0 : x[i] / t;
                             }
                         }
-                        st_cs_v4(o + off, x);
+                        if (a.keep) st_cg_v4(o + off, x); else st_cs_v4(o + off, x);
                     }
             } else {
 #pragma unroll
@@ -708,7 +723,7 @@ __global__ void __launch_bounds__(MMA_NT, MINB) k_los_mma(MmaArgs a) {
                             const double t = t_in[off];
                             x = (t == 0.0) ? 0.0 : x / t;
                         }
-                        __stcs(o + off, x);
+                        if (a.keep) __stcg(o + off, x); else __stcs(o + off, x);
                     }
             }
         }
@@ -729,6 +744,7 @@ struct sr_lut {
     int n_cells = 0, n_sets = 0, mol = 0, iso = 0, lte_unidentified = 0;
     long n_grid = 0, row_stride = 0;
     double iso_ratio = 1.0;
+    unsigned long long emis_mask = ~0ull;   // sr_lut_set_emission_mask
     sr_consts c{};
     std::vector<double> pt, Ps, Ts;
     std::vector<int> cellmap;
@@ -743,7 +759,16 @@ struct sr_lut {
     sr::DevBuf<double> g_wfrag;
     sr::DevBuf<int> g_ntau, g_ntot, g_cgrp, g_cpair;
     cudaStream_t copy_stream = nullptr; // device -> host copies of the host-buffer entry point
-    ~sr_lut() { if (copy_stream) cudaStreamDestroy(copy_stream); }
+    // One LOS call at a time per handle: the per-call scratch below lives in luts[0].  `mtx`
+    // serialises the host side of concurrent callers; `busy` is recorded on the caller's stream at
+    // the end of a call and waited for at the start of the next one, so that a call on another
+    // stream cannot overwrite scratch that queued kernels still read.
+    std::mutex mtx;
+    cudaEvent_t busy = nullptr;
+    ~sr_lut() {
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (busy) cudaEventDestroy(busy);
+    }
     // per-call scratch (owned by the first LUT of a call)
     sr::DevBuf<int> cells, nsteps, flags;
     sr::DevBuf<double> W, temp, pres, column, tvib;
@@ -919,7 +944,7 @@ int sr_lut_create_ld(const float* g32_dev, long row_stride, const double* pt_hos
         SR_CUDA(L->drowmask.alloc(n_sets));
         SR_CUDA(cudaMemset(L->drowmask.p, 0, sizeof(int) * n_sets));
         {
-            dim3 grid(8, (unsigned)(n_cells * n_sets * 3));
+            dim3 grid(8, (unsigned)std::min<long>((long)n_cells * n_sets * 3, 65535));
             SR_LAUNCH(k_row_nonzero, grid, 256, 0, 0, g32_dev, n_cells, n_sets, n_grid, row_stride,
                       L->drowmask.p);
         }
@@ -943,6 +968,14 @@ int sr_lut_create_ld(const float* g32_dev, long row_stride, const double* pt_hos
 
 int sr_lut_destroy(sr_lut* lut) {
     delete lut;
+    return SR_OK;
+}
+
+int sr_lut_set_emission_mask(sr_lut* lut, unsigned long long mask) {
+    if (!lut) return sr::fail(SR_ERR_ARG, "sr_lut_set_emission_mask: bad argument");
+    if (lut->n_sets > 64 && mask != ~0ull)
+        return sr::fail(SR_ERR_LIMIT, "emission masks cover at most 64 sets");
+    lut->emis_mask = mask;
     return SR_OK;
 }
 
@@ -1006,22 +1039,24 @@ static RecArgs rec_args(const double* tau, const double* src, const int* n_steps
     r.n_work = (long)r.n_tiles * n_los;
     r.solo = solo_absorption;
     r.src_is_j = src_is_j;
+    r.keep = 0;
     return r;
 }
 
 static int layers_launch(const double* tau, const double* src, const int* n_steps, int n_los,
                          int n_steps_max, long n_pts, const double* i0, int solo_absorption,
                          double* rad, cudaStream_t st, int src_is_j, long io_stride = -1,
-                         long io_off = 0, long lay_stride = -1) {
+                         long io_off = 0, long lay_stride = -1, int keep = 0) {
     // measured on B200 (tools/tune.py): (PPT=1, UNROLL=4) at 38 registers streams at the
     // measured copy bandwidth; wider variants lose occupancy
     int cfg = 5;
     if (const char* e = getenv("SR_K3_CFG")) cfg = atoi(e);   // tuning aid
 #define SR_K3_LAUNCH(PPT, UNROLL)                                                             \
     {                                                                                          \
-        const RecArgs r = rec_args(tau, src, n_steps, n_los, n_steps_max, n_pts, i0,           \
-                                   solo_absorption, rad, src_is_j, io_stride, io_off,          \
-                                   lay_stride, 256 * PPT);                                     \
+        RecArgs r = rec_args(tau, src, n_steps, n_los, n_steps_max, n_pts, i0,                 \
+                             solo_absorption, rad, src_is_j, io_stride, io_off,                \
+                             lay_stride, 256 * PPT);                                           \
+        r.keep = keep;                                                                         \
         SR_LAUNCH((k_los_layers<PPT, UNROLL>), dim3((unsigned)r.n_tiles, (unsigned)n_los), 256, \
                   0, st, r);                                                                   \
     }
@@ -1301,6 +1336,7 @@ struct LowSink {
     int n_chan;
     double n_sigma;
     double* low_dev;            // [n_los][n_chan]
+    int units;                  // SR_CHAN_* (sr_channels)
 };
 
 // analytic Jacobians of the batch (k_los_layers_jac)
@@ -1312,10 +1348,30 @@ struct JacSpec {
     double* jac_low_dev;        // low-res [n_los][n_par][n_chan] (with a LowSink)
 };
 
+static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
+                             const double* i0_dev, int solo, double* rad_dev, double* tau_dev,
+                             double* src_dev, cudaStream_t st, int emit_j, HostSink* sink,
+                             LowSink* low, JacSpec* jac);
+
 static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
                       const double* i0_dev, int solo, double* rad_dev, double* tau_dev,
                       double* src_dev, cudaStream_t st, int emit_j = 0, HostSink* sink = nullptr,
                       LowSink* low = nullptr, JacSpec* jac = nullptr) {
+    if (!luts || !luts[0]) return sr::fail(SR_ERR_ARG, "LOS: missing LUT");
+    sr_lut* L0 = luts[0];
+    std::lock_guard<std::mutex> guard(L0->mtx);
+    if (L0->busy) SR_CUDA(cudaEventSynchronize(L0->busy));
+    else SR_CUDA(cudaEventCreateWithFlags(&L0->busy, cudaEventDisableTiming));
+    const int rc = los_launch_locked(luts, steps, pt0, n_pts, i0_dev, solo, rad_dev, tau_dev, src_dev,
+                                     st, emit_j, sink, low, jac);
+    cudaEventRecord(L0->busy, st);
+    return rc;
+}
+
+static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
+                             const double* i0_dev, int solo, double* rad_dev, double* tau_dev,
+                             double* src_dev, cudaStream_t st, int emit_j, HostSink* sink,
+                             LowSink* low, JacSpec* jac) {
     LosArgs la;
     int rc = prepare_steps(luts, steps, st, la);
     if (rc) return rc;
@@ -1331,6 +1387,9 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
     const unsigned all_gas = (steps->n_gas >= 32) ? ~0u : ((1u << steps->n_gas) - 1u);
     const bool jac_multi = jac && (jac->gas_mask & all_gas) != all_gas;
     if (ver == 1) {
+        for (int m = 0; m < steps->n_gas; m++)
+            if (luts[m]->emis_mask != ~0ull)
+                return sr::fail(SR_ERR_ARG, "emission masks need the grouped LOS path");
         if (sink) {   // plain path: whole batch on the device, then one copy
             const size_t n = (size_t)n_los * n_pts;
             SR_CUDA(L0->ws_rad[0].ensure(n));
@@ -1452,6 +1511,8 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         pa.max_jp = P.max_jp;
         pa.n_chunks = P.n_chunks;
         pa.gas_mask = ~0u;
+        pa.grp_ntau = L0->g_ntau.p;
+        for (int m = 0; m < MAX_GAS; m++) pa.emis[m] = m < steps->n_gas ? luts[m]->emis_mask : ~0ull;
         const long n_el = (long)P.n_chunks * P.max_jp * MMA_PB;
         SR_LAUNCH(k_pack_wfrag, (unsigned)((n_el + 255) / 256), 256, 0, st, pa);
         if (jac_multi) {   // second weight set: the retrieved gas alone
@@ -1478,6 +1539,7 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         ma.tau_out = tau_dev;
         ma.src_out = src_dev;
         ma.mode = emit_j;
+        ma.keep = 0;
         dim3 grid((unsigned)P.n_chunks, (unsigned)((n_pts + TILE - 1) / TILE));
         const bool vec = rows_aligned && pt0 % 4 == 0 && n_pts % 4 == 0 &&
                          ((size_t)tau_dev | (size_t)src_dev) % 32 == 0;
@@ -1509,6 +1571,7 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
         if (low) SR_CUDA(L0->ws_jac.ensure((size_t)nl_block * jac->n_par * n_pts));
     }
     int status = SR_OK;
+    static const int l2keep = getenv("SR_LOS_L2KEEP") ? atoi(getenv("SR_LOS_L2KEEP")) : 0;
     auto body = [&]() -> int {
         for (int b = 0; b < n_blocks; b++) {
             const int l0 = P.blk_los[b], nl = P.blk_los[b + 1] - l0;
@@ -1542,6 +1605,7 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
                     ma.tau_out = L0->ws_tau.p;
                     ma.src_out = L0->ws_src.p;
                     ma.mode = 1;
+                    ma.keep = l2keep;
                     dim3 grid((unsigned)n_ch, (unsigned)((np + TILE - 1) / TILE));
                     ma.wfrag = L0->g_wfrag.p;
                     int code = mma_launch(rows_aligned && (pt0 + c0) % 4 == 0, grid, smem, st, ma);
@@ -1568,7 +1632,7 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
                 } else {
                     code = layers_launch(L0->ws_tau.p, L0->ws_src.p, la.n_steps + l0, nl,
                                          steps->n_steps_max, np, i0_blk, solo, rad_blk, st, 1, n_pts,
-                                         c0, ld_lay);
+                                         c0, ld_lay, l2keep);
                 }
                 if (code) return code;
                 if (sink) {
@@ -1588,16 +1652,16 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
                 SR_CUDA(cudaEventRecord(buf_free[b & 1], L0->copy_stream));
             }
             if (low) {
-                int code = sr_convolve_lowres_dev(low->grid_dev, n_pts, rad_blk, nl, low->centre_dev,
-                                                  low->width_dev, low->n_chan, low->n_sigma,
-                                                  low->low_dev + (size_t)l0 * low->n_chan, st);
+                const sr_channels ch{low->n_chan, low->centre_dev, low->width_dev, low->n_sigma,
+                                     low->units};
+                int code = sr_convolve_channels_dev(low->grid_dev, n_pts, rad_blk, nl, &ch,
+                                                    low->low_dev + (size_t)l0 * low->n_chan, st);
                 if (code) return code;
                 if (jac) {
-                    code = sr_convolve_lowres_dev(low->grid_dev, n_pts, L0->ws_jac.p, nl * jac->n_par,
-                                                  low->centre_dev, low->width_dev, low->n_chan,
-                                                  low->n_sigma,
-                                                  jac->jac_low_dev + (size_t)l0 * jac->n_par * low->n_chan,
-                                                  st);
+                    code = sr_convolve_channels_dev(low->grid_dev, n_pts, L0->ws_jac.p, nl * jac->n_par,
+                                                    &ch,
+                                                    jac->jac_low_dev + (size_t)l0 * jac->n_par * low->n_chan,
+                                                    st);
                     if (code) return code;
                 }
             }
@@ -1623,11 +1687,20 @@ int sr_los_rt_lut_lowres_dev(sr_lut* const* luts, const sr_los_steps* steps, lon
                              const double* width_dev, int n_chan, double n_sigma,
                              const double* i0_dev, int solo_absorption, double* low_dev,
                              void* stream) {
-    if (!grid_dev || !centre_dev || !width_dev || !low_dev || n_chan < 1 || !(n_sigma > 0.0))
-        return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_lowres_dev: bad argument");
+    const sr_channels ch{n_chan, centre_dev, width_dev, n_sigma, SR_CHAN_SAME_UNITS};
+    return sr_los_rt_lut_channels_dev(luts, steps, pt0, n_pts, grid_dev, &ch, i0_dev,
+                                      solo_absorption, low_dev, stream);
+}
+
+int sr_los_rt_lut_channels_dev(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
+                               const double* grid_dev, const sr_channels* ch, const double* i0_dev,
+                               int solo_absorption, double* low_dev, void* stream) {
+    if (!grid_dev || !ch || !ch->centre_dev || !ch->width_dev || !low_dev || ch->n_chan < 1 ||
+        !(ch->n_sigma > 0.0))
+        return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_channels_dev: bad argument");
     if (getenv("SR_LOS_VER") && atoi(getenv("SR_LOS_VER")) == 1)
-        return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_lowres_dev needs the grouped LOS path");
-    LowSink low{grid_dev, centre_dev, width_dev, n_chan, n_sigma, low_dev};
+        return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_channels_dev needs the grouped LOS path");
+    LowSink low{grid_dev, ch->centre_dev, ch->width_dev, ch->n_chan, ch->n_sigma, low_dev, ch->units};
     return los_launch(luts, steps, pt0, n_pts, i0_dev, solo_absorption, nullptr, nullptr, nullptr,
                       (cudaStream_t)stream, 0, nullptr, &low);
 }
@@ -1665,14 +1738,25 @@ int sr_los_rt_lut_jac_lowres_dev(sr_lut* const* luts, const sr_los_steps* steps,
                                  const double* width_dev, int n_chan, double n_sigma,
                                  const double* i0_dev, int solo_absorption, double* low_dev,
                                  double* jac_low_dev, void* stream) {
-    if (!grid_dev || !centre_dev || !width_dev || !low_dev || !jac_low_dev || n_chan < 1 ||
-        !(n_sigma > 0.0))
-        return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_jac_lowres_dev: bad argument");
+    const sr_channels ch{n_chan, centre_dev, width_dev, n_sigma, SR_CHAN_SAME_UNITS};
+    return sr_los_rt_lut_jac_channels_dev(luts, steps, n_par, gas_in_jac, dfrac_host, pt0, n_pts,
+                                          grid_dev, &ch, i0_dev, solo_absorption, low_dev,
+                                          jac_low_dev, stream);
+}
+
+int sr_los_rt_lut_jac_channels_dev(sr_lut* const* luts, const sr_los_steps* steps, int n_par,
+                                   const int* gas_in_jac, const double* dfrac_host, long pt0,
+                                   long n_pts, const double* grid_dev, const sr_channels* ch,
+                                   const double* i0_dev, int solo_absorption, double* low_dev,
+                                   double* jac_low_dev, void* stream) {
+    if (!grid_dev || !ch || !ch->centre_dev || !ch->width_dev || !low_dev || !jac_low_dev ||
+        ch->n_chan < 1 || !(ch->n_sigma > 0.0))
+        return sr::fail(SR_ERR_ARG, "sr_los_rt_lut_jac_channels_dev: bad argument");
     JacSpec j;
     int rc = jac_spec(steps, n_par, gas_in_jac, dfrac_host, j);
     if (rc) return rc;
     j.jac_low_dev = jac_low_dev;
-    LowSink low{grid_dev, centre_dev, width_dev, n_chan, n_sigma, low_dev};
+    LowSink low{grid_dev, ch->centre_dev, ch->width_dev, ch->n_chan, ch->n_sigma, low_dev, ch->units};
     return los_launch(luts, steps, pt0, n_pts, i0_dev, solo_absorption, nullptr, nullptr, nullptr,
                       (cudaStream_t)stream, 0, nullptr, &low, &j);
 }

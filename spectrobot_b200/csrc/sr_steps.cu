@@ -28,13 +28,14 @@ constexpr double KB_HPA = 1.38065e-19;   // spect_classes.py:34 (P in hPa, n in 
 constexpr int MAX_GAS_ST = 8;
 
 struct AtmDev {
-    int n_band, n_z, n_gas, n_sets_max, n_par, jac_gas;
+    int n_band, n_z, n_gas, n_sets_max, n_par, jac_gas, n_sza;
+    const double* sza_nodes;   // [n_sza] degrees, ascending (n_sza > 1)
     const double* lat_edges;   // [n_band+1] (n_band > 1)
     const double* z;           // [n_z]
     const double* temp;        // [n_band][n_z]
     const double* lnpres;      // [n_band][n_z] log of P (hPa): P is log-linear in z
     const double* vmr;         // [n_gas][n_band][n_z]
-    const double* tvib;        // [n_gas][n_sets_max][n_band][n_z]
+    const double* tvib;        // [n_gas][n_sets_max][n_band][n_sza][n_z]
     const int* tvib_on;        // [n_gas][n_sets_max]: 1 own profile, 0 T_vib = step T, -1 no level
     const double* masks;       // [n_par][n_band][n_z]
     double radius, top;
@@ -61,10 +62,13 @@ struct PtArgs {
     AtmDev A;
     const double* origin;      // [n_los][3]
     const double* dir;         // [n_los][3]
-    int n_los, n_pts_max, n_steps_max;
-    double delta_x, max_dT, max_dlnP;
+    const double* sun;         // [n_los][3] unit vectors towards the Sun, or nullptr
+    const double* sza_fixed;   // [n_los] degrees (use_tangent_sza), or nullptr
+    int n_los, n_pts_max, n_steps_max, photon_order;
+    double delta_x, max_dT, max_dlnP, max_tau;   // max_tau <= 0: no optical-depth limit
+    double sigma[MAX_GAS_ST];  // peak cross-section estimate per gas (cm2 / molecule)
     // per-point scratch [n_los][n_pts_max]
-    double *T, *P, *nd, *x, *alt;
+    double *T, *P, *nd, *x, *alt, *sza;
     int *band, *jz;
     int* n_pts;                // [n_los]
     int* n_steps;              // [n_los] (true count, may exceed n_steps_max)
@@ -91,9 +95,22 @@ __global__ void k_steps_points(PtArgs a) {
     const size_t o = (size_t)l * a.n_pts_max;
     int n = 0;
     double s0 = 0.0;
+    double sunx = 0.0, suny = 0.0, sunz = 0.0;
+    if (a.sun) { sunx = a.sun[3 * l]; suny = a.sun[3 * l + 1]; sunz = a.sun[3 * l + 2]; }
     // greedy merge state: current step starts at point i0; running extrema over [i0, i]
     int i0 = 0, ns = 0;
     double tmin = 0, tmax = 0, pmin = 0, pmax = 0, t_prev = 0, lp_prev = 0;
+    // optical-depth limit (max_opt_depth): running gas columns of the current step [i0, i] and of
+    // its last segment, weighted by the peak cross-section estimates
+    const bool lim_tau = a.max_tau > 0.0;
+    double tau_run = 0.0, nd_prev = 0.0, x_prev = 0.0, v_prev[MAX_GAS_ST];
+    auto close_step = [&](int last) {
+        if (ns < a.n_steps_max) {
+            a.bounds[((size_t)l * a.n_steps_max + ns) * 2] = i0;
+            a.bounds[((size_t)l * a.n_steps_max + ns) * 2 + 1] = last;
+        }
+        ns++;
+    };
     auto add_point = [&](double s) {
         const double px = ox + s * dx, py = oy + s * dy, pz = oz + s * dz;
         const double r = sqrt(px * px + py * py + pz * pz);
@@ -109,13 +126,24 @@ __global__ void k_steps_points(PtArgs a) {
         const double T = interp_at(a.A.z, a.A.temp + (size_t)band * a.A.n_z, a.A.n_z, j, alt);
         const double lnP = interp_at(a.A.z, a.A.lnpres + (size_t)band * a.A.n_z, a.A.n_z, j, alt);
         const double P = exp(lnP);
+        const double nd = P / (KB_HPA * T);
         if (n == 0) s0 = s;
+        const double x = fabs(s0 - s) * 1.e5;     // path length from the first sample, cm
+        // solar zenith angle of the sample (LineOfSight.calc_SZA_along_los, or the tangent-point
+        // value everywhere with use_tangent_sza, smm:3138-3141)
+        double sza = 0.0;
+        if (a.sza_fixed) sza = a.sza_fixed[l];
+        else if (a.sun) {
+            const double c = (px * sunx + py * suny + pz * sunz) / r;
+            sza = acos(fmin(1.0, fmax(-1.0, c))) * (180.0 / M_PI);
+        }
         if (n < a.n_pts_max) {
             a.T[o + n] = T;
             a.P[o + n] = P;
-            a.nd[o + n] = P / (KB_HPA * T);
-            a.x[o + n] = (s0 - s) * 1.e5;     // path length from the far end, cm
+            a.nd[o + n] = nd;
+            a.x[o + n] = x;
             a.alt[o + n] = alt;
+            a.sza[o + n] = sza;
             a.band[o + n] = band;
             a.jz[o + n] = j;
         }
@@ -123,38 +151,51 @@ __global__ void k_steps_points(PtArgs a) {
         // exceeds a limit and the step has at least two segments
         const double lp = log(P);
         const int i = n;
+        double tau_seg = 0.0;
+        if (lim_tau) {
+            for (int m = 0; m < a.A.n_gas; m++) {
+                const double v = interp_at(a.A.z, a.A.vmr + ((size_t)m * a.A.n_band + band) * a.A.n_z,
+                                           a.A.n_z, j, alt);
+                if (i > 0) tau_seg += a.sigma[m] * srdev::curgod_seg2(nd_prev, nd, v_prev[m], v, x - x_prev);
+                v_prev[m] = v;
+            }
+            tau_run += tau_seg;
+        }
         if (i == 0) { tmin = tmax = T; pmin = pmax = lp; }
         else {
             tmin = fmin(tmin, T); tmax = fmax(tmax, T);
             pmin = fmin(pmin, lp); pmax = fmax(pmax, lp);
-            if ((tmax - tmin > a.max_dT || pmax - pmin > a.max_dlnP) && i - i0 >= 2) {
-                if (ns < a.n_steps_max) {
-                    a.bounds[((size_t)l * a.n_steps_max + ns) * 2] = i0;
-                    a.bounds[((size_t)l * a.n_steps_max + ns) * 2 + 1] = i - 1;
-                }
-                ns++;
+            if ((tmax - tmin > a.max_dT || pmax - pmin > a.max_dlnP || (lim_tau && tau_run > a.max_tau)) &&
+                i - i0 >= 2) {
+                close_step(i - 1);
                 i0 = i - 1;
                 tmin = fmin(t_prev, T); tmax = fmax(t_prev, T);
                 pmin = fmin(lp_prev, lp); pmax = fmax(lp_prev, lp);
+                tau_run = tau_seg;
             }
         }
         t_prev = T;
         lp_prev = lp;
+        nd_prev = nd;
+        x_prev = x;
         n++;
     };
-    add_point(s_far);
-    for (int k = kmax; k >= -kmax; k--) {
-        const double s = st + a.delta_x * (double)k;
-        if (s < s_far - 1e-6 && s > s_near + 1e-6) add_point(s);
-    }
-    add_point(s_near);
-    if (n >= 2) {
-        if (ns < a.n_steps_max) {
-            a.bounds[((size_t)l * a.n_steps_max + ns) * 2] = i0;
-            a.bounds[((size_t)l * a.n_steps_max + ns) * 2 + 1] = n - 1;
+    if (!a.photon_order) {   // far end -> observer: the order of the layer recursion
+        add_point(s_far);
+        for (int k = kmax; k >= -kmax; k--) {
+            const double s = st + a.delta_x * (double)k;
+            if (s < s_far - 1e-6 && s > s_near + 1e-6) add_point(s);
         }
-        ns++;
+        add_point(s_near);
+    } else {                 // LOS_order = 'photon' (invert_LOS_direction): observer side first
+        add_point(s_near);
+        for (int k = -kmax; k <= kmax; k++) {
+            const double s = st + a.delta_x * (double)k;
+            if (s < s_far - 1e-6 && s > s_near + 1e-6) add_point(s);
+        }
+        add_point(s_far);
     }
+    if (n >= 2) close_step(n - 1);
     a.n_pts[l] = n;
     a.n_steps[l] = ns;
 }
@@ -162,7 +203,7 @@ __global__ void k_steps_points(PtArgs a) {
 struct IntArgs {
     AtmDev A;
     int n_los, n_pts_max, n_steps_max;
-    const double *T, *P, *nd, *x, *alt;
+    const double *T, *P, *nd, *x, *alt, *sza;
     const int *band, *jz, *n_steps, *bounds;
     // outputs, sr_los_steps layout
     double* temp;     // [n_los][n_steps_max]
@@ -208,6 +249,21 @@ __global__ void k_steps_integrals(IntArgs a) {
     auto prof = [&](const double* __restrict__ table, int i) {   // profile value at sample point i
         return interp_at(A.z, table + (size_t)a.band[o + i] * A.n_z, A.n_z, a.jz[o + i], a.alt[o + i]);
     };
+    // vibrational temperature table [band][sza][z]: linear in altitude, then linear between the two
+    // SZA nodes that bracket the sample's solar zenith angle (clamped outside the node range)
+    auto prof_sza = [&](const double* __restrict__ table, int i) {
+        const double* __restrict__ tb = table + (size_t)a.band[o + i] * A.n_sza * A.n_z;
+        if (A.n_sza <= 1) return interp_at(A.z, tb, A.n_z, a.jz[o + i], a.alt[o + i]);
+        const double sz = a.sza[o + i];
+        const int js = interp_index(A.sza_nodes, A.n_sza, sz);
+        const double f0 = interp_at(A.z, tb + (size_t)js * A.n_z, A.n_z, a.jz[o + i], a.alt[o + i]);
+        const double f1 = interp_at(A.z, tb + (size_t)(js + 1) * A.n_z, A.n_z, a.jz[o + i], a.alt[o + i]);
+        if (sz <= A.sza_nodes[0]) return interp_at(A.z, tb, A.n_z, a.jz[o + i], a.alt[o + i]);
+        if (sz >= A.sza_nodes[A.n_sza - 1])
+            return interp_at(A.z, tb + (size_t)(A.n_sza - 1) * A.n_z, A.n_z, a.jz[o + i], a.alt[o + i]);
+        const double w = (sz - A.sza_nodes[js]) / (A.sza_nodes[js + 1] - A.sza_nodes[js]);
+        return (1.0 - w) * f0 + w * f1;
+    };
     for (int m = 0; m < A.n_gas; m++) {
         const double* vt = A.vmr + (size_t)m * A.n_band * A.n_z;
         double col = 0.0;
@@ -223,10 +279,10 @@ __global__ void k_steps_integrals(IntArgs a) {
             double tv = 100.0;
             if (on == 0) tv = t_cg;
             else if (on > 0) {
-                const double* tt = A.tvib + ((size_t)m * A.n_sets_max + s) * A.n_band * A.n_z;
-                double acc = 0.0, w0 = prof(vt, ia), f0 = prof(tt, ia);
+                const double* tt = A.tvib + ((size_t)m * A.n_sets_max + s) * A.n_band * A.n_sza * A.n_z;
+                double acc = 0.0, w0 = prof(vt, ia), f0 = prof_sza(tt, ia);
                 for (int i = ia; i < ie; i++) {
-                    const double w1 = prof(vt, i + 1), f1 = prof(tt, i + 1);
+                    const double w1 = prof(vt, i + 1), f1 = prof_sza(tt, i + 1);
                     acc += srdev::curgod_seg3(nd[i], nd[i + 1], w0, w1, f0, f1, x[i + 1] - x[i]);
                     w0 = w1;
                     f0 = f1;
@@ -265,6 +321,35 @@ int sr_los_steps_build(const sr_atmosphere* atm, int n_los, const double* origin
                        double max_Plog_variation, int n_par, const double* masks, int jac_gas,
                        int n_steps_max, int* n_steps, double* temp, double* pres, double* column,
                        double* tvib, double* dfrac, int* n_steps_needed) {
+    sr_los_rays rays{n_los, origin, direction, nullptr, nullptr};
+    sr_steps_opt opt{delta_x_km, max_T_variation, max_Plog_variation, 0.0, nullptr, 0};
+    return sr_los_steps_build_rays(atm, &rays, &opt, n_par, masks, jac_gas, n_steps_max, n_steps, temp,
+                                   pres, column, tvib, dfrac, n_steps_needed);
+}
+
+int sr_los_steps_build_rays(const sr_atmosphere* atm, const sr_los_rays* rays, const sr_steps_opt* opt,
+                            int n_par, const double* masks, int jac_gas, int n_steps_max,
+                            int* n_steps, double* temp, double* pres, double* column, double* tvib,
+                            double* dfrac, int* n_steps_needed) {
+    if (!rays || !opt) return sr::fail(SR_ERR_ARG, "sr_los_steps_build_rays: bad argument");
+    const int n_los = rays->n_los;
+    const double* origin = rays->origin;
+    const double* direction = rays->direction;
+    const double delta_x_km = opt->delta_x_km, max_T_variation = opt->max_T_variation,
+                 max_Plog_variation = opt->max_Plog_variation;
+    if (opt->max_opt_depth > 0.0 && !opt->sigma_peak)
+        return sr::fail(SR_ERR_ARG, "sr_los_steps_build_rays: max_opt_depth needs the per-gas peak "
+                                    "cross-sections (sigma_peak)");
+    const int nsz = atm ? std::max(atm->n_sza, 1) : 1;
+    if (atm && atm->n_sza > 1) {
+        if (!atm->sza_nodes) return sr::fail(SR_ERR_ARG, "sr_los_steps_build_rays: n_sza > 1 without sza_nodes");
+        for (int i = 1; i < atm->n_sza; i++)
+            if (!(atm->sza_nodes[i] > atm->sza_nodes[i - 1]))
+                return sr::fail(SR_ERR_ARG, "sr_los_steps_build_rays: sza_nodes must ascend");
+        if (!rays->sun && !rays->sza_fixed)
+            return sr::fail(SR_ERR_ARG, "sr_los_steps_build_rays: SZA-dependent vibrational temperatures "
+                                        "need the Sun direction or a fixed SZA per LOS");
+    }
     if (!atm || n_los < 1 || !origin || !direction || !(delta_x_km > 0.0) || n_steps_max < 1 ||
         !n_steps || !temp || !pres || !column || atm->n_band < 1 || atm->n_z < 2 ||
         atm->n_gas < 1 || atm->n_gas > MAX_GAS_ST || !atm->z || !atm->temp || !atm->pres ||
@@ -278,31 +363,37 @@ int sr_los_steps_build(const sr_atmosphere* atm, int n_los, const double* origin
     cudaStream_t st = 0;
     std::vector<double> lnp((size_t)nb * nz);
     for (size_t i = 0; i < lnp.size(); i++) lnp[i] = std::log(atm->pres[i]);
-    sr::PoolBuf<double> d_edges, d_z, d_temp, d_lnp, d_vmr, d_tvib, d_masks, d_org, d_dir;
+    sr::PoolBuf<double> d_edges, d_z, d_temp, d_lnp, d_vmr, d_tvib, d_masks, d_org, d_dir, d_sun,
+        d_fsza, d_nodes, ssza;
     sr::PoolBuf<int> d_on;
     if (nb > 1) SR_CUDA(d_edges.upload(atm->lat_edges, nb + 1, st));
     SR_CUDA(d_z.upload(atm->z, nz, st));
     SR_CUDA(d_temp.upload(atm->temp, (size_t)nb * nz, st));
     SR_CUDA(d_lnp.upload(lnp.data(), lnp.size(), st));
     SR_CUDA(d_vmr.upload(atm->vmr, (size_t)ng * nb * nz, st));
-    if (atm->tvib) SR_CUDA(d_tvib.upload(atm->tvib, (size_t)ng * nsx * nb * nz, st));
+    if (atm->tvib) SR_CUDA(d_tvib.upload(atm->tvib, (size_t)ng * nsx * nb * nsz * nz, st));
+    if (nsz > 1) SR_CUDA(d_nodes.upload(atm->sza_nodes, nsz, st));
     if (nsx > 0) SR_CUDA(d_on.upload(atm->tvib_on, (size_t)ng * nsx, st));
     if (n_par > 0) SR_CUDA(d_masks.upload(masks, (size_t)n_par * nb * nz, st));
     AtmDev A;
     A.n_band = nb; A.n_z = nz; A.n_gas = ng; A.n_sets_max = nsx; A.n_par = n_par; A.jac_gas = jac_gas;
+    A.n_sza = nsz; A.sza_nodes = d_nodes.p;
     A.lat_edges = d_edges.p; A.z = d_z.p; A.temp = d_temp.p; A.lnpres = d_lnp.p; A.vmr = d_vmr.p;
     A.tvib = d_tvib.p; A.tvib_on = d_on.p; A.masks = d_masks.p;
     A.radius = atm->radius_km; A.top = atm->top_km;
     const double r_top = atm->radius_km + atm->top_km;
     const int n_pts_max = 2 * (int)std::floor(r_top / delta_x_km) + 3;
-    // LOS blocks bound the per-point scratch (48 B per point) to ~1 GiB
-    int blk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_los, ((size_t)1 << 30) / ((size_t)n_pts_max * 48)));
+    // LOS blocks bound the per-point scratch (56 B per point) to ~1 GiB
+    int blk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_los, ((size_t)1 << 30) / ((size_t)n_pts_max * 56)));
     if (const char* e = getenv("SR_STEPS_BLOCK")) blk = std::max(1, std::min(n_los, atoi(e)));   // test aid
     sr::PoolBuf<double> sT, sP, snd, sx, salt, o_temp, o_pres, o_col, o_tvib, o_dfrac;
     sr::PoolBuf<int> sband, sjz, d_npts, d_nsteps, d_bounds;
     const size_t np = (size_t)blk * n_pts_max;
     SR_CUDA(sT.alloc(np, st)); SR_CUDA(sP.alloc(np, st)); SR_CUDA(snd.alloc(np, st));
     SR_CUDA(sx.alloc(np, st)); SR_CUDA(salt.alloc(np, st)); SR_CUDA(sband.alloc(np, st));
+    SR_CUDA(ssza.alloc(np, st));
+    if (rays->sun) SR_CUDA(d_sun.alloc((size_t)3 * blk, st));
+    if (rays->sza_fixed) SR_CUDA(d_fsza.alloc((size_t)blk, st));
     SR_CUDA(sjz.alloc(np, st));
     SR_CUDA(d_npts.alloc(blk, st)); SR_CUDA(d_nsteps.alloc(blk, st));
     SR_CUDA(d_bounds.alloc((size_t)blk * n_steps_max * 2, st));
@@ -320,8 +411,21 @@ int sr_los_steps_build(const sr_atmosphere* atm, int n_los, const double* origin
                                 cudaMemcpyHostToDevice, st));
         SR_CUDA(cudaMemcpyAsync(d_dir.p, direction + (size_t)3 * l0, sizeof(double) * 3 * nl,
                                 cudaMemcpyHostToDevice, st));
+        if (rays->sun)
+            SR_CUDA(cudaMemcpyAsync(d_sun.p, rays->sun + (size_t)3 * l0, sizeof(double) * 3 * nl,
+                                    cudaMemcpyHostToDevice, st));
+        if (rays->sza_fixed)
+            SR_CUDA(cudaMemcpyAsync(d_fsza.p, rays->sza_fixed + l0, sizeof(double) * nl,
+                                    cudaMemcpyHostToDevice, st));
         PtArgs pa;
         pa.A = A; pa.origin = d_org.p; pa.dir = d_dir.p;
+        pa.sun = rays->sun ? d_sun.p : nullptr;
+        pa.sza_fixed = rays->sza_fixed ? d_fsza.p : nullptr;
+        pa.photon_order = opt->photon_order ? 1 : 0;
+        pa.max_tau = opt->max_opt_depth;
+        for (int m = 0; m < MAX_GAS_ST; m++)
+            pa.sigma[m] = (opt->sigma_peak && m < ng) ? opt->sigma_peak[m] : 0.0;
+        pa.sza = ssza.p;
         pa.n_los = nl; pa.n_pts_max = n_pts_max; pa.n_steps_max = n_steps_max;
         pa.delta_x = delta_x_km; pa.max_dT = max_T_variation; pa.max_dlnP = max_Plog_variation;
         pa.T = sT.p; pa.P = sP.p; pa.nd = snd.p; pa.x = sx.p; pa.alt = salt.p;
@@ -330,7 +434,7 @@ int sr_los_steps_build(const sr_atmosphere* atm, int n_los, const double* origin
         SR_LAUNCH(k_steps_points, (nl + 63) / 64, 64, 0, st, pa);
         IntArgs ia;
         ia.A = A; ia.n_los = nl; ia.n_pts_max = n_pts_max; ia.n_steps_max = n_steps_max;
-        ia.T = sT.p; ia.P = sP.p; ia.nd = snd.p; ia.x = sx.p; ia.alt = salt.p;
+        ia.T = sT.p; ia.P = sP.p; ia.nd = snd.p; ia.x = sx.p; ia.alt = salt.p; ia.sza = ssza.p;
         ia.band = sband.p; ia.jz = sjz.p; ia.n_steps = d_nsteps.p; ia.bounds = d_bounds.p;
         ia.temp = o_temp.p; ia.pres = o_pres.p; ia.column = o_col.p; ia.tvib = o_tvib.p;
         ia.dfrac = o_dfrac.p;

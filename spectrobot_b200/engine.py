@@ -245,6 +245,12 @@ class Lut(object):
             self.mol, self.iso, self.iso_ratio, int(self.lte_unidentified),
             C.byref(self.consts), C.byref(self._h)))
 
+    def set_emission_mask(self, mask):
+        """Bit s of `mask`: spontaneous emission of set s contributes to the source function of
+        the following LOS calls (None: all sets, the default).  Absorption is not affected."""
+        m = 0xFFFFFFFFFFFFFFFF if mask is None else int(mask) & 0xFFFFFFFFFFFFFFFF
+        check(lib().sr_lut_set_emission_mask(self._h, C.c_ulonglong(m)))
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             lib().sr_lut_destroy(self._h)
@@ -320,8 +326,23 @@ def los_rt_lut(luts, steps, pt0=0, n_pts=None, i0=None, solo_absorption=False, o
     return out
 
 
+def _channels(centres, widths, n_sigma, units):
+    """(sr_channels, tensors to keep alive).  units: 'same' (channels in the units of the grid) or
+    'nm' (grid in cm-1, channels in nm: the reference's convert_grid_to, spect_classes.py:771-778)."""
+    torch = _torch()
+    c = centres if torch.is_tensor(centres) else torch.as_tensor(as_f64(centres), device="cuda")
+    w = widths if torch.is_tensor(widths) else torch.as_tensor(as_f64(widths), device="cuda")
+    assert c.numel() == w.numel() and c.dtype == torch.float64 and w.dtype == torch.float64
+    ch = _lib.sr_channels()
+    ch.n_chan, ch.n_sigma = c.numel(), float(n_sigma)
+    ch.centre_dev, ch.width_dev = c.data_ptr(), w.data_ptr()
+    ch.units = {'same': _lib.SR_CHAN_SAME_UNITS, 'nm': _lib.SR_CHAN_NM_FROM_CM1}[units]
+    return ch, (c, w)
+
+
 def los_rt_lut_lowres(luts, steps, grid, centres, widths, pt0=0, n_pts=None, n_sigma=5.0, i0=None,
-                      solo_absorption=False, out=None, stream=None, check_status=True):
+                      solo_absorption=False, out=None, stream=None, check_status=True,
+                      units='same'):
     """K3a+K3 + instrument convolution: low-res spectra [n_los, n_chan] (CUDA float64) of a batch
     of any size; the hi-res radiances only ever exist per LOS block on the device.  grid: CUDA
     float64 tensor with the WHOLE spectral grid of the LUTs; centres/widths: channel definition in
@@ -330,20 +351,17 @@ def los_rt_lut_lowres(luts, steps, grid, centres, widths, pt0=0, n_pts=None, n_s
     if n_pts is None:
         n_pts = luts[0].n_grid - pt0
     assert grid.is_cuda and grid.dtype == torch.float64 and grid.numel() == luts[0].n_grid
-    c = centres if torch.is_tensor(centres) else torch.as_tensor(as_f64(centres), device="cuda")
-    w = widths if torch.is_tensor(widths) else torch.as_tensor(as_f64(widths), device="cuda")
-    assert c.numel() == w.numel()
+    ch, keep = _channels(centres, widths, n_sigma, units)
     if out is None:
-        out = torch.empty((steps.n_los, c.numel()), dtype=torch.float64, device="cuda")
+        out = torch.empty((steps.n_los, ch.n_chan), dtype=torch.float64, device="cuda")
     arr = _lut_array(luts)
     st = steps.struct()
     sp = _stream_ptr(stream)
     gwin = grid[pt0:pt0 + n_pts]
-    check(lib().sr_los_rt_lut_lowres_dev(arr, C.byref(st), int(pt0), int(n_pts),
-                                         C.c_void_p(gwin.data_ptr()), C.c_void_p(c.data_ptr()),
-                                         C.c_void_p(w.data_ptr()), c.numel(), float(n_sigma),
-                                         None if i0 is None else C.c_void_p(i0.data_ptr()),
-                                         int(bool(solo_absorption)), C.c_void_p(out.data_ptr()), sp))
+    check(lib().sr_los_rt_lut_channels_dev(arr, C.byref(st), int(pt0), int(n_pts),
+                                           C.c_void_p(gwin.data_ptr()), C.byref(ch),
+                                           None if i0 is None else C.c_void_p(i0.data_ptr()),
+                                           int(bool(solo_absorption)), C.c_void_p(out.data_ptr()), sp))
     if check_status:
         check(lib().sr_los_check(arr, sp))
     return out
@@ -434,7 +452,7 @@ def los_rt_lut_jac(luts, steps, dfrac, gas_in_jac=None, pt0=0, n_pts=None, i0=No
 
 def los_rt_lut_jac_lowres(luts, steps, dfrac, grid, centres, widths, gas_in_jac=None, pt0=0,
                           n_pts=None, n_sigma=5.0, i0=None, solo_absorption=False, stream=None,
-                          check_status=True):
+                          check_status=True, units='same'):
     """Same, reduced to the instrument channels on the device: (low [n_los, n_chan],
     jac_low [n_los, n_par, n_chan]); see los_rt_lut_lowres for grid / centres / widths."""
     torch = _torch()
@@ -443,19 +461,16 @@ def los_rt_lut_jac_lowres(luts, steps, dfrac, grid, centres, widths, gas_in_jac=
     dfrac, gij = _jac_args(steps, dfrac, gas_in_jac)
     n_par = dfrac.shape[2]
     assert grid.is_cuda and grid.dtype == torch.float64 and grid.numel() == luts[0].n_grid
-    c = centres if torch.is_tensor(centres) else torch.as_tensor(as_f64(centres), device="cuda")
-    w = widths if torch.is_tensor(widths) else torch.as_tensor(as_f64(widths), device="cuda")
-    assert c.numel() == w.numel()
-    low = torch.empty((steps.n_los, c.numel()), dtype=torch.float64, device="cuda")
-    jlow = torch.empty((steps.n_los, n_par, c.numel()), dtype=torch.float64, device="cuda")
+    ch, keep = _channels(centres, widths, n_sigma, units)
+    low = torch.empty((steps.n_los, ch.n_chan), dtype=torch.float64, device="cuda")
+    jlow = torch.empty((steps.n_los, n_par, ch.n_chan), dtype=torch.float64, device="cuda")
     arr = _lut_array(luts)
     st = steps.struct()
     sp = _stream_ptr(stream)
     gwin = grid[pt0:pt0 + n_pts]
-    check(lib().sr_los_rt_lut_jac_lowres_dev(
+    check(lib().sr_los_rt_lut_jac_channels_dev(
         arr, C.byref(st), n_par, None if gij is None else iptr(gij), dptr(dfrac), int(pt0),
-        int(n_pts), C.c_void_p(gwin.data_ptr()), C.c_void_p(c.data_ptr()),
-        C.c_void_p(w.data_ptr()), c.numel(), float(n_sigma),
+        int(n_pts), C.c_void_p(gwin.data_ptr()), C.byref(ch),
         None if i0 is None else C.c_void_p(i0.data_ptr()), int(bool(solo_absorption)),
         C.c_void_p(low.data_ptr()), C.c_void_p(jlow.data_ptr()), sp))
     if check_status:
@@ -488,11 +503,13 @@ class Atmosphere(object):
     """Atmosphere tables for the device step builder (sr_atmosphere in spectrobot.h).
 
     z [n_z] km; temp, pres [n_band, n_z] (or [n_z]); vmr [n_gas, n_band, n_z], one entry per LUT of
-    the later LOS call; tvib [n_gas, n_sets_max, n_band, n_z] or None; tvib_on [n_gas, n_sets_max]
-    (1 own profile, 0 T_vib = step temperature, -1 no such level); lat_edges [n_band+1] degrees."""
+    the later LOS call; tvib [n_gas, n_sets_max, n_band, n_z] or, with a solar-zenith-angle axis
+    sza_nodes [n_sza] (degrees, ascending), [n_gas, n_sets_max, n_band, n_sza, n_z], or None;
+    tvib_on [n_gas, n_sets_max] (1 own profile, 0 T_vib = step temperature, -1 no such level);
+    lat_edges [n_band+1] degrees."""
 
     def __init__(self, z, temp, pres, vmr, tvib=None, tvib_on=None, lat_edges=None,
-                 radius_km=2575.0, top_km=1500.0):
+                 radius_km=2575.0, top_km=1500.0, sza_nodes=None):
         self.z = as_f64(z)
         nz = len(self.z)
         self.temp = as_f64(np.asarray(temp, dtype=float).reshape(-1, nz))
@@ -507,8 +524,11 @@ class Atmosphere(object):
         if tvib_on is not None:
             self.tvib_on = as_i32(np.asarray(tvib_on).reshape(self.n_gas, -1))
             self.n_sets_max = self.tvib_on.shape[1]
+        self.sza_nodes = None if sza_nodes is None or len(sza_nodes) <= 1 else as_f64(sza_nodes)
+        self.n_sza = 1 if self.sza_nodes is None else len(self.sza_nodes)
         if tvib is not None:
-            self.tvib = as_f64(np.asarray(tvib, dtype=float).reshape(self.n_gas, -1, self.n_band, nz))
+            self.tvib = as_f64(np.asarray(tvib, dtype=float).reshape(self.n_gas, -1, self.n_band,
+                                                                     self.n_sza, nz))
             if self.tvib_on is None:
                 self.n_sets_max = self.tvib.shape[1]
                 self.tvib_on = as_i32(np.ones((self.n_gas, self.n_sets_max)))
@@ -526,18 +546,42 @@ class Atmosphere(object):
         st.tvib = None if self.tvib is None else dptr(self.tvib)
         st.tvib_on = None if self.tvib_on is None else iptr(self.tvib_on)
         st.radius_km, st.top_km = self.radius_km, self.top_km
+        st.n_sza = self.n_sza
+        st.sza_nodes = None if self.sza_nodes is None else dptr(self.sza_nodes)
         return st
 
 
 def los_steps_build(atm, origins, directions, delta_x=5.0, max_T_variation=5.0,
-                    max_Plog_variation=1.0, masks=None, jac_gas=-1, n_steps_max=64):
-    """LOS geometry + radtran steps of a whole batch on the device (sr_los_steps_build): rays from
-    origins [n_los, 3] (km, planetocentric Cartesian) along unit directions [n_los, 3].  Returns
+                    max_Plog_variation=1.0, masks=None, jac_gas=-1, n_steps_max=64, sun=None,
+                    sza_fixed=None, max_opt_depth=None, sigma_peak=None, photon_order=False):
+    """LOS geometry + radtran steps of a whole batch on the device (sr_los_steps_build_rays): rays
+    from origins [n_los, 3] (km, planetocentric Cartesian) along unit directions [n_los, 3].
+    sun [n_los, 3] (or [3]): direction of the Sun per LOS, for SZA-dependent vibrational
+    temperatures; sza_fixed [n_los]: one SZA per LOS instead (use_tangent_sza); max_opt_depth with
+    sigma_peak [n_gas]: optical-depth limit of a step; photon_order: LOS_order='photon'.  Returns
     (LosSteps, dfrac) - dfrac [n_los, n_steps_max, n_par] for the parameter masks [n_par, n_z] or
     [n_par, n_band, n_z] of gas entry jac_gas, or None.  The table width grows until every LOS fits."""
     org, dr = as_f64(origins).reshape(-1, 3), as_f64(directions).reshape(-1, 3)
     n_los = org.shape[0]
     assert dr.shape == org.shape
+    rays = _lib.sr_los_rays()
+    rays.n_los, rays.origin, rays.direction = n_los, dptr(org), dptr(dr)
+    if sun is not None:
+        sun = np.asarray(sun, dtype=float)
+        sun = as_f64(np.broadcast_to(sun / np.linalg.norm(sun, axis=-1, keepdims=True), (n_los, 3)))
+        rays.sun = dptr(sun)
+    if sza_fixed is not None:
+        sza_fixed = as_f64(np.broadcast_to(np.asarray(sza_fixed, dtype=float), (n_los,)))
+        rays.sza_fixed = dptr(sza_fixed)
+    opt = _lib.sr_steps_opt()
+    opt.delta_x_km, opt.max_T_variation = float(delta_x), float(max_T_variation)
+    opt.max_Plog_variation = float(max_Plog_variation)
+    opt.max_opt_depth = 0.0 if max_opt_depth is None else float(max_opt_depth)
+    opt.photon_order = int(bool(photon_order))
+    if sigma_peak is not None:
+        sigma_peak = as_f64(sigma_peak)
+        assert len(sigma_peak) == atm.n_gas
+        opt.sigma_peak = dptr(sigma_peak)
     mk = None
     if masks is not None:   # [n_par, n_z] (same in every latitude box) or [n_par, n_band, n_z]
         mk = np.asarray(masks, dtype=float)
@@ -555,12 +599,11 @@ def los_steps_build(atm, origins, directions, delta_x=5.0, max_T_variation=5.0,
         tvib = np.empty((atm.n_gas, atm.n_sets_max, n_los, n_steps_max)) if atm.n_sets_max else None
         dfrac = np.empty((n_los, n_steps_max, n_par)) if n_par else None
         need = C.c_int(0)
-        rc = lib().sr_los_steps_build(C.byref(st), n_los, dptr(org), dptr(dr), float(delta_x),
-                                      float(max_T_variation), float(max_Plog_variation), n_par,
-                                      None if mk is None else dptr(mk), int(jac_gas),
-                                      int(n_steps_max), iptr(n_steps), dptr(temp), dptr(pres),
-                                      dptr(col), None if tvib is None else dptr(tvib),
-                                      None if dfrac is None else dptr(dfrac), C.byref(need))
+        rc = lib().sr_los_steps_build_rays(C.byref(st), C.byref(rays), C.byref(opt), n_par,
+                                           None if mk is None else dptr(mk), int(jac_gas),
+                                           int(n_steps_max), iptr(n_steps), dptr(temp), dptr(pres),
+                                           dptr(col), None if tvib is None else dptr(tvib),
+                                           None if dfrac is None else dptr(dfrac), C.byref(need))
         if rc == _lib.SR_ERR_LIMIT and need.value > n_steps_max:
             n_steps_max = need.value
             continue
@@ -609,7 +652,7 @@ def lut_weights(PTcouples, Pres, Temp):
     return cell, w
 
 
-def convolve_lowres(grid, spec, centres, widths, n_sigma=5.0, out=None, stream=None):
+def convolve_lowres(grid, spec, centres, widths, n_sigma=5.0, out=None, stream=None, units='same'):
     """Instrument convolution on the device (spect_classes.py:883-918): grid [n_pts] and spec
     [n_spec, n_pts] CUDA float64 tensors, channel centres/widths (array-likes or CUDA tensors) ->
     CUDA float64 [n_spec, n_chan]."""
@@ -618,27 +661,24 @@ def convolve_lowres(grid, spec, centres, widths, n_sigma=5.0, out=None, stream=N
         spec = spec[None]
     assert spec.is_cuda and spec.dtype == torch.float64 and spec.is_contiguous()
     assert grid.is_cuda and grid.dtype == torch.float64 and grid.numel() == spec.shape[1]
-    c = centres if torch.is_tensor(centres) else torch.as_tensor(as_f64(centres), device="cuda")
-    w = widths if torch.is_tensor(widths) else torch.as_tensor(as_f64(widths), device="cuda")
-    assert c.numel() == w.numel()
+    ch, keep = _channels(centres, widths, n_sigma, units)
     if out is None:
-        out = torch.empty((spec.shape[0], c.numel()), dtype=torch.float64, device="cuda")
-    check(lib().sr_convolve_lowres_dev(C.c_void_p(grid.data_ptr()), spec.shape[1],
-                                       C.c_void_p(spec.data_ptr()), spec.shape[0],
-                                       C.c_void_p(c.data_ptr()), C.c_void_p(w.data_ptr()),
-                                       c.numel(), float(n_sigma), C.c_void_p(out.data_ptr()),
-                                       _stream_ptr(stream)))
+        out = torch.empty((spec.shape[0], ch.n_chan), dtype=torch.float64, device="cuda")
+    check(lib().sr_convolve_channels_dev(C.c_void_p(grid.data_ptr()), spec.shape[1],
+                                         C.c_void_p(spec.data_ptr()), spec.shape[0], C.byref(ch),
+                                         C.c_void_p(out.data_ptr()), _stream_ptr(stream)))
     return out
 
 
-def convolve_lowres_host(grid, spec, centres, widths, n_sigma=5.0):
+def convolve_lowres_host(grid, spec, centres, widths, n_sigma=5.0, units='same'):
     """Host-buffer form of convolve_lowres: numpy in, numpy [n_spec, n_chan] out."""
     grid = as_f64(grid)
     spec = np.atleast_2d(as_f64(spec))
     c, w = as_f64(centres), as_f64(widths)
     out = np.empty((spec.shape[0], len(c)))
-    check(lib().sr_convolve_lowres_host(dptr(grid), len(grid), dptr(spec), spec.shape[0], dptr(c),
-                                        dptr(w), len(c), float(n_sigma), dptr(out)))
+    u = {'same': _lib.SR_CHAN_SAME_UNITS, 'nm': _lib.SR_CHAN_NM_FROM_CM1}[units]
+    check(lib().sr_convolve_channels_host(dptr(grid), len(grid), dptr(spec), spec.shape[0], dptr(c),
+                                          dptr(w), len(c), float(n_sigma), u, dptr(out)))
     return out
 
 

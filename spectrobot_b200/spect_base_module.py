@@ -157,8 +157,11 @@ class AtmGrid(object):
 
 
 class AtmProfile(object):
-    """Profiles on an AtmGrid ('alt' or ('lat', 'alt')); lat coordinates are band EDGES for the
-    2-D case (box interpolation in latitude, linear / log-linear in altitude)."""
+    """Profiles on an AtmGrid: 'alt', ('lat', 'alt'), ('sza', 'alt') or ('lat', 'sza', 'alt') - the
+    last is the reference's 3-D vibrational-temperature profile, `prof.calc([lat, sza, alt])`
+    (radtran_3D_ch4.py:249-250).  lat coordinates are band EDGES (box interpolation in latitude);
+    sza coordinates are nodes in degrees (linear in between, clamped outside); altitude is linear,
+    log-linear ('exp') or box."""
 
     def __init__(self, grid, values, profname, interp):
         self.grid = grid
@@ -177,25 +180,47 @@ class AtmProfile(object):
         return self.values[name]
 
     def _band(self, lat):
-        if self.grid.n_dim == 1:
+        if 'lat' not in self.grid.names:
             return None
         edges = self.grid.coords['lat']
         return int(np.clip(np.searchsorted(edges, lat, side='right') - 1, 0, len(edges) - 2))
 
-    def calc(self, point, profname=None):
-        lat, lon, alt = point.Spherical() if hasattr(point, 'Spherical') else point
+    def _coords(self, point, sza):
+        """(lat, sza, alt) of a Coords point (+ sza keyword) or of a plain coordinate list given in
+        the order of the grid's own dimensions ([lat, alt], [lat, sza, alt], ...)."""
+        if hasattr(point, 'Spherical'):
+            lat, lon, alt = point.Spherical()
+            return lat, sza, alt
+        point = list(point)
+        if len(point) == self.grid.n_dim and self.grid.names != ['lat', 'lon', 'alt']:
+            c = dict(zip(self.grid.names, point))
+            return c.get('lat', 0.0), c.get('sza', sza), c['alt']
+        lat, lon, alt = point
+        return lat, sza, alt
+
+    def _alt_value(self, v, n, alt):
+        z = self.grid.coords['alt']
+        if self.interp[n] == 'exp':
+            return float(np.exp(np.interp(alt, z, np.log(v))))
+        if self.interp[n] == 'box':
+            return float(v[int(np.clip(np.searchsorted(z, alt, side='right') - 1, 0, len(z) - 1))])
+        return float(np.interp(alt, z, v))
+
+    def calc(self, point, profname=None, sza=None):
+        lat, sza, alt = self._coords(point, sza)
         names = [profname] if profname is not None else self.names
         res = dict()
-        z = self.grid.coords['alt']
-        b = self._band(lat)
+        b = self._band(lat) if 'lat' in self.grid.names else None
         for n in names:
             v = self.values[n] if b is None else self.values[n][b]
-            if self.interp[n] == 'exp':
-                res[n] = float(np.exp(np.interp(alt, z, np.log(v))))
-            elif self.interp[n] == 'box':
-                res[n] = float(v[int(np.clip(np.searchsorted(z, alt, side='right') - 1, 0, len(z) - 1))])
+            if 'sza' in self.grid.names:
+                nodes = self.grid.coords['sza']
+                if sza is None:
+                    raise ValueError('profile %s depends on the solar zenith angle: pass sza' % n)
+                res[n] = float(np.interp(sza, nodes, [self._alt_value(v[j], n, alt)
+                                                      for j in range(len(nodes))]))
             else:
-                res[n] = float(np.interp(alt, z, v))
+                res[n] = self._alt_value(v, n, alt)
         return res[profname] if profname is not None else res
 
     def __iadd__(self, other):
@@ -353,6 +378,14 @@ class Molec(object):
         self.iso_N += 1
         return getattr(self, nam)
 
+    def add_all_iso_from_HITRAN(self, lines, add_levels=False, n_max=None):
+        """One IsoMolec (LTE, no levels) per isotopologue number of this molecule that occurs in
+        `lines` and is not there yet (callers radtran_test_CO.py:118, run_0607_lut.py:107)."""
+        isos = sorted(set(int(lin.Iso) for lin in lines if lin.Mol == self.mol))
+        for num in isos[:n_max]:
+            if 'iso_{:1d}'.format(num) not in self.all_iso:
+                self.add_iso(num, LTE=True)
+
     def add_clim(self, profile):
         self.abundance = profile
 
@@ -443,10 +476,17 @@ class LineOfSight(object):
         return self.get_tangent_altitude()
 
     def calc_atm_intersections(self, planet, delta_x=5.0, start_from_TOA=True,
-                               stop_at_second_point=False, LOS_order='radtran'):
-        """Points along the ray inside the atmosphere, every delta_x km.  LOS_order 'radtran':
-        from the far end towards the observer (order of the layer recursion); 'photon': same
-        ordering (photons travel towards the observer)."""
+                               stop_at_second_point=False, LOS_order='radtran', verbose=False):
+        """Points along the ray inside the atmosphere, every delta_x km.  The order
+        of the points is the order of the layer recursion.  LOS_order 'radtran' (default): from the
+        far end of the ray towards the starting point (the observer).  LOS_order 'photon': from the
+        starting point's side towards the far end - photons that enter where the ray starts (the
+        solar-ray test, radtran_3D_ch4.py:311; `invert_LOS_direction`, smm:3135-3137).
+        start_from_TOA=False starts at the starting point when it lies inside the atmosphere,
+        stop_at_second_point=True ends at the second point."""
+        if LOS_order not in ('radtran', 'photon'):
+            raise ValueError("LOS_order must be 'radtran' or 'photon'")
+        self.LOS_order = LOS_order
         o = self.starting_point.Cartesian()
         st = self._s_tangent()
         rt = float(np.linalg.norm(o + st * self.direction))
@@ -459,12 +499,22 @@ class LineOfSight(object):
         s_near, s_far = st - half, st + half
         if rt < planet.radius:                       # ray hits the surface: stop there
             s_far = st - mt.sqrt(planet.radius ** 2 - rt ** 2)
+        if not start_from_TOA:
+            s_near = max(s_near, 0.0)
+        if stop_at_second_point:
+            s_far = min(s_far, float(np.linalg.norm(self.second_point.Cartesian() - o)))
+        if s_far <= s_near:
+            self.intersections = []
+            self._s = np.zeros(0)
+            return self.intersections
         # samples anchored on the tangent point, so that no two ADJACENT samples sit at the same
         # altitude (curgod_fort_* divide by log(nd2/nd1), curgods.f:17)
         kmax = int(mt.floor(half / delta_x - 1e-9))
         inner = st + delta_x * np.arange(kmax, -kmax - 1, -1)
         inner = inner[(inner < s_far - 1e-6) & (inner > s_near + 1e-6)]
         s = np.concatenate([[s_far], inner, [s_near]])
+        if LOS_order == 'photon':
+            s = s[::-1]
         self._s = s
         self.intersections = [Coords(o + si * self.direction, s_ref='Cartesian', R=planet.radius)
                               for si in s]
@@ -488,22 +538,37 @@ class LineOfSight(object):
                            bayes_set=None, max_T_variation=5.0, max_Plog_variation=1.0,
                            max_opt_depth=None):
         """Merge the intersection points into radtran steps: consecutive points are
-        merged while T varies by < max_T_variation and ln P by < max_Plog_variation; every step
-        gets air-weighted Curtis-Godson T and P (curgod_fort_1/4), the gas columns (curgod_fort_2)
-        and the column-weighted vibrational temperature of every level (curgod_fort_3)."""
+        merged while T varies by < max_T_variation, ln P by < max_Plog_variation and (with
+        max_opt_depth and `lines`) the estimated optical depth sum_gas sigma_peak*column stays below
+        max_opt_depth; every step gets air-weighted Curtis-Godson T and P (curgod_fort_1/4), the
+        gas columns (curgod_fort_2) and the column-weighted vibrational temperature of every level
+        (curgod_fort_3), evaluated at the solar zenith angles self.szas when the level's profile
+        depends on the SZA (calc_SZA_along_los, or a constant with use_tangent_sza)."""
         pts = self.intersections
         n = len(pts)
         atm = planet.atmosphere
         T = np.array([atm.calc(p, 'temp') for p in pts])
         P = np.array([atm.calc(p, 'pres') for p in pts])
         nd = P / (kb_hpa * T)
-        x = (self._s[0] - self._s) * 1.e5                       # path length from the far end, cm
+        x = np.abs(self._s[0] - self._s) * 1.e5                 # path length from the first point, cm
         lnP = np.log(P)
+        sigma = None
+        if max_opt_depth is not None and max_opt_depth > 0.0:
+            if not lines:
+                raise ValueError('max_opt_depth needs the line list (peak cross-sections)')
+            sigma = peak_cross_sections(planet, lines)
+            vmr_all = dict((g, np.array([planet.gases[g].abundance.calc(p, 'vmr') for p in pts]))
+                           for g in planet.gases)
         bounds, i0 = [], 0
         for i in range(1, n):
             seg = slice(i0, i + 1)
+            too_thick = False
+            if sigma is not None:
+                tau = sum(sigma[g] * curgods.curgod_fort_2(nd[seg], vmr_all[g][seg], x[seg], i + 1 - i0)
+                          for g in planet.gases)
+                too_thick = tau > max_opt_depth
             if (T[seg].max() - T[seg].min() > max_T_variation or
-                    lnP[seg].max() - lnP[seg].min() > max_Plog_variation) and i - i0 >= 2:
+                    lnP[seg].max() - lnP[seg].min() > max_Plog_variation or too_thick) and i - i0 >= 2:
                 bounds.append((i0, i - 1))
                 i0 = i - 1
         if n >= 2:
@@ -540,7 +605,14 @@ class LineOfSight(object):
                         if L.vibtemp is None:
                             tv = st['temp']
                         else:
-                            tvp = np.array([L.vibtemp.calc(p, 'vibtemp') for p in pts[a:e + 1]])
+                            if 'sza' in L.vibtemp.grid.names:
+                                if self.szas is None:
+                                    raise ValueError('SZA-dependent vibrational temperatures: call '
+                                                     'calc_SZA_along_los (or set los.szas) first')
+                                tvp = np.array([L.vibtemp.calc(p, 'vibtemp', sza=sz)
+                                                for p, sz in zip(pts[a:e + 1], self.szas[a:e + 1])])
+                            else:
+                                tvp = np.array([L.vibtemp.calc(p, 'vibtemp') for p in pts[a:e + 1]])
                             tv = curgods.curgod_fort_3(nd[sl], vmr, tvp, x[sl], npnt) / col
                         st['vibtemps'][(g, iso, lev)] = tv
             if jac_pars:
@@ -554,7 +626,8 @@ class LineOfSight(object):
             steps.append(st)
         self.radtran_steps = {'step': steps, 'gas_isos': gas_isos,
                               'opt': dict(max_T_variation=max_T_variation,
-                                          max_Plog_variation=max_Plog_variation)}
+                                          max_Plog_variation=max_Plog_variation,
+                                          max_opt_depth=max_opt_depth)}
         if queue is not None:
             queue.put(self)
         return self
@@ -585,15 +658,25 @@ class LineOfSight(object):
                      initial_intensity=None):
         """Hi-res radiance of this LOS on sp_grid from device-resident LUTs (one-LOS batch through
         the same C ABI entry point smm.radtrans uses for whole batches).  Returns
-        [SpectralIntensity, {}, bayes_set] like the reference (spect_main_module.py:3214-3228)."""
+        [SpectralIntensity, single_rads, bayes_set copy] like the reference
+        (spect_main_module.py:3214-3228): single_rads = {(gas, iso[, lev]): hi-res contribution of
+        that emitter} (smm.single_radiances); with calc_derivatives the hi-res derivative spectra
+        are attached to the parameters of the returned copy (par.hires_deriv, :2867-2874)."""
         from . import spect_main_module as smm
         rads = smm.los_batch_radiances([self], sp_grid, planet, LUTS,
                                        solo_absorption=solo_absorption,
                                        initial_intensity=initial_intensity)
-        out = [rads[0], dict(), copy.deepcopy(bayes_set)]
+        single = dict()
+        if not solo_absorption:
+            was = self.tag
+            self.tag = was if was is not None else 'LOS'
+            sr_ = smm.single_radiances([self], sp_grid, planet, LUTS, None, None, 'same', 1.0, None,
+                                       track_levels, solo_absorption=solo_absorption,
+                                       initial_intensity=None)
+            single = dict((k, v[self.tag]) for k, v in sr_.items())
+            self.tag = was
+        out = [rads[0], single, copy.deepcopy(bayes_set)]
         if calc_derivatives:
-            # hi-res derivative spectra of this LOS, attached to the copy of the parameter set
-            # like the reference does (par_mod.hires_deriv, spect_main_module.py:2867-2874)
             rad, jac = smm.los_batch_jacobians([self], sp_grid, planet, LUTS, bayes_set,
                                                solo_absorption=solo_absorption,
                                                initial_intensity=initial_intensity)
@@ -603,6 +686,77 @@ class LineOfSight(object):
         if queue is not None:
             queue.put(out)
         return out
+
+    def radtran(self, wn_range, planet, lines, cartLUTs=None, cartDROP=None, calc_derivatives=False,
+                bayes_set=None, LUTS=None, useLUTs=True, radtran_opt=None, g3D=False,
+                sub_solar_point=None, solo_absorption=False, initial_intensity=None,
+                track_levels=None, sp_grid=None, LUTopt=None):
+        """The single-LOS forward model of the reference's slow path (callers smm:2506-2545,
+        radtran_test_CO.py:194 through smm.inversion, radtran_3D_ch4.py:312, 336): intersections
+        (kept if already computed, e.g. with LOS_order='photon'), SZA along the LOS when g3D,
+        radtran steps, then the hi-res radiance over wn_range.  useLUTs=True interpolates the
+        look-up tables (built for this atmosphere when LUTS is None); useLUTs=False evaluates the
+        cross-sections line by line at every step's own Curtis-Godson (P, T) - no table, no
+        interpolation.  Returns [SpectralIntensity, single_rads, bayes_set copy]; with
+        calc_derivatives the hi-res derivative spectra are ALSO attached to the parameters of the
+        bayes_set that was passed in, which is where smm.inversion reads them (:2508-2515)."""
+        from . import spect_main_module as smm
+        radtran_opt = dict(radtran_opt or {})
+        if self.intersections is None:
+            self.calc_atm_intersections(planet)
+        if g3D:
+            if sub_solar_point is None:
+                raise ValueError('g3D needs the sub-solar point')
+            self.calc_SZA_along_los(planet, sub_solar_point)
+        self.calc_radtran_steps(planet, lines, calc_derivatives=calc_derivatives, bayes_set=bayes_set,
+                                **radtran_opt)
+        if sp_grid is None:
+            sp_grid = smm.prepare_spe_grid(wn_range).spectral_grid
+        if initial_intensity is not None and hasattr(initial_intensity, 'spectrum'):
+            initial_intensity = initial_intensity.spectrum
+        if not useLUTs:
+            out = smm.los_radiance_line_by_line(self, sp_grid, planet, lines,
+                                                calc_derivatives=calc_derivatives, bayes_set=bayes_set,
+                                                solo_absorption=solo_absorption,
+                                                initial_intensity=initial_intensity)
+        else:
+            if LUTS is None:
+                gases = list(planet.gases.values())
+                opt = dict(LUTopt or {})
+                if 'max_pres' not in opt:
+                    opt['max_pres'] = max(st['pres'] for st in self.radtran_steps['step']) * 1.01
+                PT = smm.calc_PT_couples_atmosphere(lines, gases, planet.atmosphere, **opt)
+                LUTS = smm.check_and_build_allluts(dict(cart_LUTS=cartLUTs), sp_grid, lines, gases,
+                                                   PTcouples=PT, LUTopt=opt)
+            out = self.radtran_fast(sp_grid, planet, cartLUTs=cartLUTs, cartDROP=cartDROP,
+                                    calc_derivatives=calc_derivatives, bayes_set=bayes_set, LUTS=LUTS,
+                                    radtran_opt=radtran_opt, track_levels=track_levels,
+                                    solo_absorption=solo_absorption,
+                                    initial_intensity=initial_intensity)
+        if calc_derivatives and bayes_set is not None:
+            for par, par_mod in zip(bayes_set.params(), out[2].params()):
+                par.hires_deriv = par_mod.hires_deriv
+                par.not_involved = not self.involved_retparams.get((par.nameset, par.key), False)
+        return out
+
+
+def peak_cross_sections(planet, lines):
+    """{gas name: largest line-centre absorption cross-section estimate, cm2 per molecule of the
+    gas}: max over the gas' lines of Strength(296 K, abundance included) / (Doppler HWHM at 296 K *
+    sqrt(pi / ln 2)) - the scale the `max_opt_depth` step limit multiplies the gas columns with
+    (DESIGN.md 6.1)."""
+    from . import spect_classes as spcl
+    out = dict()
+    for g, gas in planet.gases.items():
+        best = 0.0
+        for iso in gas.all_iso:
+            im = getattr(gas, iso)
+            for lin in lines:
+                if lin.Mol == im.mol and lin.Iso == im.iso:
+                    dw = spcl.Doppler_width(T_ref, im.MM, lin.Freq)
+                    best = max(best, lin.Strength / (dw * mt.sqrt(mt.pi / mt.log(2.0))))
+        out[g] = best
+    return out
 
 
 class VIMSPixel(object):

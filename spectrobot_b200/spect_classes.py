@@ -513,6 +513,68 @@ class SpectralGrid(object):
     def max_wn(self):
         return self.grid.max()
 
+    def half_precision(self):
+        self.grid = self.grid.astype(np.float16)
+
+    def double_precision(self):
+        self.grid = self.grid.astype(float)
+
+    # unit conversions of the axis (:396-432): nm <-> mum <-> cm_1 <-> hz; the grid is kept
+    # ascending, so conversions between wavelength-like and wavenumber-like units reverse it
+    def convertto_nm(self):
+        if self.units == 'mum':
+            self.grid = self.grid * 1.e3
+        elif self.units == 'cm_1':
+            self.grid = (1.e7 / self.grid)[::-1].copy()
+        elif self.units == 'hz':
+            self.grid = (const.c / (1.e-9 * self.grid))[::-1].copy()
+        elif self.units != 'nm':
+            raise ValueError('Cannot recognize units {}'.format(self.units))
+        self.units = 'nm'
+        return self.grid
+
+    def convertto_cm_1(self):
+        self.convertto_nm()
+        self.grid = (1.e7 / self.grid)[::-1].copy()
+        self.units = 'cm_1'
+        return self.grid
+
+    def convertto_mum(self):
+        self.grid = self.convertto_nm() * 1.e-3
+        self.units = 'mum'
+        return self.grid
+
+    def convertto_hz(self):
+        self.convertto_nm()
+        self.grid = (const.c / (1.e-9 * self.grid))[::-1].copy()
+        self.units = 'hz'
+        return self.grid
+
+
+def convertto_nm(w, units):
+    """Scalar / array axis value to nm (:2066-2078)."""
+    if units == 'nm':
+        return w
+    if units == 'mum':
+        return w * 1.e3
+    if units == 'cm_1':
+        return 1.e7 / w
+    if units == 'hz':
+        return const.c / (1.e-9 * w)
+    raise ValueError('Cannot recognize units {}'.format(units))
+
+
+def convertto_cm_1(w, units):
+    return 1.e7 / convertto_nm(w, units)
+
+
+def convertto_mum(w, units):
+    return convertto_nm(w, units) * 1.e-3
+
+
+def convertto_hz(w, units):
+    return const.c / (1.e-9 * convertto_nm(w, units))
+
 
 class SpectralObject(object):
     """A spectrum on a SpectralGrid (:435-1159; unit conversions and plotting left out)."""
@@ -577,6 +639,48 @@ class SpectralObject(object):
     def double_precision(self):
         self.spectrum = self.spectrum.astype(np.float64)
 
+    # spectral density per unit of the axis: converting the axis multiplies by |d old / d new|
+    # and, between wavelength-like and wavenumber-like axes, reverses the arrays (:753-797)
+    def convertto_nm(self):
+        u = self.spectral_grid.units
+        g = self.spectral_grid.grid
+        if u == 'mum':
+            self.spectrum = self.spectrum * 1.e-3
+        elif u == 'cm_1':
+            self.spectrum = (self.spectrum * g ** 2 * 1.e-7)[::-1].copy()
+        elif u == 'hz':
+            self.spectrum = (self.spectrum * g ** 2 * 1.e-9 / const.c)[::-1].copy()
+        self.spectral_grid.convertto_nm()
+        return self.spectral_grid.grid, self.spectrum
+
+    def convertto_mum(self):
+        self.convertto_nm()
+        self.spectrum = self.spectrum * 1.e3
+        self.spectral_grid.convertto_mum()
+        return self.spectral_grid.grid, self.spectrum
+
+    def convertto_cm_1(self):
+        self.convertto_nm()
+        self.spectrum = (self.spectrum * self.spectral_grid.grid ** 2 * 1.e-7)[::-1].copy()
+        self.spectral_grid.convertto_cm_1()
+        return self.spectral_grid.grid, self.spectrum
+
+    def convertto_hz(self):
+        self.convertto_nm()
+        self.spectrum = (self.spectrum * self.spectral_grid.grid ** 2 * 1.e-9 / const.c)[::-1].copy()
+        self.spectral_grid.convertto_hz()
+        return self.spectral_grid.grid, self.spectrum
+
+    def convert_grid_to(self, units):
+        """(:738-751)"""
+        if units == self.spectral_grid.units:
+            return self.spectral_grid.grid, self.spectrum
+        conv = dict(nm=self.convertto_nm, mum=self.convertto_mum, cm_1=self.convertto_cm_1,
+                    hz=self.convertto_hz)
+        if units not in conv:
+            raise ValueError('Cannot recognize units {}'.format(units))
+        return conv[units]()
+
     def integrate(self, w1=None, w2=None, offset=None):
         g = self.spectral_grid.grid
         cond = ~np.isnan(self.spectrum)
@@ -604,6 +708,8 @@ class SpectralObject(object):
         out.spectrum = engine.convolve_lowres_host(self.spectral_grid.grid, self.spectrum,
                                                    new_spectral_grid.grid, spectral_widths,
                                                    n_sigma)[0]
+        if hasattr(out, 'intensity'):
+            out.intensity = out.spectrum
         return out
 
     def add_lines_to_spectrum(self, lines, Strengths=None, fix_length=imxsig, n_threads=n_threads):
@@ -651,14 +757,59 @@ class SpectralIntensity(SpectralObject):
         SpectralObject.__init__(self, intensity, spectral_grid, direction=direction, units=units)
         self.intensity = self.spectrum
 
+    INTENSITY_TO_WM2 = dict(Wm2=1.0, ergscm2=1.e-3, nWcm2=1.e-5)     # (:1208-1237)
+
+    def convertto(self, new_units):
+        """Intensity units 'Wm2', 'ergscm2', 'nWcm2' (:1200-1237)."""
+        if new_units not in self.INTENSITY_TO_WM2:
+            raise ValueError('No method for units ' + str(new_units))
+        if new_units != self.units:
+            self.spectrum = self.spectrum * (self.INTENSITY_TO_WM2[self.units] /
+                                             self.INTENSITY_TO_WM2[new_units])
+            self.intensity = self.spectrum
+            self.units = new_units
+        return self.spectrum
+
+    def convertto_Wm2(self):
+        return self.convertto('Wm2')
+
+    def convertto_ergscm2(self):
+        return self.convertto('ergscm2')
+
+    def convertto_nWcm2(self):
+        return self.convertto('nWcm2')
+
+    def add_noise(self, noise):
+        self.noise = copy.deepcopy(noise)
+
+    def add_bands(self, bands):
+        self.bands = copy.deepcopy(bands)
+
     def hires_to_lowres(self, lowres_obs, spectral_widths=None, keep_original_hires=True):
-        """Low-res spectrum on the observation's grid (:1180-1191).  Both grids must be in the
-        same units here (the unit conversions of the reference are out of scope)."""
-        if lowres_obs.spectral_grid.units != self.spectral_grid.units:
-            raise ValueError('hires_to_lowres: convert the observation grid to %s first'
-                             % self.spectral_grid.units)
-        return self.convolve_to_grid_from_irregular(lowres_obs.spectral_grid,
-                                                    spectral_widths=spectral_widths)
+        """Low-res spectrum on the observation's grid, in the observation's axis and intensity
+        units (:1180-1191): the spectrum is converted to the axis of the observation
+        (convert_grid_to), convolved there, and its intensity units follow lowres_obs.units.  A
+        cm-1 spectrum seen by an nm observation (the VIMS case) is converted and convolved in one
+        device pass."""
+        gigi = copy.deepcopy(self) if keep_original_hires else self
+        want = lowres_obs.spectral_grid.units
+        if gigi.spectral_grid.units == 'cm_1' and want == 'nm':
+            if spectral_widths is None:
+                spectral_widths = [lowres_obs.spectral_grid.step()] * len(lowres_obs.spectral_grid.grid)
+            elif isinstance(spectral_widths, (int, float)):
+                spectral_widths = [spectral_widths] * len(lowres_obs.spectral_grid.grid)
+            low = copy.deepcopy(gigi)
+            low.spectral_grid = copy.deepcopy(lowres_obs.spectral_grid)
+            low.spectrum = engine.convolve_lowres_host(gigi.spectral_grid.grid, gigi.spectrum,
+                                                       lowres_obs.spectral_grid.grid,
+                                                       spectral_widths, 5., units='nm')[0]
+            low.intensity = low.spectrum
+        else:
+            gigi.convert_grid_to(want)
+            low = gigi.convolve_to_grid_from_irregular(lowres_obs.spectral_grid,
+                                                       spectral_widths=spectral_widths)
+        low.convertto(getattr(lowres_obs, 'units', low.units))
+        return low
 
 
 class SpectralGcoeff(SpectralObject):

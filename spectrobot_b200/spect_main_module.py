@@ -91,8 +91,9 @@ def calc_PT_couples_atmosphere(lines, molecs, atmosphere, pres_step_log=0.4, tem
         t_1 = (np.ceil(t_max / temp_step) + 1) * temp_step
         couples += [[pres, temp] for temp in np.arange(t_0, t_1 + 0.5 * temp_step, temp_step)]
 
-    if not isinstance(molecs, (list, tuple)):
+    if isinstance(molecs, (sbm.Molec, sbm.IsoMolec)):
         molecs = [molecs]
+    molecs = list(molecs)        # dict.values() of a Python-3 caller (planet.gases.values())
     mms = []
     for mol in molecs:
         if isinstance(mol, sbm.Molec):
@@ -813,6 +814,18 @@ class BayesSet(object):
     def VCM_apriori(self):
         return np.diag(np.array([par.apriori_err for par in self.params()], dtype=float) ** 2)
 
+    def update_params(self, delta_x):
+        """(smm:224-229)"""
+        self.old_params.append(copy.deepcopy(self.param_vector()))
+        for par, dx in zip(self.params(), delta_x):
+            par.update_par(dx)
+
+    def store_avk(self, av_kernel):
+        self.av_kernel = copy.deepcopy(av_kernel)
+
+    def store_VCM(self, VCM):
+        self.VCM = copy.deepcopy(VCM)
+
     def build_jacobian(self, masks=None):
         """[n_obs_points x n_tot] from the per-pixel derivative spectra stored on the parameters
         (smm:197-222)."""
@@ -843,27 +856,41 @@ def los_step_tables(loss, planet):
 def planet_atmosphere_tables(planet, gas_isos):
     """engine.Atmosphere (the tables of sr_atmosphere) from an sbm planet: T (linear), P
     (log-linear), one VMR profile per (gas, iso) entry and the vibrational-temperature profiles of
-    the levels, all on the atmosphere's altitude grid."""
+    the levels, all on the atmosphere's altitude grid; vibrational temperatures may carry a
+    solar-zenith-angle axis (3-D profiles on ('lat', 'sza', 'alt'), radtran_3D_ch4.py:249-250)."""
     atm = planet.atmosphere
     z = atm.grid.coords['alt']
-    two_d = atm.grid.n_dim > 1
+    two_d = 'lat' in atm.grid.names
     n_band = len(atm.grid.coords['lat']) - 1 if two_d else 1
 
-    def table(prof, name):
+    def table(prof, name, sza_nodes=None):
         if not np.array_equal(prof.grid.coords['alt'], z):
             raise ValueError('profile %s is not on the atmosphere altitude grid' % name)
         v = np.asarray(prof.values[name], dtype=float)
-        if v.ndim == 1:
-            v = np.broadcast_to(v, (n_band, len(z)))
-        elif v.shape[0] != n_band:
+        has_lat, has_sza = 'lat' in prof.grid.names, 'sza' in prof.grid.names
+        if has_sza and (sza_nodes is None or not np.array_equal(prof.grid.coords['sza'], sza_nodes)):
+            raise ValueError('profile %s: all SZA-dependent profiles must share their SZA nodes' % name)
+        if has_lat and v.shape[0] != n_band:
             raise ValueError('profile %s has %d latitude bands, atmosphere has %d'
                              % (name, v.shape[0], n_band))
+        if not has_lat:
+            v = np.broadcast_to(v, (n_band,) + v.shape)
+        if sza_nodes is not None and not has_sza:
+            v = np.broadcast_to(v[:, None, :], (n_band, len(sza_nodes), len(z)))
         return v
 
+    sza_nodes = None
+    for g, iso in gas_isos:
+        im = getattr(planet.gases[g], iso)
+        for lev in im.levels:
+            vt = getattr(im, lev).vibtemp
+            if vt is not None and 'sza' in vt.grid.names and sza_nodes is None:
+                sza_nodes = np.asarray(vt.grid.coords['sza'], dtype=float)
     n_lev = max([len(getattr(planet.gases[g], iso).levels) for g, iso in gas_isos] + [0])
     vmr = np.stack([table(planet.gases[g].abundance, 'vmr') for g, iso in gas_isos])
     tvib_on = -np.ones((len(gas_isos), n_lev), dtype=np.int32)
-    tvib = np.full((len(gas_isos), n_lev, n_band, len(z)), 100.0)
+    shape = (n_band, len(z)) if sza_nodes is None else (n_band, len(sza_nodes), len(z))
+    tvib = np.full((len(gas_isos), n_lev) + shape, 100.0)
     for m, (g, iso) in enumerate(gas_isos):
         im = getattr(planet.gases[g], iso)
         for j, lev in enumerate(im.levels):
@@ -872,34 +899,63 @@ def planet_atmosphere_tables(planet, gas_isos):
                 tvib_on[m, j] = 0
             else:
                 tvib_on[m, j] = 1
-                tvib[m, j] = table(L.vibtemp, 'vibtemp')
+                tvib[m, j] = table(L.vibtemp, 'vibtemp', sza_nodes)
     return engine.Atmosphere(z, table(atm, 'temp'), table(atm, 'pres'), vmr,
                              tvib=tvib if n_lev else None, tvib_on=tvib_on if n_lev else None,
                              lat_edges=atm.grid.coords['lat'] if two_d else None,
-                             radius_km=planet.radius, top_km=planet.atm_extension)
+                             radius_km=planet.radius, top_km=planet.atm_extension,
+                             sza_nodes=sza_nodes)
 
 
 def los_step_tables_device(loss, planet, bayes_set=None, set_name=None, delta_x=5.0,
-                           max_T_variation=5.0, max_Plog_variation=1.0, max_opt_depth=None):
-    """calc_atm_intersections + calc_radtran_steps for a whole list of sbm.LineOfSight in ONE
-    library call (sr_los_steps_build).  Returns (gas_isos, engine.LosSteps,
-    dfrac): dfrac [n_los][n_steps_max][n_par] for the parameters of bayes_set.sets[set_name] (a
-    VMR set named like a gas of the planet), else None.  Also fills los.involved_retparams."""
+                           max_T_variation=5.0, max_Plog_variation=1.0, max_opt_depth=None,
+                           lines=None, ssps=None, fszas=None, use_tangent_sza=False,
+                           LOS_order='radtran'):
+    """calc_atm_intersections + calc_SZA_along_los + calc_radtran_steps for a whole list of
+    sbm.LineOfSight in ONE library call (sr_los_steps_build_rays).
+
+    ssps: sub-solar point (sbm.Coords) per LOS -> SZA at every sample of the ray; fszas with
+    use_tangent_sza: one SZA per LOS (smm:3138-3141); LOS_order 'photon' = invert_LOS_direction
+    (smm:3135-3137); max_opt_depth needs `lines` (peak cross-sections, sbm.peak_cross_sections).
+    Returns (gas_isos, engine.LosSteps, dfrac): dfrac [n_los][n_steps_max][n_par] for the parameters
+    of bayes_set.sets[set_name] (a VMR set named like a gas of the planet), else None.  Also fills
+    los.involved_retparams."""
     gi = [(g, iso) for g in sorted(planet.gases) for iso in planet.gases[g].all_iso]
     atm = planet_atmosphere_tables(planet, gi)
     org = np.array([l.starting_point.Cartesian() for l in loss])
     drc = np.array([l.direction for l in loss])
+    sun = sza_fixed = None
+    if use_tangent_sza:
+        if fszas is None:
+            raise ValueError('use_tangent_sza needs the tangent-point SZA of every LOS')
+        sza_fixed = np.asarray(fszas, dtype=float)
+    elif ssps is not None:
+        sun = np.array([p.Cartesian() for p in ssps])
+    elif atm.n_sza > 1:
+        raise ValueError('the vibrational temperatures depend on the SZA: pass the sub-solar points '
+                         '(ssps) or use_tangent_sza with fszas')
+    sigma = None
+    if max_opt_depth is not None and max_opt_depth > 0.0:
+        if not lines:
+            raise ValueError('max_opt_depth needs the line list (peak cross-sections)')
+        sg = sbm.peak_cross_sections(planet, lines)
+        seen, sigma = set(), []
+        for g, iso in gi:     # the column of a gas is counted once, on its first isotopologue entry
+            sigma.append(0.0 if g in seen else sg[g])
+            seen.add(g)
     masks, jac_gas, pars = None, -1, []
     if bayes_set is not None and set_name is not None and set_name in planet.gases:
         pars = bayes_set.sets[set_name].set
-        lat_edges = planet.atmosphere.grid.coords['lat'] if planet.atmosphere.grid.n_dim > 1 else None
+        lat_edges = planet.atmosphere.grid.coords['lat'] if 'lat' in planet.atmosphere.grid.names else None
         masks = np.array([np.broadcast_to(p.maskgrid.table(atm.z, lat_edges), (atm.n_band, len(atm.z)))
                           for p in pars])
         jac_gas = [g for g, iso in gi].index(set_name)
     steps, dfrac = engine.los_steps_build(atm, org, drc, delta_x=delta_x,
                                           max_T_variation=max_T_variation,
                                           max_Plog_variation=max_Plog_variation, masks=masks,
-                                          jac_gas=jac_gas)
+                                          jac_gas=jac_gas, sun=sun, sza_fixed=sza_fixed,
+                                          max_opt_depth=max_opt_depth, sigma_peak=sigma,
+                                          photon_order=(LOS_order == 'photon'))
     if bayes_set is not None:
         for l, los in enumerate(loss):
             for par in bayes_set.params():
@@ -909,8 +965,32 @@ def los_step_tables_device(loss, planet, bayes_set=None, set_name=None, delta_x=
     return gi, steps, dfrac
 
 
+def observation_channels(obs, sp_gri):
+    """(centres, widths, units mode, intensity factor) that turn the device convolution into
+    SpectralIntensity.hires_to_lowres(obs, spectral_widths=obs.bands.spectrum) (spcl:1180-1191):
+    the hi-res radiances are in 'ergscm2' per cm-1 on sp_gri; the observation may be on a cm-1 axis
+    (units mode 'same'), or on a wavelength axis in nm or micron (mode 'nm': converted per point
+    and convolved on the wavelength axis on the device; micron channels are rescaled to nm), and in
+    any of the intensity units of SpectralIntensity.convertto."""
+    hi_units = getattr(sp_gri, 'units', 'cm_1')
+    lo_units = obs.spectral_grid.units
+    centres = np.asarray(obs.spectral_grid.grid, dtype=float)
+    widths = np.asarray(obs.bands.spectrum, dtype=float)
+    factor = spcl.SpectralIntensity.INTENSITY_TO_WM2['ergscm2'] / \
+        spcl.SpectralIntensity.INTENSITY_TO_WM2[getattr(obs, 'units', 'ergscm2')]
+    if lo_units == hi_units:
+        return centres, widths, 'same', factor
+    if hi_units == 'cm_1' and lo_units == 'nm':
+        return centres, widths, 'nm', factor
+    if hi_units == 'cm_1' and lo_units == 'mum':      # per micron = per nm * 1e3 (spcl:780-784)
+        return centres * 1.e3, widths * 1.e3, 'nm', factor * 1.e3
+    raise ValueError('observation axis in {} over a hi-res grid in {}: convert the observation to '
+                     'cm_1, nm or mum first'.format(lo_units, hi_units))
+
+
 def los_batch_radiances(loss, sp_grid, planet, LUTS, solo_absorption=False,
-                        initial_intensity=None, lowres=None, pt0=0, n_pts=None, tables=None):
+                        initial_intensity=None, lowres=None, pt0=0, n_pts=None, tables=None,
+                        lowres_units='same'):
     """Radiances of a batch of lines of sight in ONE launch sequence.
 
     loss: sbm.LineOfSight objects with radtran_steps; LUTS: {(mol_name, iso): LookUpTable}.
@@ -940,13 +1020,90 @@ def los_batch_radiances(loss, sp_grid, planet, LUTS, solo_absorption=False,
     if lowres is not None:   # LOS blocks are reduced to the channels on the device, batch of any size
         gdev = torch.as_tensor(np.ascontiguousarray(grid, dtype=float), device="cuda")
         return engine.los_rt_lut_lowres(luts, steps, gdev, lowres[0], lowres[1], pt0=pt0,
-                                        n_pts=n_pts, i0=i0, solo_absorption=solo_absorption)
+                                        n_pts=n_pts, i0=i0, solo_absorption=solo_absorption,
+                                        units=lowres_units)
     rad = engine.los_rt_lut(luts, steps, pt0=pt0, n_pts=n_pts, i0=i0,
                             solo_absorption=solo_absorption)
     rad = rad.cpu().numpy()
     units = getattr(sp_grid, 'units', 'cm_1')
     sub = spcl.SpectralGrid(grid[pt0:pt0 + n_pts], units=units)
     return [spcl.SpectralIntensity(rad[i], sub) for i in range(len(loss))]
+
+
+def los_radiance_line_by_line(los, sp_grid, planet, lines, calc_derivatives=False, bayes_set=None,
+                              solo_absorption=False, initial_intensity=None):
+    """Hi-res radiance of ONE line of sight WITHOUT look-up tables (`useLUTs=False`, the reference's
+    make_abscoeff_isomolec path, smm:1880-2131): the G-coefficient spectra of every isotopologue
+    are evaluated line by line (K1: sr_gcoeff_cells_dev, FP64) at each step's own Curtis-Godson
+    (P, T), weighted with the level populations (smm:2200-2250 arithmetic) into tau and J per
+    step, and run through the layer recursion (K3: sr_los_rt_layers[_jac]_dev).  Returns
+    [SpectralIntensity, {}, bayes_set copy (with hires_deriv when calc_derivatives)]."""
+    import torch
+    steps = los.radtran_steps['step']
+    gi = los.radtran_steps['gas_isos']
+    grid = sp_grid.grid
+    n, n_grid = len(steps), len(grid)
+    PT = [[st['pres'], st['temp']] for st in steps]
+    temps = np.array([st['temp'] for st in steps])
+    dev = dict(dtype=torch.float64, device="cuda")
+    tau = torch.zeros((1, n, n_grid), **dev)
+    emi = torch.zeros((1, n, n_grid), **dev)
+    per_gas = dict()
+    for g, iso in gi:
+        im = getattr(planet.gases[g], iso)
+        mine = [lin for lin in lines if lin.Mol == im.mol and lin.Iso == im.iso]
+        if not mine:
+            continue
+        lte_unid = len(im.levels) == 0
+        tab = spcl.line_table(mine, None if lte_unid else im)
+        ls = engine.LineSet(tab, grid, im.MM, tab["n_sets"])
+        G = ls.gcoeff_cells(PT)                                   # [n, n_sets, 3, n_grid]
+        ls.close()
+        q = np.array([spcl.CalcPartitionSum(im.mol, im.iso, temp=t) for t in temps])
+        if lte_unid:
+            pop = (1.0 / q)[:, None]
+        else:
+            tv = np.array([[st['vibtemps'][(g, iso, lev)] for lev in im.levels] for st in steps])
+            pop = spcl.Boltz_ratio_nodeg(im.level_energies()[None, :], tv) / q[:, None]
+        col = np.array([st['columns'][g] for st in steps]) * im.ratio
+        w = torch.as_tensor(pop * col[:, None], **dev)            # [n, n_sets]
+        a = torch.einsum('ks,ksp->kp', w, G[:, :, 2] - G[:, :, 1])
+        e = torch.einsum('ks,ksp->kp', w, G[:, :, 0])
+        del G
+        tau[0] += a
+        emi[0] += e
+        ta, te = per_gas.get(g, (0, 0))
+        per_gas[g] = (ta + a, te + e)
+    nst = torch.tensor([n], dtype=torch.int32, device="cuda")
+    i0 = None
+    if initial_intensity is not None:
+        i0 = torch.as_tensor(np.broadcast_to(np.asarray(initial_intensity, dtype=float), (1, n_grid)).copy(),
+                             device="cuda")
+    out_set = copy.deepcopy(bayes_set)
+    if calc_derivatives and bayes_set is not None:
+        rad = None
+        jacs = []
+        for nam in bayes_set.order:
+            n_par = bayes_set.sets[nam].n_par
+            if nam not in per_gas:
+                jacs.append(torch.zeros((1, n_par, n_grid), **dev))
+                continue
+            dfrac = torch.as_tensor(los_jac_tables([los], bayes_set, nam, n), **dev)
+            only = len(per_gas) == 1
+            tg = None if only else per_gas[nam][0][None].contiguous()
+            eg = None if only else per_gas[nam][1][None].contiguous()
+            rad, jac = engine.los_rt_layers_jac(tau, emi, dfrac, nst, tau_g=tg, emi_g=eg, i0=i0,
+                                                solo_absorption=solo_absorption)
+            jacs.append(jac)
+        jac = torch.cat(jacs, dim=1).cpu().numpy()[0]
+        for par, d in zip(out_set.params(), jac):
+            par.add_hires_deriv(spcl.SpectralIntensity(d, sp_grid))
+    else:
+        rad = None
+    if rad is None:
+        src = torch.where(tau == 0.0, torch.zeros_like(tau), emi / tau)
+        rad = engine.los_rt_layers(tau, src, nst, i0=i0, solo_absorption=solo_absorption)
+    return [spcl.SpectralIntensity(rad.cpu().numpy()[0], sp_grid), dict(), out_set]
 
 
 def los_jac_tables(loss, bayes_set, set_name, n_steps_max):
@@ -966,7 +1123,8 @@ def los_jac_tables(loss, bayes_set, set_name, n_steps_max):
 
 
 def los_batch_jacobians(loss, sp_grid, planet, LUTS, bayes_set, solo_absorption=False,
-                        initial_intensity=None, lowres=None, pt0=0, n_pts=None, tables=None):
+                        initial_intensity=None, lowres=None, pt0=0, n_pts=None, tables=None,
+                        lowres_units='same'):
     """Radiances AND their derivatives with respect to every parameter of bayes_set for a batch of
     lines of sight (the `calc_derivatives=True` path of radtran_fast, smm:2837-2881), one fused
     library call per retrieved gas.  Parameter sets whose name is not a gas of the planet get zero
@@ -1017,13 +1175,15 @@ def los_batch_jacobians(loss, sp_grid, planet, LUTS, bayes_set, solo_absorption=
         else:
             rad, jac = engine.los_rt_lut_jac_lowres(luts, steps, dfrac, gdev, lowres[0], lowres[1],
                                                     gas_in_jac=in_jac, pt0=pt0, n_pts=n_pts, i0=i0,
-                                                    solo_absorption=solo_absorption)
+                                                    solo_absorption=solo_absorption,
+                                                    units=lowres_units)
         blocks.append(jac)
     if rad is None:   # no parameter touches a gas with a LUT: plain forward model
         rad = (engine.los_rt_lut(luts, steps, pt0=pt0, n_pts=n_pts, i0=i0,
                                  solo_absorption=solo_absorption) if lowres is None else
                engine.los_rt_lut_lowres(luts, steps, gdev, lowres[0], lowres[1], pt0=pt0,
-                                        n_pts=n_pts, i0=i0, solo_absorption=solo_absorption))
+                                        n_pts=n_pts, i0=i0, solo_absorption=solo_absorption,
+                                        units=lowres_units))
     jac = torch.cat(blocks, dim=1)
     if lowres is not None:
         return rad, jac
@@ -1123,35 +1283,75 @@ def _pixel_los_altitudes(pix):
                      for lin in (pix.low_LOS(), pix.LOS(), pix.up_LOS())])
 
 
-def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_opt=dict(),
-             save_hires=True, save_lowres=True, LUTopt=dict(), test=False, use_tangent_sza=False,
-             group_observations=False, invert_LOS_direction=False, nome_inv='1',
-             track_levels=None, alt_step_sims=50., alt_first_los=None):
-    """Forward model for a list of pixels (smm:2990-3287), batched on the GPU.
+def check_lines_mols(lines, molecs):
+    """Only the lines of the given molecules; for an isotopologue that carries levels, only the
+    lines whose upper AND lower level it knows (smm:69-91)."""
+    lines_ok = []
+    for mol in molecs:
+        for iso in mol.all_iso:
+            isomol = getattr(mol, iso)
+            mine = [lin for lin in lines if lin.Mol == isomol.mol and lin.Iso == isomol.iso]
+            if len(isomol.levels) > 0:
+                mine = [lin for lin in mine if isomol.has_level(lin.Lo_lev_str)[0]
+                        and isomol.has_level(lin.Up_lev_str)[0]]
+            lines_ok += mine
+    return lines_ok
 
-    Three lines of sight per pixel (low, centre, up; :3091-3096) -> radtran steps (host,
-    Curtis-Godson through the `curgods` drop-in) -> ONE library call for all LOS
-    (engine.los_rt_lut_lowres), reduced to the instrument channels on the device.
-    Returns (sims, radtrans, single_rads): `radtrans` = {LOS tag: low-res SpectralIntensity};
-    `sims` = per pixel the FOV integral of its three LOS (FOV_integr_1D, :3273-3277), taken from
-    the pixel's own LOS or, with group_observations, from the altitude ladder of
-    make_group_observations through make_radtran_spline (:3263-3272); single_rads = {} (per-gas
-    tracking is not part of the hot path)."""
-    import torch
-    pixels = sorted(pixels, key=lambda p: p.limb_tg_alt)
-    if sp_gri is None:
-        if wn_range is None:
-            raise ValueError('radtrans needs wn_range or sp_gri')
-        sp_gri = prepare_spe_grid(wn_range).spectral_grid
-    if group_observations:   # altitude ladder instead of the pixels' own LOS (smm:3056-3058)
-        sim_LOSs, alts_sim, _, _ = make_group_observations(pixels, alt_step=alt_step_sims,
-                                                           alt_first_los=alt_first_los)
-    else:
-        sim_LOSs = []
-        for pix in pixels:
-            sim_LOSs += [pix.low_LOS(), pix.LOS(), pix.up_LOS()]
-    for num, los in enumerate(sim_LOSs):
-        los.tag = 'LOS{:03d}'.format(num)
+
+def keep_levels_wlines(planet, lines):
+    """Erases the levels of the planet's isotopologues that no line touches (smm:94-115)."""
+    for gas in planet.gases:
+        mol = planet.gases[gas]
+        for iso in mol.all_iso:
+            isomol = getattr(mol, iso)
+            iso_lines = [lin for lin in lines if lin.Mol == isomol.mol and lin.Iso == isomol.iso]
+            for lev in list(isomol.levels):
+                levvo = getattr(isomol, lev)
+                if not any(levvo.equiv(lin.Lo_lev_str) or levvo.equiv(lin.Up_lev_str) for lin in iso_lines):
+                    isomol.erase_level(lev)
+
+
+def keep_levels(planet, keep_levels, lines=None):
+    """Keeps only the levels listed in keep_levels[(gas, iso)] (smm:133-149)."""
+    for gas in planet.gases:
+        mol = planet.gases[gas]
+        for iso in mol.all_iso:
+            isomol = getattr(mol, iso)
+            for lev in list(isomol.levels):
+                if lev not in keep_levels[(gas, iso)]:
+                    isomol.erase_level(lev)
+
+
+def _simulated_los(pixels, group_observations, alt_step_sims, alt_first_los):
+    """(sim_LOSs, alts_sim, ssps, fszas): three LOS per pixel (low, centre, up) with the pixel's
+    sub-solar point and tangent SZA (smm:3091-3100), or the altitude ladder (smm:3056-3058)."""
+    if group_observations:
+        return make_group_observations(pixels, alt_step=alt_step_sims, alt_first_los=alt_first_los)
+    sim_LOSs, ssps, fszas = [], [], []
+    for pix in pixels:
+        sim_LOSs += [pix.low_LOS(), pix.LOS(), pix.up_LOS()]
+        ssps += 3 * [pix.sub_solar_point()]
+        fszas += 3 * [pix.limb_tg_sza]
+    alts_sim = [los.get_tangent_point().Spherical()[2] for los in sim_LOSs]
+    return sim_LOSs, alts_sim, ssps, fszas
+
+
+def _spectral_grid_of(pixels, wn_range, sp_gri):
+    """The hi-res grid of a run (smm:3000-3012): sp_gri, or prepare_spe_grid(wn_range), or - with
+    neither - the observation's own range widened by two channel widths, converted to cm-1."""
+    if sp_gri is not None:
+        return sp_gri
+    if wn_range is None:
+        obs = pixels[0].observation
+        g = copy.deepcopy(obs.spectral_grid)
+        g.grid[0] -= 2 * obs.bands.spectrum[0]
+        g.grid[-1] += 2 * obs.bands.spectrum[-1]
+        g.convertto_cm_1()
+        wn_range = [g.grid[0], g.grid[-1]]
+    return prepare_spe_grid(wn_range).spectral_grid
+
+
+def _luts_for(inputs, planet, lines, pixels, sim_LOSs, sp_gri, LUTopt):
     LUTopt = dict(LUTopt)
     if 'max_pres' not in LUTopt:   # the deepest point any simulated LOS reaches (the reference looks
         # at the pixels' low LOS only, :3010-3024, and stops with 'Extrapolating in P' when the
@@ -1161,107 +1361,191 @@ def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_
                                  [planet.atmosphere.calc(sim_LOSs[0].get_tangent_point(), 'pres')])
     gases = list(planet.gases.values())
     PT = calc_PT_couples_atmosphere(lines, gases, planet.atmosphere, **LUTopt)
-    LUTS = check_and_build_allluts(inputs, sp_gri, lines, gases, PTcouples=PT, LUTopt=LUTopt)
+    return check_and_build_allluts(inputs, sp_gri, lines, gases, PTcouples=PT, LUTopt=LUTopt)
 
-    # geometry + radtran steps of ALL lines of sight in one library call (sr_los_steps_build); the
-    # per-LOS host methods calc_atm_intersections / calc_radtran_steps stay available on sbm
-    tables = los_step_tables_device(sim_LOSs, planet, **radtran_opt)
+
+def track_all_levels(planet):
+    """{(gas, iso): all its levels} - the `track_levels` argument that follows every level."""
+    return dict(((g, iso), list(getattr(planet.gases[g], iso).levels))
+                for g in planet.gases for iso in planet.gases[g].all_iso)
+
+
+def single_radiances(sim_LOSs, sp_gri, planet, LUTS, tables, lowres, lowres_units, factor, obs,
+                     track_levels=None, **kwargs):
+    """single_rads of radtrans (smm:3176-3186, 3242-3246): per (gas, iso) - and per tracked level
+    (gas, iso, lev) - the low-res radiance each LOS receives from THAT emitter alone, absorbed by
+    the whole mixture.  The layer source is linear in the emitters, so these contributions add up
+    to the total radiance (the reference's own definition lives in the missing radtran_fast).
+    One batched device run per emitter, with the spontaneous-emission rows of every other set
+    switched off (sr_lut_set_emission_mask)."""
+    gi = tables[0] if tables is not None else sim_LOSs[0].radtran_steps['gas_isos']
+    keys = []
+    for g, iso in gi:
+        im = getattr(planet.gases[g], iso)
+        if LUTS.get((im.mol_name, im.iso)) is None:
+            continue
+        keys.append((g, iso))
+        if track_levels is not None and (g, iso) in track_levels:
+            keys += [(g, iso, lev) for lev in track_levels[(g, iso)]]
+    luts = dict(((g, iso), LUTS[(getattr(planet.gases[g], iso).mol_name,
+                                 getattr(planet.gases[g], iso).iso)]) for g, iso in gi
+                if LUTS.get((getattr(planet.gases[g], iso).mol_name,
+                             getattr(planet.gases[g], iso).iso)) is not None)
+    out = dict()
+    obs_units = getattr(obs, 'units', 'ergscm2') if obs is not None else 'ergscm2'
+    try:
+        for key in keys:
+            for gk, L in luts.items():
+                if gk != key[:2]:
+                    L.device_lut().set_emission_mask(0)
+                elif len(key) == 2:
+                    L.device_lut().set_emission_mask(None)
+                else:
+                    L.device_lut().set_emission_mask(1 << L.set_names().index(key[2]))
+            if lowres is None:   # hi-res contributions (LineOfSight.radtran_fast)
+                rads = los_batch_radiances(sim_LOSs, sp_gri, planet, LUTS, tables=tables, **kwargs)
+                out[key] = dict((los.tag, r) for los, r in zip(sim_LOSs, rads))
+                continue
+            low = los_batch_radiances(sim_LOSs, sp_gri, planet, LUTS, lowres=lowres, tables=tables,
+                                      lowres_units=lowres_units, **kwargs).cpu().numpy() * factor
+            out[key] = dict((los.tag, spcl.SpectralIntensity(low[i], obs.spectral_grid, units=obs_units))
+                            for i, los in enumerate(sim_LOSs))
+    finally:
+        for L in luts.values():
+            L.device_lut().set_emission_mask(None)
+    return out
+
+
+def radtrans(inputs, planet, lines, pixels, wn_range=None, sp_gri=None, radtran_opt=dict(),
+             save_hires=True, save_lowres=True, LUTopt=dict(), test=False, use_tangent_sza=False,
+             group_observations=False, invert_LOS_direction=False, nome_inv='1',
+             track_levels=None, alt_step_sims=50., alt_first_los=None):
+    """Forward model for a list of pixels (smm:2990-3287), batched on the GPU.
+
+    Three lines of sight per pixel (low, centre, up; :3091-3096) or the altitude ladder of
+    make_group_observations -> geometry, SZA along every LOS (or the tangent SZA with
+    use_tangent_sza) and radtran steps for ALL lines of sight in one library call -> ONE batched
+    call for the radiances, reduced to the instrument channels on the device (any observation axis
+    hires_to_lowres accepts).  invert_LOS_direction runs the layers in LOS_order='photon'.
+    Returns (sims, radtrans, single_rads): `radtrans` = {LOS tag: low-res SpectralIntensity};
+    `sims` = per pixel the FOV integral of its three LOS (FOV_integr_1D, :3273-3277), from its own
+    LOS or, with group_observations, from the ladder through make_radtran_spline (:3263-3272);
+    `single_rads` = {(gas, iso[, lev]): {LOS tag: contribution}} (see single_radiances).
+    With inputs['out_dir']: `lowres_radtran_<nome_inv>.pic` (save_lowres) and, with save_hires, the
+    hi-res radiances `hires_radtran_<nome_inv>.pic` as [0, {LOS tag: SpectralIntensity}]."""
+    lines = check_lines_mols(lines, planet.gases.values())
+    pixels = sorted(pixels, key=lambda p: p.limb_tg_alt)
+    sp_gri = _spectral_grid_of(pixels, wn_range, sp_gri)
+    sim_LOSs, alts_sim, ssps, fszas = _simulated_los(pixels, group_observations, alt_step_sims,
+                                                     alt_first_los)
+    for num, los in enumerate(sim_LOSs):
+        los.tag = 'LOS{:02d}'.format(num)
+    LUTS = _luts_for(inputs, planet, lines, pixels, sim_LOSs, sp_gri, LUTopt)
+
+    # geometry + SZA + radtran steps of ALL lines of sight in one library call; the per-LOS host
+    # methods calc_atm_intersections / calc_SZA_along_los / calc_radtran_steps stay on sbm
+    tables = los_step_tables_device(sim_LOSs, planet, lines=lines, ssps=ssps, fszas=fszas,
+                                    use_tangent_sza=use_tangent_sza,
+                                    LOS_order='photon' if invert_LOS_direction else 'radtran',
+                                    **radtran_opt)
 
     obs = pixels[0].observation
-    centres, widths = obs.spectral_grid.grid, obs.bands.spectrum
-    # one call for the whole batch and range: the library cuts it into LOS blocks x wavenumber
-    # chunks itself (the reference's n_split loop, smm:3190, was a host-memory workaround)
-    low = los_batch_radiances(sim_LOSs, sp_gri, planet, LUTS, lowres=(centres, widths),
-                              tables=tables)
-    low = low.cpu().numpy()
+    centres, widths, ch_units, factor = observation_channels(obs, sp_gri)
+    obs_units = getattr(obs, 'units', 'ergscm2')
+    out_dir = inputs.get('out_dir') if isinstance(inputs, dict) else None
+    if save_hires and out_dir:
+        # the hi-res spectra are wanted on disk: compute them once, convolve them on the device
+        import torch
+        hi = los_batch_radiances(sim_LOSs, sp_gri, planet, LUTS, tables=tables)
+        with open(os.path.join(out_dir, 'hires_radtran_{}.pic'.format(nome_inv)), 'wb') as f:
+            pickle.dump([0, dict((los.tag, h) for los, h in zip(sim_LOSs, hi))], f, protocol=-1)
+        gdev = torch.as_tensor(np.ascontiguousarray(sp_gri.grid, dtype=float), device="cuda")
+        spec = torch.as_tensor(np.array([h.spectrum for h in hi]), device="cuda")
+        low = engine.convolve_lowres(gdev, spec, centres, widths, units=ch_units).cpu().numpy() * factor
+    else:
+        # one call for the whole batch and range: the library cuts it into LOS blocks x wavenumber
+        # chunks itself (the reference's n_split loop, smm:3190, was a host-memory workaround)
+        low = los_batch_radiances(sim_LOSs, sp_gri, planet, LUTS, lowres=(centres, widths),
+                                  tables=tables, lowres_units=ch_units)
+        low = low.cpu().numpy() * factor
     radtrans_out = dict()
     for i, los in enumerate(sim_LOSs):
-        radtrans_out[los.tag] = spcl.SpectralIntensity(low[i], obs.spectral_grid)
+        radtrans_out[los.tag] = spcl.SpectralIntensity(low[i], obs.spectral_grid, units=obs_units)
+    single_rads = single_radiances(sim_LOSs, sp_gri, planet, LUTS, tables, (centres, widths),
+                                   ch_units, factor, obs, track_levels)
     if group_observations:   # spectra at the pixels' LOS altitudes from the ladder (smm:3263-3272)
         radtran_spline = make_radtran_spline(alts_sim, [radtrans_out[los.tag] for los in sim_LOSs])
         sims = []
         for pix in pixels:
             three = np.array([radtran_spline(al).spectrum for al in _pixel_los_altitudes(pix)])
             sims.append(spcl.SpectralIntensity(
-                fov_integrate(three, getattr(pix, 'pixel_rot', 0.0) or 0.0), obs.spectral_grid))
+                fov_integrate(three, getattr(pix, 'pixel_rot', 0.0) or 0.0), obs.spectral_grid,
+                units=obs_units))
     else:
         sims = [spcl.SpectralIntensity(fov_integrate(low[3 * k:3 * k + 3],
                                                      getattr(pixels[k], 'pixel_rot', 0.0) or 0.0),
-                                       obs.spectral_grid) for k in range(len(pixels))]
-    if isinstance(inputs, dict) and inputs.get('out_dir') and save_lowres:
-        with open(os.path.join(inputs['out_dir'], 'lowres_radtran_{}.pic'.format(nome_inv)), 'wb') as f:
-            pickle.dump([sims, radtrans_out], f, protocol=-1)
-    return sims, radtrans_out, dict()
+                                       obs.spectral_grid, units=obs_units) for k in range(len(pixels))]
+    if out_dir and save_lowres:
+        with open(os.path.join(out_dir, 'lowres_radtran_{}.pic'.format(nome_inv)), 'wb') as f:
+            pickle.dump([pixels, sims, sim_LOSs, radtrans_out, single_rads], f, protocol=-1)
+    return sims, radtrans_out, single_rads
 
 
-def inversion_fast_limb(inputs, planet, lines, bayes_set, pixels, wn_range=None, sp_gri=None,
-                        chi_threshold=0.01, max_it=10, lambda_LM=0.1, L1_reg=False,
-                        radtran_opt=dict(), debugfile=None, save_hires=False, save_lowres=True,
-                        LUTopt=dict(), test=False, use_tangent_sza=False, group_observations=False,
-                        nome_inv='1', solo_simulation=False, invert_LOS_direction=False,
-                        alt_step_sims=50., alt_first_los=None, track_levels=None, check_log=None):
-    """ONE forward + Jacobian evaluation of the fast limb retrieval (smm:2598-2956), batched on the
-    GPU: the a-priori / current VMR profiles of bayes_set are installed on the planet (:2626-2627),
-    all lines of sight of all pixels go through the radtran steps with derivative columns and ONE
-    fused library call per retrieved gas returns low-res radiances and derivative spectra; both are
-    FOV-integrated per pixel (:2934-2940) and the derivatives are stored on the parameters
-    (`par.store_deriv`), so that `bayes_set.build_jacobian()` gives the Jacobian the reference's
-    inversion step consumes.  The Levenberg-Marquardt update itself (:2962-2987, `max_it`,
-    `lambda_LM`, `chi_threshold`) is retrieval algebra and out of scope: this
-    function returns after the evaluation.  Returns (sims, radtrans, derivs) with
+def forward_jacobian_limb(inputs, planet, lines, bayes_set, pixels, wn_range=None, sp_gri=None,
+                          radtran_opt=dict(), save_lowres=True, LUTopt=dict(),
+                          use_tangent_sza=False, group_observations=False, nome_inv='1',
+                          invert_LOS_direction=False, alt_step_sims=50., alt_first_los=None,
+                          LUTS=None):
+    """ONE forward + Jacobian evaluation of the fast limb retrieval (the body of the iteration
+    loop, smm:2626-2940), batched on the GPU: the current VMR profiles of bayes_set are installed
+    on the planet (:2626-2627), all lines of sight of all pixels go through the radtran steps with
+    derivative columns and ONE fused library call per retrieved gas returns low-res radiances and
+    derivative spectra; both are FOV-integrated per pixel (:2934-2940) and the derivatives are
+    stored on the parameters (`par.store_deriv`), so that `bayes_set.build_jacobian()` gives the
+    Jacobian inversion_algebra consumes.  Returns (sims, radtrans, derivs) with
     derivs[(LOS tag, nameset, key)] = low-res derivative SpectralIntensity."""
     pixels = sorted(pixels, key=lambda p: p.limb_tg_alt)
-    if sp_gri is None:
-        if wn_range is None:
-            raise ValueError('inversion_fast_limb needs wn_range or sp_gri')
-        sp_gri = prepare_spe_grid(wn_range).spectral_grid
+    sp_gri = _spectral_grid_of(pixels, wn_range, sp_gri)
     for gas in bayes_set.sets.keys():
         if gas in planet.gases:
             planet.gases[gas].add_clim(bayes_set.sets[gas].profile())
-    if group_observations:
-        sim_LOSs, alts_sim, _, _ = make_group_observations(pixels, alt_step=alt_step_sims,
-                                                           alt_first_los=alt_first_los)
-    else:
-        sim_LOSs = []
-        for pix in pixels:
-            sim_LOSs += [pix.low_LOS(), pix.LOS(), pix.up_LOS()]
+    sim_LOSs, alts_sim, ssps, fszas = _simulated_los(pixels, group_observations, alt_step_sims,
+                                                     alt_first_los)
     for num, los in enumerate(sim_LOSs):
         los.tag = 'LOS{:02d}'.format(num)
-    LUTopt = dict(LUTopt)
-    if 'max_pres' not in LUTopt:   # deepest point of any simulated LOS (see radtrans)
-        LUTopt['max_pres'] = max([planet.atmosphere.calc(p.low_LOS().get_tangent_point(), 'pres')
-                                  for p in pixels] +
-                                 [planet.atmosphere.calc(sim_LOSs[0].get_tangent_point(), 'pres')])
-    gases = list(planet.gases.values())
-    PT = calc_PT_couples_atmosphere(lines, gases, planet.atmosphere, **LUTopt)
-    LUTS = check_and_build_allluts(inputs, sp_gri, lines, gases, PTcouples=PT, LUTopt=LUTopt)
+    if LUTS is None:
+        LUTS = _luts_for(inputs, planet, lines, pixels, sim_LOSs, sp_gri, LUTopt)
 
     # geometry, radtran steps and derivative columns of all LOS on the device, one call per
     # retrieved gas (the step tables themselves are identical between the calls)
+    kw = dict(lines=lines, ssps=ssps, fszas=fszas, use_tangent_sza=use_tangent_sza,
+              LOS_order='photon' if invert_LOS_direction else 'radtran')
+    kw.update(radtran_opt)
     tables = dict()
     for nam in bayes_set.order:
         if nam in planet.gases:
             tables[nam] = los_step_tables_device(sim_LOSs, planet, bayes_set=bayes_set,
-                                                 set_name=nam, **radtran_opt)
+                                                 set_name=nam, **kw)
     if not tables:
-        tables[None] = los_step_tables_device(sim_LOSs, planet, bayes_set=bayes_set, **radtran_opt)
+        tables[None] = los_step_tables_device(sim_LOSs, planet, bayes_set=bayes_set, **kw)
 
     obs = pixels[0].observation
-    centres, widths = obs.spectral_grid.grid, obs.bands.spectrum
+    centres, widths, ch_units, factor = observation_channels(obs, sp_gri)
+    obs_units = getattr(obs, 'units', 'ergscm2')
     low, jlow = los_batch_jacobians(sim_LOSs, sp_gri, planet, LUTS, bayes_set,
-                                    lowres=(centres, widths), tables=tables)
-    low, jlow = low.cpu().numpy(), jlow.cpu().numpy()
+                                    lowres=(centres, widths), tables=tables, lowres_units=ch_units)
+    low, jlow = low.cpu().numpy() * factor, jlow.cpu().numpy() * factor
     radtrans_out, derivs = dict(), dict()
     pars = bayes_set.params()
     for i, los in enumerate(sim_LOSs):
-        radtrans_out[los.tag] = spcl.SpectralIntensity(low[i], obs.spectral_grid)
+        radtrans_out[los.tag] = spcl.SpectralIntensity(low[i], obs.spectral_grid, units=obs_units)
         for q, par in enumerate(pars):
             if not los.involved_retparams.get((par.nameset, par.key), False):
                 jlow[i, q] = 0.0                                   # zeroder, smm:2871-2872
             else:
                 par.set_used()
-            derivs[(los.tag, par.nameset, par.key)] = spcl.SpectralIntensity(jlow[i, q],
-                                                                            obs.spectral_grid)
+            derivs[(los.tag, par.nameset, par.key)] = spcl.SpectralIntensity(
+                jlow[i, q], obs.spectral_grid, units=obs_units)
     sims = []
     if group_observations:   # radiances and derivatives interpolated from the ladder (:2904-2929)
         radtran_spline = make_radtran_spline(alts_sim, [radtrans_out[los.tag] for los in sim_LOSs])
@@ -1276,13 +1560,190 @@ def inversion_fast_limb(inputs, planet, lines, bayes_set, pixels, wn_range=None,
         else:
             three = low[3 * k:3 * k + 3]
             ders = [jlow[3 * k:3 * k + 3, q] for q in range(len(pars))]
-        sims.append(spcl.SpectralIntensity(fov_integrate(three, rot), obs.spectral_grid))
+        sims.append(spcl.SpectralIntensity(fov_integrate(three, rot), obs.spectral_grid, units=obs_units))
         for q, par in enumerate(pars):
-            par.store_deriv(spcl.SpectralIntensity(fov_integrate(ders[q], rot), obs.spectral_grid),
-                            num=k)
+            par.store_deriv(spcl.SpectralIntensity(fov_integrate(ders[q], rot), obs.spectral_grid,
+                                                   units=obs_units), num=k)
     for par in pars:
         par.hires_deriv = None
-    if isinstance(inputs, dict) and inputs.get('out_dir') and save_lowres:
-        with open(os.path.join(inputs['out_dir'], 'lowres_radtran_{}.pic'.format(nome_inv)), 'wb') as f:
-            pickle.dump([sims, radtrans_out], f, protocol=-1)
+    out_dir = inputs.get('out_dir') if isinstance(inputs, dict) else None
+    if out_dir and save_lowres:
+        with open(os.path.join(out_dir, 'lowres_radtran_{}.pic'.format(nome_inv)), 'wb') as f:
+            pickle.dump([pixels, sims, sim_LOSs, radtrans_out, dict()], f, protocol=-1)
     return sims, radtrans_out, derivs
+
+
+# ---------------------------------------------------------------------------------------------
+# the update step of the retrieval (smm:3399-3469): tiny dense algebra on the host, kept so that
+# inversion_fast_limb runs like the reference's; not part of the GPU hot path
+# ---------------------------------------------------------------------------------------------
+def genvec(obs, sims, noise, masks=None):
+    """Concatenated observation / simulation / noise vectors of all pixels (smm:3399-3425)."""
+    cat = lambda xs: np.concatenate([np.asarray(x.spectrum, dtype=float) for x in xs])   # noqa: E731
+    obs_vec, sim_vec, noi_vec = cat(obs), cat(sims), cat(noise)
+    if masks is not None:
+        keep = np.concatenate([np.asarray(m) for m in masks]).astype(bool)
+        obs_vec, sim_vec, noi_vec = obs_vec[keep], sim_vec[keep], noi_vec[keep]
+    return obs_vec, sim_vec, noi_vec
+
+
+def chicalc(obs, sims, noise, masks, n_ret):
+    """Reduced chi square (smm:3428-3433)."""
+    obs_vec, sim_vec, noi_vec = genvec(obs, sims, noise, masks=masks)
+    return np.sum(((obs_vec - sim_vec) / noi_vec) ** 2) / (len(obs_vec) - n_ret)
+
+
+def inversion_algebra(obs, sims, noise, bayes_set, lambda_LM=0.1, L1_reg=False, masks=None):
+    """Bayesian optimal estimation, one Levenberg-Marquardt step (smm:3435-3469):
+    dx = (K^T Sy^-1 K + Sa^-1 + lambda diag(.))^-1 [K^T Sy^-1 (y - F) + Sa^-1 (xa - x)]."""
+    from numpy.linalg import inv
+    jac = bayes_set.build_jacobian(masks=masks)
+    xi = bayes_set.param_vector()
+    obs_vec, sim_vec, noi_vec = genvec(obs, sims, noise, masks=masks)
+    KtSy = jac.T / noi_vec ** 2
+    G_inv = KtSy @ jac
+    Sa_inv = inv(bayes_set.VCM_apriori())
+    S_inv = G_inv + Sa_inv
+    SxLM = inv(S_inv + lambda_LM * np.diag(np.diag(S_inv)))
+    S_x = inv(S_inv)
+    deltax = SxLM @ (KtSy @ (obs_vec - sim_vec) + Sa_inv @ (bayes_set.apriori_vector() - xi))
+    bayes_set.update_params(deltax)
+    bayes_set.store_avk(S_x @ G_inv)
+    bayes_set.store_VCM(S_x)
+
+
+def inversion(inputs, planet, lines, bayes_set, pixels, wn_range=None, chi_threshold=0.01, max_it=10,
+              lambda_LM=0.1, L1_reg=False, radtran_opt=dict(), useLUTs=True, debugfile=None,
+              save_hires=False, save_lowres=True, LUTopt=dict(), test=False, g3D=False):
+    """The per-LOS retrieval of the reference (smm:2422-2595; radtran_test_CO.py:194): every pixel
+    is simulated by three LineOfSight.radtran calls (low / centre / up LOS, hi-res radiance and
+    hi-res derivative spectra each), convolved with hires_to_lowres and FOV-integrated; then chi,
+    the convergence tests and the Levenberg-Marquardt step.  The reference returns nothing; here
+    (chi, obs, sims, bayes_set) is returned for convenience.  useLUTs=False runs the line-by-line
+    path without look-up tables (LineOfSight.radtran)."""
+    lines = check_lines_mols(lines, planet.gases.values())
+    sp_gri = _spectral_grid_of(pixels, wn_range, None)
+    wn_range = [sp_gri.grid[0], sp_gri.grid[-1]]
+    for gas in bayes_set.sets.keys():
+        if gas in planet.gases:
+            planet.gases[gas].add_clim(bayes_set.sets[gas].profile())
+    LUTS = None
+    if useLUTs:
+        gases = list(planet.gases.values())
+        PT = calc_PT_couples_atmosphere(lines, gases, planet.atmosphere, **LUTopt)
+        LUTS = check_and_build_allluts(inputs, sp_gri, lines, gases, PTcouples=PT, LUTopt=LUTopt)
+    obs = [pix.observation for pix in pixels]
+    masks = [pix.observation.mask for pix in pixels]
+    noise = [pix.observation.noise for pix in pixels]
+    out_dir = inputs.get('out_dir') if isinstance(inputs, dict) else None
+    sims = [None] * len(pixels)
+    chi_old = chi = None
+    for num_it in range(max_it):
+        hires = []
+        for num, pix in enumerate(pixels):
+            ssp = pix.sub_solar_point() if g3D else None
+            widths = pix.observation.bands.spectrum
+            three, ders = [], []
+            for linea in (pix.low_LOS(), pix.LOS(), pix.up_LOS()):
+                res = linea.radtran(wn_range, planet, lines, cartLUTs=inputs.get('cart_LUTS'),
+                                    cartDROP=out_dir, calc_derivatives=True, bayes_set=bayes_set,
+                                    LUTS=LUTS, useLUTs=useLUTs, radtran_opt=radtran_opt, g3D=g3D,
+                                    sub_solar_point=ssp, sp_grid=sp_gri)
+                three.append(res[0].hires_to_lowres(pix.observation, spectral_widths=widths))
+                row = []
+                for par in bayes_set.params():
+                    if par.not_involved or par.hires_deriv is None:
+                        row.append(pix.observation * 0.0)
+                    else:
+                        row.append(par.hires_deriv.hires_to_lowres(pix.observation, spectral_widths=widths))
+                ders.append(row)
+                if linea is not None and len(three) == 2:
+                    hires.append([num, pix.limb_tg_alt, res])
+            sims[num] = FOV_integr_1D(three, pix.pixel_rot)
+            for q, par in enumerate(bayes_set.params()):
+                par.store_deriv(FOV_integr_1D([d[q] for d in ders], pix.pixel_rot), num=num)
+        if save_hires and out_dir:
+            with open(os.path.join(out_dir, 'hires_radtran.pic'), 'wb') as f:
+                for h in hires:
+                    pickle.dump(h, f, protocol=-1)
+        chi = chicalc(obs, sims, noise, masks, bayes_set.n_tot)
+        if chi_old is not None and (abs(chi - chi_old) / chi_old < chi_threshold or chi > chi_old):
+            return chi, obs, sims, bayes_set
+        chi_old = chi
+        inversion_algebra(obs, sims, noise, bayes_set, lambda_LM=lambda_LM, L1_reg=L1_reg, masks=masks)
+        for par in bayes_set.params():
+            par.hires_deriv = None
+        if debugfile is not None:
+            pickle.dump([num_it, obs, sims, bayes_set], debugfile)
+        for gas in bayes_set.sets.keys():
+            if gas in planet.gases:
+                planet.gases[gas].add_clim(bayes_set.sets[gas].profile())
+    return chi, obs, sims, bayes_set
+
+
+def inversion_fast_limb(inputs, planet, lines, bayes_set, pixels, wn_range=None, sp_gri=None,
+                        chi_threshold=0.01, max_it=10, lambda_LM=0.1, L1_reg=False,
+                        radtran_opt=dict(), debugfile=None, save_hires=False, save_lowres=True,
+                        LUTopt=dict(), test=False, use_tangent_sza=False, group_observations=False,
+                        nome_inv='1', solo_simulation=False, invert_LOS_direction=False,
+                        alt_step_sims=50., alt_first_los=None, track_levels=None, check_log=None,
+                        g3D=None):
+    """The fast limb retrieval (smm:2598-2987): up to max_it iterations of forward model +
+    analytic Jacobians on the GPU (forward_jacobian_limb), reduced chi square, convergence tests
+    (relative change below chi_threshold, or chi rising) and the Levenberg-Marquardt update
+    (inversion_algebra); the retrieved VMR profiles are installed on the planet after every step.
+    Returns (chi, obs, sims, bayes_set) like the reference; None after one simulation with
+    solo_simulation (:2903-2905) or when max_it iterations did not converge (:2987).  The LUTs
+    are built once and reused by every iteration.  save_hires is not supported here (the
+    derivative spectra of a batch exist on the device per LOS block only): it raises."""
+    if save_hires:
+        raise NotImplementedError('inversion_fast_limb(save_hires=True): hi-res radiances and '
+                                  'derivatives are reduced to the channels on the device; use '
+                                  'radtrans(save_hires=True) or LineOfSight.radtran_fast')
+    if track_levels is not None:
+        raise NotImplementedError('inversion_fast_limb(track_levels=...): per-level contributions '
+                                  'are available from radtrans(track_levels=...)')
+    lines = check_lines_mols(lines, planet.gases.values())
+    pixels = sorted(pixels, key=lambda p: p.limb_tg_alt)
+    sp_gri = _spectral_grid_of(pixels, wn_range, sp_gri)
+    obs = [pix.observation for pix in pixels]
+    masks = [pix.observation.mask for pix in pixels]
+    noise = [pix.observation.noise for pix in pixels]
+    for gas in bayes_set.sets.keys():
+        if gas in planet.gases:
+            planet.gases[gas].add_clim(bayes_set.sets[gas].profile())
+    sim_LOSs = _simulated_los(pixels, group_observations, alt_step_sims, alt_first_los)[0]
+    LUTS = _luts_for(inputs, planet, lines, pixels, sim_LOSs, sp_gri, LUTopt)
+    chi_old = None
+    for num_it in range(max_it):
+        sims, radtrans_out, derivs = forward_jacobian_limb(
+            inputs, planet, lines, bayes_set, pixels, sp_gri=sp_gri, radtran_opt=radtran_opt,
+            save_lowres=save_lowres, use_tangent_sza=use_tangent_sza,
+            group_observations=group_observations, nome_inv=nome_inv,
+            invert_LOS_direction=invert_LOS_direction, alt_step_sims=alt_step_sims,
+            alt_first_los=alt_first_los, LUTS=LUTS)
+        if solo_simulation:
+            return None
+        chi = chicalc(obs, sims, noise, masks, bayes_set.n_used_par())
+        if debugfile is not None:
+            pickle.dump([num_it, chi, obs, sims, bayes_set, radtrans_out, derivs], debugfile)
+        if check_log is not None:
+            check_log.write('Iteration {:2d}: chi is {:8.3f}\n'.format(num_it, chi))
+        if chi_old is not None:
+            if abs(chi - chi_old) / chi_old < chi_threshold:
+                if check_log is not None:
+                    check_log.write('Finished!\n')
+                return chi, obs, sims, bayes_set
+            if chi > chi_old:
+                if check_log is not None:
+                    check_log.write('Chi has raised.. Finished!\n')
+                return chi, obs, sims, bayes_set
+        chi_old = chi
+        inversion_algebra(obs, sims, noise, bayes_set, lambda_LM=lambda_LM, L1_reg=L1_reg, masks=masks)
+        if check_log is not None:
+            check_log.write(('Params: ' + len(bayes_set.params()) * '{:9.2e} ' + '\n').format(
+                *[par.value for par in bayes_set.params()]))
+        for gas in bayes_set.sets.keys():
+            if gas in planet.gases:
+                planet.gases[gas].add_clim(bayes_set.sets[gas].profile())
+    return None

@@ -265,9 +265,21 @@ def spect_lines(tab, mol=6, iso=1):
     return out
 
 
-def titan_planet(level_energies=None, n_bands=1, vmr=0.015, nonlte=True, sza_deg=60.0):
+SZA_NODES = np.array([0.0, 30.0, 50.0, 65.0, 80.0, 95.0])   # nodes of the 3-D T_vib tables (deg)
+
+
+def vib_temperatures_3d(z_km, temp_bands, level_energies, sza_nodes=SZA_NODES):
+    """[n_lev][n_band][n_sza][n_z] vibrational temperatures T_vib(lat band, SZA, z): the shape of
+    the reference's 3-D profiles (radtran_3D_ch4.py:249-250)."""
+    return np.stack([np.stack([vib_temperatures(z_km, t, level_energies, sz) for sz in sza_nodes],
+                              axis=1) for t in np.atleast_2d(temp_bands)], axis=1)
+
+
+def titan_planet(level_energies=None, n_bands=1, vmr=0.015, nonlte=True, sza_deg=60.0,
+                 sza_nodes=None):
     """sbm.Titan with the synthetic atmosphere, CH4 (iso 1) and, when nonlte, one vibrational
-    level per entry of level_energies carrying a vibrational-temperature profile."""
+    level per entry of level_energies carrying a vibrational-temperature profile - on
+    ('alt'), ('lat', 'alt') or, with sza_nodes, on ('lat', 'sza', 'alt') / ('sza', 'alt')."""
     from . import spect_base_module as sbm
     atm = titan_atmosphere(n_bands=max(n_bands, 1))
     planet = sbm.Titan(1500.0)
@@ -287,7 +299,15 @@ def titan_planet(level_energies=None, n_bands=1, vmr=0.015, nonlte=True, sza_deg
         tv = [vib_temperatures(atm["z"], atm["temp"][b], level_energies, sza_deg)
               for b in range(max(n_bands, 1))]
         profs = []
+        if sza_nodes is not None:
+            tv3 = vib_temperatures_3d(atm["z"], atm["temp"][:max(n_bands, 1)], level_energies, sza_nodes)
+            g3 = (sbm.AtmGrid(['sza', 'alt'], [sza_nodes, atm["z"]]) if n_bands <= 1 else
+                  sbm.AtmGrid(['lat', 'sza', 'alt'], [atm["lat_edges"], sza_nodes, atm["z"]]))
         for i in range(len(level_energies)):
+            if sza_nodes is not None:
+                v = tv3[i][0] if n_bands <= 1 else tv3[i]
+                profs.append(sbm.AtmProfile(g3, v, 'vibtemp', 'lin') if nonlte else None)
+                continue
             v = tv[0][i] if n_bands <= 1 else np.stack([t[i] for t in tv])
             profs.append(sbm.AtmProfile(grid, v, 'vibtemp', 'lin') if nonlte else None)
         im.add_levels(level_strings(len(level_energies)), level_energies, vibtemps=profs)
@@ -297,22 +317,30 @@ def titan_planet(level_energies=None, n_bands=1, vmr=0.015, nonlte=True, sza_deg
 
 
 def vims_pixels(tangent_km, lat=10.0, lon=0.0, dist=1.e5, channels=None, widths=None,
-                units='cm_1'):
+                units='cm_1', sza=60.0, obs_units='ergscm2'):
     """sbm.VIMSPixel list looking at the limb at the given tangent altitudes, with an (empty)
-    observation that defines the instrument channels."""
+    observation that defines the instrument channels.  sza (scalar or one per pixel): solar zenith
+    angle at the tangent point; the sub-solar point is placed on the tangent point's parallel."""
     from . import spect_base_module as sbm
     from . import spect_classes as spcl
     out = []
-    for ht in tangent_km:
+    szas = np.broadcast_to(np.asarray(sza, dtype=float), (len(tangent_km),))
+    for ht, sz in zip(tangent_km, szas):
         obs = None
         if channels is not None:
-            obs = spcl.SpectralIntensity(np.zeros(len(channels)), spcl.SpectralGrid(channels, units=units))
+            obs = spcl.SpectralIntensity(np.zeros(len(channels)), spcl.SpectralGrid(channels, units=units),
+                                         units=obs_units)
             obs.bands = spcl.SpectralObject(np.asarray(widths, dtype=float), obs.spectral_grid)
             obs.mask = np.ones(len(channels))
             obs.noise = None
         keys = ['sub_obs_lat', 'sub_obs_lon', 'dist', 'limb_tg_lat', 'limb_tg_lon', 'limb_tg_alt',
                 'limb_tg_sza', 'sub_solar_lat', 'sub_solar_lon', 'observation', 'pixel_rot']
         # observer on the equatorial plane 90 deg away in longitude: the ray grazes the limb
-        vals = [lat, lon + 90.0, dist, lat, lon, float(ht), 60.0, 0.0, lon - 60.0, obs, 0.0]
+        # sub-solar point on the same meridian plane offset in longitude so that the angle between
+        # the tangent point and the Sun is `sz`: cos(sz) = sin(lat)sin(ls) + cos(lat)cos(ls)cos(dlon)
+        # with ls = 0 -> cos(dlon) = cos(sz)/cos(lat)
+        cl = mt.cos(mt.radians(lat))
+        dlon = mt.degrees(mt.acos(max(-1.0, min(1.0, mt.cos(mt.radians(float(sz))) / cl))))
+        vals = [lat, lon + 90.0, dist, lat, lon, float(ht), float(sz), 0.0, lon - dlon, obs, 0.0]
         out.append(sbm.VIMSPixel(keys, vals))
     return out

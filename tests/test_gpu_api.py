@@ -184,7 +184,7 @@ def test_inversion_fast_limb_forward_and_jacobian(world):
 
     def run(bset):
         pixels = S.vims_pixels([450.0, 700.0], channels=centres, widths=widths)
-        return smm.inversion_fast_limb(inputs, planet, world["lines"], bset, pixels, sp_gri=sp,
+        return smm.forward_jacobian_limb(inputs, planet, world["lines"], bset, pixels, sp_gri=sp,
                                        radtran_opt=opt, LUTopt=dict(LUTopt))
 
     sims, rt, derivs = run(bs)
@@ -383,9 +383,9 @@ def test_inversion_fast_limb_group_observations(world):
     opt = dict(max_T_variation=5., max_Plog_variation=1.)
     mk = lambda: S.vims_pixels([470.0, 650.0], channels=centres, widths=widths)   # noqa: E731
     bs_a, bs_b = _bayes(smm, planet), _bayes(smm, planet)
-    sims_a, _, _ = smm.inversion_fast_limb(inputs, planet, world["lines"], bs_a, mk(), sp_gri=sp,
+    sims_a, _, _ = smm.forward_jacobian_limb(inputs, planet, world["lines"], bs_a, mk(), sp_gri=sp,
                                            radtran_opt=opt, LUTopt=dict(LUTopt))
-    sims_b, rt_b, _ = smm.inversion_fast_limb(inputs, planet, world["lines"], bs_b, mk(), sp_gri=sp,
+    sims_b, rt_b, _ = smm.forward_jacobian_limb(inputs, planet, world["lines"], bs_b, mk(), sp_gri=sp,
                                               radtran_opt=opt, LUTopt=dict(LUTopt),
                                               group_observations=True, alt_step_sims=12.)
     assert len(rt_b) > 15
