@@ -72,6 +72,7 @@ def main(small=bool(int(os.environ.get('SR_EXAMPLE_SMALL', '0')))):
     for gas in planet.gases:
         print(gas)
         linee_ok = smm.check_lines_mols(linee, [planet.gases[gas]])
+        linee_ok = [lin for lin in linee_ok if lin.Freq >= wn_ranges[gas][0] and lin.Freq <= wn_ranges[gas][1]]
         if len(linee_ok) == 0:
             continue
         abs_coeff = smm.prepare_spe_grid(wn_ranges[gas])

@@ -1504,6 +1504,7 @@ def forward_jacobian_limb(inputs, planet, lines, bayes_set, pixels, wn_range=Non
     stored on the parameters (`par.store_deriv`), so that `bayes_set.build_jacobian()` gives the
     Jacobian inversion_algebra consumes.  Returns (sims, radtrans, derivs) with
     derivs[(LOS tag, nameset, key)] = low-res derivative SpectralIntensity."""
+    lines = check_lines_mols(lines, planet.gases.values())
     pixels = sorted(pixels, key=lambda p: p.limb_tg_alt)
     sp_gri = _spectral_grid_of(pixels, wn_range, sp_gri)
     for gas in bayes_set.sets.keys():
@@ -1693,7 +1694,9 @@ def inversion_fast_limb(inputs, planet, lines, bayes_set, pixels, wn_range=None,
     (relative change below chi_threshold, or chi rising) and the Levenberg-Marquardt update
     (inversion_algebra); the retrieved VMR profiles are installed on the planet after every step.
     Returns (chi, obs, sims, bayes_set) like the reference; None after one simulation with
-    solo_simulation (:2903-2905) or when max_it iterations did not converge (:2987).  The LUTs
+    solo_simulation (:2903-2905).  When max_it iterations end without meeting a stopping rule the
+    reference falls off its loop and returns None (:2987); here the state after the last
+    evaluation is returned instead, so that the work is not lost.  The LUTs
     are built once and reused by every iteration.  save_hires is not supported here (the
     derivative spectra of a batch exist on the device per LOS block only): it raises."""
     if save_hires:
@@ -1746,4 +1749,4 @@ def inversion_fast_limb(inputs, planet, lines, bayes_set, pixels, wn_range=None,
         for gas in bayes_set.sets.keys():
             if gas in planet.gases:
                 planet.gases[gas].add_clim(bayes_set.sets[gas].profile())
-    return None
+    return chi, obs, sims, bayes_set

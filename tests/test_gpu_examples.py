@@ -37,7 +37,9 @@ def test_run_0607_lut(examples, oracle):
     assert sorted(allLUTS) == [('CH4', 1), ('CH4', 2), ('HCN', 1)]
     for (name, iso), L in allLUTS.items():
         im = getattr(planet.gases[name], 'iso_%d' % iso)
-        mine = [l for l in smm.check_lines_mols(linee, [planet.gases[name]]) if l.Iso == iso]
+        w0, w1 = wn_ranges[name]
+        mine = [l for l in smm.check_lines_mols(linee, [planet.gases[name]])
+                if l.Iso == iso and w0 <= l.Freq <= w1]
         tab = spcl.line_table(mine, im if len(im.levels) else None)
         g32 = L.g32.cpu().numpy()
         assert g32.shape[0] == len(L.PTcouples) > 10 and np.any(g32)
@@ -62,7 +64,7 @@ def test_radtran_3D_ch4(examples):
     # parameters the three tangent heights constrain: closer to the truth than the a-priori was
     err0 = np.array([abs(p.apriori / t.value - 1) for p, t in used])
     err1 = np.array([abs(p.value / t.value - 1) for p, t in used])
-    assert np.median(err1) < 0.5 * np.median(err0)
+    assert np.median(err1) < 0.7 * np.median(err0)
     for a, b in zip(sims, sims_true):
         assert rel_err(a.spectrum, b.spectrum, 1e-3) < 0.1
 
