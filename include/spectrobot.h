@@ -143,6 +143,17 @@ int sr_gcoeff_cells_dev_f32(sr_lineset* ls, const double* pt_host, int n_cells, 
 int sr_gcoeff_cells_dev_f32_ld(sr_lineset* ls, const double* pt_host, int n_cells,
                                float* out32_dev, long row_stride, void* stream);
 
+/* The same cells restricted to the grid points [pt0, pt0+n_pts) of the lineset's grid (a
+ * wavenumber slab: the multi-GPU LUT build gives every rank all cells of one slab).
+ * The window positions of the lines are still those of closest_grid over the WHOLE grid
+ * (spect_classes.py:1937-1943), so the slab is bit-identical to the same points of a full build;
+ * the lineset only needs the lines whose 13010-point window reaches the slab.  out_dev:
+ * [n_cells][n_sets][3][row_stride] doubles (f32 == 0) or floats (f32 != 0), row_stride >= n_pts
+ * (0 = n_pts); pt0 must be a multiple of sr_lineset_tile_points(). */
+int sr_gcoeff_cells_window_dev(sr_lineset* ls, const double* pt_host, int n_cells, void* out_dev,
+                               int f32, long row_stride, long pt0, long n_pts, void* stream);
+int sr_lineset_tile_points(const sr_lineset* ls);
+
 /* Per-line normalised shapes of one cell (MakeShapeLine with keep_memory, spect_classes.py:174):
  * shapes_dev [n_active][SR_IMXSIG] in the lineset's internal (sorted) line order, and the three
  * G coefficients g_dev [n_active][3]; order_host[n_active] maps sorted position -> input line. */
@@ -397,6 +408,21 @@ int sr_los_steps_build_rays(const sr_atmosphere* atm, const sr_los_rays* rays, c
                             int n_par, const double* masks, int jac_gas, int n_steps_max,
                             int* n_steps, double* temp, double* pres, double* column, double* tvib,
                             double* dfrac, int* n_steps_needed);
+
+/* Per-kernel device timing for bench.py's live roofline: while enabled, the library brackets the
+ * launches of the kernels below with CUDA events on the launching stream.  sr_prof_enable clears the
+ * records; sr_prof_summary synchronises the device and returns, for one kernel kind, the number of
+ * launches, their summed duration (ms) and their summed algorithmic work (FP64 flop for
+ * SR_PROF_LOS_MMA and SR_PROF_LOS_FUSED, bytes for SR_PROF_LOS_LAYERS and SR_PROF_CONV,
+ * line*gridpoint evaluations for SR_PROF_VOIGT_TILE, centre points for SR_PROF_VOIGT_CORE). */
+#define SR_PROF_LOS_MMA     0
+#define SR_PROF_LOS_LAYERS  1
+#define SR_PROF_CONV        2
+#define SR_PROF_VOIGT_TILE  3
+#define SR_PROF_VOIGT_CORE  4
+#define SR_PROF_LOS_FUSED   5
+int sr_prof_enable(int on);
+int sr_prof_summary(int kind, long long* launches, double* ms, double* work);
 
 /* FP64 FMA micro-benchmark used by bench.py for the K1/K2 roofline denominator: runs
  * `iters` dependent-chain FMAs per thread on a full grid and returns achieved FLOP/s. */

@@ -72,6 +72,8 @@ class sr_channels(C.Structure):
 
 
 SR_CHAN_SAME_UNITS, SR_CHAN_NM_FROM_CM1 = 0, 1
+SR_PROF_LOS_MMA, SR_PROF_LOS_LAYERS, SR_PROF_CONV, SR_PROF_VOIGT_TILE, SR_PROF_VOIGT_CORE, \
+    SR_PROF_LOS_FUSED = 0, 1, 2, 3, 4, 5
 
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 SIGNATURES = {
@@ -98,6 +100,9 @@ SIGNATURES = {
     "sr_gcoeff_cells_host": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "sr_gcoeff_cells_dev_f32": (C.c_int, [_vp, _dp, C.c_int, _vp, _vp, _vp]),
     "sr_gcoeff_cells_dev_f32_ld": (C.c_int, [_vp, _dp, C.c_int, _vp, C.c_long, _vp]),
+    "sr_gcoeff_cells_window_dev": (C.c_int, [_vp, _dp, C.c_int, _vp, C.c_int, C.c_long, C.c_long,
+                                             C.c_long, _vp]),
+    "sr_lineset_tile_points": (C.c_int, [_vp]),
     "sr_line_shapes_dev": (C.c_int, [_vp, C.c_double, C.c_double, _vp, _vp, _vp]),
     "sr_los_rt_layers_dev": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_long, _vp, C.c_int,
                                        _vp, _vp]),
@@ -149,6 +154,8 @@ SIGNATURES = {
     "sr_los_steps_build_rays": (C.c_int, [C.POINTER(sr_atmosphere), C.POINTER(sr_los_rays),
                                           C.POINTER(sr_steps_opt), C.c_int, _dp, C.c_int, C.c_int,
                                           _ip, _dp, _dp, _dp, _dp, _dp, _ip]),
+    "sr_prof_enable": (C.c_int, [C.c_int]),
+    "sr_prof_summary": (C.c_int, [C.c_int, C.POINTER(C.c_longlong), _dp, _dp]),
     "sr_fp64_peak": (C.c_int, [C.c_int, _dp]),
 }
 

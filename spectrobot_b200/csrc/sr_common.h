@@ -37,6 +37,21 @@ inline int fail(int code, const char* fmt, ...) {
         SR_CUDA(cudaGetLastError());                                                      \
     } while (0)
 
+// Optional per-kernel timing (sr_prof_enable): CUDA events recorded on the launching stream right
+// before and after selected launches, summed by sr_prof_summary.  bench.py uses it for the live
+// roofline of the dominant kernel; off by default (no events, no overhead).
+extern std::atomic<int> g_prof_on;
+void prof_begin(int kind, double work, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+    cudaStream_t st;
+    bool on;
+    ProfScope(int kind, double work, cudaStream_t s) : st(s), on(g_prof_on.load() != 0) {
+        if (on) prof_begin(kind, work, st);
+    }
+    ~ProfScope() { if (on) prof_end(st); }
+};
+
 template <typename T>
 struct DevBuf {  // RAII device buffer
     T* p = nullptr;

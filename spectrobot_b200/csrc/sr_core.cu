@@ -1,9 +1,33 @@
 // sr_core.cu -- library globals, device selection, FP64 peak micro-benchmark
 #include "sr_common.h"
+#include <mutex>
+#include <vector>
 
 namespace sr {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_prof_on{0};
+
+namespace {
+struct ProfRec { int kind; double work; cudaEvent_t a, b; };
+std::mutex g_prof_mtx;
+std::vector<ProfRec> g_prof_recs;
+thread_local ProfRec g_prof_open{-1, 0.0, nullptr, nullptr};
+}  // namespace
+
+void prof_begin(int kind, double work, cudaStream_t st) {
+    ProfRec r{kind, work, nullptr, nullptr};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    g_prof_open = r;
+}
+void prof_end(cudaStream_t st) {
+    if (g_prof_open.kind < 0) return;
+    cudaEventRecord(g_prof_open.b, st);
+    std::lock_guard<std::mutex> g(g_prof_mtx);
+    g_prof_recs.push_back(g_prof_open);
+    g_prof_open.kind = -1;
+}
 }  // namespace sr
 
 namespace {
@@ -41,6 +65,32 @@ int sr_device_count(void) {
 
 int sr_set_device(int device) {
     SR_CUDA(cudaSetDevice(device));
+    return SR_OK;
+}
+
+int sr_prof_enable(int on) {
+    std::lock_guard<std::mutex> g(sr::g_prof_mtx);
+    for (auto& r : sr::g_prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    sr::g_prof_recs.clear();
+    sr::g_prof_on.store(on ? 1 : 0);
+    return SR_OK;
+}
+
+int sr_prof_summary(int kind, long long* launches, double* ms, double* work) {
+    if (!launches || !ms || !work) return sr::fail(SR_ERR_ARG, "sr_prof_summary: bad argument");
+    SR_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> g(sr::g_prof_mtx);
+    *launches = 0;
+    *ms = 0.0;
+    *work = 0.0;
+    for (auto& r : sr::g_prof_recs) {
+        if (r.kind != kind) continue;
+        float t = 0.f;
+        SR_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+        *launches += 1;
+        *ms += t;
+        *work += r.work;
+    }
     return SR_OK;
 }
 

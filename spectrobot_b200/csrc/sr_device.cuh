@@ -250,6 +250,58 @@ __device__ __forceinline__ void exp_pair(double x, double& ex, double& em) {
     em = (ni == 0) ? p : fma(s, p, s - 1.0);
 }
 
+// exp(-t) and phi(t) = (1 - e^{-t})/t (1 at t = 0) of the layer update with the emission given as J
+// (I <- I e^{-t} + J phi(t)), in ~18 FP64 instructions on the common path
+// (|t| < ln2/2) instead of exp_pair + an IEEE division:
+//   x = -t = n ln2 + r (round-to-nearest by the 1.5*2^52 trick, no FRND/F2I on the XU pipe),
+//   g(r) = expm1(r)/r = sum_k r^k/(k+1)!  (degree 13, |err| < 2e-17 for |r| <= ln2/2),
+//   e^x = 2^n (1 + r g);   phi = expm1(x)/x = g when n = 0, else (e^x - 1)/x with the quotient
+//   from MUFU.RCP64H + two Newton steps (no cancellation: |x| >= ln2/2 there).
+// Relative error of both results <= 4e-16 (checked against 60-digit arithmetic).
+__device__ __forceinline__ void exp_phi(double t, double& ex, double& phi) {
+    const double x = -t;
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
+    const double z = fma(x, 1.4426950408889634, MAGIC);
+    const int ni = __double2loint(z);                        // n as an integer
+    const double n = z - MAGIC;
+    if (!(n > -1000.0 && n < 1000.0)) {                      // |t| > ~693 or NaN: library path
+        ex = exp(x);
+        phi = (t == 0.0) ? 1.0 : -expm1(x) / t;
+        return;
+    }
+    double r = fma(n, -6.93147180369123816490e-01, x);       // ln2 hi
+    r = fma(n, -1.90821492927058770002e-10, r);              // ln2 lo
+    double g = 1.0 / 87178291200.0;                          // 1/14!
+    g = fma(g, r, 1.0 / 6227020800.0);
+    g = fma(g, r, 1.0 / 479001600.0);
+    g = fma(g, r, 1.0 / 39916800.0);
+    g = fma(g, r, 1.0 / 3628800.0);
+    g = fma(g, r, 1.0 / 362880.0);
+    g = fma(g, r, 1.0 / 40320.0);
+    g = fma(g, r, 1.0 / 5040.0);
+    g = fma(g, r, 1.0 / 720.0);
+    g = fma(g, r, 1.0 / 120.0);
+    g = fma(g, r, 1.0 / 24.0);
+    g = fma(g, r, 1.0 / 6.0);
+    g = fma(g, r, 0.5);
+    g = fma(g, r, 1.0);                                      // expm1(r)/r
+    ex = fma(r, g, 1.0);                                     // e^r
+    phi = g;
+    if (ni != 0) {
+        const double s = __hiloint2double((ni + 1023) << 20, 0);   // 2^n
+        ex *= s;
+        double r0 = rcp_approx(x);
+        r0 = fma(fma(-x, r0, 1.0), r0, r0);
+        r0 = fma(fma(-x, r0, 1.0), r0, r0);
+        phi = (ex - 1.0) * r0;
+    }
+}
+__device__ __forceinline__ double layer_update_j(double I, double t, double J, bool solo) {
+    double ex, phi;
+    exp_phi(t, ex, phi);
+    return solo ? I * ex : fma(I, ex, J * phi);
+}
+
 // ---------------------------------------------------------------------------------------------
 // One segment of the Curtis-Godson integrals curgod_fort_1..4 (curgods.f:2-98): number density
 // piecewise exponential, vmr (and f in variant 3) piecewise linear, nd*f exponential in variant 4.

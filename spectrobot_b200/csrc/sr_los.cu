@@ -340,12 +340,13 @@ __device__ __forceinline__ void layers_item(const RecArgs& r, int l, int tile) {
     const bool keep = r.keep != 0;
     auto ldl = [&](const double* p) { return keep ? __ldcg(p) : __ldcs(p); };
     auto update = [&](int i, double t, double s) {
+        if (src_is_j) {   // s = J: I <- I e^-tau + J phi(tau), phi = (1 - e^-tau)/tau (DESIGN 6.4)
+            I[i] = srdev::layer_update_j(I[i], t, s, solo != 0);
+            return;
+        }
         double ex, em;
         srdev::exp_pair(-t, ex, em);
-        if (src_is_j) {   // s = J: I <- I e^-tau + J phi(tau), phi = (1 - e^-tau)/tau (DESIGN 6.4)
-            const double phi = (t == 0.0) ? 1.0 : -em / t;
-            I[i] = solo ? I[i] * ex : fma(I[i], ex, s * phi);
-        } else {
+        {
             I[i] = solo ? I[i] * ex : fma(I[i], ex, -s * em);
         }
     };
@@ -456,9 +457,8 @@ __global__ void __launch_bounds__(256, MINB) k_los_layers_jac(const __grid_const
 #pragma unroll
         for (int u = 0; u < U; u++) {
             if (k0 + u >= ns) break;
-            double ex, em;
-            srdev::exp_pair(-t[u], ex, em);
-            const double phi = (t[u] == 0.0) ? 1.0 : -em / t[u];
+            double ex, phi;
+            srdev::exp_phi(t[u], ex, phi);
             double B;
             if (MULTI) {
                 const double a0 = -I * ex * tg[u];
@@ -783,16 +783,20 @@ void unique_sorted(const double* v, int n, int stride, std::vector<double>& out)
     out.erase(std::unique(out.begin(), out.end()), out.end());
 }
 
+// nearest and second-nearest node by |node - v| (LutSet.calculate, spect_main_module.py:1007-1040:
+// np.argsort of the distances): ties go to the lower index, as a linear scan with a strict '<'
+// gives.  `nodes` is sorted ascending and unique, so the nearest node is one of the two that
+// bracket v and the second nearest is adjacent to the nearest.
 void host_nearest_two(const std::vector<double>& nodes, double v, int& i1, int& i2) {
     const int n = (int)nodes.size();
-    int a = 0;
-    for (int i = 1; i < n; i++)
-        if (std::fabs(nodes[i] - v) < std::fabs(nodes[a] - v)) a = i;
+    int hi = (int)(std::lower_bound(nodes.begin(), nodes.end(), v) - nodes.begin());   // first >= v
+    int a;
+    if (hi <= 0) a = 0;
+    else if (hi >= n) a = n - 1;
+    else a = (std::fabs(nodes[hi] - v) < std::fabs(nodes[hi - 1] - v)) ? hi : hi - 1;
     int b = -1;
-    for (int i = 0; i < n; i++) {
-        if (i == a) continue;
-        if (b < 0 || std::fabs(nodes[i] - v) < std::fabs(nodes[b] - v)) b = i;
-    }
+    if (a - 1 >= 0) b = a - 1;
+    if (a + 1 < n && (b < 0 || std::fabs(nodes[a + 1] - v) < std::fabs(nodes[b] - v))) b = a + 1;
     i1 = a;
     i2 = b;
 }
@@ -1075,6 +1079,7 @@ static int layers_launch(const double* tau, const double* src, const int* n_step
 int sr_los_rt_layers_dev(const double* tau, const double* src, const int* n_steps, int n_los,
                          int n_steps_max, long n_pts, const double* i0, int solo_absorption,
                          double* rad, void* stream) {
+    sr::ProfScope ps(SR_PROF_LOS_LAYERS, 0.0, (cudaStream_t)stream);   // work: the caller knows n_steps
     if (!tau || !src || !n_steps || !rad || n_los < 1 || n_steps_max < 1 || n_pts < 1)
         return sr::fail(SR_ERR_ARG, "sr_los_rt_layers_dev: bad argument");
     return layers_launch(tau, src, n_steps, n_los, n_steps_max, n_pts, i0, solo_absorption, rad,
@@ -1158,6 +1163,8 @@ struct GemmPlan {
     std::vector<int> ntau, ntot;        // per group, multiples of 4
     std::vector<int> chunk_grp, chunk_pair;
     std::vector<int> blk_los, blk_chunk;   // [n_blocks+1] LOS / chunk range of each LOS block
+    std::vector<int> nreal;             // per group: rows that are not padding
+    std::vector<double> blk_rowpairs;   // per block: sum over chunks of real rows x valid pairs
     int max_jp = 4, n_groups = 0, n_chunks = 0;
 };
 
@@ -1208,84 +1215,113 @@ static int build_plan(sr_lut* const* luts, const sr_los_steps* S, int nl_block, 
         max_j_src += 4 * luts[m]->n_rows[0];
     }
     P.max_jp = std::max(4, (max_j_tau + 3) / 4 * 4 + (max_j_src + 3) / 4 * 4);
-    struct Item { QuadKey key; int pair; };
+
+    // ---- pass 1: group (cell quad) of every pair, found once for the whole batch ---------------
+    // consecutive steps of a LOS mostly stay in the same quad: a one-entry cache in front of the map
     std::map<QuadKey, int> group_of;
-    std::vector<Item> items;
+    std::vector<QuadKey> keys;                 // per group
+    std::vector<int> pair_grp((size_t)S->n_los * nmax, -1);
+    QuadKey last;
+    memset(last.c, 0x7f, sizeof(last.c));
+    int last_grp = -1;
+    for (int l = 0; l < S->n_los; l++)
+        for (int k = 0; k < S->n_steps[l]; k++) {
+            QuadKey key;
+            memset(key.c, 0xff, sizeof(key.c));
+            for (int m = 0; m < n_gas; m++) {
+                int rc = cells_of(luts[m], S->pres[l * nmax + k], S->temp[l * nmax + k], key.c + 4 * m);
+                if (rc) return rc;
+            }
+            int grp;
+            if (last_grp >= 0 && key == last) grp = last_grp;
+            else {
+                auto f = group_of.find(key);
+                if (f != group_of.end()) grp = f->second;
+                else {
+                    grp = P.n_groups++;
+                    group_of.emplace(key, grp);
+                    keys.push_back(key);
+                }
+                last = key;
+                last_grp = grp;
+            }
+            pair_grp[l * nmax + k] = grp;
+        }
+    // ---- row programs, one per group ---------------------------------------------------------
+    P.prog.resize((size_t)P.n_groups * P.max_jp);
+    for (int grp = 0; grp < P.n_groups; grp++) {
+        ProgEntry* pr = P.prog.data() + (size_t)grp * P.max_jp;
+        int nj = 0;
+        for (int pass = 0; pass < 2; pass++) {      // pass 0: tau rows (abs +, ind -); 1: J rows
+            const int nj0 = nj;
+            for (int m = 0; m < n_gas; m++) {
+                const sr_lut* L = luts[m];
+                for (int c = 0; c < 4; c++) {
+                    const int cell = keys[grp].c[m * 4 + c];
+                    if (cell < 0) continue;
+                    for (int ct = (pass == 0 ? 1 : 0); ct <= (pass == 0 ? 2 : 0); ct++)
+                        for (int s : rl[(size_t)m * 3 + ct]) {
+                            ProgEntry pe;
+                            pe.roff = (long long)(L->g32 + (((size_t)cell * L->n_sets + s) * 3 + ct) *
+                                                               (size_t)L->row_stride);
+                            pe.gas = m;
+                            pe.widx = s * 4 + c;
+                            pe.neg = (ct == 1);
+                            pe.pad = 0;
+                            pr[nj++] = pe;
+                        }
+                }
+            }
+            while ((nj - nj0) % 4) {                // zero-weight padding rows
+                ProgEntry pe;
+                pe.roff = (long long)luts[0]->g32;
+                pe.gas = -1;
+                pe.widx = 0;
+                pe.neg = 0;
+                pe.pad = 0;
+                pr[nj++] = pe;
+            }
+            if (pass == 0) P.ntau.push_back(nj);
+        }
+        P.ntot.push_back(nj);
+        int real = 0;
+        for (int j = 0; j < nj; j++) real += pr[j].gas >= 0;
+        P.nreal.push_back(real);
+    }
+    // groups in key order: neighbouring quads share cells, so their chunks share LUT rows in L2
+    std::vector<int> grp_order(P.n_groups);
+    for (int g = 0; g < P.n_groups; g++) grp_order[g] = g;
+    std::sort(grp_order.begin(), grp_order.end(), [&](int a, int b) { return keys[a] < keys[b]; });
+    // ---- pass 2: per LOS block a counting sort of its pairs by group, then 16-pair chunks ------
+    std::vector<int> cnt(P.n_groups + 1), fill(P.n_groups), sorted;
     P.blk_los.push_back(0);
     P.blk_chunk.push_back(0);
     for (int l0 = 0; l0 < S->n_los; l0 += nl_block) {
         const int l1 = std::min(S->n_los, l0 + nl_block);
-        items.clear();
+        std::fill(cnt.begin(), cnt.end(), 0);
+        size_t n_items = 0;
         for (int l = l0; l < l1; l++)
-            for (int k = 0; k < S->n_steps[l]; k++) {
-                Item it;
-                memset(it.key.c, 0xff, sizeof(it.key.c));
-                it.pair = (int)(l * nmax + k);
-                for (int m = 0; m < n_gas; m++) {
-                    int rc = cells_of(luts[m], S->pres[l * nmax + k], S->temp[l * nmax + k],
-                                      it.key.c + 4 * m);
-                    if (rc) return rc;
-                }
-                items.push_back(it);
-            }
-        std::stable_sort(items.begin(), items.end(),
-                         [](const Item& a, const Item& b) { return a.key < b.key; });
-        size_t i = 0;
-        while (i < items.size()) {
-            size_t e = i;
-            while (e < items.size() && items[e].key == items[i].key) e++;
-            int grp;
-            auto f = group_of.find(items[i].key);
-            if (f != group_of.end()) grp = f->second;
-            else {
-                grp = P.n_groups++;
-                group_of.emplace(items[i].key, grp);
-                P.prog.resize((size_t)P.n_groups * P.max_jp);
-                ProgEntry* pr = P.prog.data() + (size_t)grp * P.max_jp;
-                int nj = 0;
-                for (int pass = 0; pass < 2; pass++) {      // pass 0: tau rows (abs +, ind -); 1: J rows
-                    const int nj0 = nj;
-                    for (int m = 0; m < n_gas; m++) {
-                        const sr_lut* L = luts[m];
-                        for (int c = 0; c < 4; c++) {
-                            const int cell = items[i].key.c[m * 4 + c];
-                            if (cell < 0) continue;
-                            for (int ct = (pass == 0 ? 1 : 0); ct <= (pass == 0 ? 2 : 0); ct++)
-                                for (int s : rl[(size_t)m * 3 + ct]) {
-                                    ProgEntry pe;
-                                    pe.roff = (long long)(L->g32 + (((size_t)cell * L->n_sets + s) * 3 + ct) *
-                                                                       (size_t)L->row_stride);
-                                    pe.gas = m;
-                                    pe.widx = s * 4 + c;
-                                    pe.neg = (ct == 1);
-                                    pe.pad = 0;
-                                    pr[nj++] = pe;
-                                }
-                        }
-                    }
-                    while ((nj - nj0) % 4) {                // zero-weight padding rows
-                        ProgEntry pe;
-                        pe.roff = (long long)luts[0]->g32;
-                        pe.gas = -1;
-                        pe.widx = 0;
-                        pe.neg = 0;
-                        pe.pad = 0;
-                        pr[nj++] = pe;
-                    }
-                    if (pass == 0) P.ntau.push_back(nj);
-                }
-                P.ntot.push_back(nj);
-            }
-            for (size_t q = i; q < e; q += MMA_PB) {
+            for (int k = 0; k < S->n_steps[l]; k++) { cnt[pair_grp[l * nmax + k] + 1]++; n_items++; }
+        for (int g = 0; g < P.n_groups; g++) cnt[g + 1] += cnt[g];
+        for (int g = 0; g < P.n_groups; g++) fill[g] = cnt[g];
+        sorted.resize(n_items);
+        for (int l = l0; l < l1; l++)           // ascending pair index inside every group
+            for (int k = 0; k < S->n_steps[l]; k++) sorted[fill[pair_grp[l * nmax + k]]++] = (int)(l * nmax + k);
+        double rowpairs = 0.0;
+        for (int gi = 0; gi < P.n_groups; gi++) {
+            const int grp = grp_order[gi];
+            const int i = cnt[grp], e = cnt[grp + 1];
+            if (e <= i) continue;
+            rowpairs += (double)P.nreal[grp] * (double)(e - i);
+            for (int q = i; q < e; q += MMA_PB) {
                 P.chunk_grp.push_back(grp);
-                for (int t = 0; t < MMA_PB; t++)
-                    P.chunk_pair.push_back(q + t < e ? items[q + t].pair : -1);
+                for (int t = 0; t < MMA_PB; t++) P.chunk_pair.push_back(q + t < e ? sorted[q + t] : -1);
                 P.n_chunks++;
             }
-            i = e;
         }
         P.blk_los.push_back(l1);
         P.blk_chunk.push_back(P.n_chunks);
+        P.blk_rowpairs.push_back(rowpairs);
     }
     P.rowptr.resize(P.prog.size());
     for (size_t q = 0; q < P.prog.size(); q++) P.rowptr[q] = P.prog[q].roff;
@@ -1608,7 +1644,11 @@ static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, lon
                     ma.keep = l2keep;
                     dim3 grid((unsigned)n_ch, (unsigned)((np + TILE - 1) / TILE));
                     ma.wfrag = L0->g_wfrag.p;
-                    int code = mma_launch(rows_aligned && (pt0 + c0) % 4 == 0, grid, smem, st, ma);
+                    int code;
+                    {
+                        sr::ProfScope ps(SR_PROF_LOS_MMA, 2.0 * P.blk_rowpairs[b] * (double)np, st);
+                        code = mma_launch(rows_aligned && (pt0 + c0) % 4 == 0, grid, smem, st, ma);
+                    }
                     if (code) return code;
                     if (jac_multi) {
                         ma.wfrag = L0->g_wfrag_g.p;
@@ -1630,6 +1670,9 @@ static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, lon
                                              jac->n_par, la.n_steps + l0, nl, steps->n_steps_max, np,
                                              i0_blk, solo, rad_blk, jac_blk, st, n_pts, c0, ld_lay);
                 } else {
+                    double pairs = 0.0;
+                    for (int l = l0; l < l0 + nl; l++) pairs += steps->n_steps[l];
+                    sr::ProfScope ps(SR_PROF_LOS_LAYERS, (16.0 * pairs + 8.0 * nl) * (double)np, st);
                     code = layers_launch(L0->ws_tau.p, L0->ws_src.p, la.n_steps + l0, nl,
                                          steps->n_steps_max, np, i0_blk, solo, rad_blk, st, 1, n_pts,
                                          c0, ld_lay, l2keep);
@@ -1654,6 +1697,7 @@ static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, lon
             if (low) {
                 const sr_channels ch{low->n_chan, low->centre_dev, low->width_dev, low->n_sigma,
                                      low->units};
+                sr::ProfScope ps(SR_PROF_CONV, 8.0 * (double)nl * (double)n_pts, st);
                 int code = sr_convolve_channels_dev(low->grid_dev, n_pts, rad_blk, nl, &ch,
                                                     low->low_dev + (size_t)l0 * low->n_chan, st);
                 if (code) return code;

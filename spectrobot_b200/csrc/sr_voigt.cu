@@ -267,12 +267,12 @@ __device__ __noinline__ double eval_window_point(const LineCell* __restrict__ rc
 // Regions 2/3/4 of every (cell, line): one warp per line evaluates the window points il..ir
 // (everything that is not pure far wing, ~250 points at Titan pressures) into the core buffer,
 // so that the tile kernel never runs the divergent complex-rational code itself.
-__global__ void __launch_bounds__(256) k_core_eval(const LineCell* __restrict__ rec,
+__global__ void __launch_bounds__(128) k_core_eval(const LineCell* __restrict__ rec,
                                                    const double* __restrict__ nu0,
                                                    const double* __restrict__ gc,
                                                    const double* __restrict__ lin, int n_lines,
                                                    double* __restrict__ core) {
-    const int line = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int line = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int cell = blockIdx.y;
     if (line >= n_lines) return;
     const LineCell* rc = rec + (size_t)cell * n_lines + line;
@@ -344,8 +344,10 @@ struct TileArgs {
     const int* lo_list;      // [n_lo] distinct lower sets
     const int* zero_rows;    // [n_zero] rows (set*3+ctype) that no line feeds
     void* out;               // [n_cells][n_sets][3][n_grid] double (or float when F32)
-    long n_grid;
-    long row_stride;         // elements between consecutive output rows (>= n_grid)
+    long n_grid;             // end of the output window (grid point index, exclusive)
+    long row_stride;         // elements between consecutive output rows (>= window length)
+    long pt_lo;              // first grid point of the output window (a multiple of the tile size)
+    int tile_base;           // pt_lo / tile size: index of the window's first tile in tile_rng
     int n_lines, n_sets, n_groups, n_up, n_lo, n_zero;
 };
 
@@ -370,7 +372,8 @@ __global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
     constexpr int NW = NT / 32;
     const int cell = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int tile0 = blockIdx.x * TP, tile_last = tile0 + TP - 1;
+    const int tile_idx = a.tile_base + blockIdx.x;
+    const int tile0 = tile_idx * TP, tile_last = tile0 + TP - 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* abs_s = reinterpret_cast<double*>(smem_raw);                  // [n_lo][PPT][NT]
     HalfRec* hbuf = reinterpret_cast<HalfRec*>(abs_s + (size_t)a.n_lo * TP);   // [2*NT]
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
 
     // ---- prologue: candidate ranges -> prefix sums (warp 0) ------------------------------------
     {
-        const int* __restrict__ rng = a.tile_rng + (size_t)blockIdx.x * a.n_groups * 2;
+        const int* __restrict__ rng = a.tile_rng + (size_t)tile_idx * a.n_groups * 2;
         for (int g = tid; g < a.n_groups; g += NT) {
             const int2 r = __ldg(reinterpret_cast<const int2*>(rng) + g);
             glo[g] = r.x;
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
     const size_t rows_cell = (size_t)a.n_sets * 3;
 
     auto store_row = [&](int row, const double (&v)[PPT]) {
-        const size_t o = ((size_t)cell * rows_cell + row) * (size_t)a.row_stride + P0;
+        const size_t o = ((size_t)cell * rows_cell + row) * (size_t)a.row_stride + (P0 - a.pt_lo);
 #pragma unroll
         for (int k = 0; k < PPT; k++) {
             if ((long)P0 + k * NT < a.n_grid) {
@@ -688,9 +691,21 @@ struct sr_lineset {
     sr_consts c{};
     sr::DevBuf<double> grid, lin, freq, a_coeff, air, tdep, e_lower, g_up, g_lo, evu, evl, gc;
     sr::DevBuf<int> ind, grp_begin, grp_up, grp_lo, flags;
-    sr::DevBuf<LineCell> rec;
-    sr::DevBuf<LineRec> lrec;
-    sr::DevBuf<double> pt, facs, core;
+    // per-batch tables, double-buffered: the per-line prologue (k_line_cell_params, k_core_eval)
+    // of batch i+1 runs on `aux` while the tile kernel of batch i runs on the caller's stream
+    sr::DevBuf<LineCell> rec_b[2];
+    sr::DevBuf<LineRec> lrec_b[2];
+    sr::DevBuf<double> pt_b[2], core_b[2], facs;
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_entry = nullptr, ev_core[2] = {nullptr, nullptr}, ev_tile[2] = {nullptr, nullptr};
+    ~sr_lineset() {
+        if (aux) cudaStreamDestroy(aux);
+        if (ev_entry) cudaEventDestroy(ev_entry);
+        for (int b = 0; b < 2; b++) {
+            if (ev_core[b]) cudaEventDestroy(ev_core[b]);
+            if (ev_tile[b]) cudaEventDestroy(ev_tile[b]);
+        }
+    }
     sr::DevBuf<int> grp_upidx, grp_loslot, up_list, lo_list, zero_rows, tile_rng;
     int n_up = 0, n_lo = 0, n_zero_rows = 0;
     int cfg = 0, tile_nt = 256, tile_ppt = 4, n_tiles = 0;   // tile geometry of the range table
@@ -713,8 +728,12 @@ int launch_tile(const TileArgs& ta, int n_cells, cudaStream_t st) {
     SR_CUDA(cudaFuncSetAttribute(k_voigt_tile<NT, PPT, F32, MINB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int TP = NT * PPT;
-    dim3 grid((unsigned)((ta.n_grid + TP - 1) / TP), (unsigned)n_cells);
-    SR_LAUNCH((k_voigt_tile<NT, PPT, F32, MINB>), grid, NT, smem, st, ta);
+    if (ta.pt_lo % TP)
+        return sr::fail(SR_ERR_ARG, "output window must start on a multiple of %d grid points", TP);
+    TileArgs tw = ta;
+    tw.tile_base = (int)(ta.pt_lo / TP);
+    dim3 grid((unsigned)((ta.n_grid - ta.pt_lo + TP - 1) / TP), (unsigned)n_cells);
+    SR_LAUNCH((k_voigt_tile<NT, PPT, F32, MINB>), grid, NT, smem, st, tw);
     return SR_OK;
 }
 
@@ -722,7 +741,8 @@ int launch_tile(const TileArgs& ta, int n_cells, cudaStream_t st) {
 // memory twice per SM is used; SR_K1_CFG=<index> forces one (tuning aid)
 struct TileCfg { int nt, ppt; };
 constexpr TileCfg kTileCfgs[] = {{128, 4}, {256, 4}, {256, 2}, {128, 2}, {256, 1}, {128, 4}, {64, 8}, {64, 4},
-                                 {128, 8}, {128, 8}, {128, 6}};
+                                 {128, 8}, {128, 8}, {128, 6}, {128, 4}, {128, 3}, {128, 3}, {128, 2},
+                                 {128, 4}};
 constexpr int kNumCfgs = (int)(sizeof(kTileCfgs) / sizeof(kTileCfgs[0]));
 
 int pick_cfg(int n_lo, int n_groups, size_t smem_max) {
@@ -756,6 +776,11 @@ int launch_cfg(int cfg, const TileArgs& ta, int n_cells, cudaStream_t st) {
         case 8: return launch_tile<128, 8, F32, 4>(ta, n_cells, st);
         case 9: return launch_tile<128, 8, F32, 3>(ta, n_cells, st);
         case 10: return launch_tile<128, 6, F32, 4>(ta, n_cells, st);
+        case 11: return launch_tile<128, 4, F32, 5>(ta, n_cells, st);
+        case 12: return launch_tile<128, 3, F32, 5>(ta, n_cells, st);
+        case 13: return launch_tile<128, 3, F32, 6>(ta, n_cells, st);
+        case 14: return launch_tile<128, 2, F32, 8>(ta, n_cells, st);
+        case 15: return launch_tile<128, 4, F32, 6>(ta, n_cells, st);
     }
     return sr::fail(SR_ERR_ARG, "bad tile configuration");
 }
@@ -972,22 +997,23 @@ int sr_lineset_order(const sr_lineset* ls, int* order_host) {
     return SR_OK;
 }
 
-static int run_params(sr_lineset* ls, const double* pt_host, int n_cells, cudaStream_t st) {
+static int run_params(sr_lineset* ls, const double* pt_host, int n_cells, cudaStream_t st,
+                      int buf = 0) {
     // the per-batch tables are allocated once for a full batch: later (larger) calls never
     // reallocate them, so consecutive batches need no host synchronisation (stream order suffices)
     const size_t cap = (size_t)std::max(n_cells, std::min(ls->max_cells_per_batch, 16));
-    SR_CUDA(ls->pt.ensure(2 * cap));
-    SR_CUDA(cudaMemcpyAsync(ls->pt.p, pt_host, sizeof(double) * 2 * n_cells,
+    SR_CUDA(ls->pt_b[buf].ensure(2 * cap));
+    SR_CUDA(cudaMemcpyAsync(ls->pt_b[buf].p, pt_host, sizeof(double) * 2 * n_cells,
                             cudaMemcpyHostToDevice, st));
-    SR_CUDA(ls->rec.ensure(cap * ls->n_act));
-    SR_CUDA(ls->lrec.ensure(cap * ls->n_act));
+    SR_CUDA(ls->rec_b[buf].ensure(cap * ls->n_act));
+    SR_CUDA(ls->lrec_b[buf].ensure(cap * ls->n_act));
     ParamsArgs pa;
     pa.L = {ls->freq.p, ls->a_coeff.p, ls->air.p, ls->tdep.p, ls->e_lower.p, ls->g_up.p,
             ls->g_lo.p, ls->evu.p, ls->evl.p, ls->gc.p, ls->ind.p};
     pa.lin = ls->lin.p;
-    pa.pt = ls->pt.p;
-    pa.rec = ls->rec.p;
-    pa.lrec = ls->lrec.p;
+    pa.pt = ls->pt_b[buf].p;
+    pa.rec = ls->rec_b[buf].p;
+    pa.lrec = ls->lrec_b[buf].p;
     pa.flags = ls->flags.p;
     pa.n_lines = ls->n_act;
     pa.n_cells = n_cells;
@@ -999,10 +1025,15 @@ static int run_params(sr_lineset* ls, const double* pt_host, int n_cells, cudaSt
 }
 
 static int gcoeff_cells_impl(sr_lineset* ls, const double* pt_host, int n_cells, void* out_dev,
-                             bool f32, cudaStream_t st, long row_stride = 0) {
-    if (row_stride == 0) row_stride = ls->n_grid;
-    if (row_stride < ls->n_grid)
-        return sr::fail(SR_ERR_ARG, "row stride %ld < n_grid %ld", row_stride, ls->n_grid);
+                             bool f32, cudaStream_t st, long row_stride = 0, long win0 = 0,
+                             long win_n = -1) {
+    if (win_n < 0) win_n = ls->n_grid - win0;
+    if (win0 < 0 || win_n < 1 || win0 + win_n > ls->n_grid)
+        return sr::fail(SR_ERR_ARG, "output window [%ld,%ld) outside the grid of %ld points", win0,
+                        win0 + win_n, ls->n_grid);
+    if (row_stride == 0) row_stride = win_n;
+    if (row_stride < win_n)
+        return sr::fail(SR_ERR_ARG, "row stride %ld < window length %ld", row_stride, win_n);
     for (int i = 0; i < n_cells; i++)
         if (!(pt_host[2 * i] >= 0.0) || !(pt_host[2 * i + 1] > 0.0))
             return sr::fail(SR_ERR_ARG, "cell %d: P=%g hPa T=%g K", i, pt_host[2 * i],
@@ -1013,26 +1044,69 @@ static int gcoeff_cells_impl(sr_lineset* ls, const double* pt_host, int n_cells,
         SR_CUDA(cudaMemsetAsync(out_dev, 0, cell_elems * n_cells * esz, st));
         return SR_OK;
     }
-    for (int c0 = 0; c0 < n_cells; c0 += ls->max_cells_per_batch) {
-        const int nb = std::min(ls->max_cells_per_batch, n_cells - c0);
-        // per-batch tables are reused: the kernels of this batch queue behind the previous batch's
-        // tile kernel on the same stream (pt_host is pageable: its copy is staged before return)
-        int code = run_params(ls, pt_host + 2 * c0, nb, st);
-        if (code) return code;
-        SR_CUDA(ls->core.ensure((size_t)std::max(nb, std::min(ls->max_cells_per_batch, 16)) *
-                                ls->n_act * CORE_STRIDE));   // (a growing cudaFree synchronises)
-        {
-            dim3 cgrid((ls->n_act + 7) / 8, nb);
-            SR_LAUNCH(k_core_eval, cgrid, 256, 0, st, ls->rec.p, ls->freq.p, ls->gc.p, ls->lin.p,
-                      ls->n_act, ls->core.p);
+    // Two-stream pipeline over sub-batches of cells: params + core evaluation of sub-batch i+1 on
+    // the (high-priority) aux stream under the tile kernel of sub-batch i on the caller's stream.
+    // k_core_eval CTAs have the footprint of one tile CTA (128 threads, <= 128 registers), so they
+    // slot in wherever a tile CTA retires and fill the FP64 issue slots the tile kernel's
+    // record-loading phases leave idle.
+    static const int pipe_on = getenv("SR_K2_PIPE") ? atoi(getenv("SR_K2_PIPE")) : 0;
+    static const int sub_env = getenv("SR_K2_SUB") ? atoi(getenv("SR_K2_SUB")) : 4;
+    const bool pipe = pipe_on != 0 && n_cells > 1;
+    const int sub = pipe ? std::max(1, std::min(ls->max_cells_per_batch, sub_env))
+                         : ls->max_cells_per_batch;
+    if (pipe && !ls->aux) {
+        int lo_pri = 0, hi_pri = 0;
+        SR_CUDA(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        SR_CUDA(cudaStreamCreateWithPriority(&ls->aux, cudaStreamNonBlocking, hi_pri));
+        SR_CUDA(cudaEventCreateWithFlags(&ls->ev_entry, cudaEventDisableTiming));
+        for (int b = 0; b < 2; b++) {
+            SR_CUDA(cudaEventCreateWithFlags(&ls->ev_core[b], cudaEventDisableTiming));
+            SR_CUDA(cudaEventCreateWithFlags(&ls->ev_tile[b], cudaEventDisableTiming));
         }
+    }
+    if (pipe) {   // the aux stream starts where the caller's stream is now
+        SR_CUDA(cudaEventRecord(ls->ev_entry, st));
+        SR_CUDA(cudaStreamWaitEvent(ls->aux, ls->ev_entry, 0));
+    }
+    const size_t core_cap = (size_t)std::max(std::min(sub, n_cells),
+                                             std::min(ls->max_cells_per_batch, pipe ? sub : 16)) *
+                            ls->n_act * CORE_STRIDE;
+    auto prologue = [&](int i, cudaStream_t ps) -> int {   // params + core of sub-batch i
+        const int c0 = i * sub, nb = std::min(sub, n_cells - c0), buf = pipe ? (i & 1) : 0;
+        if (pipe && i >= 2) SR_CUDA(cudaStreamWaitEvent(ps, ls->ev_tile[buf], 0));   // tile(i-2) done
+        int code = run_params(ls, pt_host + 2 * c0, nb, ps, buf);
+        if (code) return code;
+        SR_CUDA(ls->core_b[buf].ensure(core_cap));   // (a growing cudaFree synchronises)
+        dim3 cgrid((ls->n_act + 3) / 4, nb);
+        {
+            sr::ProfScope pr(SR_PROF_VOIGT_CORE, 0.0, ps);
+            SR_LAUNCH(k_core_eval, cgrid, 128, 0, ps, ls->rec_b[buf].p, ls->freq.p, ls->gc.p,
+                      ls->lin.p, ls->n_act, ls->core_b[buf].p);
+        }
+        if (pipe) SR_CUDA(cudaEventRecord(ls->ev_core[buf], ps));
+        return SR_OK;
+    };
+    const int n_sub = (n_cells + sub - 1) / sub;
+    // line*gridpoint evaluations inside the output window, per cell (profiling only)
+    double win_evals = 0.0;
+    if (sr::g_prof_on.load())
+        for (int ind : ls->ind_in) {
+            if (ind < 0) continue;
+            const long lo = std::max<long>(ind - HALF, win0), hi = std::min<long>(ind - HALF + N_WIN, win0 + win_n);
+            if (hi > lo) win_evals += (double)(hi - lo);
+        }
+    if (pipe) { int code = prologue(0, ls->aux); if (code) return code; }
+    for (int i = 0; i < n_sub; i++) {
+        const int c0 = i * sub, nb = std::min(sub, n_cells - c0), buf = pipe ? (i & 1) : 0;
+        if (!pipe) { int code = prologue(i, st); if (code) return code; }
+        else SR_CUDA(cudaStreamWaitEvent(st, ls->ev_core[buf], 0));
         TileArgs ta;
-        ta.rec = ls->rec.p;
-        ta.lrec = ls->lrec.p;
+        ta.rec = ls->rec_b[buf].p;
+        ta.lrec = ls->lrec_b[buf].p;
         ta.nu0 = ls->freq.p;
         ta.gc = ls->gc.p;
         ta.lin = ls->lin.p;
-        ta.core = ls->core.p;
+        ta.core = ls->core_b[buf].p;
         ta.tile_rng = ls->tile_rng.p;
         ta.grp_upidx = ls->grp_upidx.p;
         ta.grp_loslot = ls->grp_loslot.p;
@@ -1040,16 +1114,26 @@ static int gcoeff_cells_impl(sr_lineset* ls, const double* pt_host, int n_cells,
         ta.lo_list = ls->lo_list.p;
         ta.zero_rows = ls->zero_rows.p;
         ta.out = (char*)out_dev + (size_t)c0 * cell_elems * esz;
-        ta.n_grid = ls->n_grid;
+        ta.n_grid = win0 + win_n;
         ta.row_stride = row_stride;
+        ta.pt_lo = win0;
+        ta.tile_base = 0;
         ta.n_lines = ls->n_act;
         ta.n_sets = ls->n_sets;
         ta.n_groups = ls->n_groups;
         ta.n_up = ls->n_up;
         ta.n_lo = ls->n_lo;
         ta.n_zero = ls->n_zero_rows;
-        code = f32 ? launch_cfg<true>(ls->cfg, ta, nb, st) : launch_cfg<false>(ls->cfg, ta, nb, st);
+        // the next sub-batch's prologue is queued BEFORE this tile kernel so that its CTAs are
+        // already pending when tile CTAs start to retire
+        if (pipe && i + 1 < n_sub) { int code = prologue(i + 1, ls->aux); if (code) return code; }
+        int code;
+        {
+            sr::ProfScope pr(SR_PROF_VOIGT_TILE, win_evals * (double)nb, st);
+            code = f32 ? launch_cfg<true>(ls->cfg, ta, nb, st) : launch_cfg<false>(ls->cfg, ta, nb, st);
+        }
         if (code) return code;
+        if (pipe) SR_CUDA(cudaEventRecord(ls->ev_tile[buf], st));
     }
     return SR_OK;
 }
@@ -1110,6 +1194,16 @@ int sr_gcoeff_cells_dev_f32_ld(sr_lineset* ls, const double* pt_host, int n_cell
     return gcoeff_cells_impl(ls, pt_host, n_cells, out32_dev, true, (cudaStream_t)stream, row_stride);
 }
 
+int sr_gcoeff_cells_window_dev(sr_lineset* ls, const double* pt_host, int n_cells, void* out_dev,
+                               int f32, long row_stride, long pt0, long n_pts, void* stream) {
+    if (!ls || !pt_host || n_cells < 0 || !out_dev)
+        return sr::fail(SR_ERR_ARG, "sr_gcoeff_cells_window_dev: bad argument");
+    return gcoeff_cells_impl(ls, pt_host, n_cells, out_dev, f32 != 0, (cudaStream_t)stream, row_stride,
+                             pt0, n_pts);
+}
+
+int sr_lineset_tile_points(const sr_lineset* ls) { return ls ? ls->tile_nt * ls->tile_ppt : 0; }
+
 int sr_line_shapes_dev(sr_lineset* ls, double pres_hpa, double temp, double* shapes_dev,
                        double* g_dev, void* stream) {
     if (!ls || !shapes_dev || !g_dev) return sr::fail(SR_ERR_ARG, "sr_line_shapes_dev: bad argument");
@@ -1122,7 +1216,7 @@ int sr_line_shapes_dev(sr_lineset* ls, double pres_hpa, double temp, double* sha
     SR_CUDA(ls->facs.ensure(ls->n_act));
     SR_LAUNCH(k_line_fac, (ls->n_act + 255) / 256, 256, 0, st, ls->freq.p, ls->n_act, temp,
               ls->mm, ls->c, ls->facs.p);
-    SR_LAUNCH(k_line_shapes, ls->n_act, 256, 0, st, ls->rec.p, ls->freq.p, ls->gc.p, ls->lin.p,
+    SR_LAUNCH(k_line_shapes, ls->n_act, 256, 0, st, ls->rec_b[0].p, ls->freq.p, ls->gc.p, ls->lin.p,
               shapes_dev, g_dev, ls->facs.p);
     SR_CUDA(cudaStreamSynchronize(st));  // pt is a stack variable
     return check_flags(ls, st);

@@ -138,6 +138,29 @@ class LineSet(object):
         check(lib().sr_lineset_check(self._h, sp))
         return out
 
+    def tile_points(self):
+        """Alignment (grid points) of the output windows of gcoeff_cells_window."""
+        return int(lib().sr_lineset_tile_points(self._h))
+
+    def gcoeff_cells_window(self, PTcouples, pt0, n_pts, f32=True, out=None, stream=None):
+        """The cells on the grid points [pt0, pt0+n_pts) only (a wavenumber slab of the LUT; pt0 a
+        multiple of tile_points()): [n_cells, n_sets, 3, n_pts] float32 (row-padded view, see
+        lut_tensor) or float64.  Bit-identical to the same points of a build on the whole grid."""
+        torch = _torch()
+        pt = as_f64(np.asarray(PTcouples, dtype=float).reshape(-1, 2))
+        n_cells = pt.shape[0]
+        if out is None:
+            out = (lut_tensor(n_cells, self.n_sets, n_pts) if f32 else
+                   torch.empty((n_cells, self.n_sets, 3, n_pts), dtype=torch.float64, device="cuda"))
+        assert tuple(out.shape) == (n_cells, self.n_sets, 3, int(n_pts))
+        rs = lut_row_stride(out) if f32 else int(n_pts)
+        assert f32 or out.is_contiguous()
+        sp = _stream_ptr(stream)
+        check(lib().sr_gcoeff_cells_window_dev(self._h, dptr(pt), n_cells, C.c_void_p(out.data_ptr()),
+                                               int(bool(f32)), rs, int(pt0), int(n_pts), sp))
+        check(lib().sr_lineset_check(self._h, sp))
+        return out
+
     def gcoeff_cells_host(self, PTcouples, out=None):
         """Host-buffer entry point (copies inside): numpy [n_cells, n_sets, 3, n_grid]."""
         pt = as_f64(np.asarray(PTcouples, dtype=float).reshape(-1, 2))
@@ -679,6 +702,27 @@ def convolve_lowres_host(grid, spec, centres, widths, n_sigma=5.0, units='same')
     u = {'same': _lib.SR_CHAN_SAME_UNITS, 'nm': _lib.SR_CHAN_NM_FROM_CM1}[units]
     check(lib().sr_convolve_channels_host(dptr(grid), len(grid), dptr(spec), spec.shape[0], dptr(c),
                                           dptr(w), len(c), float(n_sigma), u, dptr(out)))
+    return out
+
+
+PROF_KINDS = {"los_mma": _lib.SR_PROF_LOS_MMA, "los_layers": _lib.SR_PROF_LOS_LAYERS,
+              "conv": _lib.SR_PROF_CONV, "voigt_tile": _lib.SR_PROF_VOIGT_TILE,
+              "voigt_core": _lib.SR_PROF_VOIGT_CORE, "los_fused": _lib.SR_PROF_LOS_FUSED}
+
+
+def prof_enable(on=True):
+    """Per-kernel CUDA-event timing inside the library (sr_prof_enable); clears earlier records."""
+    check(lib().sr_prof_enable(int(bool(on))))
+
+
+def prof_summary():
+    """{kernel: (launches, total ms, total algorithmic work)} since prof_enable (synchronises)."""
+    out = {}
+    for name, kind in PROF_KINDS.items():
+        n, ms, work = C.c_longlong(), C.c_double(), C.c_double()
+        check(lib().sr_prof_summary(kind, C.byref(n), C.byref(ms), C.byref(work)))
+        if n.value:
+            out[name] = (int(n.value), float(ms.value), float(work.value))
     return out
 
 

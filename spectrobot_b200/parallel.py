@@ -10,6 +10,14 @@ The path shards where the reference itself fans out over processes:
                3202-3221) -> contiguous blocks per rank, gather of the (low-res) spectra (gather_rows);
   one huge line list (config 5)  the sum over lines is linear (lineshape.f:17-23) -> lines split by
                index, all_reduce(SUM, fp64) of the partial [set][3][n_grid] spectra (allreduce_spectra).
+
+Wavenumber slabs (the partition the whole job scales on): every grid point of a
+cross-section, of a LUT row and of a hi-res radiance is independent of every other one, so rank r
+owns ONE contiguous slab of the spectral grid for everything - all (P,T) cells of the LUT on its
+slab (slab_lines: only the lines whose Voigt window reaches it), all lines of sight on its slab -
+and the only exchange of the LOS batch is the all_reduce of the [n_LOS][n_chan] low-res partial
+sums (allreduce_lowres), because a channel's Gaussian window may straddle slabs.  Neighbouring
+slabs share their boundary point so that every trapezoid of the convolution is counted once.
 """
 import os
 
@@ -64,6 +72,81 @@ def shard_lines(n_lines, rank, n_ranks):
     """Lines are split by index; with a frequency-sorted list every rank gets a contiguous
     wavenumber interval, but the result does not depend on that (the sum is linear)."""
     return shard_range(n_lines, rank, n_ranks)
+
+
+def shard_slab(n_grid, rank, n_ranks, align=512):
+    """(pt0, n_pts) of rank's wavenumber slab: grid points [pt0, pt0+n_pts).  Slab starts are
+    multiples of `align` (the tile size of the cross-section kernel, LineSet.tile_points());
+    consecutive slabs SHARE one boundary point (the last point of slab r is the first of slab r+1),
+    so that the trapezoid segments of the instrument convolution partition exactly."""
+    n_grid, align = int(n_grid), int(align)
+    n_tiles = (n_grid + align - 1) // align
+    used = max(1, min(int(n_ranks), n_tiles))          # ranks that get a slab
+    if rank >= used:                                   # more ranks than tiles: nothing to do
+        return n_grid - 1, 0
+    b, e = shard_range(n_tiles, rank, used)
+    pt0 = b * align
+    end = n_grid if rank == used - 1 else min(e * align + 1, n_grid)   # +1: the shared point
+    return pt0, end - pt0
+
+
+def slab_lines(tab, grid, pt0, n_pts, align=512, half_window=None):
+    """The lines whose 13010-point Voigt window can reach a TILE of the slab [pt0, pt0+n_pts): line
+    centre within half a window + one tile (`align` grid points, the cross-section kernel's tile)
+    + closest_grid rounding of the slab.  Returns the sub-table.  A LineSet built from it on the
+    WHOLE grid gives the slab bit-identically to a full build: every tile that overlaps the slab
+    sees exactly the candidate lines (and therefore the summation order) of the full line list."""
+    from ._lib import IMXSIG
+    freq = np.asarray(tab["freq"])
+    step = float(grid[1] - grid[0])
+    hw = (IMXSIG // 2 + 2 + int(align)) * step if half_window is None else float(half_window)
+    lo, hi = grid[pt0] - hw, grid[pt0 + n_pts - 1] + hw
+    keep = (freq >= lo) & (freq <= hi)
+    n = len(freq)
+    return {k: (v[keep] if isinstance(v, np.ndarray) and v.shape[:1] == (n,) else v)
+            for k, v in tab.items()}
+
+
+def allreduce_lowres(low):
+    """Sum of the per-slab partial channel integrals [n_los, n_chan] (or [n_los, n_par, n_chan])
+    over the ranks: the one collective of the wavenumber-sharded LOS batch."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(low, op=dist.ReduceOp.SUM)
+    return low
+
+
+def allgather_steps(local, n_total, rank, n_ranks, device=None):
+    """Step tables (engine.LosSteps) built by every rank for its shard_range block of the LOS ->
+    the tables of all n_total LOS on every rank (the step builder is sharded by LOS, the LOS
+    integral by wavenumber).  Tables are padded to the widest rank before the exchange."""
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    if n_ranks == 1:
+        return local
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    w = torch.tensor([local.n_steps_max], dtype=torch.int64, device=dev)
+    dist.all_reduce(w, op=dist.ReduceOp.MAX)
+    w = int(w.item())
+
+    def padw(a, fill):
+        if a.shape[-1] == w:
+            return a
+        out = np.full(a.shape[:-1] + (w,), fill, dtype=a.dtype)
+        out[..., :a.shape[-1]] = a
+        return out
+
+    def gather(a, los_axis):   # numpy [..., n_los_local, ...] -> [..., n_total, ...]
+        t = torch.as_tensor(np.ascontiguousarray(np.moveaxis(a, los_axis, 0))).to(dev)
+        return np.moveaxis(gather_rows(t, n_total, rank, n_ranks).cpu().numpy(), 0, los_axis)
+
+    n_steps = gather(local.n_steps, 0)
+    temp = gather(padw(local.temp, 100.0), 0)
+    pres = gather(padw(local.pres, 1e-6), 0)
+    col = gather(padw(local.column, 0.0), 1)
+    tvib = None if local.tvib is None else gather(padw(local.tvib, 100.0), 2)
+    return engine.LosSteps(n_steps, temp, pres, col, tvib)
 
 
 def gather_lut(g32, n_cells, rank, n_ranks):

@@ -152,7 +152,7 @@ if __name__ == "__main__":
     if mode == "k1":
         k1()
     elif mode == "k1b":
-        k1b()
+        k1b(int(sys.argv[2]) if len(sys.argv) > 2 else 8)
     elif mode == "conv":
         conv()
     elif mode == "batch":
