@@ -319,6 +319,7 @@ struct RecArgs {
     long n_work;              // n_los * n_tiles (0: nothing to do)
     int n_steps_max, n_tiles, solo, src_is_j;
     int keep;                 // layers were just written and are expected in L2: plain loads
+    int f32;                  // the layer arrays hold float32 values (same element indexing)
 };
 
 template <int PPT, int UNROLL, int NT>
@@ -334,11 +335,22 @@ __device__ __forceinline__ void layers_item(const RecArgs& r, int l, int tile) {
     }
     const int ns = r.n_steps[l];
     const long ls = r.lay_stride;
-    const double* __restrict__ tp = r.tau + (size_t)l * r.n_steps_max * ls + p0;
-    const double* __restrict__ sp = r.src + (size_t)l * r.n_steps_max * ls + p0;
+    const size_t col0 = (size_t)l * r.n_steps_max * ls + p0;
+    const double* __restrict__ tp = r.tau + col0;
+    const double* __restrict__ sp = r.src + col0;
+    const float* __restrict__ tpf = reinterpret_cast<const float*>(r.tau) + col0;
+    const float* __restrict__ spf = reinterpret_cast<const float*>(r.src) + col0;
     const int solo = r.solo, src_is_j = r.src_is_j;
-    const bool keep = r.keep != 0;
-    auto ldl = [&](const double* p) { return keep ? __ldcg(p) : __ldcs(p); };
+    const bool keep = r.keep != 0, f32 = r.f32 != 0;
+    // layer elements at offset o of this thread's column (float32 scratch: same element indexing)
+    auto ld_tau = [&](size_t o) {
+        if (f32) return (double)(keep ? __ldcg(tpf + o) : __ldcs(tpf + o));
+        return keep ? __ldcg(tp + o) : __ldcs(tp + o);
+    };
+    auto ld_src = [&](size_t o) {
+        if (f32) return (double)(keep ? __ldcg(spf + o) : __ldcs(spf + o));
+        return keep ? __ldcg(sp + o) : __ldcs(sp + o);
+    };
     auto update = [&](int i, double t, double s) {
         if (src_is_j) {   // s = J: I <- I e^-tau + J phi(tau), phi = (1 - e^-tau)/tau
             I[i] = srdev::layer_update_j(I[i], t, s, solo != 0);
@@ -358,8 +370,8 @@ __device__ __forceinline__ void layers_item(const RecArgs& r, int l, int tile) {
 #pragma unroll
             for (int i = 0; i < PPT; i++) {
                 const size_t o = (size_t)(k + u) * ls + i * NT;
-                t[u][i] = ok[i] ? ldl(tp + o) : 0.0;
-                s[u][i] = ok[i] ? ldl(sp + o) : 0.0;
+                t[u][i] = ok[i] ? ld_tau(o) : 0.0;
+                s[u][i] = ok[i] ? ld_src(o) : 0.0;
             }
 #pragma unroll
         for (int u = 0; u < UNROLL; u++)
@@ -369,7 +381,7 @@ __device__ __forceinline__ void layers_item(const RecArgs& r, int l, int tile) {
     for (; k < ns; k++)
 #pragma unroll
         for (int i = 0; i < PPT; i++)
-            if (ok[i]) update(i, ldl(tp + (size_t)k * ls + i * NT), ldl(sp + (size_t)k * ls + i * NT));
+            if (ok[i]) update(i, ld_tau((size_t)k * ls + i * NT), ld_src((size_t)k * ls + i * NT));
 #pragma unroll
     for (int i = 0; i < PPT; i++)
         if (ok[i]) __stcs(r.rad + (size_t)l * r.io_stride + r.io_off + p0 + i * NT, I[i]);
@@ -378,6 +390,48 @@ __device__ __forceinline__ void layers_item(const RecArgs& r, int l, int tile) {
 template <int PPT, int UNROLL>
 __global__ void __launch_bounds__(256, 6) k_los_layers(const __grid_constant__ RecArgs r) {
     layers_item<PPT, UNROLL, 256>(r, (int)blockIdx.y, (int)blockIdx.x);
+}
+
+// K3 over a float32 layer scratch (J form only): a thread owns two neighbouring points and reads
+// them as one float2 per array and step, so that it keeps as many bytes in flight as the FP64
+// kernel does (UNROLL steps x 2 arrays x 8 B).  Rows are 16-byte aligned (lay_stride % 4 == 0).
+template <int UNROLL>
+__global__ void __launch_bounds__(256, 6) k_los_layers_f32(const __grid_constant__ RecArgs r) {
+    const int l = blockIdx.y;
+    const long p0 = ((long)blockIdx.x * 256 + threadIdx.x) * 2;
+    if (p0 >= r.n_pts) return;
+    const bool ok1 = p0 + 1 < r.n_pts;
+    double I0 = r.i0 ? r.i0[(size_t)l * r.io_stride + r.io_off + p0] : 0.0;
+    double I1 = (r.i0 && ok1) ? r.i0[(size_t)l * r.io_stride + r.io_off + p0 + 1] : 0.0;
+    const int ns = r.n_steps[l];
+    const long ls = r.lay_stride;
+    const size_t col0 = (size_t)l * r.n_steps_max * ls + p0;
+    const float* __restrict__ tp = reinterpret_cast<const float*>(r.tau) + col0;
+    const float* __restrict__ sp = reinterpret_cast<const float*>(r.src) + col0;
+    const bool solo = r.solo != 0;
+    auto ld2 = [&](const float* p) { return __ldcs(reinterpret_cast<const float2*>(p)); };
+    int k = 0;
+    for (; k + UNROLL <= ns; k += UNROLL) {
+        float2 t[UNROLL], s[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            t[u] = ld2(tp + (size_t)(k + u) * ls);
+            s[u] = ld2(sp + (size_t)(k + u) * ls);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            I0 = srdev::layer_update_j(I0, (double)t[u].x, (double)s[u].x, solo);
+            I1 = srdev::layer_update_j(I1, (double)t[u].y, (double)s[u].y, solo);
+        }
+    }
+    for (; k < ns; k++) {
+        const float2 t = ld2(tp + (size_t)k * ls), s = ld2(sp + (size_t)k * ls);
+        I0 = srdev::layer_update_j(I0, (double)t.x, (double)s.x, solo);
+        I1 = srdev::layer_update_j(I1, (double)t.y, (double)s.y, solo);
+    }
+    double* o = r.rad + (size_t)l * r.io_stride + r.io_off + p0;
+    __stcs(o, I0);
+    if (ok1) __stcs(o + 1, I1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -428,6 +482,11 @@ __global__ void __launch_bounds__(256, MINB) k_los_layers_jac(const __grid_const
     const double* __restrict__ sp = r.src + lay0;
     const double* __restrict__ tgp = MULTI ? a.tau_g + lay0 : nullptr;
     const double* __restrict__ sgp = MULTI ? a.src_g + lay0 : nullptr;
+    const bool f32 = r.f32 != 0;   // float32 layer scratch: same element indexing, half the bytes
+    auto ldv = [&](const double* base, size_t o) {
+        if (f32) return (double)__ldcs(reinterpret_cast<const float*>(base - lay0) + lay0 + o);
+        return __ldcs(base + o);
+    };
     const int npar = min(NP, a.n_par - pz);
     // this LOS' rows of the derivative table, zero-padded to NP columns, in shared memory: the
     // inner loop reads them as broadcast LDS.128 (no per-parameter predicate, no global latency)
@@ -447,11 +506,11 @@ __global__ void __launch_bounds__(256, MINB) k_los_layers_jac(const __grid_const
         for (int u = 0; u < U; u++) {
             const bool ok = k0 + u < ns;
             const size_t o = (size_t)(k0 + u) * ls;
-            t[u] = ok ? __ldcs(tp + o) : 0.0;
-            s[u] = ok ? __ldcs(sp + o) : 0.0;
+            t[u] = ok ? ldv(tp, o) : 0.0;
+            s[u] = ok ? ldv(sp, o) : 0.0;
             if (MULTI) {
-                tg[u] = ok ? __ldcs(tgp + o) : 0.0;
-                sg[u] = ok ? __ldcs(sgp + o) : 0.0;
+                tg[u] = ok ? ldv(tgp, o) : 0.0;
+                sg[u] = ok ? ldv(sgp, o) : 0.0;
             }
         }
 #pragma unroll
@@ -518,6 +577,7 @@ struct MmaArgs {
     int mode;                     // 0: src = S = J/tau, 1: src = J
     int keep;                     // 1: the layer rows are read back at once (L2-sized scratch):
                                   // default-policy stores instead of streaming ones
+    int f32;                      // 1: the layer rows are stored as float32 (same element indexing)
 };
 
 struct PackArgs {
@@ -709,7 +769,12 @@ __global__ void __launch_bounds__(MMA_NT, MINB) k_los_mma(MmaArgs a) {
                                 x[i] = (t == 0.0) ? 0.0 : x[i] / t;
                             }
                         }
-                        if (a.keep) st_cg_v4(o + off, x); else st_cs_v4(o + off, x);
+                        if (a.f32) {
+                            float* of = reinterpret_cast<float*>(out) + (size_t)(pr - a.pair_base) * a.ld_out +
+                                        p_warp + off;
+                            __stcs(reinterpret_cast<float4*>(of),
+                                   make_float4((float)x[0], (float)x[1], (float)x[2], (float)x[3]));
+                        } else if (a.keep) st_cg_v4(o + off, x); else st_cs_v4(o + off, x);
                     }
             } else {
 #pragma unroll
@@ -723,7 +788,10 @@ __global__ void __launch_bounds__(MMA_NT, MINB) k_los_mma(MmaArgs a) {
                             const double t = t_in[off];
                             x = (t == 0.0) ? 0.0 : x / t;
                         }
-                        if (a.keep) __stcg(o + off, x); else __stcs(o + off, x);
+                        if (a.f32)
+                            __stcs(reinterpret_cast<float*>(out) + (size_t)(pr - a.pair_base) * a.ld_out + p_warp + off,
+                                   (float)x);
+                        else if (a.keep) __stcg(o + off, x); else __stcs(o + off, x);
                     }
             }
         }
@@ -732,6 +800,277 @@ __global__ void __launch_bounds__(MMA_NT, MINB) k_los_mma(MmaArgs a) {
     store(a.tau_out, false);
     pass(n_tau, n_tot);
     store(a.src_out, true);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// K3a+K3 fused (v4): the tensor-path product AND the layer recursion in one kernel; tau and J
+// never leave the SM.
+//
+// A CTA owns a LOS group (FZ_LG lines of sight that the planner sorted to be alike) and a tile of
+// FZ_TP grid points, and keeps the running intensities I[LOS][point] of the whole group in shared
+// memory.  The planner cuts the group's (LOS, step) pairs into level-synchronous rounds - round r
+// holds step r of every LOS - and inside a round into <= 16-pair chunks of one cell quad, so a LOS
+// occurs at most once per chunk and its steps arrive in order.  Per chunk:
+//   stage    one thread moves the chunk's fragment-ordered weights (<= 12.8 KB, contiguous), the
+//            quad's row pointers, the 16 LOS slots and the row counts into shared memory with
+//            TMA bulk copies (cp.async.bulk, completion on an mbarrier), one chunk ahead;
+//   product  tau[16 pairs][32 points per warp] = W_tau * G as DMMA.8x8x4, LUT rows straight from
+//            global memory (L2) as in k_los_mma;
+//   update   e^-tau and phi(tau) (srdev::exp_phi), I' = I e^-tau with I from shared memory;
+//   product  J = W_J * G over the emission rows;
+//   update   I = I' + J phi(tau) back to shared memory.
+// After the last chunk the group's radiances go to global memory once.  DRAM traffic = LUT rows
+// (through L2) + weights + 8 B per (LOS, point); the 16 B per (LOS, step, point) layer round trip
+// of the k_los_mma -> k_los_layers pair is gone.
+// ---------------------------------------------------------------------------------------------
+constexpr int FZ_LG = 64;            // LOS per CTA
+constexpr int FZ_NT = 128;           // threads per CTA (4 warps)
+constexpr int FZ_NB = 4;             // 8-point N blocks per warp: 32 points per warp
+constexpr int FZ_TP = (FZ_NT / 32) * 8 * FZ_NB;   // 128 points per CTA
+constexpr int FZ_SP = FZ_TP + 4;     // state row stride (doubles): rows 32-byte aligned, banks shifted
+
+struct FuseArgs {
+    const long long* rowptr;      // [n_groups][max_jp] device address of each program row
+    const int4* chunk_meta;       // [n_chunks] {group, n_tau, n_tot, 0}
+    const int* chunk_slot;        // [n_chunks][16] LOS slot in the CTA's group, -1 = padding
+    const double* wfrag;          // [n_chunks][max_jp/4][2][32] fragment-ordered weights
+    const int* lg_chunk;          // [n_lg + 1] chunk range of each LOS group
+    const int* lg_row;            // [n_lg][FZ_LG] output row of the slot in `rad` (-1: unused slot)
+    const int* lg_i0row;          // [n_lg][FZ_LG] row of the slot in `i0`
+    int max_jp, lg0;              // lg0: first LOS group of this launch
+    long pt0, n_pts;              // window of the LUT grid
+    long ld_min;                  // smallest LUT row stride: loads are clamped below it
+    long io_stride, io_off;       // rad / i0 rows: [row][io_stride], this window at io_off
+    const double* i0;
+    double* rad;
+    int solo;
+    int dbg;                      // ablation switches (SR_LOS_FDBG; results are wrong when set)
+    int* flags;                   // LFLAG_* word of the call (a stuck mbarrier is reported there)
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// TMA 1-D bulk copy global -> shared, completion counted on the mbarrier (bytes % 16 == 0)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes,
+                                         unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int LD>
+__global__ void __launch_bounds__(FZ_NT, 2) k_los_fused2(const __grid_constant__ FuseArgs a) {
+    constexpr int NB = FZ_NB;
+    extern __shared__ __align__(128) unsigned char fsm[];
+    // layout: state | 2 x {wA, rps, slots, meta} | mbarriers
+    double* state = reinterpret_cast<double*>(fsm);                          // [FZ_LG][FZ_SP]
+    const size_t buf_bytes = (size_t)a.max_jp * (MMA_PB * sizeof(double) + sizeof(long long)) + 64 + 16;
+    unsigned char* bufs = fsm + (size_t)FZ_LG * FZ_SP * sizeof(double);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(bufs + 2 * buf_bytes);
+    auto wA_of = [&](int b) { return reinterpret_cast<double*>(bufs + b * buf_bytes); };
+    auto rps_of = [&](int b) {
+        return reinterpret_cast<long long*>(bufs + b * buf_bytes + (size_t)a.max_jp * MMA_PB * sizeof(double));
+    };
+    auto slot_of = [&](int b) {
+        return reinterpret_cast<int*>(bufs + b * buf_bytes +
+                                      (size_t)a.max_jp * (MMA_PB * sizeof(double) + sizeof(long long)));
+    };
+    auto meta_of = [&](int b) { return reinterpret_cast<int4*>(slot_of(b) + MMA_PB); };
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int lg = a.lg0 + blockIdx.x;
+    const int c_beg = __ldg(a.lg_chunk + lg), c_end = __ldg(a.lg_chunk + lg + 1);
+    const long p_cta = (long)blockIdx.y * FZ_TP;
+    const long p_warp = p_cta + wid * (8 * NB);
+    const bool warp_live = p_warp < a.n_pts;
+
+    auto stage = [&](int c, int b) {   // one thread: chunk c -> buffer b
+        const int4 m = __ldg(a.chunk_meta + c);
+        const unsigned wb = (unsigned)m.z * MMA_PB * sizeof(double), rb = (unsigned)m.z * sizeof(long long);
+        mbar_expect_tx(bars + b, wb + rb + 64 + 16);
+        bulk_g2s(wA_of(b), a.wfrag + (size_t)c * a.max_jp * MMA_PB, wb, bars + b);
+        bulk_g2s(rps_of(b), a.rowptr + (size_t)m.x * a.max_jp, rb, bars + b);
+        bulk_g2s(slot_of(b), a.chunk_slot + (size_t)c * MMA_PB, 64, bars + b);
+        bulk_g2s(meta_of(b), a.chunk_meta + c, 16, bars + b);
+    };
+    if (tid == 0) {
+        mbar_init(bars + 0, 1);
+        mbar_init(bars + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // running intensities of the group: I0 or zero
+    {
+        const int* __restrict__ i0row = a.lg_i0row + (size_t)lg * FZ_LG;
+        for (int idx = tid; idx < FZ_LG * FZ_TP; idx += FZ_NT) {
+            const int sl = idx / FZ_TP, p = idx - sl * FZ_TP;
+            double v = 0.0;
+            if (a.i0 && p_cta + p < a.n_pts) {
+                const int row = __ldg(i0row + sl);
+                if (row >= 0) v = a.i0[(size_t)row * a.io_stride + a.io_off + p_cta + p];
+            }
+            state[sl * FZ_SP + p] = v;
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && c_beg < c_end) stage(c_beg, 0);
+
+    const int kq = lane & 3, nq = lane >> 2;
+    struct Frag { float v[NB]; };
+    // per-lane point offset inside a LUT row (one 16-byte vector: points 4(nq>>1) + 16(nq&1) + 0..3);
+    // lanes beyond the window re-read the last valid vector of the row (never stored)
+    const long loff = min(a.pt0 + p_warp + 4 * (nq >> 1) + 16 * (nq & 1), a.ld_min - 4);
+    double C0[NB][2], C1[NB][2];
+
+    for (int c = c_beg; c < c_end; c++) {
+        const int b = (c - c_beg) & 1;
+        if (tid == 0 && c + 1 < c_end) stage(c + 1, b ^ 1);   // buffer b^1: chunk c-1 is done (barrier below)
+        {   // wait for chunk c (phase parity of buffer b: it completes once every two chunks)
+            const unsigned parity = (unsigned)(((c - c_beg) >> 1) & 1);
+            unsigned spins = 0;
+            while (!mbar_try_wait(bars + b, parity)) {
+                if (++spins > (1u << 26)) {   // never in a correct run: report instead of hanging
+                    if (lane == 0) atomicOr(a.flags, LFLAG_NONFINITE);
+                    break;
+                }
+            }
+        }
+        if (warp_live) {
+            const double* __restrict__ wA = wA_of(b);
+            const long long* __restrict__ rps = rps_of(b);
+            const int* __restrict__ slot_s = slot_of(b);
+            const int4 meta = *meta_of(b);
+            const int n_tau = meta.y, n_tot = meta.z;
+            const bool two = slot_s[8] >= 0;
+            auto load = [&](int j, Frag& f) {
+                const float* __restrict__ r = reinterpret_cast<const float*>(rps[j + kq]);
+                const float4 q = ld_row4<LD>(r + loff);
+                f.v[0] = q.x; f.v[1] = q.y; f.v[2] = q.z; f.v[3] = q.w;
+            };
+            auto mma_step = [&](int j, const double (&bv)[NB]) {
+                const double a0 = wA[(j >> 2) * 64 + lane];
+                if (two) {
+                    const double a1 = wA[(j >> 2) * 64 + 32 + lane];
+#pragma unroll
+                    for (int i = 0; i < NB; i++) {
+                        dmma884(C0[i], a0, bv[i]);
+                        dmma884(C1[i], a1, bv[i]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NB; i++) dmma884(C0[i], a0, bv[i]);
+                }
+            };
+#define SR_FSTEP(J, F, RELOAD)                                            \
+    {                                                                     \
+        double b_[NB];                                                    \
+        _Pragma("unroll") for (int i = 0; i < NB; i++) b_[i] = (double)F.v[i]; \
+        if (RELOAD) load(min((J) + 20, j1 - 4), F);                       \
+        mma_step((J), b_);                                                \
+    }
+            // rows [j0, j1): five B-fragment buffers rotate, every load has four k-steps to arrive
+            // (two warps per scheduler here, against four in k_los_mma)
+            auto pass = [&](int j0, int j1) {
+#pragma unroll
+                for (int i = 0; i < NB; i++) C0[i][0] = C0[i][1] = C1[i][0] = C1[i][1] = 0.0;
+                if (j0 >= j1) return;
+                Frag f0, f1, f2, f3, f4;
+                load(j0, f0);
+                load(min(j0 + 4, j1 - 4), f1);
+                load(min(j0 + 8, j1 - 4), f2);
+                load(min(j0 + 12, j1 - 4), f3);
+                load(min(j0 + 16, j1 - 4), f4);
+                int j = j0;
+#pragma unroll 1
+                for (; j + 20 <= j1; j += 20) {
+                    SR_FSTEP(j, f0, true)
+                    SR_FSTEP(j + 4, f1, true)
+                    SR_FSTEP(j + 8, f2, true)
+                    SR_FSTEP(j + 12, f3, true)
+                    SR_FSTEP(j + 16, f4, true)
+                }
+                if (j < j1) SR_FSTEP(j, f0, false)
+                if (j + 4 < j1) SR_FSTEP(j + 4, f1, false)
+                if (j + 8 < j1) SR_FSTEP(j + 8, f2, false)
+                if (j + 12 < j1) SR_FSTEP(j + 12, f3, false)
+            };
+#undef SR_FSTEP
+            // C fragment of m-block mb, half e: 4 consecutive points at 16 e + 4 kq of pair nq
+            double Ip[2][2][4], ph[2][2][4];
+            int sl[2];
+            sl[0] = slot_s[nq];
+            sl[1] = two ? slot_s[8 + nq] : -1;
+            if (!(a.dbg & 2)) pass(0, n_tau);
+#pragma unroll
+            for (int mb = 0; mb < 2; mb++) {
+                if (sl[mb] < 0) continue;
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const double* st = state + sl[mb] * FZ_SP + wid * (8 * NB) + 16 * e + 4 * kq;
+                    const double2 q0 = *reinterpret_cast<const double2*>(st);
+                    const double2 q1 = *reinterpret_cast<const double2*>(st + 2);
+                    const double Iv[4] = {q0.x, q0.y, q1.x, q1.y};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        double ex, phi;
+                        if (a.dbg & 1) { ex = 0.5; phi = mb ? C1[i][e] : C0[i][e]; }
+                        else srdev::exp_phi(mb ? C1[i][e] : C0[i][e], ex, phi);
+                        Ip[mb][e][i] = Iv[i] * ex;
+                        ph[mb][e][i] = phi;
+                    }
+                }
+            }
+            if (!a.solo && !(a.dbg & 2)) pass(n_tau, n_tot);
+#pragma unroll
+            for (int mb = 0; mb < 2; mb++) {
+                if (sl[mb] < 0) continue;
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    double* st = state + sl[mb] * FZ_SP + wid * (8 * NB) + 16 * e + 4 * kq;
+                    double o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        o[i] = a.solo ? Ip[mb][e][i]
+                                      : fma(mb ? C1[i][e] : C0[i][e], ph[mb][e][i], Ip[mb][e][i]);
+                    *reinterpret_cast<double2*>(st) = make_double2(o[0], o[1]);
+                    *reinterpret_cast<double2*>(st + 2) = make_double2(o[2], o[3]);
+                }
+            }
+        }
+        __syncthreads();   // chunk c done by every warp: its buffer may be refilled, I is visible
+    }
+    // the group's radiances leave the SM once
+    {
+        const int* __restrict__ orow = a.lg_row + (size_t)lg * FZ_LG;
+        for (int sl = 0; sl < FZ_LG; sl++) {
+            const int row = __ldg(orow + sl);
+            if (row < 0) continue;
+            if (p_cta + tid < a.n_pts)
+                __stcs(a.rad + (size_t)row * a.io_stride + a.io_off + p_cta + tid, state[sl * FZ_SP + tid]);
+        }
+    }
+}
+
+__global__ void k_scatter_rows(const double* __restrict__ src, const int* __restrict__ dst_row, int n_rows,
+                               int n_cols, double* __restrict__ dst) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long)n_rows * n_cols) return;
+    const int r = (int)(e / n_cols), c = (int)(e - (long)r * n_cols);
+    dst[(size_t)dst_row[r] * n_cols + c] = src[e];
 }
 
 }  // namespace
@@ -758,6 +1097,8 @@ struct sr_lut {
     sr::DevBuf<long long> g_rowptr;
     sr::DevBuf<double> g_wfrag;
     sr::DevBuf<int> g_ntau, g_ntot, g_cgrp, g_cpair;
+    sr::DevBuf<int> g_cslot, g_cmeta, g_lgchunk, g_lgrow, g_lgi0, g_scat;   // fused path (k_los_fused2)
+    sr::DevBuf<double> ws_low;
     cudaStream_t copy_stream = nullptr; // device -> host copies of the host-buffer entry point
     // One LOS call at a time per handle: the per-call scratch below lives in luts[0].  `mtx`
     // serialises the host side of concurrent callers; `busy` is recorded on the caller's stream at
@@ -1044,23 +1385,36 @@ static RecArgs rec_args(const double* tau, const double* src, const int* n_steps
     r.solo = solo_absorption;
     r.src_is_j = src_is_j;
     r.keep = 0;
+    r.f32 = 0;
     return r;
 }
 
 static int layers_launch(const double* tau, const double* src, const int* n_steps, int n_los,
                          int n_steps_max, long n_pts, const double* i0, int solo_absorption,
                          double* rad, cudaStream_t st, int src_is_j, long io_stride = -1,
-                         long io_off = 0, long lay_stride = -1, int keep = 0) {
+                         long io_off = 0, long lay_stride = -1, int keep = 0, int f32 = 0) {
     // measured on B200 (tools/tune.py): (PPT=1, UNROLL=4) at 38 registers streams at the
     // measured copy bandwidth; wider variants lose occupancy
     int cfg = 5;
     if (const char* e = getenv("SR_K3_CFG")) cfg = atoi(e);   // tuning aid
+    if (f32 && src_is_j && (lay_stride < 0 ? n_pts : lay_stride) % 4 == 0) {
+        RecArgs r = rec_args(tau, src, n_steps, n_los, n_steps_max, n_pts, i0, solo_absorption, rad,
+                             src_is_j, io_stride, io_off, lay_stride, 512);
+        r.keep = keep;
+        r.f32 = 1;
+        static const int u32 = getenv("SR_K3F_UNROLL") ? atoi(getenv("SR_K3F_UNROLL")) : 4;
+        if (u32 == 8) SR_LAUNCH((k_los_layers_f32<8>), dim3((unsigned)r.n_tiles, (unsigned)n_los), 256, 0, st, r);
+        else if (u32 == 2) SR_LAUNCH((k_los_layers_f32<2>), dim3((unsigned)r.n_tiles, (unsigned)n_los), 256, 0, st, r);
+        else SR_LAUNCH((k_los_layers_f32<4>), dim3((unsigned)r.n_tiles, (unsigned)n_los), 256, 0, st, r);
+        return SR_OK;
+    }
 #define SR_K3_LAUNCH(PPT, UNROLL)                                                             \
     {                                                                                          \
         RecArgs r = rec_args(tau, src, n_steps, n_los, n_steps_max, n_pts, i0,                 \
                              solo_absorption, rad, src_is_j, io_stride, io_off,                \
                              lay_stride, 256 * PPT);                                           \
         r.keep = keep;                                                                         \
+        r.f32 = f32;                                                                           \
         SR_LAUNCH((k_los_layers<PPT, UNROLL>), dim3((unsigned)r.n_tiles, (unsigned)n_los), 256, \
                   0, st, r);                                                                   \
     }
@@ -1091,10 +1445,11 @@ static int layers_jac_launch(const double* tau, const double* src, const double*
                              const double* src_g, const double* dfrac, int n_par,
                              const int* n_steps, int n_los, int n_steps_max, long n_pts,
                              const double* i0, int solo, double* rad, double* jac, cudaStream_t st,
-                             long io_stride = -1, long io_off = 0, long lay_stride = -1) {
+                             long io_stride = -1, long io_off = 0, long lay_stride = -1, int f32 = 0) {
     JacArgs a;
     a.r = rec_args(tau, src, n_steps, n_los, n_steps_max, n_pts, i0, solo, rad, 1, io_stride,
                    io_off, lay_stride, 256);
+    a.r.f32 = f32;
     a.tau_g = tau_g;
     a.src_g = src_g;
     a.dfrac = dfrac;
@@ -1166,6 +1521,17 @@ struct GemmPlan {
     std::vector<int> nreal;             // per group: rows that are not padding
     std::vector<double> blk_rowpairs;   // per block: sum over chunks of real rows x valid pairs
     int max_jp = 4, n_groups = 0, n_chunks = 0;
+    // shared by both chunkers
+    std::vector<int> pair_grp;          // [n_los][n_steps_max] group (cell quad) of the pair, -1 = none
+    std::vector<int> grp_order;         // groups in key order
+    // fused path (k_los_fused2): LOS sorted to be alike, groups of FZ_LG, level-synchronous rounds
+    std::vector<int> perm;              // sorted position -> LOS
+    std::vector<int> chunk_slot;        // [n_chunks][16] slot of the LOS in its group
+    std::vector<int4> chunk_meta;       // [n_chunks] {group, n_tau, n_tot, 0}
+    std::vector<int> lg_chunk;          // [n_lg + 1]
+    std::vector<double> lg_rowpairs;    // per LOS group: real rows x pairs
+    double slots = 0.0, pairs = 0.0;    // compute slots (8-pair granular) and valid pairs
+    int n_lg = 0;
 };
 
 static int cells_of(const sr_lut* L, double pres, double temp, int cell[4]) {
@@ -1196,8 +1562,8 @@ static int cells_of(const sr_lut* L, double pres, double temp, int cell[4]) {
     return SR_OK;
 }
 
-// nl_block: LOS per block (the last block may be shorter)
-static int build_plan(sr_lut* const* luts, const sr_los_steps* S, int nl_block, GemmPlan& P) {
+// cell quad of every (LOS, step) pair and one row program per quad
+static int plan_groups(sr_lut* const* luts, const sr_los_steps* S, GemmPlan& P) {
     const int n_gas = S->n_gas;
     const size_t nmax = (size_t)S->n_steps_max;
     // row lists per gas and ctype (all-zero spectra are skipped like the reference's None entries)
@@ -1220,7 +1586,8 @@ static int build_plan(sr_lut* const* luts, const sr_los_steps* S, int nl_block, 
     // consecutive steps of a LOS mostly stay in the same quad: a one-entry cache in front of the map
     std::map<QuadKey, int> group_of;
     std::vector<QuadKey> keys;                 // per group
-    std::vector<int> pair_grp((size_t)S->n_los * nmax, -1);
+    std::vector<int>& pair_grp = P.pair_grp;
+    pair_grp.assign((size_t)S->n_los * nmax, -1);
     QuadKey last;
     memset(last.c, 0x7f, sizeof(last.c));
     int last_grp = -1;
@@ -1289,10 +1656,22 @@ static int build_plan(sr_lut* const* luts, const sr_los_steps* S, int nl_block, 
         P.nreal.push_back(real);
     }
     // groups in key order: neighbouring quads share cells, so their chunks share LUT rows in L2
-    std::vector<int> grp_order(P.n_groups);
+    std::vector<int>& grp_order = P.grp_order;
+    grp_order.resize(P.n_groups);
     for (int g = 0; g < P.n_groups; g++) grp_order[g] = g;
     std::sort(grp_order.begin(), grp_order.end(), [&](int a, int b) { return keys[a] < keys[b]; });
-    // ---- pass 2: per LOS block a counting sort of its pairs by group, then 16-pair chunks ------
+    P.rowptr.resize(P.prog.size());
+    for (size_t q = 0; q < P.prog.size(); q++) P.rowptr[q] = P.prog[q].roff;
+    return SR_OK;
+}
+
+// nl_block: LOS per block (the last block may be shorter)
+static int build_plan(sr_lut* const* luts, const sr_los_steps* S, int nl_block, GemmPlan& P) {
+    int rc = plan_groups(luts, S, P);
+    if (rc) return rc;
+    const size_t nmax = (size_t)S->n_steps_max;
+    const std::vector<int>&pair_grp = P.pair_grp, &grp_order = P.grp_order;
+    // ---- per LOS block a counting sort of its pairs by group, then 16-pair chunks --------------
     std::vector<int> cnt(P.n_groups + 1), fill(P.n_groups), sorted;
     P.blk_los.push_back(0);
     P.blk_chunk.push_back(0);
@@ -1323,8 +1702,73 @@ static int build_plan(sr_lut* const* luts, const sr_los_steps* S, int nl_block, 
         P.blk_chunk.push_back(P.n_chunks);
         P.blk_rowpairs.push_back(rowpairs);
     }
-    P.rowptr.resize(P.prog.size());
-    for (size_t q = 0; q < P.prog.size(); q++) P.rowptr[q] = P.prog[q].roff;
+    return SR_OK;
+}
+
+// Chunks for k_los_fused2.  LOS are sorted by (step count, quad sequence) so that the FZ_LG
+// members of a LOS group walk through the same cell quads at the same step index; round r of a
+// group holds step r of every member, cut into <= 16-pair chunks of one quad (a LOS at most once
+// per chunk, its steps in order).  A chunk with <= 8 pairs costs one 8-row M block, not two.
+static int build_fused_plan(sr_lut* const* luts, const sr_los_steps* S, GemmPlan& P) {
+    int rc = plan_groups(luts, S, P);
+    if (rc) return rc;
+    const size_t nmax = (size_t)S->n_steps_max;
+    const int n_los = S->n_los;
+    const std::vector<int>& pair_grp = P.pair_grp;
+    std::vector<int> rank_of(P.n_groups);               // group -> position in key order
+    for (int i = 0; i < P.n_groups; i++) rank_of[P.grp_order[i]] = i;
+    P.perm.resize(n_los);
+    for (int l = 0; l < n_los; l++) P.perm[l] = l;
+    std::sort(P.perm.begin(), P.perm.end(), [&](int x, int y) {
+        const int nx = S->n_steps[x], ny = S->n_steps[y];
+        if (nx != ny) return nx < ny;
+        const int* px = pair_grp.data() + (size_t)x * nmax;
+        const int* py = pair_grp.data() + (size_t)y * nmax;
+        for (int k = 0; k < nx; k++)
+            if (px[k] != py[k]) return rank_of[px[k]] < rank_of[py[k]];
+        return x < y;
+    });
+    P.n_lg = (n_los + FZ_LG - 1) / FZ_LG;
+    P.lg_chunk.assign(1, 0);
+    std::vector<std::pair<int, int>> ready;             // (group rank, slot)
+    for (int g = 0; g < P.n_lg; g++) {
+        const int s0 = g * FZ_LG, ns = std::min(FZ_LG, n_los - s0);
+        int max_r = 0;
+        for (int sl = 0; sl < ns; sl++) max_r = std::max(max_r, S->n_steps[P.perm[s0 + sl]]);
+        double rowpairs = 0.0;
+        for (int r = 0; r < max_r; r++) {
+            ready.clear();
+            for (int sl = 0; sl < ns; sl++) {
+                const int l = P.perm[s0 + sl];
+                if (S->n_steps[l] > r) ready.emplace_back(rank_of[pair_grp[(size_t)l * nmax + r]], sl);
+            }
+            std::sort(ready.begin(), ready.end());
+            size_t i = 0;
+            while (i < ready.size()) {
+                size_t e = i;
+                while (e < ready.size() && ready[e].first == ready[i].first) e++;
+                const int grp = P.grp_order[ready[i].first];
+                rowpairs += (double)P.nreal[grp] * (double)(e - i);
+                for (size_t q = i; q < e; q += MMA_PB) {
+                    const int nv = (int)std::min<size_t>(MMA_PB, e - q);
+                    P.chunk_grp.push_back(grp);
+                    P.chunk_meta.push_back(make_int4(grp, P.ntau[grp], P.ntot[grp], 0));
+                    for (int t = 0; t < MMA_PB; t++) {
+                        const bool ok = t < nv;
+                        const int sl = ok ? ready[q + t].second : -1;
+                        P.chunk_slot.push_back(sl);
+                        P.chunk_pair.push_back(ok ? (int)((size_t)P.perm[s0 + sl] * nmax + r) : -1);
+                    }
+                    P.slots += nv <= 8 ? 8.0 : 16.0;
+                    P.pairs += nv;
+                    P.n_chunks++;
+                }
+                i = e;
+            }
+        }
+        P.lg_chunk.push_back(P.n_chunks);
+        P.lg_rowpairs.push_back(rowpairs);
+    }
     return SR_OK;
 }
 
@@ -1389,6 +1833,160 @@ static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, lon
                              double* src_dev, cudaStream_t st, int emit_j, HostSink* sink,
                              LowSink* low, JacSpec* jac);
 
+}  // extern "C"
+
+template <int LD>
+static int fused_launch_t(dim3 grid, size_t smem, cudaStream_t st, const FuseArgs& fa) {
+    SR_CUDA(cudaFuncSetAttribute(k_los_fused2<LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SR_LAUNCH((k_los_fused2<LD>), grid, FZ_NT, smem, st, fa);
+    return SR_OK;
+}
+
+// v4 (k_los_fused2).  *done = false: not applicable (alignment, shared memory, or chunks too empty
+// to pay: the batch is small or its LOS too unlike) - the caller takes the v3 path.
+static int los_launch_fused(sr_lut* const* luts, const sr_los_steps* steps, const LosArgs& la, long pt0,
+                            long n_pts, const double* i0_dev, int solo, double* rad_dev, cudaStream_t st,
+                            LowSink* low, bool force, bool* done) {
+    *done = false;
+    sr_lut* L0 = luts[0];
+    const int n_los = steps->n_los;
+    const size_t nmax = (size_t)steps->n_steps_max;
+    long ld_min = luts[0]->row_stride;
+    bool aligned = pt0 % 4 == 0;
+    for (int m = 0; m < steps->n_gas; m++) {
+        aligned = aligned && luts[m]->row_stride % 4 == 0 && (size_t)luts[m]->g32 % 16 == 0;
+        ld_min = std::min(ld_min, luts[m]->row_stride);
+    }
+    if (!aligned || ld_min < 4 || (!low && !rad_dev)) return SR_OK;
+    if (!force && n_los < 2 * FZ_LG) return SR_OK;   // small batches: chunks cannot fill
+    GemmPlan P;
+    static const bool timing = getenv("SR_LOS_TIMING") != nullptr;
+    const auto t_plan0 = std::chrono::steady_clock::now();
+    int rc = build_fused_plan(luts, steps, P);
+    if (rc) return rc;
+    const double fill = P.slots > 0 ? P.pairs / P.slots : 0.0;
+    static const double min_fill = getenv("SR_LOS_FUSE_FILL") ? atof(getenv("SR_LOS_FUSE_FILL")) : 0.6;
+    if (timing)
+        fprintf(stderr, "[sr_los] fused plan: %d LOS, %d LOS groups, %d quads, %d chunks, fill %.3f: %.3f ms\n",
+                n_los, P.n_lg, P.n_groups, P.n_chunks, fill,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count());
+    if (!force && fill < min_fill) return SR_OK;
+    if (P.max_jp > GEMM_MAXJ)
+        return sr::fail(SR_ERR_LIMIT, "LOS: %d LUT rows per cell quad (limit %d)", P.max_jp, GEMM_MAXJ);
+    const size_t buf_bytes = (size_t)P.max_jp * (MMA_PB * sizeof(double) + sizeof(long long)) + 64 + 16;
+    const size_t smem = (size_t)FZ_LG * FZ_SP * sizeof(double) + 2 * buf_bytes + 16;
+    int dev = 0, smem_max = 0;
+    SR_CUDA(cudaGetDevice(&dev));
+    SR_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem > (size_t)smem_max) return SR_OK;
+    // LOS blocks (whole LOS groups): only the low-res sink needs a radiance workspace
+    int lg_block = P.n_lg;
+    if (low) {
+        size_t mem_free = 0, mem_total = 0;
+        if (cudaMemGetInfo(&mem_free, &mem_total) != cudaSuccess) mem_free = (size_t)32 << 30;
+        mem_free += L0->ws_rad[0].n * 8;
+        size_t rad_cap = std::min<size_t>((size_t)8 << 30, std::max<size_t>((size_t)1 << 30, mem_free / 8));
+        if (L0->ws_rad[0].n * 8 >= rad_cap / 2) rad_cap = std::min(L0->ws_rad[0].n * 8, (size_t)8 << 30);
+        lg_block = (int)std::max<size_t>(1, rad_cap / ((size_t)n_pts * 8 * FZ_LG));
+        if (const char* e = getenv("SR_LOS_BLOCK")) lg_block = std::max(1, atoi(e) / FZ_LG);
+        lg_block = std::min(lg_block, P.n_lg);
+    }
+    lg_block = std::min(lg_block, 65535);
+    // slot tables
+    std::vector<int> lg_row((size_t)P.n_lg * FZ_LG, -1), lg_i0((size_t)P.n_lg * FZ_LG, -1);
+    for (int pos = 0; pos < n_los; pos++) {
+        const int g = pos / FZ_LG;
+        lg_i0[pos] = P.perm[pos];
+        lg_row[pos] = low ? (g % lg_block) * FZ_LG + pos % FZ_LG : P.perm[pos];
+    }
+    SR_CUDA(L0->g_lgrow.upload(lg_row.data(), lg_row.size(), st));
+    SR_CUDA(L0->g_lgi0.upload(lg_i0.data(), lg_i0.size(), st));
+    SR_CUDA(L0->g_lgchunk.upload(P.lg_chunk.data(), P.lg_chunk.size(), st));
+    FuseArgs fa;
+    if (P.n_chunks > 0) {
+        SR_CUDA(L0->g_prog.upload(reinterpret_cast<const char*>(P.prog.data()),
+                                  P.prog.size() * sizeof(ProgEntry), st));
+        SR_CUDA(L0->g_rowptr.upload(P.rowptr.data(), P.rowptr.size(), st));
+        SR_CUDA(L0->g_ntau.upload(P.ntau.data(), P.ntau.size(), st));
+        SR_CUDA(L0->g_ntot.upload(P.ntot.data(), P.ntot.size(), st));
+        SR_CUDA(L0->g_cgrp.upload(P.chunk_grp.data(), P.chunk_grp.size(), st));
+        SR_CUDA(L0->g_cpair.upload(P.chunk_pair.data(), P.chunk_pair.size(), st));
+        SR_CUDA(L0->g_cslot.upload(P.chunk_slot.data(), P.chunk_slot.size(), st));
+        SR_CUDA(L0->g_cmeta.upload(reinterpret_cast<const int*>(P.chunk_meta.data()), P.chunk_meta.size() * 4, st));
+        SR_CUDA(L0->g_wfrag.ensure((size_t)P.n_chunks * P.max_jp * MMA_PB));
+        PackArgs pa;
+        pa.prog = reinterpret_cast<const ProgEntry*>(L0->g_prog.p);
+        pa.grp_ntot = L0->g_ntot.p;
+        pa.chunk_grp = L0->g_cgrp.p;
+        pa.chunk_pair = L0->g_cpair.p;
+        pa.W = la.W;
+        pa.wfrag = L0->g_wfrag.p;
+        pa.n_pairs_tot = (long)n_los * (long)nmax;
+        pa.n_sets_max = la.n_sets_max;
+        pa.max_jp = P.max_jp;
+        pa.n_chunks = P.n_chunks;
+        pa.gas_mask = ~0u;
+        pa.grp_ntau = L0->g_ntau.p;
+        for (int m = 0; m < MAX_GAS; m++) pa.emis[m] = m < steps->n_gas ? luts[m]->emis_mask : ~0ull;
+        const long n_el = (long)P.n_chunks * P.max_jp * MMA_PB;
+        SR_LAUNCH(k_pack_wfrag, (unsigned)((n_el + 255) / 256), 256, 0, st, pa);
+    }
+    fa.rowptr = L0->g_rowptr.p;
+    fa.chunk_meta = reinterpret_cast<const int4*>(L0->g_cmeta.p);
+    fa.chunk_slot = L0->g_cslot.p;
+    fa.wfrag = L0->g_wfrag.p;
+    fa.lg_chunk = L0->g_lgchunk.p;
+    fa.lg_row = L0->g_lgrow.p;
+    fa.lg_i0row = L0->g_lgi0.p;
+    fa.max_jp = P.max_jp;
+    fa.pt0 = pt0;
+    fa.n_pts = n_pts;
+    fa.ld_min = ld_min;
+    fa.io_stride = n_pts;
+    fa.io_off = 0;
+    fa.i0 = i0_dev;
+    fa.solo = solo;
+    fa.dbg = getenv("SR_LOS_FDBG") ? atoi(getenv("SR_LOS_FDBG")) : 0;
+    fa.flags = L0->flags.p;
+    static const int ld = getenv("SR_MMA_LD") ? atoi(getenv("SR_MMA_LD")) : 0;
+    const unsigned n_tiles = (unsigned)((n_pts + FZ_TP - 1) / FZ_TP);
+    if (low) {
+        SR_CUDA(L0->ws_rad[0].ensure((size_t)lg_block * FZ_LG * n_pts));
+        SR_CUDA(L0->ws_low.ensure((size_t)lg_block * FZ_LG * low->n_chan));
+        SR_CUDA(L0->g_scat.upload(P.perm.data(), P.perm.size(), st));
+    }
+    for (int g0 = 0; g0 < P.n_lg; g0 += lg_block) {
+        const int ng = std::min(lg_block, P.n_lg - g0);
+        const int nl = std::min(n_los - g0 * FZ_LG, ng * FZ_LG);
+        fa.lg0 = g0;
+        fa.rad = low ? L0->ws_rad[0].p : rad_dev;
+        double rowpairs = 0.0;
+        for (int g = g0; g < g0 + ng; g++) rowpairs += P.lg_rowpairs[g];
+        {
+            sr::ProfScope ps(SR_PROF_LOS_FUSED, 2.0 * rowpairs * (double)n_pts, st);
+            dim3 grid((unsigned)ng, n_tiles);
+            rc = ld == 1 ? fused_launch_t<1>(grid, smem, st, fa)
+                         : ld == 2 ? fused_launch_t<2>(grid, smem, st, fa) : fused_launch_t<0>(grid, smem, st, fa);
+            if (rc) return rc;
+        }
+        if (low) {
+            const sr_channels ch{low->n_chan, low->centre_dev, low->width_dev, low->n_sigma, low->units};
+            {
+                sr::ProfScope ps(SR_PROF_CONV, 8.0 * (double)nl * (double)n_pts, st);
+                rc = sr_convolve_channels_dev(low->grid_dev, n_pts, L0->ws_rad[0].p, nl, &ch, L0->ws_low.p, st);
+                if (rc) return rc;
+            }
+            const long n_el = (long)nl * low->n_chan;
+            SR_LAUNCH(k_scatter_rows, (unsigned)((n_el + 255) / 256), 256, 0, st, L0->ws_low.p,
+                      L0->g_scat.p + (size_t)g0 * FZ_LG, nl, low->n_chan, low->low_dev);
+        }
+    }
+    *done = true;
+    return SR_OK;
+}
+
+extern "C" {
+
 static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, long n_pts,
                       const double* i0_dev, int solo, double* rad_dev, double* tau_dev,
                       double* src_dev, cudaStream_t st, int emit_j = 0, HostSink* sink = nullptr,
@@ -1400,6 +1998,8 @@ static int los_launch(sr_lut* const* luts, const sr_los_steps* steps, long pt0, 
     else SR_CUDA(cudaEventCreateWithFlags(&L0->busy, cudaEventDisableTiming));
     const int rc = los_launch_locked(luts, steps, pt0, n_pts, i0_dev, solo, rad_dev, tau_dev, src_dev,
                                      st, emit_j, sink, low, jac);
+    // a call that failed on the host must not leave its device flag word behind for the next one
+    if (rc != SR_OK && L0->flags.p) cudaMemsetAsync(L0->flags.p, 0, sizeof(int), st);
     cudaEventRecord(L0->busy, st);
     return rc;
 }
@@ -1461,6 +2061,14 @@ static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, lon
         }
         return SR_OK;
     }
+    // ---- v4: product and recursion fused in one kernel (k_los_fused2) when the batch is large
+    // enough to fill its chunks; otherwise (and for Jacobians, host sinks, materialised layers) v3
+    if (!tau_dev && !jac && !sink && ver != 3) {
+        bool done = false;
+        rc = los_launch_fused(luts, steps, la, pt0, n_pts, i0_dev, solo, rad_dev, st, low, ver == 4, &done);
+        if (rc) return rc;
+        if (done) return SR_OK;
+    }
     // ---- v3: grouped tensor-path product into layer arrays, then the streaming recursion ------
     // blocking: the layer scratch (16 B per pair and point) stays below the budget
     // Bigger LOS blocks mean more (LOS, step) pairs per LUT cell quad, i.e. fuller 16-pair chunks
@@ -1482,9 +2090,19 @@ static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, lon
     if (const char* e = getenv("SR_LOS_SCRATCH_MB")) budget = (size_t)std::max(1L, atol(e)) << 20;
     long chunk_pts = n_pts;
     int nl_block = n_los;
+    // float32 layer scratch: tau and J are rounded to the LUT's own storage precision between the
+    // product and the recursion; every sum, exponential and the recursion itself stay FP64.  It
+    // halves the HBM round trip of the layers: k_los_mma is no longer slowed down by its own stores
+    // (0.66 -> 0.78 of the FP64 peak) and k_los_layers becomes FP64-bound.  Hi-res radiances move
+    // by <= ~1e-7 relative, channel integrals by ~1e-9 (tests/test_gpu_los.py).  Default: on for the
+    // low-resolution forward sink (results are channel integrals), off wherever hi-res radiances
+    // or derivative spectra are returned (finite-difference checks and retrievals want a forward
+    // model that is smooth to rounding).  SR_LOS_F32=0 / 1 forces it off / on for every path.
+    const int f32_env = getenv("SR_LOS_F32") ? atoi(getenv("SR_LOS_F32")) : -1;   // (per call: tests switch it)
+    const bool lay_f32 = !tau_dev && (f32_env > 0 || (f32_env < 0 && low && !jac));
     if (!tau_dev) {
         const long min_chunk = std::min<long>(n_pts, 65536);
-        const size_t lay_b = jac_multi ? 32 : 16;   // scratch bytes per (pair, point)
+        const size_t lay_b = (jac_multi ? 32 : 16) / (lay_f32 ? 2 : 1);   // scratch bytes per (pair, point)
         if ((size_t)n_los * nmax * lay_b * (size_t)min_chunk <= budget) {
             chunk_pts = (long)(budget / ((size_t)n_los * nmax * lay_b));
         } else {
@@ -1576,6 +2194,7 @@ static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, lon
         ma.src_out = src_dev;
         ma.mode = emit_j;
         ma.keep = 0;
+        ma.f32 = 0;
         dim3 grid((unsigned)P.n_chunks, (unsigned)((n_pts + TILE - 1) / TILE));
         const bool vec = rows_aligned && pt0 % 4 == 0 && n_pts % 4 == 0 &&
                          ((size_t)tau_dev | (size_t)src_dev) % 32 == 0;
@@ -1587,8 +2206,8 @@ static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, lon
     // the whole register file busy and the recursion needs >= 4 CTAs per SM of loads in flight.)
     const size_t blk_pairs = (size_t)nl_block * nmax;
     const long ld_lay = (chunk_pts + 3) / 4 * 4;   // scratch rows: 32-byte aligned for any chunk size
-    SR_CUDA(L0->ws_tau.ensure(blk_pairs * ld_lay));
-    SR_CUDA(L0->ws_src.ensure(blk_pairs * ld_lay));
+    SR_CUDA(L0->ws_tau.ensure(lay_f32 ? (blk_pairs * ld_lay + 1) / 2 : blk_pairs * ld_lay));
+    SR_CUDA(L0->ws_src.ensure(lay_f32 ? (blk_pairs * ld_lay + 1) / 2 : blk_pairs * ld_lay));
     cudaEvent_t buf_free[2] = {nullptr, nullptr};   // host sink: copies of a radiance buffer done
     if (sink) {
         if (!L0->copy_stream)
@@ -1642,6 +2261,7 @@ static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, lon
                     ma.src_out = L0->ws_src.p;
                     ma.mode = 1;
                     ma.keep = l2keep;
+                    ma.f32 = lay_f32 ? 1 : 0;
                     dim3 grid((unsigned)n_ch, (unsigned)((np + TILE - 1) / TILE));
                     ma.wfrag = L0->g_wfrag.p;
                     int code;
@@ -1653,7 +2273,7 @@ static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, lon
                     if (jac_multi) {
                         ma.wfrag = L0->g_wfrag_g.p;
                         ma.tau_out = L0->ws_tau_g.p;
-                        ma.src_out = L0->ws_src_g.p;
+                        ma.src_out = L0->ws_src_g.p;   // (float32 like the first pair when lay_f32)
                         code = mma_launch(rows_aligned && (pt0 + c0) % 4 == 0, grid, smem, st, ma);
                         if (code) return code;
                     }
@@ -1668,14 +2288,15 @@ static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, lon
                                              jac_multi ? L0->ws_src_g.p : nullptr,
                                              L0->g_dfrac.p + (size_t)l0 * nmax * jac->n_par,
                                              jac->n_par, la.n_steps + l0, nl, steps->n_steps_max, np,
-                                             i0_blk, solo, rad_blk, jac_blk, st, n_pts, c0, ld_lay);
+                                             i0_blk, solo, rad_blk, jac_blk, st, n_pts, c0, ld_lay,
+                                             lay_f32 ? 1 : 0);
                 } else {
                     double pairs = 0.0;
                     for (int l = l0; l < l0 + nl; l++) pairs += steps->n_steps[l];
-                    sr::ProfScope ps(SR_PROF_LOS_LAYERS, (16.0 * pairs + 8.0 * nl) * (double)np, st);
+                    sr::ProfScope ps(SR_PROF_LOS_LAYERS, ((lay_f32 ? 8.0 : 16.0) * pairs + 8.0 * nl) * (double)np, st);
                     code = layers_launch(L0->ws_tau.p, L0->ws_src.p, la.n_steps + l0, nl,
                                          steps->n_steps_max, np, i0_blk, solo, rad_blk, st, 1, n_pts,
-                                         c0, ld_lay, l2keep);
+                                         c0, ld_lay, l2keep, lay_f32 ? 1 : 0);
                 }
                 if (code) return code;
                 if (sink) {

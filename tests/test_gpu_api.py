@@ -193,7 +193,7 @@ def test_inversion_fast_limb_forward_and_jacobian(world):
     sims_f, rt_f, _ = smm.radtrans(inputs, planet, world["lines"], pixels, sp_gri=sp,
                                    radtran_opt=opt, LUTopt=dict(LUTopt))
     for a, b in zip(sims, sims_f):
-        assert rel_err(a.spectrum, b.spectrum) < 1e-12
+        assert rel_err(a.spectrum, b.spectrum) < 1e-7     # radtrans' low-res sink keeps its layers in float32 (~1e-9)
     # node at 300 km lies below both tangent heights (first node: mask = 1 below it, so it is
     # still involved through its triangle up to 500 km); the 1100 km node only feeds the top
     jac = bs.build_jacobian()

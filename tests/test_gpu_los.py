@@ -87,6 +87,15 @@ def test_los_blocking_and_chunking_are_invisible(case, monkeypatch):
     monkeypatch.setenv("SR_LOS_VER", "1")
     v1 = eng.los_rt_lut([case["lut"]], case["steps"]).cpu().numpy()
     assert rel_err(v1, base) < 1e-12
+    monkeypatch.delenv("SR_LOS_VER")
+    # float32 layer scratch (the default of the low-res forward sink only): tau and J rounded to the
+    # LUT's storage precision between the two kernels move a hi-res radiance by < 1e-6
+    monkeypatch.setenv("SR_LOS_F32", "1")
+    f32 = eng.los_rt_lut([case["lut"]], case["steps"]).cpu().numpy()
+    assert 0 < rel_err(f32, base) < 1e-6
+    monkeypatch.setenv("SR_LOS_BLOCK", "4")
+    monkeypatch.setenv("SR_LOS_CHUNK", "768")
+    assert np.array_equal(eng.los_rt_lut([case["lut"]], case["steps"]).cpu().numpy(), f32)
 
 
 def test_lowres_fused_matches_hires_then_convolve(case, oracle, monkeypatch):
@@ -100,6 +109,9 @@ def test_lowres_fused_matches_hires_then_convolve(case, oracle, monkeypatch):
     widths = np.full(7, 0.08)
     hi = eng.los_rt_lut([case["lut"]], case["steps"])
     ref = eng.convolve_lowres(gdev, hi, centres, widths).cpu().numpy()
+    got = eng.los_rt_lut_lowres([case["lut"]], case["steps"], gdev, centres, widths).cpu().numpy()
+    assert rel_err(got, ref) < 1e-8       # default float32 layer scratch of the low-res sink
+    monkeypatch.setenv("SR_LOS_F32", "0")
     got = eng.los_rt_lut_lowres([case["lut"]], case["steps"], gdev, centres, widths).cpu().numpy()
     assert np.array_equal(got, ref)
     monkeypatch.setenv("SR_LOS_BLOCK", "4")          # 6 LOS -> blocks of 4 + 2
@@ -200,3 +212,63 @@ def test_lut_errors(case):
     with pytest.raises(SpectrobotError) as e:
         eng.los_rt_lut([case["lut"]], bad)
     assert e.value.code == SR_ERR_LUT
+
+
+def test_fused_kernel_matches_two_kernel_path(case, oracle, monkeypatch):
+    """k_los_fused2 (SR_LOS_VER=4: product + recursion in one kernel, LOS groups in shared memory)
+    against the k_los_mma -> k_los_layers pair (SR_LOS_VER=3) and the oracle: plain, sub-window with
+    a ragged tile, initial intensity, solo absorption, emission mask, low-res sink, two gases."""
+    eng, st, torch, S = case["engine"], case["st"], case["torch"], case["S"]
+    g = case["grid"]
+    n_los, n_grid = st["temp"].shape[0], len(g)
+    # more LOS than one LOS group holds, in an order that is NOT sorted (the planner sorts them)
+    rep = np.array([3, 0, 5, 1, 4, 2] * 13)[:70]
+    steps = eng.LosSteps(st["n_steps"][rep], st["temp"][rep], st["pres"][rep], st["column"][:, rep],
+                         st["tvib"][:, :, rep])
+    i0 = torch.tensor(np.linspace(1e-8, 4e-7, 70)[:, None] * np.ones((1, n_grid)), device="cuda")
+
+    monkeypatch.setenv("SR_LOS_F32", "0")    # structural comparison: FP64 layer scratch in v3
+
+    def run(ver, **kw):
+        monkeypatch.setenv("SR_LOS_VER", str(ver))
+        out = eng.los_rt_lut([case["lut"]], steps, **kw)
+        monkeypatch.delenv("SR_LOS_VER")
+        return out.cpu().numpy()
+    base = run(3)
+    fused = run(4)
+    assert rel_err(fused, base) < 1e-12
+    ref = oracle.los_rt([case["olut"]], st["n_steps"], st["temp"], st["pres"], st["column"], st["tvib"])
+    assert rel_err(fused, ref[rep]) < TOL_RAD
+    assert rel_err(run(4, pt0=1000, n_pts=3001), base[:, 1000:4001]) < 1e-12       # ragged last tile
+    assert rel_err(run(4, i0=i0), run(3, i0=i0)) < 1e-12
+    assert rel_err(run(4, i0=i0, solo_absorption=True), run(3, i0=i0, solo_absorption=True)) < 1e-12
+    case["lut"].set_emission_mask(0b101)
+    try:
+        assert rel_err(run(4), run(3)) < 1e-12
+    finally:
+        case["lut"].set_emission_mask(None)
+    # low-res sink: LOS blocks of one LOS group, rows scattered back to the caller's order
+    gdev = torch.as_tensor(g, device="cuda")
+    centres = np.linspace(g[0] + 0.3, g[-1] - 0.3, 7)
+    widths = np.full(7, 0.08)
+    monkeypatch.setenv("SR_LOS_VER", "3")
+    low3 = eng.los_rt_lut_lowres([case["lut"]], steps, gdev, centres, widths).cpu().numpy()
+    monkeypatch.setenv("SR_LOS_VER", "4")
+    low4 = eng.los_rt_lut_lowres([case["lut"]], steps, gdev, centres, widths).cpu().numpy()
+    monkeypatch.setenv("SR_LOS_BLOCK", "64")
+    low4b = eng.los_rt_lut_lowres([case["lut"]], steps, gdev, centres, widths).cpu().numpy()
+    monkeypatch.delenv("SR_LOS_BLOCK")
+    monkeypatch.delenv("SR_LOS_VER")
+    assert rel_err(low4, low3) < 1e-12 and np.array_equal(low4b, low4)
+    # second, LTE-unidentified gas
+    lines2 = S.line_table(120, 2996.0, 3005.0, n_levels=1, seed=8, q296=107.12, iso_ratio=0.986544)
+    ls2 = eng.LineSet(lines2, g, 27.994915, 1)
+    lut2 = eng.Lut(ls2.gcoeff_cells_f32(case["cells"]), case["cells"], 5, 1, 0.986544, level_energies=None)
+    col = np.concatenate([st["column"][:, rep], 0.01 * st["column"][:, rep]], axis=0)
+    st2 = eng.LosSteps(st["n_steps"][rep], st["temp"][rep], st["pres"][rep], col, None)
+    monkeypatch.setenv("SR_LOS_VER", "3")
+    two3 = eng.los_rt_lut([case["lut"], lut2], st2).cpu().numpy()
+    monkeypatch.setenv("SR_LOS_VER", "4")
+    two4 = eng.los_rt_lut([case["lut"], lut2], st2).cpu().numpy()
+    monkeypatch.delenv("SR_LOS_VER")
+    assert rel_err(two4, two3) < 1e-12

@@ -163,16 +163,16 @@ def test_radtrans_3d_options_and_single_rads(world, oracle, tmp_path):
     _, rt2, single2 = smm.radtrans(inputs, planet, world["lines"], mk(), track_levels=allev, **kw)
     lev_sum = sum(np.array([single2[('CH4', 'iso_1', lev)][t].spectrum for t in sorted(rt2)])
                   for lev in allev[('CH4', 'iso_1')])
-    assert rel_err(lev_sum, tot) < 1e-10
+    assert rel_err(lev_sum, tot) < 1e-7      # (float32 layer scratch of the low-res sink: ~1e-9 per run)
     assert np.all(np.array([single[('CH4', 'iso_1', 'lev_01')][t].spectrum for t in sorted(rt)]) >= 0)
     # hi-res on disk + oracle LOS integral on the same step tables
     kw["save_hires"] = True
     sims_h, rt_h, _ = smm.radtrans(inputs, planet, world["lines"], mk(), nome_inv='hr', **kw)
-    assert rel_err(np.array([s.spectrum for s in sims_h]), a) < 1e-10
+    assert rel_err(np.array([s.spectrum for s in sims_h]), a) < 1e-7    # hi-res path: FP64 layers; low-res sink: float32
     nsp, hires = pickle.load(open(str(tmp_path / 'hires_radtran_hr.pic'), 'rb'))
     assert nsp == 0 and sorted(hires) == sorted(rt_h)
     low = oracle.convolve_to_grid_from_irregular(world["sp"].grid, hires['LOS01'].spectrum, centres, widths)
-    assert rel_err(rt_h['LOS01'].spectrum, low) < 1e-9
+    assert rel_err(rt_h['LOS01'].spectrum, low) < 1e-7
     pix = sorted(mk(), key=lambda p: p.limb_tg_alt)
     loss = [pix[0].low_LOS(), pix[0].LOS(), pix[0].up_LOS()]
     gi, steps, _ = smm.los_step_tables_device(loss, planet, ssps=[pix[0].sub_solar_point()] * 3, **opt)
@@ -218,13 +218,13 @@ def test_nm_observation_through_radtrans(world, oracle):
     x = world["sp"].grid
     want = oracle.convolve_to_grid_from_irregular((1.e7 / x)[::-1], (hi.spectrum * x ** 2 * 1e-7)[::-1],
                                                  c_nm, w_nm) * 1e-3
-    assert rel_err(rt['LOS01'].spectrum, want) < 1e-9
+    assert rel_err(rt['LOS01'].spectrum, want) < 1e-7
     low = hi.hires_to_lowres(pix_nm[0].observation, spectral_widths=w_nm)
-    assert rel_err(low.spectrum, want) < 1e-9 and low.units == 'Wm2'
+    assert rel_err(low.spectrum, want) < 1e-7 and low.units == 'Wm2'
     # micron axis: the same channels, per micron
     pix_um = S.vims_pixels([600.0], channels=c_nm * 1e-3, widths=w_nm * 1e-3, units='mum', obs_units='Wm2')
     _, rt_um, _ = smm.radtrans(inputs, planet, world["lines"], pix_um, **kw)
-    assert rel_err(rt_um['LOS01'].spectrum, want * 1e3) < 1e-9
+    assert rel_err(rt_um['LOS01'].spectrum, want * 1e3) < 1e-7
     pix_hz = S.vims_pixels([600.0], channels=c_cm * 3e10, widths=w_cm * 3e10, units='hz')
     with pytest.raises(ValueError):
         smm.radtrans(inputs, planet, world["lines"], pix_hz, **kw)
