@@ -420,14 +420,14 @@ __global__ void __launch_bounds__(256, 6) k_los_layers_f32(const __grid_constant
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
-            I0 = srdev::layer_update_j(I0, (double)t[u].x, (double)s[u].x, solo);
-            I1 = srdev::layer_update_j(I1, (double)t[u].y, (double)s[u].y, solo);
+            I0 = srdev::layer_update_j_f32in(I0, (double)t[u].x, (double)s[u].x, solo);
+            I1 = srdev::layer_update_j_f32in(I1, (double)t[u].y, (double)s[u].y, solo);
         }
     }
     for (; k < ns; k++) {
         const float2 t = ld2(tp + (size_t)k * ls), s = ld2(sp + (size_t)k * ls);
-        I0 = srdev::layer_update_j(I0, (double)t.x, (double)s.x, solo);
-        I1 = srdev::layer_update_j(I1, (double)t.y, (double)s.y, solo);
+        I0 = srdev::layer_update_j_f32in(I0, (double)t.x, (double)s.x, solo);
+        I1 = srdev::layer_update_j_f32in(I1, (double)t.y, (double)s.y, solo);
     }
     double* o = r.rad + (size_t)l * r.io_stride + r.io_off + p0;
     __stcs(o, I0);

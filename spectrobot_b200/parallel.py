@@ -119,7 +119,8 @@ def allreduce_lowres(low):
 def allgather_steps(local, n_total, rank, n_ranks, device=None):
     """Step tables (engine.LosSteps) built by every rank for its shard_range block of the LOS ->
     the tables of all n_total LOS on every rank (the step builder is sharded by LOS, the LOS
-    integral by wavenumber).  Tables are padded to the widest rank before the exchange."""
+    integral by wavenumber).  One all_gather per table on the device (NVLink), tables padded to the
+    widest rank and the longest block; the result comes back through pinned host memory."""
     import torch
     import torch.distributed as dist
     from . import engine
@@ -129,23 +130,38 @@ def allgather_steps(local, n_total, rank, n_ranks, device=None):
     w = torch.tensor([local.n_steps_max], dtype=torch.int64, device=dev)
     dist.all_reduce(w, op=dist.ReduceOp.MAX)
     w = int(w.item())
+    sizes = [shard_range(n_total, r, n_ranks) for r in range(n_ranks)]
+    nmax = max(e - b for b, e in sizes)
 
-    def padw(a, fill):
-        if a.shape[-1] == w:
-            return a
-        out = np.full(a.shape[:-1] + (w,), fill, dtype=a.dtype)
-        out[..., :a.shape[-1]] = a
-        return out
+    def gather(a, los_axis, fill):
+        """numpy [..., n_los_local, w_local] -> numpy [..., n_total, w] (LOS axis at los_axis)"""
+        t = torch.as_tensor(a).to(dev)
+        if los_axis != 0:
+            t = t.movedim(los_axis, 0)
+        shape = (nmax,) + tuple(t.shape[1:-1]) + ((w,) if a.ndim > 1 else ())
+        pad = torch.full(shape, fill, dtype=t.dtype, device=dev)
+        if a.ndim > 1:
+            pad[:t.shape[0], ..., :t.shape[-1]] = t
+        else:
+            pad[:t.shape[0]] = t
+        out = torch.empty((n_ranks * shape[0],) + shape[1:], dtype=t.dtype, device=dev)
+        dist.all_gather_into_tensor(out, pad)
+        out = out.view((n_ranks,) + shape)
+        full = torch.cat([out[r, :e - b] for r, (b, e) in enumerate(sizes)], dim=0)
+        if los_axis != 0:
+            full = full.movedim(0, los_axis)
+        full = full.contiguous()
+        if full.is_cuda:
+            host = torch.empty(full.shape, dtype=full.dtype, pin_memory=True)
+            host.copy_(full)
+            return host.numpy()
+        return full.numpy()
 
-    def gather(a, los_axis):   # numpy [..., n_los_local, ...] -> [..., n_total, ...]
-        t = torch.as_tensor(np.ascontiguousarray(np.moveaxis(a, los_axis, 0))).to(dev)
-        return np.moveaxis(gather_rows(t, n_total, rank, n_ranks).cpu().numpy(), 0, los_axis)
-
-    n_steps = gather(local.n_steps, 0)
-    temp = gather(padw(local.temp, 100.0), 0)
-    pres = gather(padw(local.pres, 1e-6), 0)
-    col = gather(padw(local.column, 0.0), 1)
-    tvib = None if local.tvib is None else gather(padw(local.tvib, 100.0), 2)
+    n_steps = gather(local.n_steps, 0, 0)
+    temp = gather(local.temp, 0, 100.0)
+    pres = gather(local.pres, 0, 1e-6)
+    col = gather(local.column, 1, 0.0)
+    tvib = None if local.tvib is None else gather(local.tvib, 2, 100.0)
     return engine.LosSteps(n_steps, temp, pres, col, tvib)
 
 
