@@ -82,14 +82,15 @@ struct DevBuf {  // RAII device buffer
 // Stream-ordered scratch (cudaMallocAsync): freed blocks stay in the device's default pool instead
 // of going back to the driver at every synchronisation, so per-call scratch costs no cudaMalloc.
 inline void pool_keep() {
-    static bool once = false;
-    if (once) return;
+    static std::atomic<unsigned long long> done{0};   // one bit per device (a process may use several)
     int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    if (done.load() & (1ull << dev)) return;
     cudaMemPool_t pool;
     unsigned long long keep = ~0ull;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    once = true;
+    done.fetch_or(1ull << dev);
 }
 
 template <typename T>

@@ -2079,9 +2079,12 @@ static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, lon
     mem_free += L0->ws_tau.n * 8 + L0->ws_src.n * 8 + L0->ws_tau_g.n * 8 + L0->ws_src_g.n * 8 +
                 L0->ws_jac.n * 8 + L0->ws_rad[0].n * 8 + L0->ws_rad[1].n * 8;   // our own, reusable
     size_t budget = std::min<size_t>((size_t)32 << 30, std::max<size_t>((size_t)1 << 30, mem_free / 4));
-    size_t rad_cap = std::min<size_t>((size_t)8 << 30, std::max<size_t>((size_t)1 << 30, mem_free / 8));
+    // radiance workspace of a LOS block: with the float32 layer scratch the block size is limited by
+    // this buffer, and bigger blocks fill the 16-pair chunks better
+    static const size_t rad_max = (size_t)(getenv("SR_LOS_RADCAP_MB") ? atol(getenv("SR_LOS_RADCAP_MB")) : 16384) << 20;
+    size_t rad_cap = std::min<size_t>(rad_max, std::max<size_t>((size_t)1 << 30, mem_free / 6));
     size_t jac_cap = std::min<size_t>((size_t)48 << 30, std::max<size_t>((size_t)1 << 30, mem_free / 3));
-    if (L0->ws_rad[0].n * 8 >= rad_cap / 2) rad_cap = std::min(L0->ws_rad[0].n * 8, (size_t)8 << 30);
+    if (L0->ws_rad[0].n * 8 >= rad_cap / 2) rad_cap = std::min(L0->ws_rad[0].n * 8, rad_max);
     if (L0->ws_jac.n * 8 >= jac_cap / 2) jac_cap = std::min(L0->ws_jac.n * 8, (size_t)48 << 30);
     // sticky: a workspace that already holds at least half of what a fresh budget would give is
     // used as it is, so that calls do not reallocate tens of GiB whenever the free memory moves
