@@ -410,6 +410,21 @@ __global__ void __launch_bounds__(256, 6) k_los_layers_f32(const __grid_constant
     const float* __restrict__ sp = reinterpret_cast<const float*>(r.src) + col0;
     const bool solo = r.solo != 0;
     auto ld2 = [&](const float* p) { return __ldcs(reinterpret_cast<const float2*>(p)); };
+    const unsigned live = __activemask();   // (threads beyond the window have left; ns is uniform)
+    // one (step, two points) update; the form of the exponential is chosen per warp
+    auto upd = [&](float2 t, float2 s) {
+        const float m = fmaxf(fabsf(t.x), fabsf(t.y));
+        if (__all_sync(live, m < 1.0e-2f)) {
+            I0 = srdev::layer_update_j_small(I0, (double)t.x, (double)s.x, solo);
+            I1 = srdev::layer_update_j_small(I1, (double)t.y, (double)s.y, solo);
+        } else if (__all_sync(live, m < 0.34f)) {
+            I0 = srdev::layer_update_j_medium(I0, (double)t.x, (double)s.x, solo);
+            I1 = srdev::layer_update_j_medium(I1, (double)t.y, (double)s.y, solo);
+        } else {
+            I0 = srdev::layer_update_j_f32in(I0, (double)t.x, (double)s.x, solo);
+            I1 = srdev::layer_update_j_f32in(I1, (double)t.y, (double)s.y, solo);
+        }
+    };
     int k = 0;
     for (; k + UNROLL <= ns; k += UNROLL) {
         float2 t[UNROLL], s[UNROLL];
@@ -419,16 +434,9 @@ __global__ void __launch_bounds__(256, 6) k_los_layers_f32(const __grid_constant
             s[u] = ld2(sp + (size_t)(k + u) * ls);
         }
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            I0 = srdev::layer_update_j_f32in(I0, (double)t[u].x, (double)s[u].x, solo);
-            I1 = srdev::layer_update_j_f32in(I1, (double)t[u].y, (double)s[u].y, solo);
-        }
+        for (int u = 0; u < UNROLL; u++) upd(t[u], s[u]);
     }
-    for (; k < ns; k++) {
-        const float2 t = ld2(tp + (size_t)k * ls), s = ld2(sp + (size_t)k * ls);
-        I0 = srdev::layer_update_j_f32in(I0, (double)t.x, (double)s.x, solo);
-        I1 = srdev::layer_update_j_f32in(I1, (double)t.y, (double)s.y, solo);
-    }
+    for (; k < ns; k++) upd(ld2(tp + (size_t)k * ls), ld2(sp + (size_t)k * ls));
     double* o = r.rad + (size_t)l * r.io_stride + r.io_off + p0;
     __stcs(o, I0);
     if (ok1) __stcs(o + 1, I1);
