@@ -213,14 +213,25 @@ struct IntArgs {
     double* dfrac;    // [n_los][n_steps_max][n_par]
 };
 
-__global__ void k_steps_integrals(IntArgs a) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+// Threads = (step k, task lane ty) of one LOS.  The integrals of a step are independent tasks -
+// air column, Curtis-Godson T, Curtis-Godson P, one column per gas, then (they need the columns)
+// one vibrational temperature per (gas, level) and one derivative per parameter - and the lanes of
+// a step share them round-robin, with the columns and T passed through shared memory.
+constexpr int INT_TX = 32;    // steps per block
+constexpr int INT_TY = 8;     // task lanes per step
+
+__global__ void __launch_bounds__(INT_TX * INT_TY) k_steps_integrals(IntArgs a) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int k = blockIdx.x * INT_TX + tx;
     const int l = blockIdx.y;
-    if (k >= a.n_steps_max) return;
     const AtmDev& A = a.A;
-    const size_t sk = (size_t)l * a.n_steps_max + k;
+    __shared__ double s_col[MAX_GAS_ST][INT_TX];
+    __shared__ double s_air[INT_TX], s_ct[INT_TX], s_cp[INT_TX];
+    const bool in_table = k < a.n_steps_max;
+    const size_t sk = (size_t)l * a.n_steps_max + (in_table ? k : 0);
     const size_t nls = (size_t)a.n_los * a.n_steps_max;
-    if (k >= min(a.n_steps[l], a.n_steps_max)) {   // padding, as LineOfSight.step_tables fills it
+    const bool real = in_table && k < min(a.n_steps[l], a.n_steps_max);
+    if (in_table && !real && ty == 0) {   // padding, as LineOfSight.step_tables fills it
         a.temp[sk] = 100.0;
         a.pres[sk] = 1.e-6;
         for (int m = 0; m < A.n_gas; m++) {
@@ -229,23 +240,11 @@ __global__ void k_steps_integrals(IntArgs a) {
                 a.tvib[((size_t)m * A.n_sets_max + s) * nls + sk] = 100.0;
         }
         for (int q = 0; q < A.n_par; q++) a.dfrac[sk * A.n_par + q] = 0.0;
-        return;
     }
-    const int ia = a.bounds[sk * 2], ie = a.bounds[sk * 2 + 1];
+    const int ia = real ? a.bounds[sk * 2] : 0, ie = real ? a.bounds[sk * 2 + 1] : 0;
     const size_t o = (size_t)l * a.n_pts_max;
     const double* __restrict__ nd = a.nd + o;
     const double* __restrict__ x = a.x + o;
-    // air column (curgod_fort_1), Curtis-Godson T and P (curgod_fort_4 with vmr = 1)
-    double air = 0.0, ct = 0.0, cp = 0.0;
-    for (int i = ia; i < ie; i++) {
-        const double dx = x[i + 1] - x[i];
-        air += srdev::curgod_seg1(nd[i], nd[i + 1], dx);
-        ct += srdev::curgod_seg4(nd[i], nd[i + 1], 1.0, 1.0, a.T[o + i], a.T[o + i + 1], dx);
-        cp += srdev::curgod_seg4(nd[i], nd[i + 1], 1.0, 1.0, a.P[o + i], a.P[o + i + 1], dx);
-    }
-    const double t_cg = ct / air;
-    a.temp[sk] = t_cg;
-    a.pres[sk] = cp / air;
     auto prof = [&](const double* __restrict__ table, int i) {   // profile value at sample point i
         return interp_at(A.z, table + (size_t)a.band[o + i] * A.n_z, A.n_z, a.jz[o + i], a.alt[o + i]);
     };
@@ -264,22 +263,55 @@ __global__ void k_steps_integrals(IntArgs a) {
         const double w = (sz - A.sza_nodes[js]) / (A.sza_nodes[js + 1] - A.sza_nodes[js]);
         return (1.0 - w) * f0 + w * f1;
     };
-    for (int m = 0; m < A.n_gas; m++) {
-        const double* vt = A.vmr + (size_t)m * A.n_band * A.n_z;
-        double col = 0.0;
-        double v0 = prof(vt, ia);
-        for (int i = ia; i < ie; i++) {
-            const double v1 = prof(vt, i + 1);
-            col += srdev::curgod_seg2(nd[i], nd[i + 1], v0, v1, x[i + 1] - x[i]);
-            v0 = v1;
+    // ---- phase A: air column (curgod_fort_1), Curtis-Godson T and P (curgod_fort_4 with vmr = 1),
+    // gas columns (curgod_fort_2) ---------------------------------------------------------------
+    const int n_a = 3 + A.n_gas;
+    if (real)
+        for (int t = ty; t < n_a; t += INT_TY) {
+            double acc = 0.0;
+            if (t == 0) {
+                for (int i = ia; i < ie; i++) acc += srdev::curgod_seg1(nd[i], nd[i + 1], x[i + 1] - x[i]);
+                s_air[tx] = acc;
+            } else if (t == 1) {
+                for (int i = ia; i < ie; i++)
+                    acc += srdev::curgod_seg4(nd[i], nd[i + 1], 1.0, 1.0, a.T[o + i], a.T[o + i + 1], x[i + 1] - x[i]);
+                s_ct[tx] = acc;
+            } else if (t == 2) {
+                for (int i = ia; i < ie; i++)
+                    acc += srdev::curgod_seg4(nd[i], nd[i + 1], 1.0, 1.0, a.P[o + i], a.P[o + i + 1], x[i + 1] - x[i]);
+                s_cp[tx] = acc;
+            } else {
+                const int m = t - 3;
+                const double* vt = A.vmr + (size_t)m * A.n_band * A.n_z;
+                double v0 = prof(vt, ia);
+                for (int i = ia; i < ie; i++) {
+                    const double v1 = prof(vt, i + 1);
+                    acc += srdev::curgod_seg2(nd[i], nd[i + 1], v0, v1, x[i + 1] - x[i]);
+                    v0 = v1;
+                }
+                s_col[m][tx] = acc;
+                a.column[(size_t)m * nls + sk] = acc;
+            }
         }
-        a.column[(size_t)m * nls + sk] = col;
-        for (int s = 0; s < A.n_sets_max; s++) {
-            const int on = A.tvib_on[m * A.n_sets_max + s];
+    __syncthreads();
+    if (!real) return;
+    const double t_cg = s_ct[tx] / s_air[tx];
+    if (ty == 0) {
+        a.temp[sk] = t_cg;
+        a.pres[sk] = s_cp[tx] / s_air[tx];
+    }
+    // ---- phase B: vibrational temperatures (curgod_fort_3) and parameter derivatives -----------
+    const int n_tv = A.n_gas * A.n_sets_max;
+    const bool jac_ok = A.jac_gas >= 0 && A.jac_gas < A.n_gas;
+    for (int t = ty; t < n_tv + A.n_par; t += INT_TY) {
+        if (t < n_tv) {
+            const int m = t / A.n_sets_max, sidx = t - m * A.n_sets_max;
+            const double* vt = A.vmr + (size_t)m * A.n_band * A.n_z;
+            const int on = A.tvib_on[m * A.n_sets_max + sidx];
             double tv = 100.0;
             if (on == 0) tv = t_cg;
             else if (on > 0) {
-                const double* tt = A.tvib + ((size_t)m * A.n_sets_max + s) * A.n_band * A.n_sza * A.n_z;
+                const double* tt = A.tvib + ((size_t)m * A.n_sets_max + sidx) * A.n_band * A.n_sza * A.n_z;
                 double acc = 0.0, w0 = prof(vt, ia), f0 = prof_sza(tt, ia);
                 for (int i = ia; i < ie; i++) {
                     const double w1 = prof(vt, i + 1), f1 = prof_sza(tt, i + 1);
@@ -287,29 +319,29 @@ __global__ void k_steps_integrals(IntArgs a) {
                     w0 = w1;
                     f0 = f1;
                 }
-                tv = acc / col;
+                tv = acc / s_col[m][tx];
             }
-            a.tvib[((size_t)m * A.n_sets_max + s) * nls + sk] = tv;
-        }
-        if (m == A.jac_gas) {
-            for (int q = 0; q < A.n_par; q++) {
+            a.tvib[((size_t)m * A.n_sets_max + sidx) * nls + sk] = tv;
+        } else {
+            const int q = t - n_tv;
+            double out = 0.0;
+            if (jac_ok) {
+                const double col = s_col[A.jac_gas][tx];
                 const double* mk = A.masks + (size_t)q * A.n_band * A.n_z;   // per latitude box
                 double d = 0.0;
-                bool any = false;
                 double m0 = prof(mk, ia);
-                any = m0 != 0.0;
+                bool any = m0 != 0.0;
                 for (int i = ia; i < ie; i++) {
                     const double m1 = prof(mk, i + 1);
                     any = any || m1 != 0.0;
                     d += srdev::curgod_seg2(nd[i], nd[i + 1], m0, m1, x[i + 1] - x[i]);
                     m0 = m1;
                 }
-                a.dfrac[sk * A.n_par + q] = (any && col != 0.0) ? d / col : 0.0;
+                out = (any && col != 0.0) ? d / col : 0.0;
             }
+            a.dfrac[sk * A.n_par + q] = out;
         }
     }
-    if (A.jac_gas < 0 || A.jac_gas >= A.n_gas)
-        for (int q = 0; q < A.n_par; q++) a.dfrac[sk * A.n_par + q] = 0.0;
 }
 
 }  // namespace
@@ -438,7 +470,7 @@ int sr_los_steps_build_rays(const sr_atmosphere* atm, const sr_los_rays* rays, c
         ia.band = sband.p; ia.jz = sjz.p; ia.n_steps = d_nsteps.p; ia.bounds = d_bounds.p;
         ia.temp = o_temp.p; ia.pres = o_pres.p; ia.column = o_col.p; ia.tvib = o_tvib.p;
         ia.dfrac = o_dfrac.p;
-        SR_LAUNCH(k_steps_integrals, dim3((n_steps_max + 63) / 64, nl), 64, 0, st, ia);
+        SR_LAUNCH(k_steps_integrals, dim3((n_steps_max + INT_TX - 1) / INT_TX, nl), dim3(INT_TX, INT_TY), 0, st, ia);
         // copy the block into the caller's [..][n_los][n_steps_max] tables
         SR_CUDA(cudaMemcpyAsync(n_steps + l0, d_nsteps.p, sizeof(int) * nl, cudaMemcpyDeviceToHost, st));
         const size_t row = (size_t)nl * n_steps_max;
