@@ -462,11 +462,8 @@ def run_ours(args):
                      "launches": int(k["launches"]), "ms_per_launch": k["ms"] / k["launches"],
                      "flop_per_launch": k["work"] / k["launches"],
                      "share_of_step": k["ms"] / world / (args.steps * step_ms),
-                     "peak_source": "FP64 DFMA rate measured live by sr_fp64_peak (MEASURED_PEAKS.json "
-                                    "has no FP64 entry; nominal 148 SM x 128 flop/clk x 1.965 GHz = 37.2); "
-                                    "DMMA shares that pipe (profiles/r1_ubench_dmma.txt)",
-                     "algorithmic": "2 flop x non-zero LUT rows of the 4 interpolation cells per "
-                                    "(LOS, step, point)"})
+                     "peak_source": "live sr_fp64_peak (no FP64 entry in MEASURED_PEAKS.json; nominal 37.2)",
+                     "algorithmic": "2 flop x non-zero LUT rows of the 4 cells per (LOS, step, point)"})
         tr = profile_json("r2_los_traffic.json")
         if tr and not args.small:
             roof["traffic"] = tr.get("traffic_per_launch")
@@ -484,6 +481,8 @@ def run_ours(args):
                             cdev, wdev, p0, n_slab, rank, world, barrier, max_over_ranks, fp64_peak,
                             hbm_peak, all_evals)
 
+    # key order: long descriptive objects first, the headline numbers last (a reader of the tail of
+    # the line sees value / e2e / roofline.frac)
     line = {"lut_build": lut_build}
     line.update(extras)
     line.update({
@@ -494,23 +493,24 @@ def run_ours(args):
                   "e2e_equals_device_result": same, "slab_points_per_rank": int(n_slab),
                   "collectives": "all_gather(step tables), all_reduce([n_los][%d] partial sums)" % N_CHAN
                   if world > 1 else "none"},
+        "config": workload_config(args, P),
+        "cpu_baseline": None,
+        "roofline": roof,
+        "clocks": sampler.summary(),
+        "e2e": {"value": n_los / e2e_s, "unit": "LOS/s", "h2d_bytes_per_step": info["h2d"],
+                "d2h_bytes_per_step": info["d2h"], "s_per_step": e2e_s,
+                "path": "sr_los_steps_build_rays + sr_los_rt_lut_channels_dev, pageable NumPy in and out"},
         "metric": "LOS radiances/s", "value": value, "unit": "LOS/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args, P),
-        "gpu_launches": int(launches), "clocks": sampler.summary(),
-        "roofline": roof,
-        "e2e": {"value": n_los / e2e_s, "unit": "LOS/s", "h2d_bytes_per_step": info["h2d"],
-                "d2h_bytes_per_step": info["d2h"], "s_per_step": e2e_s,
-                "path": "sr_los_steps_build_rays + sr_los_rt_lut_channels_dev: pageable NumPy "
-                        "geometry in, pageable NumPy low-res spectra out (wall clock)"},
+        "data": "synthetic", "gpu_launches": int(launches),
     })
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cs = CpuSample(args, P, threads)
         v, per, reps = cs.run(args.cpu_seconds)
-        line["cpu_baseline"] = {"value": v, "unit": "LOS/s", "cores": threads, "kind": "port",
-                                "sample": cs.describe(reps)}
+        line["cpu_baseline"] = {"sample": cs.describe(reps), "kind": "port", "cores": threads,
+                                "unit": "LOS/s", "value": v}
         if "voigt" in line:
             ve, vdesc = cpu_voigt_sample(args, P, threads)
             line["voigt"]["cpu_baseline"] = {"value": ve, "unit": "evals/s", "cores": threads,

@@ -215,6 +215,17 @@ __device__ __forceinline__ double humliv_reg1_uw(double u, double w, double c2) 
     return fma(t, e, t);
 }
 
+// same in 5 FP64 instructions + MUFU: (u + 1) / den = u r + r with r = r0 (2 - den r0).  One
+// instruction fewer than the (u, w) form at the price of one more level in the dependency chain -
+// the tile kernel is bound by instruction issue, not by latency.
+__device__ __forceinline__ double humliv_reg1_u(double u, double c2) {
+    const double den = fma(u, u, c2);
+    const double r0 = rcp_approx(den);
+    const double e = fma(-den, r0, 1.0);
+    const double r = fma(r0, e, r0);
+    return fma(u, r, r);
+}
+
 __device__ __forceinline__ long long f_nint(double x) { return llround(x); }  // Fortran NINT
 
 // exp(x) and expm1(x) from ONE range reduction and ONE polynomial (layer update of the LOS

@@ -468,7 +468,6 @@ __global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
     auto half_eval = [&](const HalfRec& h, auto full) {
         constexpr bool FULL = decltype(full)::value;
         const double xs = h.xs, b = h.b, c1 = h.c1, c2 = h.c2, g0 = h.g0, g1 = h.g1, g2 = h.g2;
-        const double c1p = c1 + 1.0;   // w = u + 1 straight from x (shorter dependency chain)
         const int lo = h.lo;
         const unsigned len = h.len;
 #pragma unroll
@@ -479,7 +478,7 @@ __global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
                 if (!__any_sync(0xffffffffu, in)) continue;
             }
             const double x = fma(Pd[k], xs, b);
-            double kp = srdev::humliv_reg1_uw(fma(x, x, c1), fma(x, x, c1p), c2);
+            double kp = srdev::humliv_reg1_u(fma(x, x, c1), c2);
             if (!FULL) kp = in ? kp : 0.0;
             acc0[k] = fma(g0, kp, acc0[k]);
             acc1[k] = fma(g1, kp, acc1[k]);
