@@ -586,6 +586,7 @@ struct MmaArgs {
     int keep;                     // 1: the layer rows are read back at once (L2-sized scratch):
                                   // default-policy stores instead of streaming ones
     int f32;                      // 1: the layer rows are stored as float32 (same element indexing)
+    int tpc;                      // point tiles per CTA
 };
 
 struct PackArgs {
@@ -678,9 +679,11 @@ __global__ void __launch_bounds__(MMA_NT, MINB) k_los_mma(MmaArgs a) {
     __syncthreads();
     const bool two = pair_s[8] >= 0;
     const int kq = lane & 3, nq = lane >> 2;
-    const long p_warp = (long)blockIdx.y * ((MMA_NT / 32) * 8 * NB) + wid * (8 * NB);
-    if (p_warp >= a.n_pts) return;
     struct Frag { float v[NB]; };
+    // a CTA walks a.tpc consecutive point tiles with the weights it staged once
+    for (int it = 0; it < a.tpc; it++) {
+    const long p_warp = ((long)blockIdx.y * a.tpc + it) * ((MMA_NT / 32) * 8 * NB) + wid * (8 * NB);
+    if (p_warp >= a.n_pts) return;
     // per-lane point offsets inside a LUT row; lanes beyond the point window re-read the last
     // valid vector of the row (their columns are never stored), so every load is unconditional
     long loff[VEC ? NB / 4 : NB];
@@ -808,6 +811,7 @@ __global__ void __launch_bounds__(MMA_NT, MINB) k_los_mma(MmaArgs a) {
     store(a.tau_out, false);
     pass(n_tau, n_tot);
     store(a.src_out, true);
+    }
 }
 
 
@@ -2206,6 +2210,7 @@ static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, lon
         ma.mode = emit_j;
         ma.keep = 0;
         ma.f32 = 0;
+        ma.tpc = 1;
         dim3 grid((unsigned)P.n_chunks, (unsigned)((n_pts + TILE - 1) / TILE));
         const bool vec = rows_aligned && pt0 % 4 == 0 && n_pts % 4 == 0 &&
                          ((size_t)tau_dev | (size_t)src_dev) % 32 == 0;
@@ -2273,7 +2278,13 @@ static int los_launch_locked(sr_lut* const* luts, const sr_los_steps* steps, lon
                     ma.mode = 1;
                     ma.keep = l2keep;
                     ma.f32 = lay_f32 ? 1 : 0;
-                    dim3 grid((unsigned)n_ch, (unsigned)((np + TILE - 1) / TILE));
+                    // point tiles per CTA (the weights are staged once per CTA): up to 8, as long as
+                    // the launch still has several waves of CTAs
+                    static const int tpc_env = getenv("SR_MMA_TPC") ? std::max(1, atoi(getenv("SR_MMA_TPC"))) : 0;
+                    const long n_t = (np + TILE - 1) / TILE;
+                    ma.tpc = tpc_env ? tpc_env
+                                     : (int)std::max<long>(1, std::min<long>(8, (long)n_ch * n_t / (148L * 4 * 4)));
+                    dim3 grid((unsigned)n_ch, (unsigned)((n_t + ma.tpc - 1) / ma.tpc));
                     ma.wfrag = L0->g_wfrag.p;
                     int code;
                     {
