@@ -23,6 +23,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <vector>
 #include "sr_common.h"
 #include "sr_device.cuh"
@@ -1596,36 +1597,97 @@ static int plan_groups(sr_lut* const* luts, const sr_los_steps* S, GemmPlan& P) 
 
     // ---- pass 1: group (cell quad) of every pair, found once for the whole batch ---------------
     // consecutive steps of a LOS mostly stay in the same quad: a one-entry cache in front of the map
-    std::map<QuadKey, int> group_of;
+    // (host threads over LOS ranges: with N GPUs every rank plans the whole batch, so this is the part
+    // of a step that does not shrink with N)
     std::vector<QuadKey> keys;                 // per group
     std::vector<int>& pair_grp = P.pair_grp;
     pair_grp.assign((size_t)S->n_los * nmax, -1);
-    QuadKey last;
-    memset(last.c, 0x7f, sizeof(last.c));
-    int last_grp = -1;
-    for (int l = 0; l < S->n_los; l++)
-        for (int k = 0; k < S->n_steps[l]; k++) {
-            QuadKey key;
-            memset(key.c, 0xff, sizeof(key.c));
-            for (int m = 0; m < n_gas; m++) {
-                int rc = cells_of(luts[m], S->pres[l * nmax + k], S->temp[l * nmax + k], key.c + 4 * m);
-                if (rc) return rc;
-            }
-            int grp;
-            if (last_grp >= 0 && key == last) grp = last_grp;
-            else {
-                auto f = group_of.find(key);
-                if (f != group_of.end()) grp = f->second;
-                else {
-                    grp = P.n_groups++;
-                    group_of.emplace(key, grp);
-                    keys.push_back(key);
+    {
+        long n_pairs = 0;
+        for (int l = 0; l < S->n_los; l++) n_pairs += S->n_steps[l];
+        int n_thr = 1;
+        if (n_pairs > 50000) n_thr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        if (const char* e = getenv("SR_LOS_PLAN_THREADS")) n_thr = std::max(1, atoi(e));
+        n_thr = std::min(n_thr, std::max(1, S->n_los));
+        struct Part {
+            std::map<QuadKey, int> ids;
+            std::vector<QuadKey> keys;
+            int rc = SR_OK, bad_l = -1, bad_k = -1;
+        };
+        std::vector<Part> parts(n_thr);
+        auto work = [&](int t) {
+            Part& pt = parts[t];
+            const int l0 = (int)((long)S->n_los * t / n_thr), l1 = (int)((long)S->n_los * (t + 1) / n_thr);
+            QuadKey last;
+            memset(last.c, 0x7f, sizeof(last.c));
+            int last_id = -1;
+            for (int l = l0; l < l1 && pt.rc == SR_OK; l++)
+                for (int k = 0; k < S->n_steps[l]; k++) {
+                    QuadKey key;
+                    memset(key.c, 0xff, sizeof(key.c));
+                    for (int m = 0; m < n_gas; m++) {
+                        int rc = cells_of(luts[m], S->pres[l * nmax + k], S->temp[l * nmax + k], key.c + 4 * m);
+                        if (rc) { pt.rc = rc; pt.bad_l = l; pt.bad_k = k; break; }
+                    }
+                    if (pt.rc) break;
+                    int id;
+                    if (last_id >= 0 && key == last) id = last_id;
+                    else {
+                        auto f = pt.ids.find(key);
+                        if (f != pt.ids.end()) id = f->second;
+                        else {
+                            id = (int)pt.keys.size();
+                            pt.ids.emplace(key, id);
+                            pt.keys.push_back(key);
+                        }
+                        last = key;
+                        last_id = id;
+                    }
+                    pair_grp[l * nmax + k] = id;       // local id, made global below
                 }
-                last = key;
-                last_grp = grp;
-            }
-            pair_grp[l * nmax + k] = grp;
+        };
+        if (n_thr == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < n_thr; t++) th.emplace_back(work, t);
+            for (auto& x : th) x.join();
         }
+        for (int t = 0; t < n_thr; t++)
+            if (parts[t].rc) {   // repeat the failing look-up on this thread: sr_last_error is per thread
+                int dummy[4];
+                for (int m = 0; m < n_gas; m++) {
+                    int rc = cells_of(luts[m], S->pres[parts[t].bad_l * nmax + parts[t].bad_k],
+                                      S->temp[parts[t].bad_l * nmax + parts[t].bad_k], dummy);
+                    if (rc) return rc;
+                }
+                return parts[t].rc;
+            }
+        std::map<QuadKey, int> group_of;
+        std::vector<std::vector<int>> remap(n_thr);
+        for (int t = 0; t < n_thr; t++) {
+            remap[t].resize(parts[t].keys.size());
+            for (size_t i = 0; i < parts[t].keys.size(); i++) {
+                auto f = group_of.find(parts[t].keys[i]);
+                if (f != group_of.end()) remap[t][i] = f->second;
+                else {
+                    remap[t][i] = P.n_groups;
+                    group_of.emplace(parts[t].keys[i], P.n_groups++);
+                    keys.push_back(parts[t].keys[i]);
+                }
+            }
+        }
+        auto fix = [&](int t) {
+            const int l0 = (int)((long)S->n_los * t / n_thr), l1 = (int)((long)S->n_los * (t + 1) / n_thr);
+            for (int l = l0; l < l1; l++)
+                for (int k = 0; k < S->n_steps[l]; k++) pair_grp[l * nmax + k] = remap[t][pair_grp[l * nmax + k]];
+        };
+        if (n_thr == 1) fix(0);
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < n_thr; t++) th.emplace_back(fix, t);
+            for (auto& x : th) x.join();
+        }
+    }
     // ---- row programs, one per group ---------------------------------------------------------
     P.prog.resize((size_t)P.n_groups * P.max_jp);
     for (int grp = 0; grp < P.n_groups; grp++) {
