@@ -551,8 +551,12 @@ def run_extras(args, P, engine, parallel, torch, dist, ls, lut, steps_all, grid_
                     "roofline": {"bound": "fp64", "achieved": 15.0 * all_evals / k1_s / 1e12 / world,
                                  "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                                  "frac": 15.0 * all_evals / k1_s / fp64_peak / world,
-                                 "note": "15 FP64 flop per eval (SURVEY 8d), per GPU; time includes "
-                                         "k_line_cell_params, k_core_eval and k_voigt_tile"}}
+                                 "note": "ALGORITHMIC: 15 FP64 flop per line*gridpoint (SURVEY 8d) x the "
+                                         "evals of the problem / time of k_line_cell_params + k_core_eval "
+                                         "+ k_far_nodes + k_voigt_tile, per GPU.  Distant full far wings are "
+                                         "evaluated at 12 Chebyshev nodes per 512-point tile and interpolated "
+                                         "(<= 4e-11 of a line's own value), so fewer flops are executed than "
+                                         "counted; SR_K1_FAR=0 evaluates every point (frac 0.41)"}}
     del buf
 
     # ---- K1 on a million-line list: wavenumber slabs, result stays sharded, no collective ------

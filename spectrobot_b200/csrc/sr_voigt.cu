@@ -313,6 +313,160 @@ __global__ void __launch_bounds__(128) k_core_eval(const LineCell* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Far field of the far wings.  A far wing that covers a whole tile and whose line centre lies more
+// than two tile lengths (+ ry + 1 Doppler widths) away is, over the TP points of the tile, a
+// smooth function with its poles far outside: FAR_NN = 12 Chebyshev nodes reproduce it to 4e-11 of
+// its own value (tools/far_field_check.py: all ry in [1e-4, 80], xs in [0.02, 0.5], both wings).
+// k_far_nodes evaluates such records at the 12 nodes instead of the TP points, sums them per output
+// row in a fixed order and leaves 12 monomial coefficients per (cell, tile, row); k_voigt_tile
+// skips the same records (same predicate on the same numbers) and adds the polynomial when it
+// stores the row.  84 % of the full far wings of the CH4 workload go this way.
+// ---------------------------------------------------------------------------------------------
+constexpr int FAR_NN = 12;
+constexpr int FAR_MAX_GROUPS = 128;
+__constant__ double c_far_t[FAR_NN];             // Chebyshev nodes on [-1, 1]
+__constant__ double c_far_M[FAR_NN * FAR_NN];    // node values -> monomial coefficients, [power][node]
+
+__device__ __forceinline__ bool far_full_half(double xs, double b, double c2, int tile0, int tile_last) {
+    const double x0 = fma((double)tile0, xs, b), x1 = fma((double)tile_last, xs, b);
+    const double d = fmin(fabs(x0), fabs(x1));
+    return x0 * x1 > 0.0 && d >= 2.0 * fabs(x1 - x0) + sqrt(0.5 * c2) + 1.0;
+}
+
+struct FarArgs {
+    const LineRec* lrec;     // [n_cells][n_lines]
+    const int* tile_rng;     // [n_tiles][n_groups][2]
+    const int* grp_up;       // [n_groups] upper set of the group
+    const int* grp_lo;       // [n_groups] lower set
+    double* coef;            // [n_cells][n_tiles_window][n_sets*3][FAR_NN]
+    int n_lines, n_groups, n_sets, tile_base, tp;
+};
+
+constexpr int FAR_NT = 256;
+constexpr int FAR_CAP = 512;   // candidates per pass
+
+// One CTA per (tile, cell).  Pass over the tile's candidate list in slices of FAR_CAP: every thread
+// loads one or two candidates (all loads of a slice are in flight at once: one L2 latency), flags
+// the wings that qualify and leaves the record in shared memory; then thread (node n, lane q) walks
+// the groups q, q+16, ... and, inside a group, the records in order - a single writer and a single
+// order per (group, node), so the sums do not depend on scheduling.
+__global__ void __launch_bounds__(FAR_NT) k_far_nodes(FarArgs a) {
+    extern __shared__ __align__(16) unsigned char fraw[];
+    double* rec = reinterpret_cast<double*>(fraw);                       // [8][FAR_CAP] xs bL bR c1 c2 g0 g1 g2
+    double* gsum = rec + 8 * FAR_CAP;                                    // [n_groups][3][FAR_NN]
+    double* rowsum = gsum + (size_t)a.n_groups * 3 * FAR_NN;             // [n_sets*3][FAR_NN]
+    double* Msm = rowsum + (size_t)a.n_sets * 3 * FAR_NN;                // [FAR_NN][FAR_NN]
+    int* fl = reinterpret_cast<int*>(Msm + FAR_NN * FAR_NN);             // [FAR_CAP]
+    int* cum = fl + FAR_CAP;                                             // [n_groups + 1]
+    int* glo = cum + a.n_groups + 1;                                     // [n_groups]
+    int* gup = glo + a.n_groups;                                         // [n_groups] upper set
+    int* gls = gup + a.n_groups;                                         // [n_groups] lower set
+    const int cell = blockIdx.y, tile_idx = a.tile_base + blockIdx.x;
+    const int tile0 = tile_idx * a.tp, tile_last = tile0 + a.tp - 1;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n_rows = a.n_sets * 3;
+    const LineRec* __restrict__ lrec = a.lrec + (size_t)cell * a.n_lines;
+    for (int g = tid; g < a.n_groups; g += FAR_NT) {
+        const int2 rg = __ldg(reinterpret_cast<const int2*>(a.tile_rng) + (size_t)tile_idx * a.n_groups + g);
+        glo[g] = rg.x;
+        cum[g + 1] = rg.y - rg.x;
+        gup[g] = __ldg(a.grp_up + g);
+        gls[g] = __ldg(a.grp_lo + g);
+    }
+    for (int i = tid; i < a.n_groups * 3 * FAR_NN; i += FAR_NT) gsum[i] = 0.0;
+    for (int i = tid; i < FAR_NN * FAR_NN; i += FAR_NT) Msm[i] = c_far_M[i];
+    __syncthreads();
+    if (wid == 0) {   // inclusive prefix sum of the group sizes (n_groups <= FAR_MAX_GROUPS = 128)
+        int carry = 0;
+        for (int g0 = 0; g0 < a.n_groups; g0 += 32) {
+            const int g = g0 + lane;
+            int v = g < a.n_groups ? cum[g + 1] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v += t;
+            }
+            if (g < a.n_groups) cum[g + 1] = carry + v;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+        if (lane == 0) cum[0] = 0;
+    }
+    __syncthreads();
+    const int n_tot = cum[a.n_groups];
+    const int node = tid & 15, q = tid >> 4;
+    const double Pn = (double)tile0 + 0.5 * (double)(a.tp - 1) * (1.0 + c_far_t[node < FAR_NN ? node : 0]);
+    for (int f0 = 0; f0 < n_tot; f0 += FAR_CAP) {
+        const int f1 = min(n_tot, f0 + FAR_CAP);
+        for (int f = f0 + tid; f < f1; f += FAR_NT) {
+            int lo = 0, hi = a.n_groups;   // largest g with cum[g] <= f
+            while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (cum[m] <= f) lo = m; else hi = m; }
+            LineRec R;
+            const int4* src = reinterpret_cast<const int4*>(lrec + glo[lo] + (f - cum[lo]));
+            int4* dst = reinterpret_cast<int4*>(&R);
+#pragma unroll
+            for (int w = 0; w < (int)(sizeof(LineRec) / 16); w++) dst[w] = __ldg(src + w);
+            const bool fL = R.PL_end >= R.Pwin_lo && R.Pwin_lo <= tile0 && R.PL_end >= tile_last;
+            const bool fR = R.Pwin_hi >= R.PR_beg && R.PR_beg <= tile0 && R.Pwin_hi >= tile_last;
+            int flag = 0;
+            if (fL && far_full_half(R.xs, R.bL, R.c2, tile0, tile_last)) flag |= 1;
+            if (fR && far_full_half(R.xs, R.bR, R.c2, tile0, tile_last)) flag |= 2;
+            const int i = f - f0;
+            fl[i] = flag;
+            if (flag) {
+                rec[0 * FAR_CAP + i] = R.xs; rec[1 * FAR_CAP + i] = R.bL; rec[2 * FAR_CAP + i] = R.bR;
+                rec[3 * FAR_CAP + i] = R.c1; rec[4 * FAR_CAP + i] = R.c2; rec[5 * FAR_CAP + i] = R.g0;
+                rec[6 * FAR_CAP + i] = R.g1; rec[7 * FAR_CAP + i] = R.g2;
+            }
+        }
+        __syncthreads();
+        if (node < FAR_NN)
+            for (int g = q; g < a.n_groups; g += FAR_NT / 16) {
+                const int ca = max(cum[g], f0), cb = min(cum[g + 1], f1);
+                if (cb <= ca) continue;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                for (int c = ca; c < cb; c++) {
+                    const int i = c - f0, flag = fl[i];
+                    if (!flag) continue;
+                    const double xs = rec[i], c1 = rec[3 * FAR_CAP + i], c2 = rec[4 * FAR_CAP + i];
+                    double kp = 0.0;
+                    if (flag & 1) {
+                        const double x = fma(Pn, xs, rec[1 * FAR_CAP + i]);
+                        kp = srdev::humliv_reg1_u(fma(x, x, c1), c2);
+                    }
+                    if (flag & 2) {
+                        const double x = fma(Pn, xs, rec[2 * FAR_CAP + i]);
+                        kp += srdev::humliv_reg1_u(fma(x, x, c1), c2);
+                    }
+                    s0 = fma(rec[5 * FAR_CAP + i], kp, s0);
+                    s1 = fma(rec[6 * FAR_CAP + i], kp, s1);
+                    s2 = fma(rec[7 * FAR_CAP + i], kp, s2);
+                }
+                gsum[((size_t)g * 3 + 0) * FAR_NN + node] += s0;
+                gsum[((size_t)g * 3 + 1) * FAR_NN + node] += s1;
+                gsum[((size_t)g * 3 + 2) * FAR_NN + node] += s2;
+            }
+        __syncthreads();
+    }
+    // rows: sp / ind emission of a set = its groups as upper set, absorption = its groups as lower set
+    for (int item = tid; item < n_rows * FAR_NN; item += FAR_NT) {
+        const int row = item / FAR_NN, n = item - row * FAR_NN, sset = row / 3, ct = row - sset * 3;
+        double sum = 0.0;
+        for (int g = 0; g < a.n_groups; g++)
+            if ((ct < 2 ? gup[g] : gls[g]) == sset) sum += gsum[((size_t)g * 3 + ct) * FAR_NN + n];
+        rowsum[item] = sum;
+    }
+    __syncthreads();
+    double* __restrict__ out = a.coef + ((size_t)cell * gridDim.x + blockIdx.x) * n_rows * FAR_NN;
+    for (int item = tid; item < n_rows * FAR_NN; item += FAR_NT) {
+        const int row = item / FAR_NN, j = item - row * FAR_NN;
+        double c = 0.0;
+#pragma unroll
+        for (int n = 0; n < FAR_NN; n++) c = fma(Msm[j * FAR_NN + n], rowsum[row * FAR_NN + n], c);
+        out[item] = c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1/K2 tile kernel (v5)
 // ---------------------------------------------------------------------------------------------
 // One far wing of one line restricted to nothing: for grid point P (absolute index)
@@ -348,6 +502,7 @@ struct TileArgs {
     long row_stride;         // elements between consecutive output rows (>= window length)
     long pt_lo;              // first grid point of the output window (a multiple of the tile size)
     int tile_base;           // pt_lo / tile size: index of the window's first tile in tile_rng
+    const double* far_coef;  // [n_cells][tiles of the window][n_sets*3][FAR_NN] or nullptr (k_far_nodes)
     int n_lines, n_sets, n_groups, n_up, n_lo, n_zero;
 };
 
@@ -376,7 +531,8 @@ __global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
     const int tile0 = tile_idx * TP, tile_last = tile0 + TP - 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* abs_s = reinterpret_cast<double*>(smem_raw);                  // [n_lo][PPT][NT]
-    HalfRec* hbuf = reinterpret_cast<HalfRec*>(abs_s + (size_t)a.n_lo * TP);   // [2*NT]
+    double* farc = abs_s + (size_t)a.n_lo * TP;                           // [n_sets*3][FAR_NN] (k_far_nodes)
+    HalfRec* hbuf = reinterpret_cast<HalfRec*>(farc + (size_t)a.n_sets * 3 * FAR_NN);   // [2*NT]
     CentreRec* cbuf = reinterpret_cast<CentreRec*>(hbuf + 2 * NT);             // [NT]
     int* pre = reinterpret_cast<int*>(cbuf + NT);                              // [NT+1] h | c<<16
     int* wsum = pre + NT + 1;                                                  // [NW]
@@ -392,6 +548,11 @@ __global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
     // ---- prologue: candidate ranges -> prefix sums (warp 0) ------------------------------------
     {
         const int* __restrict__ rng = a.tile_rng + (size_t)tile_idx * a.n_groups * 2;
+        if (a.far_coef) {   // the tile's far-field polynomials: fetched once, used when rows are stored
+            const double* __restrict__ fc =
+                a.far_coef + ((size_t)cell * gridDim.x + blockIdx.x) * (size_t)a.n_sets * 3 * FAR_NN;
+            for (int i = tid; i < a.n_sets * 3 * FAR_NN; i += NT) farc[i] = __ldg(fc + i);
+        }
         for (int g = tid; g < a.n_groups; g += NT) {
             const int2 r = __ldg(reinterpret_cast<const int2*>(rng) + g);
             glo[g] = r.x;
@@ -431,13 +592,36 @@ __global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
     int cur_g = -1, cur_up = -1, stored_up = 0;
     const size_t rows_cell = (size_t)a.n_sets * 3;
 
-    auto store_row = [&](int row, const double (&v)[PPT]) {
+    // far-field polynomial of this (cell, tile, row) at the thread's points (k_far_nodes)
+    const double far_s = 2.0 / (double)(TP - 1), far_o = -fma((double)tile0, 2.0 / (double)(TP - 1), 1.0);
+    auto store_row = [&](int row, const double (&v)[PPT], bool with_far = true) {
         const size_t o = ((size_t)cell * rows_cell + row) * (size_t)a.row_stride + (P0 - a.pt_lo);
+        double w[PPT];
+#pragma unroll
+        for (int k = 0; k < PPT; k++) w[k] = v[k];
+        if (with_far && a.far_coef) {
+            const double2* c2p = reinterpret_cast<const double2*>(farc + (size_t)row * FAR_NN);
+            double c[FAR_NN];
+#pragma unroll
+            for (int j = 0; j < FAR_NN / 2; j++) {
+                const double2 q = c2p[j];
+                c[2 * j] = q.x;
+                c[2 * j + 1] = q.y;
+            }
+#pragma unroll
+            for (int k = 0; k < PPT; k++) {
+                const double t = fma(Pd[k], far_s, far_o);
+                double f = c[FAR_NN - 1];
+#pragma unroll
+                for (int j = FAR_NN - 2; j >= 0; j--) f = fma(f, t, c[j]);
+                w[k] += f;
+            }
+        }
 #pragma unroll
         for (int k = 0; k < PPT; k++) {
             if ((long)P0 + k * NT < a.n_grid) {
-                if (F32) __stcs(reinterpret_cast<float*>(a.out) + o + k * NT, (float)v[k]);
-                else __stcs(reinterpret_cast<double*>(a.out) + o + k * NT, v[k]);
+                if (F32) __stcs(reinterpret_cast<float*>(a.out) + o + k * NT, (float)w[k]);
+                else __stcs(reinterpret_cast<double*>(a.out) + o + k * NT, w[k]);
             }
         }
     };
@@ -446,8 +630,8 @@ __global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
     auto store_up = [&](int ui) {
         for (; stored_up < ui; stored_up++) {
             const int s = __ldg(a.up_list + stored_up);
-            store_row(s * 3 + 0, zero_v);
-            store_row(s * 3 + 1, zero_v);
+            store_row(s * 3 + 0, zero_v, false);
+            store_row(s * 3 + 1, zero_v, false);
         }
         const int s = __ldg(a.up_list + ui);
         store_row(s * 3 + 0, acc0);
@@ -531,6 +715,10 @@ __global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
                 nC = (R.PR_beg - R.PL_end > 1 && R.PL_end < tile_last && R.PR_beg > tile0) ? 1 : 0;
                 fL = nL && R.Pwin_lo <= tile0 && R.PL_end >= tile_last;
                 fR = nR && R.PR_beg <= tile0 && R.Pwin_hi >= tile_last;
+                if (a.far_coef) {   // full wings of distant lines come in through k_far_nodes
+                    if (fL && far_full_half(R.xs, R.bL, R.c2, tile0, tile_last)) nL = fL = 0;
+                    if (fR && far_full_half(R.xs, R.bR, R.c2, tile0, tile_last)) nR = fR = 0;
+                }
                 // fields: full halves | partial halves << 11 | centres << 22
                 packed = (fL + fR) | ((nL + nR - fL - fR) << 11) | (nC << 22);
             }
@@ -621,8 +809,8 @@ __global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
     }
     for (; stored_up < a.n_up; stored_up++) {
         const int s = __ldg(a.up_list + stored_up);
-        store_row(s * 3 + 0, zero_v);
-        store_row(s * 3 + 1, zero_v);
+        store_row(s * 3 + 0, zero_v, false);
+        store_row(s * 3 + 1, zero_v, false);
     }
     for (int j = 0; j < a.n_lo; j++) {
         double v[PPT];
@@ -630,7 +818,7 @@ __global__ void __launch_bounds__(NT, MINB) k_voigt_tile(TileArgs a) {
         for (int k = 0; k < PPT; k++) v[k] = abs_s[(j * PPT + k) * NT + tid];
         store_row(__ldg(a.lo_list + j) * 3 + 2, v);
     }
-    for (int j = 0; j < a.n_zero; j++) store_row(__ldg(a.zero_rows + j), zero_v);
+    for (int j = 0; j < a.n_zero; j++) store_row(__ldg(a.zero_rows + j), zero_v, false);
 }
 
 // candidate line range of every (tile, group): lines whose 13010-point window touches the tile.
@@ -694,7 +882,8 @@ struct sr_lineset {
     // of batch i+1 runs on `aux` while the tile kernel of batch i runs on the caller's stream
     sr::DevBuf<LineCell> rec_b[2];
     sr::DevBuf<LineRec> lrec_b[2];
-    sr::DevBuf<double> pt_b[2], core_b[2], facs;
+    sr::DevBuf<double> pt_b[2], core_b[2], far_b[2], facs;
+    bool far_ok = false;      // far-field path usable (group count, constant tables uploaded)
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_entry = nullptr, ev_core[2] = {nullptr, nullptr}, ev_tile[2] = {nullptr, nullptr};
     ~sr_lineset() {
@@ -715,15 +904,16 @@ struct sr_lineset {
 
 namespace {
 
-size_t tile_smem(int nt, int ppt, int n_lo, int n_groups) {
-    return (size_t)n_lo * nt * ppt * sizeof(double) + (size_t)2 * nt * sizeof(HalfRec) +
+size_t tile_smem(int nt, int ppt, int n_lo, int n_groups, int n_sets) {
+    return (size_t)n_lo * nt * ppt * sizeof(double) + (size_t)n_sets * 3 * FAR_NN * sizeof(double) +
+           (size_t)2 * nt * sizeof(HalfRec) +
            (size_t)nt * sizeof(CentreRec) +
            (size_t)(nt + 1 + nt / 32 + 4 * n_groups + 1) * sizeof(int) + 16;
 }
 
 template <int NT, int PPT, bool F32, int MINB>
 int launch_tile(const TileArgs& ta, int n_cells, cudaStream_t st) {
-    const size_t smem = tile_smem(NT, PPT, ta.n_lo, ta.n_groups);
+    const size_t smem = tile_smem(NT, PPT, ta.n_lo, ta.n_groups, ta.n_sets);
     SR_CUDA(cudaFuncSetAttribute(k_voigt_tile<NT, PPT, F32, MINB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int TP = NT * PPT;
@@ -744,20 +934,20 @@ constexpr TileCfg kTileCfgs[] = {{128, 4}, {256, 4}, {256, 2}, {128, 2}, {256, 1
                                  {128, 4}};
 constexpr int kNumCfgs = (int)(sizeof(kTileCfgs) / sizeof(kTileCfgs[0]));
 
-int pick_cfg(int n_lo, int n_groups, size_t smem_max) {
+int pick_cfg(int n_lo, int n_groups, int n_sets, size_t smem_max) {
     if (const char* e = getenv("SR_K1_CFG")) {
         const int i = atoi(e);
         if (i >= 0 && i < kNumCfgs &&
-            tile_smem(kTileCfgs[i].nt, kTileCfgs[i].ppt, n_lo, n_groups) <= smem_max)
+            tile_smem(kTileCfgs[i].nt, kTileCfgs[i].ppt, n_lo, n_groups, n_sets) <= smem_max)
             return i;
     }
-    if (2 * (tile_smem(kTileCfgs[5].nt, kTileCfgs[5].ppt, n_lo, n_groups) + 1024) <= (size_t)228 * 1024)
+    if (2 * (tile_smem(kTileCfgs[5].nt, kTileCfgs[5].ppt, n_lo, n_groups, n_sets) + 1024) <= (size_t)228 * 1024)
         return 5;                    // measured best on B200 (tools/tune.py k1): 128 thr x 4 pts, 4 CTAs/SM
     for (int i = 0; i < 5; i++)      // at least two CTAs per SM
-        if (2 * (tile_smem(kTileCfgs[i].nt, kTileCfgs[i].ppt, n_lo, n_groups) + 1024) <= (size_t)228 * 1024)
+        if (2 * (tile_smem(kTileCfgs[i].nt, kTileCfgs[i].ppt, n_lo, n_groups, n_sets) + 1024) <= (size_t)228 * 1024)
             return i;
     for (int i = 0; i < 5; i++)      // one CTA per SM
-        if (tile_smem(kTileCfgs[i].nt, kTileCfgs[i].ppt, n_lo, n_groups) <= smem_max) return i;
+        if (tile_smem(kTileCfgs[i].nt, kTileCfgs[i].ppt, n_lo, n_groups, n_sets) <= smem_max) return i;
     return -1;
 }
 
@@ -946,12 +1136,36 @@ int sr_lineset_create(const sr_lines* lines, const double* grid, long n_grid,
         int smem_max = 0;
         SR_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin,
                                        ls->device));
-        ls->cfg = pick_cfg(ls->n_lo, ls->n_groups, (size_t)smem_max);
+        ls->cfg = pick_cfg(ls->n_lo, ls->n_groups, ls->n_sets, (size_t)smem_max);
         if (ls->cfg < 0)
             return sr::fail(SR_ERR_LIMIT, "%d lower levels x %d level pairs need more than %d bytes "
                             "of shared memory per tile", ls->n_lo, ls->n_groups, smem_max);
         ls->tile_nt = kTileCfgs[ls->cfg].nt;
         ls->tile_ppt = kTileCfgs[ls->cfg].ppt;
+        {   // far-field tables: Chebyshev nodes and the node-values -> monomial-coefficients matrix
+            double t[FAR_NN], M[FAR_NN * FAR_NN], T[FAR_NN][FAR_NN], C2P[FAR_NN][FAR_NN];
+            for (int n = 0; n < FAR_NN; n++) t[n] = cos((2 * n + 1) * M_PI / (2.0 * FAR_NN));
+            for (int j = 0; j < FAR_NN; j++)        // Chebyshev coefficient j from the node values
+                for (int n = 0; n < FAR_NN; n++)
+                    T[j][n] = (j == 0 ? 1.0 : 2.0) / FAR_NN * cos(j * (2 * n + 1) * M_PI / (2.0 * FAR_NN));
+            for (int j = 0; j < FAR_NN; j++)        // monomial coefficients of T_j: T_{j+1} = 2 x T_j - T_{j-1}
+                for (int p = 0; p < FAR_NN; p++) C2P[p][j] = 0.0;
+            C2P[0][0] = 1.0;
+            if (FAR_NN > 1) C2P[1][1] = 1.0;
+            for (int j = 2; j < FAR_NN; j++)
+                for (int p = 0; p < FAR_NN; p++)
+                    C2P[p][j] = (p > 0 ? 2.0 * C2P[p - 1][j - 1] : 0.0) - C2P[p][j - 2];
+            for (int p = 0; p < FAR_NN; p++)
+                for (int n = 0; n < FAR_NN; n++) {
+                    double v = 0.0;
+                    for (int j = 0; j < FAR_NN; j++) v += C2P[p][j] * T[j][n];
+                    M[p * FAR_NN + n] = v;
+                }
+            SR_CUDA(cudaMemcpyToSymbolAsync(c_far_t, t, sizeof(t), 0, cudaMemcpyHostToDevice, st));
+            SR_CUDA(cudaMemcpyToSymbolAsync(c_far_M, M, sizeof(M), 0, cudaMemcpyHostToDevice, st));
+            SR_CUDA(cudaStreamSynchronize(st));      // t and M are stack variables
+            ls->far_ok = ls->n_groups <= FAR_MAX_GROUPS;
+        }
         const int tp = ls->tile_nt * ls->tile_ppt;
         ls->n_tiles = (int)((n_grid + tp - 1) / tp);
         SR_CUDA(ls->tile_rng.alloc((size_t)ls->n_tiles * ls->n_groups * 2));
@@ -1067,6 +1281,12 @@ static int gcoeff_cells_impl(sr_lineset* ls, const double* pt_host, int n_cells,
         SR_CUDA(cudaEventRecord(ls->ev_entry, st));
         SR_CUDA(cudaStreamWaitEvent(ls->aux, ls->ev_entry, 0));
     }
+    // far field of the far wings (k_far_nodes): SR_K1_FAR=0 evaluates every wing point by point
+    const int far_env = getenv("SR_K1_FAR") ? atoi(getenv("SR_K1_FAR")) : 1;
+    const int tp = ls->tile_nt * ls->tile_ppt;
+    const bool use_far = far_env != 0 && ls->far_ok && win0 % tp == 0;
+    const long n_tiles_w = (win_n + tp - 1) / tp;
+    const int far_cap_cells = std::max(std::min(sub, n_cells), std::min(ls->max_cells_per_batch, pipe ? sub : 16));
     const size_t core_cap = (size_t)std::max(std::min(sub, n_cells),
                                              std::min(ls->max_cells_per_batch, pipe ? sub : 16)) *
                             ls->n_act * CORE_STRIDE;
@@ -1081,6 +1301,26 @@ static int gcoeff_cells_impl(sr_lineset* ls, const double* pt_host, int n_cells,
             sr::ProfScope pr(SR_PROF_VOIGT_CORE, 0.0, ps);
             SR_LAUNCH(k_core_eval, cgrid, 128, 0, ps, ls->rec_b[buf].p, ls->freq.p, ls->gc.p,
                       ls->lin.p, ls->n_act, ls->core_b[buf].p);
+        }
+        if (use_far) {   // node sums of the distant full wings, per (cell, tile of the window, row)
+            const int n_rows = ls->n_sets * 3;
+            SR_CUDA(ls->far_b[buf].ensure((size_t)far_cap_cells * n_tiles_w * n_rows * FAR_NN));
+            FarArgs fa;
+            fa.lrec = ls->lrec_b[buf].p;
+            fa.tile_rng = ls->tile_rng.p;
+            fa.grp_up = ls->grp_up.p;
+            fa.grp_lo = ls->grp_lo.p;
+            fa.coef = ls->far_b[buf].p;
+            fa.n_lines = ls->n_act;
+            fa.n_groups = ls->n_groups;
+            fa.n_sets = ls->n_sets;
+            fa.tile_base = (int)(win0 / tp);
+            fa.tp = tp;
+            const size_t fsmem = (8 * (size_t)FAR_CAP + ((size_t)ls->n_groups * 3 + n_rows) * FAR_NN +
+                                  FAR_NN * FAR_NN) * sizeof(double) +
+                                 ((size_t)FAR_CAP + 4 * ls->n_groups + 1) * sizeof(int) + 16;
+            SR_CUDA(cudaFuncSetAttribute(k_far_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            SR_LAUNCH(k_far_nodes, dim3((unsigned)n_tiles_w, (unsigned)nb), FAR_NT, fsmem, ps, fa);
         }
         if (pipe) SR_CUDA(cudaEventRecord(ls->ev_core[buf], ps));
         return SR_OK;
@@ -1117,6 +1357,7 @@ static int gcoeff_cells_impl(sr_lineset* ls, const double* pt_host, int n_cells,
         ta.row_stride = row_stride;
         ta.pt_lo = win0;
         ta.tile_base = 0;
+        ta.far_coef = use_far ? ls->far_b[buf].p : nullptr;
         ta.n_lines = ls->n_act;
         ta.n_sets = ls->n_sets;
         ta.n_groups = ls->n_groups;

@@ -234,3 +234,34 @@ def test_cell_batches_are_invisible(sb, monkeypatch):
     assert torch.equal(ls.gcoeff_cells(cells), base)
     assert torch.equal(ls.gcoeff_cells_f32(cells), base32)
     assert np.array_equal(ls.gcoeff_cells_host(cells), base.cpu().numpy())
+
+
+def test_far_field_of_the_far_wings_is_invisible(monkeypatch):
+    """k_far_nodes (distant full far wings evaluated at 12 Chebyshev nodes per tile and interpolated)
+    against the point-by-point evaluation (SR_K1_FAR=0): <= 1e-9 of the largest value of a row, over
+    Titan-like and high pressures (ry from 1e-3 to ~50) and both storage types."""
+    import torch
+    from spectrobot_b200 import engine, synthetic as S
+    g = S.spectral_grid(2990.0, 3010.0)                       # 40 001 points: lines up to 3 windows away
+    lines = S.line_table(3000, 2986.0, 3014.0, n_levels=6, seed=21)
+    ls = engine.LineSet(lines, g, S.CH4_MM, 6)
+    cells = [[1e-4, 120.0], [0.05, 160.0], [2.5, 175.0], [150.0, 200.0], [1500.0, 94.0]]
+    monkeypatch.setenv("SR_K1_FAR", "0")
+    exact = ls.gcoeff_cells(cells)
+    exact32 = ls.gcoeff_cells_f32(cells)
+    monkeypatch.setenv("SR_K1_FAR", "1")
+    far = ls.gcoeff_cells(cells)
+    far32 = ls.gcoeff_cells_f32(cells)
+    assert not torch.equal(far, exact)                        # the path is really taken
+    scale = exact.abs().amax(dim=3, keepdim=True).clamp_min(1e-300)
+    assert float(((far - exact).abs() / scale).max()) < 1e-9
+    # point-wise, wherever a row is not dominated by cancellation-free tiny far wings
+    rel = ((far - exact).abs() / exact.abs().clamp_min(1e-300))[exact.abs() > 1e-12 * scale]
+    assert float(rel.max()) < 1e-7
+    assert float(((far32.double() - exact32.double()).abs() / scale).max()) < 2e-7
+    # a slab of the grid with its own lineset is still bit-identical to the full build
+    from spectrobot_b200 import parallel
+    tp = ls.tile_points()
+    p0, n = parallel.shard_slab(len(g), 1, 3, align=tp)
+    ls_r = engine.LineSet(parallel.slab_lines(lines, g, p0, n, align=tp), g, S.CH4_MM, 6)
+    assert torch.equal(ls_r.gcoeff_cells_window(cells, p0, n, f32=False), far[..., p0:p0 + n])
