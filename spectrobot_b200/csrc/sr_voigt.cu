@@ -1284,8 +1284,11 @@ static int gcoeff_cells_impl(sr_lineset* ls, const double* pt_host, int n_cells,
     // far field of the far wings (k_far_nodes): SR_K1_FAR=0 evaluates every wing point by point
     const int far_env = getenv("SR_K1_FAR") ? atoi(getenv("SR_K1_FAR")) : 1;
     const int tp = ls->tile_nt * ls->tile_ppt;
-    const bool use_far = far_env != 0 && ls->far_ok && win0 % tp == 0;
     const long n_tiles_w = (win_n + tp - 1) / tp;
+    // (the extra kernel pays when a launch has at least two waves of CTAs; a single cell on a
+    // narrow slab - half a wave - is faster point by point.  SR_K1_FAR=2 forces it.)
+    const bool use_far = far_env != 0 && ls->far_ok && win0 % tp == 0 &&
+                         (far_env == 2 || n_tiles_w * std::min(sub, n_cells) >= 2L * 148 * 4);
     const int far_cap_cells = std::max(std::min(sub, n_cells), std::min(ls->max_cells_per_batch, pipe ? sub : 16));
     const size_t core_cap = (size_t)std::max(std::min(sub, n_cells),
                                              std::min(ls->max_cells_per_batch, pipe ? sub : 16)) *
