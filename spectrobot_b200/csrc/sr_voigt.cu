@@ -287,29 +287,29 @@ __global__ void __launch_bounds__(128) k_core_eval(const LineCell* __restrict__ 
     const double bL2 = rc->baseL2, bR2 = rc->baseR2, bL1 = rc->baseL1, bR1 = rc->baseR1;
     const double c1 = rc->c1, c2 = rc->c2, b4 = rc->b4;
     const srdev::reg2_coef k2 = srdev::humliv_reg2_coefs(ry);
-    for (int j1 = il + (threadIdx.x & 31); j1 <= ir; j1 += 32) {
-        const double j0 = (double)(j1 - 1);
-        double v;
-        if (j1 >= core_lo && j1 <= core_hi) {
-            const double x = lin[j1 - 1] + g;               // spect_classes.py:1455
-            v = srdev::humliv_core_fast(fabs(x - f) / dwp, ry);   // lineshape.f:527
-        } else if (ir2 < ir && j1 >= ir2) {
-            const double x = fma(j0, xs, bR2);
-            v = srdev::humliv_reg2_eval(k2, x * x);
-        } else if (il2 > il && j1 <= il2) {
-            const double x = fma(j0, xs, bL2);
-            v = srdev::humliv_reg2_eval(k2, x * x);
-        } else if (ir < N_WIN && j1 >= ir) {
-            const double x = fma(j0, xs, bR1);
-            v = b4 * srdev::humliv_reg1_fast(fma(x, x, c1), c2);
-        } else if (il > 1 && j1 <= il) {
-            const double x = fma(j0, xs, bL1);
-            v = b4 * srdev::humliv_reg1_fast(fma(x, x, c1), c2);
-        } else {
-            v = 0.0;
+    // Three index ranges with one code path each (the per-point precedence of eval_window_point
+    // reduces to them: region 2 left [il, il2] when il2 > il, centre [core_lo, core_hi], region 2
+    // right [ir2, ir] when ir2 < ir; region 1 only ever appears at il / ir when that side has no
+    // region 2, and then the centre range covers the point).  Separate loops keep a warp on one
+    // formula except where regions 3 and 4 meet inside the centre.
+    const int lane = threadIdx.x & 31;
+    if (il2 > il)
+        for (int j1 = il + lane; j1 <= il2; j1 += 32) {
+            const double x = fma((double)(j1 - 1), xs, bL2);
+            dst[j1 - il] = srdev::humliv_reg2_eval(k2, x * x);
         }
-        dst[j1 - il] = v;
+    __syncwarp();   // (ranges can only overlap in degenerate geometry; keep the old precedence then)
+    for (int j1 = core_lo + lane; j1 <= core_hi; j1 += 32) {
+        const double x = lin[j1 - 1] + g;               // spect_classes.py:1455
+        dst[j1 - il] = srdev::humliv_core_fast(fabs(x - f) / dwp, ry);   // lineshape.f:527
     }
+    __syncwarp();
+    if (ir2 < ir)
+        for (int j1 = ir2 + lane; j1 <= ir; j1 += 32) {
+            const double x = fma((double)(j1 - 1), xs, bR2);
+            dst[j1 - il] = srdev::humliv_reg2_eval(k2, x * x);
+        }
+    (void)bL1; (void)bR1; (void)c1; (void)c2; (void)b4;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -338,6 +338,8 @@ struct FarArgs {
     const int* tile_rng;     // [n_tiles][n_groups][2]
     const int* grp_up;       // [n_groups] upper set of the group
     const int* grp_lo;       // [n_groups] lower set
+    const int* row_ptr;      // [n_sets*3 + 1] CSR: the groups that feed each output row,
+    const int* row_grp;      //                 ascending (3 entries per group in total)
     double* coef;            // [n_cells][n_tiles_window][n_sets*3][FAR_NN]
     int n_lines, n_groups, n_sets, tile_base, tp;
 };
@@ -359,8 +361,6 @@ __global__ void __launch_bounds__(FAR_NT) k_far_nodes(FarArgs a) {
     int* fl = reinterpret_cast<int*>(Msm + FAR_NN * FAR_NN);             // [FAR_CAP]
     int* cum = fl + FAR_CAP;                                             // [n_groups + 1]
     int* glo = cum + a.n_groups + 1;                                     // [n_groups]
-    int* gup = glo + a.n_groups;                                         // [n_groups] upper set
-    int* gls = gup + a.n_groups;                                         // [n_groups] lower set
     const int cell = blockIdx.y, tile_idx = a.tile_base + blockIdx.x;
     const int tile0 = tile_idx * a.tp, tile_last = tile0 + a.tp - 1;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -370,8 +370,6 @@ __global__ void __launch_bounds__(FAR_NT) k_far_nodes(FarArgs a) {
         const int2 rg = __ldg(reinterpret_cast<const int2*>(a.tile_rng) + (size_t)tile_idx * a.n_groups + g);
         glo[g] = rg.x;
         cum[g + 1] = rg.y - rg.x;
-        gup[g] = __ldg(a.grp_up + g);
-        gls[g] = __ldg(a.grp_lo + g);
     }
     for (int i = tid; i < a.n_groups * 3 * FAR_NN; i += FAR_NT) gsum[i] = 0.0;
     for (int i = tid; i < FAR_NN * FAR_NN; i += FAR_NT) Msm[i] = c_far_M[i];
@@ -449,10 +447,10 @@ __global__ void __launch_bounds__(FAR_NT) k_far_nodes(FarArgs a) {
     }
     // rows: sp / ind emission of a set = its groups as upper set, absorption = its groups as lower set
     for (int item = tid; item < n_rows * FAR_NN; item += FAR_NT) {
-        const int row = item / FAR_NN, n = item - row * FAR_NN, sset = row / 3, ct = row - sset * 3;
+        const int row = item / FAR_NN, n = item - row * FAR_NN, ct = row % 3;
         double sum = 0.0;
-        for (int g = 0; g < a.n_groups; g++)
-            if ((ct < 2 ? gup[g] : gls[g]) == sset) sum += gsum[((size_t)g * 3 + ct) * FAR_NN + n];
+        for (int e = __ldg(a.row_ptr + row); e < __ldg(a.row_ptr + row + 1); e++)
+            sum += gsum[((size_t)__ldg(a.row_grp + e) * 3 + ct) * FAR_NN + n];
         rowsum[item] = sum;
     }
     __syncthreads();
@@ -894,7 +892,7 @@ struct sr_lineset {
             if (ev_tile[b]) cudaEventDestroy(ev_tile[b]);
         }
     }
-    sr::DevBuf<int> grp_upidx, grp_loslot, up_list, lo_list, zero_rows, tile_rng;
+    sr::DevBuf<int> grp_upidx, grp_loslot, up_list, lo_list, zero_rows, tile_rng, far_rowptr, far_rowgrp;
     int n_up = 0, n_lo = 0, n_zero_rows = 0;
     int cfg = 0, tile_nt = 256, tile_ppt = 4, n_tiles = 0;   // tile geometry of the range table
     std::vector<int> order;    // sorted position -> input line
@@ -1122,6 +1120,21 @@ int sr_lineset_create(const sr_lines* lines, const double* grid, long n_grid,
             ls->n_up = (int)up_list.size();
             ls->n_lo = (int)lo_list.size();
             ls->n_zero_rows = (int)zrows.size();
+            {   // groups per output row (far-field row sums), ascending group order
+                const int n_rows = n_sets * 3;
+                std::vector<int> rp(n_rows + 1, 0), rg;
+                for (int g = 0; g < ls->n_groups; g++) { rp[gu[g] * 3 + 0 + 1]++; rp[gu[g] * 3 + 1 + 1]++; rp[gl[g] * 3 + 2 + 1]++; }
+                for (int r = 0; r < n_rows; r++) rp[r + 1] += rp[r];
+                rg.resize(rp[n_rows]);
+                std::vector<int> fillp(rp.begin(), rp.end() - 1);
+                for (int g = 0; g < ls->n_groups; g++) {
+                    rg[fillp[gu[g] * 3 + 0]++] = g;
+                    rg[fillp[gu[g] * 3 + 1]++] = g;
+                    rg[fillp[gl[g] * 3 + 2]++] = g;
+                }
+                SR_CUDA(ls->far_rowptr.upload(rp.data(), rp.size(), st));
+                if (!rg.empty()) SR_CUDA(ls->far_rowgrp.upload(rg.data(), rg.size(), st));
+            }
             SR_CUDA(ls->grp_upidx.upload(upidx.data(), upidx.size(), st));
             SR_CUDA(ls->grp_loslot.upload(loslot.data(), loslot.size(), st));
             SR_CUDA(ls->up_list.upload(up_list.data(), up_list.size(), st));
@@ -1313,6 +1326,8 @@ static int gcoeff_cells_impl(sr_lineset* ls, const double* pt_host, int n_cells,
             fa.tile_rng = ls->tile_rng.p;
             fa.grp_up = ls->grp_up.p;
             fa.grp_lo = ls->grp_lo.p;
+            fa.row_ptr = ls->far_rowptr.p;
+            fa.row_grp = ls->far_rowgrp.p;
             fa.coef = ls->far_b[buf].p;
             fa.n_lines = ls->n_act;
             fa.n_groups = ls->n_groups;
@@ -1321,7 +1336,7 @@ static int gcoeff_cells_impl(sr_lineset* ls, const double* pt_host, int n_cells,
             fa.tp = tp;
             const size_t fsmem = (8 * (size_t)FAR_CAP + ((size_t)ls->n_groups * 3 + n_rows) * FAR_NN +
                                   FAR_NN * FAR_NN) * sizeof(double) +
-                                 ((size_t)FAR_CAP + 4 * ls->n_groups + 1) * sizeof(int) + 16;
+                                 ((size_t)FAR_CAP + 2 * ls->n_groups + 1) * sizeof(int) + 16;
             SR_CUDA(cudaFuncSetAttribute(k_far_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
             SR_LAUNCH(k_far_nodes, dim3((unsigned)n_tiles_w, (unsigned)nb), FAR_NT, fsmem, ps, fa);
         }
