@@ -1,6 +1,6 @@
 // Micro-benchmark: FP64 tensor-core mma.sync (DMMA) throughput on sm_100a, alone and interleaved
 // with DFMA, to decide whether the K3a contraction / the K1 accumulations can use it.
-// nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o ub_dmma ub_dmma.cu
+// nvcc -O3 -gencode arch=compute_100a,code=sm_100a -cudart shared -o ub_dmma ub_dmma.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 __device__ __forceinline__ void mma884(double& c0, double& c1, double a, double b) {

@@ -1,6 +1,6 @@
 // Micro-benchmark: the region-1 evaluation sequence of k_voigt_tile (10 FP64 ops + MUFU.RCP64H per
 // eval) with parameters in registers, for different ILP / warps per SM.  Gives the ceiling the
-// tile kernel can reach with its instruction mix.  nvcc -O3 -gencode arch=compute_100a,code=sm_100a
+// tile kernel can reach with its instruction mix.  nvcc -O3 -gencode arch=compute_100a,code=sm_100a -cudart shared
 #include <cstdio>
 #include <cuda_runtime.h>
 __device__ __forceinline__ double rcp_approx(double x){double r; asm("rcp.approx.ftz.f64 %0, %1;":"=d"(r):"d"(x)); return r;}

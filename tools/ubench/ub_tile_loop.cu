@@ -1,7 +1,7 @@
 // Micro-benchmark: the far-wing record loop of k_voigt_tile exactly as the kernel runs it - 64-byte
 // HalfRec records broadcast from shared memory, PPT points per thread, two records per iteration -
 // to separate the ceiling of THIS loop from the rest of the kernel (loader, centres, stores).
-// nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o ub_tile_loop ub_tile_loop.cu
+// nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -cudart shared -o ub_tile_loop ub_tile_loop.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 struct __align__(16) HalfRec { double xs, b, c1, c2, g0, g1, g2; int lo; unsigned len; };
