@@ -123,7 +123,11 @@ int sr_lineset_centres(const sr_lineset* ls, int* ind_host); /* closest_grid ind
                                                                 (-1 for dropped lines) */
 
 /* G-coefficient spectra of n_cells (P,T) cells.  pt_host: [n_cells][2] = (P_hPa, T_K) on the
- * host.  out: [n_cells][n_sets][3][n_grid] doubles, ctype order sp_emission, ind_emission,
+ * host.  (Numerics: every point of regions 2/3/4 and of the near far wings is evaluated with the
+ * formulas of lineshape.f:443-562; in launches of two waves or more, region-1 wings that cover a
+ * whole 512-point tile from more than two tile lengths away are evaluated at 12 Chebyshev nodes
+ * per tile and interpolated, <= 4e-11 of the line's own value - DESIGN.md 4, K1; the environment
+ * variable SR_K1_FAR=0 evaluates every point.)  out: [n_cells][n_sets][3][n_grid] doubles, ctype order sp_emission, ind_emission,
  * absorption; every element is written (no zero-fill needed).
  * _dev: out is a DEVICE pointer, asynchronous on `stream`.  _host: out is a HOST pointer. */
 int sr_gcoeff_cells_dev(sr_lineset* ls, const double* pt_host, int n_cells, double* out_dev,
