@@ -613,7 +613,7 @@ def run_extras(args, P, engine, parallel, torch, dist, ls, lut, steps_all, grid_
         parallel.allreduce_lowres(lo)
         parallel.allreduce_lowres(jl)
         jac_call.res = (lo, jl)
-    jac_s = timed(jac_call, 2)
+    jac_s = timed(jac_call, 3)
     out["jacobian"] = {"value": n_j / jac_s, "unit": "LOS/s (radiance + %d derivative spectra each)" % n_par,
                        "los": n_j, "ms": 1e3 * jac_s, "finite": bool(torch.isfinite(jac_call.res[1]).all().item())}
     del dfrac
