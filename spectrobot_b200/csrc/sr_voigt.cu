@@ -352,6 +352,12 @@ constexpr int FAR_CAP = 512;   // candidates per pass
 // the wings that qualify and leaves the record in shared memory; then thread (node n, lane q) walks
 // the groups q, q+16, ... and, inside a group, the records in order - a single writer and a single
 // order per (group, node), so the sums do not depend on scheduling.
+// BIG (long line lists: thousands of candidates per tile, a slice then holds two or three groups):
+// the run of a group inside a slice that is >= 64 candidates long is shared by all 16 lanes
+// (candidate ca + q, ca + q + 16, ...), their partial sums are merged in lane order.
+constexpr int FAR_BIGN = 8;    // at most 512 / 64 long runs per slice
+
+template <bool BIG>
 __global__ void __launch_bounds__(FAR_NT) k_far_nodes(FarArgs a) {
     extern __shared__ __align__(16) unsigned char fraw[];
     double* rec = reinterpret_cast<double*>(fraw);                       // [8][FAR_CAP] xs bL bR c1 c2 g0 g1 g2
@@ -361,6 +367,10 @@ __global__ void __launch_bounds__(FAR_NT) k_far_nodes(FarArgs a) {
     int* fl = reinterpret_cast<int*>(Msm + FAR_NN * FAR_NN);             // [FAR_CAP]
     int* cum = fl + FAR_CAP;                                             // [n_groups + 1]
     int* glo = cum + a.n_groups + 1;                                     // [n_groups]
+    int* big = glo + a.n_groups;                                         // BIG: [1 + 3 * FAR_BIGN] n, g, ca, cb
+    double* gpart = reinterpret_cast<double*>(
+        fraw + ((reinterpret_cast<unsigned char*>(big + 1 + 3 * FAR_BIGN) - fraw + 15) / 16) * 16);
+                                                                         // BIG: [FAR_BIGN][16][3][FAR_NN]
     const int cell = blockIdx.y, tile_idx = a.tile_base + blockIdx.x;
     const int tile0 = tile_idx * a.tp, tile_last = tile0 + a.tp - 1;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -417,32 +427,68 @@ __global__ void __launch_bounds__(FAR_NT) k_far_nodes(FarArgs a) {
             }
         }
         __syncthreads();
+        // one candidate of the slice at this thread's node
+        auto eval = [&](int i, double& s0, double& s1, double& s2) {
+            const int flag = fl[i];
+            if (!flag) return;
+            const double xs = rec[i], c1 = rec[3 * FAR_CAP + i], c2 = rec[4 * FAR_CAP + i];
+            double kp = 0.0;
+            if (flag & 1) {
+                const double x = fma(Pn, xs, rec[1 * FAR_CAP + i]);
+                kp = srdev::humliv_reg1_u(fma(x, x, c1), c2);
+            }
+            if (flag & 2) {
+                const double x = fma(Pn, xs, rec[2 * FAR_CAP + i]);
+                kp += srdev::humliv_reg1_u(fma(x, x, c1), c2);
+            }
+            s0 = fma(rec[5 * FAR_CAP + i], kp, s0);
+            s1 = fma(rec[6 * FAR_CAP + i], kp, s1);
+            s2 = fma(rec[7 * FAR_CAP + i], kp, s2);
+        };
+        if (BIG) {   // the long runs of this slice
+            if (tid == 0) {
+                int nb = 0;
+                for (int g = 0; g < a.n_groups && nb < FAR_BIGN; g++) {
+                    const int ca = max(cum[g], f0), cb = min(cum[g + 1], f1);
+                    if (cb - ca >= 64) { big[1 + nb] = g; big[1 + FAR_BIGN + nb] = ca; big[1 + 2 * FAR_BIGN + nb] = cb; nb++; }
+                }
+                big[0] = nb;
+            }
+            __syncthreads();
+        }
+        const int n_big = BIG ? big[0] : 0;
         if (node < FAR_NN)
             for (int g = q; g < a.n_groups; g += FAR_NT / 16) {
                 const int ca = max(cum[g], f0), cb = min(cum[g + 1], f1);
                 if (cb <= ca) continue;
+                bool is_big = false;
+                for (int b = 0; b < n_big; b++) is_big = is_big || big[1 + b] == g;
+                if (is_big) continue;
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-                for (int c = ca; c < cb; c++) {
-                    const int i = c - f0, flag = fl[i];
-                    if (!flag) continue;
-                    const double xs = rec[i], c1 = rec[3 * FAR_CAP + i], c2 = rec[4 * FAR_CAP + i];
-                    double kp = 0.0;
-                    if (flag & 1) {
-                        const double x = fma(Pn, xs, rec[1 * FAR_CAP + i]);
-                        kp = srdev::humliv_reg1_u(fma(x, x, c1), c2);
-                    }
-                    if (flag & 2) {
-                        const double x = fma(Pn, xs, rec[2 * FAR_CAP + i]);
-                        kp += srdev::humliv_reg1_u(fma(x, x, c1), c2);
-                    }
-                    s0 = fma(rec[5 * FAR_CAP + i], kp, s0);
-                    s1 = fma(rec[6 * FAR_CAP + i], kp, s1);
-                    s2 = fma(rec[7 * FAR_CAP + i], kp, s2);
-                }
+                for (int c = ca; c < cb; c++) eval(c - f0, s0, s1, s2);
                 gsum[((size_t)g * 3 + 0) * FAR_NN + node] += s0;
                 gsum[((size_t)g * 3 + 1) * FAR_NN + node] += s1;
                 gsum[((size_t)g * 3 + 2) * FAR_NN + node] += s2;
             }
+        if (BIG && n_big > 0) {
+            if (node < FAR_NN)
+                for (int b = 0; b < n_big; b++) {
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                    for (int c = big[1 + FAR_BIGN + b] + q; c < big[1 + 2 * FAR_BIGN + b]; c += 16)
+                        eval(c - f0, s0, s1, s2);
+                    double* o = gpart + (((size_t)b * 16 + q) * 3) * FAR_NN + node;
+                    o[0] = s0;
+                    o[FAR_NN] = s1;
+                    o[2 * FAR_NN] = s2;
+                }
+            __syncthreads();
+            for (int item = tid; item < n_big * 3 * FAR_NN; item += FAR_NT) {   // lanes in order
+                const int b = item / (3 * FAR_NN), r = item - b * 3 * FAR_NN;
+                double sum = 0.0;
+                for (int l = 0; l < 16; l++) sum += gpart[((size_t)b * 16 + l) * 3 * FAR_NN + r];
+                gsum[(size_t)big[1 + b] * 3 * FAR_NN + r] += sum;
+            }
+        }
         __syncthreads();
     }
     // rows: sp / ind emission of a set = its groups as upper set, absorption = its groups as lower set
@@ -893,6 +939,7 @@ struct sr_lineset {
         }
     }
     sr::DevBuf<int> grp_upidx, grp_loslot, up_list, lo_list, zero_rows, tile_rng, far_rowptr, far_rowgrp;
+    long ind_span = 1;        // centre-index span of the active lines (line density for k_far_nodes)
     int n_up = 0, n_lo = 0, n_zero_rows = 0;
     int cfg = 0, tile_nt = 256, tile_ppt = 4, n_tiles = 0;   // tile geometry of the range table
     std::vector<int> order;    // sorted position -> input line
@@ -1050,6 +1097,7 @@ int sr_lineset_create(const sr_lines* lines, const double* grid, long n_grid,
                                 cudaMemcpyDeviceToHost, st));
         SR_CUDA(cudaStreamSynchronize(st));
         for (int i = 0; i < n_act; i++) ls->ind_in[act[i]] = ind[i];
+        ls->ind_span = (long)*std::max_element(ind.begin(), ind.end()) - *std::min_element(ind.begin(), ind.end()) + 1;
         // sort by (group, centre index, input position)
         std::vector<int> perm(n_act);
         std::iota(perm.begin(), perm.end(), 0);
@@ -1300,8 +1348,13 @@ static int gcoeff_cells_impl(sr_lineset* ls, const double* pt_host, int n_cells,
     const long n_tiles_w = (win_n + tp - 1) / tp;
     // (the extra kernel pays when a launch has at least two waves of CTAs; a single cell on a
     // narrow slab - half a wave - is faster point by point.  SR_K1_FAR=2 forces it.)
+    // long line lists (thousands of candidates per tile): the far field pays even for half a wave,
+    // and k_far_nodes shares the long runs of a group among its lanes
+    const double cand_per_tile =
+        (double)ls->n_act * (double)(N_WIN + tp) / (double)std::max<long>(ls->ind_span, N_WIN);
+    const bool far_big = cand_per_tile > 1024.0;
     const bool use_far = far_env != 0 && ls->far_ok && win0 % tp == 0 &&
-                         (far_env == 2 || n_tiles_w * std::min(sub, n_cells) >= 2L * 148 * 4);
+                         (far_env == 2 || far_big || n_tiles_w * std::min(sub, n_cells) >= 2L * 148 * 4);
     const int far_cap_cells = std::max(std::min(sub, n_cells), std::min(ls->max_cells_per_batch, pipe ? sub : 16));
     const size_t core_cap = (size_t)std::max(std::min(sub, n_cells),
                                              std::min(ls->max_cells_per_batch, pipe ? sub : 16)) *
@@ -1337,8 +1390,15 @@ static int gcoeff_cells_impl(sr_lineset* ls, const double* pt_host, int n_cells,
             const size_t fsmem = (8 * (size_t)FAR_CAP + ((size_t)ls->n_groups * 3 + n_rows) * FAR_NN +
                                   FAR_NN * FAR_NN) * sizeof(double) +
                                  ((size_t)FAR_CAP + 2 * ls->n_groups + 1) * sizeof(int) + 16;
-            SR_CUDA(cudaFuncSetAttribute(k_far_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            SR_LAUNCH(k_far_nodes, dim3((unsigned)n_tiles_w, (unsigned)nb), FAR_NT, fsmem, ps, fa);
+            if (far_big) {
+                const size_t bsmem = fsmem + (1 + 3 * FAR_BIGN) * sizeof(int) + 16 +
+                                     (size_t)FAR_BIGN * 16 * 3 * FAR_NN * sizeof(double);
+                SR_CUDA(cudaFuncSetAttribute(k_far_nodes<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+                SR_LAUNCH(k_far_nodes<true>, dim3((unsigned)n_tiles_w, (unsigned)nb), FAR_NT, bsmem, ps, fa);
+            } else {
+                SR_CUDA(cudaFuncSetAttribute(k_far_nodes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                SR_LAUNCH(k_far_nodes<false>, dim3((unsigned)n_tiles_w, (unsigned)nb), FAR_NT, fsmem, ps, fa);
+            }
         }
         if (pipe) SR_CUDA(cudaEventRecord(ls->ev_core[buf], ps));
         return SR_OK;

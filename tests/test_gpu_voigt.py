@@ -236,14 +236,15 @@ def test_cell_batches_are_invisible(sb, monkeypatch):
     assert np.array_equal(ls.gcoeff_cells_host(cells), base.cpu().numpy())
 
 
-def test_far_field_of_the_far_wings_is_invisible(monkeypatch):
+@pytest.mark.parametrize("n_lines", [2500, 7000])     # 7000: > 1024 candidates per tile, long-run variant
+def test_far_field_of_the_far_wings_is_invisible(monkeypatch, n_lines):
     """k_far_nodes (distant full far wings evaluated at 12 Chebyshev nodes per tile and interpolated)
     against the point-by-point evaluation (SR_K1_FAR=0): <= 1e-9 of the largest value of a row, over
     Titan-like and high pressures (ry from 1e-3 to ~50) and both storage types."""
     import torch
     from spectrobot_b200 import engine, synthetic as S
     g = S.spectral_grid(2990.0, 3010.0)                       # 40 001 points: lines up to 3 windows away
-    lines = S.line_table(3000, 2986.0, 3014.0, n_levels=6, seed=21)
+    lines = S.line_table(n_lines, 2986.0, 3014.0, n_levels=6, seed=21)
     ls = engine.LineSet(lines, g, S.CH4_MM, 6)
     cells = [[1e-4, 120.0], [0.05, 160.0], [2.5, 175.0], [150.0, 200.0], [1500.0, 94.0]]
     monkeypatch.setenv("SR_K1_FAR", "0")
