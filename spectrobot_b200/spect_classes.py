@@ -12,7 +12,10 @@ What differs is where the arithmetic runs: per-line Python loops, fork/Queue fan
 f2py modules are replaced by batched calls into the CUDA library (engine.LineSet), and the level
 book-keeping by string comparison (spect_classes.py:1304-1313) is resolved once into integer set
 ids (`line_table`).  `read_line_database` parses HITRAN / "gbb" fixed-width files (SURVEY 8f row
-3).  Unit conversions, plotting and `degrade_grid*` are out of scope.
+3).  The host-side helpers of SpectralObject (slicing, arithmetic, re-gridding, degrade_grid /
+degrade_grid2, the older convolve_to_grid chain) and the scalar shape / black-body helpers are
+plain NumPy restatements pinned by tests/test_ref_golden2.py.  Not here: plotting (`plot`,
+`norm_plot`) and `degrade_grid3`, which raises NameError in the reference.
 """
 import copy
 import math as mt
@@ -145,6 +148,116 @@ def MakeShape(wn_arr, wn_0, lw, dw, Strength=1.0):
     return SpectralObject(Strength * y / fac, wn_arr)
 
 
+def closest_grid_ext(wn_arr, wn_0):
+    """closest_grid for a wavenumber that may lie outside the grid: the grid is continued with its
+    own step beyond the end that wn_0 passes (:1945-1964).  The index is that of the continued
+    grid (negative below the start)."""
+    g, step = wn_arr.grid, wn_arr.step()
+    if (g[0] <= wn_0 <= g[-1]) or sbm.isclose(wn_0, g[0]) or sbm.isclose(wn_0, g[-1]):
+        ind = int(np.argmin(np.abs(g - wn_0)))
+        return ind, g[ind]
+    if wn_0 < g[0]:
+        ext = np.arange(g[0], wn_0 - step, -step)
+        ind = int(np.argmin(np.abs(ext - wn_0)))
+        return -ind, ext[ind]
+    ext = np.arange(g[-1], wn_0 + step, step)
+    ind = int(np.argmin(np.abs(ext - wn_0)))
+    return len(g) + ind, ext[ind]
+
+
+def Lorentz_shape(wn, wn_0, lw):
+    """Normalised Lorentzian of HWHM lw (:1906-1913)."""
+    return 1 / np.pi * lw / (lw ** 2 + (wn - wn_0) ** 2)
+
+
+def Doppler_shape(wn, wn_0, dw):
+    """Normalised Gaussian of HWHM dw (:1916-1923)."""
+    return mt.sqrt(mt.log(2.0) / (np.pi * dw ** 2)) * np.exp(-(wn - wn_0) ** 2 * mt.log(2.0) / dw ** 2)
+
+
+def MakeShape_py(wn_arr, wn_0, lw, dw, Strength=1.0):
+    """Voigt profile as the discrete convolution of the two shapes on the grid (:2011-2026); the
+    reference's pure-Python cross-check of MakeShape."""
+    lor = Lorentz_shape(wn_arr.grid - wn_0, 0.0, lw)
+    dop = Doppler_shape(wn_arr.grid - wn_0, 0.0, dw)
+    return SpectralObject(np.convolve(dop, lor, mode='same') * wn_arr.step() * Strength, wn_arr)
+
+
+def Einstein_A_to_LineStrength_hitran(A_coeff, wavenumber, temp, Q_part, g_upper, E_lower, iso_ab=1.0):
+    """LTE line strength in cm-1/(molecule cm-2) from the Einstein A (:1856-1863)."""
+    return iso_ab * A_coeff * g_upper * np.exp(-c2 * E_lower / temp) * \
+        (1 - np.exp(-c2 * wavenumber / temp)) / (8 * np.pi * c_cgs * wavenumber ** 2 * Q_part)
+
+
+def Boltz_pop_at_T(wavenumber, temp, g_level, Q_part):
+    """LTE population of a level (:1866-1873)."""
+    return g_level * Boltz_ratio_nodeg(wavenumber, temp) / Q_part
+
+
+def alpha_nlte(Freq, Temp, r1, r2):
+    """Non-LTE correction of the absorption strength for population ratios r1 (lower), r2 (upper)
+    (:1485-1488)."""
+    Gm = Boltz_ratio_nodeg(Freq, Temp)
+    return r1 * (1 - Gm * r2 / r1) / (1 - Gm)
+
+
+def Calc_BB_single(nu, T):
+    """Planck function in erg/(s cm2 sr cm-1) at wavenumber nu (:1895-1903)."""
+    return 2 * h_cgs * c_cgs ** 2 * nu ** 3 / (np.exp(c2 * nu / T) - 1)
+
+
+def Calc_BB(spectral_grid, T, units='ergscm2'):
+    """SpectralIntensity with the Planck spectrum at T on a cm-1 grid (:1881-1892)."""
+    out = SpectralIntensity(Calc_BB_single(spectral_grid.grid, T), spectral_grid, units='ergscm2')
+    if units != 'ergscm2':
+        out.convertto(units)
+    return out
+
+
+def BB(T, w):
+    """Black body in nW/(cm2 sr cm-1) with the reference's rounded constants (:2080-2092)."""
+    return 1.1904e-3 * w ** 3 / (mt.exp(w * 1.4388 / T) - 1)
+
+
+def BB_erg(T, w):
+    """Black body in erg/(s cm2 sr cm-1), rounded constants (:2095-2107)."""
+    return 1.1904e-5 * w ** 3 / (mt.exp(w * 1.4388 / T) - 1)
+
+
+def BB_nm(T, w):
+    """Black body in W/(m2 sr nm) at wavelength w in nm; Wien form for T*w <= 5e5 (:2110-2125)."""
+    if T * w > 5e5:
+        return 1.1904 * mt.pow(1.e4 / w, 5) / (mt.exp(1.e7 / w * 1.4388 / T) - 1)
+    return 1.1904 * mt.pow(1.e4 / w, 5) * mt.exp(-1.e7 / w * 1.4388 / T)
+
+
+def convert_cm_1_to_J(w):
+    return const.h * 1.e2 * const.c * w
+
+
+def convert_J_to_eV(J):
+    """Joule -> eV.  (The reference's body returns its argument unchanged, :2047-2049, and its
+    convert_cm_1_to_eV raises NameError, :2043-2045; both are given their evident meaning.)"""
+    return J / const.eV
+
+
+def convert_cm_1_to_eV(w):
+    return convert_J_to_eV(convert_cm_1_to_J(w))
+
+
+def read_mw_list(db_cart, nome='mw_list.dat'):
+    """(n, tags, [w1, w2] ranges) of a microwindow list file (:1465-1482): the count on the first
+    line, then `index tag w1 w2` per line."""
+    with open(db_cart + nome, 'r') as f:
+        n_mws = int(f.readline())
+        tags, ranges = [], []
+        for _ in range(n_mws):
+            tok = f.readline().split()
+            tags.append(tok[1])
+            ranges.append([float(tok[2]), float(tok[3])])
+    return n_mws, tags, ranges
+
+
 # ---------------------------------------------------------------------------------------------
 # SpectLine
 # ---------------------------------------------------------------------------------------------
@@ -169,8 +282,51 @@ class SpectLine(object):
         self.E_vib_up = None
         self.E_vib_lo = None
 
+    def Print(self, ofile=None):
+        """Short listing of the line (:93-98); the file form leaves the rotational quanta out."""
+        if ofile is None:
+            print('{:4d}{:2d}{:8.2f}{:10.3e}{:8.2f}{:15s}{:15s}{:15s}{:15s}{:8.3f}{:8.3f}'.format(
+                self.Mol, self.Iso, self.Freq, self.Strength, self.E_lower, self.Up_lev_str,
+                self.Lo_lev_str, self.Q_num_up, self.Q_num_lo, self.g_up, self.g_lo))
+        else:
+            ofile.write('{:4d}{:2d}{:8.2f}{:10.3e}{:8.2f}{:15s}{:15s}{:8.3f}{:8.3f}\n'.format(
+                self.Mol, self.Iso, self.Freq, self.Strength, self.E_lower, self.Up_lev_str,
+                self.Lo_lev_str, self.g_up, self.g_lo))
+
+    def Print_hitran(self, ofile=None):
+        """The line as a HITRAN-like record with the reference's own field formats (:100-109);
+        format_line_record writes the fixed-width layout read_line_database reads back."""
+        oth = '' if self.others is None else self.others
+        stringa = ('{:2d}{:1d}{:12.6f}{:10.3e}{:10.3e}{:5.3f}{:5.3f}{:10.4f}{:4.2f}{:8.5f}{:15s}{:15s}'
+                   '{:15s}{:15s}{:19s}{:7.2f}{:7.2f}').format(
+            self.Mol, self.Iso, self.Freq, self.Strength, self.A_coeff, self.Air_broad,
+            self.Self_broad, self.E_lower, self.T_dep_broad, self.P_shift, self.Up_lev_str,
+            self.Lo_lev_str, self.Q_num_up, self.Q_num_lo, oth, self.g_up, self.g_lo)
+        if ofile is None:
+            print(stringa)
+        else:
+            ofile.write(stringa + '\n')
+        return stringa
+
+    def ShowCalc(self, T, P=1, nlte_ratio=1):
+        pass
+
     def CalcStrength(self, T):
         return CalcStrength_at_T(self.Mol, self.Iso, self.Strength, self.Freq, self.E_lower, T)
+
+    def CalcStrength_from_Strength(self, Temp, Q_part=None, iso_ab=None, isomolec=None,
+                                   T_vib_lower=None, T_vib_upper=None, E_vib_lo=None, E_vib_up=None):
+        """(absorption, emission) strengths in non-LTE from the tabulated strength at 296 K
+        (:256-288): S(T) x alpha_nlte(r1, r2) and S(T) x r2 x BB_erg(T, nu), r = non-LTE / LTE
+        population ratio of the lower / upper vibrational level."""
+        T_vib_lower = Temp if T_vib_lower is None else T_vib_lower
+        T_vib_upper = Temp if T_vib_upper is None else T_vib_upper
+        if E_vib_lo is None and E_vib_up is None:
+            E_vib_lo, E_vib_up = self.E_vib_lo, self.E_vib_up
+        r1 = sbm.vibtemp_to_ratio(E_vib_lo, T_vib_lower, Temp)
+        r2 = sbm.vibtemp_to_ratio(E_vib_up, T_vib_upper, Temp)
+        S = self.CalcStrength(Temp)
+        return S * alpha_nlte(self.Freq, Temp, r1, r2), S * r2 * BB_erg(Temp, self.Freq)
 
     def minimal_level_string_up(self):
         return sbm.extract_quanta_HITRAN(self.Mol, self.Iso, self.Up_lev_str)[0]
@@ -488,6 +644,78 @@ def calc_shapes_lines(wn_arr, lines, Temp, Pres, isomolec, n_threads=n_threads):
     return [lines[i] for i in sorted(order)]
 
 
+def PrepareCalcShapes(wn_arr, linee_mol, Temp, Pres, isomolec):
+    """Core of the reference's worker (:1440-1462): shape (on the 13010-point window centred on the
+    grid point nearest to the line) and G coefficients attached to EVERY line of linee_mol - no
+    level filter, lines that cannot be linked get E_vib = 0 (:318-324).  One batched GPU call."""
+    lines = list(linee_mol)
+    if len(lines) == 0:
+        return lines
+    grid = wn_arr.grid if hasattr(wn_arr, 'grid') else np.asarray(wn_arr)
+    tab = line_table(lines, None)                 # one set: every line is evaluated
+    if len(isomolec.levels) > 0:
+        for i, lin in enumerate(lines):
+            ok = lin.LinkToMolec(isomolec)
+            tab["e_vib_up"][i] = lin.E_vib_up if ok else 0.0
+            tab["e_vib_lo"][i] = lin.E_vib_lo if ok else 0.0
+    ls = engine.LineSet(tab, grid, isomolec.MM, 1)
+    shapes, g = ls.line_shapes(Pres, Temp)
+    shapes, g = shapes.cpu().numpy(), g.cpu().numpy()
+    order, centres = ls.order(), ls.centres()
+    lin_grid = engine.line_window_offsets(grid)
+    for pos, src in enumerate(order):
+        lin = lines[src]
+        lin.shape = SpectralObject(shapes[pos], SpectralGrid(lin_grid + grid[centres[src]], units='cm_1'))
+        lin.G_coeffs = dict(zip(CTYPES, g[pos]))
+    ls.close()
+    return lines
+
+
+def do_for_th_calc(wn_arr, linee_tot, Temp, Pres, isomolec, i, coda, n_threads=n_threads):
+    """The reference's per-process worker (:1418-1437): slice i of n_threads of the line list
+    through PrepareCalcShapes, result on the queue `coda` (anything with .put)."""
+    step_nlin = len(linee_tot) // n_threads
+    linee = linee_tot[step_nlin * i:] if i == n_threads - 1 else \
+        linee_tot[step_nlin * i:step_nlin * (i + 1)]
+    coda.put(PrepareCalcShapes(wn_arr, linee, Temp, Pres, isomolec))
+
+
+def sum_strength_lowres(lines, wn_range, mol, iso, Temp=None, ratios=None, res=5.0, plot=True):
+    """Band-by-band sum of the line strengths in bins of `res` cm-1 (:1490-1529).  The reference
+    only plots; here the sums are returned as (bin centres, {(upper, lower): array}) and plotted
+    when matplotlib is importable and plot is True.  With Temp the strengths are the absorption
+    strengths of CalcStrength_from_Einstein(Temp)."""
+    arr_low = np.arange(wn_range[0], wn_range[1] + res / 2., res)
+    mine = [lin for lin in lines if lin.Mol == mol and lin.Iso == iso]
+    ups = [lin.minimal_level_string_up() for lin in mine]
+    los = [lin.minimal_level_string_lo() for lin in mine]
+    out = dict()
+    for lev1 in np.unique(ups):
+        for lev2 in np.unique(los):
+            band = [lin for lin, u, l in zip(mine, ups, los) if u == lev1 and l == lev2]
+            if len(band) == 0:
+                continue
+            freqs = np.array([lin.Freq for lin in band])
+            if Temp is None:
+                strengths = np.array([lin.Strength for lin in band])
+            else:
+                strengths = np.array([lin.CalcStrength_from_Einstein(Temp)[0] for lin in band])
+            ratio = 1.0 if ratios is None else ratios[lev1]
+            out[(str(lev1), str(lev2))] = np.array(
+                [ratio * np.sum(strengths[(freqs > fr - res / 2.0) & (freqs < fr + res / 2.0)])
+                 for fr in arr_low])
+    if plot:
+        try:
+            import matplotlib.pyplot as pl
+            for (lev1, lev2), spet in out.items():
+                pl.plot(arr_low, spet, label=lev1 + ' -> ' + lev2)
+            pl.legend()
+            pl.grid()
+        except ImportError:
+            pass
+    return arr_low, out
+
+
 # ---------------------------------------------------------------------------------------------
 # spectral containers
 # ---------------------------------------------------------------------------------------------
@@ -588,14 +816,36 @@ class SpectralObject(object):
     def _other(self, obj2):
         return obj2.spectrum if isinstance(obj2, SpectralObject) else obj2
 
-    def __add__(self, obj2):
+    def __getitem__(self, key):
+        """self[w1, w2]: the part of the spectrum between w1 and w2, half a step of margin on both
+        sides (:451-460); None when no grid point falls inside.  As in the reference the new
+        SpectralGrid takes `self.units` (the units of the ordinate) as its units."""
+        g = self.spectral_grid.grid
+        half = self.spectral_grid.step() / 2.0
+        cond = (g > key[0] - half) & (g < key[1] + half)
+        if not np.any(cond):
+            return None
         out = copy.deepcopy(self)
-        out.spectrum = self.spectrum + self._other(obj2)
+        out.spectral_grid = SpectralGrid(g[cond], units=self.units)
+        out.spectrum = self.spectrum[cond]
+        return out
+
+    def __add__(self, obj2):
+        """Spectra of the same length add point by point; a shorter spectrum on the same step is
+        added where the grids overlap (add_to_spectrum, :462-472)."""
+        out = copy.deepcopy(self)
+        if isinstance(obj2, SpectralObject) and len(obj2.spectrum) != len(self.spectrum):
+            out.add_to_spectrum(obj2)
+        else:
+            out.spectrum = self.spectrum + self._other(obj2)
         return out
 
     def __sub__(self, obj2):
         out = copy.deepcopy(self)
-        out.spectrum = self.spectrum - self._other(obj2)
+        if isinstance(obj2, SpectralObject) and len(obj2.spectrum) != len(self.spectrum):
+            out.add_to_spectrum(obj2, Strength=-1.0)
+        else:
+            out.spectrum = self.spectrum - self._other(obj2)
         return out
 
     def __mul__(self, obj2):
@@ -619,6 +869,9 @@ class SpectralObject(object):
     def n_points(self):
         return len(self.spectrum)
 
+    def add_mask(self, mask):
+        self.mask = mask
+
     def multiply(self, factor, save=True):
         if save:
             self.spectrum = self.spectrum * factor
@@ -627,6 +880,112 @@ class SpectralObject(object):
         out.spectrum = self.spectrum * factor
         return out
 
+    def exp_elementwise(self, exp_factor, save=False):
+        """exp(spectrum * exp_factor) (:693-701)."""
+        new = np.exp(self.spectrum * exp_factor)
+        if save:
+            self.spectrum = new
+            return None
+        out = copy.deepcopy(self)
+        out.spectrum = new
+        return out
+
+    def multiply_elementwise(self, spectrum2, save=True):
+        """(:975-990)"""
+        if len(self.spectrum) != len(spectrum2.spectrum):
+            raise ValueError('The two spectra have different lengths!')
+        new = spectrum2.spectrum * self.spectrum
+        if save:
+            self.spectrum = new
+            return None
+        out = copy.deepcopy(self)
+        out.spectrum = new
+        return out
+
+    def divide_elementwise(self, spectrum2, save=True):
+        """(:993-1008)"""
+        if len(self.spectrum) != len(spectrum2.spectrum):
+            raise ValueError('The two spectra have different lengths!')
+        new = self.spectrum / spectrum2.spectrum
+        if save:
+            self.spectrum = new
+            return None
+        out = copy.deepcopy(self)
+        out.spectrum = new
+        return out
+
+    def sum_scalar(self, scalar):
+        self.spectrum = self.spectrum + scalar
+        return self.spectrum
+
+    def interp_to_grid(self, nugrid):
+        """Linear interpolation to another SpectralGrid, zero outside this one (:501-507)."""
+        out = copy.deepcopy(self)
+        out.spectrum = np.interp(nugrid.grid, self.spectral_grid.grid, self.spectrum, left=0.0,
+                                 right=0.0)
+        out.spectral_grid = copy.deepcopy(nugrid)
+        return out
+
+    def interp_to_regular_grid(self):
+        """In place: the same number of points, evenly spaced between the ends (:920-927)."""
+        g = self.spectral_grid.grid
+        new = SpectralGrid(np.linspace(np.min(g), np.max(g), len(g)), units=self.spectral_grid.units)
+        self.spectrum = np.interp(new.grid, g, self.spectrum)
+        self.spectral_grid = new
+
+    def _significant(self, thres, stride=1, consider_derivatives=True):
+        """Points (every `stride`-th) where the spectrum, or its first / second np.gradient, exceeds
+        thres x its own maximum - the selection rule of degrade_grid / degrade_grid2."""
+        oks = self.spectrum[::stride] > thres * self.max()
+        if consider_derivatives:
+            d1 = np.gradient(self.spectrum)
+            d2 = np.abs(np.gradient(d1))
+            d1 = np.abs(d1)
+            oks = oks | (d1[::stride] > thres * np.max(d1)) | (d2[::stride] > thres * np.max(d2))
+        return oks
+
+    def degrade_grid(self, thress=(1.e-3, 1.e-4, 1.e-5), factors=(5, 20, 100),
+                     consider_derivatives=True):
+        """Irregular grid that keeps full resolution where the spectrum (or a derivative) is above
+        thress[0] x max, every factors[0]-th point above thress[1] x max, and every
+        factors[-1]-th point everywhere; the spectrum is interpolated onto it (:509-547).  As in
+        the reference only the first two thresholds and the strides (1, factors[0]) enter, plus
+        the coarsest stride factors[-1]."""
+        strides = [1] + list(factors)
+        g = self.spectral_grid.grid
+        keep = [g[::strides[-1]]]
+        for thres, stride in list(zip(thress, strides[:-1]))[:2]:
+            keep.append(g[::stride][self._significant(thres, stride, consider_derivatives)])
+        new = SpectralGrid(np.unique(np.concatenate(keep)), units=self.spectral_grid.units)
+        return self.interp_to_grid(new)
+
+    def degrade_grid2(self, thres=1.e-4, num_aside=(10, 5, 5), res_low=(1, 2, 5),
+                      consider_derivatives=True):
+        """Keeps the points above thres x max (spectrum or derivatives) and, around them, num_aside[k]
+        rings of neighbours at distance (i+1)*res_low[k], of which every res_low[k]-th candidate (in
+        index order) is taken (:549-600)."""
+        n = len(self.spectrum)
+        hi = np.flatnonzero(self._significant(thres, 1, consider_derivatives))
+        if len(hi) == 0:
+            raise IndexError('no point above the threshold')
+        part = hi
+        for num, res in zip(num_aside, res_low):
+            for i in range(num):
+                up = hi + (i + 1) * res
+                part = np.unique(np.append(part, up[up < n][::res]))
+                dn = hi - (i + 1) * res
+                part = np.unique(np.append(part, dn[dn >= 0][::res]))
+            hi = part
+        new = SpectralGrid(self.spectral_grid.grid[np.unique(hi)], units=self.spectral_grid.units)
+        return self.interp_to_grid(new)
+
+    def compress_spectrum(self, threshold=1.e-25):
+        """Spectrum as a scipy.sparse.csr_matrix with the values below threshold zeroed (:748-755)."""
+        import scipy.sparse
+        coso = self.spectrum
+        coso[self.spectrum < threshold] = 0.0
+        self.spectrum = scipy.sparse.csr_matrix(coso)
+
     def erase_grid(self):
         self.spectral_grid = None
 
@@ -634,10 +993,16 @@ class SpectralObject(object):
         self.spectral_grid = spectral_grid if link_grid else copy.deepcopy(spectral_grid)
 
     def half_precision(self):
+        """float32 spectrum (the reference's "half" precision, :722-737); a grid that is still
+        attached goes to float16 like SpectralGrid.half_precision does."""
         self.spectrum = self.spectrum.astype(np.float32)
+        if self.spectral_grid is not None:
+            self.spectral_grid.half_precision()
 
     def double_precision(self):
         self.spectrum = self.spectrum.astype(np.float64)
+        if self.spectral_grid is not None:
+            self.spectral_grid.double_precision()
 
     # spectral density per unit of the axis: converting the axis multiplies by |d old / d new|
     # and, between wavelength-like and wavenumber-like axes, reverses the arrays (:753-797)
@@ -712,19 +1077,73 @@ class SpectralObject(object):
             out.intensity = out.spectrum
         return out
 
-    def add_lines_to_spectrum(self, lines, Strengths=None, fix_length=imxsig, n_threads=n_threads):
-        """Adds line shapes (SpectralObjects on their own 13010-point windows) to this spectrum
-        through the sum_all_lines drop-in (:1016-1097).  Window clipping follows
-        prepare_fortran_sum (:1100-1147): points of the line inside the spectrum range (tolerance
-        step/10) are kept, the rest of the 13010-wide row is zero padding on the right, or on the
-        left with a shifted start when the window sticks out at the high end."""
+    def convolve_to_grid(self, new_spectral_grid, spectral_widths=None, conv_type='gaussian',
+                         n_sigma=5.):
+        """Gaussian convolution of a spectrum on a REGULAR grid to another grid, the reference's
+        older host routine (:832-881; hires_to_lowres_old and tolowres use it): one window of
+        2*int(n_sigma*max width/step) points of the old step, centred on the old grid point
+        nearest to every new point (closest_grid_ext extrapolates the grid outside the range),
+        the part of the spectrum inside it zero-extended to the window and integrated against the
+        Gaussian with the trapezoid rule.  Host NumPy; the batched device convolution is
+        convolve_to_grid_from_irregular."""
+        if conv_type != 'gaussian':
+            raise ValueError('only the gaussian convolution exists in the reference')
+        new_len = len(new_spectral_grid.grid)
+        weed = new_spectral_grid.step() if spectral_widths is None else max(spectral_widths)
+        step_old = self.spectral_grid.step()
+        n_points = int(n_sigma * weed / step_old)
+        lin_grid = np.arange(-n_points * step_old, n_points * step_old, step_old, dtype=float)
+        if spectral_widths is None:
+            window = gaussian(lin_grid, 0.0, new_spectral_grid.step())
+            spectral_widths = [None] * new_len
+        spectrum = np.zeros(new_len, dtype=float)
+        for num, (freq, wid) in enumerate(zip(new_spectral_grid.grid, spectral_widths)):
+            if wid is not None:
+                window = gaussian(lin_grid, 0.0, wid)
+            _, fr_ok = closest_grid_ext(self.spectral_grid, freq)
+            win_grid = SpectralGrid(lin_grid + fr_ok, units=self.spectral_grid.units)
+            old = self[win_grid.grid[0], win_grid.grid[-1]]
+            if old is None:
+                continue
+            if len(old.spectrum) < len(window):
+                zero = SpectralObject(np.zeros(len(win_grid.grid)), win_grid)
+                zero.add_to_spectrum(old)
+                old = zero
+            spectrum[num] = conv_single(old, window, new_spectral_grid.step())
+        out = copy.deepcopy(self)
+        out.spectral_grid = copy.deepcopy(new_spectral_grid)
+        out.spectrum = spectrum
+        if hasattr(out, 'intensity'):
+            out.intensity = out.spectrum
+        return out
+
+    def add_to_spectrum(self, spectrum2, Strength=None, sumcheck=10.):
+        """Adds a spectrum whose grid lies (partly) inside this one and has the SAME step, where
+        the two overlap (tolerance step/10 at the ends, :929-953)."""
+        g, g2 = self.spectral_grid.grid, spectrum2.spectral_grid.grid
+        spino = self.spectral_grid.step() / 10.
+        ok = (g > g2[0] - spino) & (g < g2[-1] + spino)
+        ok2 = (g2 > g[0] - spino) & (g2 < g[-1] + spino)
+        if Strength is not None:
+            self.spectrum[ok] += Strength * spectrum2.spectrum[ok2]
+        else:
+            self.spectrum[ok] += spectrum2.spectrum[ok2]
+
+    def add_to_spectrum_slow(self, spectrum2, Strength=None):
+        """The argmin variant (:955-972): as in the reference the last overlapping point is left
+        out (half-open slices)."""
+        g, g2 = self.spectral_grid.grid, spectrum2.spectral_grid.grid
+        ini_1, fin_1 = np.argmin(np.abs(g - g2[0])), np.argmin(np.abs(g - g2[-1]))
+        ini_2, fin_2 = np.argmin(np.abs(g2 - g[0])), np.argmin(np.abs(g2 - g[-1]))
+        add = spectrum2.spectrum[ini_2:fin_2]
+        self.spectrum[ini_1:fin_1] += add if Strength is None else Strength * add
+
+    def _fortran_rows(self, lines, fix_length=imxsig, Strengths=None):
+        """(matrix [n_lines][fix_length] column-major, init, fin) of prepare_fortran_sum
+        (:1100-1147): the points of every line inside the spectrum range (tolerance step/10),
+        the rest of the row zero padding on the right, or on the left with a shifted start when
+        the window sticks out at the high end; init / fin 1-based inclusive."""
         n_lines = len(lines)
-        if n_lines == 0:
-            return self.spectrum
-        if n_lines > imxlines:
-            raise ValueError('{} are too many lines (imxlines = {})'.format(n_lines, imxlines))
-        if self.n_points() > imxsig_long:
-            raise ValueError('The input spectrum is too long (imxsig_long)')
         g = self.spectral_grid.grid
         spino = self.spectral_grid.step() / 10.
         matrix = np.zeros((n_lines, fix_length), order='F')
@@ -747,9 +1166,33 @@ class SpectralObject(object):
             else:
                 matrix[i, :] = y
             init[i], fin[i] = ini, end
+        return matrix, init, fin
+
+    def prepare_fortran_sum(self, lines, i, coda, fix_length=imxsig):
+        """The reference's worker of add_lines_to_spectrum (:1100-1147): puts [matrix, init, fin]
+        of this slice of lines on the queue `coda` (anything with .put)."""
+        matrix, init, fin = self._fortran_rows(lines, fix_length)
+        coda.put([matrix, init.astype(int), fin.astype(int)])
+
+    def add_lines_to_spectrum(self, lines, Strengths=None, fix_length=imxsig, n_threads=n_threads):
+        """Adds line shapes (SpectralObjects on their own 13010-point windows) to this spectrum
+        through the sum_all_lines drop-in (:1016-1097); window clipping as prepare_fortran_sum."""
+        n_lines = len(lines)
+        if n_lines == 0:
+            return self.spectrum
+        if n_lines > imxlines:
+            raise ValueError('{} are too many lines (imxlines = {})'.format(n_lines, imxlines))
+        if self.n_points() > imxsig_long:
+            raise ValueError('The input spectrum is too long (imxsig_long)')
+        matrix, init, fin = self._fortran_rows(lines, fix_length, Strengths)
         self.spectrum = lineshape.sum_all_lines(self.spectrum, matrix, init, fin, n_lines,
                                                 self.n_points())
         return self.spectrum
+
+
+def conv_single(spect, window, step):
+    """Trapezoid integral of spectrum x window on the spectrum's grid (:1162-1164)."""
+    return np.trapezoid(spect.spectrum * window, x=spect.spectral_grid.grid)
 
 
 class SpectralIntensity(SpectralObject):
@@ -784,6 +1227,15 @@ class SpectralIntensity(SpectralObject):
 
     def add_bands(self, bands):
         self.bands = copy.deepcopy(bands)
+
+    def hires_to_lowres_old(self, lowres_obs, spectral_widths=None):
+        """The older chain (:1193-1198): axis conversion in place, regular grid, host
+        convolve_to_grid, intensity units of the observation."""
+        self.convert_grid_to(lowres_obs.spectral_grid.units)
+        self.interp_to_regular_grid()
+        low = self.convolve_to_grid(lowres_obs.spectral_grid, spectral_widths=spectral_widths)
+        low.convertto(lowres_obs.units)
+        return low
 
     def hires_to_lowres(self, lowres_obs, spectral_widths=None, keep_original_hires=True):
         """Low-res spectrum on the observation's grid, in the observation's axis and intensity
@@ -851,6 +1303,10 @@ class SpectralGcoeff(SpectralObject):
             self.add_lines_to_spectrum([lin.shape for lin in mine],
                                        Strengths=[lin.G_coeffs[self.ctype] for lin in mine])
         return self.spectrum
+
+    def calc_shapes(self, lines, Temp, Pres, isomolec):
+        """Shapes and G coefficients of `lines` on this coefficient's grid (:1340-1347)."""
+        return calc_shapes_lines(self.spectral_grid, lines, Temp, Pres, isomolec)
 
     def interpolate(self, coeff2, Pres=None, Temp=None):
         """Linear blend with another coefficient that differs in P or in T (:1349-1375)."""

@@ -34,6 +34,43 @@ def date_stamp():
     return '_{:d}-{}-{:d}'.format(t.tm_mday, time.strftime('%b', t), t.tm_year)
 
 
+def find_free_name(filename, maxnum=1000, split_at='.'):
+    """`filename`, or the first `name_NNN.ext` that does not exist yet (smm:34-51); the counter is
+    inserted in front of the first `split_at` and has 2, 3 or 5 digits for maxnum <= 100, <= 1000,
+    larger."""
+    form = '_{:02d}' if maxnum <= 100 else ('_{:03d}' if maxnum <= 1000 else '_{:05d}')
+    orig, ind, num = filename, filename.index(split_at), 1
+    while os.path.isfile(filename):
+        filename = orig[:ind] + form.format(num) + orig[ind:]
+        num += 1
+        if num > maxnum:
+            raise ValueError('Check filenames! More than {} with the same name'.format(maxnum))
+    return filename
+
+
+def equiv(num1, num2, thres=1e-8):
+    """Two floats agree to a relative `thres` of the first (smm:53-66); 0 only equals 0."""
+    if num1 == 0:
+        return num2 == 0
+    return abs((num1 - num2) / num1) < thres
+
+
+def listbands(isomol, lines):
+    """Prints `upper -> lower : n lines` for every pair of levels of isomol that has lines
+    (smm:117-130) and returns {(upper, lower): n}."""
+    mine = [lin for lin in lines if lin.Mol == isomol.mol and lin.Iso == isomol.iso]
+    out = dict()
+    for lev in isomol.levels:
+        up = getattr(isomol, lev)
+        for lev2 in isomol.levels:
+            lo = getattr(isomol, lev2)
+            n = len([lin for lin in mine if lo.equiv(lin.Lo_lev_str) and up.equiv(lin.Up_lev_str)])
+            if n > 0:
+                print('{} -> {} : {} lines'.format(lev, lev2, n))
+                out[(lev, lev2)] = n
+    return out
+
+
 def lut_name(mol, iso, LTE):
     """LUT_molMM_isoI_{LTE|nonLTE} (smm:659-680)."""
     return 'LUT_mol{:02d}_iso{:1d}_{}'.format(mol, iso, 'LTE' if LTE else 'nonLTE')
@@ -136,6 +173,7 @@ class LutSet(object):
         self.sets = []
         self.spectral_grid = None
         self.PTcouples = None
+        self.temp_file = None  # the open per-level stream (prepare_read / prepare_export)
         self._table = None     # (LookUpTable, set index) once built on the device
 
     def find(self, Pres, Temp):
@@ -143,6 +181,121 @@ class LutSet(object):
         if [Pres, Temp] not in self.PTcouples:
             raise ValueError('{} couple not found!'.format([Pres, Temp]))
         return self.PTcouples.index([Pres, Temp])
+
+    # -- the reference's per-level pickle stream (smm:864-979, 1170-1176): PTcouples header, then
+    # one {ctype: SpectralGcoeff without grid} per cell.  Host side only; LookUpTable.import_levels
+    # / export_levels move whole tables between these files and the resident device tensor.
+    def add_file(self, filename, PTcouples):
+        """Another file of the same set, written at a different time (smm:864-870)."""
+        self.filenames.append(filename)
+        self.PTcouples += PTcouples
+
+    def _need_filename(self):
+        if self.filename is None:
+            raise ValueError('ERROR!: NO filename set for LutSet.')
+
+    def prepare_read(self):
+        """Opens the stream and returns its PTcouples header (smm:872-878)."""
+        self._need_filename()
+        self.temp_file = open(self.filename, 'rb')
+        return _RefUnpickler(self.temp_file, encoding='latin1').load()
+
+    def prepare_export(self, PTcouples, spectral_grid):
+        """Opens the stream for writing and dumps PTcouples on top (smm:880-892)."""
+        self._need_filename()
+        self.temp_file = open(self.filename, 'wb')
+        self.PTcouples = copy.deepcopy(PTcouples)
+        self.spectral_grid = spectral_grid
+        pickle.dump(PTcouples, self.temp_file, protocol=-1)
+
+    def finalize_IO(self):
+        self.temp_file.close()
+        self.temp_file = None
+
+    def _restore(self, set_, spectral_grid):
+        for co in set_.values():
+            if co is None:
+                continue
+            co.double_precision()
+            grid = self.spectral_grid if self.spectral_grid is not None else spectral_grid
+            if grid is None:
+                raise ValueError('No spectral grid given.')
+            co.restore_grid(grid)
+        return set_
+
+    def load_from_file(self, load_just_PT=False, spectral_grid=None):
+        """Header and, unless load_just_PT, every cell of self.filename into self.sets in double
+        precision with the grid restored (smm:899-921)."""
+        with open(self.filename, 'rb') as f:
+            self.PTcouples = _RefUnpickler(f, encoding='latin1').load()
+            if load_just_PT:
+                return
+            for _ in self.PTcouples:
+                self.sets.append(self._restore(_RefUnpickler(f, encoding='latin1').load(), spectral_grid))
+
+    def load_from_files(self, load_just_PT=False, spectral_grid=None, cartLUTs=None):
+        """load_from_file over all of self.filenames (smm:924-959); a file that is not found where
+        it was written is looked for under cartLUTs."""
+        self.PTcouples = []
+        for filename in self.filenames:
+            if not os.path.isfile(filename) and cartLUTs is not None:
+                filename = os.path.join(cartLUTs, os.path.basename(filename))
+            with open(filename, 'rb') as f:
+                pts = _RefUnpickler(f, encoding='latin1').load()
+                self.PTcouples += pts
+                if load_just_PT:
+                    continue
+                for _ in pts:
+                    self.sets.append(self._restore(_RefUnpickler(f, encoding='latin1').load(),
+                                                   spectral_grid))
+
+    def load_singlePT_from_file(self, spectral_grid=None):
+        """The next cell of the open stream (smm:961-979); opens it (and skips the header) first
+        when needed."""
+        if getattr(self, 'temp_file', None) is None:   # (objects unpickled from older files)
+            self.prepare_read()
+        return self._restore(_RefUnpickler(self.temp_file, encoding='latin1').load(), spectral_grid)
+
+    def add_dump(self, set_):
+        pickle.dump(set_, self.temp_file, protocol=-1)
+
+    def export(self, filename):
+        """The whole object as one pickle (smm:1170-1172)."""
+        state = copy.copy(self)
+        state._table = None
+        state.temp_file = None
+        with open(filename, 'wb') as f:
+            pickle.dump(state, f, protocol=-1)
+
+    def make(self, spectral_grid, lines, PTcouples, control=True):
+        """Every cell of PTcouples for this level, kept in memory (the reference's older
+        whole-set builder, smm:1069-1119, without its per-cell progress file): one batched GPU
+        build of this level's three ctypes."""
+        lines = [lin for lin in lines if lin.Mol == self.mol and lin.Iso == self.iso]
+        self.spectral_grid = copy.deepcopy(spectral_grid)
+        self.PTcouples = [list(map(float, pt)) for pt in PTcouples]
+        lev_str = '' if self.unidentified_lines else self.level.minimal_level_string()
+        grid = self.spectral_grid.grid
+        tab = spcl.line_table(lines, None)
+        if not self.unidentified_lines:
+            for i, lin in enumerate(lines):
+                u, l = lin.minimal_level_string_up() == lev_str, lin.minimal_level_string_lo() == lev_str
+                # set 0 = this level; lines that do not touch it are dropped (-1)
+                tab["up_set"][i] = 0 if u else (1 if l else -1)
+                tab["lo_set"][i] = 0 if l else (1 if u else -1)
+                tab["e_vib_up"][i] = self.level.energy if u else 0.0
+                tab["e_vib_lo"][i] = self.level.energy if l else 0.0
+        n_sets = 1 if self.unidentified_lines else 2
+        ls = engine.LineSet(tab, grid, self.MM, n_sets)
+        G = ls.gcoeff_cells(self.PTcouples).cpu().numpy()[:, 0]          # [n_cells, 3, n_grid]
+        ls.close()
+        self.sets = []
+        for c, (P, T) in enumerate(self.PTcouples):
+            self.sets.append(dict((ct, spcl.SpectralGcoeff(
+                ct, self.spectral_grid, self.mol, self.iso, self.MM, lev_str,
+                unidentified_lines=self.unidentified_lines, spectrum=G[c, k], Pres=P, Temp=T))
+                for k, ct in enumerate(CTYPES)))
+        return self.sets
 
     def _host_sets(self):
         if not self.sets and getattr(self, '_table', None) is not None:
@@ -210,7 +363,18 @@ class LutSet(object):
                                      unidentified_lines=self.unidentified_lines)
             co.BuildCoeff(lines, Temp, Pres, preCalc_shapes=True, n_threads=n_threads)
             set_[ctype] = co
-        if keep_memory:
+        if getattr(self, 'temp_file', None) is not None:
+            # stream opened by prepare_export: the cell goes to the file without its grid
+            # (smm:1142-1161); the header already lists the cell
+            dumped = dict()
+            for ctype, co in set_.items():
+                co = copy.copy(co)
+                co.erase_grid()
+                dumped[ctype] = co
+            pickle.dump(dumped, self.temp_file, protocol=-1)
+            if keep_memory:
+                self.sets.append(set_)
+        elif keep_memory:
             self.sets.append(set_)
             self.PTcouples.append([Pres, Temp])
         return set_
@@ -279,6 +443,12 @@ class LookUpTable(object):
             self._dev = engine.Lut(self.g32, self.PTcouples, self.mol, self.iso,
                                    self.isomolec.ratio, level_energies=energies)
         return self._dev
+
+    def CPU_time_estimate(self, lines, PTcouples):
+        """The reference's estimate of ITS build time in minutes (smm:791-801): 3 min per 30000
+        lines and cell.  Kept for scripts that print it; the GPU build takes milliseconds per cell."""
+        n_lin = len([lin for lin in lines if lin.Mol == self.mol and lin.Iso == self.iso])
+        return n_lin * 3. / 30000. * len(PTcouples)
 
     def find_lev(self, lev_string):
         for lev, st in self.sets.items():
@@ -505,6 +675,40 @@ def split_and_compress_LUTS(spectral_grid, allLUTs, cartLUTs, n_threads=n_thread
     return allLUTs, n_split, sp_grids
 
 
+def best_compressed_grid(simuls, thress=(1.e-3, 1.e-4, 1.e-5), factors=(5, 20, 100), skip_thres=1.e-20,
+                         consider_derivatives=True, factor_minor=10, thres_minor=1.e-2, alg=2):
+    """Union of the degraded grids of a collection of simulated spectra (smm:1513-1539).
+    simuls: list of {tag: SpectralObject}.  Spectra whose maximum is below skip_thres are skipped;
+    those below thres_minor x the overall maximum use thresholds factor_minor times larger.
+    alg 1: degrade_grid(thress, factors, consider_derivatives); alg 2: degrade_grid2(max threshold,
+    no derivatives).  (alg 3, degrade_grid3, raises NameError in the reference and is not here.)"""
+    maxo = max([0.] + [spe.max() for singles in simuls for spe in singles.values()])
+    grids = [np.array([])]
+    for singles in simuls:
+        for spe in singles.values():
+            if spe.max() < skip_thres:
+                continue
+            th = list(factor_minor * np.array(thress)) if spe.max() < thres_minor * maxo else list(thress)
+            if alg == 1:
+                low = spe.degrade_grid(thress=th, factors=factors, consider_derivatives=consider_derivatives)
+            elif alg == 2:
+                low = spe.degrade_grid2(thres=max(th), consider_derivatives=False)
+            else:
+                raise ValueError('alg has to be 1 or 2')
+            grids.append(low.spectral_grid.grid)
+    return np.unique(np.concatenate(grids))
+
+
+def tolowres(hires, obs):
+    """hires (converted IN PLACE to nm and to a regular grid) convolved to the observation's grid
+    with its band widths through the host convolve_to_grid, in W/m2 (smm:3472-3477)."""
+    hires.convertto_nm()
+    hires.interp_to_regular_grid()
+    lowres = hires.convolve_to_grid(obs.spectral_grid, spectral_widths=obs.bands.spectrum)
+    lowres.convertto('Wm2')
+    return lowres
+
+
 def check_LUT_exists(PTcouples, cartLUTs, mol, iso, LTE):
     """(missing cells, files holding the others): reads only the PTcouples header of the LUT
     files of this isotopologue found in cartLUTs (smm:1390-1456)."""
@@ -557,35 +761,234 @@ def check_and_build_allluts(inputs, sp_grid, lines, molecs, atmosphere=None, PTc
     return allLUTs
 
 
+def read_Gcoeffs_from_LUTs(cartLUTs, fileLUTs):
+    """The pickled LookUpTable skeleton the reference's makeLUT_nonLTE_Gcoeffs leaves next to its
+    per-level files (smm:1380-1388): level structure and file names, no spectra."""
+    with open(cartLUTs + fileLUTs, 'rb') as f:
+        return _RefUnpickler(f, encoding='latin1').load()
+
+
+class AbsSetLOS(object):
+    """Absorption or emission coefficients along one LOS, one SpectralObject per step
+    (smm:1179-1258): kept in `set` (add_set) or streamed to `filename` without their grid
+    (prepare_export / add_dump) and read back one at a time (prepare_read / read_one).
+    Indexing, len() and iteration go over `set`."""
+
+    def __init__(self, filename, spectral_grid=None, indices=None):
+        self.indices = indices if indices is not None else []
+        self.counter = 0
+        self.remaining = 0
+        self.filename = filename
+        self.temp_file = None
+        self.set = []
+        self.spectral_grid = spectral_grid
+
+    def __getitem__(self, k):
+        return self.set[k]
+
+    def __len__(self):
+        return len(self.set)
+
+    def __iter__(self):
+        return iter(self.set)
+
+    def _need_filename(self):
+        if self.filename is None:
+            raise ValueError('ERROR!: NO filename set for LutSet.')
+
+    def prepare_read(self, read_spectral_grid=True):
+        self._need_filename()
+        self.temp_file = open(self.filename, 'rb')
+        self.remaining = self.counter
+        if read_spectral_grid:
+            self.spectral_grid = _RefUnpickler(self.temp_file, encoding='latin1').load()
+
+    def prepare_export(self):
+        """Opens the file and writes the spectral grid on top (when there is one)."""
+        self._need_filename()
+        self.temp_file = open(self.filename, 'wb')
+        if self.spectral_grid is not None:
+            pickle.dump(self.spectral_grid, self.temp_file, protocol=-1)
+
+    def finalize_IO(self):
+        self.temp_file.close()
+        self.temp_file = None
+
+    def add_dump(self, set_, no_spectral_grid=True):
+        if no_spectral_grid:
+            for co in (set_.values() if type(set_) is dict else [set_]):
+                co.erase_grid()
+        pickle.dump(set_, self.temp_file, protocol=-1)
+        self.counter += 1
+
+    def add_set(self, set_):
+        self.set.append(set_)
+        self.counter += 1
+
+    def read_one(self):
+        if self.temp_file is None:
+            self.prepare_read()
+        set_ = _RefUnpickler(self.temp_file, encoding='latin1').load()
+        for co in (set_.values() if type(set_) is dict else [set_]):
+            co.restore_grid(self.spectral_grid, link_grid=True)
+        self.remaining -= 1
+        return set_
+
+
 # ---------------------------------------------------------------------------------------------
 # absorption / emission coefficients and the LOS integral
 # ---------------------------------------------------------------------------------------------
+def _abs_set_writer(spectral_grid, isomolec, tagLOS, cartDROP, to_disk):
+    """(fill(kind, tag, rows) -> AbsSetLOS, tag of this LOS and isotopologue): file names and the
+    keep-or-stream choice shared by the two make_abscoeff routines (smm:2164-2183, 2259-2274)."""
+    if cartDROP is None:
+        cartDROP = 'stuff_' + date_stamp() + '/'
+    if to_disk and not os.path.exists(cartDROP):
+        os.makedirs(cartDROP)
+
+    def fill(kind, tag, rows):
+        out = AbsSetLOS(cartDROP + kind + '_' + tag + '.pic', spectral_grid=spectral_grid)
+        if to_disk:
+            out.prepare_export()
+        for row in rows:
+            co = spcl.SpectralObject(row, spectral_grid, link_grid=True)
+            out.add_dump(co) if to_disk else out.add_set(co)
+        if to_disk:
+            out.finalize_IO()
+        return out
+
+    return fill, ('LOS' if tagLOS is None else tagLOS) + '_mol_{}_iso_{}'.format(isomolec.mol,
+                                                                                isomolec.iso)
+
+
 def make_abscoeff_LUTS_fast(spectral_grid, isomolec, Temps, Press, LTE=True, tagLOS=None,
                             allLUTs=None, cartDROP=None, store_in_memory=False, track_levels=None,
                             time_control=False):
     """Absorption and emission coefficients of one isotopologue at the LOS steps (Temps, Press)
-    from the LUT (smm:2134-2299): lists of SpectralObject, one per step.  Vibrational
-    temperatures are read from Level.local_vibtemp[step] when LTE is False."""
+    from the LUT (smm:2134-2299), as two AbsSetLOS with one SpectralObject per step (indexable);
+    with store_in_memory (the reference's name for "stream them to cartDROP") they are written to
+    `abscoeff_<tagLOS>_mol_M_iso_I.pic` / `emicoeff_...` instead of being kept in `.set`.
+    Vibrational temperatures are read from Level.local_vibtemp[step] when LTE is False.
+    track_levels (a list of level names): two more dicts {level: AbsSetLOS}, the emission and the
+    absorption of those levels alone - and, like the reference (:2263, :2273), the tracked
+    ABSORPTION sets receive the tracked EMISSION coefficients.  None / (None x 4) when the
+    isotopologue has no LUT in this range."""
     LUT = allLUTs[(isomolec.mol_name, isomolec.iso)]
     if LUT is None:
-        return None, None
-    Temps, Press = np.atleast_1d(Temps).astype(float), np.atleast_1d(Press).astype(float)
+        return (None, None) if track_levels is None else (None, None, None, None)
+    try:
+        len(Press), len(Temps)
+    except TypeError:
+        Press, Temps = [Press], [Temps]
+    Temps, Press = np.asarray(Temps, dtype=float), np.asarray(Press, dtype=float)
     n = len(Temps)
-    n_sets = len(LUT.set_names())
-    tvib = None
-    if not LUT.LTE:
-        tvib = np.empty((1, n_sets, 1, n))
-        for s, lev in enumerate(isomolec.levels):
-            L = getattr(isomolec, lev)
-            tvib[0, s, 0] = Temps if LTE else np.asarray(L.local_vibtemp[:n], dtype=float)
+    names = LUT.set_names()
+
+    def tvib_of(levels):
+        if LUT.LTE:
+            return None
+        tv = np.empty((1, len(levels), 1, n))
+        for s, lev in enumerate(levels):
+            tv[0, s, 0] = Temps if LTE else np.asarray(getattr(isomolec, lev).local_vibtemp[:n], dtype=float)
+        return tv
+
     # unit column per unit isotopic ratio: tau = abs coefficient, J = emission coefficient
-    steps = engine.LosSteps([n], Temps[None], Press[None],
-                            np.full((1, 1, n), 1.0 / LUT.isomolec.ratio), tvib)
+    column = np.full((1, 1, n), 1.0 / LUT.isomolec.ratio)
+    steps = engine.LosSteps([n], Temps[None], Press[None], column, tvib_of(names))
     a, e = engine.los_abs_emi([LUT.device_lut()], steps)
     a, e = a.cpu().numpy()[0], e.cpu().numpy()[0]
-    abs_c = [spcl.SpectralObject(a[k], spectral_grid, link_grid=True) for k in range(n)]
-    emi_c = [spcl.SpectralObject(e[k], spectral_grid, link_grid=True) for k in range(n)]
-    return abs_c, emi_c
+
+    fill, tagg = _abs_set_writer(spectral_grid, isomolec, tagLOS, cartDROP, store_in_memory)
+    abs_c, emi_c = fill('abscoeff', tagg, a), fill('emicoeff', tagg, e)
+    if track_levels is None:
+        return abs_c, emi_c
+    emi_tr, abs_tr = dict(), dict()
+    for lev in track_levels:
+        if LUT.LTE or lev not in names:
+            rows = np.zeros((n, len(spectral_grid.grid)))      # never added to (:2250-2258)
+        else:
+            s_ = names.index(lev)
+            sub = engine.lut_tensor(LUT.g32.shape[0], 1, LUT.g32.shape[3])
+            sub.copy_(LUT.g32[:, s_:s_ + 1])
+            one = engine.Lut(sub, LUT.PTcouples, LUT.mol, LUT.iso, LUT.isomolec.ratio,
+                             level_energies=[getattr(isomolec, lev).energy])
+            st1 = engine.LosSteps([n], Temps[None], Press[None], column, tvib_of([lev]))
+            rows = engine.los_abs_emi([one], st1)[1].cpu().numpy()[0]
+            one.close()
+        tagl = tagg + '_{}'.format(lev)
+        emi_tr[lev] = fill('tracklevel_emicoeff', tagl, rows)
+        abs_tr[lev] = fill('tracklevel_abscoeff', tagl, rows)
+    return abs_c, emi_c, emi_tr, abs_tr
+
+
+def make_abscoeff_isomolec(wn_range_tot, isomolec, Temps, Press, LTE=True, allLUTs=None,
+                           useLUTs=False, lines=None, store_in_memory=False, tagLOS=None,
+                           cartDROP=None, track_levels=None, n_threads=n_threads):
+    """The reference's slow twin of make_abscoeff_LUTS_fast (smm:1880-2131): with useLUTs the
+    coefficients come from the LUT (on the LUT's grid), without it from a line-by-line evaluation
+    of the G coefficients at every step's own (P, T) on prepare_spe_grid(wn_range_tot) - one
+    batched FP64 GPU call (K1) instead of the per-step calc_shapes_lines / add_PT / pickle round
+    trip through cartDROP.  Same populations, same return values and file names as the fast
+    routine; more than 10 steps switch store_in_memory on like the reference (:1894-1895)."""
+    try:
+        len(Press), len(Temps)
+    except TypeError:
+        Press, Temps = [Press], [Temps]
+    if len(Temps) > 10:
+        store_in_memory = True
+    if useLUTs:
+        LUT = allLUTs[(isomolec.mol_name, isomolec.iso)]
+        return make_abscoeff_LUTS_fast(LUT.spectral_grid, isomolec, Temps, Press, LTE=LTE,
+                                       tagLOS=tagLOS, allLUTs=allLUTs, cartDROP=cartDROP,
+                                       store_in_memory=store_in_memory, track_levels=track_levels)
+    if lines is None:
+        raise ValueError('when calling smm.make_abscoeff_isomolec() with useLUTs = False, you need '
+                         'to give the list of spectral lines of isomolec as input')
+    spectral_grid = prepare_spe_grid(wn_range_tot).spectral_grid
+    lte_unid = len(isomolec.levels) == 0
+    # a table with exactly one cell per step: interpolating at a node returns the node
+    PT = [[float(p), float(t)] for p, t in zip(Press, Temps)]
+    cells = []
+    for pt in PT:
+        if pt not in cells:
+            cells.append(pt)
+    mine = [lin for lin in lines if lin.Mol == isomolec.mol and lin.Iso == isomolec.iso]
+    tab = spcl.line_table(mine, None if lte_unid else isomolec)
+    grid = spectral_grid.grid
+    Temps, Press = np.asarray(Temps, dtype=float), np.asarray(Press, dtype=float)
+    n, names = len(Temps), (['all'] if lte_unid else list(isomolec.levels))
+    import torch
+    ls = engine.LineSet(tab, grid, isomolec.MM, tab["n_sets"])
+    G = ls.gcoeff_cells(cells)                                        # [n_cells, n_sets, 3, n_grid]
+    ls.close()
+    idx = torch.as_tensor([cells.index(pt) for pt in PT], device="cuda")
+    q = np.array([spcl.CalcPartitionSum(isomolec.mol, isomolec.iso, temp=t) for t in Temps])
+    if lte_unid:
+        pop = (1.0 / q)[:, None]
+    else:
+        tv = np.array([Temps if LTE else np.asarray(getattr(isomolec, lev).local_vibtemp[:n], dtype=float)
+                       for lev in names]).T                            # [n, n_sets]
+        pop = spcl.Boltz_ratio_nodeg(isomolec.level_energies()[None, :], tv) / q[:, None]
+    w = torch.as_tensor(pop, dtype=torch.float64, device="cuda")
+    Gs = G[idx]                                                       # [n, n_sets, 3, n_grid]
+    a = torch.einsum('ks,ksp->kp', w, Gs[:, :, 2] - Gs[:, :, 1]).cpu().numpy()
+    e = torch.einsum('ks,ksp->kp', w, Gs[:, :, 0]).cpu().numpy()
+
+    fill, tagg = _abs_set_writer(spectral_grid, isomolec, tagLOS, cartDROP, store_in_memory)
+    abs_c, emi_c = fill('abscoeff', tagg, a), fill('emicoeff', tagg, e)
+    if track_levels is None:
+        return abs_c, emi_c
+    emi_tr, abs_tr = dict(), dict()
+    for lev in track_levels:
+        if lte_unid or lev not in names:
+            rows = np.zeros((n, len(grid)))
+        else:
+            s_ = names.index(lev)
+            rows = (w[:, s_, None] * Gs[:, s_, 0]).cpu().numpy()
+        tagl = tagg + '_{}'.format(lev)
+        emi_tr[lev] = fill('tracklevel_emicoeff', tagl, rows)
+        abs_tr[lev] = fill('tracklevel_abscoeff', tagl, rows)
+    return abs_c, emi_c, emi_tr, abs_tr
 
 
 # ---------------------------------------------------------------------------------------------
@@ -819,6 +1222,11 @@ class BayesSet(object):
         self.old_params.append(copy.deepcopy(self.param_vector()))
         for par, dx in zip(self.params(), delta_x):
             par.update_par(dx)
+
+    def update_parerror(self):
+        """ret_error of every parameter = sqrt of its diagonal element of the stored VCM (smm:191-194)."""
+        for num, par in enumerate(self.params()):
+            par.ret_error = np.sqrt(self.VCM[num, num])
 
     def store_avk(self, av_kernel):
         self.av_kernel = copy.deepcopy(av_kernel)
