@@ -223,6 +223,29 @@ class AtmProfile(object):
                 res[n] = self._alt_value(v, n, alt)
         return res[profname] if profname is not None else res
 
+    def __add__(self, other):
+        """New profile: every field plus a number or plus the other profile's (single / same-named)
+        field."""
+        out = copy.deepcopy(self)
+        for n in out.names:
+            add = other if np.isscalar(other) else other.values[n if n in other.values else other.names[0]]
+            out.values[n] = out.values[n] + add
+            setattr(out, n, out.values[n])
+        return out
+
+    __radd__ = __add__
+
+    def __mul__(self, factor):
+        """New profile: every field times a number or times the other profile's field."""
+        out = copy.deepcopy(self)
+        for n in out.names:
+            f = factor if np.isscalar(factor) else factor.values[n if n in factor.values else factor.names[0]]
+            out.values[n] = out.values[n] * f
+            setattr(out, n, out.values[n])
+        return out
+
+    __rmul__ = __mul__
+
     def __iadd__(self, other):
         """prof += maskgrid*value (RetSet.profile, smm:483-489): adds the other profile's single
         field to every field of this one."""
@@ -339,16 +362,53 @@ class IsoMolec(object):
         self.levels = []
         self.n_lev = 0
 
-    def add_levels(self, lev_strings, energies, vibtemps=None, degeneracies=None, simmetries=None):
+    def add_levels(self, lev_strings, energies, vibtemps=None, degeneracies=None, simmetries=None,
+                   add_fundamental=False):
+        """Levels `lev_NN` in the order given (call sites radtran_3D_ch4.py:236-255,
+        run_0607_lut.py:94).  add_fundamental puts the ground state (all quanta zero, energy 0, no
+        vibrational temperature: LTE population) in front when the list does not hold it."""
+        lev_strings, energies = list(lev_strings), list(energies)
+        extra = 0
+        if add_fundamental and len(lev_strings) > 0:
+            quanta = extract_quanta_HITRAN(self.mol, self.iso, lev_strings[0])[1]
+            ground = ' '.join('0' for _ in quanta)
+            known = [extract_quanta_HITRAN(self.mol, self.iso, ls_)[0] for ls_ in lev_strings] + \
+                [getattr(self, lev).minimal_level_string() for lev in self.levels]
+            if ground not in known:
+                lev_strings, energies, extra = [ground] + lev_strings, [0.0] + energies, 1
         for i, (ls_, en) in enumerate(zip(lev_strings, energies)):
+            j = i - extra                      # index into the caller's optional lists
             name = 'lev_{:02d}'.format(self.n_lev)
-            lev = Level(ls_, en)
-            if vibtemps is not None and vibtemps[i] is not None:
-                lev.add_vibtemp(vibtemps[i])
+            lev = Level(ls_, en,
+                        degen=None if degeneracies is None or j < 0 else degeneracies[j],
+                        simmetry=None if simmetries is None or j < 0 else simmetries[j])
+            if vibtemps is not None and j >= 0 and vibtemps[j] is not None:
+                lev.add_vibtemp(vibtemps[j])
                 self.is_in_LTE = False
             setattr(self, name, lev)
             self.levels.append(name)
             self.n_lev += 1
+
+    def add_simmetries_levels(self, lines):
+        """Collects, per level, the symmetry labels its vibrational quanta appear with in the
+        global-quanta strings of `lines` (CH4: '0 0 1 0 1F2' -> '1F2'; call sites
+        run_0607_lut.py:95,100).  Levels are matched by quanta only (Level.equiv), so the labels
+        are book-keeping: they do not change which lines feed a level.  Returns {level: labels}."""
+        found = dict((lev, []) for lev in self.levels)
+        for lin in lines:
+            if lin.Mol != self.mol or lin.Iso != self.iso:
+                continue
+            for string in (lin.Up_lev_str, lin.Lo_lev_str):
+                ms, _, sym = extract_quanta_HITRAN(self.mol, self.iso, string)
+                if not sym:
+                    continue
+                for lev in self.levels:
+                    if getattr(self, lev).minimal_level_string() == ms and sym not in found[lev]:
+                        found[lev].append(sym)
+        for lev, syms in found.items():
+            L = getattr(self, lev)
+            L.simmetry = sorted(set(list(L.simmetry) + syms))
+        return found
 
     def has_level(self, lev_string):
         for lev in self.levels:
@@ -411,6 +471,18 @@ class Titan(Planet):
     def __init__(self, atm_extension=1500.0):
         Planet.__init__(self, 'Titan', 2575.0, atm_extension)
         self.mass = 1.3452e23
+
+    def add_default_atm(self):
+        """A smooth single-band Titan-like atmosphere up to atm_extension (temp linear, pres
+        log-linear in altitude): the analytic profiles of spectrobot_b200.synthetic.  (The
+        reference reads its default climatology from files that are not shipped;
+        spect_robot.py:22.)"""
+        from . import synthetic as S
+        atm = S.titan_atmosphere(n_bands=1, z_top=self.atm_extension)
+        prof = AtmProfile(AtmGrid('alt', atm["z"]), atm["temp"][0], 'temp', 'lin')
+        prof.add_profile(atm["pres"][0], 'pres', 'exp')
+        self.add_atmosphere(prof)
+        return prof
 
 
 # ---------------------------------------------------------------------------------------------

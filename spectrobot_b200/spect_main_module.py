@@ -699,6 +699,33 @@ def best_compressed_grid(simuls, thress=(1.e-3, 1.e-4, 1.e-5), factors=(5, 20, 1
     return np.unique(np.concatenate(grids))
 
 
+ORBIT_FIELDS = ('num dist sub_obs_lat sub_obs_lon limb_tg_alt limb_tg_lat limb_tg_lon limb_tg_sza '
+                'pixel_rot phase_ang sub_solar_lat sub_solar_lon sun_dist time').split()
+
+
+def read_orbits(filename, formato='VIMSselect', tag=None):
+    """Geometry records of a 'VIMSselect' orbit file (smm:2328-2347): after the '#' header line,
+    one line of 14 numbers per observation -> list of dicts (ORBIT_FIELDS + filename, tag) ready
+    for sbm.VIMSPixel(orb.keys(), orb.values()).  The spectra / band / noise readers that go with
+    it (sbm.read_obs, read_bands, read_noise) belong to the module that is missing upstream and
+    their file formats are not documented anywhere in the reference: not provided."""
+    if formato != 'VIMSselect':
+        raise ValueError('formato {} not available'.format(formato))
+    orbits = []
+    with open(filename, 'r') as infile:
+        sbm.find_spip(infile)
+        for lin in infile.readlines():
+            if not lin.strip():
+                continue
+            cose = list(map(float, lin.split()))
+            orb = dict(zip(ORBIT_FIELDS, cose))
+            orb['num'] = int(cose[0])
+            orb['filename'] = filename
+            orb['tag'] = tag
+            orbits.append(orb)
+    return orbits
+
+
 def tolowres(hires, obs):
     """hires (converted IN PLACE to nm and to a regular grid) convolved to the observation's grid
     with its band widths through the host convolve_to_grid, in W/m2 (smm:3472-3477)."""

@@ -420,3 +420,64 @@ def test_latitude_boxes_and_2d_profile():
     assert prof.check_involved((30.0, 600.), dict(alt=[650., 1000.], lat=[35., 50.]))
     assert not prof.check_involved((60.0, 600.), dict(alt=[650., 1000.], lat=[35., 50.]))
     assert not prof.check_involved((30.0, 300.), dict(alt=[650., 1000.], lat=[35., 50.]))
+
+
+def test_levels_fundamental_symmetries_and_default_atmosphere():
+    """IsoMolec.add_levels(add_fundamental=True), add_simmetries_levels (run_0607_lut.py:94-100),
+    Titan.add_default_atm (spect_robot.py:22), AtmProfile arithmetic."""
+    im = sbm.IsoMolec(6, 1, LTE=False)
+    im.add_levels(['0 0 1 0 1F2', '0 1 0 0 1E'], [3019.4935, 1533.3326], degeneracies=[3, 2],
+                  add_fundamental=True)
+    assert im.levels == ['lev_00', 'lev_01', 'lev_02']
+    assert im.lev_00.minimal_level_string() == '0 0 0 0' and im.lev_00.energy == 0.0
+    assert im.lev_01.degen == 3 and im.lev_02.energy == 1533.3326
+    im.add_levels(['0 0 0 0 1A1'], [0.0], add_fundamental=True)     # already there by quanta: only the new entry
+    assert im.n_lev == 4
+    lines = [spcl.SpectLine(dict(Mol=6, Iso=1, Up_lev_str='    0 0 1 0 1F2', Lo_lev_str='    0 0 0 0 1A1')),
+             spcl.SpectLine(dict(Mol=6, Iso=1, Up_lev_str='    0 0 1 0 1F1', Lo_lev_str='    0 1 0 0 1E ')),
+             spcl.SpectLine(dict(Mol=6, Iso=2, Up_lev_str='    0 0 1 0 1A2', Lo_lev_str='    0 0 0 0 1A1'))]
+    found = im.add_simmetries_levels(lines)
+    assert found['lev_01'] == ['1F2', '1F1'] and im.lev_01.simmetry == ['1F1', '1F2']
+    assert im.lev_02.simmetry == ['1E'] and im.lev_00.simmetry == ['1A1']
+    planet = sbm.Titan(1200.)
+    atm = planet.add_default_atm()
+    assert planet.atmosphere is atm and atm.grid.coords['alt'][-1] == 1200.0
+    p0 = atm.calc([0.0, 0.0, 0.0], 'pres')
+    assert p0 == pytest.approx(1467.0) and atm.calc([0.0, 0.0, 300.0], 'pres') < 1.0
+    two = atm * 2.0 + 1.0
+    assert two.calc([0.0, 0.0, 100.0], 'temp') == pytest.approx(2 * atm.calc([0.0, 0.0, 100.0], 'temp') + 1)
+    assert atm.calc([0.0, 0.0, 0.0], 'pres') == p0                     # operands untouched
+    both = atm + atm
+    assert both.temp[3] == 2 * atm.temp[3] and both.pres[3] == 2 * atm.pres[3]
+
+
+def test_read_orbits(tmp_path):
+    """smm.read_orbits (smm:2328-2347): '#' header, 14 numbers per line -> VIMSPixel."""
+    fn = str(tmp_path / 'orbit_T34.dat')
+    with open(fn, 'w') as f:
+        f.write('geometry of the selected pixels\n#\n')
+        f.write('3 12000. -10. 45. 512.5 -33. 120. 61.5 12. 90. -20. 200. 9.5 2007.55\n')
+        f.write('4 12500. -11. 46. 612.5 -30. 121. 58.0 -5. 91. -20. 200. 9.5 2007.56\n\n')
+    orbs = smm.read_orbits(fn, tag='T34')
+    assert len(orbs) == 2 and orbs[0]['num'] == 3 and isinstance(orbs[0]['num'], int)
+    assert orbs[1]['limb_tg_alt'] == 612.5 and orbs[1]['pixel_rot'] == -5.0 and orbs[0]['tag'] == 'T34'
+    pix = sbm.VIMSPixel(orbs[0].keys(), orbs[0].values())
+    assert pix.limb_tg_sza == 61.5 and pix.sub_solar_point().Spherical()[0] == pytest.approx(-20.0)
+    assert pix.LOS().starting_point.Spherical()[2] == pytest.approx(12000.0)
+    with pytest.raises(ValueError):
+        smm.read_orbits(fn, formato='other')
+
+
+def test_bayes_set_parerror_and_cpu_time_estimate(world):
+    """BayesSet.update_parerror (smm:191-194), LookUpTable.CPU_time_estimate (smm:791-801)."""
+    z = np.arange(0.0, 1001.0, 50.0)
+    prof = smm.LinearProfile_1D_new('CH4', z, [200.0, 500.0, 800.0], [1e-2, 2e-2, 3e-2], [1e-3, 1e-3, 1e-3])
+    bs = smm.BayesSet('t')
+    bs.add_set(prof)
+    bs.store_VCM(np.diag([4.0, 9.0, 16.0]))
+    bs.update_parerror()
+    assert [p.ret_error for p in bs.params()] == [2.0, 3.0, 4.0]
+    im = world["planet"].gases['CH4'].iso_1
+    lut = smm.LookUpTable(im, [2995.0, 3005.0], False)
+    n = len([l for l in world["lines"] if l.Mol == im.mol and l.Iso == im.iso])
+    assert lut.CPU_time_estimate(world["lines"], [[1, 2]] * 7) == pytest.approx(n * 3. / 30000. * 7)
