@@ -159,38 +159,63 @@ class AtmGrid(object):
 class AtmProfile(object):
     """Profiles on an AtmGrid: 'alt', ('lat', 'alt'), ('sza', 'alt') or ('lat', 'sza', 'alt') - the
     last is the reference's 3-D vibrational-temperature profile, `prof.calc([lat, sza, alt])`
-    (radtran_3D_ch4.py:249-250).  lat coordinates are band EDGES (box interpolation in latitude);
-    sza coordinates are nodes in degrees (linear in between, clamped outside); altitude is linear,
+    (radtran_3D_ch4.py:249-250).  Latitude with interp 'box' (radtran_3D_ch4.py:83-88): the
+    coordinates are the band START latitudes, one per row of values, the last band ending at the
+    pole - or the n+1 band EDGES; with interp 'lin' (radtran_3Dvs2D_radtrans_new.py:82-87) they are
+    band centres and values are interpolated linearly between them, constant outside (host
+    evaluation only: the device step builder works on bands and refuses such a profile).  sza
+    coordinates are nodes in degrees (linear in between, clamped outside); altitude is linear,
     log-linear ('exp') or box."""
 
     def __init__(self, grid, values, profname, interp):
         self.grid = grid
         self.names = []
         self.interp = dict()
+        self.lat_interp = dict()
         self.values = dict()
         self.add_profile(values, profname, interp)
 
     def add_profile(self, values, profname, interp='lin'):
         self.names.append(profname)
         self.values[profname] = np.asarray(values, dtype=float)
-        self.interp[profname] = interp if isinstance(interp, str) else interp[-1]
+        per_axis = [interp] if isinstance(interp, str) else list(interp)
+        self.interp[profname] = per_axis[-1]
+        has_lat = 'lat' in self.grid.names and len(per_axis) > 1
+        self.lat_interp[profname] = per_axis[0] if has_lat else 'box'
+        if 'lat' in self.grid.names:
+            self.lat_edges()                                     # checks rows against coordinates
         setattr(self, profname, self.values[profname])
 
     def get(self, name):
         return self.values[name]
 
+    def n_band(self):
+        return self.values[self.names[0]].shape[0] if 'lat' in self.grid.names else 1
+
+    def lat_edges(self):
+        """The n_band + 1 band edges, from band starts (the reference's own call sites) or edges."""
+        lat, rows = self.grid.coords['lat'], self.n_band()
+        if len(lat) == rows + 1:
+            return lat
+        if len(lat) == rows:
+            return np.append(lat, 90.0 if lat[-1] < 90.0 else lat[-1] + 1.0)
+        raise ValueError('{} latitude coordinates for {} rows of values'.format(len(lat), rows))
+
     def _band(self, lat):
         if 'lat' not in self.grid.names:
             return None
-        edges = self.grid.coords['lat']
+        edges = self.lat_edges()
         return int(np.clip(np.searchsorted(edges, lat, side='right') - 1, 0, len(edges) - 2))
 
     def _coords(self, point, sza):
         """(lat, sza, alt) of a Coords point (+ sza keyword) or of a plain coordinate list given in
-        the order of the grid's own dimensions ([lat, alt], [lat, sza, alt], ...)."""
+        the order of the grid's own dimensions ([lat, alt], [lat, sza, alt], ...); a bare number is
+        an altitude (radtran_3Dvs2D_radtrans_new.py:243)."""
         if hasattr(point, 'Spherical'):
             lat, lon, alt = point.Spherical()
             return lat, sza, alt
+        if np.isscalar(point):
+            return 0.0, sza, float(point)
         point = list(point)
         if len(point) == self.grid.n_dim and self.grid.names != ['lat', 'lon', 'alt']:
             c = dict(zip(self.grid.names, point))
@@ -206,21 +231,37 @@ class AtmProfile(object):
             return float(v[int(np.clip(np.searchsorted(z, alt, side='right') - 1, 0, len(z) - 1))])
         return float(np.interp(alt, z, v))
 
+    def _row_value(self, v, n, sza, alt):
+        """Value of one latitude row (or of a profile without latitude) at (sza, alt)."""
+        if 'sza' in self.grid.names:
+            nodes = self.grid.coords['sza']
+            if sza is None:
+                raise ValueError('profile %s depends on the solar zenith angle: pass sza' % n)
+            return float(np.interp(sza, nodes, [self._alt_value(v[j], n, alt) for j in range(len(nodes))]))
+        return self._alt_value(v, n, alt)
+
     def calc(self, point, profname=None, sza=None):
         lat, sza, alt = self._coords(point, sza)
         names = [profname] if profname is not None else self.names
         res = dict()
-        b = self._band(lat) if 'lat' in self.grid.names else None
         for n in names:
-            v = self.values[n] if b is None else self.values[n][b]
-            if 'sza' in self.grid.names:
-                nodes = self.grid.coords['sza']
-                if sza is None:
-                    raise ValueError('profile %s depends on the solar zenith angle: pass sza' % n)
-                res[n] = float(np.interp(sza, nodes, [self._alt_value(v[j], n, alt)
-                                                      for j in range(len(nodes))]))
+            v = self.values[n]
+            if 'lat' not in self.grid.names:
+                res[n] = self._row_value(v, n, sza, alt)
+            elif self.lat_interp.get(n, 'box') == 'lin':
+                cen = self.grid.coords['lat'][:v.shape[0]]
+                j = int(np.clip(np.searchsorted(cen, lat, side='right') - 1, 0, max(len(cen) - 2, 0)))
+                if len(cen) == 1:
+                    res[n] = self._row_value(v[0], n, sza, alt)
+                else:
+                    w = float(np.clip((lat - cen[j]) / (cen[j + 1] - cen[j]), 0.0, 1.0))
+                    res[n] = (1.0 - w) * self._row_value(v[j], n, sza, alt) + \
+                        w * self._row_value(v[j + 1], n, sza, alt)
             else:
-                res[n] = self._alt_value(v, n, alt)
+                res[n] = self._row_value(v[self._band(lat)], n, sza, alt)
+        if profname is None and len(self.names) == 1:
+            return res[self.names[0]]           # single-field profile: the number itself, as the
+            # reference's drivers use it (radtran_3D_ch4.py:139, radtran_3Dvs2D_radtrans_new.py:243)
         return res[profname] if profname is not None else res
 
     def __add__(self, other):

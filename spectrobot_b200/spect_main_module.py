@@ -1296,13 +1296,20 @@ def planet_atmosphere_tables(planet, gas_isos):
     atm = planet.atmosphere
     z = atm.grid.coords['alt']
     two_d = 'lat' in atm.grid.names
-    n_band = len(atm.grid.coords['lat']) - 1 if two_d else 1
+    n_band = atm.n_band()
 
     def table(prof, name, sza_nodes=None):
         if not np.array_equal(prof.grid.coords['alt'], z):
             raise ValueError('profile %s is not on the atmosphere altitude grid' % name)
         v = np.asarray(prof.values[name], dtype=float)
         has_lat, has_sza = 'lat' in prof.grid.names, 'sza' in prof.grid.names
+        if has_lat and prof.lat_interp.get(name, 'box') != 'box':
+            raise NotImplementedError(
+                'profile %s is interpolated linearly in latitude: the device step builder works '
+                'on latitude bands (interp [\'box\', ...]); use the per-LOS host methods '
+                'LineOfSight.calc_atm_intersections / calc_radtran_steps for such an atmosphere' % name)
+        if has_lat and not np.array_equal(prof.lat_edges(), atm.lat_edges()):
+            raise ValueError('profile %s is not on the latitude bands of the atmosphere' % name)
         if has_sza and (sza_nodes is None or not np.array_equal(prof.grid.coords['sza'], sza_nodes)):
             raise ValueError('profile %s: all SZA-dependent profiles must share their SZA nodes' % name)
         if has_lat and v.shape[0] != n_band:
@@ -1337,9 +1344,56 @@ def planet_atmosphere_tables(planet, gas_isos):
                 tvib[m, j] = table(L.vibtemp, 'vibtemp', sza_nodes)
     return engine.Atmosphere(z, table(atm, 'temp'), table(atm, 'pres'), vmr,
                              tvib=tvib if n_lev else None, tvib_on=tvib_on if n_lev else None,
-                             lat_edges=atm.grid.coords['lat'] if two_d else None,
+                             lat_edges=atm.lat_edges() if two_d else None,
                              radius_km=planet.radius, top_km=planet.atm_extension,
                              sza_nodes=sza_nodes)
+
+
+def latitude_linear_profiles(planet):
+    """Names of the profiles of the planet (atmosphere, VMRs, vibrational temperatures) that are
+    interpolated LINEARLY in latitude between band centres (radtran_3Dvs2D_radtrans_new.py:82-111,
+    `lat_interp='lin'`) - the device step builder works on latitude bands and cannot take them."""
+    found = []
+
+    def look(prof, label):
+        if prof is not None and 'lat' in prof.grid.names:
+            found.extend(label + ':' + n for n in prof.names if prof.lat_interp.get(n, 'box') != 'box')
+
+    look(planet.atmosphere, 'atmosphere')
+    for g in sorted(planet.gases):
+        look(planet.gases[g].abundance, g)
+        for iso in planet.gases[g].all_iso:
+            im = getattr(planet.gases[g], iso)
+            for lev in im.levels:
+                look(getattr(im, lev).vibtemp, '{}/{}/{}'.format(g, iso, lev))
+    return found
+
+
+def los_step_tables_host(loss, planet, bayes_set=None, set_name=None, delta_x=5.0,
+                         max_T_variation=5.0, max_Plog_variation=1.0, max_opt_depth=None,
+                         lines=None, ssps=None, fszas=None, use_tangent_sza=False,
+                         LOS_order='radtran'):
+    """The same tables as los_step_tables_device from the per-LOS host methods
+    (calc_atm_intersections, calc_SZA_along_los or the tangent SZA, calc_radtran_steps - what the
+    reference itself runs per LOS, smm:3133-3147): the route for atmospheres the device builder
+    does not take (latitude-linear profiles).  Host time grows with the number of LOS; the
+    radiances are computed on the device from these tables like any other."""
+    for k, los in enumerate(loss):
+        los.calc_atm_intersections(planet, delta_x=delta_x, LOS_order=LOS_order)
+        if use_tangent_sza:
+            if fszas is None:
+                raise ValueError('use_tangent_sza needs the tangent-point SZA of every LOS')
+            los.szas = np.full(len(los.intersections), float(fszas[k]))
+        elif ssps is not None:
+            los.calc_SZA_along_los(planet, ssps[k])
+        los.calc_radtran_steps(planet, lines, calc_derivatives=bayes_set is not None,
+                               bayes_set=bayes_set, max_T_variation=max_T_variation,
+                               max_Plog_variation=max_Plog_variation, max_opt_depth=max_opt_depth)
+    gi, steps = los_step_tables(loss, planet)
+    dfrac = None
+    if bayes_set is not None and set_name is not None and set_name in planet.gases:
+        dfrac = los_jac_tables(loss, bayes_set, set_name, steps.n_steps_max)
+    return gi, steps, dfrac
 
 
 def los_step_tables_device(loss, planet, bayes_set=None, set_name=None, delta_x=5.0,
@@ -1356,6 +1410,12 @@ def los_step_tables_device(loss, planet, bayes_set=None, set_name=None, delta_x=
     of bayes_set.sets[set_name] (a VMR set named like a gas of the planet), else None.  Also fills
     los.involved_retparams."""
     gi = [(g, iso) for g in sorted(planet.gases) for iso in planet.gases[g].all_iso]
+    if latitude_linear_profiles(planet):
+        return los_step_tables_host(loss, planet, bayes_set=bayes_set, set_name=set_name,
+                                    delta_x=delta_x, max_T_variation=max_T_variation,
+                                    max_Plog_variation=max_Plog_variation,
+                                    max_opt_depth=max_opt_depth, lines=lines, ssps=ssps, fszas=fszas,
+                                    use_tangent_sza=use_tangent_sza, LOS_order=LOS_order)
     atm = planet_atmosphere_tables(planet, gi)
     org = np.array([l.starting_point.Cartesian() for l in loss])
     drc = np.array([l.direction for l in loss])
@@ -1381,7 +1441,7 @@ def los_step_tables_device(loss, planet, bayes_set=None, set_name=None, delta_x=
     masks, jac_gas, pars = None, -1, []
     if bayes_set is not None and set_name is not None and set_name in planet.gases:
         pars = bayes_set.sets[set_name].set
-        lat_edges = planet.atmosphere.grid.coords['lat'] if 'lat' in planet.atmosphere.grid.names else None
+        lat_edges = planet.atmosphere.lat_edges() if 'lat' in planet.atmosphere.grid.names else None
         masks = np.array([np.broadcast_to(p.maskgrid.table(atm.z, lat_edges), (atm.n_band, len(atm.z)))
                           for p in pars])
         jac_gas = [g for g, iso in gi].index(set_name)

@@ -481,3 +481,41 @@ def test_bayes_set_parerror_and_cpu_time_estimate(world):
     lut = smm.LookUpTable(im, [2995.0, 3005.0], False)
     n = len([l for l in world["lines"] if l.Mol == im.mol and l.Iso == im.iso])
     assert lut.CPU_time_estimate(world["lines"], [[1, 2]] * 7) == pytest.approx(n * 3. / 30000. * 7)
+
+
+def test_atmprofile_latitude_conventions():
+    """Latitude coordinates as the reference's drivers pass them: band STARTS with ['box', ...]
+    (radtran_3D_ch4.py:83-88) equal the band-edge form; band centres with ['lin', ...]
+    (radtran_3Dvs2D_radtrans_new.py:82-87) interpolate linearly, constant outside; the device
+    tables refuse the latter instead of silently treating centres as edges."""
+    z = np.arange(0.0, 1001.0, 100.0)
+    lat_ext = [-90., -75., -60., -30., 30., 60., 75., 90.]
+    TT = np.array([150.0 + 5.0 * b + 0.01 * z for b in range(7)])
+    starts = sbm.AtmProfile(sbm.AtmGrid(['lat', 'alt'], [lat_ext[:-1], z]), TT, 'temp', ['box', 'lin'])
+    edges = sbm.AtmProfile(sbm.AtmGrid(['lat', 'alt'], [lat_ext, z]), TT, 'temp', ['box', 'lin'])
+    assert np.array_equal(starts.lat_edges(), np.array(lat_ext)) and starts.n_band() == 7
+    for lat in (-90.0, -80.0, -75.0, 0.0, 74.9, 75.0, 89.0, 90.0):
+        assert starts.calc([lat, 250.0], 'temp') == edges.calc([lat, 250.0], 'temp')
+    assert starts.calc([80.0, 0.0], 'temp') == 180.0                 # the last band is reachable
+    with pytest.raises(ValueError):
+        sbm.AtmProfile(sbm.AtmGrid(['lat', 'alt'], [lat_ext[:-2], z]), TT, 'temp', ['box', 'lin'])
+    lat_c = [(a + b) / 2.0 for a, b in zip(lat_ext[:-1], lat_ext[1:])]
+    lin = sbm.AtmProfile(sbm.AtmGrid(['lat', 'alt'], [lat_c, z]), TT, 'temp', ['lin', 'lin'])
+    lin.add_profile(np.exp(-TT / 50.0), 'pres', ['lin', 'exp'])
+    assert lin.calc([lat_c[2], 300.0], 'temp') == pytest.approx(TT[2, 3])
+    mid = 0.5 * (lat_c[2] + lat_c[3])
+    assert lin.calc([mid, 300.0], 'temp') == pytest.approx(0.5 * (TT[2, 3] + TT[3, 3]))
+    assert lin.calc([-89.0, 300.0], 'temp') == TT[0, 3] and lin.calc([88.0, 300.0], 'temp') == TT[6, 3]
+    assert lin.calc([mid, 350.0], 'pres') == pytest.approx(
+        0.5 * (np.sqrt(lin.pres[2, 3] * lin.pres[2, 4]) + np.sqrt(lin.pres[3, 3] * lin.pres[3, 4])))
+    one = sbm.AtmProfile(sbm.AtmGrid('alt', z), TT[0], 'vmr', 'lin')
+    assert one.calc(250.0) == one.calc([0.0, 0.0, 250.0], 'vmr') == pytest.approx(152.5)
+    planet = sbm.Titan(1000.)
+    planet.add_atmosphere(lin)
+    ch4 = sbm.Molec(6, 'CH4')
+    ch4.add_iso(1)
+    ch4.add_clim(sbm.AtmProfile(lin.grid, np.full(TT.shape, 0.015), 'vmr', ['lin', 'lin']))
+    planet.add_gas(ch4)
+    with pytest.raises(NotImplementedError):
+        smm.planet_atmosphere_tables(planet, [('CH4', 'iso_1')])
+
