@@ -31,7 +31,14 @@ def write_hitran_file(path, wn_range, specs, seed=20067):
     return path
 
 
-def atmosphere(n_bands=7, z_top=1500.0):
+def lat_coords(n_bands, lat_interp='box'):
+    """Latitude coordinates of the profiles: the band edges for 'box' (radtran_3D_ch4.py:83), the
+    band centres for 'lin' (radtran_3Dvs2D_radtrans_new.py:72,82)."""
+    ext = LAT_EXT[:n_bands + 1]
+    return ext if lat_interp == 'box' else [(a + b) / 2.0 for a, b in zip(ext[:-1], ext[1:])]
+
+
+def atmosphere(n_bands=7, z_top=1500.0, lat_interp='box'):
     """(AtmGrid, AtmProfile 'temp'+'pres', altitude grid): the p-T climatology files."""
     atm = S.titan_atmosphere(n_bands=n_bands, z_top=z_top)
     if n_bands == 1:
@@ -39,33 +46,36 @@ def atmosphere(n_bands=7, z_top=1500.0):
         prof = sbm.AtmProfile(grid, atm['temp'][0], 'temp', 'lin')
         prof.add_profile(atm['pres'][0], 'pres', 'exp')
     else:
-        grid = sbm.AtmGrid(['lat', 'alt'], [LAT_EXT[:n_bands + 1], atm['z']])
-        prof = sbm.AtmProfile(grid, atm['temp'], 'temp', ['box', 'lin'])
-        prof.add_profile(atm['pres'], 'pres', ['box', 'exp'])
+        grid = sbm.AtmGrid(['lat', 'alt'], [lat_coords(n_bands, lat_interp), atm['z']])
+        prof = sbm.AtmProfile(grid, atm['temp'], 'temp', [lat_interp, 'lin'])
+        prof.add_profile(atm['pres'], 'pres', [lat_interp, 'exp'])
     return grid, prof, atm
 
 
-def vmr_profile(grid, atm, value, n_bands):
+def vmr_profile(grid, atm, value, n_bands, lat_interp='box'):
     shape = (len(atm['z']),) if n_bands == 1 else (n_bands, len(atm['z']))
-    return sbm.AtmProfile(grid, np.full(shape, value), 'vmr', 'lin' if n_bands == 1 else ['box', 'lin'])
+    return sbm.AtmProfile(grid, np.full(shape, value), 'vmr', 'lin' if n_bands == 1 else [lat_interp, 'lin'])
 
 
-def nlte_molec(mol, name, atm, level_energies, n_bands, sza_nodes=None):
+def nlte_molec(mol, name, atm, level_energies, n_bands, sza_nodes=None, lat_interp='box'):
     """A Molec whose iso_1 carries vibrational levels with T_vib profiles (the vt_* files read by
-    add_nLTE_molecs_from_tvibmanuel[_3D]); 3-D (lat, SZA, alt) with sza_nodes."""
+    add_nLTE_molecs_from_tvibmanuel[_3D]); 3-D (lat, SZA, alt) with sza_nodes; lat_interp as the
+    reader's keyword of the same name."""
     gas = sbm.Molec(mol, name)
     im = gas.add_iso(1, LTE=False)
     z = atm['z']
+    lats = lat_coords(n_bands, lat_interp)
     if sza_nodes is None:
         tv = np.stack([S.vib_temperatures(z, atm['temp'][b], level_energies, 60.0)
                        for b in range(n_bands)], axis=1)                  # [lev][band][z]
-        g = sbm.AtmGrid('alt', z) if n_bands == 1 else sbm.AtmGrid(['lat', 'alt'], [LAT_EXT[:n_bands + 1], z])
-        profs = [sbm.AtmProfile(g, t[0] if n_bands == 1 else t, 'vibtemp', 'lin') for t in tv]
+        g = sbm.AtmGrid('alt', z) if n_bands == 1 else sbm.AtmGrid(['lat', 'alt'], [lats, z])
+        interp = 'lin' if n_bands == 1 else [lat_interp, 'lin']
     else:
         tv = S.vib_temperatures_3d(z, atm['temp'][:n_bands], level_energies, sza_nodes)
         g = (sbm.AtmGrid(['sza', 'alt'], [sza_nodes, z]) if n_bands == 1 else
-             sbm.AtmGrid(['lat', 'sza', 'alt'], [LAT_EXT[:n_bands + 1], sza_nodes, z]))
-        profs = [sbm.AtmProfile(g, t[0] if n_bands == 1 else t, 'vibtemp', 'lin') for t in tv]
+             sbm.AtmGrid(['lat', 'sza', 'alt'], [lats, sza_nodes, z]))
+        interp = 'lin' if n_bands == 1 else [lat_interp, 'lin', 'lin']
+    profs = [sbm.AtmProfile(g, t[0] if n_bands == 1 else t, 'vibtemp', interp) for t in tv]
     im.add_levels(S.level_strings(len(level_energies)), level_energies, vibtemps=profs)
     return gas
 

@@ -660,6 +660,18 @@ class LineOfSight(object):
         pts = self.intersections
         n = len(pts)
         atm = planet.atmosphere
+        if n == 0:                       # the ray misses the atmosphere: no steps
+            self.radtran_steps = {'step': [], 'gas_isos': [(g, iso) for g in sorted(planet.gases)
+                                                            for iso in planet.gases[g].all_iso],
+                                  'opt': dict(max_T_variation=max_T_variation,
+                                              max_Plog_variation=max_Plog_variation,
+                                              max_opt_depth=max_opt_depth)}
+            if calc_derivatives and bayes_set is not None:
+                for par in bayes_set.params():
+                    self.involved_retparams[(par.nameset, par.key)] = False
+            if queue is not None:
+                queue.put(self)
+            return self
         T = np.array([atm.calc(p, 'temp') for p in pts])
         P = np.array([atm.calc(p, 'pres') for p in pts])
         nd = P / (kb_hpa * T)

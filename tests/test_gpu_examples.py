@@ -94,3 +94,75 @@ def test_radtran_test_CO(examples, oracle):
     scale = np.abs(no_lut.spectrum).max()
     assert np.abs(with_lut.spectrum - no_lut.spectrum).max() < 0.05 * scale
     assert np.abs(with_lut.spectrum - no_lut.spectrum).max() > 0.0
+
+
+def test_radtran_3Dvs2D_radtrans_new(examples):
+    """The 3-D vs 2-D driver (BASELINE configs[3]) on a planet whose profiles are latitude-LINEAR
+    (host step builder): radtrans with the altitude ladder, tracked levels and hi-res files in the
+    three geometries (SZA along the LOS, tangent SZA, inverted LOS), then the three retrievals."""
+    results, truth, sims_true, planet, linee, pixels = \
+        examples("radtran_3Dvs2D_radtrans_new_py3").main(small=True)
+    sims3, rt3, single3 = results['radtran_tracklevels_szavar_all']
+    sims2, rt2, single2 = results['radtran_tracklevels_noszavar_short']
+    simsi, rti, singlei = results['radtran_3D_tracklevels_inverseLOS_short']
+    assert len(sims3) == len(pixels) == 3 and len(rt3) >= 8          # the ladder, not 3 LOS per pixel
+    assert all(s.units == 'Wm2' and s.spectral_grid.units == 'nm' for s in sims3 + sims2 + simsi)
+    tags = sorted(rt3)
+    ch4_levels = planet.gases['CH4'].iso_1.levels
+    assert set(single3) == set([('CH4', 'iso_1'), ('HCN', 'iso_1')] +
+                               [('CH4', 'iso_1', l) for l in ch4_levels] +
+                               [('HCN', 'iso_1', l) for l in planet.gases['HCN'].iso_1.levels])
+    assert set(k for k in single2 if len(k) == 3) == set(
+        [('CH4', 'iso_1', l) for l in ch4_levels[1:3]] + [('HCN', 'iso_1', planet.gases['HCN'].iso_1.levels[1])])
+    for tag in (tags[1], tags[len(tags) // 2], tags[-2]):
+        total = rt3[tag].spectrum
+        gases = sum(single3[k][tag].spectrum for k in single3 if len(k) == 2)
+        assert rel_err(gases, total, 1e-3) < 1e-4                     # the source is linear in the emitters
+        levels = sum(single3[('CH4', 'iso_1', l)][tag].spectrum for l in ch4_levels)
+        assert rel_err(levels, single3[('CH4', 'iso_1')][tag].spectrum, 1e-3) < 1e-4
+    a3 = np.array([s.spectrum for s in sims3])
+    a2 = np.array([s.spectrum for s in sims2])
+    ai = np.array([s.spectrum for s in simsi])
+    assert np.all(np.isfinite(a3)) and np.all(a3 > 0)
+    assert 0.0 < np.abs(a2 - a3).max() < 0.5 * a3.max()               # the SZA along the LOS matters
+    assert np.abs(ai - a3).max() > 0.0                                 # so does the direction
+    out = os.environ["SR_EXAMPLE_DIR"]
+    for teag in ('tracklevels_szavar_all', 'tracklevels_noszavar_short'):
+        assert os.path.exists(os.path.join(out, 'out', 'hires_radtran_%s.pic' % teag))
+        assert os.path.exists(os.path.join(out, 'out', 'radtran_%s.pic' % teag))
+    for teag in ('2Dvs3D_szavar_lin', '2Dvs3D_noszavar_lin', '2Dvs3D_inverseLOS_lin'):
+        chi, obs, sims, bayes = results['out_' + teag]
+        assert np.isfinite(chi) and len(sims) == 3
+        assert os.path.getsize(os.path.join(out, 'out', 'out_%s.pic' % teag)) > 0
+    chi, obs, sims, bayes = results['out_2Dvs3D_szavar_lin']          # the geometry the truth was made with
+    used = [(p, t) for p, t in zip(bayes.params(), truth.params()) if p.is_used]
+    assert len(used) >= 3
+    err0 = np.array([abs(p.apriori / t.value - 1) for p, t in used])
+    err1 = np.array([abs(p.value / t.value - 1) for p, t in used])
+    assert np.median(err1) < np.median(err0)
+
+
+def test_inversion_sequences_20067(examples):
+    """The sequence-retrieval driver (BASELINE configs[4] shape): every sequence retrieved with
+    inversion_fast_limb(group_observations=True, alt_first_los=300., check_log=...), results and
+    log written like the reference's."""
+    import pickle
+    num, sequences, results_tot, truth, planet = examples("inversion_sequences_20067_py3").main(small=True)
+    assert num == 2 and len(sequences) == len(results_tot) == 2
+    out = os.path.join(os.environ["SR_EXAMPLE_DIR"], 'out')
+    log = open(os.path.join(out, 'check_log_allinv.dat')).read()
+    assert log.count('SEQ: n_pix 3') == 2 and log.count('Iteration  0: chi is') == 2
+    assert 'LATITUDE -40 - -30' in log and 'LATITUDE 20 - 30' in log and 'Fine!' in log
+    with open(os.path.join(out, 'results_inversion_0607.pic'), 'rb') as f:
+        n2, seq2, res2 = pickle.load(f)
+    assert n2 == 2 and len(seq2[0]['pixels']) == 3
+    for bayes, bayes2 in zip(results_tot, res2):
+        got = np.array([p.value for p in bayes.params()])
+        assert np.array_equal(got, np.array([p.value for p in bayes2.params()]))
+        used = [(p, t) for p, t in zip(bayes.params(), truth.params()) if p.is_used]
+        assert len(used) >= 3 and np.all(got > 0)
+        err0 = np.array([abs(p.apriori / t.value - 1) for p, t in used])
+        err1 = np.array([abs(p.value / t.value - 1) for p, t in used])
+        assert np.median(err1) < np.median(err0)
+    for k in (1, 2):
+        assert os.path.getsize(os.path.join(out, 'out_inversion_0607_seq_%03d.pic' % k)) > 0
