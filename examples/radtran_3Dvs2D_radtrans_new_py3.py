@@ -115,7 +115,7 @@ def main(small=bool(int(os.environ.get('SR_EXAMPLE_SMALL', '0')))):
 
     ###################################################################
     tangents = [520., 700., 880.] if small else list(np.arange(460., 1021., 40.))
-    pixels = syn.observed_pixels(tangents, wn_range, 12 if small else 36, lat=40.0,
+    pixels = syn.observed_pixels(tangents, wn_range, 12 if small else 36, lat=12.0,
                                  sza=np.linspace(55., 75., len(tangents)))
     for pix in pixels:
         pix.pixel_rot = 0.0

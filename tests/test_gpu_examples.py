@@ -152,7 +152,7 @@ def test_inversion_sequences_20067(examples):
     out = os.path.join(os.environ["SR_EXAMPLE_DIR"], 'out')
     log = open(os.path.join(out, 'check_log_allinv.dat')).read()
     assert log.count('SEQ: n_pix 3') == 2 and log.count('Iteration  0: chi is') == 2
-    assert 'LATITUDE -40 - -30' in log and 'LATITUDE 20 - 30' in log and 'Fine!' in log
+    assert 'LATITUDE -20 - -10' in log and 'LATITUDE 10 - 20' in log and 'Fine!' in log
     with open(os.path.join(out, 'results_inversion_0607.pic'), 'rb') as f:
         n2, seq2, res2 = pickle.load(f)
     assert n2 == 2 and len(seq2[0]['pixels']) == 3
