@@ -2096,7 +2096,7 @@ def inversion_algebra(obs, sims, noise, bayes_set, lambda_LM=0.1, L1_reg=False, 
     jac = bayes_set.build_jacobian(masks=masks)
     xi = bayes_set.param_vector()
     obs_vec, sim_vec, noi_vec = genvec(obs, sims, noise, masks=masks)
-    KtSy = jac.T / noi_vec ** 2
+    KtSy = jac.T * (1.0 / noi_vec ** 2)      # K^T Sy^-1 for the diagonal Sy (the reference forms inv(S_y), :3445-3452)
     G_inv = KtSy @ jac
     Sa_inv = inv(bayes_set.VCM_apriori())
     S_inv = G_inv + Sa_inv
