@@ -78,6 +78,58 @@ def main():
         out['vcm_' + tag] = np.array(bs.VCM)
     out['old_params'] = np.array(bs.old_params)
     out['old_values_last'] = np.array(pars[-1].old_values)
+    # ---- involvement rule of a parameter (LinearProfile_1D_new.check_involved, smm:492-501) --------
+    ch4 = bs.sets['CH4']
+    ranges = [[0., 400.], [500., 700.], [760., 900.], [1060., 1400.]]
+    out['involved_ranges'] = np.array(ranges)
+    out['involved'] = np.array([[ch4.check_involved(key, {'alt': r}) for key in ch4.alts] for r in ranges])
+
+    # ---- the ladder spline (make_radtran_spline, smm:3377-3396) -----------------------------------
+    rng = np.random.default_rng(5)
+    alts = np.arange(400., 901., 50.)
+    grid = spcl.SpectralGrid(np.linspace(3280., 3320., 9), units='nm')
+    ladder = [spcl.SpectralIntensity(1e-7 * np.exp(-a / 300.) * (1 + 0.3 * rng.uniform(size=9)), grid, units='Wm2')
+              for a in alts]
+    spl = smm.make_radtran_spline(alts, ladder)
+    probes = np.array([400., 437.5, 612.0, 650., 899.9])
+    out['spline_alts'], out['spline_probes'] = alts, probes
+    out['spline_in'] = np.array([l.spectrum for l in ladder])
+    out['spline_out'] = np.array([spl(x).spectrum for x in probes])
+
+    # ---- line / level filters (smm:69-160) on the fixture's line file -----------------------------
+    import types
+    import make_ref_golden as M
+    lines = spcl.read_line_database(os.path.join(HERE, 'ref_lines.par'))
+    dec = (lambda v: v.decode() if isinstance(v, bytes) else v)
+    for l in lines:
+        for k in ('Up_lev_str', 'Lo_lev_str'):
+            setattr(l, k, dec(getattr(l, k)))
+        l.Mol, l.Iso = int(l.Mol), int(l.Iso)
+
+    def planet():
+        ch4 = sbm.Molec(6, 'CH4')
+        ch4.add_iso(1).add_levels(M.LEVELS + ['1 0 0 0 1A1', '0 0 0 1 1F2'], M.ENERGIES + [2916.5, 1310.8])
+        ch4.add_iso(2)
+        hcn = sbm.Molec(23, 'HCN')
+        hcn.add_iso(1)
+        return types.SimpleNamespace(gases={'CH4': ch4, 'HCN': hcn})
+
+    pl = planet()
+    with R.quiet():
+        ok = smm.check_lines_mols(lines, [pl.gases['CH4'], pl.gases['HCN']])
+    out['filter_lines_ok'] = np.array([l.Freq for l in ok])
+    out['track_all'] = np.array(sorted('%s/%s/%s' % (g, i, lev) for (g, i), levs in smm.track_all_levels(pl).items()
+                                       for lev in levs))
+    with R.quiet():
+        smm.keep_levels_wlines(pl, lines)
+    out['levels_wlines'] = np.array(pl.gases['CH4'].iso_1.levels)
+    with R.quiet():
+        smm.keep_levels(pl, {('CH4', 'iso_1'): ['lev_00', 'lev_02'], ('CH4', 'iso_2'): [], ('HCN', 'iso_1'): []})
+    out['levels_kept'] = np.array(pl.gases['CH4'].iso_1.levels)
+    with R.quiet():
+        ok = smm.check_lines_mols(lines, [pl.gases['CH4']])
+    out['filter_lines_ok2'] = np.array([l.Freq for l in ok])
+
     np.savez_compressed(os.path.join(HERE, 'ref_golden3.npz'), **out)
     print('wrote', os.path.join(HERE, 'ref_golden3.npz'), 'with', len(out), 'arrays')
 

@@ -139,6 +139,10 @@ class IsoMolec(object):
                 return True, lev
         return False, None
 
+    def erase_level(self, lev):
+        self.levels.remove(lev)
+        delattr(self, lev)
+
 
 class Molec(object):
     def __init__(self, mol, name, MM=None):

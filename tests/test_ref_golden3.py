@@ -72,3 +72,42 @@ def test_levenberg_marquardt_step_matches_reference(ref):
     assert bs.params()[-1].value < ref["values0"][-1]
     bs.update_parerror()
     assert bs.params()[3].ret_error == pytest.approx(np.sqrt(ref["vcm_b"][3, 3]), rel=1e-8)
+
+
+def test_involvement_spline_and_level_filters_match_reference(ref):
+    """LinearProfile_1D_new.check_involved (smm:492-501), make_radtran_spline (smm:3377-3396),
+    check_lines_mols / track_all_levels / keep_levels_wlines / keep_levels (smm:69-160)."""
+    from spectrobot_b200 import spect_base_module as sbm, spect_classes as spcl, spect_main_module as smm
+    smm_, bs, *_ = _case(ref)
+    ch4 = bs.sets['CH4']
+    got = np.array([[ch4.check_involved(key, {'alt': list(r)}) for key in ch4.alts]
+                    for r in ref["involved_ranges"]])
+    assert np.array_equal(got, ref["involved"])
+    grid = spcl.SpectralGrid(np.linspace(3280., 3320., 9), units='nm')
+    ladder = [spcl.SpectralIntensity(v, grid, units='Wm2') for v in ref["spline_in"]]
+    spl = smm.make_radtran_spline(ref["spline_alts"], ladder)
+    got = np.array([spl(x).spectrum for x in ref["spline_probes"]])
+    assert np.allclose(got, ref["spline_out"], rtol=1e-13, atol=0.0)
+    assert np.allclose(got[0], ref["spline_in"][0], rtol=1e-12)            # interpolating at a node
+
+    lines = spcl.read_line_database(os.path.join(GOLD, "ref_lines.par"))
+    levels = ['0 0 0 0 1A1', '0 0 1 0 1F2', '0 1 0 0 1E', '1 0 0 0 1A1', '0 0 0 1 1F2']
+    ch4m = sbm.Molec(6, 'CH4')
+    ch4m.add_iso(1).add_levels(levels, [0.0, 3019.4935, 1533.3326, 2916.5, 1310.8])
+    ch4m.add_iso(2)
+    hcn = sbm.Molec(23, 'HCN')
+    hcn.add_iso(1)
+    planet = sbm.Titan(1500.)
+    planet.gases = {'CH4': ch4m, 'HCN': hcn}
+    ok = smm.check_lines_mols(lines, [ch4m, hcn])
+    assert [l.Freq for l in ok] == list(ref["filter_lines_ok"])
+    got = sorted('%s/%s/%s' % (g, i, lev) for (g, i), levs in smm.track_all_levels(planet).items() for lev in levs)
+    assert got == list(ref["track_all"])
+    smm.keep_levels_wlines(planet, lines)
+    assert ch4m.iso_1.levels == list(ref["levels_wlines"])
+    smm.keep_levels(planet, {('CH4', 'iso_1'): ['lev_00', 'lev_02'], ('CH4', 'iso_2'): [], ('HCN', 'iso_1'): []})
+    assert ch4m.iso_1.levels == list(ref["levels_kept"])
+    ok = smm.check_lines_mols(lines, [ch4m])
+    assert [l.Freq for l in ok] == list(ref["filter_lines_ok2"])
+    with pytest.raises(KeyError):
+        smm.keep_levels(planet, {})                                          # like the reference (:144)
