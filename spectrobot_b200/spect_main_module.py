@@ -1728,7 +1728,7 @@ def FOV_integr_1D(radtrans, pixel_rot=0.0):
 
 def make_group_observations(pixels, alt_step=50., alt_first_los=None):
     """A ladder of lines of sight with a fixed step in tangent altitude that stands in for the
-    pixels' own LOS (smm:3290-3338): pixels are assumed to share the cube and to have close
+    pixels' own LOS (restated from smm:3290-3338, same rules in the same order): pixels are assumed to share the cube and to have close
     tangent latitude / longitude / SZA; the ladder runs from alt_first_los (at most the lowest LOS
     of the lowest pixel) to past the highest LOS of the highest pixel, at the mean tangent
     latitude / longitude, seen from the first pixel's spacecraft position."""
@@ -1756,7 +1756,7 @@ def make_group_observations(pixels, alt_step=50., alt_first_los=None):
 
 def make_radtran_spline(alts, radtrans):
     """Function of the tangent altitude that interpolates the simulated LOS spectra
-    (smm:3377-3396): the same RectBivariateSpline(alts, grid, spectra, kx=2, ky=2) the reference
+    (restated from smm:3377-3396): the same RectBivariateSpline(alts, grid, spectra, kx=2, ky=2) the reference
     builds, evaluated on the spectra's own grid."""
     from scipy.interpolate import RectBivariateSpline as spline2D
     alts = np.array(alts)
