@@ -18,6 +18,7 @@ import math as mt
 import os
 import pickle
 import time
+import types
 
 import numpy as np
 
@@ -469,11 +470,14 @@ class LookUpTable(object):
             st.free_memory()
         self._dev = None
 
-    def export_levels(self, cartLUTs, stamp=None, dtype=np.float64):
+    def export_levels(self, cartLUTs, stamp=None, dtype=np.float64, for_reference=False):
         """Writes the table in the reference's on-disk form (smm:726-788, 880-892, 1122-1161): one
         pickle stream per vibrational level (`<tag>_<lev><date>.pic`, `_alllev` for an LTE
         isotopologue) holding the PTcouples header and then, per cell, the dict
-        {ctype: SpectralGcoeff} with the grid erased.  Returns {set name: filename}."""
+        {ctype: SpectralGcoeff} with the grid erased.  Returns {set name: filename}.
+        for_reference: pickles the reference itself can load (_RefPickler: its module names,
+        protocol 2) plus the skeleton file `<tag><date>.pic` that its check_LUT_exists /
+        check_and_build_allluts look for (export_skeleton)."""
         stamp = date_stamp() if stamp is None else stamp
         names = self.set_names()
         host = self.g32.cpu().numpy()
@@ -483,7 +487,7 @@ class LookUpTable(object):
             fn = os.path.join(cartLUTs, self.tag + ('_alllev' if self.LTE else '_' + nam) + stamp + '.pic')
             lev_string = '' if st.level is None else st.level.minimal_level_string()
             with open(fn, 'wb') as f:
-                pickle.dump(self.PTcouples, f, protocol=-1)
+                _dump(self.PTcouples, f, for_reference)
                 for c, (P, T) in enumerate(self.PTcouples):
                     set_ = dict()
                     for k, ct in enumerate(CTYPES):
@@ -492,11 +496,33 @@ class LookUpTable(object):
                                                    spectrum=host[c, s, k].astype(dtype), Pres=P, Temp=T)
                         gigi.erase_grid()
                         set_[ct] = gigi
-                    pickle.dump(set_, f, protocol=-1)
+                    _dump(set_, f, for_reference)
             st.filename = fn
             st.filenames = [fn]
             files[nam] = fn
+        if for_reference:
+            files['skeleton'] = self.export_skeleton(os.path.join(cartLUTs, self.tag + stamp + '.pic'),
+                                                     for_reference=True)
         return files
+
+    def skeleton(self):
+        """A copy without spectra: level structure, PTcouples, spectral grid and, per LutSet, the
+        names of the per-level files - what the reference pickles as `<tag><date>.pic` after a
+        build (makeLUT_nonLTE_Gcoeffs, smm:1872-1875) and reads back in check_LUT_exists /
+        check_and_build_allluts (smm:1405-1420, 1480-1485)."""
+        sk = copy.copy(self)
+        sk.g32, sk._dev = None, None
+        sk.sets = dict()
+        for nam, st in self.sets.items():
+            s2 = copy.copy(st)
+            s2._table, s2.temp_file, s2.sets = None, None, []
+            sk.sets[nam] = s2
+        return sk
+
+    def export_skeleton(self, filename, for_reference=False):
+        with open(filename, 'wb') as f:
+            _dump(self.skeleton(), f, for_reference)
+        return filename
 
     def import_levels(self, files, spectral_grid):
         """Reads per-level streams written by export_levels (or by the reference's
@@ -592,6 +618,46 @@ class _RefUnpickler(pickle.Unpickler):
         return pickle.Unpickler.find_class(self, module, name)
 
 
+_REF_MODULE_NAMES = {
+    __package__ + '.spect_classes': 'spect_classes',
+    __package__ + '.spect_main_module': 'spect_main_module',
+    __package__ + '.spect_base_module': 'spect_base_module',
+    'numpy._core.multiarray': 'numpy.core.multiarray',      # NumPy >= 2 names its reconstructors
+    'numpy._core.numeric': 'numpy.core.numeric',            # under numpy._core
+}
+
+
+class _RefPickler(pickle._Pickler):
+    """The inverse of _RefUnpickler: writes pickles the REFERENCE can load - classes of this
+    package are stored under the reference's top-level module names (`spect_classes`,
+    `spect_main_module`, `spect_base_module`), NumPy's reconstructors under their pre-2.0 module
+    path, protocol 2 (the highest Python 2 reads; bytes travel as latin-1 text, which Python 2 loads
+    as str).  Pure-Python pickler: meant for LUT files of interoperable size, not for speed."""
+
+    def __init__(self, file):
+        pickle._Pickler.__init__(self, file, protocol=2, fix_imports=True)
+
+    def save_global(self, obj, name=None):
+        new = _REF_MODULE_NAMES.get(getattr(obj, '__module__', None))
+        if new is None:
+            return pickle._Pickler.save_global(self, obj, name)
+        name = name or getattr(obj, '__qualname__', None) or obj.__name__
+        self.write(pickle.GLOBAL + new.encode('ascii') + b'\n' + name.encode('ascii') + b'\n')
+        self.memoize(obj)
+
+    dispatch = dict(pickle._Pickler.dispatch)
+    dispatch[types.FunctionType] = save_global          # (type objects reach it through save_type)
+
+
+def _dump(obj, f, for_reference=False):
+    """One pickle.dump of the LUT writers: this interpreter's highest protocol, or the
+    reference-readable form."""
+    if for_reference:
+        _RefPickler(f).dump(obj)
+    else:
+        pickle.dump(obj, f, protocol=-1)
+
+
 def read_lutset_stream(filename):
     """(PTcouples, [ {ctype: SpectralGcoeff}, ... ]) of one per-level LUT stream (smm:900-921):
     the header, then one dict per cell until the stream ends (a build that was interrupted
@@ -625,7 +691,7 @@ def read_split_file(filename):
 
 
 def split_and_compress_LUTS(spectral_grid, allLUTs, cartLUTs, n_threads=n_threads, n_split=None,
-                            ram_max=8., dim_tot=20., low_thres=1.e-30):
+                            ram_max=8., dim_tot=20., low_thres=1.e-30, for_reference=False):
     """Writes every LUT as n_split contiguous wavenumber chunks in the reference's split format
     (smm:1614-1728): chunks of ceil(n_grid/n_split) points, float32, all-zero spectra as None, one
     file `LUT_csplitNN_...<date>.pic` per chunk.  The LOS path here keeps the whole float32 table
@@ -670,7 +736,7 @@ def split_and_compress_LUTS(spectral_grid, allLUTs, cartLUTs, n_threads=n_thread
                             d[ct] = co
                         st.sets.append(d)
                     del st._table
-                    pickle.dump([nam, st], f, protocol=-1)
+                    _dump([nam, st], f, for_reference)     # for_reference: see _RefPickler
             LUT.splitfiles.append(fn)
     return allLUTs, n_split, sp_grids
 
@@ -737,20 +803,35 @@ def tolowres(hires, obs):
 
 
 def check_LUT_exists(PTcouples, cartLUTs, mol, iso, LTE):
-    """(missing cells, files holding the others): reads only the PTcouples header of the LUT
-    files of this isotopologue found in cartLUTs (smm:1390-1456)."""
+    """(exists, PTcouples still to do, [[file, its PTcouples], ...], wn_ranges) for the LUT files of
+    this isotopologue in cartLUTs, with the reference's rule (smm:1390-1456): the files whose name
+    holds the LUT tag and not 'lev' - the pickled LookUpTable skeletons written next to the
+    per-level streams (export_skeleton, or the reference's own) and the single-file tables of
+    LookUpTable.export - are opened for their PTcouples and spectral range; a couple counts as done
+    when both numbers are close (sbm.isclose).  (False, PTcouples, None, None) when there is no
+    such file; the reference returns three values there and its caller fails to unpack them.)"""
     tag = lut_name(mol, iso, LTE)
-    have, files = [], []
+    found = []
     if cartLUTs is not None and os.path.isdir(cartLUTs):
-        for fn in sorted(os.listdir(cartLUTs)):
-            if fn.startswith(tag) and fn.endswith('.pic'):
-                with open(os.path.join(cartLUTs, fn), 'rb') as f:
-                    pts = pickle.load(f)
-                have += [list(map(float, pt)) for pt in pts]
-                files.append(os.path.join(cartLUTs, fn))
-    missing = [list(map(float, pt)) for pt in PTcouples
-               if not any(sbm.isclose(pt[0], h[0]) and sbm.isclose(pt[1], h[1]) for h in have)]
-    return missing, files
+        found = sorted(fn for fn in os.listdir(cartLUTs) if tag in fn and 'lev' not in fn)
+    if len(found) == 0:
+        return False, PTcouples, None, None
+    pt_done, pt_map, wn_ranges = [], [], []
+    for fn in found:
+        path = os.path.join(cartLUTs, fn)
+        with open(path, 'rb') as f:
+            first = _RefUnpickler(f, encoding='latin1').load()
+            if isinstance(first, LookUpTable):                   # skeleton
+                pts, grid = first.PTcouples, first.spectral_grid.grid
+            else:                                                # LookUpTable.export: header, table
+                pts, grid = first, _RefUnpickler(f, encoding='latin1').load()['grid']
+        pts = [list(map(float, pt)) for pt in pts]
+        pt_done += pts
+        pt_map.append([path, pts])
+        wn_ranges.append([float(np.min(grid)), float(np.max(grid))])
+    pt_to_do = [pt for pt in PTcouples
+                if not any(np.all(sbm.isclose(np.array(pt, dtype=float), np.array(ptd))) for ptd in pt_done)]
+    return True, pt_to_do, pt_map, wn_ranges
 
 
 def makeLUT_nonLTE_Gcoeffs(spectral_grid, lines, isomolec, LTE=True, atmosphere=None,

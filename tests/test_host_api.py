@@ -1,6 +1,7 @@
 """CPU tests of the host-side mirror of the reference API (spect_classes / spect_main_module /
 spect_base_module): everything here is index logic and scalar physics, no GPU."""
 import math as mt
+import os
 
 import numpy as np
 import pytest
@@ -519,3 +520,103 @@ def test_atmprofile_latitude_conventions():
     with pytest.raises(NotImplementedError):
         smm.planet_atmosphere_tables(planet, [('CH4', 'iso_1')])
 
+
+
+def _small_lut(tmp_path):
+    import torch
+    rng = np.random.default_rng(9)
+    im = sbm.IsoMolec(6, 1, LTE=False)
+    im.add_levels(S.level_strings(2), [0.0, 1310.76])
+    grid = spcl.SpectralGrid(np.linspace(3000.0, 3000.1, 33), units='cm_1')
+    PT = [[0.01, 150.0], [0.01, 155.0], [0.1, 150.0]]
+    lut = smm.LookUpTable(im, [3000.0, 3000.1], LTE=False)
+    lut.PTcouples, lut.spectral_grid = PT, grid
+    g = rng.uniform(0.5, 1.5, (3, 2, 3, 33)).astype(np.float32)
+    lut.g32 = torch.as_tensor(g)
+    for s, nam in enumerate(im.levels):
+        st = smm.LutSet(6, 1, im.MM, level=getattr(im, nam))
+        st.PTcouples, st.spectral_grid, st._table = PT, grid, (lut, s)
+        lut.sets[nam] = st
+    return lut, im, PT, g
+
+
+def test_reference_readable_lut_files_and_check_lut_exists(tmp_path):
+    """export_levels(for_reference=True): protocol-2 pickles under the reference's module names
+    (and NumPy's pre-2.0 reconstructor path) + the skeleton file; check_LUT_exists with the
+    reference's return values (smm:1390-1456) on that directory and on a LookUpTable.export file."""
+    import pickle
+    lut, im, PT, g = _small_lut(tmp_path)
+    cart = str(tmp_path) + '/'
+    assert smm.check_LUT_exists(PT, cart, 6, 1, False) == (False, PT, None, None)
+    files = lut.export_levels(cart, stamp='_test', for_reference=True)
+    assert sorted(files) == sorted(im.levels) + ['skeleton']
+    raw = open(files[im.levels[1]], 'rb').read()
+    assert raw[:2] == b'\x80\x02' and b'cspect_classes\nSpectralGcoeff\n' in raw
+    assert b'spectrobot_b200' not in raw and b'numpy._core' not in raw and b'cnumpy.core.multiarray\n' in raw
+    raw = open(files['skeleton'], 'rb').read()
+    assert b'cspect_main_module\nLookUpTable\n' in raw and b'cspect_base_module\nIsoMolec\n' in raw
+    assert b'spectrobot_b200' not in raw
+    pts, sets = smm.read_lutset_stream(files[im.levels[1]])             # ... and reads back here
+    assert pts == PT and np.array_equal(np.asarray(sets[2]['absorption'].spectrum, dtype=np.float32), g[2, 1, 2])
+    sk = smm.read_Gcoeffs_from_LUTs(cart, os.path.basename(files['skeleton']))
+    assert isinstance(sk, smm.LookUpTable) and sk.g32 is None and sk.PTcouples == PT
+    assert sk.sets['lev_01'].filename == files['lev_01'] and sk.sets['lev_01'].sets == []
+    assert lut.g32 is not None and lut.sets['lev_00']._table is not None      # the table itself is untouched
+    st = sk.sets['lev_01']
+    st.load_from_file(spectral_grid=lut.spectral_grid)
+    assert np.array_equal(st.sets[0]['sp_emission'].spectrum, g[0, 1, 0].astype(float))
+    want = PT + [[1.0, 160.0]]
+    exists, todo, pt_map, wn_ranges = smm.check_LUT_exists(want, cart, 6, 1, False)
+    assert exists and todo == [[1.0, 160.0]] and pt_map == [[files['skeleton'], PT]]
+    assert wn_ranges == [[3000.0, 3000.1]]
+    assert smm.check_LUT_exists(PT, cart, 6, 2, False)[0] is False              # another isotopologue
+    one = lut.export(os.path.join(cart, 'LUT_mol06_iso1_nonLTE_single.pic'))    # the one-file form
+    exists, todo, pt_map, wn_ranges = smm.check_LUT_exists(want[2:], cart, 6, 1, False)
+    assert exists and todo == [[1.0, 160.0]] and len(pt_map) == 2 and pt_map[0][0] == one
+    assert wn_ranges[0] == wn_ranges[1]
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference/spect_main_module.py'),
+                    reason="reference tree not present (GPU box)")
+def test_reference_loads_the_files_written_for_it(tmp_path):
+    """In a fresh interpreter that holds ONLY the reference's own modules (tests/golden/ref_exec.py),
+    the for_reference files unpickle into the reference's classes, its LutSet.load_from_file reads
+    the per-level stream and its check_LUT_exists finds the skeleton."""
+    import subprocess
+    import sys
+    lut, im, PT, g = _small_lut(tmp_path)
+    cart = str(tmp_path) + '/'
+    files = lut.export_levels(cart, stamp='_test', for_reference=True)
+    np.save(os.path.join(cart, 'g.npy'), g)
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = r"""
+import sys, pickle, numpy as np, warnings
+warnings.simplefilter('ignore')
+sys.path.insert(0, %r)
+import ref_exec as R
+spcl, smm, sbm = R.load()
+assert 'spectrobot_b200.spect_classes' not in sys.modules
+cart, lev = %r, %r
+g = np.load(cart + 'g.npy')
+with open(lev, 'rb') as f:
+    pts = pickle.load(f)
+    first = pickle.load(f)
+assert type(first['absorption']) is spcl.SpectralGcoeff, type(first['absorption'])
+st = smm.LutSet(6, 1, 16.0313, level=None, filename=lev)
+grid = spcl.SpectralGrid(np.linspace(3000.0, 3000.1, 33), units='cm_1')
+st.spectral_grid = grid
+st.load_from_file()
+assert st.PTcouples == %r and len(st.sets) == 3
+assert np.array_equal(st.sets[2]['ind_emission'].spectrum, g[2, 1, 1].astype(float))
+assert st.sets[2]['ind_emission'].integrate() > 0
+with R.quiet():
+    exists, todo, pt_map, wn = smm.check_LUT_exists(%r + [[1.0, 160.0]], cart, 6, 1, False)
+assert exists and todo == [[1.0, 160.0]] and len(pt_map) == 1, (exists, todo)
+sk = pickle.load(open(pt_map[0][0], 'rb'))
+assert type(sk) is smm.LookUpTable and type(sk.sets['lev_01']) is smm.LutSet
+assert type(sk.isomolec) is sbm.IsoMolec and sk.find_lev(sk.isomolec.lev_01.lev_string) == (True, 'lev_01')
+print('reference loaded the files')
+""" % (os.path.join(here, 'golden'), cart, files['lev_01'], PT, PT)
+    env = dict(os.environ, PYTHONPATH='')
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert out.returncode == 0 and 'reference loaded the files' in out.stdout, out.stderr[-2000:]
