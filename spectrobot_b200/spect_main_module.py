@@ -11,7 +11,8 @@ LUT, smm:1676); radtrans runs all lines of sight of a wavenumber chunk in one la
 forked process per LOS, and reduces each LOS block to the instrument channels on the device;
 FOV_integr_1D integrates the three LOS of a pixel in closed form.  LUT files can be written and
 read in the reference's per-level pickle stream (LookUpTable.export_levels / import_levels).  The
-retrieval algebra and the observation readers are out of scope.
+retrieval algebra runs on the host under the reference's names (tiny dense matrices); observation
+readers whose formats live in the missing spect_base_module are not provided.
 """
 import copy
 import math as mt
@@ -1101,7 +1102,7 @@ def make_abscoeff_isomolec(wn_range_tot, isomolec, Temps, Press, LTE=True, allLU
 
 # ---------------------------------------------------------------------------------------------
 # parameter space of the retrieval (smm:161-296, 319-352, 442-656): only what the forward model
-# and its Jacobians need - the update / regularisation algebra is out of scope
+# and its Jacobians need; the update step itself (inversion_algebra) is further down, host NumPy
 # ---------------------------------------------------------------------------------------------
 def alt_triangle(alt_grid, node_alt, step=None, node_lo=None, node_up=None, first=False,
                  last=False):
