@@ -620,3 +620,26 @@ print('reference loaded the files')
     env = dict(os.environ, PYTHONPATH='')
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, cwd=str(tmp_path))
     assert out.returncode == 0 and 'reference loaded the files' in out.stdout, out.stderr[-2000:]
+
+
+def test_split_files_default_and_reference_readable(tmp_path):
+    """split_and_compress_LUTS (smm:1614-1728) on a table held in host memory: chunk files in this
+    interpreter's pickle protocol and, with for_reference, under the reference's module names;
+    both read back through read_split_file / LookUpTable.load_split's reader."""
+    lut, im, PT, g = _small_lut(tmp_path)
+    for k, for_ref in enumerate((False, True)):
+        cart = str(tmp_path / ('split%d' % k)) + '/'
+        os.makedirs(cart)
+        allL, n_split, sp_grids = smm.split_and_compress_LUTS(lut.spectral_grid, {('CH4', 1): lut}, cart,
+                                                              n_split=3, for_reference=for_ref)
+        assert n_split == 3 and [len(s.grid) for s in sp_grids] == [11, 11, 11]
+        assert len(lut.splitfiles) == 3 and os.path.basename(lut.splitfiles[1]).startswith('LUT_csplit01_mol06_iso1_nonLTE')
+        raw = open(lut.splitfiles[1], 'rb').read()
+        assert (b'cspect_main_module\nLutSet\n' in raw) == for_ref and (b'spectrobot_b200' in raw) != for_ref
+        split = smm.read_split_file(lut.splitfiles[1])
+        assert sorted(split) == ['lev_00', 'lev_01']
+        st = split['lev_01']
+        assert np.array_equal(st.spectral_grid.grid, lut.spectral_grid.grid[11:22]) and st.PTcouples == PT
+        co = st.sets[2]['absorption']
+        assert co.spectrum.dtype == np.float32 and co.spectral_grid is None
+        assert np.array_equal(co.spectrum, g[2, 1, 2, 11:22])
