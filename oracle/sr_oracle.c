@@ -7,10 +7,17 @@
  *
  * The reference cannot be built in this environment (no Fortran compiler, no meson for f2py,
  * Python-2 sources, spect_base_module missing), so every routine here follows the
- * reference source line by line and cites it.  PARITY PINNING: the reference ships no golden
- * vectors, fixtures or tests.  The Voigt, line-sum, TIPS and
- * Curtis-Godson routines are pinned by the shipped identities (tests/test_oracle_*.py);
- * the LOS integral (orc_los_*) restates OUR OWN published spec because the
+ * reference source line by line and cites it.  PARITY PINNING: the
+ * reference ships no golden vectors, fixtures or tests.  Everything
+ * the reference does in PYTHON around these routines - window placement, widths, G coefficients,
+ * level selection, clipping and the staging matrix, the LUT it builds and pickles, the Lagrange
+ * rule of the partition sums, LutSet.calculate, make_abscoeff_LUTS_fast, the convolution - is
+ * pinned by fixtures produced by EXECUTING the reference's own spect_classes.py /
+ * spect_main_module.py (tests/golden/ref_exec.py, tests/test_ref_golden*.py), with this file
+ * standing in for the f2py modules.  The Fortran itself (humliv_bb, the inner loop of
+ * sum_all_lines, the TIPS tables, curgod_fort_*) is restated only - no Fortran compiler exists
+ * here - and checked by the identities the reference states (tests/test_oracle.py).  The LOS
+ * integral (orc_los_*) restates OUR OWN published spec because the
  * reference's sbm.LineOfSight.radtran_fast is not in the tree: for that part "parity unpinned".
  *
  * Build: see oracle/Makefile (plain gcc, -ffp-contract=off so no FMA contraction sneaks in).
