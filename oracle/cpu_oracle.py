@@ -537,14 +537,19 @@ def FOV_integr_1D(spectra, grid, pixel_rot=0.0):
 def los_steps_build(z, temp, pres, vmr, origins, directions, tvib=None, tvib_on=None,
                     lat_edges=None, radius=2575.0, top=1500.0, delta_x=5.0, max_T_variation=5.0,
                     max_Plog_variation=1.0, masks=None, jac_gas=-1, sza_nodes=None, sun=None,
-                    sza_fixed=None, photon_order=False, max_opt_depth=None, sigma_peak=None):
+                    sza_fixed=None, photon_order=False, max_opt_depth=None, sigma_peak=None,
+                    lat_centres=None):
     """CPU restatement of the LOS geometry + radtran-step specification with
     the oracle's own Curtis-Godson integrals (orc_curgod_1..4, curgods.f:2-98).  Array conventions
     as sr_atmosphere / sr_los_rays / sr_steps_opt in include/spectrobot.h: tvib may carry an SZA
     axis [n_gas][n_sets][n_band][n_sza][n_z] with sza_nodes (linear between nodes, clamped); the SZA
     of a sample is the angle between its position and `sun` [n_los][3], or sza_fixed[n_los];
     photon_order reverses the sample sequence; max_opt_depth closes a step when sum_gas sigma_peak *
-    column exceeds it.  Returns per LOS a dict with n_steps, temp[], pres[], column[n_gas][],
+    column exceeds it.  lat_centres (instead of lat_edges): the rows are given AT these latitudes
+    and every profile value is the linear blend of the two rows that bracket the sample's latitude,
+    each interpolated in altitude (and SZA) first, constant outside the first / last centre
+    (`['lin', ...]` profiles of radtran_3Dvs2D_radtrans_new.py:82-111; P rows are interpolated
+    log-linearly in altitude and blended linearly).  Returns per LOS a dict with n_steps, temp[], pres[], column[n_gas][],
     tvib[n_gas][n_sets][], dfrac[][n_par].  Plain Python loops: small cases only."""
     kb_hpa = 1.38065e-19
     z = np.asarray(z, dtype=float)
@@ -598,22 +603,33 @@ def los_steps_build(z, temp, pres, vmr, origins, directions, tvib=None, tvib_on=
         elif sun is not None:
             sza = np.degrees(np.arccos(np.clip(pts @ sun[il] / r, -1.0, 1.0)))
         band = np.zeros(len(s), dtype=int)
-        if n_band > 1:
+        wlat = np.zeros(len(s))
+        lat_lin = lat_centres is not None and n_band > 1
+        if lat_lin:
+            cen = np.asarray(lat_centres, dtype=float)
+            lat = np.degrees(np.arcsin(pts[:, 2] / r))
+            band = np.clip(np.searchsorted(cen, lat, side='right') - 1, 0, n_band - 2)
+            wlat = np.clip((lat - cen[band]) / (cen[band + 1] - cen[band]), 0.0, 1.0)
+        elif n_band > 1:
             lat = np.degrees(np.arcsin(pts[:, 2] / r))
             band = np.clip(np.searchsorted(lat_edges, lat, side='right') - 1, 0, n_band - 1)
-        at = lambda tab: np.array([np.interp(a, z, tab[b]) for a, b in zip(alt, band)])  # noqa: E731
+
+        def blend(row_value):   # row_value(i, b): value of row b at sample i
+            if not lat_lin:
+                return np.array([row_value(i, b) for i, b in enumerate(band)])
+            return np.array([(1.0 - w) * row_value(i, b) + w * row_value(i, b + 1)
+                             for i, (b, w) in enumerate(zip(band, wlat))])
+
+        at = lambda tab: blend(lambda i, b: np.interp(alt[i], z, tab[b]))  # noqa: E731
 
         def at_sza(tab):   # [n_band][n_sza][n_z]: linear in z, then linear between SZA nodes
             if tab.shape[1] == 1:
                 return at(tab[:, 0])
-            res = np.empty(len(s))
-            for i, (a, b, sz) in enumerate(zip(alt, band, sza)):
-                col = np.array([np.interp(a, z, tab[b, j]) for j in range(tab.shape[1])])
-                res[i] = np.interp(sz, sza_nodes, col)
-            return res
+            return blend(lambda i, b: np.interp(
+                sza[i], sza_nodes, np.array([np.interp(alt[i], z, tab[b, j]) for j in range(tab.shape[1])])))
 
         T = at(temp)
-        P = np.exp(at(np.log(pres)))
+        P = blend(lambda i, b: np.exp(np.interp(alt[i], z, np.log(pres[b]))))
         nd = P / (kb_hpa * T)
         x = np.abs(s[0] - s) * 1.e5
         lnP = np.log(P)

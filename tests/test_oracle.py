@@ -249,3 +249,48 @@ def test_oracle_step_builder_identities(oracle):
     dn = np.array([0.0, 0.0, 2575.0 - 800.0]) - org[0]
     hit = oracle.los_steps_build(z, atm["temp"], atm["pres"], vmr, org, [dn / np.linalg.norm(dn)])[0]
     assert hit["n_steps"] > 3 and hit["pres"][0] > 1000.0            # first (far) step is at the surface
+
+
+def test_oracle_step_builder_latitude_linear(oracle):
+    """lat_centres mode of the oracle's step builder (`['lin', ...]` profiles of
+    radtran_3Dvs2D_radtrans_new.py:82-111): identical rows give the tables of the 1-D planet; a
+    temperature that rises linearly with latitude gives, on a ray inside one meridian plane slab,
+    step temperatures between those of the two bracketing rows; outside the first / last centre
+    the profile is constant."""
+    from spectrobot_b200 import synthetic as S
+    atm = S.titan_atmosphere(n_bands=1)
+    z = atm["z"]
+    cen = np.array([-60.0, 0.0, 60.0])
+    rep = lambda a: np.repeat(np.asarray(a), 3, axis=0)   # noqa: E731
+    vmr1 = np.full((1, 1, len(z)), 0.015)
+    vmr3 = np.full((1, 3, len(z)), 0.015)
+    org = np.array([[1.0e5, 0.0, 0.0]])
+    tg = np.array([0.0, 2575.0 + 500.0, 900.0])       # tangent point at about 16 deg latitude
+    d = (tg - org[0]) / np.linalg.norm(tg - org[0])
+    one = oracle.los_steps_build(z, atm["temp"], atm["pres"], vmr1, org, [d])[0]
+    same = oracle.los_steps_build(z, rep(atm["temp"]), rep(atm["pres"]), vmr3, org, [d],
+                                  lat_centres=cen)[0]
+    assert same["n_steps"] == one["n_steps"] > 3
+    for k in ("temp", "pres"):
+        assert np.allclose(same[k], one[k], rtol=1e-12)
+    assert np.allclose(same["column"][0], one["column"][0], rtol=1e-12)
+    # rows 0 K, +10 K, +20 K warmer: every step lies between the 1-D value + 10 and + 20 K
+    # (all samples of this ray are between 0 and 60 degrees north)
+    t3 = np.stack([atm["temp"][0], atm["temp"][0] + 10.0, atm["temp"][0] + 20.0])
+    warm = oracle.los_steps_build(z, t3, rep(atm["pres"]), vmr3, org, [d], lat_centres=cen,
+                                  max_T_variation=1e9, max_Plog_variation=0.2)[0]
+    base = oracle.los_steps_build(z, atm["temp"], atm["pres"], vmr1, org, [d],
+                                  max_T_variation=1e9, max_Plog_variation=0.2)[0]
+    assert warm["n_steps"] == base["n_steps"]
+    dt = np.array(warm["temp"]) - np.array(base["temp"])
+    assert np.all(dt > 10.0) and np.all(dt < 20.0)
+    # a ray over the pole region beyond the last centre sees the last row only
+    tgp = np.array([0.0, 300.0, 2575.0 + 500.0])
+    dp = (tgp - org[0]) / np.linalg.norm(tgp - org[0])
+    pole = oracle.los_steps_build(z, t3, rep(atm["pres"]), vmr3, org, [dp], lat_centres=cen,
+                                  max_T_variation=1e9, max_Plog_variation=0.2)[0]
+    pole1 = oracle.los_steps_build(z, atm["temp"] + 20.0, atm["pres"], vmr1, org, [dp],
+                                   max_T_variation=1e9, max_Plog_variation=0.2)[0]
+    assert pole["n_steps"] == pole1["n_steps"]
+    mid = pole["n_steps"] // 2
+    assert abs(pole["temp"][mid] - pole1["temp"][mid]) < 1e-9    # tangent region: > 60 deg north
