@@ -78,6 +78,15 @@ int sr_partition_sum(int mol, int iso, double temp, double* q);
  * the variants that do not take them (k=1: nd,x; k=2: nd,vmr,x; k=3,4: nd,vmr,f,x). */
 int sr_curgod(int k, const double* nd, const double* vmr, const double* f, const double* x,
               int n_p, int n_batch, double* res);
+/* The same four integrals under the f2py names, one integral per call, n_p valid points:
+ * curgod_fort_1(nd,x,n_p) [curgods.f:2-21], _2(nd,vmr,x,n_p) [:24-45], _3 / _4(nd,vmr,f,x,n_p)
+ * [:48-73, :76-97] -> *res. */
+int sr_curgod_1(const double* nd, const double* x, int n_p, double* res);
+int sr_curgod_2(const double* nd, const double* vmr, const double* x, int n_p, double* res);
+int sr_curgod_3(const double* nd, const double* vmr, const double* f, const double* x, int n_p,
+                double* res);
+int sr_curgod_4(const double* nd, const double* vmr, const double* f, const double* x, int n_p,
+                double* res);
 
 /* ===========================================================================================
  * Tier 2 -- fused cross-section path (K1/K2): calc_shapes_lines + Calc_Gcoeffs + BuildCoeff +

@@ -88,6 +88,10 @@ SIGNATURES = {
     "sr_bd_tips_2003": (C.c_int, [C.c_int, C.c_int, _dp, _dp, _dp]),
     "sr_partition_sum": (C.c_int, [C.c_int, C.c_int, C.c_double, _dp]),
     "sr_curgod": (C.c_int, [C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.c_int, _dp]),
+    "sr_curgod_1": (C.c_int, [_dp, _dp, C.c_int, _dp]),
+    "sr_curgod_2": (C.c_int, [_dp, _dp, _dp, C.c_int, _dp]),
+    "sr_curgod_3": (C.c_int, [_dp, _dp, _dp, _dp, C.c_int, _dp]),
+    "sr_curgod_4": (C.c_int, [_dp, _dp, _dp, _dp, C.c_int, _dp]),
     "sr_default_consts": (None, [C.POINTER(sr_consts)]),
     "sr_lineset_create": (C.c_int, [C.POINTER(sr_lines), _dp, C.c_long, _dp, C.c_int, C.c_double,
                                     C.POINTER(sr_consts), C.POINTER(_vp)]),

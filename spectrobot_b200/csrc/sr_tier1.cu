@@ -259,4 +259,20 @@ int sr_curgod(int k, const double* nd, const double* vmr, const double* f, const
     return SR_OK;
 }
 
+// The four f2py entry points under their own names (curgods.f:2, 24, 48, 76): one integral each.
+int sr_curgod_1(const double* nd, const double* x, int n_p, double* res) {
+    return sr_curgod(1, nd, nullptr, nullptr, x, n_p, 1, res);
+}
+int sr_curgod_2(const double* nd, const double* vmr, const double* x, int n_p, double* res) {
+    return sr_curgod(2, nd, vmr, nullptr, x, n_p, 1, res);
+}
+int sr_curgod_3(const double* nd, const double* vmr, const double* f, const double* x, int n_p,
+                double* res) {
+    return sr_curgod(3, nd, vmr, f, x, n_p, 1, res);
+}
+int sr_curgod_4(const double* nd, const double* vmr, const double* f, const double* x, int n_p,
+                double* res) {
+    return sr_curgod(4, nd, vmr, f, x, n_p, 1, res);
+}
+
 }  // extern "C"

@@ -6,11 +6,12 @@ from ._lib import as_f64, check, dptr, lib
 
 
 def _run(k, nd, vmr, f, x, n_p):
+    """One integral through the entry point of its own name, sr_curgod_<k> (include/spectrobot.h)."""
     n_p = int(n_p)
-    arrs = [None if a is None else as_f64(np.asarray(a, dtype=float)[:n_p]) for a in (nd, vmr, f, x)]
+    arrs = [as_f64(np.asarray(a, dtype=float)[:n_p]) for a in (nd, vmr, f, x) if a is not None]
     res = np.empty(1)
-    p = [None if a is None else dptr(a) for a in arrs]
-    check(lib().sr_curgod(k, p[0], p[1], p[2], p[3], n_p, 1, dptr(res)))
+    fn = getattr(lib(), "sr_curgod_%d" % k)
+    check(fn(*([dptr(a) for a in arrs] + [n_p, dptr(res)])))
     return float(res[0])
 
 

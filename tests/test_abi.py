@@ -54,6 +54,23 @@ def test_no_cpu_fallback_without_device():
     assert e.value.code == _lib.SR_ERR_CUDA
 
 
+def test_curgod_entry_points_under_their_f2py_names():
+    """sr_curgod_1..4 (one symbol per curgods.f routine) reject bad arguments with
+    SR_ERR_ARG before any device work, and fail loudly without a device otherwise."""
+    from spectrobot_b200 import _lib, curgods
+    L = _lib.lib()
+    a = np.linspace(1.0, 2.0, 8)
+    res = np.zeros(1)
+    assert L.sr_curgod_1(_lib.dptr(a), _lib.dptr(a), 0, _lib.dptr(res)) == _lib.SR_ERR_ARG
+    assert L.sr_curgod_2(_lib.dptr(a), None, _lib.dptr(a), 8, _lib.dptr(res)) == _lib.SR_ERR_ARG
+    assert L.sr_curgod_3(_lib.dptr(a), _lib.dptr(a), None, _lib.dptr(a), 8, _lib.dptr(res)) == _lib.SR_ERR_ARG
+    assert L.sr_curgod_4(None, _lib.dptr(a), _lib.dptr(a), _lib.dptr(a), 8, _lib.dptr(res)) == _lib.SR_ERR_ARG
+    if not _lib.cuda_available():
+        with pytest.raises(_lib.SpectrobotError) as e:
+            curgods.curgod_fort_2(a, a, a, 8)
+        assert e.value.code == _lib.SR_ERR_CUDA
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "spectrobot_b200")
     for dp, _, files in os.walk(pkg):
