@@ -14,9 +14,13 @@
  * rule of the partition sums, LutSet.calculate, make_abscoeff_LUTS_fast, the convolution - is
  * pinned by fixtures produced by EXECUTING the reference's own spect_classes.py /
  * spect_main_module.py (tests/golden/ref_exec.py, tests/test_ref_golden*.py), with this file
- * standing in for the f2py modules.  The Fortran itself (humliv_bb, the inner loop of
- * sum_all_lines, the TIPS tables, curgod_fort_*) is restated only - no Fortran compiler exists
- * here - and checked by the identities the reference states (tests/test_oracle.py).  The LOS
+ * standing in for the f2py modules.  The Fortran itself cannot be compiled (no Fortran compiler
+ * exists here); humliv_bb, humli_bb, sum_all_lines and curgod_fort_* below are BIT-IDENTICAL to
+ * the reference's own Fortran source executed statement by statement by the mechanical FORTRAN 77
+ * executor tests/golden/f77_exec.py (fixtures tests/golden/f77_golden.npz, all three humliv_bb
+ * branches; tests/test_f77_golden.py), under gfortran / x86-64 semantics (no FMA contraction).
+ * The TIPS tables are generated from fparts_mod.f by tools/gen_tables.py and restated only.  The
+ * identities the reference states run on top (tests/test_oracle.py).  The LOS
  * integral (orc_los_*) restates OUR OWN published spec because the
  * reference's sbm.LineOfSight.radtran_fast is not in the tree: for that part "parity unpinned".
  *
