@@ -19,8 +19,9 @@
  * the reference's own Fortran source executed statement by statement by the mechanical FORTRAN 77
  * executor tests/golden/f77_exec.py (fixtures tests/golden/f77_golden.npz, all three humliv_bb
  * branches; tests/test_f77_golden.py), under gfortran / x86-64 semantics (no FMA contraction).
- * The TIPS tables are generated from fparts_mod.f by tools/gen_tables.py and restated only.  The
- * identities the reference states run on top (tests/test_oracle.py).  The LOS
+ * The TIPS tables (generated from fparts_mod.f by tools/gen_tables.py) equal what bd_tips_2003
+ * -> QT_* return when executed the same way, for all 108 (mol, iso).  The identities the
+ * reference states run on top (tests/test_oracle.py).  The LOS
  * integral (orc_los_*) restates OUR OWN published spec because the
  * reference's sbm.LineOfSight.radtran_fast is not in the tree: for that part "parity unpinned".
  *

@@ -1,5 +1,6 @@
 """TEST INFRASTRUCTURE: a mechanical executor for the FORTRAN 77 the reference's numeric routines
-are written in (lineshape.f: sum_all_lines, humliv_bb; curgods.f: curgod_fort_1..4).
+are written in (lineshape.f: sum_all_lines, humliv_bb, humli_bb; curgods.f: curgod_fort_1..4;
+fparts_mod.f: bd_tips_2003 and the QT_* table routines it calls).
 
 No Fortran compiler exists in this image, so the reference's Fortran cannot be compiled.  This
 module does the next best thing to running it: it READS THE SOURCE TEXT WHERE IT LIES
@@ -18,11 +19,21 @@ written here - only the language rules:
     -fcx-fortran-rules: the plain four-product form, and division with range reduction
     (Smith: the ratio of the smaller to the larger part of the divisor); no FMA contraction
     (x86-64 baseline);
-  * x**n with an integer n is repeated multiplication; NINT rounds half away from zero;
+  * x**n with a literal integer n <= 3 is repeated multiplication (every chain a compiler may
+    pick gives the same roundings), with an integer variable n libgfortran's square-and-multiply;
+    NINT rounds half away from zero;
   * DO loops evaluate their trip count once and leave the variable one step past the end;
     DO WHILE; block IF / ELSE IF / ELSE; logical IF; STOP raises F77Stop; WRITE is ignored;
   * arrays are passed by reference (NumPy arrays, 1-based subscripts, Fortran order for 2-D);
-    a whole-array assignment copies.
+    a whole-array assignment copies; local arrays with literal bounds are allocated at entry;
+  * IMPLICIT statements and the default rule (i-n INTEGER, else REAL*4) - but not in a unit with
+    an INCLUDE, whose declarations are not read; DIMENSION; DATA (value lists, repeat counts,
+    implied DO over one row of a 2-D array), applied at entry; CALL of another unit of the file,
+    scalar arguments copied back by position; GO TO a label that stands on a RETURN.
+
+Everything else - other labels and jumps, COMMON storage not filled by DATA in the same unit,
+assignment to a DATA variable (SAVE semantics), array elements as actual arguments, FORMAT, ... -
+makes the unit F77Unsupported: it is left out, never guessed.
 
 REAL*8 is a Python float and COMPLEX*16 a Python complex handled component-wise by the helpers
 below (IEEE binary64 operations, correctly rounded, the same the compiled code executes).
@@ -30,7 +41,7 @@ exp / cos / log go to the C library.
 
 Used by tests/golden/make_f77_golden.py to produce reference-executed fixtures for the rows of
 SURVEY section 8 that were pinned by a hand restatement only (A2 humliv_bb, the inner loop of A6
-sum_all_lines, A13 curgod_fort_*), and by tests/test_f77_golden.py to re-check them whenever
+sum_all_lines, the TIPS tables of A9, A13 curgod_fort_*), and by tests/test_f77_golden.py to re-check them whenever
 /root/reference is present.
 """
 import math
@@ -103,6 +114,20 @@ def _ipow(a, n):
     return r
 
 
+def _ipow_var(a, n):
+    """x**n with an integer VARIABLE n: libgfortran's pow_r8_i4 (square and multiply)."""
+    if n < 0:
+        raise F77Unsupported("negative integer power")
+    pw, x, u = (1 if isinstance(a, int) else 1.0), a, n
+    while u:
+        if u & 1:
+            pw = pw * x
+        u >>= 1
+        if u:
+            x = x * x
+    return pw
+
+
 def _nint(v):
     """NINT: nearest integer, halves away from zero."""
     m = abs(v)
@@ -120,7 +145,7 @@ def _stop(msg):
     raise F77Stop(msg)
 
 
-_RUNTIME = dict(_f4=_f4, _cmul=_cmul, _cmul_r=_cmul_r, _cdiv=_cdiv, _idiv=_idiv, _ipow=_ipow,
+_RUNTIME = dict(np=np, _ipow_var=_ipow_var, _f4=_f4, _cmul=_cmul, _cmul_r=_cmul_r, _cdiv=_cdiv, _idiv=_idiv, _ipow=_ipow,
                 _nint=_nint, _trip=_trip, _stop=_stop, math=math, complex=complex, float=float,
                 int=int, abs=abs, max=max, min=min, range=range)
 
@@ -172,7 +197,7 @@ def logical_lines(path):
                 out[-1] = (out[-1][0], out[-1][1] + line[6:])
                 continue
             if line[:5].strip():            # a labelled statement: its unit is outside the subset
-                out.append((no, '@label ' + line[6:]))
+                out.append((no, '@label %s %s' % (line[:5].strip(), line[6:].strip())))
                 continue
             out.append((no, line[6:]))
     return [(no, _lower_outside_quotes(t).strip()) for no, t in out]
@@ -356,9 +381,13 @@ class ExprParser(object):
         if self.peek() == ('op', '**'):
             self.take()
             b = self.power()                      # right-associative
-            if b[1] != 'i':
+            if b[1] != 'i' or a[1] not in _RANK:
                 raise F77Unsupported("non-integer exponent")
-            return ('_ipow(%s, %s)' % (a[0], b[0]), a[1])
+            if re.fullmatch(r'\d+', b[0]):
+                if not 1 <= int(b[0]) <= 3:      # longer chains: the compiler picks the order
+                    raise F77Unsupported("literal integer power above 3")
+                return ('_ipow(%s, %s)' % (a[0], b[0]), a[1])
+            return ('_ipow_var(%s, %s)' % (a[0], b[0]), a[1])
         return a
 
     @staticmethod
@@ -427,10 +456,12 @@ class ExprParser(object):
                 if val in self.arrays:
                     if any(x[1] != 'i' for x in a) or len(a) != self.arrays[val]:
                         raise F77Unsupported("subscripts of %s" % val)
+                    self.types.used.add(val)
                     return ('%s[%s]' % (val, ', '.join('%s - 1' % x[0] for x in a)), self.types[val])
                 return self.intrinsic(val, a)
-            if val not in self.types:
+            if self.types.lookup(val) is None:
                 raise F77Unsupported("undeclared name %s" % val)
+            self.types.used.add(val)
             if val in self.arrays:
                 return (val, 'array:' + self.types[val])
             return (val, self.types[val])
@@ -499,11 +530,34 @@ def _matching_paren(s, k):
     raise F77Unsupported("unbalanced parentheses in %r" % s)
 
 
+class TypeTable(dict):
+    """name -> type, with the IMPLICIT rule of the unit for names that were never declared
+    (`implicit none`, or an INCLUDE whose declarations are not read: undeclared names are
+    refused)."""
+
+    def __init__(self):
+        dict.__init__(self)
+        # the standard's default: i-n INTEGER, everything else REAL
+        self.implicit = dict((chr(c), 'i' if chr(c) in 'ijklmn' else 'r4')
+                             for c in range(ord('a'), ord('z') + 1))
+        self.used = set()
+
+    def lookup(self, name):
+        if name in self:
+            return self[name]
+        if self.implicit is None:
+            return None
+        self[name] = self.implicit[name[0]]
+        return self[name]
+
+
 class Translator(object):
     def __init__(self, name, dummies, stmts):
         self.name, self.dummies, self.stmts = name, dummies, stmts
-        self.types, self.arrays = {}, {}
+        self.types, self.arrays = TypeTable(), {}
+        self.dims, self.common, self.data = {}, set(), []
         self.lines, self.depth, self.tmp = [], 1, 0
+        self.return_labels = set()
 
     def emit(self, code):
         self.lines.append('    ' * self.depth + code)
@@ -515,19 +569,116 @@ class Translator(object):
             raise F77Unsupported("trailing tokens in %r" % text)
         return r
 
+    def declare_items(self, text, t):
+        for item in _split_top(text):
+            mm = re.match(r'(\w+)\s*(\((.*)\))?$', item)
+            if not mm:
+                raise F77Unsupported("declaration %r" % text)
+            nam = mm.group(1)
+            if t is not None:
+                self.types[nam] = t
+            elif self.types.lookup(nam) is None:
+                raise F77Unsupported("dimension of the untyped name %s" % nam)
+            if mm.group(2):
+                dims = _split_top(mm.group(3))
+                self.arrays[nam] = len(dims)
+                self.dims[nam] = [d.strip() for d in dims]
+
     def declaration(self, st):
+        if st == 'implicit none':
+            self.types.implicit = None
+            return True
+        m = re.match(r'implicit\s+(.*?)\s*\(([a-z,\s-]+)\)\s*$', st)
+        if m:
+            t = [tt for pat, tt in _TYPES if re.fullmatch(pat, m.group(1))]
+            if not t:
+                raise F77Unsupported("statement %r" % st)
+            rule = dict((chr(c), 'i' if chr(c) in 'ijklmn' else 'r4') for c in range(ord('a'), ord('z') + 1))
+            for rng in m.group(2).split(','):
+                lo, _, hi = rng.strip().partition('-')
+                for c in range(ord(lo.strip()), ord((hi or lo).strip()) + 1):
+                    rule[chr(c)] = t[0]
+            self.types.implicit = rule
+            return True
+        if st.startswith('include'):               # its declarations are not read, so an undeclared
+            self.types.implicit = None             # name may be one of them: refuse, do not guess
+            return True
+        m = re.match(r'common\s*/\s*\w*\s*/(.*)$', st)
+        if m:                                      # storage association is not modelled: a COMMON
+            for nam in _split_top(m.group(1)):     # variable may only be used where DATA fills it
+                self.common.add(re.match(r'\w+', nam).group(0))
+            return True
+        m = re.match(r'dimension\s+(.*)$', st)
+        if m:
+            self.declare_items(m.group(1), None)
+            return True
+        m = re.match(r'data\s*(.*)$', st)
+        if m and '/' in st:
+            self.data.append(m.group(1))
+            return True
         for pat, t in _TYPES:
             m = re.match(r'(?:%s)\s+(?![=(])' % pat, st)
             if m:
-                for item in _split_top(st[m.end():]):
-                    mm = re.match(r'(\w+)\s*(\((.*)\))?$', item)
-                    if not mm:
-                        raise F77Unsupported("declaration %r" % st)
-                    self.types[mm.group(1)] = t
-                    if mm.group(2):
-                        self.arrays[mm.group(1)] = len(_split_top(mm.group(3)))
+                self.declare_items(st[m.end():], t)
                 return True
         return False
+
+    def data_values(self, text, t):
+        vals = []
+        for item in _split_top(text):
+            rep, _, v = item.rpartition('*')
+            toks = tokenize(v)
+            sign = 1
+            if toks and toks[0] in (('op', '-'), ('op', '+')):
+                sign = -1 if toks[0][1] == '-' else 1
+                toks = toks[1:]
+            if len(toks) != 1 or toks[0][0] != 'num':
+                raise F77Unsupported("DATA value %r" % item)
+            kind, txt = toks[0][1]
+            x = int(txt) if kind == 'i' else (float(txt) if kind == 'r8' else f4_literal(txt))
+            x = sign * x
+            if t == 'i':
+                if kind != 'i':
+                    raise F77Unsupported("real DATA value for an integer")
+            elif t == 'r4':
+                x = _f4(x)
+            elif t == 'r8':
+                x = float(x)
+            else:
+                raise F77Unsupported("DATA for type %s" % t)
+            vals += [x] * (int(rep) if rep.strip() else 1)
+        return vals
+
+    def emit_data(self):
+        """DATA statements: `name / list /` (a scalar or a whole array in storage order) and
+        `(name(k, j), j = a, b) / list /`.  Emitted as initialisation at entry; a DATA variable
+        that the body assigns would need SAVE semantics and is refused (see assignment)."""
+        done = set()
+        for text in self.data:
+            m = re.match(r'\(\s*(\w+)\s*\(\s*(\d+)\s*,\s*(\w+)\s*\)\s*,\s*(\w+)\s*=\s*(\d+)\s*,\s*(\d+)\s*\)\s*/(.*)/\s*$', text)
+            if m and m.group(3) == m.group(4) and self.arrays.get(m.group(1)) == 2:
+                nam, row, lo, hi = m.group(1), int(m.group(2)), int(m.group(5)), int(m.group(6))
+                vals = self.data_values(m.group(7), self.types[nam])
+                if len(vals) != hi - lo + 1:
+                    raise F77Unsupported("DATA count for %s" % nam)
+                self.emit('%s[%d, %d:%d] = %r' % (nam, row - 1, lo - 1, hi, vals))
+                done.add(nam)
+                continue
+            m = re.match(r'(\w+)\s*/(.*)/\s*$', text)
+            if not m or self.types.lookup(m.group(1)) is None:
+                raise F77Unsupported("DATA statement %r" % text)
+            nam = m.group(1)
+            vals = self.data_values(m.group(2), self.types[nam])
+            if nam in self.arrays:
+                if self.arrays[nam] != 1 or len(vals) != int(self.dims[nam][0]):
+                    raise F77Unsupported("DATA count for %s" % nam)
+                self.emit('%s[:] = %r' % (nam, vals))
+            else:
+                if len(vals) != 1:
+                    raise F77Unsupported("DATA count for %s" % nam)
+                self.emit('%s = %r' % (nam, vals[0]))
+            done.add(nam)
+        return done
 
     def assignment(self, st):
         depth = 0
@@ -539,9 +690,11 @@ class Translator(object):
             raise F77Unsupported("statement %r" % st)
         lhs, rhs = st[:k].strip(), st[k + 1:].strip()
         m = re.match(r'(\w+)\s*(\(.*\))?$', lhs)
-        if not m or m.group(1) not in self.types:
+        if not m or self.types.lookup(m.group(1)) is None:
             raise F77Unsupported("left-hand side %r" % lhs)
         nam, t = m.group(1), self.types[m.group(1)]
+        if nam in self.data_names:
+            raise F77Unsupported("assignment to the DATA variable %s" % nam)
         val = self.parse(rhs)
         if nam in self.arrays and not m.group(2):              # whole-array assignment
             if val[1] != 'array:' + t:
@@ -555,6 +708,26 @@ class Translator(object):
             target = nam
         self.emit('%s = %s' % (target, code))
 
+    def call(self, st):
+        """CALL name(a, b, ...): actual arguments must be plain names; arrays travel by reference,
+        scalars are copied back from the callee's final values (by position)."""
+        m = re.match(r'call\s+(\w+)\s*\((.*)\)\s*$', st)
+        if not m:
+            raise F77Unsupported("statement %r" % st)
+        args = _split_top(m.group(2))
+        for a in args:
+            if not re.fullmatch(r'\w+', a) or self.types.lookup(a) is None:
+                raise F77Unsupported("actual argument %r" % a)
+            self.types.used.add(a)
+        self.tmp += 1
+        r = '_call%d' % self.tmp
+        self.emit('%s = _call(_units, %r, [%s])' % (r, m.group(1), ', '.join(args)))
+        for k, a in enumerate(args):
+            if a not in self.arrays:
+                if a in self.data_names:
+                    raise F77Unsupported("DATA variable %s as an actual argument" % a)
+                self.emit('%s = %s[%d]' % (a, r, k))
+
     def simple(self, st):
         if st.startswith('stop'):
             self.emit('_stop(%r)' % st[4:].strip().strip("'\""))
@@ -562,28 +735,66 @@ class Translator(object):
             self.emit('pass')
         elif st == 'return':
             self.emit('return _result()')
+        elif re.match(r'call\s', st):
+            self.call(st)
+        elif re.fullmatch(r'go\s*to\s*(\d+)', st):
+            lab = re.fullmatch(r'go\s*to\s*(\d+)', st).group(1)
+            if lab not in self.return_labels:      # only a jump to a labelled RETURN is known
+                raise F77Unsupported("go to %s" % lab)
+            self.emit('return _result()')
         else:
             self.assignment(st)
 
     def translate(self):
         body = []
         for no, st in self.stmts:
-            if st.startswith('implicit') or st.startswith('include'):
+            m = re.match(r'@label (\d+) (.*)$', st)
+            if m:
+                if m.group(2).strip() != 'return':
+                    raise F77Unsupported("statement label at line %d" % no)
+                self.return_labels.add(m.group(1))
+                body.append((no, 'return'))
                 continue
-            if st.startswith('@label'):
-                raise F77Unsupported("statement label at line %d" % no)
-            if self.declaration(st):
+            if not body and self.declaration(st):
+                continue
+            if body and (re.match(r'(implicit|dimension|common|data)\b', st) or
+                         any(re.match(r'(?:%s)\s+(?![=(])' % pat, st) for pat, _ in _TYPES)):
+                if not self.declaration(st):
+                    raise F77Unsupported("statement %r" % st)
                 continue
             body.append((no, st))
         for d in self.dummies:
-            if d not in self.types:
+            if self.types.lookup(d) is None:
                 raise F77Unsupported("dummy %s undeclared" % d)
-        local = [n for n in self.types if n not in self.dummies]
         self.lines.append('def %s(%s):' % (self.name, ', '.join(self.dummies)))
+        self.data_names = set()
+        for text in self.data:                    # names first: the body must not assign them
+            m = re.match(r'\(\s*(\w+)', text) or re.match(r'(\w+)', text)
+            self.data_names.add(m.group(1))
+        if self.data_names & set(self.dummies):
+            raise F77Unsupported("DATA for a dummy argument")
+        body_lines, self.lines = self.lines, []
+        self.body(body)
+        code, self.lines = self.lines, body_lines
+        local = [n for n in self.types if n not in self.dummies]
         for n in local:
             if n in self.arrays:
-                raise F77Unsupported("local array %s" % n)
-            self.emit('%s = None' % n)
+                try:
+                    shape = tuple(int(d) for d in self.dims[n])
+                except ValueError:
+                    if n in self.types.used:
+                        raise F77Unsupported("local array %s with symbolic bounds" % n)
+                    continue
+                dt = {'i': 'np.int64', 'r4': 'np.float64', 'r8': 'np.float64'}.get(self.types[n])
+                if dt is None:
+                    raise F77Unsupported("local array %s of type %s" % (n, self.types[n]))
+                self.emit("%s = np.zeros(%r, dtype=%s, order='F')" % (n, shape, dt))
+            else:
+                self.emit('%s = None' % n)
+        inited = self.emit_data()
+        for n in self.common:
+            if n in self.types.used and n not in inited:
+                raise F77Unsupported("COMMON variable %s used without DATA in this unit" % n)
         scal = [d for d in self.dummies if d not in self.arrays]
         self.emit('def _result():')
         self.emit('    return {%s}' % ', '.join('%r: %s' % (d, d) for d in scal))
@@ -591,6 +802,11 @@ class Translator(object):
             if self.types[d] not in ('i', 'r8'):
                 raise F77Unsupported("scalar dummy %s of type %s" % (d, self.types[d]))
             self.emit('%s = %s(%s)' % (d, 'int' if self.types[d] == 'i' else 'float', d))
+        self.lines += code
+        self.emit('return _result()')
+        return '\n'.join(self.lines) + '\n'
+
+    def body(self, body):
         stack = []
         for no, st in body:
             self.emit('# line %d' % no)
@@ -606,6 +822,7 @@ class Translator(object):
                         self.emit('if %s:' % cond[0])
                         stack.append('if')
                         self.depth += 1
+                        self.emit('pass')
                     else:
                         self.emit('if %s:' % cond[0])
                         self.depth += 1
@@ -617,6 +834,7 @@ class Translator(object):
                     self.depth -= 1
                     self.emit('elif %s:' % cond[0])
                     self.depth += 1
+                    self.emit('pass')
                 continue
             if st == 'else':
                 if not stack or stack[-1] != 'if':
@@ -644,7 +862,7 @@ class Translator(object):
             if m:
                 var = m.group(1)
                 parts = _split_top(m.group(2))
-                if self.types.get(var) != 'i' or len(parts) not in (2, 3):
+                if self.types.lookup(var) != 'i' or len(parts) not in (2, 3):
                     raise F77Unsupported("do statement %r" % st)
                 ex = [self.parse(p) for p in parts]
                 if any(e[1] != 'i' for e in ex):
@@ -670,8 +888,17 @@ class Translator(object):
             self.simple(st)
         if stack:
             raise F77Unsupported("unterminated block in %s" % self.name)
-        self.emit('return _result()')
-        return '\n'.join(self.lines) + '\n'
+
+
+def _call(units, name, actuals):
+    """Run-time side of CALL: the callee's final scalar values by position (None for arrays)."""
+    fn = units.get(name)
+    if fn is None:
+        raise F77Unsupported("call of %s, which is outside the subset" % name)
+    if len(actuals) != len(fn.dummies):
+        raise F77Unsupported("argument count in the call of %s" % name)
+    res = fn(*actuals)
+    return [res.get(d) for d in fn.dummies]
 
 
 _CACHE = {}
@@ -679,7 +906,7 @@ _CACHE = {}
 
 def load(path):
     """{name: python function} for every subroutine of the file the executor can translate;
-    `.source` on each function holds the generated Python."""
+    `.source` on each function holds the generated Python, `.dummies` the argument names."""
     if path in _CACHE:
         return _CACHE[path]
     out = {}
@@ -689,9 +916,12 @@ def load(path):
         except F77Unsupported:
             continue
         ns = dict(_RUNTIME)
+        ns['_units'] = out
+        ns['_call'] = _call
         exec(compile(src, '<f77:%s:%s>' % (path, name), 'exec'), ns)
         fn = ns[name]
         fn.source = src
+        fn.dummies = list(dummies)
         out[name] = fn
     _CACHE[path] = out
     return out

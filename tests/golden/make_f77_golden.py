@@ -1,6 +1,7 @@
 """Fourth set of reference-executed fixtures (tests/golden/f77_golden.npz): the reference's
 FORTRAN routines on the hot path - lineshape.f humliv_bb (A2), sum_all_lines (inner loop of A6),
-humli_bb, and curgods.f curgod_fort_1..4 (A13) - executed FROM THEIR OWN SOURCE TEXT by the
+humli_bb, curgods.f curgod_fort_1..4 (A13) and fparts_mod.f bd_tips_2003 with the QT_* routines it
+calls (the table of A9) - executed FROM THEIR OWN SOURCE TEXT by the
 mechanical FORTRAN 77 executor f77_exec.py (no Fortran compiler exists in this image; see its
 header for the language rules it applies).  Run from the repo root in a container that has
 /root/reference:
@@ -175,9 +176,36 @@ def main():
     out["cg_in"] = np.array(cg_in)
     out["cg_res"] = np.array(cg_res)
 
+    # --- bd_tips_2003 (fparts_mod.f:33-295 + the QT_* routines it calls): every (mol, iso) the
+    # dispatcher reaches; Q values are REAL*4 literals stored in DOUBLE PRECISION arrays, so they
+    # are float32-valued and stored as float32 without loss
+    fp = F.load(os.path.join(REF, "fparts_mod.f"))
+    keys, gis, qs, t_grid = [], [], [], None
+    for mol in range(1, 60):
+        for iso in range(1, 20):
+            t, q = np.zeros(119), np.full(119, -7.0)
+            try:
+                r = fp["bd_tips_2003"](mol, iso, -7.0, t, q)
+            except IndexError:                   # iso beyond the DIMENSION of the routine's tables
+                break
+            except F.F77Unsupported:             # QT_H3P (mol 42): COMMON storage association
+                break
+            if np.all(q == -7.0):                # no branch of the dispatcher took this molecule
+                break
+            assert np.array_equal(q.astype(np.float32).astype(float), q)
+            keys.append((mol, iso))
+            gis.append(r["gi"])
+            qs.append(q.astype(np.float32))
+            assert t_grid is None or np.array_equal(t, t_grid)
+            t_grid = t
+    out["tips_keys"] = np.array(keys, dtype=np.int32)
+    out["tips_gi"] = np.array(gis)
+    out["tips_q"] = np.array(qs)
+    out["tips_t"] = t_grid
+
     fn = os.path.join(HERE, "f77_golden.npz")
     np.savez_compressed(fn, **out)
-    print("wrote", fn, os.path.getsize(fn), "bytes;", len(cases), "humliv_bb cases")
+    print("wrote", fn, os.path.getsize(fn), "bytes;", len(cases), "humliv_bb cases,", len(keys), "TIPS tables")
 
 
 if __name__ == "__main__":

@@ -1,5 +1,5 @@
 """CPU tests: the oracle's restatement of the reference's FORTRAN (oracle/sr_oracle.c: humliv_bb,
-humli_bb, sum_all_lines, curgod_fort_1..4) against fixtures produced by EXECUTING the reference's
+humli_bb, sum_all_lines, curgod_fort_1..4, the TIPS tables) against fixtures produced by EXECUTING the reference's
 own Fortran source text with the mechanical FORTRAN 77 executor tests/golden/f77_exec.py
 (tests/golden/make_f77_golden.py -> f77_golden.npz).  Bit for bit: both sides perform the same
 IEEE operations in the same order.  Also: the executor's language rules on small programs written
@@ -78,6 +78,21 @@ def test_curgod_restatement(oracle, gold):
         got = [oracle.curgod(1, nd, x), oracle.curgod(2, nd, vmr, x), oracle.curgod(3, nd, vmr, f, x),
                oracle.curgod(4, nd, vmr, f, x)]
         assert got == list(gold["cg_res"][k]), (k, got, gold["cg_res"][k])
+
+
+def test_tips_tables_of_oracle_and_product_are_the_executed_fortran(oracle, gold):
+    """fparts_mod.f bd_tips_2003 -> QT_*: gi, the 119-node temperature grid and Q(T) of every
+    (mol, iso) the dispatcher reaches, for the oracle's table and for the PRODUCT's
+    sr_bd_tips_2003 (a host-only entry point of libspectrobot.so: runs without a GPU)."""
+    from spectrobot_b200 import fparts_mod
+    keys = gold["tips_keys"]
+    assert len(keys) >= 100 and [6, 1] in keys.tolist() and [23, 1] in keys.tolist() and [26, 1] in keys.tolist()
+    for k, (mol, iso) in enumerate(keys):
+        q = gold["tips_q"][k].astype(float)
+        for impl in (oracle.bd_tips_2003, fparts_mod.bd_tips_2003):
+            gi, t, qq = impl(int(mol), int(iso))
+            assert gi == gold["tips_gi"][k], (mol, iso)
+            assert np.array_equal(np.asarray(t), gold["tips_t"]) and np.array_equal(np.asarray(qq), q), (mol, iso)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -183,14 +198,63 @@ def test_executor_language_rules(f77, tmp_path):
 
 
 def test_executor_refuses_what_it_does_not_know(f77, tmp_path):
-    """Labels, GOTO, CALL, undeclared names: the unit is left out, nothing is guessed."""
+    """Labels other than on RETURN, jumps, undeclared names under IMPLICIT NONE, assignment to a
+    DATA variable: the unit is left out, nothing is guessed; a CALL of such a unit fails when it
+    is reached."""
     fn = tmp_path / "no.f"
     fn.write_text("      subroutine a(x)\n      real*8 x\n      goto 10\n 10   x = 1.d0\n      end\n"
-                  "      subroutine b(x)\n      real*8 x\n      x = y\n      end\n"
+                  "      subroutine b(x)\n      implicit none\n      real*8 x\n      x = y\n      end\n"
                   "      subroutine c(x)\n      real*8 x\n      call a(x)\n      end\n"
-                  "      subroutine d(x)\n      real*8 x\n      x = 2.d0*x\n      end\n")
+                  "      subroutine d(x)\n      real*8 x\n      x = 2.d0*x\n      end\n"
+                  "      subroutine e(x)\n      real*8 x, t(2)\n      data t/1.,2./\n      t(1) = x\n      end\n")
     got = f77.load(str(fn))
-    assert sorted(got) == ["d"] and got["d"](1.5)["x"] == 3.0
+    assert sorted(got) == ["c", "d"] and got["d"](1.5)["x"] == 3.0
+    with pytest.raises(f77.F77Unsupported):
+        got["c"](1.0)
+
+
+_PROGRAM2 = """\
+      subroutine outer(k, g, tab)
+      integer*4 k
+      real*8 g, tab(4), loc(3)
+      data loc/ 0.1, 2*0.25E+01/
+      tab(4) = loc(1) + loc(3)
+      if (k .eq. 1) then
+      call inner(k, g, tab)
+      go to 100
+      endif
+      g = -1.d0
+ 100  return
+      end
+      subroutine inner(iso, gsi, q)
+      implicit double precision (a-h,o-z)
+      dimension xg(2), qq(2,3), q(4)
+      data xg/ 1.,6./
+      data (qq( 1,j),j=1,3)/ 0.54791E+02, 0.1, 3./
+      data (qq( 2,j),j=1,3)/ 1., 2., 3./
+      eps = 0.01
+      gsi = xg(iso+1)
+\tdo i=1,3
+\t  q(i) = qq(iso,i)
+\tenddo
+   99 return
+      end
+"""
+
+
+def test_executor_data_call_implicit_and_return_labels(f77, tmp_path):
+    """The constructs of fparts_mod.f: IMPLICIT typing, DIMENSION, DATA (lists, repeat counts,
+    implied DO over a row), CALL with scalars copied back, `go to` a labelled RETURN, tab-indented
+    statements."""
+    fn = tmp_path / "tips.f"
+    fn.write_text(_PROGRAM2)
+    units = f77.load(str(fn))
+    tab = np.zeros(4)
+    out = units["outer"](1, 0.0, tab)
+    f32 = lambda t: float(np.float32(t))   # noqa: E731
+    assert out == {"k": 1, "g": 6.0}
+    assert list(tab) == [f32(54.791), f32(0.1), 3.0, f32(0.1) + 2.5]
+    assert units["outer"](2, 0.0, tab)["g"] == -1.0
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not on this box")
@@ -218,3 +282,10 @@ def test_f77_fixture_is_what_the_reference_source_computes_now(f77, gold):
     nd, vmr, f, x = [a[:n_p].copy() for a in gold["cg_in"][k]]
     assert cg["curgod_fort_3"](nd, vmr, f, x, n_p, 0.0)["res"] == gold["cg_res"][k][2]
     assert ls["humli_bb"](gold["hb_rx"][3], gold["hb_ry"][3], 0.0)["rre"] == gold["hb_rre"][3]
+    fp = f77.load(os.path.join(REF, "fparts_mod.f"))
+    assert len(fp) >= 40 and "qt_ch4" in fp and "qt_h3p" not in fp
+    for mol, iso in ((6, 1), (6, 3), (23, 2), (26, 1), (5, 4)):
+        k = gold["tips_keys"].tolist().index([mol, iso])
+        t, q = np.zeros(119), np.zeros(119)
+        assert fp["bd_tips_2003"](mol, iso, 0.0, t, q)["gi"] == gold["tips_gi"][k]
+        assert np.array_equal(q, gold["tips_q"][k].astype(float)) and np.array_equal(t, gold["tips_t"])
