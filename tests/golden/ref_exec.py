@@ -14,8 +14,12 @@ stand-ins for what does not exist here:
 What this pins: every Python-level formula and every piece of book-keeping of SURVEY 8a rows
 A1, A3-A11 and 8f rows 1 and 3 (widths, G coefficients, window placement and clipping, level
 selection, the zero-padded staging matrix, LUT files, LutSet.calculate, make_abscoeff_LUTS_fast,
-calc_PT_couples_atmosphere, convolution, FOV integration).  What it cannot pin: the Fortran itself
-(A2, A6's inner loop, A9's table, A13 - no Fortran compiler) and A12 (source missing upstream).
+calc_PT_couples_atmosphere, convolution, FOV integration).  The Fortran itself (A2, A6's inner
+loop, A9's table, A13) is pinned separately by f77_exec.py, which executes the reference's Fortran
+source text; `with fortran_from_source():` below swaps the C stand-ins for those executed routines,
+and tests/test_f77_golden.py uses it to show that the reference's Python together with the
+reference's Fortran reproduce the committed fixtures bit for bit.  What stays unpinned: A12 (source
+missing upstream).
 
 Only tests/golden/make_ref_golden.py and tests/ use this module; /root/reference does not exist on
 the GPU box, so the fixtures it produces are committed.
@@ -145,3 +149,48 @@ class quiet(object):
     def __exit__(self, *a):
         sys.stdout.close()
         sys.stdout = self._out
+
+
+class fortran_from_source(object):
+    """Context manager: while active, the `lineshape` and `fparts_mod` stand-ins execute the
+    reference's OWN Fortran source (lineshape.f, fparts_mod.f, read where they lie and run by the
+    mechanical FORTRAN 77 executor f77_exec.py) instead of the C restatement - so that the
+    reference's Python and the reference's Fortran run together with nothing of this repository
+    in the arithmetic.  f2py shapes: every output is a new array."""
+
+    def __enter__(self):
+        if HERE not in sys.path:
+            sys.path.insert(0, HERE)
+        import f77_exec as F
+        ls = F.load(os.path.join(REFERENCE, 'lineshape.f'))
+        fp = F.load(os.path.join(REFERENCE, 'fparts_mod.f'))
+
+        def humliv_bb(x, i1, i2, x0, lw, dw):
+            x = np.ascontiguousarray(x, dtype=float)
+            y = np.zeros(len(x))
+            ls['humliv_bb'](x, int(i1), int(i2), float(x0), float(lw), float(dw), y)
+            return y
+
+        def sum_all_lines(spe_ini, matrix, init, fin, n_lines, n_spe):
+            spe_ini = np.ascontiguousarray(spe_ini, dtype=float)
+            out = np.empty_like(spe_ini)
+            ls['sum_all_lines'](spe_ini, np.asarray(matrix), np.asarray(init), np.asarray(fin),
+                                int(n_lines), int(n_spe), out)
+            return out
+
+        def bd_tips_2003(mol, iso):
+            t, q = np.zeros(119), np.zeros(119)
+            gi = fp['bd_tips_2003'](int(mol), int(iso), 0.0, t, q)['gi']
+            return gi, t, q
+
+        self._saved = []
+        for mod, name, fn in (('lineshape', 'humliv_bb', humliv_bb),
+                              ('lineshape', 'sum_all_lines', sum_all_lines),
+                              ('fparts_mod', 'bd_tips_2003', bd_tips_2003)):
+            self._saved.append((mod, name, getattr(sys.modules[mod], name)))
+            setattr(sys.modules[mod], name, fn)
+        return self
+
+    def __exit__(self, *a):
+        for mod, name, fn in self._saved:
+            setattr(sys.modules[mod], name, fn)

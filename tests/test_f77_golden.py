@@ -289,3 +289,48 @@ def test_f77_fixture_is_what_the_reference_source_computes_now(f77, gold):
         t, q = np.zeros(119), np.zeros(119)
         assert fp["bd_tips_2003"](mol, iso, 0.0, t, q)["gi"] == gold["tips_gi"][k]
         assert np.array_equal(q, gold["tips_q"][k].astype(float)) and np.array_equal(t, gold["tips_t"])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not on this box")
+def test_reference_python_with_reference_fortran_builds_the_committed_lut(f77):
+    """The reference's Python (LookUpTable.make -> LutSet.add_PT -> BuildCoeff ->
+    add_lines_to_spectrum -> prepare_fortran_sum, CalcPartitionSum) run TOGETHER WITH the
+    reference's Fortran (humliv_bb, sum_all_lines, bd_tips_2003 executed from lineshape.f /
+    fparts_mod.f by f77_exec) - nothing of this repository in the arithmetic - reproduces, bit for
+    bit, the LUT cell, shapes and partition sums of the first fixture set (ref_golden.npz, which
+    was generated with the C restatement standing in for the f2py modules)."""
+    import shutil
+    import tempfile
+    sys.path.insert(0, GOLD)
+    import ref_exec as R
+    import make_ref_golden as M
+    ref = np.load(os.path.join(GOLD, "ref_golden.npz"))
+    spcl, smm, sbm = R.load()
+    lines = spcl.read_line_database(os.path.join(GOLD, "ref_lines.par"))
+    dec = (lambda v: v.decode() if isinstance(v, bytes) else v)
+    for l in lines:
+        for k in ('Up_lev_str', 'Lo_lev_str'):
+            setattr(l, k, dec(getattr(l, k)))
+    iso1, _ = M.case_isomolecs(sbm)
+    sp = smm.prepare_spe_grid(M.WN_RANGE).spectral_grid
+    work = tempfile.mkdtemp() + os.sep
+    try:
+        with R.fortran_from_source(), R.quiet():
+            assert sys.modules['lineshape'].humliv_bb.__qualname__.startswith('fortran_from_source')
+            q = [[spcl.CalcPartitionSum(int(m), int(i), temp=92.3) for m, i in ref["q_molisos"]]]
+            shp = spcl.calc_shapes_lines(sp, [l for l in lines if l.Iso == 1], M.CELLS[0][1],
+                                         M.CELLS[0][0], iso1, n_threads=1)
+            lut = smm.LookUpTable(iso1, sp.wn_range(), False)
+            lut.make(sp, lines, M.CELLS[:1], cartLUTs=work, n_threads=1)
+        assert np.array_equal(np.array(q)[0], ref["q_values"][:, 4])
+        pick = ref["shape_pick"]
+        assert np.array_equal(np.array([shp[i].shape.spectrum for i in pick]), ref["shape_spectra"])
+        n_set = 0
+        for s, lev in enumerate(iso1.levels):
+            pts, sets = M.read_stream(lut.sets[lev].filename)
+            for k, ct in enumerate(M.CTYPES):
+                assert np.array_equal(sets[0][ct].spectrum, ref["cells_nonlte"][s, k]), (lev, ct)
+                n_set += bool(np.any(sets[0][ct].spectrum))
+        assert n_set >= 6
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
