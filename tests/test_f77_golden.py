@@ -292,7 +292,7 @@ def test_f77_fixture_is_what_the_reference_source_computes_now(f77, gold):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not on this box")
-def test_reference_python_with_reference_fortran_builds_the_committed_lut(f77):
+def test_reference_python_with_reference_fortran_builds_the_committed_lut(f77, monkeypatch):
     """The reference's Python (LookUpTable.make -> LutSet.add_PT -> BuildCoeff ->
     add_lines_to_spectrum -> prepare_fortran_sum, CalcPartitionSum) run TOGETHER WITH the
     reference's Fortran (humliv_bb, sum_all_lines, bd_tips_2003 executed from lineshape.f /
@@ -314,6 +314,7 @@ def test_reference_python_with_reference_fortran_builds_the_committed_lut(f77):
     iso1, _ = M.case_isomolecs(sbm)
     sp = smm.prepare_spe_grid(M.WN_RANGE).spectral_grid
     work = tempfile.mkdtemp() + os.sep
+    monkeypatch.chdir(work)                  # the reference appends to ./control_spectrobot
     try:
         with R.fortran_from_source(), R.quiet():
             assert sys.modules['lineshape'].humliv_bb.__qualname__.startswith('fortran_from_source')
