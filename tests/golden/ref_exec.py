@@ -174,8 +174,8 @@ class fortran_from_source(object):
         def sum_all_lines(spe_ini, matrix, init, fin, n_lines, n_spe):
             spe_ini = np.ascontiguousarray(spe_ini, dtype=float)
             out = np.empty_like(spe_ini)
-            ls['sum_all_lines'](spe_ini, np.asarray(matrix), np.asarray(init), np.asarray(fin),
-                                int(n_lines), int(n_spe), out)
+            ls['sum_all_lines'](spe_ini, np.asarray(matrix), np.asarray(init).astype(np.int32),
+                                np.asarray(fin).astype(np.int32), int(n_lines), int(n_spe), out)
             return out
 
         def bd_tips_2003(mol, iso):

@@ -335,3 +335,45 @@ def test_reference_python_with_reference_fortran_builds_the_committed_lut(f77, m
         assert n_set >= 6
     finally:
         shutil.rmtree(work, ignore_errors=True)
+
+
+_REGEN = r"""
+import sys, warnings
+warnings.simplefilter('ignore')
+gold, root = sys.argv[1], sys.argv[2]
+sys.path.insert(0, gold)
+sys.path.insert(1, root)
+import ref_exec as R
+R.load()
+for name in ('make_ref_golden', 'make_ref_golden2', 'make_ref_golden3'):
+    M = __import__(name)
+    with R.fortran_from_source(), R.quiet():
+        M.main()
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not on this box")
+def test_every_reference_executed_fixture_set_regenerates_with_the_executed_fortran(tmp_path):
+    """All three generators of the reference-executed fixtures (make_ref_golden{,2,3}.py: LUT
+    builds, shapes, LTE / non-LTE cells, split files, prepare_fortran_sum, the slow line-by-line
+    coefficients, ...) re-run in a scratch copy with the reference's Fortran executed from source
+    in place of the C stand-ins: every array of ref_golden{,2,3}.npz comes out bit-identical.  The
+    committed fixtures are therefore outputs of the reference's Python AND Fortran."""
+    import shutil
+    import subprocess
+    scratch = tmp_path / "tests" / "golden"
+    shutil.copytree(GOLD, str(scratch), ignore=shutil.ignore_patterns("__pycache__"))
+    script = tmp_path / "regen.py"
+    script.write_text(_REGEN)
+    subprocess.run([sys.executable, str(script), str(scratch), ROOT], check=True, cwd=str(tmp_path),
+                   stdout=subprocess.DEVNULL)
+    n = 0
+    for f in ("ref_golden.npz", "ref_golden2.npz", "ref_golden3.npz"):
+        a, b = np.load(str(scratch / f), allow_pickle=True), np.load(os.path.join(GOLD, f), allow_pickle=True)
+        assert sorted(a.files) == sorted(b.files)
+        for k in a.files:
+            assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype, (f, k)
+            same = np.array_equal(a[k], b[k]) if a[k].dtype.kind in "USO" else np.array_equal(a[k], b[k], equal_nan=True)
+            assert same, (f, k)
+            n += 1
+    assert n >= 190
